@@ -1,0 +1,175 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED
+reference (imported from /root/reference) on seeded synthetic inputs.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed): kernels_n60.npz, kernels_n160.npz, model_c1.npz,
+kalman_n120.npz, checkpoint_n80.npz.  Every file stores its inputs next to the
+reference's outputs, so replaying it needs neither the reference nor the
+generator.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+warnings.filterwarnings("ignore")
+
+from tx_fast_hydrology.muskingum import Muskingum            # noqa: E402
+from tx_fast_hydrology.nutils import (_ax_bu, _ax, _apply_gain, _ap_par, _aqat_par,   # noqa: E402
+                                      interpolate_sample)
+from tx_fast_hydrology.da import KalmanFilter                 # noqa: E402
+from tx_fast_hydrology.simulation import CheckPoint           # noqa: E402
+from tx_fast_hydrology_b200 import synthetic as S             # noqa: E402
+
+T0 = "2024-01-01T00:00:00Z"
+
+
+def frame(times_ns, table, cols):
+    idx = pd.DatetimeIndex(pd.to_datetime(times_ns, unit="ns", utc=True)).as_unit("ns")
+    return pd.DataFrame(table, index=idx, columns=cols)
+
+
+def kernels(n, seed, fname):
+    net = S.make_network(n, seed)
+    prm = S.make_params(n, seed)
+    d = S.model_dict(net, prm, dt_s=300.0, t0=T0)
+    mdl = Muskingum(d)
+    rng = np.random.default_rng(seed + 77)
+    heads = mdl.startnodes[mdl.indegree == 0]
+    q = rng.gamma(0.5, 2.0, size=n)
+    i_prev = mdl.i_t_next.copy(); o_prev = mdl.o_t_next.copy()
+    i1, o1 = _ax_bu(heads, mdl.endnodes, mdl.alpha, mdl.beta, mdl.chi, mdl.gamma,
+                    i_prev, o_prev, q, mdl.indegree)
+    i2, o2 = _ax(heads, mdl.endnodes, mdl.alpha, mdl.beta, mdl.chi, i_prev, o_prev,
+                 mdl.indegree)
+    gain = rng.standard_normal(n)
+    ig, og = _apply_gain(heads, mdl.endnodes, gain, mdl.indegree)
+    Pm = rng.standard_normal((n, n))
+    P = Pm @ Pm.T / n + np.eye(n)
+    ap = _ap_par(P, np.empty((n, n)), heads, mdl.endnodes, mdl.alpha, mdl.beta, mdl.chi,
+                 mdl.indegree).copy()
+    aqat_sym = np.ascontiguousarray(_aqat_par(P, np.empty((n, n)), heads, mdl.endnodes,
+                                              mdl.alpha, mdl.beta, mdl.chi, mdl.indegree))
+    aqat_gen = np.ascontiguousarray(_aqat_par(Pm, np.empty((n, n)), heads, mdl.endnodes,
+                                              mdl.alpha, mdl.beta, mdl.chi, mdl.indegree))
+    # interpolation: inside, on a knot, before, after; linear + nearest
+    xp = (1.7e18 + np.arange(6) * 3.6e12)
+    fp = rng.standard_normal((6, 7))
+    xs = np.array([xp[0] - 5.0e11, xp[0], xp[2] + 9.0e11, xp[3], xp[4] + 1.8e12,
+                   xp[5], xp[5] + 1e12])
+    lin = np.stack([interpolate_sample(float(x), xp, fp, 1) for x in xs])
+    near = np.stack([interpolate_sample(float(x), xp, fp, 0) for x in xs])
+    np.savez_compressed(
+        os.path.join(HERE, fname), endnodes=mdl.endnodes, K=mdl.K, X=mdl.X, dt=300.0,
+        indegree=mdl.indegree, alpha=mdl.alpha, beta=mdl.beta, chi=mdl.chi,
+        gamma=mdl.gamma, o_init=prm["o_t"], i_init=i_prev, q=q,
+        axbu_i=i1, axbu_o=o1, ax_i=i2, ax_o=o2, gain=gain, gain_i=ig, gain_o=og,
+        P_sym=P, P_gen=Pm, ap=ap, aqat_sym=aqat_sym, aqat_gen=aqat_gen,
+        xp=xp, fp=fp, xs=xs, interp_lin=lin, interp_near=near)
+    print(fname, "ok")
+
+
+def model_c1():
+    """BASELINE.json configs[0]: 1,000 reaches, 288 five-minute steps, Muskingum.simulate."""
+    n, T, seed = 1000, 288, 1
+    net = S.make_network(n, seed)
+    prm = S.make_params(n, seed)
+    d = S.model_dict(net, prm, dt_s=300.0, t0=T0)
+    mdl = Muskingum(d)
+    t0_ns = mdl.datetime.value
+    times, table = S.make_forcing(n, T, 300.0, seed, t0_ns=t0_ns)
+    df = frame(times, table, d["reach_ids"])
+    keep = list(range(0, T, 12)) + [T - 1]
+    O = []; I = []
+    total = np.zeros(n)
+    for k, state in enumerate(mdl.simulate(df)):
+        total += state.o_t_next
+        if k in keep:
+            O.append(state.o_t_next.copy()); I.append(state.i_t_next.copy())
+    assert k == T - 1
+    np.savez_compressed(
+        os.path.join(HERE, "model_c1.npz"), endnodes=mdl.endnodes, K=mdl.K, X=mdl.X,
+        o_init=prm["o_t"], dt=300.0, t0_ns=t0_ns, times=times, table=table,
+        keep=np.asarray(keep), O=np.stack(O), I=np.stack(I), o_sum=total,
+        final_time_ns=mdl.datetime.value)
+    print("model_c1.npz ok")
+
+
+def kalman():
+    n, m, T, seed = 120, 8, 24, 11
+    net = S.make_network(n, seed)
+    prm = S.make_params(n, seed, well_posed=True)
+    d = S.model_dict(net, prm, dt_s=300.0, t0=T0)
+    mdl = Muskingum(d)
+    t0_ns = mdl.datetime.value
+    times, table = S.make_forcing(n, T, 300.0, seed, t0_ns=t0_ns, rows_every=6)
+    df = frame(times, table, d["reach_ids"])
+    gidx = S.make_gauges(net["endnodes"], m, seed=seed)
+    rng = np.random.default_rng(seed + 5)
+    gidx_cols = rng.permutation(gidx)                 # unsorted columns: exercises da.py:36-44
+    mt = t0_ns + np.arange(0, T + 1, 3, dtype=np.int64) * int(300e9)
+    mt = mt[mt <= t0_ns + 18 * int(300e9)]            # measurements end before the run does
+    meas = rng.uniform(0.5, 8.0, size=(mt.size, m))
+    mdf = frame(mt, meas, [d["reach_ids"][j] for j in gidx_cols])
+    Rm = rng.standard_normal((m, m)); R = 1e-2 * np.eye(m) + 1e-3 * (Rm @ Rm.T)
+    Q = 2.0 * np.eye(n); P0 = Q.copy()
+    kf = KalmanFilter(mdl, mdf, Q, R, P0)
+    mdl.bind_callback(kf, key="kf")
+    O = []; I = []; Pd = []; gains = []
+    for state in mdl.simulate(df):
+        O.append(state.o_t_next.copy()); I.append(state.i_t_next.copy())
+        Pd.append(np.diag(kf.P_t_next).copy()); gains.append(kf.gain.copy())
+    np.savez_compressed(
+        os.path.join(HERE, "kalman_n120.npz"), endnodes=mdl.endnodes, K=mdl.K, X=mdl.X,
+        o_init=prm["o_t"], dt=300.0, t0_ns=t0_ns, times=times, table=table,
+        gauge_cols=gidx_cols, meas_times=mt, meas=meas, R=R, Q=Q, P0=P0,
+        O=np.stack(O), I=np.stack(I), P_diag=np.stack(Pd), gains=np.stack(gains),
+        P_final=kf.P_t_next, K_final=kf.K, sorted_idx=kf.reach_indices)
+    print("kalman_n120.npz ok")
+
+
+def checkpoint():
+    """CheckPoint + save_state/load_state rewind (simulation.py:169-211, muskingum.py:573-588)."""
+    n, T, seed = 80, 36, 21
+    net = S.make_network(n, seed)
+    prm = S.make_params(n, seed)
+    d = S.model_dict(net, prm, dt_s=300.0, t0=T0)
+    mdl = Muskingum(d)
+    t0_ns = mdl.datetime.value
+    times, table = S.make_forcing(n, T, 300.0, seed, t0_ns=t0_ns)
+    df = frame(times, table, d["reach_ids"])
+    cp = CheckPoint(mdl, timedelta=3600)
+    mdl.bind_callback(cp, key="checkpoint")
+    for state in mdl.simulate(df):
+        pass
+    o_end = mdl.o_t_next.copy(); t_end = mdl.datetime.value
+    saved_o = mdl.saved_states["o_t_next"].copy(); saved_i = mdl.saved_states["i_t_next"].copy()
+    saved_t = mdl.saved_states["datetime"].value
+    mdl.load_state()
+    o_loaded = mdl.o_t_next.copy(); t_loaded = mdl.datetime.value
+    for state in mdl.simulate(df):       # second cycle from the checkpoint
+        pass
+    np.savez_compressed(
+        os.path.join(HERE, "checkpoint_n80.npz"), endnodes=mdl.endnodes, K=mdl.K, X=mdl.X,
+        o_init=prm["o_t"], dt=300.0, t0_ns=t0_ns, times=times, table=table,
+        o_end=o_end, t_end=t_end, saved_o=saved_o, saved_i=saved_i, saved_t=saved_t,
+        o_loaded=o_loaded, t_loaded=t_loaded, o_end2=mdl.o_t_next.copy(),
+        t_end2=mdl.datetime.value, saved_t2=mdl.saved_states["datetime"].value)
+    print("checkpoint_n80.npz ok")
+
+
+if __name__ == "__main__":
+    kernels(60, 7, "kernels_n60.npz")
+    kernels(160, 8, "kernels_n160.npz")
+    model_c1()
+    kalman()
+    checkpoint()
