@@ -1,0 +1,145 @@
+/*
+ * txh.h -- C ABI of libtxh, the B200 (sm_100a) routing + assimilation hot path
+ * that replaces the numba/scipy kernels of future-water/tx-fast-hydrology.
+ *
+ * The reference has no FFI layer; its boundary is a handful of free functions
+ * imported by name from tx_fast_hydrology/nutils.py plus the attribute protocol of
+ * the `Muskingum` object.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference root).
+ * The ctypes binding a maintainer would add is shown in INTEGRATION.md and is what
+ * tx_fast_hydrology_b200/_lib.py does.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative TXH_E_* code on failure;
+ *     txh_last_error() returns the message of the calling thread's last failure.
+ *   - no exceptions cross the boundary; plain pointers and sizes only.
+ *   - `host` pointers are ordinary process memory; `dev` pointers are CUDA device
+ *     memory owned by the caller (e.g. torch tensors' data_ptr()).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Launches
+ *     are asynchronous unless stated; a handle is not thread-safe, distinct handles are.
+ *   - member-batched state is stored in "schedule order": a row per reach, rows
+ *     permuted into task order, `ld` doubles per row with the
+ *     ensemble members contiguous: X[pos * ld + member].  txh_row_stride(M) gives
+ *     ld; txh_pack_* / txh_unpack_* convert from and to the reference's reach order.
+ */
+#ifndef TXH_H
+#define TXH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TXH_OK             0
+#define TXH_E_INVALID     -1   /* bad argument */
+#define TXH_E_TOPOLOGY    -2   /* cycle / out-of-range endnodes */
+#define TXH_E_CUDA        -3   /* CUDA runtime error */
+#define TXH_E_NODEVICE    -4   /* no CUDA device: the product path has no CPU fallback */
+#define TXH_E_WATCHDOG    -5   /* a dataflow wait exceeded its bound (kernel bailed out) */
+#define TXH_E_STATE       -6   /* call order (e.g. coefficients not set) */
+
+typedef struct txh_net txh_net;           /* topology + schedule + device descriptors */
+typedef struct txh_forcing txh_forcing;   /* lateral-inflow table resident in HBM */
+
+const char* txh_last_error(void);
+int txh_version(void);
+/* number of visible CUDA devices (0 on a CPU-only box; never fails) */
+int txh_device_count(void);
+
+/* ---- topology pass ---------------------------------------------------------------
+ * Replaces Muskingum.compute_indegree (muskingum.py:322-330), the per-step headwater
+ * mask (muskingum.py:444) and the implicit ordering of the walk in nutils.py:72-88.
+ * Host-only, exact integers; works without a GPU.  `endnodes[j]` is the downstream
+ * reach of j, an outlet is endnodes[j] == j (muskingum.py:897-902); startnodes is
+ * arange(n) as the reference kernels assume (nutils.py:73-83).
+ * sched_params = {long_path_min, spine_cap, pocket_cap, max_slots}, NULL = defaults. */
+int txh_create(int64_t n, const int64_t* endnodes, const int32_t* sched_params, txh_net** out);
+void txh_destroy(txh_net* net);
+int64_t txh_n(const txh_net* net);
+int txh_get_indegree(const txh_net* net, int64_t* indegree /*[n]*/);
+int txh_get_headwaters(const txh_net* net, int64_t* heads /*[n]*/, int64_t* count);
+int txh_get_levels(const txh_net* net, int64_t* level /*[n]*/, int64_t* nlevels);
+int txh_get_level_order(const txh_net* net, int64_t* order /*[n]*/, int64_t* offsets /*[nlevels+1]*/);
+int txh_get_chains(const txh_net* net, int64_t* chain_id /*[n]*/, int64_t* chain_pos /*[n]*/,
+                   int64_t* chain_len /*[n] (first nchains used)*/, int64_t* nchains);
+int txh_get_paths(const txh_net* net, int64_t* path_id /*[n]*/, int64_t* path_pos /*[n]*/);
+int txh_get_visit_order(const txh_net* net, int64_t* order /*[n]*/);      /* nutils.py:72-88 */
+/* schedule introspection (tests, tuning).  info = {n_tasks, n_spine, n_pocket,
+ * n_input_words, n_deps, slots_used, row_fallbacks, cp_tasks, cp_cost, nlevels} */
+int txh_get_schedule_info(const txh_net* net, int64_t info[10]);
+int txh_get_schedule(const txh_net* net, int64_t* pos_of_reach /*[n]*/, int32_t* task_desc /*[n_tasks*6]*/,
+                     int32_t* deps, uint32_t* hdr /*[n]*/, uint32_t* inw);
+
+/* ---- coefficients ----------------------------------------------------------------
+ * txh_compute_coeffs replaces Muskingum.compute_muskingum_coeffs (muskingum.py:332-360):
+ * host arithmetic in the reference's operation order; results returned in reach order
+ * and installed on the handle.  txh_set_coeffs installs user-mutated arrays
+ * (Muskingum.set_transmissive_boundary, muskingum.py:567-571). */
+int txh_compute_coeffs(txh_net* net, const double* K, const double* X, double dt,
+                       double* alpha, double* beta, double* chi, double* gamma /* host [n], may be NULL */);
+int txh_set_coeffs(txh_net* net, const double* alpha, const double* beta, const double* chi,
+                   const double* gamma /* host [n] */);
+
+/* ---- layout ------------------------------------------------------------------------ */
+int64_t txh_row_stride(int64_t M);                       /* doubles per row for M members */
+/* host reach-order -> device schedule-order.  layout 0: src[reach*M + m]; 1: src[m*n + reach] */
+int txh_pack_host(txh_net* net, const double* src_host, int64_t M, int layout, double* dst_dev, void* stream);
+int txh_unpack_host(txh_net* net, const double* src_dev, int64_t M, int layout, double* dst_host, void* stream);
+/* device reach-order [n][M] <-> device schedule-order */
+int txh_pack_dev(txh_net* net, const double* src_dev, int64_t M, double* dst_dev, void* stream);
+int txh_unpack_dev(txh_net* net, const double* src_dev, int64_t M, double* dst_dev, void* stream);
+/* gather rows of the listed reaches: out[k*M + m] = X[pos(reach_idx[k])*ld + m]  (device out) */
+int txh_gather_rows(txh_net* net, const double* X_dev, int64_t M, const int64_t* reach_idx_host,
+                    int64_t count, double* out_dev, void* stream);
+
+/* ---- state initialisation ------------------------------------------------------------
+ * Muskingum.init_states (muskingum.py:410-419) and numba_init_inflows (nutils.py:136-141):
+ * I[j] = sum of upstream O, PLUS the reach's own O at self-loop outlets (no guard there). */
+int txh_init_inflows(txh_net* net, const double* O_dev, double* I_dev, int64_t M, void* stream);
+
+/* ---- forcing table -------------------------------------------------------------------
+ * The (T x n) lateral-inflow table `simulate` interpolates every step
+ * (muskingum.py:526-531 -> nutils.interpolate_sample, nutils.py:5-39), uploaded once.
+ * times: float64 ns since epoch (index.astype(int).astype(float)); table: host [R][n] in
+ * reach order.  member_mul (optional, host [R][M]): member m sees table[r][j]*member_mul[r][m]. */
+int txh_forcing_create(txh_net* net, int64_t R, const double* times, const double* table_host,
+                       int64_t M, const double* member_mul_host, txh_forcing** out);
+void txh_forcing_destroy(txh_forcing* f);
+
+/* ---- routing ---------------------------------------------------------------------------
+ * txh_route_run: `nsteps` timesteps of _ax_bu (nutils.py:64-89) as called from the simulate
+ * loop (muskingum.py:527-533), forcing interpolated at t0 + (s+1)*dt for step s exactly as
+ * nutils.py:21-34 does (searchsorted-left, clamped ends, linear; times are integer ns as
+ * Timestamp.value is, muskingum.py:528-530).  One persistent dataflow
+ * kernel; O/I are updated in place ([n rows][ld], schedule order).
+ *   method: 1 linear, 0 nearest.   forcing == NULL: zero lateral inflow.
+ *   rec_*: optional recording of the outflow of `rec_count` reaches after every
+ *   `rec_every`-th step into rec_out_dev[(step/rec_every)][k][M] (device). */
+int txh_route_run(txh_net* net, double* O_dev, double* I_dev, int64_t M,
+                  const txh_forcing* forcing, int64_t t0_ns, int64_t dt_ns, int64_t nsteps, int method,
+                  const int64_t* rec_reach_host, int64_t rec_count, int64_t rec_every,
+                  double* rec_out_dev, void* stream);
+/* one step with an explicit lateral-inflow vector (Muskingum.step, muskingum.py:467-483):
+ * q_dev is [n] in REACH order on the device (shared by all members), or NULL. */
+int txh_route_step(txh_net* net, double* O_dev, double* I_dev, int64_t M, const double* q_dev, void* stream);
+/* the same step evaluated level by level (one launch per topological level); the
+ * level-scheduled triangular solve kept as a second, independent device path. */
+int txh_route_step_levels(txh_net* net, double* O_dev, double* I_dev, int64_t M, const double* q_dev, void* stream);
+/* X <- A.X for every column: numba_init_inflows + _ax (nutils.py:143-169, `_ap_par`);
+ * I_scratch_dev is a caller buffer of the same shape as X. */
+int txh_route_apply(txh_net* net, double* X_dev, double* I_scratch_dev, int64_t M, void* stream);
+/* _apply_gain (nutils.py:116-134) + the in-place update of da.py:124-126:
+ * O += G ; I[j] += sum_{u->j, u!=j} G[u]   (G in schedule order, same shape) */
+int txh_apply_gain(txh_net* net, const double* G_dev, double* O_dev, double* I_dev, int64_t M, void* stream);
+
+/* Synchronise `stream` and report a poisoned launch (TXH_E_WATCHDOG) or a CUDA fault. */
+int txh_check(txh_net* net, void* stream);
+
+/* kernel-launch counter (bench.py's gpu_launches claim) */
+int64_t txh_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TXH_H */

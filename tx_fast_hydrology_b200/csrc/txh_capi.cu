@@ -1,0 +1,563 @@
+// txh_capi.cu -- the C ABI declared in include/txh.h.
+// Handles own the topology, the schedule and their device copies; all member-batched
+// state lives in caller-owned device buffers.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/txh.h"
+#include "txh_kernels.cuh"
+#include "txh_topology.hpp"
+
+using namespace txh;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? TXH_E_NODEVICE : TXH_E_CUDA;
+}
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);      \
+    } while (0)
+
+template <class T>
+int upload(T** dptr, const std::vector<T>& v)
+{
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CU(cudaMalloc((void**)dptr, bytes));
+    if (!v.empty()) CU(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return TXH_OK;
+}
+
+}  // namespace
+
+struct txh_net {
+    Topology topo;
+    Schedule sched;
+    std::vector<double> coef_host;      // [n][4] schedule order
+    bool have_coef = false, coef_dirty = false;
+    // device side
+    bool dev_ready = false;
+    int num_sms = 0;
+    unsigned long long watchdog_ns = 10000000000ull;
+    TaskDesc* d_tasks = nullptr;
+    int32_t *d_deps = nullptr, *d_up_off = nullptr, *d_up_pos = nullptr, *d_lvl_pos = nullptr,
+            *d_reach_of_pos = nullptr, *d_pos_of_reach = nullptr;
+    uint32_t *d_hdr = nullptr, *d_inw = nullptr;
+    uint8_t* d_outlet = nullptr;
+    double* d_coef = nullptr;
+    double* d_qtmp = nullptr;           // [n] schedule-order scratch for txh_route_step
+    int32_t* d_done = nullptr; size_t done_cap = 0;
+    unsigned long long* d_ticket = nullptr;   // [0] ticket, followed by status word
+    int32_t* d_status = nullptr;
+    StepInterp* d_steps = nullptr; size_t steps_cap = 0;
+    StepInterp* d_unit_step = nullptr;
+    int32_t* d_rec_slot = nullptr;
+    int32_t* d_tmp_idx = nullptr; size_t tmp_idx_cap = 0;
+    int32_t* h_status = nullptr;        // pinned mirror of d_status
+};
+
+struct txh_forcing {
+    txh_net* net;
+    int64_t R, M;
+    std::vector<double> times;
+    double* d_F = nullptr;              // [R][n] schedule order
+    double* d_W = nullptr;              // [R][M] or nullptr
+};
+
+namespace {
+
+int ensure_device(txh_net* net)
+{
+    if (net->dev_ready) return TXH_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(TXH_E_NODEVICE, "no CUDA device visible: libtxh has no CPU fallback");
+    }
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&net->num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const Schedule& s = net->sched;
+    int rc;
+    if ((rc = upload(&net->d_tasks, s.tasks))) return rc;
+    if ((rc = upload(&net->d_deps, s.deps))) return rc;
+    if ((rc = upload(&net->d_hdr, s.hdr))) return rc;
+    if ((rc = upload(&net->d_inw, s.inw))) return rc;
+    if ((rc = upload(&net->d_up_off, s.up_off))) return rc;
+    if ((rc = upload(&net->d_up_pos, s.up_pos))) return rc;
+    if ((rc = upload(&net->d_lvl_pos, s.lvl_pos))) return rc;
+    if ((rc = upload(&net->d_reach_of_pos, s.reach_of_pos))) return rc;
+    if ((rc = upload(&net->d_pos_of_reach, s.pos_of_reach))) return rc;
+    if ((rc = upload(&net->d_outlet, s.is_outlet_pos))) return rc;
+    CU(cudaMalloc((void**)&net->d_coef, sizeof(double) * 4 * net->topo.n));
+    CU(cudaMalloc((void**)&net->d_qtmp, sizeof(double) * net->topo.n));
+    CU(cudaMalloc((void**)&net->d_ticket, 64));
+    net->d_status = reinterpret_cast<int32_t*>(net->d_ticket + 1);
+    CU(cudaMemset(net->d_ticket, 0, 64));
+    CU(cudaMalloc((void**)&net->d_rec_slot, sizeof(int32_t) * net->topo.n));
+    CU(cudaMallocHost((void**)&net->h_status, sizeof(int32_t)));
+    *net->h_status = 0;
+    const StepInterp unit{0, 0, 1.0, 0.0};
+    CU(cudaMalloc((void**)&net->d_unit_step, sizeof(StepInterp)));
+    CU(cudaMemcpy(net->d_unit_step, &unit, sizeof(unit), cudaMemcpyHostToDevice));
+    if (const char* w = getenv("TXH_WATCHDOG_MS")) {
+        const long ms = atol(w);
+        if (ms > 0) net->watchdog_ns = (unsigned long long)ms * 1000000ull;
+    }
+    net->dev_ready = true;
+    return TXH_OK;
+}
+
+int ensure_coef(txh_net* net, cudaStream_t st)
+{
+    if (!net->have_coef) return fail(TXH_E_STATE, "coefficients not set: call txh_compute_coeffs or txh_set_coeffs first");
+    if (net->coef_dirty) {
+        // synchronous on purpose: coef_host may be rewritten by the caller right after
+        CU(cudaMemcpyAsync(net->d_coef, net->coef_host.data(), sizeof(double) * 4 * net->topo.n,
+                           cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        net->coef_dirty = false;
+    }
+    return TXH_OK;
+}
+
+int check_M(int64_t M)
+{
+    if (M < 1 || M > (int64_t(1) << 24)) return fail(TXH_E_INVALID, "member count out of range");
+    return TXH_OK;
+}
+
+// common launcher for the persistent dataflow kernel
+int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F, const double* W, int wm_ld,
+                 const StepInterp* d_steps, int64_t nsteps, const int32_t* rec_slot, double* rec_out,
+                 int rec_every, int rec_count, cudaStream_t st)
+{
+    const Schedule& s = net->sched;
+    const int ld = (int)txh_row_stride(M);
+    const int nmb = (ld + kMemberBlock - 1) / kMemberBlock;
+    const size_t need = (size_t)s.tasks.size() * nmb;
+    if (need > net->done_cap) {
+        if (net->d_done) CU(cudaFree(net->d_done));
+        CU(cudaMalloc((void**)&net->d_done, need * sizeof(int32_t)));
+        net->done_cap = need;
+    }
+    CU(cudaMemsetAsync(net->d_done, 0, need * sizeof(int32_t), st));
+    CU(cudaMemsetAsync(net->d_ticket, 0, sizeof(unsigned long long), st));   // status stays sticky
+    RouteArgs a{};
+    a.tasks = net->d_tasks; a.deps = net->d_deps; a.hdr = net->d_hdr; a.inw = net->d_inw;
+    a.coef = net->d_coef; a.O = O; a.I = I; a.F = F; a.steps = d_steps; a.Wmul = W;
+    a.rec_slot = rec_slot; a.rec_out = rec_out; a.done = net->d_done; a.ticket = net->d_ticket;
+    a.status = net->d_status; a.n = net->topo.n; a.n_tasks = (int32_t)s.tasks.size(); a.n_mblocks = nmb;
+    a.nsteps = (int32_t)nsteps; a.slots = std::max(1, s.slots_used); a.ld = ld; a.M = (int32_t)M;
+    a.wm_ld = wm_ld; a.rec_every = rec_every; a.rec_count = rec_count;
+    a.watchdog_ns = net->watchdog_ns;
+    CU(launch_route_dataflow(a, net->num_sms, st));
+    CU(cudaMemcpyAsync(net->h_status, net->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    return TXH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* txh_last_error(void) { return g_err.c_str(); }
+int txh_version(void) { return 100; }
+int txh_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+int64_t txh_launch_count(void) { return launch_count(); }
+int64_t txh_row_stride(int64_t M) { return (M + 1) & ~int64_t(1); }
+
+int txh_create(int64_t n, const int64_t* endnodes, const int32_t* sp, txh_net** out)
+{
+    if (!endnodes || !out) return fail(TXH_E_INVALID, "null argument");
+    txh_net* net = new (std::nothrow) txh_net();
+    if (!net) return fail(TXH_E_INVALID, "out of memory");
+    std::string err;
+    if (!net->topo.build(n, endnodes, err)) { delete net; return fail(TXH_E_TOPOLOGY, err); }
+    SchedParams p;
+    if (sp) { p.long_path_min = sp[0]; p.spine_cap = sp[1]; p.pocket_cap = sp[2]; p.max_slots = sp[3]; }
+    if (!net->sched.build(net->topo, p, err)) { delete net; return fail(TXH_E_INVALID, err); }
+    *out = net;
+    return TXH_OK;
+}
+
+void txh_destroy(txh_net* net)
+{
+    if (!net) return;
+    if (net->dev_ready) {
+        cudaFree(net->d_tasks); cudaFree(net->d_deps); cudaFree(net->d_hdr); cudaFree(net->d_inw);
+        cudaFree(net->d_up_off); cudaFree(net->d_up_pos); cudaFree(net->d_lvl_pos);
+        cudaFree(net->d_reach_of_pos); cudaFree(net->d_pos_of_reach); cudaFree(net->d_outlet);
+        cudaFree(net->d_coef); cudaFree(net->d_qtmp); cudaFree(net->d_ticket); cudaFree(net->d_rec_slot);
+        cudaFree(net->d_unit_step);
+        if (net->d_done) cudaFree(net->d_done);
+        if (net->d_steps) cudaFree(net->d_steps);
+        if (net->d_tmp_idx) cudaFree(net->d_tmp_idx);
+        if (net->h_status) cudaFreeHost(net->h_status);
+    }
+    delete net;
+}
+
+int64_t txh_n(const txh_net* net) { return net ? net->topo.n : 0; }
+
+static void widen(const std::vector<int32_t>& v, int64_t* out) { for (size_t i = 0; i < v.size(); ++i) out[i] = v[i]; }
+
+int txh_get_indegree(const txh_net* net, int64_t* out)
+{
+    if (!net || !out) return fail(TXH_E_INVALID, "null argument");
+    widen(net->topo.indeg, out); return TXH_OK;
+}
+int txh_get_headwaters(const txh_net* net, int64_t* heads, int64_t* count)
+{
+    if (!net || !heads || !count) return fail(TXH_E_INVALID, "null argument");
+    widen(net->topo.heads, heads); *count = (int64_t)net->topo.heads.size(); return TXH_OK;
+}
+int txh_get_levels(const txh_net* net, int64_t* level, int64_t* nlevels)
+{
+    if (!net || !nlevels) return fail(TXH_E_INVALID, "null argument");
+    if (level) widen(net->topo.level, level);
+    *nlevels = net->topo.nlevels; return TXH_OK;
+}
+int txh_get_level_order(const txh_net* net, int64_t* order, int64_t* offsets)
+{
+    if (!net || !order || !offsets) return fail(TXH_E_INVALID, "null argument");
+    widen(net->topo.topo, order); widen(net->topo.level_off, offsets); return TXH_OK;
+}
+int txh_get_chains(const txh_net* net, int64_t* cid, int64_t* cpos, int64_t* clen, int64_t* nchains)
+{
+    if (!net || !cid || !cpos || !clen || !nchains) return fail(TXH_E_INVALID, "null argument");
+    widen(net->topo.chain_id, cid); widen(net->topo.chain_pos, cpos); widen(net->topo.chain_len, clen);
+    *nchains = (int64_t)net->topo.chain_len.size(); return TXH_OK;
+}
+int txh_get_paths(const txh_net* net, int64_t* pid, int64_t* ppos)
+{
+    if (!net || !pid || !ppos) return fail(TXH_E_INVALID, "null argument");
+    widen(net->topo.path_id, pid); widen(net->topo.path_pos, ppos); return TXH_OK;
+}
+int txh_get_visit_order(const txh_net* net, int64_t* order)
+{
+    if (!net || !order) return fail(TXH_E_INVALID, "null argument");
+    widen(net->topo.visit, order); return TXH_OK;
+}
+int txh_get_schedule_info(const txh_net* net, int64_t info[10])
+{
+    if (!net || !info) return fail(TXH_E_INVALID, "null argument");
+    const Schedule& s = net->sched;
+    info[0] = (int64_t)s.tasks.size(); info[1] = s.n_spine; info[2] = s.n_pocket;
+    info[3] = (int64_t)s.inw.size(); info[4] = (int64_t)s.deps.size(); info[5] = s.slots_used;
+    info[6] = s.row_fallbacks; info[7] = s.cp_tasks; info[8] = s.cp_cost; info[9] = net->topo.nlevels;
+    return TXH_OK;
+}
+int txh_get_schedule(const txh_net* net, int64_t* pos_of_reach, int32_t* task_desc, int32_t* deps,
+                     uint32_t* hdr, uint32_t* inw)
+{
+    if (!net) return fail(TXH_E_INVALID, "null argument");
+    const Schedule& s = net->sched;
+    if (pos_of_reach) widen(s.pos_of_reach, pos_of_reach);
+    if (task_desc) std::memcpy(task_desc, s.tasks.data(), s.tasks.size() * sizeof(TaskDesc));
+    if (deps) std::memcpy(deps, s.deps.data(), s.deps.size() * sizeof(int32_t));
+    if (hdr) std::memcpy(hdr, s.hdr.data(), s.hdr.size() * sizeof(uint32_t));
+    if (inw) std::memcpy(inw, s.inw.data(), s.inw.size() * sizeof(uint32_t));
+    return TXH_OK;
+}
+
+int txh_set_coeffs(txh_net* net, const double* al, const double* be, const double* ch, const double* ga)
+{
+    if (!net || !al || !be || !ch || !ga) return fail(TXH_E_INVALID, "null argument");
+    const int64_t n = net->topo.n;
+    net->coef_host.resize(4 * n);
+    for (int64_t k = 0; k < n; ++k) {
+        const int32_t j = net->sched.reach_of_pos[k];
+        net->coef_host[4 * k] = al[j]; net->coef_host[4 * k + 1] = be[j];
+        net->coef_host[4 * k + 2] = ch[j]; net->coef_host[4 * k + 3] = ga[j];
+    }
+    net->have_coef = true; net->coef_dirty = true;
+    return TXH_OK;
+}
+
+int txh_compute_coeffs(txh_net* net, const double* K, const double* X, double dt, double* al, double* be,
+                       double* ch, double* ga)
+{
+    if (!net || !K || !X) return fail(TXH_E_INVALID, "null argument");
+    const int64_t n = net->topo.n;
+    std::vector<double> a(n), b(n), c(n), g(n);
+    for (int64_t j = 0; j < n; ++j) {
+        // muskingum.py:332-347, same operation order
+        const double k = K[j], x = X[j];
+        a[j] = (dt - 2 * k * x) / (2 * k * (1 - x) + dt);
+        b[j] = (dt + 2 * k * x) / (2 * k * (1 - x) + dt);
+        c[j] = (2 * k * (1 - x) - dt) / (2 * k * (1 - x) + dt);
+        g[j] = dt / (k * (1 - x) + dt / 2);
+    }
+    if (al) std::memcpy(al, a.data(), n * sizeof(double));
+    if (be) std::memcpy(be, b.data(), n * sizeof(double));
+    if (ch) std::memcpy(ch, c.data(), n * sizeof(double));
+    if (ga) std::memcpy(ga, g.data(), n * sizeof(double));
+    return txh_set_coeffs(net, a.data(), b.data(), c.data(), g.data());
+}
+
+int txh_pack_host(txh_net* net, const double* src, int64_t M, int layout, double* dst, void* stream)
+{
+    if (!net || !src || !dst) return fail(TXH_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_M(M)) || (rc = ensure_device(net))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = net->topo.n;
+    double* tmp = nullptr;
+    CU(cudaMallocAsync((void**)&tmp, sizeof(double) * n * M, st));
+    CU(cudaMemcpyAsync(tmp, src, sizeof(double) * n * M, cudaMemcpyHostToDevice, st));
+    CU(launch_pack(net->d_reach_of_pos, tmp, dst, n, (int)M, (int)txh_row_stride(M), layout, st));
+    CU(cudaFreeAsync(tmp, st));
+    return TXH_OK;
+}
+
+int txh_unpack_host(txh_net* net, const double* src, int64_t M, int layout, double* dst, void* stream)
+{
+    if (!net || !src || !dst) return fail(TXH_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_M(M)) || (rc = ensure_device(net))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = net->topo.n;
+    double* tmp = nullptr;
+    CU(cudaMallocAsync((void**)&tmp, sizeof(double) * n * M, st));
+    CU(launch_unpack(net->d_reach_of_pos, src, tmp, n, (int)M, (int)txh_row_stride(M), layout, st));
+    CU(cudaMemcpyAsync(dst, tmp, sizeof(double) * n * M, cudaMemcpyDeviceToHost, st));
+    CU(cudaFreeAsync(tmp, st));
+    CU(cudaStreamSynchronize(st));
+    if (*net->h_status != 0) return fail(TXH_E_WATCHDOG, "a routing launch bailed out on its dataflow watchdog");
+    return TXH_OK;
+}
+
+int txh_pack_dev(txh_net* net, const double* src, int64_t M, double* dst, void* stream)
+{
+    if (!net || !src || !dst) return fail(TXH_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_M(M)) || (rc = ensure_device(net))) return rc;
+    CU(launch_pack(net->d_reach_of_pos, src, dst, net->topo.n, (int)M, (int)txh_row_stride(M), 0, (cudaStream_t)stream));
+    return TXH_OK;
+}
+
+int txh_unpack_dev(txh_net* net, const double* src, int64_t M, double* dst, void* stream)
+{
+    if (!net || !src || !dst) return fail(TXH_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_M(M)) || (rc = ensure_device(net))) return rc;
+    CU(launch_unpack(net->d_reach_of_pos, src, dst, net->topo.n, (int)M, (int)txh_row_stride(M), 0, (cudaStream_t)stream));
+    return TXH_OK;
+}
+
+int txh_gather_rows(txh_net* net, const double* X, int64_t M, const int64_t* idx, int64_t count, double* out,
+                    void* stream)
+{
+    if (!net || !X || !idx || !out || count < 0) return fail(TXH_E_INVALID, "bad argument");
+    int rc;
+    if ((rc = check_M(M)) || (rc = ensure_device(net))) return rc;
+    if (count == 0) return TXH_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int32_t> pos(count);
+    for (int64_t k = 0; k < count; ++k) {
+        if (idx[k] < 0 || idx[k] >= net->topo.n) return fail(TXH_E_INVALID, "reach index out of range");
+        pos[k] = net->sched.pos_of_reach[idx[k]];
+    }
+    if ((size_t)count > net->tmp_idx_cap) {
+        if (net->d_tmp_idx) CU(cudaFree(net->d_tmp_idx));
+        CU(cudaMalloc((void**)&net->d_tmp_idx, sizeof(int32_t) * count));
+        net->tmp_idx_cap = count;
+    }
+    CU(cudaMemcpyAsync(net->d_tmp_idx, pos.data(), sizeof(int32_t) * count, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));      // `pos` is a stack-lifetime buffer
+    CU(launch_gather_rows(net->d_tmp_idx, count, X, (int)txh_row_stride(M), (int)M, out, st));
+    return TXH_OK;
+}
+
+int txh_init_inflows(txh_net* net, const double* O, double* I, int64_t M, void* stream)
+{
+    if (!net || !O || !I) return fail(TXH_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_M(M)) || (rc = ensure_device(net))) return rc;
+    CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, O, I, net->topo.n,
+                           (int)txh_row_stride(M), (int)M, (cudaStream_t)stream));
+    return TXH_OK;
+}
+
+int txh_forcing_create(txh_net* net, int64_t R, const double* times, const double* table, int64_t M,
+                       const double* mul, txh_forcing** out)
+{
+    if (!net || !times || !table || !out || R < 1) return fail(TXH_E_INVALID, "bad argument");
+    int rc;
+    if ((rc = ensure_device(net))) return rc;
+    for (int64_t r = 1; r < R; ++r)
+        if (!(times[r] >= times[r - 1])) return fail(TXH_E_INVALID, "forcing times must be sorted ascending");
+    const int64_t n = net->topo.n;
+    txh_forcing* f = new (std::nothrow) txh_forcing();
+    if (!f) return fail(TXH_E_INVALID, "out of memory");
+    f->net = net; f->R = R; f->M = mul ? M : 0;
+    f->times.assign(times, times + R);
+    // permute columns into schedule order on the host (one-time), then one H2D copy
+    std::vector<double> perm((size_t)R * n);
+    for (int64_t r = 0; r < R; ++r) {
+        const double* src = table + (size_t)r * n;
+        double* dst = perm.data() + (size_t)r * n;
+        for (int64_t k = 0; k < n; ++k) dst[k] = src[net->sched.reach_of_pos[k]];
+    }
+    cudaError_t e = cudaMalloc((void**)&f->d_F, sizeof(double) * R * n);
+    if (e == cudaSuccess) e = cudaMemcpy(f->d_F, perm.data(), sizeof(double) * R * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && mul) {
+        if (M < 1) { cudaFree(f->d_F); delete f; return fail(TXH_E_INVALID, "member multipliers need M >= 1"); }
+        e = cudaMalloc((void**)&f->d_W, sizeof(double) * R * M);
+        if (e == cudaSuccess) e = cudaMemcpy(f->d_W, mul, sizeof(double) * R * M, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) { cudaFree(f->d_F); cudaFree(f->d_W); delete f; return cuda_fail(e, "forcing upload"); }
+    *out = f;
+    return TXH_OK;
+}
+
+void txh_forcing_destroy(txh_forcing* f)
+{
+    if (!f) return;
+    cudaFree(f->d_F);
+    if (f->d_W) cudaFree(f->d_W);
+    delete f;
+}
+
+int txh_route_run(txh_net* net, double* O, double* I, int64_t M, const txh_forcing* fo, int64_t t0_ns,
+                  int64_t dt_ns, int64_t nsteps, int method, const int64_t* rec_reach, int64_t rec_count,
+                  int64_t rec_every, double* rec_out, void* stream)
+{
+    if (!net || !O || !I) return fail(TXH_E_INVALID, "null argument");
+    if (nsteps < 0 || nsteps > (1 << 24)) return fail(TXH_E_INVALID, "nsteps out of range");
+    if (fo && fo->net != net) return fail(TXH_E_INVALID, "forcing belongs to another network");
+    if (fo && fo->d_W && fo->M != M) return fail(TXH_E_INVALID, "forcing member multipliers do not match M");
+    if (rec_count > 0 && (!rec_reach || !rec_out || rec_every < 1)) return fail(TXH_E_INVALID, "bad recording arguments");
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_M(M)) || (rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
+    if (nsteps == 0) return TXH_OK;
+    const StepInterp* d_steps = net->d_unit_step;
+    if (fo) {
+        // nutils.py:21-34 resolved per step on the host, in float64 as the reference does
+        std::vector<StepInterp> steps(nsteps);
+        const double* xp = fo->times.data();
+        const int64_t R = fo->R;
+        for (int64_t s = 0; s < nsteps; ++s) {
+            const double x = (double)(t0_ns + (s + 1) * dt_ns);          // float(next_timestep.value)
+            const int64_t ix = std::lower_bound(xp, xp + R, x) - xp;     // np.searchsorted, side='left'
+            StepInterp si;
+            if (ix == 0) si = {0, 0, 1.0, 0.0};
+            else if (ix >= R) si = {(int32_t)(R - 1), (int32_t)(R - 1), 1.0, 0.0};
+            else {
+                const double dx_0 = x - xp[ix - 1], dx_1 = xp[ix] - x;
+                if (method == 1) {
+                    const double frac = dx_0 / (dx_0 + dx_1);
+                    si = {(int32_t)(ix - 1), (int32_t)ix, 1 - frac, frac};
+                } else {
+                    const int32_t r = std::fabs(dx_0) <= std::fabs(dx_1) ? (int32_t)(ix - 1) : (int32_t)ix;
+                    si = {r, r, 1.0, 0.0};
+                }
+            }
+            steps[s] = si;
+        }
+        if ((size_t)nsteps > net->steps_cap) {
+            if (net->d_steps) CU(cudaFree(net->d_steps));
+            CU(cudaMalloc((void**)&net->d_steps, sizeof(StepInterp) * nsteps));
+            net->steps_cap = nsteps;
+        }
+        CU(cudaMemcpyAsync(net->d_steps, steps.data(), sizeof(StepInterp) * nsteps, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        d_steps = net->d_steps;
+    }
+    const int32_t* rec_slot = nullptr;
+    if (rec_count > 0) {
+        std::vector<int32_t> slot(net->topo.n, -1);
+        for (int64_t k = 0; k < rec_count; ++k) {
+            if (rec_reach[k] < 0 || rec_reach[k] >= net->topo.n) return fail(TXH_E_INVALID, "recorded reach out of range");
+            slot[net->sched.pos_of_reach[rec_reach[k]]] = (int32_t)k;
+        }
+        CU(cudaMemcpyAsync(net->d_rec_slot, slot.data(), sizeof(int32_t) * net->topo.n, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        rec_slot = net->d_rec_slot;
+    }
+    return run_dataflow(net, O, I, M, fo ? fo->d_F : nullptr, fo ? fo->d_W : nullptr, fo ? (int)fo->M : 0,
+                        d_steps, nsteps, rec_slot, rec_out, (int)rec_every, (int)rec_count, st);
+}
+
+int txh_route_step(txh_net* net, double* O, double* I, int64_t M, const double* q, void* stream)
+{
+    if (!net || !O || !I) return fail(TXH_E_INVALID, "null argument");
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_M(M)) || (rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
+    if (q) CU(launch_permute_vec(net->d_reach_of_pos, q, net->d_qtmp, net->topo.n, st));
+    return run_dataflow(net, O, I, M, q ? net->d_qtmp : nullptr, nullptr, 0, net->d_unit_step, 1, nullptr,
+                        nullptr, 1, 0, st);
+}
+
+int txh_route_step_levels(txh_net* net, double* O, double* I, int64_t M, const double* q, void* stream)
+{
+    if (!net || !O || !I) return fail(TXH_E_INVALID, "null argument");
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_M(M)) || (rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
+    if (q) CU(launch_permute_vec(net->d_reach_of_pos, q, net->d_qtmp, net->topo.n, st));
+    const Schedule& s = net->sched;
+    for (int32_t l = 0; l + 1 < (int32_t)s.lvl_off.size(); ++l) {
+        LevelArgs a{};
+        a.lvl_pos = net->d_lvl_pos + s.lvl_off[l]; a.count = s.lvl_off[l + 1] - s.lvl_off[l];
+        a.up_off = net->d_up_off; a.up_pos = net->d_up_pos; a.coef = net->d_coef;
+        a.q = q ? net->d_qtmp : nullptr; a.O = O; a.I = I; a.ld = (int)txh_row_stride(M); a.M = (int)M;
+        CU(launch_route_level(a, st));
+    }
+    return TXH_OK;
+}
+
+int txh_route_apply(txh_net* net, double* X, double* Iscr, int64_t M, void* stream)
+{
+    if (!net || !X || !Iscr) return fail(TXH_E_INVALID, "null argument");
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_M(M)) || (rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
+    // nutils.py:148-154: i_prev = init_inflows(o_prev) (self-loop included), then _ax
+    CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, X, Iscr, net->topo.n,
+                           (int)txh_row_stride(M), (int)M, st));
+    return run_dataflow(net, X, Iscr, M, nullptr, nullptr, 0, net->d_unit_step, 1, nullptr, nullptr, 1, 0, st);
+}
+
+int txh_apply_gain(txh_net* net, const double* G, double* O, double* I, int64_t M, void* stream)
+{
+    if (!net || !G || !O || !I) return fail(TXH_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_M(M)) || (rc = ensure_device(net))) return rc;
+    CU(launch_apply_gain(net->d_up_off, net->d_up_pos, G, O, I, net->topo.n, (int)txh_row_stride(M), (int)M,
+                         (cudaStream_t)stream));
+    return TXH_OK;
+}
+
+int txh_check(txh_net* net, void* stream)
+{
+    if (!net) return fail(TXH_E_INVALID, "null argument");
+    if (!net->dev_ready) return TXH_OK;
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    if (*net->h_status != 0) return fail(TXH_E_WATCHDOG, "a routing launch bailed out on its dataflow watchdog");
+    return TXH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// txh_kernels.cuh -- device-side argument blocks and launcher prototypes (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "txh_topology.hpp"
+
+namespace txh {
+
+// Interpolation of the forcing table for one step, resolved on the host exactly as
+// nutils.py:21-34 does (searchsorted-left, clamped ends): q = w0*F[r0] + w1*F[r1].
+struct StepInterp {
+    int32_t r0, r1;
+    double w0, w1;
+};
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kMemberBlock = 64;          // members per warp: one double2 per lane
+
+struct RouteArgs {
+    const TaskDesc* tasks;
+    const int32_t* deps;
+    const uint32_t* hdr;
+    const uint32_t* inw;
+    const double* coef;                   // [n][4] = alpha, beta, chi, gamma (schedule order)
+    double* O;
+    double* I;
+    const double* F;                      // [R][n] schedule order, or nullptr
+    const StepInterp* steps;              // [nsteps]
+    const double* Wmul;                   // [R][wm_ld] member multipliers, or nullptr
+    const int32_t* rec_slot;              // [n] recording slot of each position or -1; nullptr = off
+    double* rec_out;                      // [nrec_steps][rec_count][M]
+    int32_t* done;                        // [n_tasks * n_mblocks] steps completed in this launch
+    unsigned long long* ticket;
+    int32_t* status;
+    unsigned long long watchdog_ns;
+    int64_t n;
+    int32_t n_tasks, n_mblocks, nsteps, slots;
+    int32_t ld, M, wm_ld, rec_every, rec_count;
+};
+
+struct LevelArgs {
+    const int32_t* lvl_pos;               // positions of this level
+    int32_t count;
+    const int32_t* up_off;
+    const int32_t* up_pos;
+    const double* coef;
+    const double* q;                      // [n] schedule order or nullptr
+    double* O;
+    double* I;
+    int32_t ld, M;
+};
+
+cudaError_t launch_route_dataflow(const RouteArgs& a, int num_sms, cudaStream_t st);
+cudaError_t launch_route_level(const LevelArgs& a, cudaStream_t st);
+cudaError_t launch_init_inflows(const int32_t* up_off, const int32_t* up_pos, const uint8_t* is_outlet,
+                                const double* O, double* I, int64_t n, int ld, int M, cudaStream_t st);
+cudaError_t launch_apply_gain(const int32_t* up_off, const int32_t* up_pos, const double* G, double* O,
+                              double* I, int64_t n, int ld, int M, cudaStream_t st);
+// dst[pos][m] = src[reach_of_pos[pos]][m]   (src [n][M] dense, dst [n][ld])
+cudaError_t launch_pack(const int32_t* reach_of_pos, const double* src, double* dst, int64_t n, int M,
+                        int ld, int src_member_major, cudaStream_t st);
+cudaError_t launch_unpack(const int32_t* reach_of_pos, const double* src, double* dst, int64_t n, int M,
+                          int ld, int dst_member_major, cudaStream_t st);
+cudaError_t launch_gather_rows(const int32_t* pos, int64_t count, const double* X, int ld, int M,
+                               double* out, cudaStream_t st);
+// vector permute: dst[pos] = src[reach_of_pos[pos]]
+cudaError_t launch_permute_vec(const int32_t* reach_of_pos, const double* src, double* dst, int64_t n,
+                               cudaStream_t st);
+
+int64_t launch_count();
+
+}  // namespace txh

@@ -1,0 +1,85 @@
+// txh_topology.hpp -- one-time host pass over the river network.
+//
+// Replaces the implicit ordering of the reference's headwater walk
+// (tx_fast_hydrology/nutils.py:72-88) and `Muskingum.compute_indegree`
+// (tx_fast_hydrology/muskingum.py:322-330) by explicit integer artefacts:
+// indegree, headwaters, topological levels, level order, unbranched chains,
+// the reference's own visit sequence (test hook), and the dataflow schedule
+// the persistent routing kernel consumes.  Pure C++17, no CUDA, exact integers.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace txh {
+
+struct Topology {
+    int64_t n = 0;
+    std::vector<int32_t> end;         // downstream reach; self-loop at outlets
+    std::vector<int32_t> indeg;       // muskingum.py:322-330 (self-loops excluded)
+    std::vector<int32_t> child_off;   // CSR of upstream reaches, ascending id
+    std::vector<int32_t> child;
+    std::vector<int32_t> heads;       // indegree == 0, ascending (muskingum.py:444)
+    std::vector<int32_t> topo;        // a topological order (Kahn, by level then id)
+    std::vector<int32_t> level;       // 0 at headwaters, else 1 + max(level[upstream])
+    int32_t nlevels = 0;
+    std::vector<int32_t> level_off;   // reaches of level l are topo[level_off[l]..level_off[l+1])
+    std::vector<int32_t> subtree;     // reaches draining through j (inclusive)
+    std::vector<int32_t> main_child;  // upstream reach of highest level (ties: lowest id), -1 at headwaters
+    std::vector<int32_t> path_id;     // longest-path decomposition: path index of each reach
+    std::vector<int32_t> path_pos;    // position along the path, 0 at the headwater
+    std::vector<int32_t> path_len;    // per path
+    std::vector<int32_t> chain_id;    // maximal unbranched runs (u -> v with indegree[v] == 1)
+    std::vector<int32_t> chain_pos;
+    std::vector<int32_t> chain_len;   // per chain
+    std::vector<int32_t> visit;       // order in which nutils.py:72-88 evaluates reaches
+
+    bool build(int64_t n_, const int64_t* endnodes, std::string& err);
+};
+
+struct SchedParams {
+    int long_path_min = 16;   // paths at least this long become spines
+    int spine_cap = 32;       // reaches per spine task (pure chain segments)
+    int pocket_cap = 48;      // reaches per pocket task (bundled side subtrees)
+    int max_slots = 12;       // shared-memory scratch rows per warp
+};
+
+// Per-reach header word consumed by the routing kernel.
+//   bit 0      : inflow starts from the running accumulator (previous reach's outflow)
+//   bits 1..5  : (scratch slot + 1) the outflow is also parked in, 0 = none
+//   bits 6..31 : number of input words that follow in `inw`
+// Input word: bit 31 set -> state row (position) to gather; else scratch slot id.
+constexpr uint32_t HDR_ACC = 1u;
+constexpr uint32_t INW_ROW = 0x80000000u;
+
+struct TaskDesc {
+    int32_t begin;     // first position (rows [begin, begin+len) are contiguous)
+    int32_t len;
+    int32_t in_off;    // offset of the task's first input word
+    int32_t dep_off;   // offset into `deps`
+    int32_t n_raw;     // producers: tasks whose rows this task gathers (same step)
+    int32_t n_war;     // consumers: tasks that gather this task's rows (previous step)
+};
+
+struct Schedule {
+    SchedParams prm;
+    std::vector<int32_t> pos_of_reach, reach_of_pos;
+    std::vector<TaskDesc> tasks;            // in claim (topological, critical-path-first) order
+    std::vector<int32_t> deps;
+    std::vector<uint32_t> hdr;              // per position
+    std::vector<uint32_t> inw;
+    std::vector<int32_t> task_of_pos;
+    std::vector<uint8_t> task_kind;         // 0 spine, 1 pocket
+    // position-space CSR of upstream rows (level kernel, init_inflows, apply_gain)
+    std::vector<int32_t> up_off, up_pos;
+    std::vector<int32_t> lvl_pos, lvl_off;  // positions sorted by level
+    std::vector<uint8_t> is_outlet_pos;
+    // statistics
+    int32_t n_spine = 0, n_pocket = 0, slots_used = 0, row_fallbacks = 0;
+    int32_t cp_tasks = 0;                   // tasks on the longest dependent chain
+    int64_t cp_cost = 0;
+
+    bool build(const Topology& t, const SchedParams& p, std::string& err);
+};
+
+}  // namespace txh

@@ -1,0 +1,229 @@
+"""`RiverNetwork`: Python owner of a `txh_net` handle (topology + schedule +
+device descriptors) and thin typed wrappers over the routing entry points.
+
+Device state is held in torch CUDA tensors (torch is the allocator / stream
+plumbing); only raw pointers cross into libtxh.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _cuda_ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Forcing:
+    """Lateral-inflow table resident in HBM (`txh_forcing`)."""
+
+    def __init__(self, net, times_ns, table, member_mul=None):
+        lib = L.load()
+        self.net = net
+        times = L.as_f64(np.asarray(times_ns).astype(np.float64))
+        table = L.as_f64(table)
+        R, n = table.shape
+        if n != net.n or times.size != R:
+            raise ValueError("forcing table must be [len(times)][n]")
+        M = 0
+        mp = L.p_f64()
+        if member_mul is not None:
+            member_mul = L.as_f64(member_mul)
+            if member_mul.shape[0] != R:
+                raise ValueError("member multipliers must be [len(times)][M]")
+            M = member_mul.shape[1]
+            mp = L.ptr_f64(member_mul)
+        h = ctypes.c_void_p()
+        L.check(lib.txh_forcing_create(net.handle, R, L.ptr_f64(times), L.ptr_f64(table), M, mp,
+                                       ctypes.byref(h)))
+        self.handle = h
+        self.R = R
+        self.M = M
+        self.h2d_bytes = table.nbytes + (member_mul.nbytes if member_mul is not None else 0)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            L.load().txh_forcing_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RiverNetwork:
+    def __init__(self, endnodes, sched_params=None):
+        lib = L.load()
+        self._lib = lib
+        end = L.as_i64(endnodes)
+        self.n = int(end.size)
+        sp = None
+        if sched_params is not None:
+            sp = (ctypes.c_int32 * 4)(*[int(x) for x in sched_params])
+        h = ctypes.c_void_p()
+        L.check(lib.txh_create(self.n, L.ptr_i64(end), sp, ctypes.byref(h)))
+        self.handle = h
+        self.endnodes = end
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.txh_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- topology (host, exact integers) -------------------------------------------------
+    def indegree(self):
+        out = np.empty(self.n, dtype=np.int64)
+        L.check(self._lib.txh_get_indegree(self.handle, L.ptr_i64(out)))
+        return out
+
+    def headwaters(self):
+        out = np.empty(self.n, dtype=np.int64)
+        cnt = ctypes.c_int64()
+        L.check(self._lib.txh_get_headwaters(self.handle, L.ptr_i64(out), ctypes.byref(cnt)))
+        return out[:cnt.value].copy()
+
+    def levels(self):
+        out = np.empty(self.n, dtype=np.int64)
+        nl = ctypes.c_int64()
+        L.check(self._lib.txh_get_levels(self.handle, L.ptr_i64(out), ctypes.byref(nl)))
+        return out, int(nl.value)
+
+    def level_order(self):
+        _, nl = self.levels()
+        order = np.empty(self.n, dtype=np.int64)
+        off = np.empty(nl + 1, dtype=np.int64)
+        L.check(self._lib.txh_get_level_order(self.handle, L.ptr_i64(order), L.ptr_i64(off)))
+        return order, off
+
+    def chains(self):
+        cid = np.empty(self.n, dtype=np.int64); cpos = np.empty(self.n, dtype=np.int64)
+        clen = np.empty(self.n, dtype=np.int64); nc = ctypes.c_int64()
+        L.check(self._lib.txh_get_chains(self.handle, L.ptr_i64(cid), L.ptr_i64(cpos), L.ptr_i64(clen),
+                                         ctypes.byref(nc)))
+        return cid, cpos, clen[:nc.value].copy()
+
+    def paths(self):
+        pid = np.empty(self.n, dtype=np.int64); ppos = np.empty(self.n, dtype=np.int64)
+        L.check(self._lib.txh_get_paths(self.handle, L.ptr_i64(pid), L.ptr_i64(ppos)))
+        return pid, ppos
+
+    def visit_order(self):
+        out = np.empty(self.n, dtype=np.int64)
+        L.check(self._lib.txh_get_visit_order(self.handle, L.ptr_i64(out)))
+        return out
+
+    def schedule_info(self):
+        info = np.zeros(10, dtype=np.int64)
+        L.check(self._lib.txh_get_schedule_info(self.handle, L.ptr_i64(info)))
+        keys = ["n_tasks", "n_spine", "n_pocket", "n_input_words", "n_deps", "slots_used",
+                "row_fallbacks", "cp_tasks", "cp_cost", "nlevels"]
+        return dict(zip(keys, (int(x) for x in info)))
+
+    def schedule(self):
+        info = self.schedule_info()
+        pos = np.empty(self.n, dtype=np.int64)
+        tasks = np.empty((info["n_tasks"], 6), dtype=np.int32)
+        deps = np.empty(max(1, info["n_deps"]), dtype=np.int32)
+        hdr = np.empty(self.n, dtype=np.uint32)
+        inw = np.empty(max(1, info["n_input_words"]), dtype=np.uint32)
+        L.check(self._lib.txh_get_schedule(
+            self.handle, L.ptr_i64(pos), tasks.ctypes.data_as(L.p_i32), deps.ctypes.data_as(L.p_i32),
+            hdr.ctypes.data_as(L.p_u32), inw.ctypes.data_as(L.p_u32)))
+        return {"pos_of_reach": pos, "tasks": tasks, "deps": deps[:info["n_deps"]], "hdr": hdr,
+                "inw": inw[:info["n_input_words"]]}
+
+    # ---- coefficients ---------------------------------------------------------------------
+    def compute_coeffs(self, K, X, dt):
+        K = L.as_f64(K); X = L.as_f64(X)
+        out = [np.empty(self.n) for _ in range(4)]
+        L.check(self._lib.txh_compute_coeffs(self.handle, L.ptr_f64(K), L.ptr_f64(X), float(dt),
+                                             *[L.ptr_f64(o) for o in out]))
+        return tuple(out)
+
+    def set_coeffs(self, alpha, beta, chi, gamma):
+        arrs = [L.as_f64(a) for a in (alpha, beta, chi, gamma)]
+        L.check(self._lib.txh_set_coeffs(self.handle, *[L.ptr_f64(a) for a in arrs]))
+
+    # ---- device state ---------------------------------------------------------------------
+    @staticmethod
+    def row_stride(M):
+        return int(L.load().txh_row_stride(int(M)))
+
+    def alloc_state(self, M, device="cuda"):
+        import torch
+        return torch.zeros((self.n, self.row_stride(M)), dtype=torch.float64, device=device)
+
+    def pack_host(self, src, M, dst, member_major=False):
+        src = L.as_f64(src)
+        L.check(self._lib.txh_pack_host(self.handle, L.ptr_f64(src), int(M), int(member_major),
+                                        _cuda_ptr(dst), _stream_ptr()))
+
+    def unpack_host(self, src, M, member_major=False):
+        out = np.empty((M, self.n) if member_major else (self.n, M), dtype=np.float64)
+        L.check(self._lib.txh_unpack_host(self.handle, _cuda_ptr(src), int(M), int(member_major),
+                                          L.ptr_f64(out), _stream_ptr()))
+        return out
+
+    def pack_dev(self, src, M, dst):
+        L.check(self._lib.txh_pack_dev(self.handle, _cuda_ptr(src), int(M), _cuda_ptr(dst), _stream_ptr()))
+
+    def unpack_dev(self, src, M, dst):
+        L.check(self._lib.txh_unpack_dev(self.handle, _cuda_ptr(src), int(M), _cuda_ptr(dst), _stream_ptr()))
+
+    def gather_rows(self, X, M, reach_idx, out):
+        idx = L.as_i64(reach_idx)
+        L.check(self._lib.txh_gather_rows(self.handle, _cuda_ptr(X), int(M), L.ptr_i64(idx), idx.size,
+                                          _cuda_ptr(out), _stream_ptr()))
+
+    def init_inflows(self, O, I, M):
+        L.check(self._lib.txh_init_inflows(self.handle, _cuda_ptr(O), _cuda_ptr(I), int(M), _stream_ptr()))
+
+    # ---- routing ----------------------------------------------------------------------------
+    def route_run(self, O, I, M, forcing, t0_ns, dt_ns, nsteps, method=1, rec_reach=None, rec_every=1,
+                  rec_out=None):
+        fh = forcing.handle if forcing is not None else None
+        if rec_reach is not None:
+            rr = L.as_i64(rec_reach)
+            rp, rc, ro = L.ptr_i64(rr), rr.size, _cuda_ptr(rec_out)
+        else:
+            rp, rc, ro = L.p_i64(), 0, None
+        L.check(self._lib.txh_route_run(self.handle, _cuda_ptr(O), _cuda_ptr(I), int(M), fh, int(t0_ns),
+                                        int(dt_ns), int(nsteps), int(method), rp, rc, int(rec_every), ro,
+                                        _stream_ptr()))
+
+    def route_step(self, O, I, M, q_dev=None, levels=False):
+        fn = self._lib.txh_route_step_levels if levels else self._lib.txh_route_step
+        L.check(fn(self.handle, _cuda_ptr(O), _cuda_ptr(I), int(M),
+                   _cuda_ptr(q_dev) if q_dev is not None else None, _stream_ptr()))
+
+    def route_apply(self, X, Iscr, M):
+        L.check(self._lib.txh_route_apply(self.handle, _cuda_ptr(X), _cuda_ptr(Iscr), int(M), _stream_ptr()))
+
+    def apply_gain(self, G, O, I, M):
+        L.check(self._lib.txh_apply_gain(self.handle, _cuda_ptr(G), _cuda_ptr(O), _cuda_ptr(I), int(M),
+                                         _stream_ptr()))
+
+    def check(self):
+        L.check(self._lib.txh_check(self.handle, _stream_ptr() if self._has_cuda() else None))
+
+    @staticmethod
+    def _has_cuda():
+        try:
+            import torch
+            return torch.cuda.is_available()
+        except Exception:
+            return False
