@@ -1,0 +1,470 @@
+"""`Muskingum`: drop-in for the reference's model object (tx_fast_hydrology/muskingum.py:20-606)
+whose routing runs on the GPU.
+
+Same constructor, attributes, `step` / `simulate` entry points, callback firing
+order and state save/load behaviour as the reference; the numba call at
+muskingum.py:456 (`_ax_bu`) is replaced by `txh_route_step` and the Python loop of
+`simulate_iter` (muskingum.py:527-533) gains a device-resident fast path, `run()`,
+that keeps Python out of the per-step loop.
+
+State lives in HBM in the library's schedule order.  `o_t_next`, `i_t_next`,
+`o_t_prev`, `i_t_prev` are numpy views of it, materialised on access; once
+looked at they may have been mutated in place (KalmanFilter does, da.py:125-126),
+so the host copy is pushed back before the next launch.  Reference quirks kept
+on purpose: self-loop inflow in `init_states` (A.3),
+`dt = timedelta.seconds` (A.4), the variable-timestep behaviour of `step` (A.5),
+`load_state` aliasing (A.12), the never-raised ValueError in `simulate` (A.13).
+
+Extension: `members=M` batches M ensemble members; state arrays are then (n, M).
+"""
+import copy as _copy
+import datetime as _dt
+import json
+import logging
+import uuid
+
+import numpy as np
+import pandas as pd
+
+from .callbacks import BaseCallback
+from .network import Forcing, RiverNetwork
+
+DEFAULT_START_TIME = pd.to_datetime(0., utc=True)
+DEFAULT_TIMEDELTA = pd.to_timedelta(3600, unit='s')
+
+_REQUIRED = ('name', 'datetime', 'timedelta', 'reach_ids', 'startnodes', 'endnodes', 'K', 'X', 'o_t')
+_OPTIONAL = ('paths', 'dx')
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("tx_fast_hydrology_b200 needs a CUDA device: there is no CPU fallback")
+    return torch
+
+
+class Muskingum:
+    def __init__(self, data, load_optional=True, create_state_space=False, sparse=False,
+                 members=1, sched_params=None):
+        self.sparse = sparse
+        self.callbacks = {}
+        self.saved_states = {}
+        self.sinks = []
+        self.sources = []
+        self.members = int(members)
+        self._sched_params = sched_params
+        if isinstance(data, dict):
+            self.load_model(data, load_optional=load_optional)
+        elif isinstance(data, str):
+            self.load_model_file(data, load_optional=load_optional)
+        else:
+            raise TypeError('`data` must be a file path or dictionary.')
+        self.logger = logging.getLogger(self.name)
+        n = self.n
+        # dense A/B of muskingum.py:163-168 are out of scope (O(n^2), unused by the hot path)
+        self.A = None
+        self.B = None
+        if create_state_space:
+            raise NotImplementedError('dense state-space matrices are not built by the GPU drop-in')
+        self.alpha = np.zeros(n, dtype=np.float64)
+        self.beta = np.zeros(n, dtype=np.float64)
+        self.chi = np.zeros(n, dtype=np.float64)
+        self.gamma = np.zeros(n, dtype=np.float64)
+        self._coef_seen = None
+        self._dev = None                 # device tensors, created on first use
+        self._host = {}                  # materialised numpy views
+        self._host_dirty = False         # host copy may have been mutated since materialised
+        shape = (n,) if self.members == 1 else (n, self.members)
+        o0 = np.asarray(self.o_t_next, dtype=np.float64)
+        if o0.shape != shape:
+            o0 = np.broadcast_to(o0.reshape(n, -1), (n, self.members)).reshape(shape)
+        self._host = {'o_t_next': np.array(o0, dtype=np.float64), 'i_t_next': np.zeros(shape),
+                      'o_t_prev': np.zeros(shape), 'i_t_prev': np.zeros(shape)}
+        self._host_dirty = True
+        self._dev_valid = False
+        self.init_states(o_t_next=self._host['o_t_next'])
+        self._host['o_t_prev'] = self._host['o_t_next'].copy()
+        self._host['i_t_prev'] = self._host['i_t_next'].copy()
+        self.compute_muskingum_coeffs()
+        self.save_state()
+
+    # ------------------------------------------------------------------ metadata
+    @property
+    def info(self):
+        return {'name': self.name, 'datetime': self.datetime, 'timedelta': self.timedelta,
+                'reach_ids': self.reach_ids, 'startnodes': self.startnodes, 'endnodes': self.endnodes,
+                'K': self.K, 'X': self.X, 'o_t': self.o_t_next, 'dx': self.dx, 'paths': self.paths}
+
+    @property
+    def name(self):
+        return self._name
+
+    @name.setter
+    def name(self, new_name):
+        if not isinstance(new_name, str):
+            new_name = str(new_name)
+        self._name = new_name
+
+    @property
+    def datetime(self):
+        return self._datetime
+
+    @datetime.setter
+    def datetime(self, new_datetime):
+        if not isinstance(new_datetime, pd.Timestamp):
+            raise TypeError('New datetime must be of type `pd.Timestamp`')
+        if new_datetime.tz != _dt.timezone.utc:
+            raise ValueError('New datetime must be UTC.')
+        self._datetime = new_datetime
+
+    @property
+    def timedelta(self):
+        return self._timedelta
+
+    @timedelta.setter
+    def timedelta(self, new_timedelta):
+        if not isinstance(new_timedelta, pd.Timedelta):
+            raise TypeError('New timedelta must be of type `pd.Timedelta`')
+        self._timedelta = new_timedelta
+
+    @property
+    def dt(self):
+        return float(self.timedelta.seconds)          # muskingum.py:247-250 (seconds component)
+
+    # ------------------------------------------------------------------ state views
+    def _materialise(self):
+        if not self._host:
+            net, M, d = self.network, self.members, self._dev
+            net.check()
+            shape = (self.n,) if M == 1 else (self.n, M)
+            self._host = {
+                'o_t_next': net.unpack_host(d['O'], M).reshape(shape),
+                'i_t_next': net.unpack_host(d['I'], M).reshape(shape),
+                'o_t_prev': net.unpack_host(d['Op'], M).reshape(shape),
+                'i_t_prev': net.unpack_host(d['Ip'], M).reshape(shape),
+            }
+        # a caller holding these arrays may write into them (da.py:125-126 does)
+        self._host_dirty = True
+        return self._host
+
+    def _state_get(self, key):
+        return self._materialise()[key]
+
+    def _state_set(self, key, value):
+        h = self._materialise()
+        h[key] = value
+        self._host_dirty = True
+
+    o_t_next = property(lambda self: self._state_get('o_t_next'),
+                        lambda self, v: self._state_set('o_t_next', v))
+    i_t_next = property(lambda self: self._state_get('i_t_next'),
+                        lambda self, v: self._state_set('i_t_next', v))
+    o_t_prev = property(lambda self: self._state_get('o_t_prev'),
+                        lambda self, v: self._state_set('o_t_prev', v))
+    i_t_prev = property(lambda self: self._state_get('i_t_prev'),
+                        lambda self, v: self._state_set('i_t_prev', v))
+
+    @property
+    def o_t(self):
+        return self.o_t_next
+
+    @o_t.setter
+    def o_t(self, new_o_t):
+        try:
+            new_o_t = np.asarray(new_o_t, dtype=np.float64)
+        except Exception:
+            raise TypeError('New `o_t` must be convertible to float64 np.ndarray')
+        self.o_t_next = new_o_t
+
+    # ------------------------------------------------------------------ loading
+    def load_model(self, obj, load_optional=True):
+        defaults = {'name': str(uuid.uuid4()), 'datetime': DEFAULT_START_TIME,
+                    'timedelta': DEFAULT_TIMEDELTA, 'dx': None, 'paths': []}
+        if not set(_REQUIRED).issubset(obj.keys()):
+            raise ValueError(f'Model field must contain fields {set(_REQUIRED)}')
+        for key, dtype in (('startnodes', np.int64), ('endnodes', np.int64), ('K', np.float64),
+                           ('X', np.float64), ('o_t', np.float64)):
+            v = obj[key]
+            if not isinstance(v, np.ndarray) or v.dtype != dtype:
+                raise TypeError('Typing of input arrays is incorrect.')
+        n = obj['startnodes'].size
+        if not (obj['endnodes'].size == obj['K'].size == obj['X'].size == n) or obj['o_t'].shape[0] != n:
+            raise ValueError('Arrays are not the same length')
+        fields = _REQUIRED + (_OPTIONAL if load_optional else ())
+        for field in fields:
+            value = obj.setdefault(field, defaults[field]) if field in defaults else obj[field]
+            if field == 'o_t':
+                self.__dict__['_o_t_initial'] = value
+            else:
+                setattr(self, field, value)
+        if not load_optional:
+            self.dx, self.paths = None, []
+        self.n = n
+        if not (self.startnodes == np.arange(n)).all():
+            # the reference silently mis-indexes in this case (nutils.py:73-83)
+            raise ValueError('`startnodes` must equal arange(n)')
+        self.network = RiverNetwork(self.endnodes, self._sched_params)
+        self.indegree = self.compute_indegree(self.startnodes, self.endnodes)
+        self._host = {'o_t_next': self._o_t_initial}
+
+    def load_model_file(self, file_path, load_optional=True):
+        self.load_model(load_model_file(file_path, load_optional=load_optional))
+
+    def dump_model_file(self, file_path, dump_optional=True):
+        return dump_model_file(self.info, file_path, dump_optional=dump_optional)
+
+    @classmethod
+    def from_model_file(cls, file_path, load_optional=True, **kwargs):
+        return cls(load_model_file(file_path, load_optional=load_optional), **kwargs)
+
+    def compute_indegree(self, startnodes, endnodes):
+        """muskingum.py:322-330, from the exact-integer topology pass."""
+        return self.network.indegree()
+
+    # ------------------------------------------------------------------ coefficients
+    def compute_alpha(self, K, X, dt):
+        return (dt - 2 * K * X) / (2 * K * (1 - X) + dt)
+
+    def compute_beta(self, K, X, dt):
+        return (dt + 2 * K * X) / (2 * K * (1 - X) + dt)
+
+    def compute_chi(self, K, X, dt):
+        return (2 * K * (1 - X) - dt) / (2 * K * (1 - X) + dt)
+
+    def compute_gamma(self, K, X, dt):
+        return dt / (K * (1 - X) + dt / 2)
+
+    def compute_muskingum_coeffs(self, K=None, X=None, dt=None):
+        self.logger.info('Computing Muskingum coefficients...')
+        K = self.K if K is None else K
+        X = self.X if X is None else X
+        dt = self.dt if dt is None else dt
+        a, b, c, g = self.network.compute_coeffs(K, X, dt)     # muskingum.py:332-360 on the handle
+        self.alpha[:] = a
+        self.beta[:] = b
+        self.chi[:] = c
+        self.gamma[:] = g
+        self._coef_seen = (a, b, c, g)
+
+    def set_transmissive_boundary(self, index):
+        self.alpha[index] = 1.
+        self.beta[index] = 0.
+        self.chi[index] = 0.
+        self.gamma[index] = 0.
+
+    def _sync_coeffs(self):
+        """The coefficient arrays are user-mutable (muskingum.py:567-571): re-install on change."""
+        cur = (self.alpha, self.beta, self.chi, self.gamma)
+        if self._coef_seen is None or any(not np.array_equal(x, y) for x, y in zip(cur, self._coef_seen)):
+            self.network.set_coeffs(*cur)
+            self._coef_seen = tuple(x.copy() for x in cur)
+
+    # ------------------------------------------------------------------ device plumbing
+    def _ensure_device(self):
+        torch = _torch()
+        net, M = self.network, self.members
+        if self._dev is None:
+            self._dev = {k: net.alloc_state(M) for k in ('O', 'I', 'Op', 'Ip')}
+            self._dev_valid = False
+        if self._host and (self._host_dirty or not self._dev_valid):
+            h, d = self._host, self._dev
+            for hk, dk in (('o_t_next', 'O'), ('i_t_next', 'I'), ('o_t_prev', 'Op'), ('i_t_prev', 'Ip')):
+                net.pack_host(np.asarray(h[hk], dtype=np.float64).reshape(self.n, M), M, d[dk])
+        self._dev_valid = True
+        self._host_dirty = False
+        return torch
+
+    def _device_advanced(self):
+        self._host = {}
+        self._host_dirty = False
+
+    def init_states(self, o_t_next=None, i_t_next=None):
+        """muskingum.py:410-419: i = scatter-add of o over endnodes (self-loops included)."""
+        h = self._materialise()
+        shape = h['o_t_next'].shape if 'o_t_next' in h and hasattr(h['o_t_next'], 'shape') else None
+        full = (self.n,) if self.members == 1 else (self.n, self.members)
+        o = np.zeros(full) if o_t_next is None else np.array(
+            np.broadcast_to(np.asarray(o_t_next, dtype=np.float64).reshape(self.n, -1),
+                            (self.n, self.members)).reshape(full))
+        h['o_t_next'] = o
+        if i_t_next is None:
+            i = np.zeros(full)
+            np.add.at(i, self.endnodes, o[self.startnodes])
+            h['i_t_next'] = i
+        else:
+            h['i_t_next'] = np.array(np.asarray(i_t_next, dtype=np.float64).reshape(full))
+        for k in ('o_t_prev', 'i_t_prev'):
+            if k not in h or np.shape(h[k]) != full:
+                h[k] = np.zeros(full)
+        self._host_dirty = True
+        del shape
+
+    # ------------------------------------------------------------------ stepping
+    def step_iter(self, p_t_next, timedelta=None):
+        """muskingum.py:435-465 with the numba call replaced by one device launch."""
+        if timedelta is None:
+            timedelta = self.timedelta
+            dt = self.dt
+        else:
+            dt = float(timedelta.seconds)
+        if dt != self.dt:
+            self.logger.warning('Timestep has changed. Recomputing Muskingum coefficients.')
+            self.compute_muskingum_coeffs(dt=dt)
+        for _, callback in self.callbacks.items():
+            callback.__on_step_start__()
+        torch = self._ensure_device()
+        self._sync_coeffs()
+        d, net, M = self._dev, self.network, self.members
+        d['Op'].copy_(d['O'])
+        d['Ip'].copy_(d['I'])
+        q = torch.from_numpy(np.ascontiguousarray(p_t_next, dtype=np.float64)).cuda()
+        net.route_step(d['O'], d['I'], M, q)
+        self._device_advanced()
+        self.datetime += timedelta
+        for _, callback in self.callbacks.items():
+            callback.__on_step_end__()
+        self.logger.debug('Stepped to time %s', self.datetime)
+
+    def step(self, p_t_next, timedelta=None):
+        return self.step_iter(p_t_next, timedelta=timedelta)
+
+    def simulate_iter(self, dataframe, start_time=None, end_time=None, o_t_init=None, **kwargs):
+        """muskingum.py:499-536: generator yielding `self` after every step."""
+        assert isinstance(dataframe.index, pd.DatetimeIndex)
+        assert (dataframe.index.tz == _dt.timezone.utc)
+        cols = pd.Index(dataframe.columns)
+        assert cols.get_indexer(pd.Index(self.reach_ids)).min() >= 0
+        if end_time is None:
+            end_time = dataframe.index.max()
+        elif not isinstance(end_time, pd.Timestamp):
+            raise TypeError('`end_time` must be of type `pd.Timestamp`')
+        if start_time is not None:
+            self.datetime = start_time          # (the reference builds, but never raises, a ValueError here)
+        if o_t_init is not None:
+            self.init_states(o_t_next=o_t_init)
+        for _, callback in self.callbacks.items():
+            callback.__on_simulation_start__()
+        dataframe = dataframe[self.reach_ids]
+        times = dataframe.index.astype(int).astype(float).values
+        table = np.ascontiguousarray(dataframe.values, dtype=np.float64)
+        from .nutils import interpolate_sample
+        while self.datetime < end_time:
+            next_timestep = self.datetime + self.timedelta
+            p_t_next = interpolate_sample(float(next_timestep.value), times, table)
+            self.step_iter(p_t_next, **kwargs)
+            yield self
+        for _, callback in self.callbacks.items():
+            callback.__on_simulation_end__()
+
+    def simulate(self, dataframe, start_time=None, end_time=None, o_t_init=None, **kwargs):
+        return self.simulate_iter(dataframe, start_time=start_time, end_time=end_time,
+                                  o_t_init=o_t_init, **kwargs)
+
+    # ------------------------------------------------------------------ device-resident fast path
+    def make_forcing(self, dataframe=None, times_ns=None, table=None, member_mul=None):
+        """Upload a forcing table once.  Either a DataFrame (as `simulate` takes) or raw arrays."""
+        if dataframe is not None:
+            dataframe = dataframe[self.reach_ids]
+            times_ns = dataframe.index.astype(int).values
+            table = dataframe.values
+        return Forcing(self.network, times_ns, table, member_mul)
+
+    def run(self, forcing, nsteps, record_reaches=None, record_every=1, method='linear'):
+        """`nsteps` steps of the simulate loop (muskingum.py:527-533) in ONE persistent kernel
+        launch: forcing interpolated on the device at t + dt, state updated in HBM, Python out
+        of the loop.  Fires no per-step callbacks (bind-free fast path); returns the recorded
+        outflows [nsteps // record_every][len(record_reaches)][members] as a CUDA tensor, or None.
+        `o_t_prev` / `i_t_prev` afterwards hold the state before the last step only if nsteps == 1."""
+        torch = self._ensure_device()
+        self._sync_coeffs()
+        d, net, M = self._dev, self.network, self.members
+        rec = None
+        if record_reaches is not None:
+            rec = torch.zeros((nsteps // record_every, len(record_reaches), M), dtype=torch.float64,
+                              device='cuda')
+        step_ns = int(self.timedelta.value)
+        if step_ns != int(round(self.dt * 1e9)):
+            raise ValueError('run() needs a whole-second timestep below one day')
+        if nsteps == 1:
+            d['Op'].copy_(d['O']); d['Ip'].copy_(d['I'])
+        net.route_run(d['O'], d['I'], M, forcing, int(self.datetime.value), step_ns, int(nsteps),
+                      method=1 if method == 'linear' else 0, rec_reach=record_reaches,
+                      rec_every=record_every, rec_out=rec)
+        self._device_advanced()
+        self.datetime = self.datetime + nsteps * self.timedelta
+        return rec
+
+    @property
+    def device_state(self):
+        """(O, I) CUDA tensors [n][row_stride(members)] in schedule order."""
+        self._ensure_device()
+        return self._dev['O'], self._dev['I']
+
+    # ------------------------------------------------------------------ checkpointing
+    def save_state(self):
+        """muskingum.py:573-580: snapshot (copies) + callback fan-out."""
+        self.logger.info(f'Saving state for model {self.name} at time {self.datetime}...')
+        self.saved_states['datetime'] = self.datetime
+        self.saved_states['i_t_next'] = self.i_t_next.copy()
+        self.saved_states['o_t_next'] = self.o_t_next.copy()
+        for _, callback in self.callbacks.items():
+            callback.__on_save_state__()
+
+    def load_state(self):
+        """muskingum.py:582-588: restore by reference (aliasing kept)."""
+        self.datetime = self.saved_states['datetime']
+        self.i_t_next = self.saved_states['i_t_next']
+        self.o_t_next = self.saved_states['o_t_next']
+        self.logger.info(f'Loading state for model {self.name} at time {self.datetime}...')
+        for _, callback in self.callbacks.items():
+            callback.__on_load_state__()
+
+    def bind_callback(self, callback, key='callback'):
+        assert isinstance(callback, BaseCallback)
+        self.callbacks[key] = callback
+
+    def unbind_callback(self, key):
+        return self.callbacks.pop(key)
+
+    def copy(self):
+        """Independent model with the same parameters, state and clock (callbacks are not copied)."""
+        d = {k: _copy.deepcopy(v) for k, v in self.info.items()}
+        d['o_t'] = np.array(self.o_t_next)
+        new = type(self)(d, members=self.members, sched_params=self._sched_params)
+        new.init_states(o_t_next=self.o_t_next, i_t_next=self.i_t_next)
+        new.alpha[:], new.beta[:], new.chi[:], new.gamma[:] = self.alpha, self.beta, self.chi, self.gamma
+        return new
+
+
+# ---------------------------------------------------------------------- JSON I/O
+class _Encoder(json.JSONEncoder):
+    def default(self, obj):
+        if isinstance(obj, np.ndarray):
+            return obj.tolist()
+        if isinstance(obj, (pd.Timestamp, pd.Timedelta)):
+            return obj.isoformat()
+        return json.JSONEncoder.default(self, obj)
+
+
+def load_model_file(file_path, load_optional=True):
+    """Model JSON -> the dict `Muskingum` takes (reference: muskingum.py:839-862, io.py)."""
+    with open(file_path) as f:
+        obj = json.load(f)
+    for key, dtype in (('startnodes', np.int64), ('endnodes', np.int64), ('K', np.float64),
+                       ('X', np.float64), ('o_t', np.float64), ('dx', np.float64)):
+        if obj.get(key) is not None:
+            obj[key] = np.asarray(obj[key], dtype=dtype)
+    if 'datetime' in obj:
+        obj['datetime'] = pd.Timestamp(obj['datetime'])
+    if 'timedelta' in obj:
+        obj['timedelta'] = pd.Timedelta(obj['timedelta'])
+    if not load_optional:
+        obj.pop('dx', None)
+        obj.pop('paths', None)
+    return obj
+
+
+def dump_model_file(obj, file_path, dump_optional=True):
+    keys = _REQUIRED + (_OPTIONAL if dump_optional else ())
+    with open(file_path, 'w') as f:
+        json.dump({k: obj[k] for k in keys if k in obj}, f, cls=_Encoder)
