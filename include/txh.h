@@ -65,11 +65,12 @@ int txh_get_chains(const txh_net* net, int64_t* chain_id /*[n]*/, int64_t* chain
                    int64_t* chain_len /*[n] (first nchains used)*/, int64_t* nchains);
 int txh_get_paths(const txh_net* net, int64_t* path_id /*[n]*/, int64_t* path_pos /*[n]*/);
 int txh_get_visit_order(const txh_net* net, int64_t* order /*[n]*/);      /* nutils.py:72-88 */
-/* schedule introspection (tests, tuning).  info = {n_tasks, n_spine, n_pocket,
- * n_input_words, n_deps, slots_used, row_fallbacks, cp_tasks, cp_cost, nlevels} */
+/* schedule introspection (tests, tuning).  info = {n_tasks, n_spine_segments, n_pocket_tasks,
+ * n_input_words, n_notify, slots_used, row_fallbacks, cp_tasks, cp_cost, nlevels}.
+ * task_desc rows are 12 int32: begin, len, in_off, nfy_off, n_same, n_next, need0, need, kind, pad x3 */
 int txh_get_schedule_info(const txh_net* net, int64_t info[10]);
-int txh_get_schedule(const txh_net* net, int64_t* pos_of_reach /*[n]*/, int32_t* task_desc /*[n_tasks*6]*/,
-                     int32_t* deps, uint32_t* hdr /*[n]*/, uint32_t* inw);
+int txh_get_schedule(const txh_net* net, int64_t* pos_of_reach /*[n]*/, int32_t* task_desc /*[n_tasks*12]*/,
+                     int32_t* notify, uint32_t* hdr /*[n]*/, uint32_t* inw);
 
 /* ---- coefficients ----------------------------------------------------------------
  * txh_compute_coeffs replaces Muskingum.compute_muskingum_coeffs (muskingum.py:332-360):

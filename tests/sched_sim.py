@@ -1,0 +1,95 @@
+"""Test-only CPU interpreter of the device schedule (NOT a product path).
+
+Executes the very descriptor arrays the routing kernel consumes (`txh_get_schedule`)
+under the kernel's dataflow protocol -- pending counters, re-arm on completion,
+same-step / next-step notifications, ready set -- with tasks picked in a seeded
+random order, so that both the descriptors and the protocol's invariants are
+checked without a GPU.  Arithmetic follows the kernel's (PRE / CHAIN / POCKET).
+"""
+import numpy as np
+
+ROW = 0x80000000
+POCKET, PRE, CHAIN = 0, 1, 2
+
+
+def simulate(sched, coef, O, I, q_of_step, nsteps, seed=0, order="random"):
+    """coef [n][4], O/I [n] (schedule order, float64; updated in place),
+    q_of_step(s) -> [n] schedule-order forcing.  Returns #tasks executed."""
+    tasks = sched["tasks"]; hdr = sched["hdr"]; inw = sched["inw"]; nfy = sched["notify"]
+    nt = tasks.shape[0]
+    rng = np.random.default_rng(seed)
+    pending = tasks[:, 6].astype(np.int64).copy()           # need0
+    stepno = np.zeros(nt, dtype=np.int64)
+    ready = [k for k in range(nt) if pending[k] == 0]
+    running_guard = np.zeros(nt, dtype=bool)
+    scratch = np.full(32, np.nan)
+    executed = 0
+    while ready:
+        if order == "random":
+            k = ready.pop(int(rng.integers(len(ready))))
+        elif order == "lifo":
+            k = ready.pop()
+        else:
+            k = ready.pop(0)
+        begin, ln, in_off, nfy_off, n_same, n_next, need0, need, kind = (int(x) for x in tasks[k, :9])
+        s = int(stepno[k])
+        assert s < nsteps and pending[k] == 0 and not running_guard[k]
+        running_guard[k] = True
+        q = q_of_step(s)
+        w = in_off
+        if kind == POCKET:
+            acc = 0.0
+            for p in range(begin, begin + ln):
+                h = int(hdr[p]); infl = acc if (h & 1) else 0.0
+                for _ in range(h >> 6):
+                    x = int(inw[w]); w += 1
+                    if x & ROW:
+                        infl += O[x & 0x7fffffff]
+                    else:
+                        assert not np.isnan(scratch[x]); infl += scratch[x]; scratch[x] = np.nan
+                a, b, c, g = coef[p]
+                on = a * infl + (b * I[p] + c * O[p] + g * q[p])
+                I[p] = infl; O[p] = on
+                sl = (h >> 1) & 31
+                if sl:
+                    scratch[sl - 1] = on
+                acc = on
+        elif kind == PRE:
+            for p in range(begin, begin + ln):
+                h = int(hdr[p]); side = 0.0
+                for _ in range((h >> 6) & 0x1fff):
+                    x = int(inw[w]); w += 1
+                    assert x & ROW
+                    side += O[x & 0x7fffffff]
+                a, b, c, g = coef[p]
+                bb = a * side + (b * I[p] + c * O[p] + g * q[p])
+                I[p] = side; O[p] = bb
+        else:
+            o = 0.0
+            for p in range(begin, begin + ln):
+                h = int(hdr[p]); infl = o if (h & 1) else 0.0
+                for _ in range(h >> 19):
+                    x = int(inw[w]); w += 1
+                    assert x & ROW
+                    infl += O[x & 0x7fffffff]
+                on = coef[p][0] * infl + O[p]
+                I[p] = infl + I[p]; O[p] = on
+                o = on
+        executed += 1
+        # completion protocol (route_dataflow_kernel)
+        assert pending[k] == 0, "an event for the next step arrived before the task re-armed"
+        stepno[k] = s + 1
+        more = s + 1 < nsteps
+        if more:
+            pending[k] = need
+        running_guard[k] = False
+        targets = list(nfy[nfy_off:nfy_off + n_same]) + (list(nfy[nfy_off + n_same:nfy_off + n_same + n_next]) if more else [])
+        for t in targets:
+            t = int(t)
+            pending[t] -= 1
+            assert pending[t] >= 0, "dependency counter underflow"
+            if pending[t] == 0:
+                assert stepno[t] < nsteps
+                ready.append(t)
+    assert (stepno == nsteps).all(), "not every task ran every step"
+    return executed

@@ -54,14 +54,15 @@ struct txh_net {
     int num_sms = 0;
     unsigned long long watchdog_ns = 10000000000ull;
     TaskDesc* d_tasks = nullptr;
-    int32_t *d_deps = nullptr, *d_up_off = nullptr, *d_up_pos = nullptr, *d_lvl_pos = nullptr,
+    int32_t *d_notify = nullptr, *d_init_ready = nullptr, *d_up_off = nullptr, *d_up_pos = nullptr, *d_lvl_pos = nullptr,
             *d_reach_of_pos = nullptr, *d_pos_of_reach = nullptr;
     uint32_t *d_hdr = nullptr, *d_inw = nullptr;
     uint8_t* d_outlet = nullptr;
     double* d_coef = nullptr;
     double* d_qtmp = nullptr;           // [n] schedule-order scratch for txh_route_step
-    int32_t* d_done = nullptr; size_t done_cap = 0;
-    unsigned long long* d_ticket = nullptr;   // [0] ticket, followed by status word
+    int32_t* d_pending = nullptr; size_t pairs_cap = 0;    // [pairs] pending, then [pairs] stepno
+    uint32_t* d_queue = nullptr; size_t queue_cap = 0;
+    unsigned long long* d_qctl = nullptr;     // [0] head, [1] tail, [2] completed, [4] status word
     int32_t* d_status = nullptr;
     StepInterp* d_steps = nullptr; size_t steps_cap = 0;
     StepInterp* d_unit_step = nullptr;
@@ -95,7 +96,8 @@ int ensure_device(txh_net* net)
     const Schedule& s = net->sched;
     int rc;
     if ((rc = upload(&net->d_tasks, s.tasks))) return rc;
-    if ((rc = upload(&net->d_deps, s.deps))) return rc;
+    if ((rc = upload(&net->d_notify, s.notify))) return rc;
+    if ((rc = upload(&net->d_init_ready, s.init_ready))) return rc;
     if ((rc = upload(&net->d_hdr, s.hdr))) return rc;
     if ((rc = upload(&net->d_inw, s.inw))) return rc;
     if ((rc = upload(&net->d_up_off, s.up_off))) return rc;
@@ -106,9 +108,9 @@ int ensure_device(txh_net* net)
     if ((rc = upload(&net->d_outlet, s.is_outlet_pos))) return rc;
     CU(cudaMalloc((void**)&net->d_coef, sizeof(double) * 4 * net->topo.n));
     CU(cudaMalloc((void**)&net->d_qtmp, sizeof(double) * net->topo.n));
-    CU(cudaMalloc((void**)&net->d_ticket, 64));
-    net->d_status = reinterpret_cast<int32_t*>(net->d_ticket + 1);
-    CU(cudaMemset(net->d_ticket, 0, 64));
+    CU(cudaMalloc((void**)&net->d_qctl, 64));
+    net->d_status = reinterpret_cast<int32_t*>(net->d_qctl + 4);
+    CU(cudaMemset(net->d_qctl, 0, 64));
     CU(cudaMalloc((void**)&net->d_rec_slot, sizeof(int32_t) * net->topo.n));
     CU(cudaMallocHost((void**)&net->h_status, sizeof(int32_t)));
     *net->h_status = 0;
@@ -150,23 +152,49 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
     const Schedule& s = net->sched;
     const int ld = (int)txh_row_stride(M);
     const int nmb = (ld + kMemberBlock - 1) / kMemberBlock;
-    const size_t need = (size_t)s.tasks.size() * nmb;
-    if (need > net->done_cap) {
-        if (net->d_done) CU(cudaFree(net->d_done));
-        CU(cudaMalloc((void**)&net->d_done, need * sizeof(int32_t)));
-        net->done_cap = need;
+    const size_t pairs = (size_t)s.tasks.size() * nmb;
+    if (pairs >= (size_t(1) << 31)) return fail(TXH_E_INVALID, "too many (task, member block) pairs");
+    if (pairs > net->pairs_cap) {
+        if (net->d_pending) CU(cudaFree(net->d_pending));
+        CU(cudaMalloc((void**)&net->d_pending, 2 * pairs * sizeof(int32_t)));
+        net->pairs_cap = pairs;
     }
-    CU(cudaMemsetAsync(net->d_done, 0, need * sizeof(int32_t), st));
-    CU(cudaMemsetAsync(net->d_ticket, 0, sizeof(unsigned long long), st));   // status stays sticky
-    RouteArgs a{};
-    a.tasks = net->d_tasks; a.deps = net->d_deps; a.hdr = net->d_hdr; a.inw = net->d_inw;
-    a.coef = net->d_coef; a.O = O; a.I = I; a.F = F; a.steps = d_steps; a.Wmul = W;
-    a.rec_slot = rec_slot; a.rec_out = rec_out; a.done = net->d_done; a.ticket = net->d_ticket;
-    a.status = net->d_status; a.n = net->topo.n; a.n_tasks = (int32_t)s.tasks.size(); a.n_mblocks = nmb;
-    a.nsteps = (int32_t)nsteps; a.slots = std::max(1, s.slots_used); a.ld = ld; a.M = (int32_t)M;
-    a.wm_ld = wm_ld; a.rec_every = rec_every; a.rec_count = rec_count;
-    a.watchdog_ns = net->watchdog_ns;
-    CU(launch_route_dataflow(a, net->num_sms, st));
+    // the ready queue never wraps: one slot per (pair, step); long runs go out in several launches
+    const int64_t max_entries = int64_t(1) << 26;
+    int64_t steps_per_launch = std::max<int64_t>(1, std::min<int64_t>(nsteps, max_entries / (int64_t)pairs));
+    if (rec_slot && rec_every > 1 && steps_per_launch < nsteps)
+        steps_per_launch = std::max<int64_t>(rec_every, steps_per_launch / rec_every * rec_every);
+    const size_t qneed = pairs * (size_t)steps_per_launch;
+    if (qneed > net->queue_cap) {
+        if (net->d_queue) CU(cudaFree(net->d_queue));
+        CU(cudaMalloc((void**)&net->d_queue, qneed * sizeof(uint32_t)));
+        net->queue_cap = qneed;
+    }
+    for (int64_t s0 = 0; s0 < nsteps; s0 += steps_per_launch) {
+        const int64_t ns = std::min<int64_t>(steps_per_launch, nsteps - s0);
+        CU(cudaMemsetAsync(net->d_queue, 0, pairs * (size_t)ns * sizeof(uint32_t), st));
+        InitArgs ia{};
+        ia.tasks = net->d_tasks; ia.init_ready = net->d_init_ready; ia.pending = net->d_pending;
+        ia.stepno = net->d_pending + net->pairs_cap; ia.queue = net->d_queue; ia.q_head = net->d_qctl;
+        ia.n_tasks = (int32_t)s.tasks.size(); ia.n_mblocks = nmb; ia.n_init = (int32_t)s.init_ready.size();
+        CU(launch_dataflow_init(ia, st));
+        RouteArgs a{};
+        a.tasks = net->d_tasks; a.notify = net->d_notify; a.hdr = net->d_hdr; a.inw = net->d_inw;
+        a.coef = net->d_coef; a.O = O; a.I = I; a.F = F; a.steps = d_steps + s0; a.Wmul = W;
+        a.rec_slot = rec_slot;
+        a.rec_out = rec_out;
+        if (rec_slot && s0 > 0) {
+            if (s0 % rec_every != 0) return fail(TXH_E_INVALID, "internal: launch split not aligned with rec_every");
+            a.rec_out = rec_out + (size_t)(s0 / rec_every) * rec_count * M;
+        }
+        a.pending = ia.pending; a.stepno = ia.stepno; a.queue = net->d_queue; a.q_head = net->d_qctl;
+        a.status = net->d_status; a.watchdog_ns = net->watchdog_ns;
+        a.total = (long long)pairs * ns;
+        a.n = net->topo.n; a.n_tasks = ia.n_tasks; a.n_mblocks = nmb; a.nsteps = (int32_t)ns;
+        a.slots = std::max(1, s.slots_used); a.ld = ld; a.M = (int32_t)M;
+        a.wm_ld = wm_ld; a.rec_every = rec_every; a.rec_count = rec_count;
+        CU(launch_route_dataflow(a, net->num_sms, st));
+    }
     CU(cudaMemcpyAsync(net->h_status, net->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return TXH_OK;
 }
@@ -204,12 +232,13 @@ void txh_destroy(txh_net* net)
 {
     if (!net) return;
     if (net->dev_ready) {
-        cudaFree(net->d_tasks); cudaFree(net->d_deps); cudaFree(net->d_hdr); cudaFree(net->d_inw);
+        cudaFree(net->d_tasks); cudaFree(net->d_notify); cudaFree(net->d_init_ready); cudaFree(net->d_hdr); cudaFree(net->d_inw);
         cudaFree(net->d_up_off); cudaFree(net->d_up_pos); cudaFree(net->d_lvl_pos);
         cudaFree(net->d_reach_of_pos); cudaFree(net->d_pos_of_reach); cudaFree(net->d_outlet);
-        cudaFree(net->d_coef); cudaFree(net->d_qtmp); cudaFree(net->d_ticket); cudaFree(net->d_rec_slot);
+        cudaFree(net->d_coef); cudaFree(net->d_qtmp); cudaFree(net->d_qctl); cudaFree(net->d_rec_slot);
         cudaFree(net->d_unit_step);
-        if (net->d_done) cudaFree(net->d_done);
+        if (net->d_pending) cudaFree(net->d_pending);
+        if (net->d_queue) cudaFree(net->d_queue);
         if (net->d_steps) cudaFree(net->d_steps);
         if (net->d_tmp_idx) cudaFree(net->d_tmp_idx);
         if (net->h_status) cudaFreeHost(net->h_status);
@@ -263,18 +292,18 @@ int txh_get_schedule_info(const txh_net* net, int64_t info[10])
     if (!net || !info) return fail(TXH_E_INVALID, "null argument");
     const Schedule& s = net->sched;
     info[0] = (int64_t)s.tasks.size(); info[1] = s.n_spine; info[2] = s.n_pocket;
-    info[3] = (int64_t)s.inw.size(); info[4] = (int64_t)s.deps.size(); info[5] = s.slots_used;
+    info[3] = (int64_t)s.inw.size(); info[4] = (int64_t)s.notify.size(); info[5] = s.slots_used;
     info[6] = s.row_fallbacks; info[7] = s.cp_tasks; info[8] = s.cp_cost; info[9] = net->topo.nlevels;
     return TXH_OK;
 }
-int txh_get_schedule(const txh_net* net, int64_t* pos_of_reach, int32_t* task_desc, int32_t* deps,
+int txh_get_schedule(const txh_net* net, int64_t* pos_of_reach, int32_t* task_desc, int32_t* notify,
                      uint32_t* hdr, uint32_t* inw)
 {
     if (!net) return fail(TXH_E_INVALID, "null argument");
     const Schedule& s = net->sched;
     if (pos_of_reach) widen(s.pos_of_reach, pos_of_reach);
     if (task_desc) std::memcpy(task_desc, s.tasks.data(), s.tasks.size() * sizeof(TaskDesc));
-    if (deps) std::memcpy(deps, s.deps.data(), s.deps.size() * sizeof(int32_t));
+    if (notify) std::memcpy(notify, s.notify.data(), s.notify.size() * sizeof(int32_t));
     if (hdr) std::memcpy(hdr, s.hdr.data(), s.hdr.size() * sizeof(uint32_t));
     if (inw) std::memcpy(inw, s.inw.data(), s.inw.size() * sizeof(uint32_t));
     return TXH_OK;

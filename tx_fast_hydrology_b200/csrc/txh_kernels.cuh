@@ -19,7 +19,7 @@ constexpr int kMemberBlock = 64;          // members per warp: one double2 per l
 
 struct RouteArgs {
     const TaskDesc* tasks;
-    const int32_t* deps;
+    const int32_t* notify;
     const uint32_t* hdr;
     const uint32_t* inw;
     const double* coef;                   // [n][4] = alpha, beta, chi, gamma (schedule order)
@@ -30,13 +30,27 @@ struct RouteArgs {
     const double* Wmul;                   // [R][wm_ld] member multipliers, or nullptr
     const int32_t* rec_slot;              // [n] recording slot of each position or -1; nullptr = off
     double* rec_out;                      // [nrec_steps][rec_count][M]
-    int32_t* done;                        // [n_tasks * n_mblocks] steps completed in this launch
-    unsigned long long* ticket;
+    // dataflow runtime state (one entry per (task, member block) pair)
+    int32_t* pending;                     // outstanding dependencies of the pair's next step
+    int32_t* stepno;                      // steps the pair has completed
+    uint32_t* queue;                      // ready queue: pair index + 1, 0 = not yet pushed
+    unsigned long long* q_head;           // pop cursor; q_head[1] = push cursor
     int32_t* status;
     unsigned long long watchdog_ns;
+    long long total;                      // pairs * nsteps = entries ever pushed
     int64_t n;
     int32_t n_tasks, n_mblocks, nsteps, slots;
     int32_t ld, M, wm_ld, rec_every, rec_count;
+};
+
+struct InitArgs {
+    const TaskDesc* tasks;
+    const int32_t* init_ready;
+    int32_t* pending;
+    int32_t* stepno;
+    uint32_t* queue;
+    unsigned long long* q_head;
+    int32_t n_tasks, n_mblocks, n_init;
 };
 
 struct LevelArgs {
@@ -51,6 +65,7 @@ struct LevelArgs {
     int32_t ld, M;
 };
 
+cudaError_t launch_dataflow_init(const InitArgs& a, cudaStream_t st);
 cudaError_t launch_route_dataflow(const RouteArgs& a, int num_sms, cudaStream_t st);
 cudaError_t launch_route_level(const LevelArgs& a, cudaStream_t st);
 cudaError_t launch_init_inflows(const int32_t* up_off, const int32_t* up_pos, const uint8_t* is_outlet,

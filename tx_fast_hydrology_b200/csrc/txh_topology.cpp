@@ -119,12 +119,18 @@ bool Topology::build(int64_t n_, const int64_t* e, std::string& err)
 // ---------------------------------------------------------------------------
 namespace {
 
-struct Emit {
-    std::vector<int32_t> reach;       // reaches in processing order, all tasks concatenated
-    std::vector<uint32_t> hdr;        // parallel to `reach`
-    std::vector<uint32_t> inw;        // ROW entries hold REACH ids until positions are known
-    std::vector<int32_t> in_off;      // per emitted reach
+struct Unit {
+    int32_t grp;                      // row group (contiguous rows in the final layout)
+    int32_t kind;
+    std::vector<uint32_t> ins;        // input words; ROW entries hold REACH ids until positions are known
+    std::vector<int32_t> A, B;        // same-step / previous-step dependencies (unit ids)
 };
+
+void sort_unique(std::vector<int32_t>& v)
+{
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+}
 
 }  // namespace
 
@@ -132,35 +138,28 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
 {
     prm = p;
     const int64_t n = t.n;
-    if (p.spine_cap < 1 || p.pocket_cap < 1 || p.pocket_cap > 4096 || p.long_path_min < 2 ||
-        p.max_slots < 0 || p.max_slots > 30) {
+    if (p.spine_cap < 1 || p.spine_cap > 4096 || p.pocket_cap < 1 || p.pocket_cap > 4096 ||
+        p.long_path_min < 2 || p.max_slots < 0 || p.max_slots > 30) {
         err = "bad schedule parameters"; return false;
     }
     std::vector<uint8_t> is_long(n);
     for (int64_t j = 0; j < n; ++j) is_long[j] = t.path_len[t.path_id[j]] >= p.long_path_min;
 
-    // ---- units (tasks before ordering): members in processing order --------------------
-    std::vector<int32_t> unit(n, -1);
-    std::vector<int32_t> u_begin, u_len;          // into Emit arrays
-    std::vector<uint8_t> u_kind;
-    Emit em;
-    em.reach.reserve(n); em.hdr.reserve(n); em.in_off.reserve(n + 1);
+    // row groups: reaches in processing order + their header words
+    std::vector<int32_t> g_begin, g_len, rows;
+    std::vector<uint32_t> rhdr;
+    rows.reserve(n); rhdr.reserve(n);
+    std::vector<Unit> units;
+    std::vector<int32_t> final_unit(n, -1);   // unit that writes the final value of the reach's rows
+    std::vector<int32_t> pre_unit(n, -1);     // spine reaches: the PRE unit of their segment
 
-    auto push_reach = [&](int32_t j, uint32_t h, const std::vector<uint32_t>& ins) {
-        em.reach.push_back(j);
-        em.in_off.push_back((int32_t)em.inw.size());
-        em.hdr.push_back(h | ((uint32_t)ins.size() << 6));
-        em.inw.insert(em.inw.end(), ins.begin(), ins.end());
-    };
-
-    // ---- spines: long paths cut into pure-chain segments -------------------------------
+    // ---- spines: long paths cut into pure-chain segments, each a PRE and a CHAIN task ------
     {
         const int32_t npaths = (int32_t)t.path_len.size();
         std::vector<int32_t> poff(npaths + 1, 0);
         for (int32_t q = 0; q < npaths; ++q) poff[q + 1] = poff[q] + t.path_len[q];
         std::vector<int32_t> member(n);
         for (int64_t j = 0; j < n; ++j) member[poff[t.path_id[j]] + t.path_pos[j]] = (int32_t)j;
-        std::vector<uint32_t> ins;
         for (int32_t q = 0; q < npaths; ++q) {
             const int32_t len = t.path_len[q];
             if (len < p.long_path_min) continue;
@@ -168,23 +167,34 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
             const int32_t seglen = (len + nseg - 1) / nseg;
             for (int32_t s0 = 0; s0 < len; s0 += seglen) {
                 const int32_t s1 = std::min(len, s0 + seglen);
-                const int32_t u = (int32_t)u_begin.size();
-                u_begin.push_back((int32_t)em.reach.size()); u_len.push_back(s1 - s0); u_kind.push_back(0);
+                const int32_t g = (int32_t)g_begin.size();
+                g_begin.push_back((int32_t)rows.size()); g_len.push_back(s1 - s0);
+                const int32_t up = (int32_t)units.size();
+                units.push_back(Unit{g, TASK_PRE, {}, {}, {}});
+                units.push_back(Unit{g, TASK_CHAIN, {}, {}, {}});
                 for (int32_t k = s0; k < s1; ++k) {
                     const int32_t j = member[poff[q] + k];
-                    unit[j] = u;
-                    ins.clear();
-                    uint32_t h = 0;
+                    final_unit[j] = up + 1; pre_unit[j] = up;
+                    uint32_t h = 0, n_early = 0, n_late = 0;
                     const int32_t m = t.main_child[j];
-                    if (m >= 0) { if (k > s0) h |= HDR_ACC; else ins.push_back(INW_ROW | (uint32_t)m); }
-                    for (int32_t c = t.child_off[j]; c < t.child_off[j + 1]; ++c)
-                        if (t.child[c] != m) ins.push_back(INW_ROW | (uint32_t)t.child[c]);
-                    push_reach(j, h, ins);
+                    if (m >= 0) {
+                        if (k > s0) h |= HDR_ACC;
+                        else { units[up + 1].ins.push_back(INW_ROW | (uint32_t)m); ++n_late; }
+                    }
+                    for (int32_t c = t.child_off[j]; c < t.child_off[j + 1]; ++c) {
+                        const int32_t ch = t.child[c];
+                        if (ch == m) continue;
+                        if (is_long[ch]) { units[up + 1].ins.push_back(INW_ROW | (uint32_t)ch); ++n_late; }
+                        else { units[up].ins.push_back(INW_ROW | (uint32_t)ch); ++n_early; }
+                    }
+                    if (n_early >= (1u << 13) || n_late >= (1u << 13)) { err = "confluence too wide"; return false; }
+                    rows.push_back(j);
+                    rhdr.push_back(h | (n_early << 6) | (n_late << 19));
                 }
             }
         }
     }
-    n_spine = (int32_t)u_begin.size();
+    n_spine = (int32_t)g_begin.size();
 
     // ---- pockets: side subtrees made of short paths only -------------------------------
     // split oversized pockets bottom-up; `closed[j]` marks roots of mini-trees
@@ -231,7 +241,7 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
         if (is_long[j] || !closed[j]) continue;
         const int32_t d = t.end[j];
         if (d == j) grpB.push_back({(int64_t)j, (int32_t)j});
-        else if (is_long[d]) grpA.push_back({((int64_t)unit[d] << 32) | (uint32_t)t.path_pos[d], (int32_t)j});
+        else if (is_long[d]) grpA.push_back({((int64_t)pre_unit[d] << 32) | (uint32_t)t.path_pos[d], (int32_t)j});
         else grpC.push_back({(int64_t)j, (int32_t)j});
     }
     auto by_key = [](const Mini& a, const Mini& b) { return a.key != b.key ? a.key < b.key : a.root < b.root; };
@@ -256,24 +266,26 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
                     const int32_t s = free_slots.back(); free_slots.pop_back();
                     slot_of[c] = s;
                     slots_hi = std::max(slots_hi, s + 1);
-                    em.hdr.back() |= (uint32_t)(s + 1) << 1;   // c is the reach just emitted
+                    rhdr.back() |= (uint32_t)(s + 1) << 1;     // c is the reach just emitted
                 } else {
                     row_fallbacks += 1;
                 }
             }
         }
-        std::vector<uint32_t> ins;
-        uint32_t h = 0;
+        Unit& u = units.back();
+        uint32_t h = 0, nin = 0;
         if (!kids.empty()) h |= HDR_ACC;                       // last in-tree child was emitted just before v
         for (size_t i = 0; i + 1 < kids.size(); ++i) {
             const int32_t c = kids[i].second;
-            if (slot_of[c] >= 0) { ins.push_back((uint32_t)slot_of[c]); free_slots.push_back(slot_of[c]); slot_of[c] = -1; }
-            else ins.push_back(INW_ROW | (uint32_t)c);
+            if (slot_of[c] >= 0) { u.ins.push_back((uint32_t)slot_of[c]); free_slots.push_back(slot_of[c]); slot_of[c] = -1; }
+            else u.ins.push_back(INW_ROW | (uint32_t)c);
+            ++nin;
         }
         for (int32_t c = t.child_off[v]; c < t.child_off[v + 1]; ++c)
-            if (closed[t.child[c]]) ins.push_back(INW_ROW | (uint32_t)t.child[c]);
-        unit[v] = (int32_t)u_begin.size() - 1;
-        push_reach(v, h, ins);
+            if (closed[t.child[c]]) { u.ins.push_back(INW_ROW | (uint32_t)t.child[c]); ++nin; }
+        final_unit[v] = (int32_t)units.size() - 1;
+        rows.push_back(v);
+        rhdr.push_back(h | (nin << 6));
     };
     auto reset_slots = [&]() {
         free_slots.clear();
@@ -287,46 +299,59 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
             const bool fits = bundle && cur >= 0 && cur_size + sz <= p.pocket_cap &&
                               (!same_high_key || hi == cur_hi);
             if (!fits) {
-                cur = (int32_t)u_begin.size();
-                u_begin.push_back((int32_t)em.reach.size()); u_len.push_back(0); u_kind.push_back(1);
+                cur = (int32_t)g_begin.size();
+                g_begin.push_back((int32_t)rows.size()); g_len.push_back(0);
+                units.push_back(Unit{cur, TASK_POCKET, {}, {}, {}});
                 cur_size = 0; cur_hi = hi;
             }
             reset_slots();
             emit_tree(m.root);
             cur_size += sz;
-            u_len[cur] = (int32_t)em.reach.size() - u_begin[cur];
+            g_len[cur] = (int32_t)rows.size() - g_begin[cur];
         }
     };
     pack(grpC, false, false);
     pack(grpA, true, true);
     pack(grpB, true, false);
-    n_pocket = (int32_t)u_begin.size() - n_spine;
+    n_pocket = (int32_t)g_begin.size() - n_spine;
     slots_used = slots_hi;
-    if ((int64_t)em.reach.size() != n) { err = "internal: schedule does not cover every reach"; return false; }
-    em.in_off.push_back((int32_t)em.inw.size());
+    if ((int64_t)rows.size() != n) { err = "internal: schedule does not cover every reach"; return false; }
 
-    // ---- task DAG -----------------------------------------------------------------------
-    const int32_t nu = (int32_t)u_begin.size();
-    std::vector<std::vector<int32_t>> prod(nu), cons(nu);
+    // ---- dependencies ------------------------------------------------------------------------
+    const int32_t nu = (int32_t)units.size();
     for (int32_t u = 0; u < nu; ++u) {
-        std::vector<int32_t>& pr = prod[u];
-        for (int32_t e = u_begin[u]; e < u_begin[u] + u_len[u]; ++e)
-            for (int32_t w = em.in_off[e]; w < em.in_off[e + 1]; ++w)
-                if (em.inw[w] & INW_ROW) {
-                    const int32_t pu = unit[em.inw[w] & ~INW_ROW];
-                    if (pu != u) pr.push_back(pu);
-                }
-        std::sort(pr.begin(), pr.end());
-        pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
-        for (int32_t pu : pr) cons[pu].push_back(u);
+        Unit& U = units[u];
+        U.B.push_back(u);                                                  // self: one step in flight per task
+        if (U.kind == TASK_CHAIN) U.A.push_back(u - 1);                    // its own PRE (emitted just before)
+        if (U.kind == TASK_PRE) U.B.push_back(u + 1);                      // rows are rewritten: own CHAIN must be done
+        for (uint32_t w : U.ins) {
+            if (!(w & INW_ROW)) continue;
+            const int32_t c = (int32_t)(w & ~INW_ROW);
+            const int32_t prod = final_unit[c];
+            if (units[prod].grp == U.grp) continue;                        // a row of this task itself (slot fallback)
+            U.A.push_back(prod);
+            // U reads row c at step s: the unit that next overwrites it must wait for U
+            const int32_t writer = pre_unit[c] >= 0 ? pre_unit[c] : prod;
+            units[writer].B.push_back(u);
+        }
     }
-    // plain Kahn for a first topological order, then critical-path-to-sink costs
+    for (Unit& U : units) { sort_unique(U.A); sort_unique(U.B); }
+    std::vector<std::vector<int32_t>> same(nu), next(nu);
+    for (int32_t u = 0; u < nu; ++u) {
+        for (int32_t a : units[u].A) same[a].push_back(u);
+        for (int32_t b : units[u].B) next[b].push_back(u);
+    }
+    // topological order over the A-edges, longest remaining critical path first
+    auto cost = [&](int32_t u) -> int64_t {
+        const int32_t len = g_len[units[u].grp];
+        return units[u].kind == TASK_CHAIN ? 12 + len / 2 : 24 + len;
+    };
     std::vector<int32_t> order0; order0.reserve(nu);
     {
         std::vector<int32_t> pend(nu);
-        for (int32_t u = 0; u < nu; ++u) { pend[u] = (int32_t)prod[u].size(); if (!pend[u]) order0.push_back(u); }
+        for (int32_t u = 0; u < nu; ++u) { pend[u] = (int32_t)units[u].A.size(); if (!pend[u]) order0.push_back(u); }
         for (size_t k = 0; k < order0.size(); ++k)
-            for (int32_t c : cons[order0[k]]) if (--pend[c] == 0) order0.push_back(c);
+            for (int32_t c : same[order0[k]]) if (--pend[c] == 0) order0.push_back(c);
         if ((int32_t)order0.size() != nu) { err = "internal: task graph has a cycle"; return false; }
     }
     std::vector<int64_t> cp(nu, 0);
@@ -334,23 +359,22 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
     for (int32_t k = nu - 1; k >= 0; --k) {
         const int32_t u = order0[k];
         int64_t best = 0; int32_t bt = 0;
-        for (int32_t c : cons[u]) { if (cp[c] > best) best = cp[c]; if (cpt[c] > bt) bt = cpt[c]; }
-        cp[u] = best + 24 + u_len[u];
+        for (int32_t c : same[u]) { if (cp[c] > best) best = cp[c]; if (cpt[c] > bt) bt = cpt[c]; }
+        cp[u] = best + cost(u);
         cpt[u] = bt + 1;
     }
     cp_cost = 0; cp_tasks = 0;
     for (int32_t u = 0; u < nu; ++u) { cp_cost = std::max(cp_cost, cp[u]); cp_tasks = std::max(cp_tasks, cpt[u]); }
-    // claim order: topological, longest remaining critical path first
     std::vector<int32_t> order; order.reserve(nu);
     {
         auto cmp = [&](int32_t a, int32_t b) { return cp[a] != cp[b] ? cp[a] < cp[b] : a > b; };
         std::priority_queue<int32_t, std::vector<int32_t>, decltype(cmp)> pq(cmp);
         std::vector<int32_t> pend(nu);
-        for (int32_t u = 0; u < nu; ++u) { pend[u] = (int32_t)prod[u].size(); if (!pend[u]) pq.push(u); }
+        for (int32_t u = 0; u < nu; ++u) { pend[u] = (int32_t)units[u].A.size(); if (!pend[u]) pq.push(u); }
         while (!pq.empty()) {
             const int32_t u = pq.top(); pq.pop();
             order.push_back(u);
-            for (int32_t c : cons[u]) if (--pend[c] == 0) pq.push(c);
+            for (int32_t c : same[u]) if (--pend[c] == 0) pq.push(c);
         }
     }
     std::vector<int32_t> rank(nu);
@@ -358,42 +382,41 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
 
     // ---- positions and device descriptors -------------------------------------------------
     pos_of_reach.assign(n, -1); reach_of_pos.assign(n, -1);
-    task_of_pos.assign(n, -1);
-    tasks.assign(nu, TaskDesc{});
-    task_kind.assign(nu, 0);
     hdr.assign(n, 0);
-    inw.clear(); inw.reserve(em.inw.size());
-    deps.clear();
     {
+        const int32_t ng = (int32_t)g_begin.size();
+        std::vector<int32_t> gpos(ng, -1);
         int32_t pos = 0;
         for (int32_t k = 0; k < nu; ++k) {
-            const int32_t u = order[k];
-            tasks[k].begin = pos; tasks[k].len = u_len[u];
-            task_kind[k] = u_kind[u];
-            for (int32_t e = u_begin[u]; e < u_begin[u] + u_len[u]; ++e, ++pos) {
-                pos_of_reach[em.reach[e]] = pos; reach_of_pos[pos] = em.reach[e]; task_of_pos[pos] = k;
+            const int32_t g = units[order[k]].grp;
+            if (gpos[g] >= 0) continue;
+            gpos[g] = pos;
+            for (int32_t e = g_begin[g]; e < g_begin[g] + g_len[g]; ++e, ++pos) {
+                pos_of_reach[rows[e]] = pos; reach_of_pos[pos] = rows[e]; hdr[pos] = rhdr[e];
             }
         }
+        tasks.assign(nu, TaskDesc{});
+        inw.clear(); notify.clear(); init_ready.clear();
         for (int32_t k = 0; k < nu; ++k) {
-            const int32_t u = order[k];
-            tasks[k].in_off = (int32_t)inw.size();
-            int32_t pos = tasks[k].begin;
-            for (int32_t e = u_begin[u]; e < u_begin[u] + u_len[u]; ++e, ++pos) {
-                hdr[pos] = em.hdr[e];
-                for (int32_t w = em.in_off[e]; w < em.in_off[e + 1]; ++w) {
-                    uint32_t x = em.inw[w];
-                    if (x & INW_ROW) x = INW_ROW | (uint32_t)pos_of_reach[x & ~INW_ROW];
-                    inw.push_back(x);
-                }
+            const Unit& U = units[order[k]];
+            TaskDesc& td = tasks[k];
+            td.begin = gpos[U.grp]; td.len = g_len[U.grp]; td.kind = U.kind;
+            td.in_off = (int32_t)inw.size();
+            for (uint32_t x : U.ins) {
+                if (x & INW_ROW) x = INW_ROW | (uint32_t)pos_of_reach[x & ~INW_ROW];
+                inw.push_back(x);
             }
-            tasks[k].dep_off = (int32_t)deps.size();
-            tasks[k].n_raw = (int32_t)prod[u].size();
-            tasks[k].n_war = (int32_t)cons[u].size();
-            for (int32_t pu : prod[u]) {
-                if (rank[pu] >= k) { err = "internal: producer ordered after consumer"; return false; }
-                deps.push_back(rank[pu]);
+            td.nfy_off = (int32_t)notify.size();
+            td.n_same = (int32_t)same[order[k]].size();
+            td.n_next = (int32_t)next[order[k]].size();
+            for (int32_t c : same[order[k]]) {
+                if (rank[c] <= k) { err = "internal: producer ordered after consumer"; return false; }
+                notify.push_back(rank[c]);
             }
-            for (int32_t cu : cons[u]) deps.push_back(rank[cu]);
+            for (int32_t c : next[order[k]]) notify.push_back(rank[c]);
+            td.need0 = (int32_t)U.A.size();
+            td.need = (int32_t)(U.A.size() + U.B.size());
+            if (td.need0 == 0) init_ready.push_back(k);
         }
     }
 

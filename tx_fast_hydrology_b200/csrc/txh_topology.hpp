@@ -39,44 +39,55 @@ struct Topology {
 
 struct SchedParams {
     int long_path_min = 16;   // paths at least this long become spines
-    int spine_cap = 32;       // reaches per spine task (pure chain segments)
+    int spine_cap = 32;       // reaches per spine segment (pure chains: a PRE and a CHAIN task each)
     int pocket_cap = 48;      // reaches per pocket task (bundled side subtrees)
     int max_slots = 12;       // shared-memory scratch rows per warp
 };
 
 // Per-reach header word consumed by the routing kernel.
-//   bit 0      : inflow starts from the running accumulator (previous reach's outflow)
-//   bits 1..5  : (scratch slot + 1) the outflow is also parked in, 0 = none
-//   bits 6..31 : number of input words that follow in `inw`
+//   pocket rows : bit 0      inflow starts from the running accumulator (previous reach's outflow)
+//                 bits 1..5  (scratch slot + 1) the outflow is also parked in, 0 = none
+//                 bits 6..31 number of input words that follow in the task's input stream
+//   spine rows  : bit 0      inflow includes the previous reach of the segment
+//                 bits 6..18 number of EARLY inputs (rows of pocket roots; PRE task stream)
+//                 bits 19..31 number of LATE inputs (last rows of other spine segments; CHAIN stream)
 // Input word: bit 31 set -> state row (position) to gather; else scratch slot id.
 constexpr uint32_t HDR_ACC = 1u;
 constexpr uint32_t INW_ROW = 0x80000000u;
+constexpr int TASK_POCKET = 0, TASK_PRE = 1, TASK_CHAIN = 2;
 
+// Dataflow task.  A task T may run step s once (a) every task in A(T) has finished step s and
+// (b) every task in B(T) (T itself included) has finished step s-1.  Completion of U at step s
+// decrements the pending counter of every T with U in A(T) ("same" targets, for T's step s) and
+// of every T with U in B(T) ("next" targets, for T's step s+1).
 struct TaskDesc {
     int32_t begin;     // first position (rows [begin, begin+len) are contiguous)
     int32_t len;
     int32_t in_off;    // offset of the task's first input word
-    int32_t dep_off;   // offset into `deps`
-    int32_t n_raw;     // producers: tasks whose rows this task gathers (same step)
-    int32_t n_war;     // consumers: tasks that gather this task's rows (previous step)
+    int32_t nfy_off;   // offset into `notify`: n_same targets, then n_next targets
+    int32_t n_same;
+    int32_t n_next;
+    int32_t need0;     // |A(T)|           pending count before step 0
+    int32_t need;      // |A(T)| + |B(T)|  re-arm value after each completed step
+    int32_t kind;      // TASK_POCKET / TASK_PRE / TASK_CHAIN
+    int32_t pad_[3];
 };
 
 struct Schedule {
     SchedParams prm;
     std::vector<int32_t> pos_of_reach, reach_of_pos;
-    std::vector<TaskDesc> tasks;            // in claim (topological, critical-path-first) order
-    std::vector<int32_t> deps;
+    std::vector<TaskDesc> tasks;            // in a topological (critical-path-first) order of the A-edges
+    std::vector<int32_t> notify;
+    std::vector<int32_t> init_ready;        // tasks with need0 == 0
     std::vector<uint32_t> hdr;              // per position
     std::vector<uint32_t> inw;
-    std::vector<int32_t> task_of_pos;
-    std::vector<uint8_t> task_kind;         // 0 spine, 1 pocket
     // position-space CSR of upstream rows (level kernel, init_inflows, apply_gain)
     std::vector<int32_t> up_off, up_pos;
     std::vector<int32_t> lvl_pos, lvl_off;  // positions sorted by level
     std::vector<uint8_t> is_outlet_pos;
     // statistics
     int32_t n_spine = 0, n_pocket = 0, slots_used = 0, row_fallbacks = 0;
-    int32_t cp_tasks = 0;                   // tasks on the longest dependent chain
+    int32_t cp_tasks = 0;                   // tasks on the longest same-step dependent chain
     int64_t cp_cost = 0;
 
     bool build(const Topology& t, const SchedParams& p, std::string& err);

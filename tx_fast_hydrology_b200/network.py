@@ -129,21 +129,21 @@ class RiverNetwork:
     def schedule_info(self):
         info = np.zeros(10, dtype=np.int64)
         L.check(self._lib.txh_get_schedule_info(self.handle, L.ptr_i64(info)))
-        keys = ["n_tasks", "n_spine", "n_pocket", "n_input_words", "n_deps", "slots_used",
+        keys = ["n_tasks", "n_spine", "n_pocket", "n_input_words", "n_notify", "slots_used",
                 "row_fallbacks", "cp_tasks", "cp_cost", "nlevels"]
         return dict(zip(keys, (int(x) for x in info)))
 
     def schedule(self):
         info = self.schedule_info()
         pos = np.empty(self.n, dtype=np.int64)
-        tasks = np.empty((info["n_tasks"], 6), dtype=np.int32)
-        deps = np.empty(max(1, info["n_deps"]), dtype=np.int32)
+        tasks = np.empty((info["n_tasks"], 12), dtype=np.int32)
+        deps = np.empty(max(1, info["n_notify"]), dtype=np.int32)
         hdr = np.empty(self.n, dtype=np.uint32)
         inw = np.empty(max(1, info["n_input_words"]), dtype=np.uint32)
         L.check(self._lib.txh_get_schedule(
             self.handle, L.ptr_i64(pos), tasks.ctypes.data_as(L.p_i32), deps.ctypes.data_as(L.p_i32),
             hdr.ctypes.data_as(L.p_u32), inw.ctypes.data_as(L.p_u32)))
-        return {"pos_of_reach": pos, "tasks": tasks, "deps": deps[:info["n_deps"]], "hdr": hdr,
+        return {"pos_of_reach": pos, "tasks": tasks, "notify": deps[:info["n_notify"]], "hdr": hdr,
                 "inw": inw[:info["n_input_words"]]}
 
     # ---- coefficients ---------------------------------------------------------------------
