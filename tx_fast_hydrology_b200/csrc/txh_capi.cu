@@ -60,8 +60,8 @@ struct txh_net {
     uint8_t* d_outlet = nullptr;
     double* d_coef = nullptr;
     double* d_qtmp = nullptr;           // [n] schedule-order scratch for txh_route_step
-    int32_t* d_pending = nullptr; size_t pairs_cap = 0;    // [pairs] pending, then [pairs] stepno
-    uint32_t* d_queue = nullptr; size_t queue_cap = 0;
+    int32_t* d_pending = nullptr; size_t pairs_cap = 0;
+    unsigned long long* d_queue = nullptr; size_t queue_cap = 0;
     unsigned long long* d_qctl = nullptr;     // [0] head, [1] tail, [2] completed, [4] status word
     int32_t* d_status = nullptr;
     StepInterp* d_steps = nullptr; size_t steps_cap = 0;
@@ -156,26 +156,26 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
     if (pairs >= (size_t(1) << 31)) return fail(TXH_E_INVALID, "too many (task, member block) pairs");
     if (pairs > net->pairs_cap) {
         if (net->d_pending) CU(cudaFree(net->d_pending));
-        CU(cudaMalloc((void**)&net->d_pending, 2 * pairs * sizeof(int32_t)));
+        CU(cudaMalloc((void**)&net->d_pending, pairs * sizeof(int32_t)));
         net->pairs_cap = pairs;
     }
     // the ready queue never wraps: one slot per (pair, step); long runs go out in several launches
-    const int64_t max_entries = int64_t(1) << 26;
+    const int64_t max_entries = int64_t(1) << 25;
     int64_t steps_per_launch = std::max<int64_t>(1, std::min<int64_t>(nsteps, max_entries / (int64_t)pairs));
     if (rec_slot && rec_every > 1 && steps_per_launch < nsteps)
         steps_per_launch = std::max<int64_t>(rec_every, steps_per_launch / rec_every * rec_every);
     const size_t qneed = pairs * (size_t)steps_per_launch;
     if (qneed > net->queue_cap) {
         if (net->d_queue) CU(cudaFree(net->d_queue));
-        CU(cudaMalloc((void**)&net->d_queue, qneed * sizeof(uint32_t)));
+        CU(cudaMalloc((void**)&net->d_queue, qneed * sizeof(unsigned long long)));
         net->queue_cap = qneed;
     }
     for (int64_t s0 = 0; s0 < nsteps; s0 += steps_per_launch) {
         const int64_t ns = std::min<int64_t>(steps_per_launch, nsteps - s0);
-        CU(cudaMemsetAsync(net->d_queue, 0, pairs * (size_t)ns * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(net->d_queue, 0, pairs * (size_t)ns * sizeof(unsigned long long), st));
         InitArgs ia{};
         ia.tasks = net->d_tasks; ia.init_ready = net->d_init_ready; ia.pending = net->d_pending;
-        ia.stepno = net->d_pending + net->pairs_cap; ia.queue = net->d_queue; ia.q_head = net->d_qctl;
+        ia.queue = net->d_queue; ia.q_head = net->d_qctl;
         ia.n_tasks = (int32_t)s.tasks.size(); ia.n_mblocks = nmb; ia.n_init = (int32_t)s.init_ready.size();
         CU(launch_dataflow_init(ia, st));
         RouteArgs a{};
@@ -187,13 +187,45 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
             if (s0 % rec_every != 0) return fail(TXH_E_INVALID, "internal: launch split not aligned with rec_every");
             a.rec_out = rec_out + (size_t)(s0 / rec_every) * rec_count * M;
         }
-        a.pending = ia.pending; a.stepno = ia.stepno; a.queue = net->d_queue; a.q_head = net->d_qctl;
+        a.pending = ia.pending; a.queue = net->d_queue; a.q_head = net->d_qctl;
         a.status = net->d_status; a.watchdog_ns = net->watchdog_ns;
         a.total = (long long)pairs * ns;
         a.n = net->topo.n; a.n_tasks = ia.n_tasks; a.n_mblocks = nmb; a.nsteps = (int32_t)ns;
         a.slots = std::max(1, s.slots_used); a.ld = ld; a.M = (int32_t)M;
         a.wm_ld = wm_ld; a.rec_every = rec_every; a.rec_count = rec_count;
+        // per-warp staging area: [scratch slots][coef][f0][f1][hdr][inw], every part 16-byte aligned
+        auto up16 = [](int x) { return (x + 15) & ~15; };
+        const int L = std::max(1, s.max_len);
+        a.max_words = 256;
+        a.off_coef = a.slots * 32 * (int)sizeof(double2);
+        a.off_f0 = a.off_coef + 4 * L * (int)sizeof(double);
+        a.off_f1 = a.off_f0 + up16(L * (int)sizeof(double));
+        a.off_hdr = a.off_f1 + up16(L * (int)sizeof(double));
+        a.off_inw = a.off_hdr + up16(L * (int)sizeof(uint32_t));
+        a.smem_per_warp = a.off_inw + up16(a.max_words * (int)sizeof(uint32_t));
+        a.trace = nullptr;
+        { const char* e = getenv("TXH_ROWOP"); a.weak_rows = e ? atoi(e) : 1; }
+        const char* trace_file = getenv("TXH_TRACE_FILE");
+        unsigned long long* d_trace = nullptr;
+        if (trace_file && *trace_file) {
+            CU(cudaMalloc((void**)&d_trace, (size_t)a.total * 4 * sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(d_trace, 0, (size_t)a.total * 4 * sizeof(unsigned long long), st));
+            a.trace = d_trace;
+        }
         CU(launch_route_dataflow(a, net->num_sms, st));
+        if (d_trace) {
+            // development aid: dump the per-task timeline of this launch (synchronous)
+            std::vector<unsigned long long> h((size_t)a.total * 4);
+            CU(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            CU(cudaFree(d_trace));
+            if (FILE* fp = fopen(trace_file, "wb")) {
+                const long long hd[4] = {(long long)pairs, (long long)ns, (long long)s.tasks.size(), (long long)nmb};
+                fwrite(hd, sizeof(hd), 1, fp);
+                fwrite(h.data(), sizeof(unsigned long long), h.size(), fp);
+                fclose(fp);
+            }
+        }
     }
     CU(cudaMemcpyAsync(net->h_status, net->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return TXH_OK;

@@ -14,7 +14,7 @@ struct StepInterp {
     double w0, w1;
 };
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 4;
 constexpr int kMemberBlock = 64;          // members per warp: one double2 per lane
 
 struct RouteArgs {
@@ -32,8 +32,7 @@ struct RouteArgs {
     double* rec_out;                      // [nrec_steps][rec_count][M]
     // dataflow runtime state (one entry per (task, member block) pair)
     int32_t* pending;                     // outstanding dependencies of the pair's next step
-    int32_t* stepno;                      // steps the pair has completed
-    uint32_t* queue;                      // ready queue: pair index + 1, 0 = not yet pushed
+    unsigned long long* queue;            // ready queue: (step << 32) | (pair + 1), 0 = not yet pushed
     unsigned long long* q_head;           // pop cursor; q_head[1] = push cursor
     int32_t* status;
     unsigned long long watchdog_ns;
@@ -41,14 +40,17 @@ struct RouteArgs {
     int64_t n;
     int32_t n_tasks, n_mblocks, nsteps, slots;
     int32_t ld, M, wm_ld, rec_every, rec_count;
+    // per-warp shared-memory staging area (bytes): [scratch slots][coef][f0][f1][hdr][inw]
+    int32_t smem_per_warp, off_coef, off_f0, off_f1, off_hdr, off_inw, max_words;
+    unsigned long long* trace;            // optional [total][4] timeline, nullptr = off
+    int32_t weak_rows;                    // row loads/stores: 1 = weak (L1::no_allocate), 0 = .cg
 };
 
 struct InitArgs {
     const TaskDesc* tasks;
     const int32_t* init_ready;
     int32_t* pending;
-    int32_t* stepno;
-    uint32_t* queue;
+    unsigned long long* queue;
     unsigned long long* q_head;
     int32_t n_tasks, n_mblocks, n_init;
 };

@@ -37,23 +37,90 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 // state rows are produced and consumed by different SMs inside one launch: bypass L1
 __device__ __forceinline__ double2 ld_row(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ void st_row(double* p, double2 v) { __stcg(reinterpret_cast<double2*>(p), v); }
+// Weak variants for the dataflow kernel: every task starts behind an acquire fence (which
+// invalidates L1), its inputs were final before that fence, and rows are never allocated in L1,
+// so plain loads cannot observe stale data -- and, unlike the strong forms, they do not queue
+// behind this warp's own earlier row stores.
+template <bool WEAK>
+__device__ __forceinline__ double2 ldr(const double* p)
+{
+    if (WEAK) {
+        double2 v;
+        asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+        return v;
+    }
+    return __ldcg(reinterpret_cast<const double2*>(p));
+}
+template <bool WEAK>
+__device__ __forceinline__ void str(double* p, double2 v)
+{
+    if (WEAK) asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    else __stcg(reinterpret_cast<double2*>(p), v);
+}
 
 
-constexpr int kPF = 4;      // row prefetch distance (reaches ahead) inside a task
+constexpr int kPF = 4;       // row prefetch distance (reaches ahead) in PRE / POCKET tasks
+constexpr int kPFChain = 8;  // ... and on the latency-critical CHAIN tasks
+
+__device__ __forceinline__ void cp_async4(void* s, const void* g)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* s, const void* g)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* s, const void* g)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ double lds_f64(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(unsigned a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Per-warp shared-memory staging of one task's per-reach metadata: filled once per task by
+// asynchronous global->shared copies (LDGSTS), read back as broadcast LDS in the reach loop,
+// so no reach pays an L2 round trip for its coefficients, header, forcing or input words.
+struct Stage {
+    unsigned coef;           // shared-window byte addresses: [len][4] doubles
+    unsigned f0, f1;         // [len] doubles
+    unsigned hdr;            // [len] words
+    unsigned inw;            // the task's input words, when they fit
+    const uint32_t* inw_g;   // ... else read from global memory
+    __device__ __forceinline__ double al(int i) const { return lds_f64(coef + 32u * i); }
+    __device__ __forceinline__ double be(int i) const { return lds_f64(coef + 32u * i + 8u); }
+    __device__ __forceinline__ double ch(int i) const { return lds_f64(coef + 32u * i + 16u); }
+    __device__ __forceinline__ double ga(int i) const { return lds_f64(coef + 32u * i + 24u); }
+    __device__ __forceinline__ uint32_t h(int i) const { return lds_u32(hdr + 4u * i); }
+    __device__ __forceinline__ uint32_t word(int t) const { return inw_g ? __ldg(inw_g + t) : lds_u32(inw + 4u * t); }
+};
 
 struct StepCtx {
     double w0, w1;
     double2 wm0, wm1;
-    const double* F0;
-    const double* F1;
 };
 
 template <bool HAS_F, bool HAS_W>
-__device__ __forceinline__ double2 forcing_q(const StepCtx& c, int k)
+__device__ __forceinline__ double2 forcing_q(const StepCtx& c, const Stage& st, int i)
 {
     double2 q = make_double2(0.0, 0.0);
     if (HAS_F) {
-        const double f0 = __ldg(c.F0 + k), f1 = __ldg(c.F1 + k);
+        const double f0 = lds_f64(st.f0 + 8u * i), f1 = lds_f64(st.f1 + 8u * i);
         if (HAS_W) { q.x = c.wm0.x * f0 + c.wm1.x * f1; q.y = c.wm0.y * f0 + c.wm1.y * f1; }
         else { q.x = c.w0 * f0 + c.w1 * f1; q.y = q.x; }
     }
@@ -75,50 +142,50 @@ __device__ __forceinline__ void record(const RouteArgs& a, int k, int s, int col
 
 // POCKET: a bundle of side subtrees evaluated depth-first by one warp.  Intermediate
 // outflows travel through the accumulator or this lane's scratch column.
-template <bool HAS_F, bool HAS_W, bool REC>
-__device__ __forceinline__ void run_pocket(const RouteArgs& a, const TaskDesc& td, int s, int col, bool active,
-                                           double2* scratch, const StepCtx& sc)
+template <bool HAS_F, bool HAS_W, bool REC, bool WK>
+__device__ __forceinline__ void run_pocket(const RouteArgs& a, const TaskDesc& td, const Stage& st, int s, int col,
+                                           bool active, double2* scratch, const StepCtx& sc)
 {
-    const int ld = a.ld, begin = td.begin, end = td.begin + td.len;
+    const int ld = a.ld, len = td.len;
     const int ccol = active ? col : 0;
     double* Ob = a.O + ccol;
-    double* Ib = a.I + ccol;
-    const uint32_t* inp = a.inw + td.in_off;
+    double* Or = Ob + (size_t)td.begin * ld;
+    double* Ir = a.I + ccol + (size_t)td.begin * ld;
+    int wi = 0;
     double2 acc = make_double2(0.0, 0.0);
     double2 pi[kPF], po[kPF];
 #pragma unroll
     for (int j = 0; j < kPF; ++j) {
         pi[j] = po[j] = make_double2(0.0, 0.0);
-        if (active && begin + j < end) { pi[j] = ld_row(Ib + (size_t)(begin + j) * ld); po[j] = ld_row(Ob + (size_t)(begin + j) * ld); }
+        if (active && j < len) { pi[j] = ldr<WK>(Ir + (size_t)j * ld); po[j] = ldr<WK>(Or + (size_t)j * ld); }
     }
-    for (int k0 = begin; k0 < end; k0 += kPF) {
+    for (int i0 = 0; i0 < len; i0 += kPF) {
 #pragma unroll
         for (int j = 0; j < kPF; ++j) {
-            const int k = k0 + j;
-            if (k < end) {
+            const int i = i0 + j;
+            if (i < len) {
                 const double2 io = pi[j], oo = po[j];
-                if (active && k + kPF < end) { pi[j] = ld_row(Ib + (size_t)(k + kPF) * ld); po[j] = ld_row(Ob + (size_t)(k + kPF) * ld); }
-                const uint32_t h = __ldg(a.hdr + k);
-                const double2 c01 = __ldg(reinterpret_cast<const double2*>(a.coef + 4 * (size_t)k));
-                const double2 c23 = __ldg(reinterpret_cast<const double2*>(a.coef + 4 * (size_t)k) + 1);
+                if (active && i + kPF < len) { pi[j] = ldr<WK>(Ir + (size_t)(i + kPF) * ld); po[j] = ldr<WK>(Or + (size_t)(i + kPF) * ld); }
+                const uint32_t h = st.h(i);
+                const double al = st.al(i), be = st.be(i), ch = st.ch(i), ga = st.ga(i);
                 double2 inflow = (h & HDR_ACC) ? acc : make_double2(0.0, 0.0);
                 const int nin = (int)(h >> 6);
                 for (int t = 0; t < nin; ++t) {
-                    const uint32_t w = __ldg(inp++);
+                    const uint32_t w = st.word(wi++);
                     double2 v;
-                    if (w & INW_ROW) v = active ? ld_row(Ob + (size_t)(w & ~INW_ROW) * ld) : make_double2(0.0, 0.0);
+                    if (w & INW_ROW) v = active ? ldr<WK>(Ob + (size_t)(w & ~INW_ROW) * ld) : make_double2(0.0, 0.0);
                     else v = scratch[w * 32];
                     inflow.x += v.x; inflow.y += v.y;
                 }
-                const double2 q = forcing_q<HAS_F, HAS_W>(sc, k);
+                const double2 q = forcing_q<HAS_F, HAS_W>(sc, st, i);
                 double2 on;
-                on.x = c01.x * inflow.x + (c01.y * io.x + c23.x * oo.x + c23.y * q.x);
-                on.y = c01.x * inflow.y + (c01.y * io.y + c23.x * oo.y + c23.y * q.y);
-                if (active) { st_row(Ib + (size_t)k * ld, inflow); st_row(Ob + (size_t)k * ld, on); }
+                on.x = al * inflow.x + (be * io.x + ch * oo.x + ga * q.x);
+                on.y = al * inflow.y + (be * io.y + ch * oo.y + ga * q.y);
+                if (active) { str<WK>(Ir + (size_t)i * ld, inflow); str<WK>(Or + (size_t)i * ld, on); }
                 const uint32_t slot = (h >> 1) & 31u;
                 if (slot) scratch[(slot - 1) * 32] = on;
                 acc = on;
-                record<REC>(a, k, s, col, on);
+                record<REC>(a, td.begin + i, s, col, on);
             }
         }
     }
@@ -127,45 +194,51 @@ __device__ __forceinline__ void run_pocket(const RouteArgs& a, const TaskDesc& t
 // PRE: every reach of a spine segment independently -- gathers the side inflow from the pocket
 // roots, folds the old state and the forcing into  b = alpha*side + beta*i_prev + chi*o_prev + gamma*q
 // and parks (side, b) in the segment's own I / O rows for the CHAIN task.
-template <bool HAS_F, bool HAS_W>
-__device__ __forceinline__ void run_pre(const RouteArgs& a, const TaskDesc& td, int col, bool active,
+template <bool HAS_F, bool HAS_W, bool WK>
+__device__ __forceinline__ void run_pre(const RouteArgs& a, const TaskDesc& td, const Stage& st, int col, bool active,
                                         const StepCtx& sc)
 {
-    const int ld = a.ld, begin = td.begin, end = td.begin + td.len;
+    const int ld = a.ld, len = td.len;
     const int ccol = active ? col : 0;
     double* Ob = a.O + ccol;
-    double* Ib = a.I + ccol;
-    const uint32_t* inp = a.inw + td.in_off;
-    double2 pi[kPF], po[kPF];
-#pragma unroll
-    for (int j = 0; j < kPF; ++j) {
-        pi[j] = po[j] = make_double2(0.0, 0.0);
-        if (active && begin + j < end) { pi[j] = ld_row(Ib + (size_t)(begin + j) * ld); po[j] = ld_row(Ob + (size_t)(begin + j) * ld); }
-    }
-    for (int k0 = begin; k0 < end; k0 += kPF) {
+    double* Or = Ob + (size_t)td.begin * ld;
+    double* Ir = a.I + ccol + (size_t)td.begin * ld;
+    int wi = 0;
+    for (int i0 = 0; i0 < len; i0 += kPF) {
+        // the reaches of a PRE task are independent: issue every row load of the group first
+        double2 io[kPF], oo[kPF], g0[kPF];
+        int nin[kPF], w0[kPF];
 #pragma unroll
         for (int j = 0; j < kPF; ++j) {
-            const int k = k0 + j;
-            if (k < end) {
-                const double2 io = pi[j], oo = po[j];
-                if (active && k + kPF < end) { pi[j] = ld_row(Ib + (size_t)(k + kPF) * ld); po[j] = ld_row(Ob + (size_t)(k + kPF) * ld); }
-                const uint32_t h = __ldg(a.hdr + k);
-                const double2 c01 = __ldg(reinterpret_cast<const double2*>(a.coef + 4 * (size_t)k));
-                const double2 c23 = __ldg(reinterpret_cast<const double2*>(a.coef + 4 * (size_t)k) + 1);
-                double2 side = make_double2(0.0, 0.0);
-                const int nin = (int)((h >> 6) & 0x1fffu);
-                for (int t = 0; t < nin; ++t) {
-                    const uint32_t w = __ldg(inp++);
+            const int i = i0 + j;
+            io[j] = oo[j] = g0[j] = make_double2(0.0, 0.0);
+            nin[j] = 0; w0[j] = wi;
+            if (i < len) {
+                nin[j] = (int)((st.h(i) >> 6) & 0x1fffu);
+                wi += nin[j];
+                if (active) {
+                    io[j] = ldr<WK>(Ir + (size_t)i * ld); oo[j] = ldr<WK>(Or + (size_t)i * ld);
+                    if (nin[j] > 0) g0[j] = ldr<WK>(Ob + (size_t)(st.word(w0[j]) & ~INW_ROW) * ld);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kPF; ++j) {
+            const int i = i0 + j;
+            if (i < len) {
+                double2 side = g0[j];
+                for (int t = 1; t < nin[j]; ++t) {
                     if (active) {
-                        const double2 v = ld_row(Ob + (size_t)(w & ~INW_ROW) * ld);
+                        const double2 v = ldr<WK>(Ob + (size_t)(st.word(w0[j] + t) & ~INW_ROW) * ld);
                         side.x += v.x; side.y += v.y;
                     }
                 }
-                const double2 q = forcing_q<HAS_F, HAS_W>(sc, k);
+                const double al = st.al(i), be = st.be(i), ch = st.ch(i), ga = st.ga(i);
+                const double2 q = forcing_q<HAS_F, HAS_W>(sc, st, i);
                 double2 b;
-                b.x = c01.x * side.x + (c01.y * io.x + c23.x * oo.x + c23.y * q.x);
-                b.y = c01.x * side.y + (c01.y * io.y + c23.x * oo.y + c23.y * q.y);
-                if (active) { st_row(Ib + (size_t)k * ld, side); st_row(Ob + (size_t)k * ld, b); }
+                b.x = al * side.x + (be * io[j].x + ch * oo[j].x + ga * q.x);
+                b.y = al * side.y + (be * io[j].y + ch * oo[j].y + ga * q.y);
+                if (active) { str<WK>(Ir + (size_t)i * ld, side); str<WK>(Or + (size_t)i * ld, b); }
             }
         }
     }
@@ -174,36 +247,40 @@ __device__ __forceinline__ void run_pre(const RouteArgs& a, const TaskDesc& td, 
 // CHAIN: the first-order recurrence down the segment,  o_k = alpha_k * (o_{k-1} + late_k) + b_k,
 // i_k = o_{k-1} + late_k + side_k, where late_k are outflows of other spine segments (the
 // upstream segment of the same path, long tributaries).  One FMA per reach on the critical path.
-template <bool REC>
-__device__ __forceinline__ void run_chain(const RouteArgs& a, const TaskDesc& td, int s, int col, bool active)
+template <bool REC, bool WK>
+__device__ __forceinline__ void run_chain(const RouteArgs& a, const TaskDesc& td, const Stage& st, int s, int col,
+                                          bool active)
 {
-    const int ld = a.ld, begin = td.begin, end = td.begin + td.len;
+    const int ld = a.ld, len = td.len;
     const int ccol = active ? col : 0;
     double* Ob = a.O + ccol;
-    double* Ib = a.I + ccol;
-    const uint32_t* inp = a.inw + td.in_off;
+    double* Or = Ob + (size_t)td.begin * ld;
+    double* Ir = a.I + ccol + (size_t)td.begin * ld;
+    int wi = 0;
     double2 o = make_double2(0.0, 0.0);
-    double2 ps[kPF], pb[kPF];
+    double2 ps[kPFChain], pb[kPFChain];
 #pragma unroll
-    for (int j = 0; j < kPF; ++j) {
+    for (int j = 0; j < kPFChain; ++j) {
         ps[j] = pb[j] = make_double2(0.0, 0.0);
-        if (active && begin + j < end) { ps[j] = ld_row(Ib + (size_t)(begin + j) * ld); pb[j] = ld_row(Ob + (size_t)(begin + j) * ld); }
+        if (active && j < len) { ps[j] = ldr<WK>(Ir + (size_t)j * ld); pb[j] = ldr<WK>(Or + (size_t)j * ld); }
     }
-    for (int k0 = begin; k0 < end; k0 += kPF) {
+    for (int i0 = 0; i0 < len; i0 += kPFChain) {
 #pragma unroll
-        for (int j = 0; j < kPF; ++j) {
-            const int k = k0 + j;
-            if (k < end) {
+        for (int j = 0; j < kPFChain; ++j) {
+            const int i = i0 + j;
+            if (i < len) {
                 const double2 side = ps[j], b = pb[j];
-                if (active && k + kPF < end) { ps[j] = ld_row(Ib + (size_t)(k + kPF) * ld); pb[j] = ld_row(Ob + (size_t)(k + kPF) * ld); }
-                const uint32_t h = __ldg(a.hdr + k);
-                const double al = __ldg(a.coef + 4 * (size_t)k);
+                if (active && i + kPFChain < len) {
+                    ps[j] = ldr<WK>(Ir + (size_t)(i + kPFChain) * ld); pb[j] = ldr<WK>(Or + (size_t)(i + kPFChain) * ld);
+                }
+                const uint32_t h = st.h(i);
+                const double al = st.al(i);
                 double2 inflow = (h & HDR_ACC) ? o : make_double2(0.0, 0.0);
                 const int nlate = (int)(h >> 19);
                 for (int t = 0; t < nlate; ++t) {
-                    const uint32_t w = __ldg(inp++);
+                    const uint32_t w = st.word(wi++);
                     if (active) {
-                        const double2 v = ld_row(Ob + (size_t)(w & ~INW_ROW) * ld);
+                        const double2 v = ldr<WK>(Ob + (size_t)(w & ~INW_ROW) * ld);
                         inflow.x += v.x; inflow.y += v.y;
                     }
                 }
@@ -212,27 +289,24 @@ __device__ __forceinline__ void run_chain(const RouteArgs& a, const TaskDesc& td
                 on.y = al * inflow.y + b.y;
                 it.x = inflow.x + side.x;
                 it.y = inflow.y + side.y;
-                if (active) { st_row(Ib + (size_t)k * ld, it); st_row(Ob + (size_t)k * ld, on); }
+                if (active) { str<WK>(Ir + (size_t)i * ld, it); str<WK>(Or + (size_t)i * ld, on); }
                 o = on;
-                record<REC>(a, k, s, col, on);
+                record<REC>(a, td.begin + i, s, col, on);
             }
         }
     }
 }
 
-// Prepares the dataflow runtime for one launch: dependency counters, step counters and the
-// ready queue seeded with every task that has no same-step producer.
+// Prepares the dataflow runtime for one launch: dependency counters and the ready queue seeded
+// with every task that has no same-step producer.  Queue entry = (step << 32) | (pair + 1).
 __global__ void __launch_bounds__(256) dataflow_init_kernel(const InitArgs a)
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int pairs = a.n_tasks * a.n_mblocks;
-    if (gid < pairs) {
-        a.pending[gid] = a.tasks[gid / a.n_mblocks].need0;
-        a.stepno[gid] = 0;
-    }
+    if (gid < pairs) a.pending[gid] = a.tasks[gid / a.n_mblocks].need0;
     if (gid < a.n_init * a.n_mblocks) {
         const int t = a.init_ready[gid / a.n_mblocks];
-        a.queue[gid] = (uint32_t)(t * a.n_mblocks + gid % a.n_mblocks) + 1u;
+        a.queue[gid] = (unsigned long long)(t * a.n_mblocks + gid % a.n_mblocks) + 1ull;
     }
     if (gid == 0) {
         a.q_head[0] = 0ull;
@@ -241,38 +315,43 @@ __global__ void __launch_bounds__(256) dataflow_init_kernel(const InitArgs a)
     }
 }
 
-template <bool HAS_F, bool HAS_W, bool REC>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+template <bool HAS_F, bool HAS_W, bool REC, bool WK>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
 route_dataflow_kernel(const RouteArgs a)
 {
-    extern __shared__ double2 scratch_all[];
+    extern __shared__ __align__(16) unsigned char smem_all[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    double2* scratch = scratch_all + (size_t)warp * a.slots * 32 + lane;   // this lane's column
+    unsigned char* wbase = smem_all + (size_t)warp * a.smem_per_warp;
+    double2* scratch = reinterpret_cast<double2*>(wbase) + lane;            // this lane's column of every slot
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(wbase);
     const int nmb = a.n_mblocks;
     unsigned long long* q_tail = a.q_head + 1;
     unsigned long long* n_done = a.q_head + 2;
+    const long long pairs = (long long)a.n_tasks * nmb;
 
     if (ld_relaxed(a.status) != 0) return;          // a previous launch on this handle was poisoned
 
-    int next_pair = -1;                             // task made ready by this warp: run it without queueing
+    long long next_entry = 0;                       // task made ready by this warp: run it without queueing
     for (;;) {
-        int pair = next_pair;
-        next_pair = -1;
-        if (pair < 0) {
+        unsigned long long t_pop = 0;
+        if (a.trace && lane == 0) t_pop = globaltimer_ns();
+        long long entry = next_entry;
+        next_entry = 0;
+        if (entry == 0) {
             // ---- pop: claim a queue position, wait until its producer has published it ----
             if (lane == 0) {
                 const unsigned long long idx = atomicAdd(a.q_head, 1ull);
-                pair = -2;
+                entry = -1;
                 if ((long long)idx < a.total) {
-                    const uint32_t* slot = a.queue + idx;
-                    unsigned spins = 0;
+                    const unsigned long long* slot = a.queue + idx;
+                    unsigned spins = 0, nap = 64;
                     unsigned long long t0 = 0;
                     for (;;) {
-                        uint32_t v;
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
-                        if (v != 0u) { pair = (int)(v - 1u); break; }
-                        if ((++spins & 63u) == 0) {
+                        unsigned long long v;
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+                        if (v != 0ull) { entry = (long long)v; break; }
+                        if ((++spins & 15u) == 0) {
                             unsigned long long fin;
                             asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(fin) : "l"(n_done) : "memory");
                             if ((long long)fin >= a.total) break;           // everything ran (inline continuations skip the queue)
@@ -281,53 +360,72 @@ route_dataflow_kernel(const RouteArgs a)
                             if (t0 == 0) t0 = now;
                             else if (now - t0 > a.watchdog_ns) { atomicExch(a.status, 1); break; }
                         }
-                        __nanosleep(32);
+                        __nanosleep(nap);
+                        if (nap < 1024u) nap <<= 1;
                     }
+                    if (entry > 0) fence_acq_rel();                          // acquire: the producers' rows are visible
                 }
             }
-            pair = __shfl_sync(0xffffffffu, pair, 0);
-            if (pair < 0) break;
+            entry = __shfl_sync(0xffffffffu, entry, 0);
+            if (entry <= 0) break;
         }
+        const int pair = (int)((unsigned long long)entry & 0xffffffffull) - 1;
+        const int s = (int)((unsigned long long)entry >> 32);
         const int task = pair / nmb;
         const int mb = pair - task * nmb;
         const TaskDesc td = a.tasks[task];
-        const int s = ld_relaxed(a.stepno + pair);  // written by the pair's previous run (another SM): L1 must not serve it
+        unsigned long long t_begin = 0;
+        if (a.trace && lane == 0) t_begin = globaltimer_ns();
 
-        const int col = mb * kMemberBlock + lane * 2;
-        const bool active = col < a.ld;
-
-        if (td.kind == TASK_CHAIN) {
-            run_chain<REC>(a, td, s, col, active);
-        } else {
-            StepCtx sc;
-            sc.w0 = sc.w1 = 0.0; sc.wm0 = sc.wm1 = make_double2(0.0, 0.0); sc.F0 = sc.F1 = nullptr;
-            if (HAS_F) {
-                const StepInterp si = a.steps[s];
-                sc.F0 = a.F + (size_t)si.r0 * a.n;
-                sc.F1 = a.F + (size_t)si.r1 * a.n;
-                sc.w0 = si.w0; sc.w1 = si.w1;
-                if (HAS_W) {
-                    // member m sees  (w0*mul[r0][m])*F[r0] + (w1*mul[r1][m])*F[r1]
-                    const int c0 = min(col, a.wm_ld - 1), c1 = min(col + 1, a.wm_ld - 1);
-                    const double* m0 = a.Wmul + (size_t)si.r0 * a.wm_ld;
-                    const double* m1 = a.Wmul + (size_t)si.r1 * a.wm_ld;
-                    sc.wm0 = make_double2(si.w0 * __ldg(m0 + c0), si.w0 * __ldg(m0 + c1));
-                    sc.wm1 = make_double2(si.w1 * __ldg(m1 + c0), si.w1 * __ldg(m1 + c1));
+        // ---- stage the task's metadata in shared memory (asynchronous copies) ----------------
+        StepInterp si;
+        si.r0 = si.r1 = 0; si.w0 = si.w1 = 0.0;
+        Stage st;
+        st.coef = sbase + a.off_coef; st.f0 = sbase + a.off_f0; st.f1 = sbase + a.off_f1;
+        st.hdr = sbase + a.off_hdr; st.inw = sbase + a.off_inw; st.inw_g = nullptr;
+        {
+            const double* gc = a.coef + 4 * (size_t)td.begin;
+            for (int i = lane; i < 2 * td.len; i += 32) cp_async16(wbase + a.off_coef + 16 * i, gc + 2 * i);
+            for (int i = lane; i < td.len; i += 32) cp_async4(wbase + a.off_hdr + 4 * i, a.hdr + td.begin + i);
+            if (td.n_words <= a.max_words)
+                for (int i = lane; i < td.n_words; i += 32) cp_async4(wbase + a.off_inw + 4 * i, a.inw + td.in_off + i);
+            else
+                st.inw_g = a.inw + td.in_off;
+            if (HAS_F && td.kind != TASK_CHAIN) {
+                si = a.steps[s];
+                const double* F0 = a.F + (size_t)si.r0 * a.n + td.begin;
+                const double* F1 = a.F + (size_t)si.r1 * a.n + td.begin;
+                for (int i = lane; i < td.len; i += 32) {
+                    cp_async8(wbase + a.off_f0 + 8 * i, F0 + i);
+                    cp_async8(wbase + a.off_f1 + 8 * i, F1 + i);
                 }
             }
-            if (td.kind == TASK_PRE) run_pre<HAS_F, HAS_W>(a, td, col, active, sc);
-            else run_pocket<HAS_F, HAS_W, REC>(a, td, s, col, active, scratch, sc);
         }
+        const int col = mb * kMemberBlock + lane * 2;
+        const bool active = col < a.ld;
+        StepCtx sc;
+        sc.w0 = si.w0; sc.w1 = si.w1; sc.wm0 = sc.wm1 = make_double2(0.0, 0.0);
+        if (HAS_F && HAS_W && td.kind != TASK_CHAIN) {
+            // member m sees  (w0*mul[r0][m])*F[r0] + (w1*mul[r1][m])*F[r1]
+            const int c0 = min(col, a.wm_ld - 1), c1 = min(col + 1, a.wm_ld - 1);
+            const double* m0 = a.Wmul + (size_t)si.r0 * a.wm_ld;
+            const double* m1 = a.Wmul + (size_t)si.r1 * a.wm_ld;
+            sc.wm0 = make_double2(si.w0 * __ldg(m0 + c0), si.w0 * __ldg(m0 + c1));
+            sc.wm1 = make_double2(si.w1 * __ldg(m1 + c0), si.w1 * __ldg(m1 + c1));
+        }
+        cp_async_wait_all();
+        __syncwarp();
 
-        // ---- completion: re-arm, publish, notify dependants --------------------------------
-        __syncwarp();
+        if (td.kind == TASK_CHAIN) run_chain<REC, WK>(a, td, st, s, col, active);
+        else if (td.kind == TASK_PRE) run_pre<HAS_F, HAS_W, WK>(a, td, st, col, active, sc);
+        else run_pocket<HAS_F, HAS_W, REC, WK>(a, td, st, s, col, active, scratch, sc);
+
+        // ---- completion: re-arm, then notify dependants with release atomics -----------------
+        unsigned long long t_comp = 0;
+        if (a.trace && lane == 0) t_comp = globaltimer_ns();
         const bool more = s + 1 < a.nsteps;
-        if (lane == 0) {
-            a.stepno[pair] = s + 1;
-            if (more) a.pending[pair] = td.need;    // nobody can signal step s+1 before the notifications below
-            __threadfence();
-        }
-        __syncwarp();
+        if (more && lane == 0) a.pending[pair] = td.need;   // nobody can signal step s+1 before the notifications below
+        __syncwarp();                                        // every lane's rows + the re-arm precede the releases
         const int nn = td.n_same + (more ? td.n_next : 0);
         for (int d0 = 0; d0 < nn; d0 += 32) {
             const int d = d0 + lane;
@@ -335,24 +433,39 @@ route_dataflow_kernel(const RouteArgs a)
             bool ready = false;
             if (d < nn) {
                 tgt = a.notify[td.nfy_off + d] * nmb + mb;
-                ready = atomicSub(a.pending + tgt, 1) == 1;
-                if (ready) __threadfence();
+                int old;
+                asm volatile("atom.release.gpu.global.add.s32 %0, [%1], -1;" : "=r"(old) : "l"(a.pending + tgt) : "memory");
+                ready = old == 1;
             }
-            unsigned mask = __ballot_sync(0xffffffffu, ready);
-            if (mask != 0u && next_pair < 0) {
-                // keep one ready dependant for this warp (a CHAIN if there is one): no queue round trip
-                const bool is_chain = ready && a.tasks[tgt / nmb].kind == TASK_CHAIN;
-                const unsigned cm = __ballot_sync(0xffffffffu, is_chain);
-                const int keep = __ffs(cm ? cm : mask) - 1;
-                next_pair = __shfl_sync(0xffffffffu, tgt, keep);
-                if (lane == keep) ready = false;
-            }
-            if (ready) {
-                const unsigned long long idx = atomicAdd(q_tail, 1ull);
-                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.queue + idx), "r"((uint32_t)tgt + 1u) : "memory");
+            const unsigned mask = __ballot_sync(0xffffffffu, ready);
+            if (mask != 0u) {
+                if (ready) fence_acq_rel();          // acquire the other contributors' releases, release for the hand-off
+                // entry of the dependant: same-step targets run step s, next-step targets step s + 1
+                const long long e = ((long long)(d < td.n_same ? s : s + 1) << 32) | (long long)(unsigned)(tgt + 1);
+                if (next_entry == 0) {
+                    // keep one ready dependant for this warp (a CHAIN if there is one): no queue round trip
+                    const bool is_chain = ready && a.tasks[tgt / nmb].kind == TASK_CHAIN;
+                    const unsigned cm = __ballot_sync(0xffffffffu, is_chain);
+                    const int keep = __ffs(cm ? cm : mask) - 1;
+                    next_entry = __shfl_sync(0xffffffffu, e, keep);
+                    if (lane == keep) ready = false;
+                }
+                if (ready) {
+                    const unsigned long long idx = atomicAdd(q_tail, 1ull);
+                    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.queue + idx), "l"(e) : "memory");
+                }
             }
         }
-        if (lane == 0) atomicAdd(n_done, 1ull);
+        if (lane == 0) {
+            atomicAdd(n_done, 1ull);
+            if (a.trace) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                unsigned long long* tr = a.trace + 4 * ((size_t)s * pairs + pair);
+                tr[0] = t_pop; tr[1] = t_begin; tr[2] = t_comp;
+                tr[3] = (globaltimer_ns() << 16) | ((unsigned long long)(smid & 0xffu) << 8) | (unsigned)td.kind;
+            }
+        }
         __syncwarp();
     }
 }
@@ -488,12 +601,18 @@ cudaError_t launch_dataflow_init(const InitArgs& a, cudaStream_t st)
 
 cudaError_t launch_route_dataflow(const RouteArgs& a, int num_sms, cudaStream_t st)
 {
-    const size_t smem = (size_t)kWarpsPerCta * a.slots * 32 * sizeof(double2);
+    const size_t smem = (size_t)kWarpsPerCta * a.smem_per_warp;
     void (*kern)(const RouteArgs) = nullptr;
     const bool f = a.F != nullptr, w = a.Wmul != nullptr, r = a.rec_slot != nullptr;
-    if (!f) kern = r ? route_dataflow_kernel<false, false, true> : route_dataflow_kernel<false, false, false>;
-    else if (!w) kern = r ? route_dataflow_kernel<true, false, true> : route_dataflow_kernel<true, false, false>;
-    else kern = r ? route_dataflow_kernel<true, true, true> : route_dataflow_kernel<true, true, false>;
+    if (a.weak_rows) {
+        if (!f) kern = r ? route_dataflow_kernel<false, false, true, true> : route_dataflow_kernel<false, false, false, true>;
+        else if (!w) kern = r ? route_dataflow_kernel<true, false, true, true> : route_dataflow_kernel<true, false, false, true>;
+        else kern = r ? route_dataflow_kernel<true, true, true, true> : route_dataflow_kernel<true, true, false, true>;
+    } else {
+        if (!f) kern = r ? route_dataflow_kernel<false, false, true, false> : route_dataflow_kernel<false, false, false, false>;
+        else if (!w) kern = r ? route_dataflow_kernel<true, false, true, false> : route_dataflow_kernel<true, false, false, false>;
+        else kern = r ? route_dataflow_kernel<true, true, true, false> : route_dataflow_kernel<true, true, false, false>;
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;

@@ -396,7 +396,7 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
             }
         }
         tasks.assign(nu, TaskDesc{});
-        inw.clear(); notify.clear(); init_ready.clear();
+        inw.clear(); notify.clear(); init_ready.clear(); max_len = 0;
         for (int32_t k = 0; k < nu; ++k) {
             const Unit& U = units[order[k]];
             TaskDesc& td = tasks[k];
@@ -414,6 +414,8 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
                 notify.push_back(rank[c]);
             }
             for (int32_t c : next[order[k]]) notify.push_back(rank[c]);
+            td.n_words = (int32_t)U.ins.size();
+            max_len = std::max(max_len, td.len);
             td.need0 = (int32_t)U.A.size();
             td.need = (int32_t)(U.A.size() + U.B.size());
             if (td.need0 == 0) init_ready.push_back(k);

@@ -70,7 +70,8 @@ struct TaskDesc {
     int32_t need0;     // |A(T)|           pending count before step 0
     int32_t need;      // |A(T)| + |B(T)|  re-arm value after each completed step
     int32_t kind;      // TASK_POCKET / TASK_PRE / TASK_CHAIN
-    int32_t pad_[3];
+    int32_t n_words;   // input words of this task
+    int32_t pad_[2];
 };
 
 struct Schedule {
@@ -87,6 +88,7 @@ struct Schedule {
     std::vector<uint8_t> is_outlet_pos;
     // statistics
     int32_t n_spine = 0, n_pocket = 0, slots_used = 0, row_fallbacks = 0;
+    int32_t max_len = 0;                    // longest task (rows)
     int32_t cp_tasks = 0;                   // tasks on the longest same-step dependent chain
     int64_t cp_cost = 0;
 
