@@ -202,9 +202,9 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
         a.off_f1 = a.off_f0 + up16(L * (int)sizeof(double));
         a.off_hdr = a.off_f1 + up16(L * (int)sizeof(double));
         a.off_inw = a.off_hdr + up16(L * (int)sizeof(uint32_t));
-        a.smem_per_warp = a.off_inw + up16(a.max_words * (int)sizeof(uint32_t));
+        a.off_ring = a.off_inw + up16(a.max_words * (int)sizeof(uint32_t));
+        a.smem_per_warp = a.off_ring + kRingBytes;
         a.trace = nullptr;
-        { const char* e = getenv("TXH_ROWOP"); a.weak_rows = e ? atoi(e) : 1; }
         const char* trace_file = getenv("TXH_TRACE_FILE");
         unsigned long long* d_trace = nullptr;
         if (trace_file && *trace_file) {

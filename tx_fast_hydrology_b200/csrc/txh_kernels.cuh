@@ -16,6 +16,7 @@ struct StepInterp {
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kMemberBlock = 64;          // members per warp: one double2 per lane
+constexpr int kRingBytes = 2 * 12 * 512;  // per-warp row ring: 2 arrays x 12 rows x 512 B (see txh_route.cu)
 
 struct RouteArgs {
     const TaskDesc* tasks;
@@ -40,10 +41,9 @@ struct RouteArgs {
     int64_t n;
     int32_t n_tasks, n_mblocks, nsteps, slots;
     int32_t ld, M, wm_ld, rec_every, rec_count;
-    // per-warp shared-memory staging area (bytes): [scratch slots][coef][f0][f1][hdr][inw]
-    int32_t smem_per_warp, off_coef, off_f0, off_f1, off_hdr, off_inw, max_words;
+    // per-warp shared-memory area (bytes): [scratch slots][coef][f0][f1][hdr][inw][row ring]
+    int32_t smem_per_warp, off_coef, off_f0, off_f1, off_hdr, off_inw, off_ring, max_words;
     unsigned long long* trace;            // optional [total][4] timeline, nullptr = off
-    int32_t weak_rows;                    // row loads/stores: 1 = weak (L1::no_allocate), 0 = .cg
 };
 
 struct InitArgs {

@@ -37,30 +37,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 // state rows are produced and consumed by different SMs inside one launch: bypass L1
 __device__ __forceinline__ double2 ld_row(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ void st_row(double* p, double2 v) { __stcg(reinterpret_cast<double2*>(p), v); }
-// Weak variants for the dataflow kernel: every task starts behind an acquire fence (which
-// invalidates L1), its inputs were final before that fence, and rows are never allocated in L1,
-// so plain loads cannot observe stale data -- and, unlike the strong forms, they do not queue
-// behind this warp's own earlier row stores.
-template <bool WEAK>
-__device__ __forceinline__ double2 ldr(const double* p)
-{
-    if (WEAK) {
-        double2 v;
-        asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-        return v;
-    }
-    return __ldcg(reinterpret_cast<const double2*>(p));
-}
-template <bool WEAK>
-__device__ __forceinline__ void str(double* p, double2 v)
-{
-    if (WEAK) asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-    else __stcg(reinterpret_cast<double2*>(p), v);
-}
-
-
-constexpr int kPF = 4;       // row prefetch distance (reaches ahead) in PRE / POCKET tasks
-constexpr int kPFChain = 8;  // ... and on the latency-critical CHAIN tasks
+constexpr int kRing = 12;     // rows in flight per warp and state array (cp.async ring in shared memory)
+constexpr int kRingPre = 8;   // PRE tasks stream three arrays (I, O, first side row): 3 x 8 == 2 x 12 slots
 
 __device__ __forceinline__ void cp_async4(void* s, const void* g)
 {
@@ -78,6 +56,20 @@ __device__ __forceinline__ void cp_async16(void* s, const void* g)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// row copy global -> this lane's 16-byte cell of a ring slot (LDGSTS, L1 bypass)
+__device__ __forceinline__ void cp_row(unsigned saddr, const double* g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ double2 lds_row(unsigned saddr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(saddr));
+    return v;
+}
 
 __device__ __forceinline__ double lds_f64(unsigned a)
 {
@@ -140,161 +132,188 @@ __device__ __forceinline__ void record(const RouteArgs& a, int k, int s, int col
     }
 }
 
+// Row streaming.  A task's I / O rows are contiguous (schedule order), so the warp keeps the next
+// kRing rows of both arrays in flight with asynchronous global->shared copies; every lane copies and
+// later reads back only its own 16-byte cell (its two member columns), so completion is tracked
+// per thread with cp.async groups: one group per row, committed even when empty.
+// ring cell address: ring + ((arr * D + slot) * 32 + lane) * 16, `ring` already includes the lane term.
+
 // POCKET: a bundle of side subtrees evaluated depth-first by one warp.  Intermediate
 // outflows travel through the accumulator or this lane's scratch column.
-template <bool HAS_F, bool HAS_W, bool REC, bool WK>
+template <bool HAS_F, bool HAS_W, bool REC>
 __device__ __forceinline__ void run_pocket(const RouteArgs& a, const TaskDesc& td, const Stage& st, int s, int col,
-                                           bool active, double2* scratch, const StepCtx& sc)
+                                           bool active, double2* scratch, const StepCtx& sc, unsigned ring)
 {
     const int ld = a.ld, len = td.len;
     const int ccol = active ? col : 0;
     double* Ob = a.O + ccol;
     double* Or = Ob + (size_t)td.begin * ld;
     double* Ir = a.I + ccol + (size_t)td.begin * ld;
-    int wi = 0;
+    const unsigned ringO = ring + kRing * 512u;
+#pragma unroll
+    for (int j = 0; j < kRing; ++j) {
+        if (active && j < len) { cp_row(ring + j * 512u, Ir + (size_t)j * ld); cp_row(ringO + j * 512u, Or + (size_t)j * ld); }
+        cp_async_commit();
+    }
+    cp_async_wait_group<kRing>();                       // this thread's share of the staged metadata ...
+    __syncwarp();                                       // ... and every other lane's
+    int wi = 0, sl = 0;
     double2 acc = make_double2(0.0, 0.0);
-    double2 pi[kPF], po[kPF];
-#pragma unroll
-    for (int j = 0; j < kPF; ++j) {
-        pi[j] = po[j] = make_double2(0.0, 0.0);
-        if (active && j < len) { pi[j] = ldr<WK>(Ir + (size_t)j * ld); po[j] = ldr<WK>(Or + (size_t)j * ld); }
-    }
-    for (int i0 = 0; i0 < len; i0 += kPF) {
-#pragma unroll
-        for (int j = 0; j < kPF; ++j) {
-            const int i = i0 + j;
-            if (i < len) {
-                const double2 io = pi[j], oo = po[j];
-                if (active && i + kPF < len) { pi[j] = ldr<WK>(Ir + (size_t)(i + kPF) * ld); po[j] = ldr<WK>(Or + (size_t)(i + kPF) * ld); }
-                const uint32_t h = st.h(i);
-                const double al = st.al(i), be = st.be(i), ch = st.ch(i), ga = st.ga(i);
-                double2 inflow = (h & HDR_ACC) ? acc : make_double2(0.0, 0.0);
-                const int nin = (int)(h >> 6);
-                for (int t = 0; t < nin; ++t) {
-                    const uint32_t w = st.word(wi++);
-                    double2 v;
-                    if (w & INW_ROW) v = active ? ldr<WK>(Ob + (size_t)(w & ~INW_ROW) * ld) : make_double2(0.0, 0.0);
-                    else v = scratch[w * 32];
-                    inflow.x += v.x; inflow.y += v.y;
-                }
-                const double2 q = forcing_q<HAS_F, HAS_W>(sc, st, i);
-                double2 on;
-                on.x = al * inflow.x + (be * io.x + ch * oo.x + ga * q.x);
-                on.y = al * inflow.y + (be * io.y + ch * oo.y + ga * q.y);
-                if (active) { str<WK>(Ir + (size_t)i * ld, inflow); str<WK>(Or + (size_t)i * ld, on); }
-                const uint32_t slot = (h >> 1) & 31u;
-                if (slot) scratch[(slot - 1) * 32] = on;
-                acc = on;
-                record<REC>(a, td.begin + i, s, col, on);
-            }
+    for (int i = 0; i < len; ++i) {
+        cp_async_wait_group<kRing - 1>();               // row i has landed
+        const double2 io = lds_row(ring + sl * 512u), oo = lds_row(ringO + sl * 512u);
+        if (active && i + kRing < len) {
+            cp_row(ring + sl * 512u, Ir + (size_t)(i + kRing) * ld);
+            cp_row(ringO + sl * 512u, Or + (size_t)(i + kRing) * ld);
         }
+        cp_async_commit();
+        sl = sl + 1 == kRing ? 0 : sl + 1;
+        const uint32_t h = st.h(i);
+        const double al = st.al(i), be = st.be(i), ch = st.ch(i), ga = st.ga(i);
+        double2 inflow = (h & HDR_ACC) ? acc : make_double2(0.0, 0.0);
+        const int nin = (int)(h >> 6);
+        for (int t = 0; t < nin; ++t) {
+            const uint32_t w = st.word(wi++);
+            double2 v;
+            if (w & INW_ROW) v = active ? ld_row(Ob + (size_t)(w & ~INW_ROW) * ld) : make_double2(0.0, 0.0);
+            else v = scratch[w * 32];
+            inflow.x += v.x; inflow.y += v.y;
+        }
+        const double2 q = forcing_q<HAS_F, HAS_W>(sc, st, i);
+        double2 on;
+        on.x = al * inflow.x + (be * io.x + ch * oo.x + ga * q.x);
+        on.y = al * inflow.y + (be * io.y + ch * oo.y + ga * q.y);
+        if (active) { st_row(Ir + (size_t)i * ld, inflow); st_row(Or + (size_t)i * ld, on); }
+        const uint32_t slot = (h >> 1) & 31u;
+        if (slot) scratch[(slot - 1) * 32] = on;
+        acc = on;
+        record<REC>(a, td.begin + i, s, col, on);
     }
+    cp_async_wait_all();
 }
 
 // PRE: every reach of a spine segment independently -- gathers the side inflow from the pocket
 // roots, folds the old state and the forcing into  b = alpha*side + beta*i_prev + chi*o_prev + gamma*q
-// and parks (side, b) in the segment's own I / O rows for the CHAIN task.
-template <bool HAS_F, bool HAS_W, bool WK>
+// and parks (side, b) in the segment's own I / O rows for the CHAIN task.  The first side row of
+// each reach travels through the ring with the state rows.
+template <bool HAS_F, bool HAS_W>
 __device__ __forceinline__ void run_pre(const RouteArgs& a, const TaskDesc& td, const Stage& st, int col, bool active,
-                                        const StepCtx& sc)
+                                        const StepCtx& sc, unsigned ring)
 {
     const int ld = a.ld, len = td.len;
     const int ccol = active ? col : 0;
     double* Ob = a.O + ccol;
     double* Or = Ob + (size_t)td.begin * ld;
     double* Ir = a.I + ccol + (size_t)td.begin * ld;
-    int wi = 0;
-    for (int i0 = 0; i0 < len; i0 += kPF) {
-        // the reaches of a PRE task are independent: issue every row load of the group first
-        double2 io[kPF], oo[kPF], g0[kPF];
-        int nin[kPF], w0[kPF];
+    const unsigned ringO = ring + kRingPre * 512u, ringG = ring + 2 * kRingPre * 512u;
+    cp_async_wait_all();                                // the gather addresses come from the staged words
+    __syncwarp();
+    int wq = 0;                                         // word cursor of the prefetcher
 #pragma unroll
-        for (int j = 0; j < kPF; ++j) {
-            const int i = i0 + j;
-            io[j] = oo[j] = g0[j] = make_double2(0.0, 0.0);
-            nin[j] = 0; w0[j] = wi;
-            if (i < len) {
-                nin[j] = (int)((st.h(i) >> 6) & 0x1fffu);
-                wi += nin[j];
-                if (active) {
-                    io[j] = ldr<WK>(Ir + (size_t)i * ld); oo[j] = ldr<WK>(Or + (size_t)i * ld);
-                    if (nin[j] > 0) g0[j] = ldr<WK>(Ob + (size_t)(st.word(w0[j]) & ~INW_ROW) * ld);
-                }
+    for (int j = 0; j < kRingPre; ++j) {
+        if (j < len) {
+            const int nin = (int)((st.h(j) >> 6) & 0x1fffu);
+            if (active) {
+                cp_row(ring + j * 512u, Ir + (size_t)j * ld); cp_row(ringO + j * 512u, Or + (size_t)j * ld);
+                if (nin > 0) cp_row(ringG + j * 512u, Ob + (size_t)(st.word(wq) & ~INW_ROW) * ld);
             }
+            wq += nin;
         }
-#pragma unroll
-        for (int j = 0; j < kPF; ++j) {
-            const int i = i0 + j;
-            if (i < len) {
-                double2 side = g0[j];
-                for (int t = 1; t < nin[j]; ++t) {
-                    if (active) {
-                        const double2 v = ldr<WK>(Ob + (size_t)(st.word(w0[j] + t) & ~INW_ROW) * ld);
-                        side.x += v.x; side.y += v.y;
-                    }
-                }
-                const double al = st.al(i), be = st.be(i), ch = st.ch(i), ga = st.ga(i);
-                const double2 q = forcing_q<HAS_F, HAS_W>(sc, st, i);
-                double2 b;
-                b.x = al * side.x + (be * io[j].x + ch * oo[j].x + ga * q.x);
-                b.y = al * side.y + (be * io[j].y + ch * oo[j].y + ga * q.y);
-                if (active) { str<WK>(Ir + (size_t)i * ld, side); str<WK>(Or + (size_t)i * ld, b); }
-            }
-        }
+        cp_async_commit();
     }
+    int wi = 0, sl = 0;
+    for (int i = 0; i < len; ++i) {
+        cp_async_wait_group<kRingPre - 1>();
+        const uint32_t h = st.h(i);
+        const int nin = (int)((h >> 6) & 0x1fffu);
+        const double2 io = lds_row(ring + sl * 512u), oo = lds_row(ringO + sl * 512u);
+        double2 side = nin > 0 ? lds_row(ringG + sl * 512u) : make_double2(0.0, 0.0);
+        const int ip = i + kRingPre;
+        if (ip < len) {
+            const int np = (int)((st.h(ip) >> 6) & 0x1fffu);
+            if (active) {
+                cp_row(ring + sl * 512u, Ir + (size_t)ip * ld); cp_row(ringO + sl * 512u, Or + (size_t)ip * ld);
+                if (np > 0) cp_row(ringG + sl * 512u, Ob + (size_t)(st.word(wq) & ~INW_ROW) * ld);
+            }
+            wq += np;
+        }
+        cp_async_commit();
+        sl = sl + 1 == kRingPre ? 0 : sl + 1;
+        for (int t = 1; t < nin; ++t) {
+            if (active) {
+                const double2 v = ld_row(Ob + (size_t)(st.word(wi + t) & ~INW_ROW) * ld);
+                side.x += v.x; side.y += v.y;
+            }
+        }
+        wi += nin;
+        const double al = st.al(i), be = st.be(i), ch = st.ch(i), ga = st.ga(i);
+        const double2 q = forcing_q<HAS_F, HAS_W>(sc, st, i);
+        double2 b;
+        b.x = al * side.x + (be * io.x + ch * oo.x + ga * q.x);
+        b.y = al * side.y + (be * io.y + ch * oo.y + ga * q.y);
+        if (active) { st_row(Ir + (size_t)i * ld, side); st_row(Or + (size_t)i * ld, b); }
+    }
+    cp_async_wait_all();
 }
 
 // CHAIN: the first-order recurrence down the segment,  o_k = alpha_k * (o_{k-1} + late_k) + b_k,
 // i_k = o_{k-1} + late_k + side_k, where late_k are outflows of other spine segments (the
 // upstream segment of the same path, long tributaries).  One FMA per reach on the critical path.
-template <bool REC, bool WK>
+template <bool REC>
 __device__ __forceinline__ void run_chain(const RouteArgs& a, const TaskDesc& td, const Stage& st, int s, int col,
-                                          bool active)
+                                          bool active, unsigned ring)
 {
     const int ld = a.ld, len = td.len;
     const int ccol = active ? col : 0;
     double* Ob = a.O + ccol;
     double* Or = Ob + (size_t)td.begin * ld;
     double* Ir = a.I + ccol + (size_t)td.begin * ld;
-    int wi = 0;
-    double2 o = make_double2(0.0, 0.0);
-    double2 ps[kPFChain], pb[kPFChain];
+    const unsigned ringO = ring + kRing * 512u;
+    // the upstream segment's outflow (first late input of the first reach) is fetched before anything else
+    double2 first = make_double2(0.0, 0.0);
+    if (td.first_in >= 0 && active) first = ld_row(Ob + (size_t)td.first_in * ld);
 #pragma unroll
-    for (int j = 0; j < kPFChain; ++j) {
-        ps[j] = pb[j] = make_double2(0.0, 0.0);
-        if (active && j < len) { ps[j] = ldr<WK>(Ir + (size_t)j * ld); pb[j] = ldr<WK>(Or + (size_t)j * ld); }
+    for (int j = 0; j < kRing; ++j) {
+        if (active && j < len) { cp_row(ring + j * 512u, Ir + (size_t)j * ld); cp_row(ringO + j * 512u, Or + (size_t)j * ld); }
+        cp_async_commit();
     }
-    for (int i0 = 0; i0 < len; i0 += kPFChain) {
-#pragma unroll
-        for (int j = 0; j < kPFChain; ++j) {
-            const int i = i0 + j;
-            if (i < len) {
-                const double2 side = ps[j], b = pb[j];
-                if (active && i + kPFChain < len) {
-                    ps[j] = ldr<WK>(Ir + (size_t)(i + kPFChain) * ld); pb[j] = ldr<WK>(Or + (size_t)(i + kPFChain) * ld);
-                }
-                const uint32_t h = st.h(i);
-                const double al = st.al(i);
-                double2 inflow = (h & HDR_ACC) ? o : make_double2(0.0, 0.0);
-                const int nlate = (int)(h >> 19);
-                for (int t = 0; t < nlate; ++t) {
-                    const uint32_t w = st.word(wi++);
-                    if (active) {
-                        const double2 v = ldr<WK>(Ob + (size_t)(w & ~INW_ROW) * ld);
-                        inflow.x += v.x; inflow.y += v.y;
-                    }
-                }
-                double2 on, it;
-                on.x = al * inflow.x + b.x;
-                on.y = al * inflow.y + b.y;
-                it.x = inflow.x + side.x;
-                it.y = inflow.y + side.y;
-                if (active) { str<WK>(Ir + (size_t)i * ld, it); str<WK>(Or + (size_t)i * ld, on); }
-                o = on;
-                record<REC>(a, td.begin + i, s, col, on);
+    cp_async_wait_group<kRing>();
+    __syncwarp();
+    int wi = 0, sl = 0;
+    double2 o = make_double2(0.0, 0.0);
+    for (int i = 0; i < len; ++i) {
+        cp_async_wait_group<kRing - 1>();
+        const double2 side = lds_row(ring + sl * 512u), b = lds_row(ringO + sl * 512u);
+        if (active && i + kRing < len) {
+            cp_row(ring + sl * 512u, Ir + (size_t)(i + kRing) * ld);
+            cp_row(ringO + sl * 512u, Or + (size_t)(i + kRing) * ld);
+        }
+        cp_async_commit();
+        sl = sl + 1 == kRing ? 0 : sl + 1;
+        const uint32_t h = st.h(i);
+        const double al = st.al(i);
+        double2 inflow = (h & HDR_ACC) ? o : make_double2(0.0, 0.0);
+        const int nlate = (int)(h >> 19);
+        int t = 0;
+        if (i == 0 && td.first_in >= 0) { inflow.x += first.x; inflow.y += first.y; t = 1; }
+        for (; t < nlate; ++t) {
+            const uint32_t w = st.word(wi + t);
+            if (active) {
+                const double2 v = ld_row(Ob + (size_t)(w & ~INW_ROW) * ld);
+                inflow.x += v.x; inflow.y += v.y;
             }
         }
+        wi += nlate;
+        double2 on, it;
+        on.x = al * inflow.x + b.x;
+        on.y = al * inflow.y + b.y;
+        it.x = inflow.x + side.x;
+        it.y = inflow.y + side.y;
+        if (active) { st_row(Ir + (size_t)i * ld, it); st_row(Or + (size_t)i * ld, on); }
+        o = on;
+        record<REC>(a, td.begin + i, s, col, on);
     }
+    cp_async_wait_all();
 }
 
 // Prepares the dataflow runtime for one launch: dependency counters and the ready queue seeded
@@ -315,7 +334,7 @@ __global__ void __launch_bounds__(256) dataflow_init_kernel(const InitArgs a)
     }
 }
 
-template <bool HAS_F, bool HAS_W, bool REC, bool WK>
+template <bool HAS_F, bool HAS_W, bool REC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
 route_dataflow_kernel(const RouteArgs a)
 {
@@ -413,12 +432,12 @@ route_dataflow_kernel(const RouteArgs a)
             sc.wm0 = make_double2(si.w0 * __ldg(m0 + c0), si.w0 * __ldg(m0 + c1));
             sc.wm1 = make_double2(si.w1 * __ldg(m1 + c0), si.w1 * __ldg(m1 + c1));
         }
-        cp_async_wait_all();
+        cp_async_commit();                              // group 0 of this task: the staged metadata
         __syncwarp();
-
-        if (td.kind == TASK_CHAIN) run_chain<REC, WK>(a, td, st, s, col, active);
-        else if (td.kind == TASK_PRE) run_pre<HAS_F, HAS_W, WK>(a, td, st, col, active, sc);
-        else run_pocket<HAS_F, HAS_W, REC, WK>(a, td, st, s, col, active, scratch, sc);
+        const unsigned ring = sbase + a.off_ring + lane * 16u;
+        if (td.kind == TASK_CHAIN) run_chain<REC>(a, td, st, s, col, active, ring);
+        else if (td.kind == TASK_PRE) run_pre<HAS_F, HAS_W>(a, td, st, col, active, sc, ring);
+        else run_pocket<HAS_F, HAS_W, REC>(a, td, st, s, col, active, scratch, sc, ring);
 
         // ---- completion: re-arm, then notify dependants with release atomics -----------------
         unsigned long long t_comp = 0;
@@ -604,15 +623,9 @@ cudaError_t launch_route_dataflow(const RouteArgs& a, int num_sms, cudaStream_t 
     const size_t smem = (size_t)kWarpsPerCta * a.smem_per_warp;
     void (*kern)(const RouteArgs) = nullptr;
     const bool f = a.F != nullptr, w = a.Wmul != nullptr, r = a.rec_slot != nullptr;
-    if (a.weak_rows) {
-        if (!f) kern = r ? route_dataflow_kernel<false, false, true, true> : route_dataflow_kernel<false, false, false, true>;
-        else if (!w) kern = r ? route_dataflow_kernel<true, false, true, true> : route_dataflow_kernel<true, false, false, true>;
-        else kern = r ? route_dataflow_kernel<true, true, true, true> : route_dataflow_kernel<true, true, false, true>;
-    } else {
-        if (!f) kern = r ? route_dataflow_kernel<false, false, true, false> : route_dataflow_kernel<false, false, false, false>;
-        else if (!w) kern = r ? route_dataflow_kernel<true, false, true, false> : route_dataflow_kernel<true, false, false, false>;
-        else kern = r ? route_dataflow_kernel<true, true, true, false> : route_dataflow_kernel<true, true, false, false>;
-    }
+    if (!f) kern = r ? route_dataflow_kernel<false, false, true> : route_dataflow_kernel<false, false, false>;
+    else if (!w) kern = r ? route_dataflow_kernel<true, false, true> : route_dataflow_kernel<true, false, false>;
+    else kern = r ? route_dataflow_kernel<true, true, true> : route_dataflow_kernel<true, true, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;

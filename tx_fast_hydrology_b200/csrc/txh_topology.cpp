@@ -415,6 +415,8 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
             }
             for (int32_t c : next[order[k]]) notify.push_back(rank[c]);
             td.n_words = (int32_t)U.ins.size();
+            td.first_in = -1;
+            if (U.kind == TASK_CHAIN && (hdr[td.begin] >> 19) > 0) td.first_in = (int32_t)(inw[td.in_off] & ~INW_ROW);
             max_len = std::max(max_len, td.len);
             td.need0 = (int32_t)U.A.size();
             td.need = (int32_t)(U.A.size() + U.B.size());

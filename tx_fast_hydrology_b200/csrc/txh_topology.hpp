@@ -71,7 +71,8 @@ struct TaskDesc {
     int32_t need;      // |A(T)| + |B(T)|  re-arm value after each completed step
     int32_t kind;      // TASK_POCKET / TASK_PRE / TASK_CHAIN
     int32_t n_words;   // input words of this task
-    int32_t pad_[2];
+    int32_t first_in;  // CHAIN: row feeding the first reach (its first late input), else -1
+    int32_t pad_;
 };
 
 struct Schedule {
