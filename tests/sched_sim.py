@@ -4,12 +4,12 @@ Executes the very descriptor arrays the routing kernel consumes (`txh_get_schedu
 under the kernel's dataflow protocol -- pending counters, re-arm on completion,
 same-step / next-step notifications, ready set -- with tasks picked in a seeded
 random order, so that both the descriptors and the protocol's invariants are
-checked without a GPU.  Arithmetic follows the kernel's (PRE / CHAIN / POCKET).
+checked without a GPU.  Arithmetic follows the kernel's (POCKET / PRE / LINK / FIX).
 """
 import numpy as np
 
 ROW = 0x80000000
-POCKET, PRE, CHAIN = 0, 1, 2
+POCKET, PRE, LINK, FIX = 0, 1, 2, 3
 
 
 def simulate(sched, coef, O, I, q_of_step, nsteps, seed=0, order="random"):
@@ -23,6 +23,10 @@ def simulate(sched, coef, O, I, q_of_step, nsteps, seed=0, order="random"):
     ready = [k for k in range(nt) if pending[k] == 0]
     running_guard = np.zeros(nt, dtype=bool)
     scratch = np.full(32, np.nan)
+    # prefix product of alpha along each segment (rows whose header carries the continue bit)
+    cumA = np.empty(O.size)
+    for p in range(O.size):
+        cumA[p] = cumA[p - 1] * coef[p][0] if (p > 0 and (int(hdr[p]) & 1)) else coef[p][0]
     executed = 0
     while ready:
         if order == "random":
@@ -31,7 +35,7 @@ def simulate(sched, coef, O, I, q_of_step, nsteps, seed=0, order="random"):
             k = ready.pop()
         else:
             k = ready.pop(0)
-        begin, ln, in_off, nfy_off, n_same, n_next, need0, need, kind = (int(x) for x in tasks[k, :9])
+        begin, ln, in_off, nfy_off, n_same, n_next, need0, need, kind, nwords = (int(x) for x in tasks[k, :10])
         s = int(stepno[k])
         assert s < nsteps and pending[k] == 0 and not running_guard[k]
         running_guard[k] = True
@@ -55,6 +59,7 @@ def simulate(sched, coef, O, I, q_of_step, nsteps, seed=0, order="random"):
                     scratch[sl - 1] = on
                 acc = on
         elif kind == PRE:
+            B = 0.0
             for p in range(begin, begin + ln):
                 h = int(hdr[p]); side = 0.0
                 for _ in range((h >> 6) & 0x1fff):
@@ -62,19 +67,34 @@ def simulate(sched, coef, O, I, q_of_step, nsteps, seed=0, order="random"):
                     assert x & ROW
                     side += O[x & 0x7fffffff]
                 a, b, c, g = coef[p]
-                bb = a * side + (b * I[p] + c * O[p] + g * q[p])
-                I[p] = side; O[p] = bb
-        else:
+                infl = side + (B if (h & 1) else 0.0)
+                B = a * infl + (b * I[p] + c * O[p] + g * q[p])
+                I[p] = side; O[p] = B
+        elif kind == LINK:
             o = 0.0
-            for p in range(begin, begin + ln):
-                h = int(hdr[p]); infl = o if (h & 1) else 0.0
-                for _ in range(h >> 19):
+            for _ in range(ln):                      # one record per segment of the path
+                last = int(inw[w]) & 0x7fffffff; nl = int(inw[w + 1]); w += 2
+                oin = o
+                for _ in range(nl):
                     x = int(inw[w]); w += 1
                     assert x & ROW
-                    infl += O[x & 0x7fffffff]
-                on = coef[p][0] * infl + O[p]
-                I[p] = infl + I[p]; O[p] = on
-                o = on
+                    oin += O[x & 0x7fffffff]
+                o = cumA[last] * oin + O[last]
+                O[last] = o
+        else:
+            oin = 0.0
+            for _ in range(nwords):
+                x = int(inw[w]); w += 1
+                assert x & ROW
+                oin += O[x & 0x7fffffff]
+            op = oin
+            for p in range(begin, begin + ln):
+                on = O[p]
+                if p + 1 < begin + ln:
+                    on = cumA[p] * oin + O[p]
+                    O[p] = on
+                I[p] = op + I[p]
+                op = on
         executed += 1
         # completion protocol (route_dataflow_kernel)
         assert pending[k] == 0, "an event for the next step arrived before the task re-armed"

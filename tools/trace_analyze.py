@@ -18,8 +18,8 @@ def main(path):
     t0 = t_pop[t_pop > 0].min()
     span = (t_end.max() - t0) / 1e3
     print(f"pairs={pairs} steps={ns} tasks={ntasks} nmb={nmb}  span={span:.1f} us  ({span / ns:.1f} us/step)")
-    names = {0: "POCKET", 1: "PRE", 2: "CHAIN"}
-    for k in (0, 1, 2):
+    names = {0: "POCKET", 1: "PRE", 2: "LINK", 3: "FIX"}
+    for k in (0, 1, 2, 3):
         m = kind == k
         if not m.any():
             continue
@@ -35,7 +35,7 @@ def main(path):
     s = 0
     m = np.flatnonzero(kind[s] == 2)
     order = m[np.argsort(t_end[s][m])]
-    print(" last CHAIN tasks of step 0 (pair, begin, body_end, end) us:")
+    print(" last LINK tasks of step 0 (pair, begin, body_end, end) us:")
     for p in order[-12:]:
         print(f"   {p:6d} {(t_beg[s][p] - t0) / 1e3:9.2f} {(t_cmp[s][p] - t0) / 1e3:9.2f} {(t_end[s][p] - t0) / 1e3:9.2f}")
 

@@ -47,7 +47,7 @@ int upload(T** dptr, const std::vector<T>& v)
 struct txh_net {
     Topology topo;
     Schedule sched;
-    std::vector<double> coef_host;      // [n][4] schedule order
+    std::vector<double> coef_host;      // [n][4] schedule order, then cumA [n], then linkA [n_link]
     bool have_coef = false, coef_dirty = false;
     // device side
     bool dev_ready = false;
@@ -58,7 +58,7 @@ struct txh_net {
             *d_reach_of_pos = nullptr, *d_pos_of_reach = nullptr;
     uint32_t *d_hdr = nullptr, *d_inw = nullptr;
     uint8_t* d_outlet = nullptr;
-    double* d_coef = nullptr;
+    double* d_coef = nullptr;           // same layout as coef_host
     double* d_qtmp = nullptr;           // [n] schedule-order scratch for txh_route_step
     int32_t* d_pending = nullptr; size_t pairs_cap = 0;
     unsigned long long* d_queue = nullptr; size_t queue_cap = 0;
@@ -106,7 +106,7 @@ int ensure_device(txh_net* net)
     if ((rc = upload(&net->d_reach_of_pos, s.reach_of_pos))) return rc;
     if ((rc = upload(&net->d_pos_of_reach, s.pos_of_reach))) return rc;
     if ((rc = upload(&net->d_outlet, s.is_outlet_pos))) return rc;
-    CU(cudaMalloc((void**)&net->d_coef, sizeof(double) * 4 * net->topo.n));
+    CU(cudaMalloc((void**)&net->d_coef, sizeof(double) * (5 * net->topo.n + net->sched.link_last.size() + 1)));
     CU(cudaMalloc((void**)&net->d_qtmp, sizeof(double) * net->topo.n));
     CU(cudaMalloc((void**)&net->d_qctl, 64));
     net->d_status = reinterpret_cast<int32_t*>(net->d_qctl + 4);
@@ -130,7 +130,7 @@ int ensure_coef(txh_net* net, cudaStream_t st)
     if (!net->have_coef) return fail(TXH_E_STATE, "coefficients not set: call txh_compute_coeffs or txh_set_coeffs first");
     if (net->coef_dirty) {
         // synchronous on purpose: coef_host may be rewritten by the caller right after
-        CU(cudaMemcpyAsync(net->d_coef, net->coef_host.data(), sizeof(double) * 4 * net->topo.n,
+        CU(cudaMemcpyAsync(net->d_coef, net->coef_host.data(), sizeof(double) * net->coef_host.size(),
                            cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));
         net->coef_dirty = false;
@@ -180,7 +180,8 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
         CU(launch_dataflow_init(ia, st));
         RouteArgs a{};
         a.tasks = net->d_tasks; a.notify = net->d_notify; a.hdr = net->d_hdr; a.inw = net->d_inw;
-        a.coef = net->d_coef; a.O = O; a.I = I; a.F = F; a.steps = d_steps + s0; a.Wmul = W;
+        a.coef = net->d_coef; a.cumA = net->d_coef + 4 * net->topo.n; a.linkA = net->d_coef + 5 * net->topo.n;
+        a.O = O; a.I = I; a.F = F; a.steps = d_steps + s0; a.Wmul = W;
         a.rec_slot = rec_slot;
         a.rec_out = rec_out;
         if (rec_slot && s0 > 0) {
@@ -345,12 +346,17 @@ int txh_set_coeffs(txh_net* net, const double* al, const double* be, const doubl
 {
     if (!net || !al || !be || !ch || !ga) return fail(TXH_E_INVALID, "null argument");
     const int64_t n = net->topo.n;
-    net->coef_host.resize(4 * n);
+    const Schedule& sc = net->sched;
+    net->coef_host.resize(5 * n + sc.link_last.size());
+    double* cum = net->coef_host.data() + 4 * n;
     for (int64_t k = 0; k < n; ++k) {
-        const int32_t j = net->sched.reach_of_pos[k];
+        const int32_t j = sc.reach_of_pos[k];
         net->coef_host[4 * k] = al[j]; net->coef_host[4 * k + 1] = be[j];
         net->coef_host[4 * k + 2] = ch[j]; net->coef_host[4 * k + 3] = ga[j];
+        // prefix product of alpha along the segment (rows whose header carries the continue bit)
+        cum[k] = (k > 0 && (sc.hdr[k] & HDR_ACC)) ? cum[k - 1] * al[j] : al[j];
     }
+    for (size_t e = 0; e < sc.link_last.size(); ++e) net->coef_host[5 * n + e] = cum[sc.link_last[e]];
     net->have_coef = true; net->coef_dirty = true;
     return TXH_OK;
 }

@@ -24,6 +24,8 @@ struct RouteArgs {
     const uint32_t* hdr;
     const uint32_t* inw;
     const double* coef;                   // [n][4] = alpha, beta, chi, gamma (schedule order)
+    const double* cumA;                   // [n] prefix product of alpha from the first reach of the segment
+    const double* linkA;                  // [link entries] cumA at the last reach of each segment
     double* O;
     double* I;
     const double* F;                      // [R][n] schedule order, or nullptr

@@ -192,10 +192,10 @@ __device__ __forceinline__ void run_pocket(const RouteArgs& a, const TaskDesc& t
     cp_async_wait_all();
 }
 
-// PRE: every reach of a spine segment independently -- gathers the side inflow from the pocket
-// roots, folds the old state and the forcing into  b = alpha*side + beta*i_prev + chi*o_prev + gamma*q
-// and parks (side, b) in the segment's own I / O rows for the CHAIN task.  The first side row of
-// each reach travels through the ring with the state rows.
+// PRE: one spine segment -- gathers the side inflow from the pocket roots, folds the old state
+// and the forcing into r = beta*i_prev + chi*o_prev + gamma*q, and runs the segment's recurrence
+// with no flow entering it:  B_k = alpha_k (B_{k-1} + side_k) + r_k.  (side_k, B_k) are parked in the
+// segment's own I / O rows.  The first side row of each reach travels through the ring.
 template <bool HAS_F, bool HAS_W>
 __device__ __forceinline__ void run_pre(const RouteArgs& a, const TaskDesc& td, const Stage& st, int col, bool active,
                                         const StepCtx& sc, unsigned ring)
@@ -222,6 +222,7 @@ __device__ __forceinline__ void run_pre(const RouteArgs& a, const TaskDesc& td, 
         cp_async_commit();
     }
     int wi = 0, sl = 0;
+    double2 B = make_double2(0.0, 0.0);
     for (int i = 0; i < len; ++i) {
         cp_async_wait_group<kRingPre - 1>();
         const uint32_t h = st.h(i);
@@ -248,20 +249,86 @@ __device__ __forceinline__ void run_pre(const RouteArgs& a, const TaskDesc& td, 
         wi += nin;
         const double al = st.al(i), be = st.be(i), ch = st.ch(i), ga = st.ga(i);
         const double2 q = forcing_q<HAS_F, HAS_W>(sc, st, i);
-        double2 b;
-        b.x = al * side.x + (be * io.x + ch * oo.x + ga * q.x);
-        b.y = al * side.y + (be * io.y + ch * oo.y + ga * q.y);
-        if (active) { st_row(Ir + (size_t)i * ld, side); st_row(Or + (size_t)i * ld, b); }
+        double2 inflow = side;
+        if (h & HDR_ACC) { inflow.x += B.x; inflow.y += B.y; }
+        B.x = al * inflow.x + (be * io.x + ch * oo.x + ga * q.x);
+        B.y = al * inflow.y + (be * io.y + ch * oo.y + ga * q.y);
+        if (active) { st_row(Ir + (size_t)i * ld, side); st_row(Or + (size_t)i * ld, B); }
     }
     cp_async_wait_all();
 }
 
-// CHAIN: the first-order recurrence down the segment,  o_k = alpha_k * (o_{k-1} + late_k) + b_k,
-// i_k = o_{k-1} + late_k + side_k, where late_k are outflows of other spine segments (the
-// upstream segment of the same path, long tributaries).  One FMA per reach on the critical path.
+// LINK: one long path.  Walks its segments in order; the flow entering a segment is the previous
+// segment's outflow plus the outlets of the long tributaries joining there, and the segment's
+// outflow is  out = A_last * o_in + B_last  (B_last parked by PRE in the segment's last O row,
+// A_last staged from linkA).  Writes the final outflow of every segment's last reach.
 template <bool REC>
-__device__ __forceinline__ void run_chain(const RouteArgs& a, const TaskDesc& td, const Stage& st, int s, int col,
-                                          bool active, unsigned ring)
+__device__ __forceinline__ void run_link(const RouteArgs& a, const TaskDesc& td, const Stage& st, int s, int col,
+                                         bool active, unsigned ring)
+{
+    const int ld = a.ld, len = td.len;
+    const int ccol = active ? col : 0;
+    double* Ob = a.O + ccol;
+    const unsigned ringG = ring + kRing * 512u;
+    cp_async_wait_all();                                // records and A_last come from the staging area
+    __syncwarp();
+    int wq = 0;
+#pragma unroll
+    for (int j = 0; j < kRing; ++j) {
+        if (j < len) {
+            const uint32_t last = st.word(wq) & ~INW_ROW;
+            const int nl = (int)st.word(wq + 1);
+            if (active) {
+                cp_row(ring + j * 512u, Ob + (size_t)last * ld);
+                if (nl > 0) cp_row(ringG + j * 512u, Ob + (size_t)(st.word(wq + 2) & ~INW_ROW) * ld);
+            }
+            wq += 2 + nl;
+        }
+        cp_async_commit();
+    }
+    int wi = 0, sl = 0;
+    double2 o = make_double2(0.0, 0.0);
+    for (int j = 0; j < len; ++j) {
+        cp_async_wait_group<kRing - 1>();
+        const uint32_t last = st.word(wi) & ~INW_ROW;
+        const int nl = (int)st.word(wi + 1);
+        const double2 B = lds_row(ring + sl * 512u);
+        double2 oin = o;
+        if (nl > 0) { const double2 v = lds_row(ringG + sl * 512u); oin.x += v.x; oin.y += v.y; }
+        for (int t = 1; t < nl; ++t) {
+            if (active) {
+                const double2 v = ld_row(Ob + (size_t)(st.word(wi + 2 + t) & ~INW_ROW) * ld);
+                oin.x += v.x; oin.y += v.y;
+            }
+        }
+        wi += 2 + nl;
+        if (j + kRing < len) {
+            const uint32_t lastp = st.word(wq) & ~INW_ROW;
+            const int np = (int)st.word(wq + 1);
+            if (active) {
+                cp_row(ring + sl * 512u, Ob + (size_t)lastp * ld);
+                if (np > 0) cp_row(ringG + sl * 512u, Ob + (size_t)(st.word(wq + 2) & ~INW_ROW) * ld);
+            }
+            wq += 2 + np;
+        }
+        cp_async_commit();
+        sl = sl + 1 == kRing ? 0 : sl + 1;
+        const double A = lds_f64(st.f0 + 8u * j);
+        o.x = A * oin.x + B.x;
+        o.y = A * oin.y + B.y;
+        if (active) st_row(Ob + (size_t)last * ld, o);
+        record<REC>(a, (int)last, s, col, o);
+    }
+    cp_async_wait_all();
+}
+
+// FIX: one spine segment, every reach independent:  o_k = B_k + A_k * o_in,  i_k = o_{k-1} + side_k,
+// with o_in the flow entering the segment (rows listed in the task's stream) and A_k the prefix
+// product of alpha from the segment's first reach (staged from cumA).  The last row already holds
+// its final outflow (LINK).
+template <bool REC>
+__device__ __forceinline__ void run_fix(const RouteArgs& a, const TaskDesc& td, const Stage& st, int s, int col,
+                                        bool active, unsigned ring)
 {
     const int ld = a.ld, len = td.len;
     const int ccol = active ? col : 0;
@@ -269,9 +336,6 @@ __device__ __forceinline__ void run_chain(const RouteArgs& a, const TaskDesc& td
     double* Or = Ob + (size_t)td.begin * ld;
     double* Ir = a.I + ccol + (size_t)td.begin * ld;
     const unsigned ringO = ring + kRing * 512u;
-    // the upstream segment's outflow (first late input of the first reach) is fetched before anything else
-    double2 first = make_double2(0.0, 0.0);
-    if (td.first_in >= 0 && active) first = ld_row(Ob + (size_t)td.first_in * ld);
 #pragma unroll
     for (int j = 0; j < kRing; ++j) {
         if (active && j < len) { cp_row(ring + j * 512u, Ir + (size_t)j * ld); cp_row(ringO + j * 512u, Or + (size_t)j * ld); }
@@ -279,39 +343,36 @@ __device__ __forceinline__ void run_chain(const RouteArgs& a, const TaskDesc& td
     }
     cp_async_wait_group<kRing>();
     __syncwarp();
-    int wi = 0, sl = 0;
-    double2 o = make_double2(0.0, 0.0);
+    double2 oin = make_double2(0.0, 0.0);
+    for (int t = 0; t < td.n_words; ++t) {
+        if (active) {
+            const double2 v = ld_row(Ob + (size_t)(st.word(t) & ~INW_ROW) * ld);
+            oin.x += v.x; oin.y += v.y;
+        }
+    }
+    int sl = 0;
+    double2 op = oin;
     for (int i = 0; i < len; ++i) {
         cp_async_wait_group<kRing - 1>();
-        const double2 side = lds_row(ring + sl * 512u), b = lds_row(ringO + sl * 512u);
+        const double2 side = lds_row(ring + sl * 512u), B = lds_row(ringO + sl * 512u);
         if (active && i + kRing < len) {
             cp_row(ring + sl * 512u, Ir + (size_t)(i + kRing) * ld);
             cp_row(ringO + sl * 512u, Or + (size_t)(i + kRing) * ld);
         }
         cp_async_commit();
         sl = sl + 1 == kRing ? 0 : sl + 1;
-        const uint32_t h = st.h(i);
-        const double al = st.al(i);
-        double2 inflow = (h & HDR_ACC) ? o : make_double2(0.0, 0.0);
-        const int nlate = (int)(h >> 19);
-        int t = 0;
-        if (i == 0 && td.first_in >= 0) { inflow.x += first.x; inflow.y += first.y; t = 1; }
-        for (; t < nlate; ++t) {
-            const uint32_t w = st.word(wi + t);
-            if (active) {
-                const double2 v = ld_row(Ob + (size_t)(w & ~INW_ROW) * ld);
-                inflow.x += v.x; inflow.y += v.y;
-            }
+        double2 it, on = B;
+        it.x = op.x + side.x;
+        it.y = op.y + side.y;
+        if (i + 1 < len) {
+            const double A = lds_f64(st.f0 + 8u * i);
+            on.x = A * oin.x + B.x;
+            on.y = A * oin.y + B.y;
+            if (active) st_row(Or + (size_t)i * ld, on);
+            record<REC>(a, td.begin + i, s, col, on);
         }
-        wi += nlate;
-        double2 on, it;
-        on.x = al * inflow.x + b.x;
-        on.y = al * inflow.y + b.y;
-        it.x = inflow.x + side.x;
-        it.y = inflow.y + side.y;
-        if (active) { st_row(Ir + (size_t)i * ld, it); st_row(Or + (size_t)i * ld, on); }
-        o = on;
-        record<REC>(a, td.begin + i, s, col, on);
+        if (active) st_row(Ir + (size_t)i * ld, it);
+        op = on;
     }
     cp_async_wait_all();
 }
@@ -402,29 +463,36 @@ route_dataflow_kernel(const RouteArgs a)
         Stage st;
         st.coef = sbase + a.off_coef; st.f0 = sbase + a.off_f0; st.f1 = sbase + a.off_f1;
         st.hdr = sbase + a.off_hdr; st.inw = sbase + a.off_inw; st.inw_g = nullptr;
+        const bool walks = td.kind == TASK_POCKET || td.kind == TASK_PRE;     // evaluates the Muskingum update itself
         {
-            const double* gc = a.coef + 4 * (size_t)td.begin;
-            for (int i = lane; i < 2 * td.len; i += 32) cp_async16(wbase + a.off_coef + 16 * i, gc + 2 * i);
-            for (int i = lane; i < td.len; i += 32) cp_async4(wbase + a.off_hdr + 4 * i, a.hdr + td.begin + i);
             if (td.n_words <= a.max_words)
                 for (int i = lane; i < td.n_words; i += 32) cp_async4(wbase + a.off_inw + 4 * i, a.inw + td.in_off + i);
             else
                 st.inw_g = a.inw + td.in_off;
-            if (HAS_F && td.kind != TASK_CHAIN) {
-                si = a.steps[s];
-                const double* F0 = a.F + (size_t)si.r0 * a.n + td.begin;
-                const double* F1 = a.F + (size_t)si.r1 * a.n + td.begin;
-                for (int i = lane; i < td.len; i += 32) {
-                    cp_async8(wbase + a.off_f0 + 8 * i, F0 + i);
-                    cp_async8(wbase + a.off_f1 + 8 * i, F1 + i);
+            if (walks) {
+                const double* gc = a.coef + 4 * (size_t)td.begin;
+                for (int i = lane; i < 2 * td.len; i += 32) cp_async16(wbase + a.off_coef + 16 * i, gc + 2 * i);
+                for (int i = lane; i < td.len; i += 32) cp_async4(wbase + a.off_hdr + 4 * i, a.hdr + td.begin + i);
+                if (HAS_F) {
+                    si = a.steps[s];
+                    const double* F0 = a.F + (size_t)si.r0 * a.n + td.begin;
+                    const double* F1 = a.F + (size_t)si.r1 * a.n + td.begin;
+                    for (int i = lane; i < td.len; i += 32) {
+                        cp_async8(wbase + a.off_f0 + 8 * i, F0 + i);
+                        cp_async8(wbase + a.off_f1 + 8 * i, F1 + i);
+                    }
                 }
+            } else {
+                // prefix products of alpha: per reach of the segment (FIX) / per segment of the path (LINK)
+                const double* ga = (td.kind == TASK_FIX ? a.cumA : a.linkA) + td.begin;
+                for (int i = lane; i < td.len; i += 32) cp_async8(wbase + a.off_f0 + 8 * i, ga + i);
             }
         }
         const int col = mb * kMemberBlock + lane * 2;
         const bool active = col < a.ld;
         StepCtx sc;
         sc.w0 = si.w0; sc.w1 = si.w1; sc.wm0 = sc.wm1 = make_double2(0.0, 0.0);
-        if (HAS_F && HAS_W && td.kind != TASK_CHAIN) {
+        if (HAS_F && HAS_W && walks) {
             // member m sees  (w0*mul[r0][m])*F[r0] + (w1*mul[r1][m])*F[r1]
             const int c0 = min(col, a.wm_ld - 1), c1 = min(col + 1, a.wm_ld - 1);
             const double* m0 = a.Wmul + (size_t)si.r0 * a.wm_ld;
@@ -433,11 +501,11 @@ route_dataflow_kernel(const RouteArgs a)
             sc.wm1 = make_double2(si.w1 * __ldg(m1 + c0), si.w1 * __ldg(m1 + c1));
         }
         cp_async_commit();                              // group 0 of this task: the staged metadata
-        __syncwarp();
         const unsigned ring = sbase + a.off_ring + lane * 16u;
-        if (td.kind == TASK_CHAIN) run_chain<REC>(a, td, st, s, col, active, ring);
+        if (td.kind == TASK_POCKET) run_pocket<HAS_F, HAS_W, REC>(a, td, st, s, col, active, scratch, sc, ring);
         else if (td.kind == TASK_PRE) run_pre<HAS_F, HAS_W>(a, td, st, col, active, sc, ring);
-        else run_pocket<HAS_F, HAS_W, REC>(a, td, st, s, col, active, scratch, sc, ring);
+        else if (td.kind == TASK_LINK) run_link<REC>(a, td, st, s, col, active, ring);
+        else run_fix<REC>(a, td, st, s, col, active, ring);
 
         // ---- completion: re-arm, then notify dependants with release atomics -----------------
         unsigned long long t_comp = 0;
@@ -462,8 +530,8 @@ route_dataflow_kernel(const RouteArgs a)
                 // entry of the dependant: same-step targets run step s, next-step targets step s + 1
                 const long long e = ((long long)(d < td.n_same ? s : s + 1) << 32) | (long long)(unsigned)(tgt + 1);
                 if (next_entry == 0) {
-                    // keep one ready dependant for this warp (a CHAIN if there is one): no queue round trip
-                    const bool is_chain = ready && a.tasks[tgt / nmb].kind == TASK_CHAIN;
+                    // keep one ready dependant for this warp (a LINK if there is one): no queue round trip
+                    const bool is_chain = ready && a.tasks[tgt / nmb].kind == TASK_LINK;
                     const unsigned cm = __ballot_sync(0xffffffffu, is_chain);
                     const int keep = __ffs(cm ? cm : mask) - 1;
                     next_entry = __shfl_sync(0xffffffffu, e, keep);

@@ -120,8 +120,9 @@ bool Topology::build(int64_t n_, const int64_t* e, std::string& err)
 namespace {
 
 struct Unit {
-    int32_t grp;                      // row group (contiguous rows in the final layout)
+    int32_t grp;                      // row group (contiguous rows in the final layout), -1 for LINK
     int32_t kind;
+    int32_t link_off, link_len;       // LINK: its entries in link_last
     std::vector<uint32_t> ins;        // input words; ROW entries hold REACH ids until positions are known
     std::vector<int32_t> A, B;        // same-step / previous-step dependencies (unit ids)
 };
@@ -150,47 +151,77 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
     std::vector<uint32_t> rhdr;
     rows.reserve(n); rhdr.reserve(n);
     std::vector<Unit> units;
-    std::vector<int32_t> final_unit(n, -1);   // unit that writes the final value of the reach's rows
+    std::vector<int32_t> final_unit(n, -1);   // pocket reaches: their task; last reach of a segment: the path's LINK
     std::vector<int32_t> pre_unit(n, -1);     // spine reaches: the PRE unit of their segment
+    std::vector<int32_t> link_reach;          // per LINK entry: last reach of the segment
+    auto mk = [](int32_t grp, int32_t kind) { Unit u; u.grp = grp; u.kind = kind; u.link_off = u.link_len = 0; return u; };
 
-    // ---- spines: long paths cut into pure-chain segments, each a PRE and a CHAIN task ------
+    // ---- spines: long paths cut into segments (PRE + FIX each) and one LINK per path ---------
     {
         const int32_t npaths = (int32_t)t.path_len.size();
         std::vector<int32_t> poff(npaths + 1, 0);
         for (int32_t q = 0; q < npaths; ++q) poff[q + 1] = poff[q] + t.path_len[q];
         std::vector<int32_t> member(n);
         for (int64_t j = 0; j < n; ++j) member[poff[t.path_id[j]] + t.path_pos[j]] = (int32_t)j;
+        std::vector<int32_t> cuts;
         for (int32_t q = 0; q < npaths; ++q) {
             const int32_t len = t.path_len[q];
             if (len < p.long_path_min) continue;
-            const int32_t nseg = (len + p.spine_cap - 1) / p.spine_cap;
-            const int32_t seglen = (len + nseg - 1) / nseg;
-            for (int32_t s0 = 0; s0 < len; s0 += seglen) {
-                const int32_t s1 = std::min(len, s0 + seglen);
+            // a reach joined by another long path starts a segment: its inflow is only known to LINK
+            std::vector<int32_t> forced{0};
+            for (int32_t k = 1; k < len; ++k) {
+                const int32_t j = member[poff[q] + k];
+                for (int32_t c = t.child_off[j]; c < t.child_off[j + 1]; ++c)
+                    if (t.child[c] != t.main_child[j] && is_long[t.child[c]]) { forced.push_back(k); break; }
+            }
+            forced.push_back(len);
+            cuts.clear();
+            for (size_t f = 0; f + 1 < forced.size(); ++f) {
+                const int32_t a0 = forced[f], a1 = forced[f + 1];
+                const int32_t nseg = (a1 - a0 + p.spine_cap - 1) / p.spine_cap;
+                const int32_t seglen = (a1 - a0 + nseg - 1) / nseg;
+                for (int32_t s0 = a0; s0 < a1; s0 += seglen) cuts.push_back(s0);
+            }
+            cuts.push_back(len);
+            const int32_t link_u = (int32_t)units.size();
+            units.push_back(mk(-1, TASK_LINK));
+            units[link_u].link_off = (int32_t)link_reach.size();
+            units[link_u].link_len = (int32_t)cuts.size() - 1;
+            for (size_t cseg = 0; cseg + 1 < cuts.size(); ++cseg) {
+                const int32_t s0 = cuts[cseg], s1 = cuts[cseg + 1];
                 const int32_t g = (int32_t)g_begin.size();
                 g_begin.push_back((int32_t)rows.size()); g_len.push_back(s1 - s0);
                 const int32_t up = (int32_t)units.size();
-                units.push_back(Unit{g, TASK_PRE, {}, {}, {}});
-                units.push_back(Unit{g, TASK_CHAIN, {}, {}, {}});
+                units.push_back(mk(g, TASK_PRE));
+                units.push_back(mk(g, TASK_FIX));
+                std::vector<uint32_t> late;
                 for (int32_t k = s0; k < s1; ++k) {
                     const int32_t j = member[poff[q] + k];
-                    final_unit[j] = up + 1; pre_unit[j] = up;
-                    uint32_t h = 0, n_early = 0, n_late = 0;
+                    pre_unit[j] = up;
+                    uint32_t h = 0, n_early = 0, n_first = 0;
                     const int32_t m = t.main_child[j];
-                    if (m >= 0) {
-                        if (k > s0) h |= HDR_ACC;
-                        else { units[up + 1].ins.push_back(INW_ROW | (uint32_t)m); ++n_late; }
-                    }
+                    if (k > s0) h |= HDR_ACC;
+                    else if (m >= 0) { units[up + 1].ins.push_back(INW_ROW | (uint32_t)m); ++n_first; }
                     for (int32_t c = t.child_off[j]; c < t.child_off[j + 1]; ++c) {
                         const int32_t ch = t.child[c];
                         if (ch == m) continue;
-                        if (is_long[ch]) { units[up + 1].ins.push_back(INW_ROW | (uint32_t)ch); ++n_late; }
-                        else { units[up].ins.push_back(INW_ROW | (uint32_t)ch); ++n_early; }
+                        if (is_long[ch]) {
+                            if (k != s0) { err = "internal: long tributary inside a segment"; return false; }
+                            units[up + 1].ins.push_back(INW_ROW | (uint32_t)ch); ++n_first;
+                            late.push_back(INW_ROW | (uint32_t)ch);
+                        } else { units[up].ins.push_back(INW_ROW | (uint32_t)ch); ++n_early; }
                     }
-                    if (n_early >= (1u << 13) || n_late >= (1u << 13)) { err = "confluence too wide"; return false; }
+                    if (n_early >= (1u << 13) || n_first >= (1u << 13)) { err = "confluence too wide"; return false; }
                     rows.push_back(j);
-                    rhdr.push_back(h | (n_early << 6) | (n_late << 19));
+                    rhdr.push_back(h | (n_early << 6) | (n_first << 19));
                 }
+                const int32_t last = member[poff[q] + s1 - 1];
+                final_unit[last] = link_u;
+                link_reach.push_back(last);
+                Unit& L = units[link_u];
+                L.ins.push_back(INW_ROW | (uint32_t)last);
+                L.ins.push_back((uint32_t)late.size());
+                L.ins.insert(L.ins.end(), late.begin(), late.end());
             }
         }
     }
@@ -301,7 +332,7 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
             if (!fits) {
                 cur = (int32_t)g_begin.size();
                 g_begin.push_back((int32_t)rows.size()); g_len.push_back(0);
-                units.push_back(Unit{cur, TASK_POCKET, {}, {}, {}});
+                units.push_back(mk(cur, TASK_POCKET));
                 cur_size = 0; cur_hi = hi;
             }
             reset_slots();
@@ -318,21 +349,41 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
     if ((int64_t)rows.size() != n) { err = "internal: schedule does not cover every reach"; return false; }
 
     // ---- dependencies ------------------------------------------------------------------------
+    // Who finalises a row at step s, and who is the first to overwrite it at step s+1:
+    //   pocket row           : its pocket task / the same task
+    //   last row of a segment: the path's LINK / the segment's PRE
+    // (other spine rows are only ever read by their own segment's tasks.)
     const int32_t nu = (int32_t)units.size();
+    // U reads row c (a pocket root or the last row of a segment) at step s
+    auto reads_row = [&](int32_t u, int32_t c) {
+        Unit& U = units[u];
+        if (pre_unit[c] < 0) {
+            const int32_t prod = final_unit[c];
+            if (units[prod].grp == U.grp) return;                          // a row of this task itself (slot fallback)
+            U.A.push_back(prod);
+            units[prod].B.push_back(u);                                    // the pocket rewrites the row next step
+        } else {
+            U.A.push_back(final_unit[c]);                                  // final once its path's LINK has run
+            units[pre_unit[c]].B.push_back(u);                             // ... rewritten by that segment's PRE
+        }
+    };
     for (int32_t u = 0; u < nu; ++u) {
         Unit& U = units[u];
         U.B.push_back(u);                                                  // self: one step in flight per task
-        if (U.kind == TASK_CHAIN) U.A.push_back(u - 1);                    // its own PRE (emitted just before)
-        if (U.kind == TASK_PRE) U.B.push_back(u + 1);                      // rows are rewritten: own CHAIN must be done
-        for (uint32_t w : U.ins) {
-            if (!(w & INW_ROW)) continue;
-            const int32_t c = (int32_t)(w & ~INW_ROW);
-            const int32_t prod = final_unit[c];
-            if (units[prod].grp == U.grp) continue;                        // a row of this task itself (slot fallback)
-            U.A.push_back(prod);
-            // U reads row c at step s: the unit that next overwrites it must wait for U
-            const int32_t writer = pre_unit[c] >= 0 ? pre_unit[c] : prod;
-            units[writer].B.push_back(u);
+        if (U.kind == TASK_PRE) U.B.push_back(u + 1);                      // rows are rewritten: own FIX must be done
+        if (U.kind == TASK_FIX)                                            // its path's LINK (implies its own PRE)
+            U.A.push_back(final_unit[rows[g_begin[U.grp] + g_len[U.grp] - 1]]);
+        if (U.kind == TASK_LINK) {
+            for (int32_t e = U.link_off; e < U.link_off + U.link_len; ++e) U.A.push_back(pre_unit[link_reach[e]]);
+            size_t w = 0;
+            while (w < U.ins.size()) {                                     // records: [last row][n_late][rows...]
+                const uint32_t nl = U.ins[w + 1];
+                w += 2;
+                for (uint32_t q = 0; q < nl; ++q, ++w) reads_row(u, (int32_t)(U.ins[w] & ~INW_ROW));
+            }
+        } else {
+            for (uint32_t x : U.ins)
+                if (x & INW_ROW) reads_row(u, (int32_t)(x & ~INW_ROW));
         }
     }
     for (Unit& U : units) { sort_unique(U.A); sort_unique(U.B); }
@@ -343,8 +394,9 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
     }
     // topological order over the A-edges, longest remaining critical path first
     auto cost = [&](int32_t u) -> int64_t {
+        if (units[u].kind == TASK_LINK) return 12 + 2 * units[u].link_len;
         const int32_t len = g_len[units[u].grp];
-        return units[u].kind == TASK_CHAIN ? 12 + len / 2 : 24 + len;
+        return units[u].kind == TASK_FIX ? 12 + len / 2 : 24 + len;
     };
     std::vector<int32_t> order0; order0.reserve(nu);
     {
@@ -389,7 +441,7 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
         int32_t pos = 0;
         for (int32_t k = 0; k < nu; ++k) {
             const int32_t g = units[order[k]].grp;
-            if (gpos[g] >= 0) continue;
+            if (g < 0 || gpos[g] >= 0) continue;
             gpos[g] = pos;
             for (int32_t e = g_begin[g]; e < g_begin[g] + g_len[g]; ++e, ++pos) {
                 pos_of_reach[rows[e]] = pos; reach_of_pos[pos] = rows[e]; hdr[pos] = rhdr[e];
@@ -397,10 +449,14 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
         }
         tasks.assign(nu, TaskDesc{});
         inw.clear(); notify.clear(); init_ready.clear(); max_len = 0;
+        link_last.resize(link_reach.size());
+        for (size_t e = 0; e < link_reach.size(); ++e) link_last[e] = pos_of_reach[link_reach[e]];
         for (int32_t k = 0; k < nu; ++k) {
             const Unit& U = units[order[k]];
             TaskDesc& td = tasks[k];
-            td.begin = gpos[U.grp]; td.len = g_len[U.grp]; td.kind = U.kind;
+            td.kind = U.kind;
+            if (U.kind == TASK_LINK) { td.begin = U.link_off; td.len = U.link_len; }
+            else { td.begin = gpos[U.grp]; td.len = g_len[U.grp]; }
             td.in_off = (int32_t)inw.size();
             for (uint32_t x : U.ins) {
                 if (x & INW_ROW) x = INW_ROW | (uint32_t)pos_of_reach[x & ~INW_ROW];
@@ -415,8 +471,6 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
             }
             for (int32_t c : next[order[k]]) notify.push_back(rank[c]);
             td.n_words = (int32_t)U.ins.size();
-            td.first_in = -1;
-            if (U.kind == TASK_CHAIN && (hdr[td.begin] >> 19) > 0) td.first_in = (int32_t)(inw[td.in_off] & ~INW_ROW);
             max_len = std::max(max_len, td.len);
             td.need0 = (int32_t)U.A.size();
             td.need = (int32_t)(U.A.size() + U.B.size());

@@ -48,31 +48,41 @@ struct SchedParams {
 //   pocket rows : bit 0      inflow starts from the running accumulator (previous reach's outflow)
 //                 bits 1..5  (scratch slot + 1) the outflow is also parked in, 0 = none
 //                 bits 6..31 number of input words that follow in the task's input stream
-//   spine rows  : bit 0      inflow includes the previous reach of the segment
+//   spine rows  : bit 0      not the first reach of its segment (the recurrence continues)
 //                 bits 6..18 number of EARLY inputs (rows of pocket roots; PRE task stream)
-//                 bits 19..31 number of LATE inputs (last rows of other spine segments; CHAIN stream)
+//                 bits 19..31 first row of a segment only: number of rows whose sum is the flow
+//                             entering the segment (last row of the upstream segment + outlets of
+//                             long tributaries; FIX task stream)
 // Input word: bit 31 set -> state row (position) to gather; else scratch slot id.
+// LINK stream, one record per segment of the path: [last row position][n_late][n_late rows].
 constexpr uint32_t HDR_ACC = 1u;
 constexpr uint32_t INW_ROW = 0x80000000u;
-constexpr int TASK_POCKET = 0, TASK_PRE = 1, TASK_CHAIN = 2;
+constexpr int TASK_POCKET = 0, TASK_PRE = 1, TASK_LINK = 2, TASK_FIX = 3;
 
 // Dataflow task.  A task T may run step s once (a) every task in A(T) has finished step s and
 // (b) every task in B(T) (T itself included) has finished step s-1.  Completion of U at step s
 // decrements the pending counter of every T with U in A(T) ("same" targets, for T's step s) and
 // of every T with U in B(T) ("next" targets, for T's step s+1).
+//
+// Spines (long paths) are cut into segments.  Along a segment the step is the recurrence
+// o_k = alpha_k (o_{k-1} + side_k) + r_k, an affine map of the flow o_in entering the segment:
+//   PRE   per segment : side_k, r_k from the old state and the pocket roots; B_k = the recurrence
+//                       with o_in = 0; parks (side_k, B_k) in the segment's I / O rows
+//   LINK  per path    : walks the segments once, out = A_last * o_in + B_last  (A = prefix product
+//                       of alpha), one FMA per segment on the critical path
+//   FIX   per segment : o_k = B_k + A_k * o_in, i_k = o_{k-1} + side_k, all reaches independent
 struct TaskDesc {
-    int32_t begin;     // first position (rows [begin, begin+len) are contiguous)
-    int32_t len;
+    int32_t begin;     // first position (rows [begin, begin+len) are contiguous); LINK: first link entry
+    int32_t len;       // rows; LINK: segments of the path
     int32_t in_off;    // offset of the task's first input word
     int32_t nfy_off;   // offset into `notify`: n_same targets, then n_next targets
     int32_t n_same;
     int32_t n_next;
     int32_t need0;     // |A(T)|           pending count before step 0
     int32_t need;      // |A(T)| + |B(T)|  re-arm value after each completed step
-    int32_t kind;      // TASK_POCKET / TASK_PRE / TASK_CHAIN
+    int32_t kind;      // TASK_POCKET / TASK_PRE / TASK_LINK / TASK_FIX
     int32_t n_words;   // input words of this task
-    int32_t first_in;  // CHAIN: row feeding the first reach (its first late input), else -1
-    int32_t pad_;
+    int32_t pad_[2];
 };
 
 struct Schedule {
@@ -83,13 +93,14 @@ struct Schedule {
     std::vector<int32_t> init_ready;        // tasks with need0 == 0
     std::vector<uint32_t> hdr;              // per position
     std::vector<uint32_t> inw;
+    std::vector<int32_t> link_last;         // per LINK entry: position of the segment's last row
     // position-space CSR of upstream rows (level kernel, init_inflows, apply_gain)
     std::vector<int32_t> up_off, up_pos;
     std::vector<int32_t> lvl_pos, lvl_off;  // positions sorted by level
     std::vector<uint8_t> is_outlet_pos;
     // statistics
     int32_t n_spine = 0, n_pocket = 0, slots_used = 0, row_fallbacks = 0;
-    int32_t max_len = 0;                    // longest task (rows)
+    int32_t max_len = 0;                    // longest task (rows, or segments of a LINK task)
     int32_t cp_tasks = 0;                   // tasks on the longest same-step dependent chain
     int64_t cp_cost = 0;
 
