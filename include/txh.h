@@ -53,7 +53,7 @@ int txh_device_count(void);
  * Host-only, exact integers; works without a GPU.  `endnodes[j]` is the downstream
  * reach of j, an outlet is endnodes[j] == j (muskingum.py:897-902); startnodes is
  * arange(n) as the reference kernels assume (nutils.py:73-83).
- * sched_params = {long_path_min, spine_cap, pocket_cap, max_slots}, NULL = defaults. */
+ * sched_params = {long_path_min, spine_cap, pocket_cap, max_slots, link_cap}, NULL = defaults. */
 int txh_create(int64_t n, const int64_t* endnodes, const int32_t* sched_params, txh_net** out);
 void txh_destroy(txh_net* net);
 int64_t txh_n(const txh_net* net);

@@ -23,6 +23,7 @@ def simulate(sched, coef, O, I, q_of_step, nsteps, seed=0, order="random"):
     ready = [k for k in range(nt) if pending[k] == 0]
     running_guard = np.zeros(nt, dtype=bool)
     scratch = np.full(32, np.nan)
+    side_buf = np.full(max(1, int(sched.get('n_side', O.size))), np.nan)
     # prefix product of alpha along each segment (rows whose header carries the continue bit)
     cumA = np.empty(O.size)
     for p in range(O.size):
@@ -45,7 +46,7 @@ def simulate(sched, coef, O, I, q_of_step, nsteps, seed=0, order="random"):
             acc = 0.0
             for p in range(begin, begin + ln):
                 h = int(hdr[p]); infl = acc if (h & 1) else 0.0
-                for _ in range(h >> 6):
+                for _ in range((h >> 6) & 0x1ffffff):
                     x = int(inw[w]); w += 1
                     if x & ROW:
                         infl += O[x & 0x7fffffff]
@@ -54,18 +55,19 @@ def simulate(sched, coef, O, I, q_of_step, nsteps, seed=0, order="random"):
                 a, b, c, g = coef[p]
                 on = a * infl + (b * I[p] + c * O[p] + g * q[p])
                 I[p] = infl; O[p] = on
+                if h >> 31:                            # pocket root: push to the spine's side slab
+                    side_buf[int(inw[w])] = on; w += 1
                 sl = (h >> 1) & 31
                 if sl:
                     scratch[sl - 1] = on
                 acc = on
         elif kind == PRE:
             B = 0.0
+            cur = int(tasks[k, 10])                    # side_off
             for p in range(begin, begin + ln):
                 h = int(hdr[p]); side = 0.0
                 for _ in range((h >> 6) & 0x1fff):
-                    x = int(inw[w]); w += 1
-                    assert x & ROW
-                    side += O[x & 0x7fffffff]
+                    assert not np.isnan(side_buf[cur]); side += side_buf[cur]; side_buf[cur] = np.nan; cur += 1
                 a, b, c, g = coef[p]
                 infl = side + (B if (h & 1) else 0.0)
                 B = a * infl + (b * I[p] + c * O[p] + g * q[p])

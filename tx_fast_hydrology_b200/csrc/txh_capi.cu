@@ -62,6 +62,7 @@ struct txh_net {
     double* d_qtmp = nullptr;           // [n] schedule-order scratch for txh_route_step
     int32_t* d_pending = nullptr; size_t pairs_cap = 0;
     unsigned long long* d_queue = nullptr; size_t queue_cap = 0;
+    double* d_side = nullptr; size_t side_cap = 0;   // side buffer [n_side][ld]
     unsigned long long* d_qctl = nullptr;     // [0] head, [1] tail, [2] completed, [4] status word
     int32_t* d_status = nullptr;
     StepInterp* d_steps = nullptr; size_t steps_cap = 0;
@@ -165,6 +166,12 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
     if (rec_slot && rec_every > 1 && steps_per_launch < nsteps)
         steps_per_launch = std::max<int64_t>(rec_every, steps_per_launch / rec_every * rec_every);
     const size_t qneed = pairs * (size_t)steps_per_launch;
+    const size_t side_need = (size_t)std::max(1, s.n_side) * ld;
+    if (side_need > net->side_cap) {
+        if (net->d_side) CU(cudaFree(net->d_side));
+        CU(cudaMalloc((void**)&net->d_side, side_need * sizeof(double)));
+        net->side_cap = side_need;
+    }
     if (qneed > net->queue_cap) {
         if (net->d_queue) CU(cudaFree(net->d_queue));
         CU(cudaMalloc((void**)&net->d_queue, qneed * sizeof(unsigned long long)));
@@ -181,7 +188,7 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
         RouteArgs a{};
         a.tasks = net->d_tasks; a.notify = net->d_notify; a.hdr = net->d_hdr; a.inw = net->d_inw;
         a.coef = net->d_coef; a.cumA = net->d_coef + 4 * net->topo.n; a.linkA = net->d_coef + 5 * net->topo.n;
-        a.O = O; a.I = I; a.F = F; a.steps = d_steps + s0; a.Wmul = W;
+        a.O = O; a.I = I; a.Side = net->d_side; a.F = F; a.steps = d_steps + s0; a.Wmul = W;
         a.rec_slot = rec_slot;
         a.rec_out = rec_out;
         if (rec_slot && s0 > 0) {
@@ -194,16 +201,21 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
         a.n = net->topo.n; a.n_tasks = ia.n_tasks; a.n_mblocks = nmb; a.nsteps = (int32_t)ns;
         a.slots = std::max(1, s.slots_used); a.ld = ld; a.M = (int32_t)M;
         a.wm_ld = wm_ld; a.rec_every = rec_every; a.rec_count = rec_count;
-        // per-warp staging area: [scratch slots][coef][f0][f1][hdr][inw], every part 16-byte aligned
+        // per-warp shared memory: [scratch slots][staging][row ring].  Staging of a walking task:
+        // [coef][f0][f1][hdr][words]; of a LINK task: [A_last per segment][records]; 16-byte aligned parts.
         auto up16 = [](int x) { return (x + 15) & ~15; };
         const int L = std::max(1, s.max_len);
-        a.max_words = 256;
+        a.max_words = std::min(1024, std::max(16, s.max_words));
+        a.max_words_link = std::min(2048, std::max(16, s.max_link_words));
         a.off_coef = a.slots * 32 * (int)sizeof(double2);
         a.off_f0 = a.off_coef + 4 * L * (int)sizeof(double);
         a.off_f1 = a.off_f0 + up16(L * (int)sizeof(double));
         a.off_hdr = a.off_f1 + up16(L * (int)sizeof(double));
         a.off_inw = a.off_hdr + up16(L * (int)sizeof(uint32_t));
-        a.off_ring = a.off_inw + up16(a.max_words * (int)sizeof(uint32_t));
+        const int end_walk = a.off_inw + up16(a.max_words * (int)sizeof(uint32_t));
+        a.off_inw_link = a.off_coef + up16(std::max(1, s.max_link_len) * (int)sizeof(double));
+        const int end_link = a.off_inw_link + up16(a.max_words_link * (int)sizeof(uint32_t));
+        a.off_ring = std::max(end_walk, end_link);
         a.smem_per_warp = a.off_ring + kRingBytes;
         a.trace = nullptr;
         const char* trace_file = getenv("TXH_TRACE_FILE");
@@ -255,7 +267,7 @@ int txh_create(int64_t n, const int64_t* endnodes, const int32_t* sp, txh_net** 
     std::string err;
     if (!net->topo.build(n, endnodes, err)) { delete net; return fail(TXH_E_TOPOLOGY, err); }
     SchedParams p;
-    if (sp) { p.long_path_min = sp[0]; p.spine_cap = sp[1]; p.pocket_cap = sp[2]; p.max_slots = sp[3]; }
+    if (sp) { p.long_path_min = sp[0]; p.spine_cap = sp[1]; p.pocket_cap = sp[2]; p.max_slots = sp[3]; p.link_cap = sp[4]; }
     if (!net->sched.build(net->topo, p, err)) { delete net; return fail(TXH_E_INVALID, err); }
     *out = net;
     return TXH_OK;
@@ -272,6 +284,7 @@ void txh_destroy(txh_net* net)
         cudaFree(net->d_unit_step);
         if (net->d_pending) cudaFree(net->d_pending);
         if (net->d_queue) cudaFree(net->d_queue);
+        if (net->d_side) cudaFree(net->d_side);
         if (net->d_steps) cudaFree(net->d_steps);
         if (net->d_tmp_idx) cudaFree(net->d_tmp_idx);
         if (net->h_status) cudaFreeHost(net->h_status);

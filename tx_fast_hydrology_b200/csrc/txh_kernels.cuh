@@ -28,6 +28,7 @@ struct RouteArgs {
     const double* linkA;                  // [link entries] cumA at the last reach of each segment
     double* O;
     double* I;
+    double* Side;                         // [n_side][ld] outflows of the pocket roots, in PRE order (scratch)
     const double* F;                      // [R][n] schedule order, or nullptr
     const StepInterp* steps;              // [nsteps]
     const double* Wmul;                   // [R][wm_ld] member multipliers, or nullptr
@@ -45,6 +46,7 @@ struct RouteArgs {
     int32_t ld, M, wm_ld, rec_every, rec_count;
     // per-warp shared-memory area (bytes): [scratch slots][coef][f0][f1][hdr][inw][row ring]
     int32_t smem_per_warp, off_coef, off_f0, off_f1, off_hdr, off_inw, off_ring, max_words;
+    int32_t off_inw_link, max_words_link; // LINK layout: A_last at off_coef, records at off_inw_link
     unsigned long long* trace;            // optional [total][4] timeline, nullptr = off
 };
 

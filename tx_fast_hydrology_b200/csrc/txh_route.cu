@@ -38,7 +38,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 __device__ __forceinline__ double2 ld_row(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ void st_row(double* p, double2 v) { __stcg(reinterpret_cast<double2*>(p), v); }
 constexpr int kRing = 12;     // rows in flight per warp and state array (cp.async ring in shared memory)
-constexpr int kRingPre = 8;   // PRE tasks stream three arrays (I, O, first side row): 3 x 8 == 2 x 12 slots
+constexpr int kRingPre = 6;   // PRE tasks stream four arrays (I, O, two side rows): 4 x 6 == 2 x 12 slots
 
 __device__ __forceinline__ void cp_async4(void* s, const void* g)
 {
@@ -171,7 +171,7 @@ __device__ __forceinline__ void run_pocket(const RouteArgs& a, const TaskDesc& t
         const uint32_t h = st.h(i);
         const double al = st.al(i), be = st.be(i), ch = st.ch(i), ga = st.ga(i);
         double2 inflow = (h & HDR_ACC) ? acc : make_double2(0.0, 0.0);
-        const int nin = (int)(h >> 6);
+        const int nin = (int)((h >> 6) & 0x1ffffffu);
         for (int t = 0; t < nin; ++t) {
             const uint32_t w = st.word(wi++);
             double2 v;
@@ -184,6 +184,10 @@ __device__ __forceinline__ void run_pocket(const RouteArgs& a, const TaskDesc& t
         on.x = al * inflow.x + (be * io.x + ch * oo.x + ga * q.x);
         on.y = al * inflow.y + (be * io.y + ch * oo.y + ga * q.y);
         if (active) { st_row(Ir + (size_t)i * ld, inflow); st_row(Or + (size_t)i * ld, on); }
+        if (h & HDR_PUSH) {                             // pocket root: hand the outflow to the spine's side slab
+            const uint32_t sidx = st.word(wi++);
+            if (active) st_row(a.Side + (size_t)sidx * ld + ccol, on);
+        }
         const uint32_t slot = (h >> 1) & 31u;
         if (slot) scratch[(slot - 1) * 32] = on;
         acc = on;
@@ -192,36 +196,38 @@ __device__ __forceinline__ void run_pocket(const RouteArgs& a, const TaskDesc& t
     cp_async_wait_all();
 }
 
-// PRE: one spine segment -- gathers the side inflow from the pocket roots, folds the old state
-// and the forcing into r = beta*i_prev + chi*o_prev + gamma*q, and runs the segment's recurrence
-// with no flow entering it:  B_k = alpha_k (B_{k-1} + side_k) + r_k.  (side_k, B_k) are parked in the
-// segment's own I / O rows.  The first side row of each reach travels through the ring.
+// PRE: one spine segment -- sums the side inflow pushed by the pocket roots (a contiguous slab
+// of the side buffer, consumed in order), folds the old state and the forcing into
+// r = beta*i_prev + chi*o_prev + gamma*q, and runs the segment's recurrence with no flow entering
+// it:  B_k = alpha_k (B_{k-1} + side_k) + r_k.  (side_k, B_k) are parked in the segment's own I / O
+// rows.  State rows and the first two side rows of every reach travel through the ring.
 template <bool HAS_F, bool HAS_W>
 __device__ __forceinline__ void run_pre(const RouteArgs& a, const TaskDesc& td, const Stage& st, int col, bool active,
                                         const StepCtx& sc, unsigned ring)
 {
     const int ld = a.ld, len = td.len;
     const int ccol = active ? col : 0;
-    double* Ob = a.O + ccol;
-    double* Or = Ob + (size_t)td.begin * ld;
+    double* Or = a.O + ccol + (size_t)td.begin * ld;
     double* Ir = a.I + ccol + (size_t)td.begin * ld;
-    const unsigned ringO = ring + kRingPre * 512u, ringG = ring + 2 * kRingPre * 512u;
-    cp_async_wait_all();                                // the gather addresses come from the staged words
+    const double* Sr = a.Side + ccol + (size_t)td.side_off * ld;
+    const unsigned ringO = ring + kRingPre * 512u, ringG = ring + 2 * kRingPre * 512u, ringH = ring + 3 * kRingPre * 512u;
+    cp_async_wait_all();                                // the side-row counts come from the staged headers
     __syncwarp();
-    int wq = 0;                                         // word cursor of the prefetcher
+    int cq = 0;                                         // side-row cursor of the prefetcher
 #pragma unroll
     for (int j = 0; j < kRingPre; ++j) {
         if (j < len) {
             const int nin = (int)((st.h(j) >> 6) & 0x1fffu);
             if (active) {
                 cp_row(ring + j * 512u, Ir + (size_t)j * ld); cp_row(ringO + j * 512u, Or + (size_t)j * ld);
-                if (nin > 0) cp_row(ringG + j * 512u, Ob + (size_t)(st.word(wq) & ~INW_ROW) * ld);
+                if (nin > 0) cp_row(ringG + j * 512u, Sr + (size_t)cq * ld);
+                if (nin > 1) cp_row(ringH + j * 512u, Sr + (size_t)(cq + 1) * ld);
             }
-            wq += nin;
+            cq += nin;
         }
         cp_async_commit();
     }
-    int wi = 0, sl = 0;
+    int ci = 0, sl = 0;
     double2 B = make_double2(0.0, 0.0);
     for (int i = 0; i < len; ++i) {
         cp_async_wait_group<kRingPre - 1>();
@@ -229,24 +235,26 @@ __device__ __forceinline__ void run_pre(const RouteArgs& a, const TaskDesc& td, 
         const int nin = (int)((h >> 6) & 0x1fffu);
         const double2 io = lds_row(ring + sl * 512u), oo = lds_row(ringO + sl * 512u);
         double2 side = nin > 0 ? lds_row(ringG + sl * 512u) : make_double2(0.0, 0.0);
+        if (nin > 1) { const double2 v = lds_row(ringH + sl * 512u); side.x += v.x; side.y += v.y; }
         const int ip = i + kRingPre;
         if (ip < len) {
             const int np = (int)((st.h(ip) >> 6) & 0x1fffu);
             if (active) {
                 cp_row(ring + sl * 512u, Ir + (size_t)ip * ld); cp_row(ringO + sl * 512u, Or + (size_t)ip * ld);
-                if (np > 0) cp_row(ringG + sl * 512u, Ob + (size_t)(st.word(wq) & ~INW_ROW) * ld);
+                if (np > 0) cp_row(ringG + sl * 512u, Sr + (size_t)cq * ld);
+                if (np > 1) cp_row(ringH + sl * 512u, Sr + (size_t)(cq + 1) * ld);
             }
-            wq += np;
+            cq += np;
         }
         cp_async_commit();
         sl = sl + 1 == kRingPre ? 0 : sl + 1;
-        for (int t = 1; t < nin; ++t) {
+        for (int t = 2; t < nin; ++t) {
             if (active) {
-                const double2 v = ld_row(Ob + (size_t)(st.word(wi + t) & ~INW_ROW) * ld);
+                const double2 v = ld_row(Sr + (size_t)(ci + t) * ld);
                 side.x += v.x; side.y += v.y;
             }
         }
-        wi += nin;
+        ci += nin;
         const double al = st.al(i), be = st.be(i), ch = st.ch(i), ga = st.ga(i);
         const double2 q = forcing_q<HAS_F, HAS_W>(sc, st, i);
         double2 inflow = side;
@@ -461,12 +469,17 @@ route_dataflow_kernel(const RouteArgs a)
         StepInterp si;
         si.r0 = si.r1 = 0; si.w0 = si.w1 = 0.0;
         Stage st;
-        st.coef = sbase + a.off_coef; st.f0 = sbase + a.off_f0; st.f1 = sbase + a.off_f1;
-        st.hdr = sbase + a.off_hdr; st.inw = sbase + a.off_inw; st.inw_g = nullptr;
         const bool walks = td.kind == TASK_POCKET || td.kind == TASK_PRE;     // evaluates the Muskingum update itself
+        const bool link = td.kind == TASK_LINK;
+        // LINK tasks lay the staging area out differently: [A_last per segment][records]
+        const int off_f0 = link ? a.off_coef : a.off_f0;
+        const int off_inw = link ? a.off_inw_link : a.off_inw;
+        const int cap_words = link ? a.max_words_link : a.max_words;
+        st.coef = sbase + a.off_coef; st.f0 = sbase + off_f0; st.f1 = sbase + a.off_f1;
+        st.hdr = sbase + a.off_hdr; st.inw = sbase + off_inw; st.inw_g = nullptr;
         {
-            if (td.n_words <= a.max_words)
-                for (int i = lane; i < td.n_words; i += 32) cp_async4(wbase + a.off_inw + 4 * i, a.inw + td.in_off + i);
+            if (td.n_words <= cap_words)
+                for (int i = lane; i < td.n_words; i += 32) cp_async4(wbase + off_inw + 4 * i, a.inw + td.in_off + i);
             else
                 st.inw_g = a.inw + td.in_off;
             if (walks) {
@@ -484,8 +497,8 @@ route_dataflow_kernel(const RouteArgs a)
                 }
             } else {
                 // prefix products of alpha: per reach of the segment (FIX) / per segment of the path (LINK)
-                const double* ga = (td.kind == TASK_FIX ? a.cumA : a.linkA) + td.begin;
-                for (int i = lane; i < td.len; i += 32) cp_async8(wbase + a.off_f0 + 8 * i, ga + i);
+                const double* ga = (link ? a.linkA : a.cumA) + td.begin;
+                for (int i = lane; i < td.len; i += 32) cp_async8(wbase + off_f0 + 8 * i, ga + i);
             }
         }
         const int col = mb * kMemberBlock + lane * 2;
@@ -521,12 +534,13 @@ route_dataflow_kernel(const RouteArgs a)
             if (d < nn) {
                 tgt = a.notify[td.nfy_off + d] * nmb + mb;
                 int old;
-                asm volatile("atom.release.gpu.global.add.s32 %0, [%1], -1;" : "=r"(old) : "l"(a.pending + tgt) : "memory");
+                // release: this task's rows precede the signal; acquire: a lane that completes the
+                // dependant's count has the other contributors' rows ordered before the hand-off
+                asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], -1;" : "=r"(old) : "l"(a.pending + tgt) : "memory");
                 ready = old == 1;
             }
             const unsigned mask = __ballot_sync(0xffffffffu, ready);
             if (mask != 0u) {
-                if (ready) fence_acq_rel();          // acquire the other contributors' releases, release for the hand-off
                 // entry of the dependant: same-step targets run step s, next-step targets step s + 1
                 const long long e = ((long long)(d < td.n_same ? s : s + 1) << 32) | (long long)(unsigned)(tgt + 1);
                 if (next_entry == 0) {
@@ -537,9 +551,16 @@ route_dataflow_kernel(const RouteArgs a)
                     next_entry = __shfl_sync(0xffffffffu, e, keep);
                     if (lane == keep) ready = false;
                 }
-                if (ready) {
-                    const unsigned long long idx = atomicAdd(q_tail, 1ull);
-                    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.queue + idx), "l"(e) : "memory");
+                const unsigned pm = __ballot_sync(0xffffffffu, ready);      // lanes that still have to queue theirs
+                if (pm != 0u) {
+                    unsigned long long base = 0;
+                    const int leader = __ffs(pm) - 1;
+                    if (lane == leader) base = atomicAdd(q_tail, (unsigned long long)__popc(pm));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (ready) {
+                        const unsigned long long idx = base + __popc(pm & ((1u << lane) - 1u));
+                        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.queue + idx), "l"(e) : "memory");
+                    }
                 }
             }
         }

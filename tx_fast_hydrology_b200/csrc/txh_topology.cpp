@@ -123,6 +123,7 @@ struct Unit {
     int32_t grp;                      // row group (contiguous rows in the final layout), -1 for LINK
     int32_t kind;
     int32_t link_off, link_len;       // LINK: its entries in link_last
+    int32_t side_off;                 // PRE: first side-buffer row
     std::vector<uint32_t> ins;        // input words; ROW entries hold REACH ids until positions are known
     std::vector<int32_t> A, B;        // same-step / previous-step dependencies (unit ids)
 };
@@ -140,7 +141,7 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
     prm = p;
     const int64_t n = t.n;
     if (p.spine_cap < 1 || p.spine_cap > 4096 || p.pocket_cap < 1 || p.pocket_cap > 4096 ||
-        p.long_path_min < 2 || p.max_slots < 0 || p.max_slots > 30) {
+        p.long_path_min < 2 || p.max_slots < 0 || p.max_slots > 30 || p.link_cap < 1) {
         err = "bad schedule parameters"; return false;
     }
     std::vector<uint8_t> is_long(n);
@@ -154,7 +155,9 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
     std::vector<int32_t> final_unit(n, -1);   // pocket reaches: their task; last reach of a segment: the path's LINK
     std::vector<int32_t> pre_unit(n, -1);     // spine reaches: the PRE unit of their segment
     std::vector<int32_t> link_reach;          // per LINK entry: last reach of the segment
-    auto mk = [](int32_t grp, int32_t kind) { Unit u; u.grp = grp; u.kind = kind; u.link_off = u.link_len = 0; return u; };
+    auto mk = [](int32_t grp, int32_t kind) { Unit u; u.grp = grp; u.kind = kind; u.link_off = u.link_len = 0; u.side_off = 0; return u; };
+    std::vector<int32_t> push_of(n, -1);      // pocket roots feeding a spine: their side-buffer row
+    n_side = 0;
 
     // ---- spines: long paths cut into segments (PRE + FIX each) and one LINK per path ---------
     {
@@ -183,17 +186,23 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
                 for (int32_t s0 = a0; s0 < a1; s0 += seglen) cuts.push_back(s0);
             }
             cuts.push_back(len);
-            const int32_t link_u = (int32_t)units.size();
-            units.push_back(mk(-1, TASK_LINK));
-            units[link_u].link_off = (int32_t)link_reach.size();
-            units[link_u].link_len = (int32_t)cuts.size() - 1;
+            int32_t link_u = -1, prev_last = -1;
             for (size_t cseg = 0; cseg + 1 < cuts.size(); ++cseg) {
                 const int32_t s0 = cuts[cseg], s1 = cuts[cseg + 1];
+                const bool new_block = link_u < 0 || units[link_u].link_len == p.link_cap;
+                if (new_block) {
+                    // LINK tasks cover blocks of consecutive segments and are chained along the path
+                    link_u = (int32_t)units.size();
+                    units.push_back(mk(-1, TASK_LINK));
+                    units[link_u].link_off = (int32_t)link_reach.size();
+                }
+                units[link_u].link_len += 1;
                 const int32_t g = (int32_t)g_begin.size();
                 g_begin.push_back((int32_t)rows.size()); g_len.push_back(s1 - s0);
                 const int32_t up = (int32_t)units.size();
                 units.push_back(mk(g, TASK_PRE));
                 units.push_back(mk(g, TASK_FIX));
+                units[up].side_off = n_side;
                 std::vector<uint32_t> late;
                 for (int32_t k = s0; k < s1; ++k) {
                     const int32_t j = member[poff[q] + k];
@@ -209,7 +218,7 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
                             if (k != s0) { err = "internal: long tributary inside a segment"; return false; }
                             units[up + 1].ins.push_back(INW_ROW | (uint32_t)ch); ++n_first;
                             late.push_back(INW_ROW | (uint32_t)ch);
-                        } else { units[up].ins.push_back(INW_ROW | (uint32_t)ch); ++n_early; }
+                        } else { units[up].ins.push_back(INW_ROW | (uint32_t)ch); ++n_early; push_of[ch] = n_side++; }
                     }
                     if (n_early >= (1u << 13) || n_first >= (1u << 13)) { err = "confluence too wide"; return false; }
                     rows.push_back(j);
@@ -219,9 +228,12 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
                 final_unit[last] = link_u;
                 link_reach.push_back(last);
                 Unit& L = units[link_u];
+                // a block's first record also takes the outflow of the previous block's last reach
+                if (new_block && prev_last >= 0) late.insert(late.begin(), INW_ROW | (uint32_t)prev_last);
                 L.ins.push_back(INW_ROW | (uint32_t)last);
                 L.ins.push_back((uint32_t)late.size());
                 L.ins.insert(L.ins.end(), late.begin(), late.end());
+                prev_last = last;
             }
         }
     }
@@ -314,6 +326,7 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
         }
         for (int32_t c = t.child_off[v]; c < t.child_off[v + 1]; ++c)
             if (closed[t.child[c]]) { u.ins.push_back(INW_ROW | (uint32_t)t.child[c]); ++nin; }
+        if (push_of[v] >= 0) { h |= HDR_PUSH; u.ins.push_back((uint32_t)push_of[v]); }
         final_unit[v] = (int32_t)units.size() - 1;
         rows.push_back(v);
         rhdr.push_back(h | (nin << 6));
@@ -448,7 +461,7 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
             }
         }
         tasks.assign(nu, TaskDesc{});
-        inw.clear(); notify.clear(); init_ready.clear(); max_len = 0;
+        inw.clear(); notify.clear(); init_ready.clear(); max_len = max_link_len = max_words = max_link_words = 0;
         link_last.resize(link_reach.size());
         for (size_t e = 0; e < link_reach.size(); ++e) link_last[e] = pos_of_reach[link_reach[e]];
         for (int32_t k = 0; k < nu; ++k) {
@@ -458,10 +471,12 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
             if (U.kind == TASK_LINK) { td.begin = U.link_off; td.len = U.link_len; }
             else { td.begin = gpos[U.grp]; td.len = g_len[U.grp]; }
             td.in_off = (int32_t)inw.size();
-            for (uint32_t x : U.ins) {
-                if (x & INW_ROW) x = INW_ROW | (uint32_t)pos_of_reach[x & ~INW_ROW];
-                inw.push_back(x);
-            }
+            td.side_off = U.side_off;
+            if (U.kind != TASK_PRE)                                // PRE reads its inputs from the side buffer
+                for (uint32_t x : U.ins) {
+                    if (x & INW_ROW) x = INW_ROW | (uint32_t)pos_of_reach[x & ~INW_ROW];
+                    inw.push_back(x);
+                }
             td.nfy_off = (int32_t)notify.size();
             td.n_same = (int32_t)same[order[k]].size();
             td.n_next = (int32_t)next[order[k]].size();
@@ -470,8 +485,9 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
                 notify.push_back(rank[c]);
             }
             for (int32_t c : next[order[k]]) notify.push_back(rank[c]);
-            td.n_words = (int32_t)U.ins.size();
-            max_len = std::max(max_len, td.len);
+            td.n_words = (int32_t)inw.size() - td.in_off;
+            if (U.kind == TASK_LINK) { max_link_len = std::max(max_link_len, td.len); max_link_words = std::max(max_link_words, td.n_words); }
+            else { max_len = std::max(max_len, td.len); max_words = std::max(max_words, td.n_words); }
             td.need0 = (int32_t)U.A.size();
             td.need = (int32_t)(U.A.size() + U.B.size());
             if (td.need0 == 0) init_ready.push_back(k);

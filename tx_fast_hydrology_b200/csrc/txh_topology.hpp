@@ -38,24 +38,30 @@ struct Topology {
 };
 
 struct SchedParams {
-    int long_path_min = 16;   // paths at least this long become spines
-    int spine_cap = 32;       // reaches per spine segment (pure chains: a PRE and a CHAIN task each)
+    int long_path_min = 32;   // paths at least this long become spines
+    int spine_cap = 32;       // reaches per spine segment (a PRE and a FIX task each)
     int pocket_cap = 48;      // reaches per pocket task (bundled side subtrees)
     int max_slots = 12;       // shared-memory scratch rows per warp
+    int link_cap = 8;         // segments per LINK task (blocks chained along the path)
 };
 
 // Per-reach header word consumed by the routing kernel.
 //   pocket rows : bit 0      inflow starts from the running accumulator (previous reach's outflow)
 //                 bits 1..5  (scratch slot + 1) the outflow is also parked in, 0 = none
-//                 bits 6..31 number of input words that follow in the task's input stream
+//                 bits 6..30 number of input words that follow in the task's input stream
+//                 bit 31     pocket root feeding a spine: one more word follows, the row of the
+//                            side buffer the outflow is also pushed to (read back by that
+//                            segment's PRE as a contiguous slab instead of a gather)
 //   spine rows  : bit 0      not the first reach of its segment (the recurrence continues)
-//                 bits 6..18 number of EARLY inputs (rows of pocket roots; PRE task stream)
+//                 bits 6..18 number of side-buffer rows the reach consumes (its pocket roots, in
+//                            the order the PRE task walks them, starting at TaskDesc::side_off)
 //                 bits 19..31 first row of a segment only: number of rows whose sum is the flow
 //                             entering the segment (last row of the upstream segment + outlets of
 //                             long tributaries; FIX task stream)
 // Input word: bit 31 set -> state row (position) to gather; else scratch slot id.
 // LINK stream, one record per segment of the path: [last row position][n_late][n_late rows].
 constexpr uint32_t HDR_ACC = 1u;
+constexpr uint32_t HDR_PUSH = 0x80000000u;
 constexpr uint32_t INW_ROW = 0x80000000u;
 constexpr int TASK_POCKET = 0, TASK_PRE = 1, TASK_LINK = 2, TASK_FIX = 3;
 
@@ -68,8 +74,8 @@ constexpr int TASK_POCKET = 0, TASK_PRE = 1, TASK_LINK = 2, TASK_FIX = 3;
 // o_k = alpha_k (o_{k-1} + side_k) + r_k, an affine map of the flow o_in entering the segment:
 //   PRE   per segment : side_k, r_k from the old state and the pocket roots; B_k = the recurrence
 //                       with o_in = 0; parks (side_k, B_k) in the segment's I / O rows
-//   LINK  per path    : walks the segments once, out = A_last * o_in + B_last  (A = prefix product
-//                       of alpha), one FMA per segment on the critical path
+//   LINK  per block of consecutive segments, chained along the path: out = A_last * o_in + B_last
+//                       (A = prefix product of alpha), one FMA per segment on the critical path
 //   FIX   per segment : o_k = B_k + A_k * o_in, i_k = o_{k-1} + side_k, all reaches independent
 struct TaskDesc {
     int32_t begin;     // first position (rows [begin, begin+len) are contiguous); LINK: first link entry
@@ -82,7 +88,8 @@ struct TaskDesc {
     int32_t need;      // |A(T)| + |B(T)|  re-arm value after each completed step
     int32_t kind;      // TASK_POCKET / TASK_PRE / TASK_LINK / TASK_FIX
     int32_t n_words;   // input words of this task
-    int32_t pad_[2];
+    int32_t side_off;  // PRE: first side-buffer row of the segment
+    int32_t pad_;
 };
 
 struct Schedule {
@@ -100,7 +107,10 @@ struct Schedule {
     std::vector<uint8_t> is_outlet_pos;
     // statistics
     int32_t n_spine = 0, n_pocket = 0, slots_used = 0, row_fallbacks = 0;
-    int32_t max_len = 0;                    // longest task (rows, or segments of a LINK task)
+    int32_t max_len = 0;                    // longest POCKET / PRE / FIX task (rows)
+    int32_t max_link_len = 0;               // longest LINK task (segments)
+    int32_t max_words = 0, max_link_words = 0;   // longest input streams (walking tasks / LINK)
+    int32_t n_side = 0;                     // rows of the side buffer
     int32_t cp_tasks = 0;                   // tasks on the longest same-step dependent chain
     int64_t cp_cost = 0;
 

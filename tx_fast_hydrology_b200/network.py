@@ -67,7 +67,8 @@ class RiverNetwork:
         self.n = int(end.size)
         sp = None
         if sched_params is not None:
-            sp = (ctypes.c_int32 * 4)(*[int(x) for x in sched_params])
+            sp = list(sched_params) + [8] * (5 - len(sched_params))
+            sp = (ctypes.c_int32 * 5)(*[int(x) for x in sp])
         h = ctypes.c_void_p()
         L.check(lib.txh_create(self.n, L.ptr_i64(end), sp, ctypes.byref(h)))
         self.handle = h
