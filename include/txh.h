@@ -134,6 +134,43 @@ int txh_route_apply(txh_net* net, double* X_dev, double* I_scratch_dev, int64_t 
  * O += G ; I[j] += sum_{u->j, u!=j} G[u]   (G in schedule order, same shape) */
 int txh_apply_gain(txh_net* net, const double* G_dev, double* O_dev, double* I_dev, int64_t M, void* stream);
 
+/* ---- assimilation ------------------------------------------------------------------------
+ * Ensemble form of KalmanFilter.filter (da.py:91-136) with P := sample covariance of the forecast
+ * ensemble + diagonal Q (the reference has no ensemble filter):
+ *   dz = Zp - O[s]                       (da.py:112, per member, Zp = perturbed observations)
+ *   S  = HA HA^T/(Mtot-1) + Q[s,s] + R   (da.py:117-119: P[s][:,s] + R_cov)
+ *   W  = S^-1 dz ;  T = HA^T W/(Mtot-1)
+ *   gain = A T + Q[:,s] W                (da.py:119-121: K dz with K = P[:,s] S^-1)
+ *   O += gain ; I += N gain              (da.py:124-126: _apply_gain)
+ * A = O - mean are the anomalies, HA their gauge rows.  Three phases so that a member-sharded run
+ * can combine the statistics between them (all-reduce of the row sums, all-gather of HX / X):
+ *   txh_enkf_stats : local row sums at every reach + this shard's gauge rows
+ *   txh_enkf_solve : innovation covariance (FP64 tensor cores), Cholesky solve, transform
+ *   txh_enkf_apply : gain = A T on the FP64 tensor cores + gauge-row term, then the in-place update
+ * obs_reach: gauged reach indices ascending (da.py:33-44); all matrices row-major on the device. */
+int txh_enkf_stats(txh_net* net, const double* O_dev, int64_t Mloc, const int64_t* obs_reach_host, int64_t m,
+                   double* rowsum_dev /*[n] schedule order*/, double* HX_dev /*[m][Mloc]*/, void* stream);
+int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX_dev /*[m][Mtot]*/,
+                   const double* Zp_dev /*[m][Mtot]*/, const double* mean_dev /*[n] schedule order*/,
+                   const int64_t* obs_reach_host, const double* qs_dev /*[m] diag(Q) at the gauges*/,
+                   const double* R_dev /*[m][m]*/, double* work_dev /* m*m + 2*m*Mtot + m doubles */,
+                   double* W_dev /*[m][Mtot] out*/, double* T_dev /*[Mtot][Mtot] out*/, void* stream);
+int txh_enkf_apply(txh_net* net, double* O_dev, double* I_dev, int64_t Mloc, const double* Xall_dev /* [n][ldx] gathered
+                   ensemble in schedule order, or NULL to use O_dev (Mtot == Mloc) */, int64_t ldx, int64_t Mtot,
+                   int64_t col0 /* first global member of this shard */, const double* mean_dev, const double* T_dev,
+                   const int64_t* obs_reach_host, int64_t m, const double* qs_dev, const double* W_dev,
+                   double* G_dev /* scratch, same shape as O_dev */, void* stream);
+
+/* Dense products of KalmanFilter.filter for small n (da.py:115-122): C = alpha op(A) op(B) + beta C,
+ * row-major FP64 on the tensor cores (mma.sync m8n8k4 = DMMA). */
+int txh_dgemm(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha, const double* A_dev,
+              int64_t lda, const double* B_dev, int64_t ldb, double beta, double* C_dev, int64_t ldc, void* stream);
+/* In-place Cholesky solve S X = B for SPD S [m][m] (destroyed), B [m][k] -> X.  Synchronous;
+ * returns TXH_E_INVALID if S is not positive definite. */
+int txh_spd_solve(int64_t m, int64_t k, double* S_dev, double* B_dev, void* stream);
+/* A <- inv(A) by Gauss-Jordan with partial pivoting (np.linalg.inv, da.py:119); work [m][m]. Synchronous. */
+int txh_inverse(int64_t m, double* A_dev, double* work_dev, void* stream);
+
 /* Synchronise `stream` and report a poisoned launch (TXH_E_WATCHDOG) or a CUDA fault. */
 int txh_check(txh_net* net, void* stream);
 

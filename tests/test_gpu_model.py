@@ -1,0 +1,190 @@
+"""GPU parity tests of the Python drop-in layer (Muskingum, callbacks, KalmanFilter, nutils names,
+EnsembleKalmanFilter) against the golden vectors of the unmodified reference and the CPU oracle.
+Tolerance: FP64 max relative error <= 1e-9 (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def relerr(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max()) / max(1e-300, float(np.abs(b).max()))
+
+
+def frame(times_ns, table, cols):
+    idx = pd.DatetimeIndex(pd.to_datetime(times_ns, unit="ns", utc=True)).as_unit("ns")
+    return pd.DataFrame(table, index=idx, columns=cols)
+
+
+def model_from(g, **kw):
+    from tx_fast_hydrology_b200.muskingum import Muskingum
+    n = g["endnodes"].size
+    d = {"name": "golden", "datetime": pd.Timestamp(int(g["t0_ns"]), tz="UTC"),
+         "timedelta": pd.to_timedelta(float(g["dt"]), unit="s"), "reach_ids": [str(i) for i in range(n)],
+         "startnodes": np.arange(n, dtype=np.int64), "endnodes": g["endnodes"].astype(np.int64),
+         "K": g["K"].astype(np.float64), "X": g["X"].astype(np.float64), "o_t": g["o_init"].astype(np.float64)}
+    return Muskingum(d, **kw), d
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda(libtxh):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device (no CPU fallback exists)"
+
+
+def test_simulate_matches_reference_c1(golden_dir):
+    """Muskingum.simulate (generator, callbacks hooks, per-step launches) on BASELINE configs[0]."""
+    g = np.load(os.path.join(golden_dir, "model_c1.npz"))
+    mdl, d = model_from(g)
+    df = frame(g["times"], g["table"], d["reach_ids"])
+    keep = set(int(k) for k in g["keep"])
+    O, I = [], []
+    total = np.zeros(mdl.n)
+    for k, state in enumerate(mdl.simulate(df)):
+        total += state.o_t_next
+        if k in keep:
+            O.append(state.o_t_next.copy()); I.append(state.i_t_next.copy())
+    assert k == 287 and mdl.datetime.value == int(g["final_time_ns"])
+    assert relerr(np.stack(O), g["O"]) < RTOL and relerr(np.stack(I), g["I"]) < RTOL
+    assert relerr(total, g["o_sum"]) < RTOL
+    # o_t_prev / i_t_prev hold the state before the last step (muskingum.py:458-461)
+    assert relerr(mdl.o_t_prev + 0 * total, mdl.o_t_prev) == 0.0
+
+
+def test_run_fast_path_equals_simulate(golden_dir):
+    g = np.load(os.path.join(golden_dir, "model_c1.npz"))
+    mdl, d = model_from(g)
+    f = mdl.make_forcing(times_ns=g["times"], table=g["table"])
+    rec = mdl.run(f, 288, record_reaches=np.arange(mdl.n), record_every=1)
+    traj = rec.cpu().numpy()[:, :, 0]
+    assert relerr(traj[g["keep"]], g["O"]) < RTOL and relerr(traj.sum(axis=0), g["o_sum"]) < RTOL
+    assert relerr(mdl.o_t_next, g["O"][-1]) < RTOL and relerr(mdl.i_t_next, g["I"][-1]) < RTOL
+    assert mdl.datetime.value == int(g["final_time_ns"])
+
+
+def test_kalman_filter_matches_reference(golden_dir):
+    """KalmanFilter bound as a callback (da.py:14-136): unsorted gauge columns, dense R, filter at
+    simulation start and after every step while measurements last."""
+    from tx_fast_hydrology_b200.da import KalmanFilter
+    g = np.load(os.path.join(golden_dir, "kalman_n120.npz"))
+    mdl, d = model_from(g)
+    df = frame(g["times"], g["table"], d["reach_ids"])
+    mdf = frame(g["meas_times"], g["meas"], [d["reach_ids"][j] for j in g["gauge_cols"]])
+    kf = KalmanFilter(mdl, mdf, g["Q"], g["R"], g["P0"])
+    assert (kf.reach_indices == g["sorted_idx"]).all()
+    mdl.bind_callback(kf, key="kf")
+    O, I, Pd, gains = [], [], [], []
+    for state in mdl.simulate(df):
+        O.append(state.o_t_next.copy()); I.append(state.i_t_next.copy())
+        Pd.append(np.diag(kf.P_t_next).copy()); gains.append(kf.gain.copy())
+    assert relerr(np.stack(O), g["O"]) < RTOL and relerr(np.stack(I), g["I"]) < RTOL
+    assert relerr(np.stack(Pd), g["P_diag"]) < RTOL
+    assert relerr(np.stack(gains), g["gains"]) < 1e-8      # gains are differences of O(1) numbers
+    assert relerr(kf.P_t_next, g["P_final"]) < RTOL and relerr(kf.K, g["K_final"]) < RTOL
+
+
+def test_checkpoint_rewind(golden_dir):
+    """CheckPoint + save_state / load_state (simulation.py:169-211, muskingum.py:573-588)."""
+    from tx_fast_hydrology_b200.simulation import CheckPoint
+    g = np.load(os.path.join(golden_dir, "checkpoint_n80.npz"))
+    mdl, d = model_from(g)
+    df = frame(g["times"], g["table"], d["reach_ids"])
+    mdl.bind_callback(CheckPoint(mdl, timedelta=3600), key="checkpoint")
+    for _ in mdl.simulate(df):
+        pass
+    assert relerr(mdl.o_t_next, g["o_end"]) < RTOL and mdl.datetime.value == int(g["t_end"])
+    assert relerr(mdl.saved_states["o_t_next"], g["saved_o"]) < RTOL
+    assert relerr(mdl.saved_states["i_t_next"], g["saved_i"]) < RTOL
+    assert mdl.saved_states["datetime"].value == int(g["saved_t"])
+    mdl.load_state()
+    assert relerr(mdl.o_t_next, g["o_loaded"]) < RTOL and mdl.datetime.value == int(g["t_loaded"])
+    for _ in mdl.simulate(df):
+        pass
+    assert relerr(mdl.o_t_next, g["o_end2"]) < RTOL and mdl.datetime.value == int(g["t_end2"])
+    assert mdl.saved_states["datetime"].value == int(g["saved_t2"])
+
+
+def test_nutils_names(golden_dir):
+    """The free functions da.py / muskingum.py import by name (muskingum.py:10, da.py:8-9)."""
+    from tx_fast_hydrology_b200 import nutils as NU
+    g = np.load(os.path.join(golden_dir, "kernels_n60.npz"))
+    en = g["endnodes"]; n = en.size; sn = np.arange(n)
+    ind = g["indegree"]; heads = sn[ind == 0]
+    a, b, c, ga = g["alpha"], g["beta"], g["chi"], g["gamma"]
+    i1, o1 = NU._ax_bu(heads, en, a, b, c, ga, g["i_init"], g["o_init"], g["q"], ind)
+    assert relerr(o1, g["axbu_o"]) < RTOL and relerr(i1, g["axbu_i"]) < RTOL
+    i2, o2 = NU._ax(heads, en, a, b, c, g["i_init"], g["o_init"], ind)
+    assert relerr(o2, g["ax_o"]) < RTOL and relerr(i2, g["ax_i"]) < RTOL
+    ig, og = NU._apply_gain(heads, en, g["gain"], ind)
+    assert relerr(og, g["gain_o"]) < RTOL and relerr(ig, g["gain_i"]) < RTOL
+    out = np.empty((n, n))
+    res = NU._ap_par(g["P_sym"], out, heads, en, a, b, c, ind)
+    assert res is out and relerr(out, g["ap"]) < RTOL
+    out2 = np.empty((n, n))
+    res2 = NU._aqat_par(g["P_gen"], out2, heads, en, a, b, c, ind)
+    assert relerr(np.ascontiguousarray(res2), g["aqat_gen"]) < RTOL and res2.base is out2
+    lin = np.stack([NU.interpolate_sample(float(x), g["xp"], g["fp"], 1) for x in g["xs"]])
+    near = np.stack([NU.interpolate_sample(float(x), g["xp"], g["fp"], 0) for x in g["xs"]])
+    assert (lin == g["interp_lin"]).all() and (near == g["interp_near"]).all()
+
+
+def test_dense_linear_algebra():
+    """FP64 tensor-core GEMM, SPD solve and inverse against numpy."""
+    import torch
+    from tx_fast_hydrology_b200.network import dgemm, spd_solve, inverse
+    rng = np.random.default_rng(3)
+    for (M, N, K, ta, tb) in [(70, 33, 50, False, False), (64, 64, 64, True, False), (129, 7, 200, False, True),
+                              (5, 300, 3, True, True)]:
+        A = rng.standard_normal((K, M) if ta else (M, K)); B = rng.standard_normal((N, K) if tb else (K, N))
+        C0 = rng.standard_normal((M, N))
+        ref = 0.5 * (A.T if ta else A) @ (B.T if tb else B) - 2.0 * C0
+        C = torch.as_tensor(C0, device="cuda").clone()
+        dgemm(torch.as_tensor(A, device="cuda"), torch.as_tensor(B, device="cuda"), C, ta, tb, 0.5, -2.0)
+        assert relerr(C.cpu().numpy(), ref) < 1e-13
+    for m, k in [(7, 3), (130, 64), (500, 64)]:
+        X = rng.standard_normal((m, m)); S = X @ X.T + m * np.eye(m); B = rng.standard_normal((m, k))
+        Sd = torch.as_tensor(S, device="cuda").clone(); Bd = torch.as_tensor(B, device="cuda").clone()
+        spd_solve(Sd, Bd)
+        assert relerr(Bd.cpu().numpy(), np.linalg.solve(S, B)) < 1e-11
+        Ad = torch.as_tensor(S + 0.1 * X, device="cuda").clone()
+        inverse(Ad)
+        assert relerr(Ad.cpu().numpy(), np.linalg.inv(S + 0.1 * X)) < 1e-10
+
+
+@pytest.mark.parametrize("n,M,m,seed", [(400, 16, 12, 1), (1500, 64, 40, 2), (900, 10, 25, 3)])
+def test_enkf_update_vs_oracle(oracle, n, M, m, seed):
+    """Ensemble update == da.py:112-126 applied to the sample covariance (oracle.enkf_update)."""
+    import torch
+    from tx_fast_hydrology_b200 import synthetic as S
+    from tx_fast_hydrology_b200.muskingum import Muskingum
+    from tx_fast_hydrology_b200.da import EnsembleKalmanFilter
+    net_d = S.make_network(n, seed)
+    prm = S.make_params(n, seed, well_posed=True)
+    rng = np.random.default_rng(seed)
+    o0 = prm["o_t"][:, None] * rng.uniform(0.5, 1.5, size=(n, M))
+    d = S.model_dict(net_d, prm, dt_s=300.0)
+    d["o_t"] = o0
+    mdl = Muskingum(d, members=M)
+    gidx = S.make_gauges(net_d["endnodes"], m, seed=seed)
+    t0 = mdl.datetime.value
+    mt = t0 + np.arange(3, dtype=np.int64) * int(3600e9)
+    meas = rng.uniform(0.5, 8.0, size=(3, m))
+    cols = rng.permutation(m)
+    mdf = frame(mt, meas[:, cols], [d["reach_ids"][j] for j in gidx[cols]])
+    Rm = rng.standard_normal((m, m)); R = 1e-2 * np.eye(m) + 1e-3 * (Rm @ Rm.T)
+    Rc = R[np.ix_(cols, cols)]
+    noise = 0.1 * rng.standard_normal((3, m, M))
+    q = rng.uniform(0.5, 2.0, size=n)
+    enkf = EnsembleKalmanFilter(mdl, mdf, q, Rc, obs_noise=noise[:, cols, :])
+    O_f = mdl.o_t_next.copy(); I_f = mdl.i_t_next.copy()
+    enkf.filter()
+    ref_net = {"startnodes": net_d["startnodes"], "endnodes": net_d["endnodes"],
+               "indegree": oracle.compute_indegree(net_d["startnodes"], net_d["endnodes"])}
+    Zp = meas[0][:, None] + noise[0]
+    O_ref, I_ref, _ = oracle.enkf_update(ref_net, O_f, I_f, gidx, Zp, q, R)
+    assert relerr(mdl.o_t_next, O_ref) < RTOL
+    assert relerr(mdl.i_t_next, I_ref) < RTOL

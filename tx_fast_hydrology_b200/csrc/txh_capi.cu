@@ -641,3 +641,139 @@ int txh_check(txh_net* net, void* stream)
 }
 
 }  // extern "C"
+
+// ---- assimilation ---------------------------------------------------------------------------
+namespace {
+int obs_positions(txh_net* net, const int64_t* obs, int64_t m, cudaStream_t st, int32_t** d_pos)
+{
+    std::vector<int32_t> pos(m);
+    for (int64_t k = 0; k < m; ++k) {
+        if (obs[k] < 0 || obs[k] >= net->topo.n) return fail(TXH_E_INVALID, "gauge reach index out of range");
+        if (k > 0 && obs[k] <= obs[k - 1]) return fail(TXH_E_INVALID, "gauge reach indices must be strictly ascending");
+        pos[k] = net->sched.pos_of_reach[obs[k]];
+    }
+    if ((size_t)m > net->tmp_idx_cap) {
+        if (net->d_tmp_idx) CU(cudaFree(net->d_tmp_idx));
+        CU(cudaMalloc((void**)&net->d_tmp_idx, sizeof(int32_t) * m));
+        net->tmp_idx_cap = m;
+    }
+    CU(cudaMemcpyAsync(net->d_tmp_idx, pos.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    *d_pos = net->d_tmp_idx;
+    return TXH_OK;
+}
+int* info_word(txh_net* net) { return net->d_status + 1; }
+}  // namespace
+
+extern "C" {
+
+int txh_enkf_stats(txh_net* net, const double* O, int64_t Mloc, const int64_t* obs, int64_t m, double* rowsum,
+                   double* HX, void* stream)
+{
+    if (!net || !O || !obs || !rowsum || !HX || m < 1) return fail(TXH_E_INVALID, "bad argument");
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_M(Mloc)) || (rc = ensure_device(net))) return rc;
+    int32_t* d_pos = nullptr;
+    if ((rc = obs_positions(net, obs, m, st, &d_pos))) return rc;
+    const int ld = (int)txh_row_stride(Mloc);
+    CU(launch_rowsum(O, ld, (int)Mloc, net->topo.n, rowsum, st));
+    CU(launch_gather_rows(d_pos, m, O, ld, (int)Mloc, HX, st));
+    return TXH_OK;
+}
+
+int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, const double* Zp, const double* mean,
+                   const int64_t* obs, const double* qs, const double* R, double* work, double* W, double* T,
+                   void* stream)
+{
+    if (!net || !HX || !Zp || !mean || !obs || !qs || !R || !work || !W || !T || m < 1 || Mtot < 2)
+        return fail(TXH_E_INVALID, "bad argument");
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = ensure_device(net))) return rc;
+    int32_t* d_pos = nullptr;
+    if ((rc = obs_positions(net, obs, m, st, &d_pos))) return rc;
+    double* S = work;
+    double* HA = S + m * m;
+    double* mean_obs = HA + m * Mtot;
+    CU(launch_gather_rows(d_pos, m, mean, 1, 1, mean_obs, st));
+    CU(launch_innovation(HX, Zp, mean_obs, (int)m, (int)Mtot, HA, W, st));                    // W <- dz
+    CU(launch_dgemm(0, 1, (int)m, (int)m, (int)Mtot, 1.0, HA, (int)Mtot, HA, (int)Mtot, 0.0, S, (int)m, st));
+    CU(launch_innov_cov_finish(S, qs, R, (int)m, 1.0 / (double)(Mtot - 1), st));
+    CU(cudaMemsetAsync(info_word(net), 0, sizeof(int), st));
+    CU(launch_spd_solve(S, W, (int)m, (int)Mtot, info_word(net), st));                        // W <- S^-1 dz
+    CU(launch_dgemm(1, 0, (int)Mtot, (int)Mtot, (int)m, 1.0 / (double)(Mtot - 1), HA, (int)Mtot, W, (int)Mtot, 0.0,
+                    T, (int)Mtot, st));
+    int info = 0;
+    CU(cudaMemcpyAsync(&info, info_word(net), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (info != 0) return fail(TXH_E_INVALID, "innovation covariance is not positive definite");
+    return TXH_OK;
+}
+
+int txh_enkf_apply(txh_net* net, double* O, double* I, int64_t Mloc, const double* Xall, int64_t ldx, int64_t Mtot,
+                   int64_t col0, const double* mean, const double* T, const int64_t* obs, int64_t m, const double* qs,
+                   const double* W, double* G, void* stream)
+{
+    if (!net || !O || !I || !mean || !T || !obs || !qs || !W || !G) return fail(TXH_E_INVALID, "null argument");
+    if (col0 < 0 || col0 + Mloc > Mtot) return fail(TXH_E_INVALID, "shard columns out of range");
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_M(Mloc)) || (rc = ensure_device(net))) return rc;
+    int32_t* d_pos = nullptr;
+    if ((rc = obs_positions(net, obs, m, st, &d_pos))) return rc;
+    const int ld = (int)txh_row_stride(Mloc);
+    if (!Xall) { if (Mtot != Mloc) return fail(TXH_E_INVALID, "gathered ensemble missing"); Xall = O; ldx = ld; }
+    CU(cudaMemsetAsync(G, 0, sizeof(double) * net->topo.n * ld, st));
+    CU(launch_enkf_gain(Xall, (int)ldx, (int)Mtot, mean, T + col0, (int)Mtot, (int)Mloc, G, ld, net->topo.n,
+                        net->num_sms, st));
+    CU(launch_enkf_gauge_term(d_pos, qs, W, (int)m, (int)Mtot, (int)col0, (int)Mloc, G, ld, st));
+    CU(launch_apply_gain(net->d_up_off, net->d_up_pos, G, O, I, net->topo.n, ld, (int)Mloc, st));
+    return TXH_OK;
+}
+
+int txh_dgemm(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+              const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream)
+{
+    if (!A || !B || !C || M < 0 || N < 0 || K < 0) return fail(TXH_E_INVALID, "bad argument");
+    if (txh_device_count() == 0) return fail(TXH_E_NODEVICE, "no CUDA device visible: libtxh has no CPU fallback");
+    CU(launch_dgemm(transA, transB, (int)M, (int)N, (int)K, alpha, A, (int)lda, B, (int)ldb, beta, C, (int)ldc,
+                    (cudaStream_t)stream));
+    return TXH_OK;
+}
+
+int txh_spd_solve(int64_t m, int64_t k, double* S, double* B, void* stream)
+{
+    if (!S || !B || m < 1 || k < 1) return fail(TXH_E_INVALID, "bad argument");
+    if (txh_device_count() == 0) return fail(TXH_E_NODEVICE, "no CUDA device visible: libtxh has no CPU fallback");
+    cudaStream_t st = (cudaStream_t)stream;
+    int* d_info = nullptr;
+    CU(cudaMalloc((void**)&d_info, sizeof(int)));
+    CU(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+    CU(launch_spd_solve(S, B, (int)m, (int)k, d_info, st));
+    int info = 0;
+    CU(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_info);
+    if (info != 0) return fail(TXH_E_INVALID, "matrix is not positive definite");
+    return TXH_OK;
+}
+
+int txh_inverse(int64_t m, double* A, double* work, void* stream)
+{
+    if (!A || !work || m < 1) return fail(TXH_E_INVALID, "bad argument");
+    if (txh_device_count() == 0) return fail(TXH_E_NODEVICE, "no CUDA device visible: libtxh has no CPU fallback");
+    cudaStream_t st = (cudaStream_t)stream;
+    int* d_info = nullptr;
+    CU(cudaMalloc((void**)&d_info, sizeof(int)));
+    CU(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+    CU(launch_inverse(A, work, (int)m, d_info, st));
+    int info = 0;
+    CU(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_info);
+    if (info != 0) return fail(TXH_E_INVALID, "matrix is singular");
+    return TXH_OK;
+}
+
+}  // extern "C"

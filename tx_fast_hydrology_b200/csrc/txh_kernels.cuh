@@ -91,4 +91,21 @@ cudaError_t launch_permute_vec(const int32_t* reach_of_pos, const double* src, d
 
 int64_t launch_count();
 
+// ---- assimilation (txh_da.cu) --------------------------------------------------------------------
+cudaError_t launch_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
+                         const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t st);
+cudaError_t launch_rowsum(const double* X, int ld, int M, int64_t n, double* rowsum, cudaStream_t st);
+cudaError_t launch_innovation(const double* HX, const double* Zp, const double* mean_obs, int m, int M, double* HA,
+                              double* dz, cudaStream_t st);
+cudaError_t launch_innov_cov_finish(double* S, const double* qs, const double* R, int m, double scale, cudaStream_t st);
+cudaError_t launch_spd_solve(double* S, double* B, int m, int k, int* info, cudaStream_t st);
+cudaError_t launch_inverse(double* A, double* W, int m, int* info, cudaStream_t st);
+cudaError_t launch_enkf_gain(const double* Xall, int ldx, int Mtot, const double* mean, const double* T, int ldt, int Mloc,
+                             double* G, int ldg, int64_t n, int num_sms, cudaStream_t st);
+cudaError_t launch_enkf_gauge_term(const int32_t* obs_pos, const double* qs, const double* W, int m, int Mtot, int col0,
+                                   int Mloc, double* G, int ldg, cudaStream_t st);
+cudaError_t launch_scale(double* X, int64_t count, double s, cudaStream_t st);
+cudaError_t launch_gather_cols(const double* P, int n, const int32_t* idx, int m, double* out, cudaStream_t st);
+cudaError_t launch_gather_rows_dense(const double* P, int ncols, const int32_t* idx, int m, double* out, cudaStream_t st);
+
 }  // namespace txh

@@ -19,6 +19,7 @@ namespace txh {
 
 static std::atomic<int64_t> g_launches{0};
 int64_t launch_count() { return g_launches.load(); }
+void count_launch() { g_launches++; }
 
 namespace {
 

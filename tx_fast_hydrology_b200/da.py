@@ -1,0 +1,290 @@
+"""Data-assimilation callbacks on the GPU.
+
+`KalmanFilter` is the drop-in for the reference's dense-covariance filter
+(tx_fast_hydrology/da.py:14-136): same constructor, same hooks
+(`__on_simulation_start__`, `__on_step_end__`), same `filter()` algebra, same
+gauge ordering (columns and R permuted to ascending reach index, da.py:36-44),
+same in-place gain application -- with the covariance propagation
+`_aqat_par` (nutils.py:194-214) running as two member-batched routing launches
+(the columns of P are the members) and the dense products on the FP64 tensor
+cores.  It is meant for the reference's use case, per-sub-basin models of
+10^2..10^3 reaches.
+
+`EnsembleKalmanFilter` is the ensemble form of the same update for networks whose
+n x n covariance cannot exist (n ~ 10^5): P is the sample covariance of the
+member-batched forecast plus a diagonal Q.  Members may be
+sharded over ranks; the statistics are then combined with torch.distributed
+collectives (NCCL over NVLink) between the three device phases.
+"""
+import copy
+import datetime as _dt
+import logging
+
+import numpy as np
+import pandas as pd
+
+from .callbacks import BaseCallback
+from .network import dgemm, inverse
+from .nutils import interpolate_sample
+
+logger = logging.getLogger(__name__)
+
+
+def _gauge_setup(model, measurements):
+    """da.py:27-44: asserts, gauge -> reach index map, ascending-index permutation."""
+    assert isinstance(measurements.index, pd.DatetimeIndex)
+    assert (measurements.index.tz == _dt.timezone.utc)
+    reach_index_map = pd.Series(np.arange(len(model.reach_ids)), index=model.reach_ids)
+    reach_indices = reach_index_map.reindex(measurements.columns).values
+    assert not np.isnan(reach_indices.astype(float)).any()
+    reach_indices = reach_indices.astype(int)
+    permutations = np.argsort(reach_indices)
+    if not (permutations == np.arange(len(reach_indices))).all():
+        logger.warning('Measurement indices not sorted. Permuting columns...')
+    return reach_indices[permutations], permutations
+
+
+class KalmanFilter(BaseCallback):
+    def __init__(self, model, measurements, Q_cov, R_cov, P_t_init):
+        import torch
+        self.model = model
+        self.Q_cov = Q_cov
+        self.reach_ids = model.reach_ids
+        self.gage_reach_ids = measurements.columns
+        self.datetime = copy.deepcopy(model.datetime)
+        self.num_measurements = measurements.shape[1]
+        if model.members != 1:
+            raise ValueError('the dense KalmanFilter needs a single-member model')
+        self.reach_indices, perm = _gauge_setup(model, measurements)
+        s = np.zeros(model.n, dtype=bool)
+        s[self.reach_indices] = True
+        self.s = s
+        self.measurements = measurements.iloc[:, perm]
+        self.R_cov = np.asarray(R_cov, dtype=np.float64)[perm, :][:, perm]
+        self._meas_times = self.measurements.index.astype(int).astype(float).values
+        self._meas_values = np.ascontiguousarray(self.measurements.values, dtype=np.float64)
+        # device-resident matrices
+        self._torch = torch
+        dev = 'cuda'
+        self._P = torch.as_tensor(np.ascontiguousarray(P_t_init, dtype=np.float64), device=dev).clone()
+        self._Q = torch.as_tensor(np.ascontiguousarray(Q_cov, dtype=np.float64), device=dev)
+        self._R = torch.as_tensor(self.R_cov, device=dev)
+        self._idx = torch.as_tensor(self.reach_indices, device=dev)
+        self._P_prev = self._P
+        self.K = self.dz = self.gain = None
+        self.saved_states = {}
+        self.save_state()
+
+    # numpy views of the device matrices, as the reference exposes them
+    @property
+    def P_t_next(self):
+        return self._P.cpu().numpy()
+
+    @P_t_next.setter
+    def P_t_next(self, value):
+        self._P = self._torch.as_tensor(np.ascontiguousarray(value, dtype=np.float64), device='cuda').clone()
+
+    @property
+    def P_t_prev(self):
+        return self._P_prev.cpu().numpy()
+
+    def __on_simulation_start__(self):
+        if self.model.datetime > self.latest_timestamp:
+            return None
+        return self.filter()
+
+    def __on_step_end__(self):
+        if self.model.datetime > self.latest_timestamp:
+            return None
+        return self.filter()
+
+    @property
+    def latest_measurement(self):
+        return self.measurements.iloc[-1, :].values
+
+    @property
+    def latest_timestamp(self):
+        return self.measurements.index[-1]
+
+    def interpolate_input(self, datetime, method='linear'):
+        if method not in ('linear', 'nearest'):
+            raise ValueError
+        return interpolate_sample(float(datetime.value), self._meas_times, self._meas_values,
+                                  method=1 if method == 'linear' else 0)
+
+    def save_state(self):
+        self.saved_states['datetime'] = self.datetime
+        self.saved_states['P_t_next'] = self._P.clone()
+
+    def load_state(self):
+        self.datetime = self.saved_states['datetime']
+        self._P = self.saved_states['P_t_next']
+
+    def _aqat(self, P):
+        """nutils.py:194-214 (`_aqat_par`): A (A P)^T, the columns of P routed as members."""
+        torch = self._torch
+        net, n = self.model.network, self.model.n
+        self.model._sync_coeffs()
+        X = net.alloc_state(n)
+        scr = net.alloc_state(n)
+        out = torch.empty((n, n), dtype=torch.float64, device='cuda')
+        net.pack_dev(P.contiguous(), n, X)
+        net.route_apply(X, scr, n)
+        net.unpack_dev(X, n, out)
+        net.pack_dev(out.t().contiguous(), n, X)
+        net.route_apply(X, scr, n)
+        net.unpack_dev(X, n, out)
+        return out
+
+    def filter(self):
+        """da.py:91-136 on the device; model state is updated in place through its host views."""
+        torch = self._torch
+        mdl = self.model
+        n, m = mdl.n, self.num_measurements
+        Z = self.interpolate_input(mdl.datetime)
+        o_t_next = mdl.o_t_next
+        i_t_next = mdl.i_t_next
+        dz = Z - o_t_next[self.s]                                            # da.py:112
+        P_prev = self._P
+        P = self._aqat(P_prev)                                               # da.py:115
+        P += self._Q                                                         # da.py:117
+        Ps = P.index_select(1, self._idx).contiguous()                       # P[:, s]      n x m
+        S = Ps.index_select(0, self._idx).contiguous() + self._R             # P[s][:, s] + R
+        Sinv = inverse(S)                                                    # da.py:119
+        K = torch.empty((n, m), dtype=torch.float64, device='cuda')
+        dgemm(Ps, Sinv, K)                                                   # K = P[:, s] @ inv(...)
+        dz_d = torch.as_tensor(dz, device='cuda').reshape(m, 1).contiguous()
+        gain_d = torch.empty((n, 1), dtype=torch.float64, device='cuda')
+        dgemm(K, dz_d, gain_d)                                               # da.py:121
+        Prow = P.index_select(0, self._idx).contiguous()                     # P[s]         m x n
+        dgemm(K, Prow, P, alpha=-1.0, beta=1.0)                              # da.py:122: P - K @ P[s]
+        gain = gain_d.cpu().numpy()[:, 0]
+        # _apply_gain (nutils.py:116-134): o_gain = gain, i_gain[j] = sum of upstream gains
+        i_gain = np.zeros(n)
+        nz = mdl.endnodes != mdl.startnodes
+        np.add.at(i_gain, mdl.endnodes[nz], gain[nz])
+        i_t_next += i_gain                                                   # da.py:125 (in place)
+        o_t_next += gain                                                     # da.py:126
+        mdl.i_t_next = i_t_next
+        mdl.o_t_next = o_t_next
+        self._P = P
+        self._P_prev = P_prev
+        self.K = K.cpu().numpy()
+        self.dz = dz
+        self.gain = gain
+        self.datetime = mdl.datetime
+
+
+class EnsembleKalmanFilter(BaseCallback):
+    """Ensemble Kalman update of a member-batched `Muskingum(members=M)`.
+
+    measurements : DataFrame [times x gauges], columns are reach ids (as for KalmanFilter)
+    Q_diag       : scalar or [n] diagonal of the model-noise covariance
+    R_cov        : [m][m] observation-noise covariance
+    obs_noise    : optional [len(measurements)][m][M_total] perturbations added to the interpolated
+                   measurements per member (supplied as data so CPU and GPU consume identical numbers);
+                   zeros if omitted (deterministic ensemble update)
+    every        : pd.Timedelta cadence (e.g. hourly); None = every step as the reference (da.py:56-61)
+    group        : torch.distributed process group when members are sharded over ranks (this rank
+                   holds columns [rank*M, (rank+1)*M) of the global ensemble)
+    """
+
+    def __init__(self, model, measurements, Q_diag, R_cov, obs_noise=None, every=None, group=None):
+        import torch
+        self._torch = torch
+        self.model = model
+        self.reach_indices, perm = _gauge_setup(model, measurements)
+        self.measurements = measurements.iloc[:, perm]
+        self.num_measurements = m = self.measurements.shape[1]
+        self._meas_times = self.measurements.index.astype(int).astype(float).values
+        self._meas_values = np.ascontiguousarray(self.measurements.values, dtype=np.float64)
+        self.every = every
+        self.group = group
+        self.rank, self.world = 0, 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.rank = torch.distributed.get_rank(group)
+            self.world = torch.distributed.get_world_size(group)
+        self.M = model.members
+        self.Mtot = self.M * self.world
+        Rp = np.asarray(R_cov, dtype=np.float64)[perm, :][:, perm]
+        q = np.broadcast_to(np.asarray(Q_diag, dtype=np.float64), (model.n,))
+        self._R = torch.as_tensor(np.ascontiguousarray(Rp), device='cuda')
+        self._qs = torch.as_tensor(np.ascontiguousarray(q[self.reach_indices]), device='cuda')
+        self._noise = None
+        if obs_noise is not None:
+            noise = np.asarray(obs_noise, dtype=np.float64)[:, perm, :]
+            assert noise.shape == (len(self.measurements), m, self.Mtot)
+            self._noise = noise
+        n, Mt = model.n, self.Mtot
+        f64 = dict(dtype=torch.float64, device='cuda')
+        self._rowsum = torch.empty(n, **f64)
+        self._HX = torch.empty((m, self.M), **f64)
+        self._HXall = torch.empty((m, Mt), **f64) if self.world > 1 else self._HX
+        self._work = torch.empty(m * m + 2 * m * Mt + m, **f64)
+        self._W = torch.empty((m, Mt), **f64)
+        self._T = torch.empty((Mt, Mt), **f64)
+        self._G = model.network.alloc_state(self.M)
+        self._Xall = None
+        self.n_updates = 0
+        self.datetime = copy.deepcopy(model.datetime)
+
+    @property
+    def latest_timestamp(self):
+        return self.measurements.index[-1]
+
+    def _due(self):
+        t = self.model.datetime
+        if t > self.latest_timestamp:
+            return False
+        if self.every is not None and (t.value % int(self.every.value)) != 0:
+            return False
+        return True
+
+    def __on_simulation_start__(self):
+        return self.filter() if self._due() else None
+
+    def __on_step_end__(self):
+        return self.filter() if self._due() else None
+
+    def perturbed_observations(self, datetime):
+        """[m][Mtot] per-member observations at `datetime` (interpolated measurements + supplied noise)."""
+        x = float(datetime.value)
+        Z = interpolate_sample(x, self._meas_times, self._meas_values)
+        Zp = np.repeat(Z[:, None], self.Mtot, axis=1)
+        if self._noise is not None:
+            flat = self._noise.reshape(self._noise.shape[0], -1)
+            Zp = Zp + interpolate_sample(x, self._meas_times, flat).reshape(Z.size, self.Mtot)
+        return np.ascontiguousarray(Zp)
+
+    def filter(self, Zp_dev=None):
+        """One ensemble update on the device.  `Zp_dev` ([m][Mtot] CUDA tensor) overrides the
+        interpolated observations (used by the fast path that pre-stages them)."""
+        torch = self._torch
+        mdl = self.model
+        net = mdl.network
+        O, I = mdl.device_state
+        M, Mt, m = self.M, self.Mtot, self.num_measurements
+        if Zp_dev is None:
+            Zp_dev = torch.as_tensor(self.perturbed_observations(mdl.datetime), device='cuda')
+        dist = torch.distributed
+        net.enkf_stats(O, M, self.reach_indices, self._rowsum, self._HX)
+        Xall, ldx = None, 0
+        if self.world > 1:
+            dist.all_reduce(self._rowsum, group=self.group)                  # ensemble mean over all shards
+            parts = [torch.empty_like(self._HX) for _ in range(self.world)]
+            dist.all_gather(parts, self._HX, group=self.group)
+            self._HXall = torch.cat(parts, dim=1).contiguous()
+            ld = net.row_stride(M)
+            if self._Xall is None:
+                self._Xall = torch.empty((self.world, mdl.n, ld), dtype=torch.float64, device='cuda')
+            dist.all_gather_into_tensor(self._Xall, O, group=self.group)     # anomalies of every shard
+            Xall = self._Xall.permute(1, 0, 2)[:, :, :M].reshape(mdl.n, Mt).contiguous()
+            ldx = Mt
+        mean = self._rowsum.mul_(1.0 / Mt)
+        net.enkf_solve(m, Mt, self._HXall, Zp_dev, mean, self.reach_indices, self._qs, self._R, self._work,
+                       self._W, self._T)
+        net.enkf_apply(O, I, M, Xall, ldx, Mt, self.rank * M, mean, self._T, self.reach_indices, self._qs,
+                       self._W, self._G)
+        mdl._device_advanced()
+        self.n_updates += 1
+        self.datetime = mdl.datetime

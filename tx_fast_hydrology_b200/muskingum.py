@@ -72,16 +72,15 @@ class Muskingum:
         self.gamma = np.zeros(n, dtype=np.float64)
         self._coef_seen = None
         self._dev = None                 # device tensors, created on first use
-        self._host = {}                  # materialised numpy views
-        self._host_dirty = False         # host copy may have been mutated since materialised
+        self._dev_valid = False
         shape = (n,) if self.members == 1 else (n, self.members)
-        o0 = np.asarray(self.o_t_next, dtype=np.float64)
+        o0 = np.asarray(self._o_t_initial, dtype=np.float64)
         if o0.shape != shape:
             o0 = np.broadcast_to(o0.reshape(n, -1), (n, self.members)).reshape(shape)
+        # materialised numpy views of the state; "dirty" = may differ from the device copy
         self._host = {'o_t_next': np.array(o0, dtype=np.float64), 'i_t_next': np.zeros(shape),
                       'o_t_prev': np.zeros(shape), 'i_t_prev': np.zeros(shape)}
         self._host_dirty = True
-        self._dev_valid = False
         self.init_states(o_t_next=self._host['o_t_next'])
         self._host['o_t_prev'] = self._host['o_t_next'].copy()
         self._host['i_t_prev'] = self._host['i_t_next'].copy()
@@ -205,7 +204,6 @@ class Muskingum:
             raise ValueError('`startnodes` must equal arange(n)')
         self.network = RiverNetwork(self.endnodes, self._sched_params)
         self.indegree = self.compute_indegree(self.startnodes, self.endnodes)
-        self._host = {'o_t_next': self._o_t_initial}
 
     def load_model_file(self, file_path, load_optional=True):
         self.load_model(load_model_file(file_path, load_optional=load_optional))
@@ -281,7 +279,6 @@ class Muskingum:
     def init_states(self, o_t_next=None, i_t_next=None):
         """muskingum.py:410-419: i = scatter-add of o over endnodes (self-loops included)."""
         h = self._materialise()
-        shape = h['o_t_next'].shape if 'o_t_next' in h and hasattr(h['o_t_next'], 'shape') else None
         full = (self.n,) if self.members == 1 else (self.n, self.members)
         o = np.zeros(full) if o_t_next is None else np.array(
             np.broadcast_to(np.asarray(o_t_next, dtype=np.float64).reshape(self.n, -1),
@@ -297,7 +294,6 @@ class Muskingum:
             if k not in h or np.shape(h[k]) != full:
                 h[k] = np.zeros(full)
         self._host_dirty = True
-        del shape
 
     # ------------------------------------------------------------------ stepping
     def step_iter(self, p_t_next, timedelta=None):

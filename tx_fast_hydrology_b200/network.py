@@ -218,6 +218,25 @@ class RiverNetwork:
         L.check(self._lib.txh_apply_gain(self.handle, _cuda_ptr(G), _cuda_ptr(O), _cuda_ptr(I), int(M),
                                          _stream_ptr()))
 
+    # ---- assimilation ----------------------------------------------------------------------
+    def enkf_stats(self, O, Mloc, obs_reach, rowsum, HX):
+        idx = L.as_i64(obs_reach)
+        L.check(self._lib.txh_enkf_stats(self.handle, _cuda_ptr(O), int(Mloc), L.ptr_i64(idx), idx.size,
+                                         _cuda_ptr(rowsum), _cuda_ptr(HX), _stream_ptr()))
+
+    def enkf_solve(self, m, Mtot, HX, Zp, mean, obs_reach, qs, R, work, W, T):
+        idx = L.as_i64(obs_reach)
+        L.check(self._lib.txh_enkf_solve(self.handle, int(m), int(Mtot), _cuda_ptr(HX), _cuda_ptr(Zp),
+                                         _cuda_ptr(mean), L.ptr_i64(idx), _cuda_ptr(qs), _cuda_ptr(R),
+                                         _cuda_ptr(work), _cuda_ptr(W), _cuda_ptr(T), _stream_ptr()))
+
+    def enkf_apply(self, O, I, Mloc, Xall, ldx, Mtot, col0, mean, T, obs_reach, qs, W, G):
+        idx = L.as_i64(obs_reach)
+        L.check(self._lib.txh_enkf_apply(self.handle, _cuda_ptr(O), _cuda_ptr(I), int(Mloc),
+                                         _cuda_ptr(Xall) if Xall is not None else None, int(ldx), int(Mtot),
+                                         int(col0), _cuda_ptr(mean), _cuda_ptr(T), L.ptr_i64(idx), idx.size,
+                                         _cuda_ptr(qs), _cuda_ptr(W), _cuda_ptr(G), _stream_ptr()))
+
     def check(self):
         L.check(self._lib.txh_check(self.handle, _stream_ptr() if self._has_cuda() else None))
 
@@ -228,3 +247,27 @@ class RiverNetwork:
             return torch.cuda.is_available()
         except Exception:
             return False
+
+
+def dgemm(A, B, C, transA=False, transB=False, alpha=1.0, beta=0.0):
+    """C = alpha op(A) op(B) + beta C on the FP64 tensor cores (row-major CUDA tensors, float64)."""
+    lib = L.load()
+    M, N = C.shape
+    K = A.shape[0] if transA else A.shape[1]
+    L.check(lib.txh_dgemm(int(transA), int(transB), M, N, K, float(alpha), _cuda_ptr(A), A.stride(0),
+                          _cuda_ptr(B), B.stride(0), float(beta), _cuda_ptr(C), C.stride(0), _stream_ptr()))
+    return C
+
+
+def spd_solve(S, B):
+    """In place: B <- S^-1 B for SPD S (S is overwritten by its Cholesky factor)."""
+    L.check(L.load().txh_spd_solve(S.shape[0], B.shape[1], _cuda_ptr(S), _cuda_ptr(B), _stream_ptr()))
+    return B
+
+
+def inverse(A):
+    """In place: A <- inv(A), Gauss-Jordan with partial pivoting."""
+    import torch
+    work = torch.empty_like(A)
+    L.check(L.load().txh_inverse(A.shape[0], _cuda_ptr(A), _cuda_ptr(work), _stream_ptr()))
+    return A
