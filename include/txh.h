@@ -103,9 +103,10 @@ int txh_init_inflows(txh_net* net, const double* O_dev, double* I_dev, int64_t M
  * The (T x n) lateral-inflow table `simulate` interpolates every step
  * (muskingum.py:526-531 -> nutils.interpolate_sample, nutils.py:5-39), uploaded once.
  * times: float64 ns since epoch (index.astype(int).astype(float)); table: host [R][n] in
- * reach order.  member_mul (optional, host [R][M]): member m sees table[r][j]*member_mul[r][m]. */
+ * reach order (pinned memory makes the upload asynchronous; the call returns after it completed).
+ * member_mul (optional, host [R][M]): member m sees table[r][j]*member_mul[r][m]. */
 int txh_forcing_create(txh_net* net, int64_t R, const double* times, const double* table_host,
-                       int64_t M, const double* member_mul_host, txh_forcing** out);
+                       int64_t M, const double* member_mul_host, void* stream, txh_forcing** out);
 void txh_forcing_destroy(txh_forcing* f);
 
 /* ---- routing ---------------------------------------------------------------------------
@@ -171,7 +172,8 @@ int txh_spd_solve(int64_t m, int64_t k, double* S_dev, double* B_dev, void* stre
 /* A <- inv(A) by Gauss-Jordan with partial pivoting (np.linalg.inv, da.py:119); work [m][m]. Synchronous. */
 int txh_inverse(int64_t m, double* A_dev, double* work_dev, void* stream);
 
-/* Synchronise `stream` and report a poisoned launch (TXH_E_WATCHDOG) or a CUDA fault. */
+/* Synchronise `stream` and report a poisoned launch (TXH_E_WATCHDOG), an innovation covariance that was
+ * not positive definite in an earlier txh_enkf_solve (TXH_E_INVALID), or a CUDA fault. */
 int txh_check(txh_net* net, void* stream);
 
 /* kernel-launch counter (bench.py's gpu_launches claim) */

@@ -69,7 +69,11 @@ struct txh_net {
     StepInterp* d_unit_step = nullptr;
     int32_t* d_rec_slot = nullptr;
     int32_t* d_tmp_idx = nullptr; size_t tmp_idx_cap = 0;
-    int32_t* h_status = nullptr;        // pinned mirror of d_status
+    int32_t* h_status = nullptr;        // pinned mirror of d_status (word 0) and the solver info (word 1)
+    StepInterp* h_steps = nullptr; size_t h_steps_cap = 0;   // pinned staging of the per-step interpolation
+    cudaEvent_t steps_copied = nullptr;
+    std::vector<int64_t> obs_cached;    // gauge list whose positions are resident in d_obs
+    int32_t* d_obs = nullptr; size_t obs_cap = 0;
 };
 
 struct txh_forcing {
@@ -113,8 +117,9 @@ int ensure_device(txh_net* net)
     net->d_status = reinterpret_cast<int32_t*>(net->d_qctl + 4);
     CU(cudaMemset(net->d_qctl, 0, 64));
     CU(cudaMalloc((void**)&net->d_rec_slot, sizeof(int32_t) * net->topo.n));
-    CU(cudaMallocHost((void**)&net->h_status, sizeof(int32_t)));
-    *net->h_status = 0;
+    CU(cudaMallocHost((void**)&net->h_status, 2 * sizeof(int32_t)));
+    net->h_status[0] = net->h_status[1] = 0;
+    CU(cudaEventCreateWithFlags(&net->steps_copied, cudaEventDisableTiming));
     const StepInterp unit{0, 0, 1.0, 0.0};
     CU(cudaMalloc((void**)&net->d_unit_step, sizeof(StepInterp)));
     CU(cudaMemcpy(net->d_unit_step, &unit, sizeof(unit), cudaMemcpyHostToDevice));
@@ -240,7 +245,7 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
             }
         }
     }
-    CU(cudaMemcpyAsync(net->h_status, net->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return TXH_OK;
 }
 
@@ -287,6 +292,9 @@ void txh_destroy(txh_net* net)
         if (net->d_side) cudaFree(net->d_side);
         if (net->d_steps) cudaFree(net->d_steps);
         if (net->d_tmp_idx) cudaFree(net->d_tmp_idx);
+        if (net->d_obs) cudaFree(net->d_obs);
+        if (net->h_steps) cudaFreeHost(net->h_steps);
+        if (net->steps_copied) cudaEventDestroy(net->steps_copied);
         if (net->h_status) cudaFreeHost(net->h_status);
     }
     delete net;
@@ -480,11 +488,12 @@ int txh_init_inflows(txh_net* net, const double* O, double* I, int64_t M, void* 
 }
 
 int txh_forcing_create(txh_net* net, int64_t R, const double* times, const double* table, int64_t M,
-                       const double* mul, txh_forcing** out)
+                       const double* mul, void* stream, txh_forcing** out)
 {
     if (!net || !times || !table || !out || R < 1) return fail(TXH_E_INVALID, "bad argument");
     int rc;
     if ((rc = ensure_device(net))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
     for (int64_t r = 1; r < R; ++r)
         if (!(times[r] >= times[r - 1])) return fail(TXH_E_INVALID, "forcing times must be sorted ascending");
     const int64_t n = net->topo.n;
@@ -492,20 +501,20 @@ int txh_forcing_create(txh_net* net, int64_t R, const double* times, const doubl
     if (!f) return fail(TXH_E_INVALID, "out of memory");
     f->net = net; f->R = R; f->M = mul ? M : 0;
     f->times.assign(times, times + R);
-    // permute columns into schedule order on the host (one-time), then one H2D copy
-    std::vector<double> perm((size_t)R * n);
-    for (int64_t r = 0; r < R; ++r) {
-        const double* src = table + (size_t)r * n;
-        double* dst = perm.data() + (size_t)r * n;
-        for (int64_t k = 0; k < n; ++k) dst[k] = src[net->sched.reach_of_pos[k]];
-    }
+    // one H2D copy of the table as given (pinned or pageable), columns permuted into schedule
+    // order on the device
+    double* tmp = nullptr;
     cudaError_t e = cudaMalloc((void**)&f->d_F, sizeof(double) * R * n);
-    if (e == cudaSuccess) e = cudaMemcpy(f->d_F, perm.data(), sizeof(double) * R * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&tmp, sizeof(double) * R * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, table, sizeof(double) * R * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_permute_rows(net->d_reach_of_pos, tmp, f->d_F, n, R, st);
     if (e == cudaSuccess && mul) {
-        if (M < 1) { cudaFree(f->d_F); delete f; return fail(TXH_E_INVALID, "member multipliers need M >= 1"); }
+        if (M < 1) { cudaFree(f->d_F); cudaFree(tmp); delete f; return fail(TXH_E_INVALID, "member multipliers need M >= 1"); }
         e = cudaMalloc((void**)&f->d_W, sizeof(double) * R * M);
-        if (e == cudaSuccess) e = cudaMemcpy(f->d_W, mul, sizeof(double) * R * M, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_W, mul, sizeof(double) * R * M, cudaMemcpyHostToDevice, st);
     }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
     if (e != cudaSuccess) { cudaFree(f->d_F); cudaFree(f->d_W); delete f; return cuda_fail(e, "forcing upload"); }
     *out = f;
     return TXH_OK;
@@ -561,8 +570,16 @@ int txh_route_run(txh_net* net, double* O, double* I, int64_t M, const txh_forci
             CU(cudaMalloc((void**)&net->d_steps, sizeof(StepInterp) * nsteps));
             net->steps_cap = nsteps;
         }
-        CU(cudaMemcpyAsync(net->d_steps, steps.data(), sizeof(StepInterp) * nsteps, cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));
+        // pinned staging + an event instead of a stream synchronisation: launches stay back to back
+        CU(cudaEventSynchronize(net->steps_copied));
+        if ((size_t)nsteps > net->h_steps_cap) {
+            if (net->h_steps) CU(cudaFreeHost(net->h_steps));
+            CU(cudaMallocHost((void**)&net->h_steps, sizeof(StepInterp) * nsteps));
+            net->h_steps_cap = nsteps;
+        }
+        std::memcpy(net->h_steps, steps.data(), sizeof(StepInterp) * nsteps);
+        CU(cudaMemcpyAsync(net->d_steps, net->h_steps, sizeof(StepInterp) * nsteps, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(net->steps_copied, st));
         d_steps = net->d_steps;
     }
     const int32_t* rec_slot = nullptr;
@@ -636,7 +653,8 @@ int txh_check(txh_net* net, void* stream)
     if (!net) return fail(TXH_E_INVALID, "null argument");
     if (!net->dev_ready) return TXH_OK;
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    if (*net->h_status != 0) return fail(TXH_E_WATCHDOG, "a routing launch bailed out on its dataflow watchdog");
+    if (net->h_status[0] != 0) return fail(TXH_E_WATCHDOG, "a routing launch bailed out on its dataflow watchdog");
+    if (net->h_status[1] != 0) return fail(TXH_E_INVALID, "an innovation covariance was not positive definite");
     return TXH_OK;
 }
 
@@ -646,20 +664,25 @@ int txh_check(txh_net* net, void* stream)
 namespace {
 int obs_positions(txh_net* net, const int64_t* obs, int64_t m, cudaStream_t st, int32_t** d_pos)
 {
+    if ((int64_t)net->obs_cached.size() == m && std::equal(obs, obs + m, net->obs_cached.begin())) {
+        *d_pos = net->d_obs;                              // same gauges as last time: already resident
+        return TXH_OK;
+    }
     std::vector<int32_t> pos(m);
     for (int64_t k = 0; k < m; ++k) {
         if (obs[k] < 0 || obs[k] >= net->topo.n) return fail(TXH_E_INVALID, "gauge reach index out of range");
         if (k > 0 && obs[k] <= obs[k - 1]) return fail(TXH_E_INVALID, "gauge reach indices must be strictly ascending");
         pos[k] = net->sched.pos_of_reach[obs[k]];
     }
-    if ((size_t)m > net->tmp_idx_cap) {
-        if (net->d_tmp_idx) CU(cudaFree(net->d_tmp_idx));
-        CU(cudaMalloc((void**)&net->d_tmp_idx, sizeof(int32_t) * m));
-        net->tmp_idx_cap = m;
+    if ((size_t)m > net->obs_cap) {
+        if (net->d_obs) CU(cudaFree(net->d_obs));
+        CU(cudaMalloc((void**)&net->d_obs, sizeof(int32_t) * m));
+        net->obs_cap = m;
     }
-    CU(cudaMemcpyAsync(net->d_tmp_idx, pos.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(net->d_obs, pos.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
-    *d_pos = net->d_tmp_idx;
+    net->obs_cached.assign(obs, obs + m);
+    *d_pos = net->d_obs;
     return TXH_OK;
 }
 int* info_word(txh_net* net) { return net->d_status + 1; }
@@ -700,14 +723,11 @@ int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, cons
     CU(launch_innovation(HX, Zp, mean_obs, (int)m, (int)Mtot, HA, W, st));                    // W <- dz
     CU(launch_dgemm(0, 1, (int)m, (int)m, (int)Mtot, 1.0, HA, (int)Mtot, HA, (int)Mtot, 0.0, S, (int)m, st));
     CU(launch_innov_cov_finish(S, qs, R, (int)m, 1.0 / (double)(Mtot - 1), st));
-    CU(cudaMemsetAsync(info_word(net), 0, sizeof(int), st));
     CU(launch_spd_solve(S, W, (int)m, (int)Mtot, info_word(net), st));                        // W <- S^-1 dz
     CU(launch_dgemm(1, 0, (int)Mtot, (int)Mtot, (int)m, 1.0 / (double)(Mtot - 1), HA, (int)Mtot, W, (int)Mtot, 0.0,
                     T, (int)Mtot, st));
-    int info = 0;
-    CU(cudaMemcpyAsync(&info, info_word(net), sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (info != 0) return fail(TXH_E_INVALID, "innovation covariance is not positive definite");
+    // asynchronous: a failed factorisation leaves a non-zero info word that txh_check reports
+    CU(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return TXH_OK;
 }
 

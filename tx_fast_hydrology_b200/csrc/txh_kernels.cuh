@@ -85,6 +85,8 @@ cudaError_t launch_unpack(const int32_t* reach_of_pos, const double* src, double
                           int ld, int dst_member_major, cudaStream_t st);
 cudaError_t launch_gather_rows(const int32_t* pos, int64_t count, const double* X, int ld, int M,
                                double* out, cudaStream_t st);
+cudaError_t launch_permute_rows(const int32_t* reach_of_pos, const double* src, double* dst, int64_t n, int64_t R,
+                                cudaStream_t st);
 // vector permute: dst[pos] = src[reach_of_pos[pos]]
 cudaError_t launch_permute_vec(const int32_t* reach_of_pos, const double* src, double* dst, int64_t n,
                                cudaStream_t st);

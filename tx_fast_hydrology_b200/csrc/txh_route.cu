@@ -689,6 +689,16 @@ gather_rows_kernel(const int32_t* pos, long long count, const double* X, int ld,
     out[gid] = X[(size_t)pos[k] * ld + m];
 }
 
+// dst[r][k] = src[r][reach_of_pos[k]] for a row-major [R][n] table
+__global__ void __launch_bounds__(256)
+permute_rows_kernel(const int32_t* reach_of_pos, const double* src, double* dst, long long n, long long R)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n * R) return;
+    const long long r = gid / n, k = gid - r * n;
+    dst[gid] = src[r * n + reach_of_pos[k]];
+}
+
 __global__ void __launch_bounds__(256)
 permute_vec_kernel(const int32_t* reach_of_pos, const double* src, double* dst, long long n)
 {
@@ -777,6 +787,14 @@ cudaError_t launch_gather_rows(const int32_t* pos, int64_t count, const double* 
                                double* out, cudaStream_t st)
 {
     gather_rows_kernel<<<blocks_for(count * M, 256), 256, 0, st>>>(pos, count, X, ld, M, out);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_permute_rows(const int32_t* reach_of_pos, const double* src, double* dst, int64_t n, int64_t R,
+                                cudaStream_t st)
+{
+    permute_rows_kernel<<<blocks_for(n * R, 256), 256, 0, st>>>(reach_of_pos, src, dst, n, R);
     g_launches++;
     return cudaGetLastError();
 }

@@ -25,6 +25,7 @@ import pandas as pd
 
 from .callbacks import BaseCallback
 from .network import dgemm, inverse
+from .sharding import combine_statistics
 from .nutils import interpolate_sample
 
 logger = logging.getLogger(__name__)
@@ -270,10 +271,8 @@ class EnsembleKalmanFilter(BaseCallback):
         net.enkf_stats(O, M, self.reach_indices, self._rowsum, self._HX)
         Xall, ldx = None, 0
         if self.world > 1:
-            dist.all_reduce(self._rowsum, group=self.group)                  # ensemble mean over all shards
-            parts = [torch.empty_like(self._HX) for _ in range(self.world)]
-            dist.all_gather(parts, self._HX, group=self.group)
-            self._HXall = torch.cat(parts, dim=1).contiguous()
+            # ensemble mean over all shards (all-reduce) + every shard's gauge rows (all-gather)
+            self._rowsum, self._HXall = combine_statistics(self._rowsum, self._HX, 1, group=self.group)
             ld = net.row_stride(M)
             if self._Xall is None:
                 self._Xall = torch.empty((self.world, mdl.n, ld), dtype=torch.float64, device='cuda')

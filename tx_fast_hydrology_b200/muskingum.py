@@ -390,6 +390,30 @@ class Muskingum:
         self.datetime = self.datetime + nsteps * self.timedelta
         return rec
 
+    def run_assimilating(self, forcing, nsteps, enkf, every, observations):
+        """Device-resident run with periodic ensemble assimilation: `every` routing steps in one
+        persistent launch, then one `EnsembleKalmanFilter` update with `observations[k]` ([m][Mtot]
+        CUDA tensor of per-member observations for the k-th update), repeated; nothing returns to
+        the host in between.  Mirrors simulate + a KalmanFilter callback gated to every `every`-th
+        step (the reference filters every step, da.py:56-61; SURVEY.md section 8c iv)."""
+        self._ensure_device()
+        self._sync_coeffs()
+        d, net, M = self._dev, self.network, self.members
+        step_ns = int(self.timedelta.value)
+        t = int(self.datetime.value)
+        nwin = nsteps // every
+        for k in range(nwin):
+            net.route_run(d['O'], d['I'], M, forcing, t, step_ns, every)
+            t += every * step_ns
+            self._datetime = pd.Timestamp(t, tz='UTC')
+            enkf.filter(observations[k])
+        rest = nsteps - nwin * every
+        if rest:
+            net.route_run(d['O'], d['I'], M, forcing, t, step_ns, rest)
+            t += rest * step_ns
+        self._datetime = pd.Timestamp(t, tz='UTC')
+        self._device_advanced()
+
     @property
     def device_state(self):
         """(O, I) CUDA tensors [n][row_stride(members)] in schedule order."""

@@ -24,28 +24,35 @@ class Forcing:
     """Lateral-inflow table resident in HBM (`txh_forcing`)."""
 
     def __init__(self, net, times_ns, table, member_mul=None):
+        """`table` [R][n] and `member_mul` [R][M]: numpy arrays or (pinned) CPU torch tensors, float64."""
         lib = L.load()
         self.net = net
         times = L.as_f64(np.asarray(times_ns).astype(np.float64))
-        table = L.as_f64(table)
-        R, n = table.shape
+        tptr, tshape, self._keep_t = self._host_ptr(table)
+        R, n = tshape
         if n != net.n or times.size != R:
             raise ValueError("forcing table must be [len(times)][n]")
-        M = 0
-        mp = L.p_f64()
+        M, mp = 0, None
+        self.h2d_bytes = R * n * 8
         if member_mul is not None:
-            member_mul = L.as_f64(member_mul)
-            if member_mul.shape[0] != R:
+            mp, mshape, self._keep_m = self._host_ptr(member_mul)
+            if mshape[0] != R:
                 raise ValueError("member multipliers must be [len(times)][M]")
-            M = member_mul.shape[1]
-            mp = L.ptr_f64(member_mul)
+            M = mshape[1]
+            self.h2d_bytes += R * M * 8
         h = ctypes.c_void_p()
-        L.check(lib.txh_forcing_create(net.handle, R, L.ptr_f64(times), L.ptr_f64(table), M, mp,
-                                       ctypes.byref(h)))
+        L.check(lib.txh_forcing_create(net.handle, R, L.ptr_f64(times), tptr, M, mp, _stream_ptr(), ctypes.byref(h)))
         self.handle = h
         self.R = R
         self.M = M
-        self.h2d_bytes = table.nbytes + (member_mul.nbytes if member_mul is not None else 0)
+
+    @staticmethod
+    def _host_ptr(a):
+        if hasattr(a, "data_ptr"):                      # CPU torch tensor (possibly pinned)
+            assert a.dtype.is_floating_point and a.element_size() == 8 and a.is_contiguous() and not a.is_cuda
+            return ctypes.c_void_p(a.data_ptr()), tuple(a.shape), a
+        a = L.as_f64(a)
+        return ctypes.c_void_p(a.ctypes.data), a.shape, a
 
     def close(self):
         if getattr(self, "handle", None):
@@ -169,14 +176,21 @@ class RiverNetwork:
         return torch.zeros((self.n, self.row_stride(M)), dtype=torch.float64, device=device)
 
     def pack_host(self, src, M, dst, member_major=False):
-        src = L.as_f64(src)
-        L.check(self._lib.txh_pack_host(self.handle, L.ptr_f64(src), int(M), int(member_major),
+        """Host array (numpy, or a pinned CPU torch tensor) in reach order -> device schedule order."""
+        ptr, _, keep = Forcing._host_ptr(src)
+        L.check(self._lib.txh_pack_host(self.handle, ctypes.cast(ptr, L.p_f64), int(M), int(member_major),
                                         _cuda_ptr(dst), _stream_ptr()))
+        del keep
 
-    def unpack_host(self, src, M, member_major=False):
-        out = np.empty((M, self.n) if member_major else (self.n, M), dtype=np.float64)
-        L.check(self._lib.txh_unpack_host(self.handle, _cuda_ptr(src), int(M), int(member_major),
-                                          L.ptr_f64(out), _stream_ptr()))
+    def unpack_host(self, src, M, member_major=False, out=None):
+        """Device schedule order -> host reach order; `out` may be a pinned CPU torch tensor."""
+        if out is None:
+            out = np.empty((M, self.n) if member_major else (self.n, M), dtype=np.float64)
+            optr = L.ptr_f64(out)
+        else:
+            optr = ctypes.cast(ctypes.c_void_p(out.data_ptr()), L.p_f64)
+        L.check(self._lib.txh_unpack_host(self.handle, _cuda_ptr(src), int(M), int(member_major), optr,
+                                          _stream_ptr()))
         return out
 
     def pack_dev(self, src, M, dst):
