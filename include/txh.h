@@ -151,10 +151,16 @@ int txh_apply_gain(txh_net* net, const double* G_dev, double* O_dev, double* I_d
  * obs_reach: gauged reach indices ascending (da.py:33-44); all matrices row-major on the device. */
 int txh_enkf_stats(txh_net* net, const double* O_dev, int64_t Mloc, const int64_t* obs_reach_host, int64_t m,
                    double* rowsum_dev /*[n] schedule order*/, double* HX_dev /*[m][Mloc]*/, void* stream);
+/* doubles of workspace txh_enkf_solve needs */
+int64_t txh_enkf_work_size(int64_t m, int64_t Mtot);
+/* Dinv (optional): the inverse of D = R + diag(qs), which is constant between updates -- dinv_kind 1: its
+ * diagonal [m] (R diagonal), 2: dense [m][m], 0: not supplied.  When it is supplied and Mtot < m the m x m
+ * solve collapses to an Mtot x Mtot one in ensemble space (Sherman-Morrison-Woodbury; txh_da.cu). */
 int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX_dev /*[m][Mtot]*/,
                    const double* Zp_dev /*[m][Mtot]*/, const double* mean_dev /*[n] schedule order*/,
                    const int64_t* obs_reach_host, const double* qs_dev /*[m] diag(Q) at the gauges*/,
-                   const double* R_dev /*[m][m]*/, double* work_dev /* m*m + 2*m*Mtot + m doubles */,
+                   const double* R_dev /*[m][m]*/, const double* Dinv_dev, int dinv_kind,
+                   double* work_dev /* txh_enkf_work_size(m, Mtot) doubles */,
                    double* W_dev /*[m][Mtot] out*/, double* T_dev /*[Mtot][Mtot] out*/, void* stream);
 int txh_enkf_apply(txh_net* net, double* O_dev, double* I_dev, int64_t Mloc, const double* Xall_dev /* [n][ldx] gathered
                    ensemble in schedule order, or NULL to use O_dev (Mtot == Mloc) */, int64_t ldx, int64_t Mtot,

@@ -155,9 +155,12 @@ def test_dense_linear_algebra():
         assert relerr(Ad.cpu().numpy(), np.linalg.inv(S + 0.1 * X)) < 1e-10
 
 
-@pytest.mark.parametrize("n,M,m,seed", [(400, 16, 12, 1), (1500, 64, 40, 2), (900, 10, 25, 3)])
-def test_enkf_update_vs_oracle(oracle, n, M, m, seed):
-    """Ensemble update == da.py:112-126 applied to the sample covariance (oracle.enkf_update)."""
+@pytest.mark.parametrize("n,M,m,seed,diag", [(400, 16, 12, 1, False), (1500, 64, 40, 2, False), (900, 10, 25, 3, False),
+                                             (2000, 64, 100, 4, True), (1200, 32, 80, 5, False),
+                                             (1000, 96, 130, 6, True)])
+def test_enkf_update_vs_oracle(oracle, n, M, m, seed, diag):
+    """Ensemble update == da.py:112-126 applied to the sample covariance (oracle.enkf_update).  Covers the
+    direct m x m solve (M >= m) and the ensemble-space solve (M < m) with diagonal and dense R."""
     import torch
     from tx_fast_hydrology_b200 import synthetic as S
     from tx_fast_hydrology_b200.muskingum import Muskingum
@@ -175,7 +178,7 @@ def test_enkf_update_vs_oracle(oracle, n, M, m, seed):
     meas = rng.uniform(0.5, 8.0, size=(3, m))
     cols = rng.permutation(m)
     mdf = frame(mt, meas[:, cols], [d["reach_ids"][j] for j in gidx[cols]])
-    Rm = rng.standard_normal((m, m)); R = 1e-2 * np.eye(m) + 1e-3 * (Rm @ Rm.T)
+    Rm = rng.standard_normal((m, m)); R = 1e-2 * np.eye(m) + (0.0 if diag else 1e-3) * (Rm @ Rm.T)
     Rc = R[np.ix_(cols, cols)]
     noise = 0.1 * rng.standard_normal((3, m, M))
     q = rng.uniform(0.5, 2.0, size=n)

@@ -705,27 +705,51 @@ int txh_enkf_stats(txh_net* net, const double* O, int64_t Mloc, const int64_t* o
     return TXH_OK;
 }
 
+int64_t txh_enkf_work_size(int64_t m, int64_t Mtot)
+{
+    const int64_t direct = m * m + 2 * m * Mtot + m;
+    const int64_t nsplit = 8;
+    const int64_t woodbury = 4 * m * Mtot + nsplit * 2 * Mtot * Mtot;
+    return std::max(direct, woodbury);
+}
+
 int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, const double* Zp, const double* mean,
-                   const int64_t* obs, const double* qs, const double* R, double* work, double* W, double* T,
-                   void* stream)
+                   const int64_t* obs, const double* qs, const double* R, const double* Dinv, int dinv_kind,
+                   double* work, double* W, double* T, void* stream)
 {
     if (!net || !HX || !Zp || !mean || !obs || !qs || !R || !work || !W || !T || m < 1 || Mtot < 2)
         return fail(TXH_E_INVALID, "bad argument");
+    if (dinv_kind < 0 || dinv_kind > 2 || (dinv_kind != 0 && !Dinv)) return fail(TXH_E_INVALID, "bad D^-1 argument");
     int rc;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = ensure_device(net))) return rc;
     int32_t* d_pos = nullptr;
     if ((rc = obs_positions(net, obs, m, st, &d_pos))) return rc;
-    double* S = work;
-    double* HA = S + m * m;
-    double* mean_obs = HA + m * Mtot;
-    CU(launch_gather_rows(d_pos, m, mean, 1, 1, mean_obs, st));
-    CU(launch_innovation(HX, Zp, mean_obs, (int)m, (int)Mtot, HA, W, st));                    // W <- dz
-    CU(launch_dgemm(0, 1, (int)m, (int)m, (int)Mtot, 1.0, HA, (int)Mtot, HA, (int)Mtot, 0.0, S, (int)m, st));
-    CU(launch_innov_cov_finish(S, qs, R, (int)m, 1.0 / (double)(Mtot - 1), st));
-    CU(launch_spd_solve(S, W, (int)m, (int)Mtot, info_word(net), st));                        // W <- S^-1 dz
-    CU(launch_dgemm(1, 0, (int)Mtot, (int)Mtot, (int)m, 1.0 / (double)(Mtot - 1), HA, (int)Mtot, W, (int)Mtot, 0.0,
-                    T, (int)Mtot, st));
+    if (dinv_kind != 0 && Mtot < m && Mtot <= 96) {
+        // ensemble-space form (txh_da.cu): the Mtot x Mtot system replaces the m x m one and T is its solution
+        const int Mt = (int)Mtot, nsplit = 8;
+        double* Bc = work;                                  // [m][2Mt] = [HA | dz]
+        double* Y = Bc + 2 * m * Mtot;                      // [m][2Mt] = D^-1 Bc
+        double* Cp = Y + 2 * m * Mtot;                      // [nsplit][Mt][2Mt] split-K partials of HA^T Y
+        CU(launch_innovation_cat(HX, Zp, mean, d_pos, dinv_kind == 1 ? Dinv : nullptr, (int)m, Mt, Bc, Y, st));
+        if (dinv_kind == 2)
+            CU(launch_dgemm(0, 0, (int)m, 2 * Mt, (int)m, 1.0, Dinv, (int)m, Bc, 2 * Mt, 0.0, Y, 2 * Mt, st));
+        CU(launch_dgemm_splitk(1, 0, Mt, 2 * Mt, (int)m, Bc, 2 * Mt, Y, 2 * Mt, Cp, 2 * Mt, nsplit,
+                               (long long)Mt * 2 * Mt, st));
+        CU(launch_chol_solve_small(Cp, nsplit, (long long)Mt * 2 * Mt, Mt, (double)(Mtot - 1), T, info_word(net), st));
+        CU(launch_woodbury_w(Y, T, (int)m, Mt, W, st));
+    } else {
+        double* S = work;
+        double* HA = S + m * m;
+        double* mean_obs = HA + m * Mtot;
+        CU(launch_gather_rows(d_pos, m, mean, 1, 1, mean_obs, st));
+        CU(launch_innovation(HX, Zp, mean_obs, (int)m, (int)Mtot, HA, W, st));                    // W <- dz
+        CU(launch_dgemm(0, 1, (int)m, (int)m, (int)Mtot, 1.0, HA, (int)Mtot, HA, (int)Mtot, 0.0, S, (int)m, st));
+        CU(launch_innov_cov_finish(S, qs, R, (int)m, 1.0 / (double)(Mtot - 1), st));
+        CU(launch_spd_solve(S, W, (int)m, (int)Mtot, info_word(net), st));                        // W <- S^-1 dz
+        CU(launch_dgemm(1, 0, (int)Mtot, (int)Mtot, (int)m, 1.0 / (double)(Mtot - 1), HA, (int)Mtot, W, (int)Mtot, 0.0,
+                        T, (int)Mtot, st));
+    }
     // asynchronous: a failed factorisation leaves a non-zero info word that txh_check reports
     CU(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return TXH_OK;

@@ -30,9 +30,12 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 // CTA tile 64x64, K tile 16; 8 warps, each a 16x32 sub-tile = 2x4 DMMA tiles.
 constexpr int GB_M = 64, GB_N = 64, GB_K = 16;
 
+// Split-K: blockIdx.z owns the k range [z*kchunk, (z+1)*kchunk) and writes its partial product to
+// C + z*cstride (kchunk == K, gridDim.z == 1: the plain product).
 __global__ void __launch_bounds__(256)
 dgemm_kernel(int transA, int transB, int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
-             const double* __restrict__ B, int ldb, double beta, double* __restrict__ C, int ldc)
+             const double* __restrict__ B, int ldb, double beta, double* __restrict__ C, int ldc, int kchunk,
+             long long cstride)
 {
     __shared__ double sA[GB_M][GB_K + 1];      // sA[m][k]
     __shared__ double sB[GB_K][GB_N + 1];      // sB[k][n]
@@ -46,7 +49,10 @@ dgemm_kernel(int transA, int transB, int M, int N, int K, double alpha, const do
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int k0 = 0; k0 < K; k0 += GB_K) {
+    const int kbeg = blockIdx.z * kchunk;
+    K = min(K, kbeg + kchunk);
+    C += (size_t)blockIdx.z * cstride;
+    for (int k0 = kbeg; k0 < K; k0 += GB_K) {
         for (int e = tid; e < GB_M * GB_K; e += 256) {
             int m, k;
             if (transA) { m = e % GB_M; k = e / GB_M; } else { k = e % GB_K; m = e / GB_K; }
@@ -232,6 +238,107 @@ inverse_kernel(double* __restrict__ A, double* __restrict__ W, int m, int* __res
     for (int e = tid; e < m * m; e += blockDim.x) A[e] = W[e];
 }
 
+
+// ---- ensemble-space (Woodbury) form of the innovation solve ----------------------------------------
+// With D = R + diag(Q[s,s]) constant between updates and its inverse precomputed, the m x m system
+// S W = dz,  S = HA HA^T/(Mt-1) + D,  collapses to an Mt x Mt one:
+//     Y  = D^-1 [HA | dz]                      C = HA^T Y = [C0 | C1]
+//     (C0 + (Mt-1) I) Z = C1                   T = HA^T W/(Mt-1) = Z          W = Y_dz - Y_HA Z
+// (HA^T S^-1 = (Mt-1) (C0 + (Mt-1) I)^-1 HA^T D^-1, so the ensemble transform IS the small solve.)
+
+// Bc[k] = [HA_k | dz_k] (2*Mt doubles per gauge); Y = dinv_k * Bc when D is diagonal.
+__global__ void __launch_bounds__(256)
+innovation_cat_kernel(const double* __restrict__ HX, const double* __restrict__ Zp, const double* __restrict__ mean,
+                      const int32_t* __restrict__ obs_pos, const double* __restrict__ dinv_diag, int m, int Mt,
+                      double* __restrict__ Bc, double* __restrict__ Y)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= m * Mt) return;
+    const int k = gid / Mt, c = gid - k * Mt;
+    const double hx = HX[gid];
+    const double ha = hx - mean[obs_pos[k]], dz = Zp[gid] - hx;
+    const size_t o = (size_t)k * 2 * Mt + c;
+    Bc[o] = ha; Bc[o + Mt] = dz;
+    if (dinv_diag) { const double d = dinv_diag[k]; Y[o] = d * ha; Y[o + Mt] = d * dz; }
+}
+
+// (sum of the split-K partials of C) -> A = C0 + shift*I, B = C1; Cholesky A = L L^T in shared
+// memory (right-looking, one CTA), then L Y = B, L^T Z = Y for the Mt right-hand sides; Z -> global.
+// Mt <= 128.
+__global__ void __launch_bounds__(512)
+chol_solve_small_kernel(const double* __restrict__ Cpart, int nsplit, long long pstride, int Mt, double shift,
+                        double* __restrict__ Z, int* __restrict__ info)
+{
+    extern __shared__ double sm[];
+    const int ldA = Mt + 1;
+    double* A = sm;                       // [Mt][Mt+1]
+    double* B = sm + (size_t)Mt * ldA;    // [Mt][Mt+1]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < Mt * 2 * Mt; e += nt) {
+        const int i = e / (2 * Mt), j = e - i * 2 * Mt;
+        double v = 0.0;
+        for (int s = 0; s < nsplit; ++s) v += Cpart[(size_t)s * pstride + e];
+        if (j < Mt) A[i * ldA + j] = v + (i == j ? shift : 0.0);
+        else B[i * ldA + (j - Mt)] = v;
+    }
+    __syncthreads();
+    for (int j = 0; j < Mt; ++j) {
+        const double d = A[j * ldA + j];                      // every thread reads the pivot
+        if (tid == 0 && !(d > 0.0)) *info = j + 1;
+        const double r = 1.0 / sqrt(d > 0.0 ? d : 1.0);
+        __syncthreads();
+        for (int i = j + tid; i < Mt; i += nt) A[i * ldA + j] *= r;          // column j of L (the pivot too)
+        __syncthreads();
+        // trailing update of the lower triangle: A[i][c] -= L[i][j] L[c][j], j < c <= i
+        const int rem = Mt - j - 1;
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int ii = e / rem, cc = e - ii * rem;
+            if (cc <= ii) {
+                const int i = j + 1 + ii, c = j + 1 + cc;
+                A[i * ldA + c] -= A[i * ldA + j] * A[c * ldA + j];
+            }
+        }
+        __syncthreads();
+    }
+    // triangular solves: 8 threads per right-hand-side column, 64 columns per pass
+    const int q = tid & 7, cl = tid >> 3, cper = nt >> 3;
+    for (int c0 = 0; c0 < Mt; c0 += cper) {
+        const int c = c0 + cl;
+        const bool on = c < Mt;
+        for (int i = 0; i < Mt; ++i) {
+            double s = 0.0;
+            if (on) for (int p = q; p < i; p += 8) s += A[i * ldA + p] * B[p * ldA + c];
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 8);
+            if (on && q == 0) B[i * ldA + c] = (B[i * ldA + c] - s) / A[i * ldA + i];
+            __syncwarp();
+        }
+        for (int i = Mt - 1; i >= 0; --i) {
+            double s = 0.0;
+            if (on) for (int p = i + 1 + q; p < Mt; p += 8) s += A[p * ldA + i] * B[p * ldA + c];
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 8);
+            if (on && q == 0) B[i * ldA + c] = (B[i * ldA + c] - s) / A[i * ldA + i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < Mt * Mt; e += nt) Z[e] = B[(e / Mt) * ldA + (e % Mt)];
+}
+
+// W[k][c] = Y_dz[k][c] - sum_j Y_HA[k][j] Z[j][c]      (Y rows are [Y_HA | Y_dz], 2*Mt doubles)
+__global__ void __launch_bounds__(256)
+woodbury_w_kernel(const double* __restrict__ Y, const double* __restrict__ Z, int m, int Mt, double* __restrict__ W)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= m * Mt) return;
+    const int k = gid / Mt, c = gid - k * Mt;
+    const double* y = Y + (size_t)k * 2 * Mt;
+    double s = y[Mt + c];
+    for (int j = 0; j < Mt; ++j) s -= y[j] * Z[(size_t)j * Mt + c];
+    W[gid] = s;
+}
+
 // G[k][c] = sum_m (X[k][m] - mean_k) T[m][c]  for the shard's columns c: the ensemble transform
 // applied to every reach.  CTA = 4 warps, 32 rows per CTA; T staged in shared memory once; each
 // warp owns 8 rows and walks the 8x8 output tiles with FP64 tensor-core MMAs.
@@ -323,7 +430,45 @@ cudaError_t launch_dgemm(int transA, int transB, int M, int N, int K, double alp
 {
     if (M <= 0 || N <= 0) return cudaSuccess;
     dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M);
-    dgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    dgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K > 0 ? K : 1, 0);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dgemm_splitk(int transA, int transB, int M, int N, int K, const double* A, int lda, const double* B,
+                                int ldb, double* Cpart, int ldc, int nsplit, long long pstride, cudaStream_t st)
+{
+    if (M <= 0 || N <= 0 || nsplit < 1) return cudaSuccess;
+    int kchunk = (K + nsplit - 1) / nsplit;
+    kchunk = (kchunk + GB_K - 1) / GB_K * GB_K;
+    dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M, nsplit);
+    dgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, 1.0, A, lda, B, ldb, 0.0, Cpart, ldc, kchunk, pstride);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_innovation_cat(const double* HX, const double* Zp, const double* mean, const int32_t* obs_pos,
+                                  const double* dinv_diag, int m, int Mt, double* Bc, double* Y, cudaStream_t st)
+{
+    innovation_cat_kernel<<<nblk((long long)m * Mt, 256), 256, 0, st>>>(HX, Zp, mean, obs_pos, dinv_diag, m, Mt, Bc, Y);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long pstride, int Mt, double shift, double* Z,
+                                    int* info, cudaStream_t st)
+{
+    const size_t smem = 2 * (size_t)Mt * (Mt + 1) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(chol_solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    chol_solve_small_kernel<<<1, 512, smem, st>>>(Cpart, nsplit, pstride, Mt, shift, Z, info);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_woodbury_w(const double* Y, const double* Z, int m, int Mt, double* W, cudaStream_t st)
+{
+    woodbury_w_kernel<<<nblk((long long)m * Mt, 256), 256, 0, st>>>(Y, Z, m, Mt, W);
     count_launch();
     return cudaGetLastError();
 }

@@ -96,6 +96,13 @@ int64_t launch_count();
 // ---- assimilation (txh_da.cu) --------------------------------------------------------------------
 cudaError_t launch_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
                          const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t st);
+cudaError_t launch_dgemm_splitk(int transA, int transB, int M, int N, int K, const double* A, int lda, const double* B,
+                                int ldb, double* Cpart, int ldc, int nsplit, long long pstride, cudaStream_t st);
+cudaError_t launch_innovation_cat(const double* HX, const double* Zp, const double* mean, const int32_t* obs_pos,
+                                  const double* dinv_diag, int m, int Mt, double* Bc, double* Y, cudaStream_t st);
+cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long pstride, int Mt, double shift, double* Z,
+                                    int* info, cudaStream_t st);
+cudaError_t launch_woodbury_w(const double* Y, const double* Z, int m, int Mt, double* W, cudaStream_t st);
 cudaError_t launch_rowsum(const double* X, int ld, int M, int64_t n, double* rowsum, cudaStream_t st);
 cudaError_t launch_innovation(const double* HX, const double* Zp, const double* mean_obs, int m, int M, double* HA,
                               double* dz, cudaStream_t st);

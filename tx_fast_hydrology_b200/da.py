@@ -221,7 +221,14 @@ class EnsembleKalmanFilter(BaseCallback):
         self._rowsum = torch.empty(n, **f64)
         self._HX = torch.empty((m, self.M), **f64)
         self._HXall = torch.empty((m, Mt), **f64) if self.world > 1 else self._HX
-        self._work = torch.empty(m * m + 2 * m * Mt + m, **f64)
+        self._work = torch.empty(model.network.enkf_work_size(m, Mt), **f64)
+        # D = R + diag(Q[s,s]) never changes: its inverse (diagonal or dense) lets the update solve in
+        # ensemble space when the ensemble is smaller than the gauge network
+        D = Rp + np.diag(q[self.reach_indices])
+        if np.count_nonzero(D - np.diag(np.diagonal(D))) == 0:
+            self._Dinv, self._dinv_kind = torch.as_tensor(1.0 / np.diagonal(D), device='cuda').contiguous(), 1
+        else:
+            self._Dinv, self._dinv_kind = inverse(torch.as_tensor(np.ascontiguousarray(D), device='cuda').clone()), 2
         self._W = torch.empty((m, Mt), **f64)
         self._T = torch.empty((Mt, Mt), **f64)
         self._G = model.network.alloc_state(self.M)
@@ -281,7 +288,7 @@ class EnsembleKalmanFilter(BaseCallback):
             ldx = Mt
         mean = self._rowsum.mul_(1.0 / Mt)
         net.enkf_solve(m, Mt, self._HXall, Zp_dev, mean, self.reach_indices, self._qs, self._R, self._work,
-                       self._W, self._T)
+                       self._W, self._T, self._Dinv, self._dinv_kind)
         net.enkf_apply(O, I, M, Xall, ldx, Mt, self.rank * M, mean, self._T, self.reach_indices, self._qs,
                        self._W, self._G)
         mdl._device_advanced()

@@ -390,20 +390,27 @@ class Muskingum:
         self.datetime = self.datetime + nsteps * self.timedelta
         return rec
 
-    def run_assimilating(self, forcing, nsteps, enkf, every, observations):
+    def run_assimilating(self, forcing, nsteps, enkf, every, observations, timers=None):
         """Device-resident run with periodic ensemble assimilation: `every` routing steps in one
         persistent launch, then one `EnsembleKalmanFilter` update with `observations[k]` ([m][Mtot]
         CUDA tensor of per-member observations for the k-th update), repeated; nothing returns to
         the host in between.  Mirrors simulate + a KalmanFilter callback gated to every `every`-th
-        step (the reference filters every step, da.py:56-61; SURVEY.md section 8c iv)."""
-        self._ensure_device()
+        step (the reference filters every step, da.py:56-61; SURVEY.md section 8c iv).
+        `timers`: optional list that receives a (start, end) CUDA-event pair around every routing launch."""
+        torch = self._ensure_device()
         self._sync_coeffs()
         d, net, M = self._dev, self.network, self.members
         step_ns = int(self.timedelta.value)
         t = int(self.datetime.value)
         nwin = nsteps // every
         for k in range(nwin):
+            if timers is not None:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
             net.route_run(d['O'], d['I'], M, forcing, t, step_ns, every)
+            if timers is not None:
+                e1.record()
+                timers.append((e0, e1))
             t += every * step_ns
             self._datetime = pd.Timestamp(t, tz='UTC')
             enkf.filter(observations[k])
@@ -413,6 +420,27 @@ class Muskingum:
             t += rest * step_ns
         self._datetime = pd.Timestamp(t, tz='UTC')
         self._device_advanced()
+
+    def upload_state(self, o_t_next, i_t_next=None):
+        """`init_states` (muskingum.py:410-419) without the host round trip: `o_t_next` ([n][members],
+        numpy or a pinned CPU torch tensor) goes straight to HBM and the inflows are the device
+        scatter-add of the outflows over `endnodes` (self-loops included) unless given."""
+        self._ensure_device()
+        d, net, M = self._dev, self.network, self.members
+        net.pack_host(o_t_next, M, d['O'])
+        if i_t_next is None:
+            net.init_inflows(d['O'], d['I'], M)
+        else:
+            net.pack_host(i_t_next, M, d['I'])
+        self._device_advanced()
+
+    def download_state(self, out_o=None, out_i=None):
+        """(o_t_next, i_t_next) in reach order; `out_*` may be pinned CPU torch tensors [n][members]."""
+        self._ensure_device()
+        d, net, M = self._dev, self.network, self.members
+        o = net.unpack_host(d['O'], M, out=out_o)
+        i = net.unpack_host(d['I'], M, out=out_i) if out_i is not None else None
+        return o, i
 
     @property
     def device_state(self):

@@ -238,10 +238,15 @@ class RiverNetwork:
         L.check(self._lib.txh_enkf_stats(self.handle, _cuda_ptr(O), int(Mloc), L.ptr_i64(idx), idx.size,
                                          _cuda_ptr(rowsum), _cuda_ptr(HX), _stream_ptr()))
 
-    def enkf_solve(self, m, Mtot, HX, Zp, mean, obs_reach, qs, R, work, W, T):
+    @staticmethod
+    def enkf_work_size(m, Mtot):
+        return int(L.load().txh_enkf_work_size(int(m), int(Mtot)))
+
+    def enkf_solve(self, m, Mtot, HX, Zp, mean, obs_reach, qs, R, work, W, T, Dinv=None, dinv_kind=0):
         idx = L.as_i64(obs_reach)
         L.check(self._lib.txh_enkf_solve(self.handle, int(m), int(Mtot), _cuda_ptr(HX), _cuda_ptr(Zp),
                                          _cuda_ptr(mean), L.ptr_i64(idx), _cuda_ptr(qs), _cuda_ptr(R),
+                                         _cuda_ptr(Dinv) if Dinv is not None else None, int(dinv_kind),
                                          _cuda_ptr(work), _cuda_ptr(W), _cuda_ptr(T), _stream_ptr()))
 
     def enkf_apply(self, O, I, Mloc, Xall, ldx, Mtot, col0, mean, T, obs_reach, qs, W, G):
