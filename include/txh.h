@@ -145,11 +145,12 @@ int txh_apply_gain(txh_net* net, const double* G_dev, double* O_dev, double* I_d
  *   O += gain ; I += N gain              (da.py:124-126: _apply_gain)
  * A = O - mean are the anomalies, HA their gauge rows.  Three phases so that a member-sharded run
  * can combine the statistics between them (all-reduce of the row sums, all-gather of HX / X):
- *   txh_enkf_stats : local row sums at every reach + this shard's gauge rows
+ *   txh_enkf_stats : local row sums at every reach + this shard's gauge rows (one pass over the state)
  *   txh_enkf_solve : innovation covariance (FP64 tensor cores), Cholesky solve, transform
  *   txh_enkf_apply : gain = A T on the FP64 tensor cores + gauge-row term, then the in-place update
  * obs_reach: gauged reach indices ascending (da.py:33-44); all matrices row-major on the device. */
 int txh_enkf_stats(txh_net* net, const double* O_dev, int64_t Mloc, const int64_t* obs_reach_host, int64_t m,
+                   double scale /* rowsum = scale * sum; 1/Mtot gives the mean of an unsharded ensemble */,
                    double* rowsum_dev /*[n] schedule order*/, double* HX_dev /*[m][Mloc]*/, void* stream);
 /* doubles of workspace txh_enkf_solve needs */
 int64_t txh_enkf_work_size(int64_t m, int64_t Mtot);

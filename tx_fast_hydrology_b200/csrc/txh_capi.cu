@@ -70,16 +70,16 @@ struct txh_net {
     int32_t* d_rec_slot = nullptr;
     int32_t* d_tmp_idx = nullptr; size_t tmp_idx_cap = 0;
     int32_t* h_status = nullptr;        // pinned mirror of d_status (word 0) and the solver info (word 1)
-    StepInterp* h_steps = nullptr; size_t h_steps_cap = 0;   // pinned staging of the per-step interpolation
-    cudaEvent_t steps_copied = nullptr;
     std::vector<int64_t> obs_cached;    // gauge list whose positions are resident in d_obs
     int32_t* d_obs = nullptr; size_t obs_cap = 0;
+    int32_t* d_gauge_of_pos = nullptr;  // [n] gauge index of each schedule position, or -1
 };
 
 struct txh_forcing {
     txh_net* net;
     int64_t R, M;
     std::vector<double> times;
+    double* d_times = nullptr;          // [R] the same on the device
     double* d_F = nullptr;              // [R][n] schedule order
     double* d_W = nullptr;              // [R][M] or nullptr
 };
@@ -119,7 +119,6 @@ int ensure_device(txh_net* net)
     CU(cudaMalloc((void**)&net->d_rec_slot, sizeof(int32_t) * net->topo.n));
     CU(cudaMallocHost((void**)&net->h_status, 2 * sizeof(int32_t)));
     net->h_status[0] = net->h_status[1] = 0;
-    CU(cudaEventCreateWithFlags(&net->steps_copied, cudaEventDisableTiming));
     const StepInterp unit{0, 0, 1.0, 0.0};
     CU(cudaMalloc((void**)&net->d_unit_step, sizeof(StepInterp)));
     CU(cudaMemcpy(net->d_unit_step, &unit, sizeof(unit), cudaMemcpyHostToDevice));
@@ -151,8 +150,14 @@ int check_M(int64_t M)
 }
 
 // common launcher for the persistent dataflow kernel
+struct StepPlan {                   // forcing interpolation resolved by the init kernel (times == nullptr: unit step)
+    const double* times = nullptr;
+    int64_t R = 0, t0_ns = 0, dt_ns = 0;
+    int method = 1;
+};
+
 int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F, const double* W, int wm_ld,
-                 const StepInterp* d_steps, int64_t nsteps, const int32_t* rec_slot, double* rec_out,
+                 const StepPlan& plan, int64_t nsteps, const int32_t* rec_slot, double* rec_out,
                  int rec_every, int rec_count, cudaStream_t st)
 {
     const Schedule& s = net->sched;
@@ -182,18 +187,29 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
         CU(cudaMalloc((void**)&net->d_queue, qneed * sizeof(unsigned long long)));
         net->queue_cap = qneed;
     }
+    const StepInterp* d_steps = net->d_unit_step;
+    if (plan.times) {
+        if ((size_t)steps_per_launch > net->steps_cap) {
+            if (net->d_steps) CU(cudaFree(net->d_steps));
+            CU(cudaMalloc((void**)&net->d_steps, sizeof(StepInterp) * steps_per_launch));
+            net->steps_cap = steps_per_launch;
+        }
+        d_steps = net->d_steps;
+    }
     for (int64_t s0 = 0; s0 < nsteps; s0 += steps_per_launch) {
         const int64_t ns = std::min<int64_t>(steps_per_launch, nsteps - s0);
-        CU(cudaMemsetAsync(net->d_queue, 0, pairs * (size_t)ns * sizeof(unsigned long long), st));
         InitArgs ia{};
         ia.tasks = net->d_tasks; ia.init_ready = net->d_init_ready; ia.pending = net->d_pending;
         ia.queue = net->d_queue; ia.q_head = net->d_qctl;
         ia.n_tasks = (int32_t)s.tasks.size(); ia.n_mblocks = nmb; ia.n_init = (int32_t)s.init_ready.size();
+        ia.queue_entries = (long long)pairs * ns;
+        ia.times = plan.times; ia.steps_out = net->d_steps; ia.t0_ns = plan.t0_ns; ia.dt_ns = plan.dt_ns;
+        ia.step_base = s0; ia.R = (int32_t)plan.R; ia.nsteps = (int32_t)ns; ia.method = plan.method;
         CU(launch_dataflow_init(ia, st));
         RouteArgs a{};
         a.tasks = net->d_tasks; a.notify = net->d_notify; a.hdr = net->d_hdr; a.inw = net->d_inw;
         a.coef = net->d_coef; a.cumA = net->d_coef + 4 * net->topo.n; a.linkA = net->d_coef + 5 * net->topo.n;
-        a.O = O; a.I = I; a.Side = net->d_side; a.F = F; a.steps = d_steps + s0; a.Wmul = W;
+        a.O = O; a.I = I; a.Side = net->d_side; a.F = F; a.steps = d_steps; a.Wmul = W;
         a.rec_slot = rec_slot;
         a.rec_out = rec_out;
         if (rec_slot && s0 > 0) {
@@ -245,7 +261,6 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
             }
         }
     }
-    CU(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return TXH_OK;
 }
 
@@ -293,8 +308,7 @@ void txh_destroy(txh_net* net)
         if (net->d_steps) cudaFree(net->d_steps);
         if (net->d_tmp_idx) cudaFree(net->d_tmp_idx);
         if (net->d_obs) cudaFree(net->d_obs);
-        if (net->h_steps) cudaFreeHost(net->h_steps);
-        if (net->steps_copied) cudaEventDestroy(net->steps_copied);
+        if (net->d_gauge_of_pos) cudaFree(net->d_gauge_of_pos);
         if (net->h_status) cudaFreeHost(net->h_status);
     }
     delete net;
@@ -430,6 +444,7 @@ int txh_unpack_host(txh_net* net, const double* src, int64_t M, int layout, doub
     CU(launch_unpack(net->d_reach_of_pos, src, tmp, n, (int)M, (int)txh_row_stride(M), layout, st));
     CU(cudaMemcpyAsync(dst, tmp, sizeof(double) * n * M, cudaMemcpyDeviceToHost, st));
     CU(cudaFreeAsync(tmp, st));
+    CU(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (*net->h_status != 0) return fail(TXH_E_WATCHDOG, "a routing launch bailed out on its dataflow watchdog");
     return TXH_OK;
@@ -505,17 +520,19 @@ int txh_forcing_create(txh_net* net, int64_t R, const double* times, const doubl
     // order on the device
     double* tmp = nullptr;
     cudaError_t e = cudaMalloc((void**)&f->d_F, sizeof(double) * R * n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_times, sizeof(double) * R);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_times, f->times.data(), sizeof(double) * R, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMalloc((void**)&tmp, sizeof(double) * R * n);
     if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, table, sizeof(double) * R * n, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = launch_permute_rows(net->d_reach_of_pos, tmp, f->d_F, n, R, st);
     if (e == cudaSuccess && mul) {
-        if (M < 1) { cudaFree(f->d_F); cudaFree(tmp); delete f; return fail(TXH_E_INVALID, "member multipliers need M >= 1"); }
+        if (M < 1) { cudaFree(f->d_F); cudaFree(f->d_times); cudaFree(tmp); delete f; return fail(TXH_E_INVALID, "member multipliers need M >= 1"); }
         e = cudaMalloc((void**)&f->d_W, sizeof(double) * R * M);
         if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_W, mul, sizeof(double) * R * M, cudaMemcpyHostToDevice, st);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(tmp);
-    if (e != cudaSuccess) { cudaFree(f->d_F); cudaFree(f->d_W); delete f; return cuda_fail(e, "forcing upload"); }
+    if (e != cudaSuccess) { cudaFree(f->d_F); cudaFree(f->d_W); cudaFree(f->d_times); delete f; return cuda_fail(e, "forcing upload"); }
     *out = f;
     return TXH_OK;
 }
@@ -524,6 +541,7 @@ void txh_forcing_destroy(txh_forcing* f)
 {
     if (!f) return;
     cudaFree(f->d_F);
+    if (f->d_times) cudaFree(f->d_times);
     if (f->d_W) cudaFree(f->d_W);
     delete f;
 }
@@ -541,47 +559,8 @@ int txh_route_run(txh_net* net, double* O, double* I, int64_t M, const txh_forci
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = check_M(M)) || (rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
     if (nsteps == 0) return TXH_OK;
-    const StepInterp* d_steps = net->d_unit_step;
-    if (fo) {
-        // nutils.py:21-34 resolved per step on the host, in float64 as the reference does
-        std::vector<StepInterp> steps(nsteps);
-        const double* xp = fo->times.data();
-        const int64_t R = fo->R;
-        for (int64_t s = 0; s < nsteps; ++s) {
-            const double x = (double)(t0_ns + (s + 1) * dt_ns);          // float(next_timestep.value)
-            const int64_t ix = std::lower_bound(xp, xp + R, x) - xp;     // np.searchsorted, side='left'
-            StepInterp si;
-            if (ix == 0) si = {0, 0, 1.0, 0.0};
-            else if (ix >= R) si = {(int32_t)(R - 1), (int32_t)(R - 1), 1.0, 0.0};
-            else {
-                const double dx_0 = x - xp[ix - 1], dx_1 = xp[ix] - x;
-                if (method == 1) {
-                    const double frac = dx_0 / (dx_0 + dx_1);
-                    si = {(int32_t)(ix - 1), (int32_t)ix, 1 - frac, frac};
-                } else {
-                    const int32_t r = std::fabs(dx_0) <= std::fabs(dx_1) ? (int32_t)(ix - 1) : (int32_t)ix;
-                    si = {r, r, 1.0, 0.0};
-                }
-            }
-            steps[s] = si;
-        }
-        if ((size_t)nsteps > net->steps_cap) {
-            if (net->d_steps) CU(cudaFree(net->d_steps));
-            CU(cudaMalloc((void**)&net->d_steps, sizeof(StepInterp) * nsteps));
-            net->steps_cap = nsteps;
-        }
-        // pinned staging + an event instead of a stream synchronisation: launches stay back to back
-        CU(cudaEventSynchronize(net->steps_copied));
-        if ((size_t)nsteps > net->h_steps_cap) {
-            if (net->h_steps) CU(cudaFreeHost(net->h_steps));
-            CU(cudaMallocHost((void**)&net->h_steps, sizeof(StepInterp) * nsteps));
-            net->h_steps_cap = nsteps;
-        }
-        std::memcpy(net->h_steps, steps.data(), sizeof(StepInterp) * nsteps);
-        CU(cudaMemcpyAsync(net->d_steps, net->h_steps, sizeof(StepInterp) * nsteps, cudaMemcpyHostToDevice, st));
-        CU(cudaEventRecord(net->steps_copied, st));
-        d_steps = net->d_steps;
-    }
+    StepPlan plan;
+    if (fo) { plan.times = fo->d_times; plan.R = fo->R; plan.t0_ns = t0_ns; plan.dt_ns = dt_ns; plan.method = method; }
     const int32_t* rec_slot = nullptr;
     if (rec_count > 0) {
         std::vector<int32_t> slot(net->topo.n, -1);
@@ -594,7 +573,7 @@ int txh_route_run(txh_net* net, double* O, double* I, int64_t M, const txh_forci
         rec_slot = net->d_rec_slot;
     }
     return run_dataflow(net, O, I, M, fo ? fo->d_F : nullptr, fo ? fo->d_W : nullptr, fo ? (int)fo->M : 0,
-                        d_steps, nsteps, rec_slot, rec_out, (int)rec_every, (int)rec_count, st);
+                        plan, nsteps, rec_slot, rec_out, (int)rec_every, (int)rec_count, st);
 }
 
 int txh_route_step(txh_net* net, double* O, double* I, int64_t M, const double* q, void* stream)
@@ -604,7 +583,7 @@ int txh_route_step(txh_net* net, double* O, double* I, int64_t M, const double* 
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = check_M(M)) || (rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
     if (q) CU(launch_permute_vec(net->d_reach_of_pos, q, net->d_qtmp, net->topo.n, st));
-    return run_dataflow(net, O, I, M, q ? net->d_qtmp : nullptr, nullptr, 0, net->d_unit_step, 1, nullptr,
+    return run_dataflow(net, O, I, M, q ? net->d_qtmp : nullptr, nullptr, 0, StepPlan(), 1, nullptr,
                         nullptr, 1, 0, st);
 }
 
@@ -635,7 +614,7 @@ int txh_route_apply(txh_net* net, double* X, double* Iscr, int64_t M, void* stre
     // nutils.py:148-154: i_prev = init_inflows(o_prev) (self-loop included), then _ax
     CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, X, Iscr, net->topo.n,
                            (int)txh_row_stride(M), (int)M, st));
-    return run_dataflow(net, X, Iscr, M, nullptr, nullptr, 0, net->d_unit_step, 1, nullptr, nullptr, 1, 0, st);
+    return run_dataflow(net, X, Iscr, M, nullptr, nullptr, 0, StepPlan(), 1, nullptr, nullptr, 1, 0, st);
 }
 
 int txh_apply_gain(txh_net* net, const double* G, double* O, double* I, int64_t M, void* stream)
@@ -652,6 +631,8 @@ int txh_check(txh_net* net, void* stream)
 {
     if (!net) return fail(TXH_E_INVALID, "null argument");
     if (!net->dev_ready) return TXH_OK;
+    // the status word (watchdog) and the solver info word travel only here: launches stay back to back
+    CU(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     if (net->h_status[0] != 0) return fail(TXH_E_WATCHDOG, "a routing launch bailed out on its dataflow watchdog");
     if (net->h_status[1] != 0) return fail(TXH_E_INVALID, "an innovation covariance was not positive definite");
@@ -679,7 +660,11 @@ int obs_positions(txh_net* net, const int64_t* obs, int64_t m, cudaStream_t st, 
         CU(cudaMalloc((void**)&net->d_obs, sizeof(int32_t) * m));
         net->obs_cap = m;
     }
+    std::vector<int32_t> gop(net->topo.n, -1);
+    for (int64_t k = 0; k < m; ++k) gop[pos[k]] = (int32_t)k;
+    if (!net->d_gauge_of_pos) CU(cudaMalloc((void**)&net->d_gauge_of_pos, sizeof(int32_t) * net->topo.n));
     CU(cudaMemcpyAsync(net->d_obs, pos.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(net->d_gauge_of_pos, gop.data(), sizeof(int32_t) * net->topo.n, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
     net->obs_cached.assign(obs, obs + m);
     *d_pos = net->d_obs;
@@ -690,8 +675,8 @@ int* info_word(txh_net* net) { return net->d_status + 1; }
 
 extern "C" {
 
-int txh_enkf_stats(txh_net* net, const double* O, int64_t Mloc, const int64_t* obs, int64_t m, double* rowsum,
-                   double* HX, void* stream)
+int txh_enkf_stats(txh_net* net, const double* O, int64_t Mloc, const int64_t* obs, int64_t m, double scale,
+                   double* rowsum, double* HX, void* stream)
 {
     if (!net || !O || !obs || !rowsum || !HX || m < 1) return fail(TXH_E_INVALID, "bad argument");
     int rc;
@@ -700,8 +685,7 @@ int txh_enkf_stats(txh_net* net, const double* O, int64_t Mloc, const int64_t* o
     int32_t* d_pos = nullptr;
     if ((rc = obs_positions(net, obs, m, st, &d_pos))) return rc;
     const int ld = (int)txh_row_stride(Mloc);
-    CU(launch_rowsum(O, ld, (int)Mloc, net->topo.n, rowsum, st));
-    CU(launch_gather_rows(d_pos, m, O, ld, (int)Mloc, HX, st));
+    CU(launch_enkf_stats(O, ld, (int)Mloc, net->topo.n, scale, net->d_gauge_of_pos, rowsum, HX, st));
     return TXH_OK;
 }
 
@@ -737,7 +721,8 @@ int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, cons
         CU(launch_dgemm_splitk(1, 0, Mt, 2 * Mt, (int)m, Bc, 2 * Mt, Y, 2 * Mt, Cp, 2 * Mt, nsplit,
                                (long long)Mt * 2 * Mt, st));
         CU(launch_chol_solve_small(Cp, nsplit, (long long)Mt * 2 * Mt, Mt, (double)(Mtot - 1), T, info_word(net), st));
-        CU(launch_woodbury_w(Y, T, (int)m, Mt, W, st));
+        // W = Y_dz - Y_HA Z
+        CU(launch_dgemm_ex(0, 0, (int)m, Mt, Mt, -1.0, Y, 2 * Mt, T, Mt, 1.0, Y + Mt, 2 * Mt, W, Mt, st));
     } else {
         double* S = work;
         double* HA = S + m * m;
@@ -751,7 +736,6 @@ int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, cons
                         T, (int)Mtot, st));
     }
     // asynchronous: a failed factorisation leaves a non-zero info word that txh_check reports
-    CU(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return TXH_OK;
 }
 
@@ -768,11 +752,15 @@ int txh_enkf_apply(txh_net* net, double* O, double* I, int64_t Mloc, const doubl
     if ((rc = obs_positions(net, obs, m, st, &d_pos))) return rc;
     const int ld = (int)txh_row_stride(Mloc);
     if (!Xall) { if (Mtot != Mloc) return fail(TXH_E_INVALID, "gathered ensemble missing"); Xall = O; ldx = ld; }
-    CU(cudaMemsetAsync(G, 0, sizeof(double) * net->topo.n * ld, st));
-    CU(launch_enkf_gain(Xall, (int)ldx, (int)Mtot, mean, T + col0, (int)Mtot, (int)Mloc, G, ld, net->topo.n,
-                        net->num_sms, st));
-    CU(launch_enkf_gauge_term(d_pos, qs, W, (int)m, (int)Mtot, (int)col0, (int)Mloc, G, ld, st));
-    CU(launch_apply_gain(net->d_up_off, net->d_up_pos, G, O, I, net->topo.n, ld, (int)Mloc, st));
+    // O += gain and G = gain (tensor cores), gauge rows, then I += sum of the upstream gains.  The in-place
+    // update of O is row-local; when the ensemble being transformed IS O and a row spans several 64-column
+    // groups, a later group would read members an earlier one has already updated: then O is updated from G
+    // afterwards instead.
+    const bool fuse_o = Xall != O || ld <= 64;
+    CU(launch_enkf_update(Xall, (int)ldx, (int)Mtot, mean, T + col0, (int)Mtot, (int)Mloc, fuse_o ? O : nullptr, G, ld,
+                          net->topo.n, net->d_gauge_of_pos, qs, W, (int)col0, net->num_sms, st));
+    if (fuse_o) CU(launch_inflow_gain(net->d_up_off, net->d_up_pos, G, I, net->topo.n, ld, st));
+    else CU(launch_apply_gain(net->d_up_off, net->d_up_pos, G, O, I, net->topo.n, ld, (int)Mloc, st));
     return TXH_OK;
 }
 

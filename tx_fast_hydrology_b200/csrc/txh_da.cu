@@ -34,8 +34,8 @@ constexpr int GB_M = 64, GB_N = 64, GB_K = 16;
 // C + z*cstride (kchunk == K, gridDim.z == 1: the plain product).
 __global__ void __launch_bounds__(256)
 dgemm_kernel(int transA, int transB, int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
-             const double* __restrict__ B, int ldb, double beta, double* __restrict__ C, int ldc, int kchunk,
-             long long cstride)
+             const double* __restrict__ B, int ldb, double beta, double* C, int ldc, int kchunk,
+             long long cstride, const double* Cin, int ldcin)
 {
     __shared__ double sA[GB_M][GB_K + 1];      // sA[m][k]
     __shared__ double sB[GB_K][GB_N + 1];      // sB[k][n]
@@ -52,24 +52,36 @@ dgemm_kernel(int transA, int transB, int M, int N, int K, double alpha, const do
     const int kbeg = blockIdx.z * kchunk;
     K = min(K, kbeg + kchunk);
     C += (size_t)blockIdx.z * cstride;
-    for (int k0 = kbeg; k0 < K; k0 += GB_K) {
-        for (int e = tid; e < GB_M * GB_K; e += 256) {
+    // software pipeline: the next k tile travels global -> registers while the current one is multiplied
+    double ra[4], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + u * 256;
             int m, k;
             if (transA) { m = e % GB_M; k = e / GB_M; } else { k = e % GB_K; m = e / GB_K; }
             const int gm = m0 + m, gk = k0 + k;
-            double v = 0.0;
-            if (gm < M && gk < K) v = transA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
-            sA[m][k] = v;
+            ra[u] = (gm < M && gk < K) ? (transA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk]) : 0.0;
+            int kb, n;
+            if (transB) { kb = e % GB_K; n = e / GB_K; } else { n = e % GB_N; kb = e / GB_N; }
+            const int gkb = k0 + kb, gn = n0 + n;
+            rb[u] = (gkb < K && gn < N) ? (transB ? B[(size_t)gn * ldb + gkb] : B[(size_t)gkb * ldb + gn]) : 0.0;
         }
-        for (int e = tid; e < GB_K * GB_N; e += 256) {
-            int k, n;
-            if (transB) { k = e % GB_K; n = e / GB_K; } else { n = e % GB_N; k = e / GB_N; }
-            const int gk = k0 + k, gn = n0 + n;
-            double v = 0.0;
-            if (gk < K && gn < N) v = transB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
-            sB[k][n] = v;
+    };
+    if (kbeg < K) fetch(kbeg);
+    for (int k0 = kbeg; k0 < K; k0 += GB_K) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + u * 256;
+            int m, k;
+            if (transA) { m = e % GB_M; k = e / GB_M; } else { k = e % GB_K; m = e / GB_K; }
+            sA[m][k] = ra[u];
+            int kb, n;
+            if (transB) { kb = e % GB_K; n = e / GB_K; } else { n = e % GB_N; kb = e / GB_N; }
+            sB[kb][n] = rb[u];
         }
         __syncthreads();
+        if (k0 + GB_K < K) fetch(k0 + GB_K);
 #pragma unroll
         for (int kk = 0; kk < GB_K; kk += 4) {
             double a[2], b[4];
@@ -92,26 +104,35 @@ dgemm_kernel(int transA, int transB, int M, int N, int K, double alpha, const do
             for (int c = 0; c < 2; ++c) {
                 const int gm = m0 + wm + 8 * i + g, gn = n0 + wn + 8 * j + 2 * t + c;
                 if (gm < M && gn < N) {
-                    double* p = C + (size_t)gm * ldc + gn;
-                    *p = alpha * acc[i][j][c] + (beta == 0.0 ? 0.0 : beta * *p);
+                    C[(size_t)gm * ldc + gn] =
+                        alpha * acc[i][j][c] + (beta == 0.0 ? 0.0 : beta * Cin[(size_t)gm * ldcin + gn]);
                 }
             }
 }
 
 // ---- ensemble statistics ---------------------------------------------------------------------
-// rowsum[k] = sum over this shard's members of X[k][:]   (one warp per row)
+// rowsum[k] = scale * sum over this shard's members of X[k][:]  (one warp per row; scale = 1/Mtot turns it
+// into the ensemble mean when the shard is the whole ensemble), and the rows of the gauged reaches copied
+// to HX[g][0..M) in the same pass (gauge_of_pos[k] = gauge index or -1).
 __global__ void __launch_bounds__(256)
-rowsum_kernel(const double* __restrict__ X, int ld, int M, long long n, double* __restrict__ rowsum)
+enkf_stats_kernel(const double* __restrict__ X, int ld, int M, long long n, double scale,
+                  const int32_t* __restrict__ gauge_of_pos, double* __restrict__ rowsum, double* __restrict__ HX)
 {
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n) return;
     const double* p = X + (size_t)row * ld;
+    const int gi = gauge_of_pos[row];
     double s = 0.0;
-    for (int m = lane; m < M; m += 32) s += p[m];
+    for (int m = 2 * lane; m < M; m += 64) {
+        const double2 v = *reinterpret_cast<const double2*>(p + m);
+        s += v.x;
+        if (m + 1 < M) s += v.y;
+        if (gi >= 0) { HX[(size_t)gi * M + m] = v.x; if (m + 1 < M) HX[(size_t)gi * M + m + 1] = v.y; }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) rowsum[row] = s;
+    if (lane == 0) rowsum[row] = s * scale;
 }
 
 // HA[k][m] = HX[k][m] - mean_k ; dz[k][m] = Zp[k][m] - HX[k][m]     (da.py:112)
@@ -262,136 +283,230 @@ innovation_cat_kernel(const double* __restrict__ HX, const double* __restrict__ 
     if (dinv_diag) { const double d = dinv_diag[k]; Y[o] = d * ha; Y[o + Mt] = d * dz; }
 }
 
-// (sum of the split-K partials of C) -> A = C0 + shift*I, B = C1; Cholesky A = L L^T in shared
-// memory (right-looking, one CTA), then L Y = B, L^T Z = Y for the Mt right-hand sides; Z -> global.
-// Mt <= 128.
-__global__ void __launch_bounds__(512)
-chol_solve_small_kernel(const double* __restrict__ Cpart, int nsplit, long long pstride, int Mt, double shift,
+// (sum of the split-K partials of C) -> A = C0 + shift*I, B = C1, then (C0 + shift I) Z = C1 by Cholesky.
+// One CTA of 8*MT threads; the matrices live in REGISTERS: thread (rg, c) = (tid / MT, tid % MT) owns rows
+// {8r + rg} of column c of A (lower triangle), of the right-hand sides B and of V (starts as the identity).
+// The forward substitutions ride on the factorisation, so a step is one shared-memory broadcast and ONE
+// barrier: at step j the owners publish column j of A (unscaled) and row j of B and V; with r = 1/sqrt(d_j)
+// everyone applies   A[i][c] -= A[i][j] A[c][j] r^2,   B[i][c] -= A[i][j] B[j][c] r^2,   V likewise,
+// and row j becomes final:  Y[j] = B[j] r,  L^-1[j] = V[j] r.  After MT steps Y = L^-1 B and V = L^-1, and
+// the backward substitution is the product Z = (L^-1)^T Y -- no second sequential sweep.
+// The system is padded with the identity up to MT (64 or 96) so that all register indices are static.
+constexpr int CS_NSPLIT = 8;
+
+template <int MT>
+__global__ void __launch_bounds__(8 * MT)
+chol_solve_small_kernel(const double* __restrict__ Cpart, long long pstride, int Mt, double shift,
                         double* __restrict__ Z, int* __restrict__ info)
 {
+    constexpr int R = MT / 8, LDS_ = MT + 1;
     extern __shared__ double sm[];
-    const int ldA = Mt + 1;
-    double* A = sm;                       // [Mt][Mt+1]
-    double* B = sm + (size_t)Mt * ldA;    // [Mt][Mt+1]
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int e = tid; e < Mt * 2 * Mt; e += nt) {
-        const int i = e / (2 * Mt), j = e - i * 2 * Mt;
-        double v = 0.0;
-        for (int s = 0; s < nsplit; ++s) v += Cpart[(size_t)s * pstride + e];
-        if (j < Mt) A[i * ldA + j] = v + (i == j ? shift : 0.0);
-        else B[i * ldA + (j - Mt)] = v;
-    }
-    __syncthreads();
-    for (int j = 0; j < Mt; ++j) {
-        const double d = A[j * ldA + j];                      // every thread reads the pivot
-        if (tid == 0 && !(d > 0.0)) *info = j + 1;
-        const double r = 1.0 / sqrt(d > 0.0 ? d : 1.0);
-        __syncthreads();
-        for (int i = j + tid; i < Mt; i += nt) A[i * ldA + j] *= r;          // column j of L (the pivot too)
-        __syncthreads();
-        // trailing update of the lower triangle: A[i][c] -= L[i][j] L[c][j], j < c <= i
-        const int rem = Mt - j - 1;
-        for (int e = tid; e < rem * rem; e += nt) {
-            const int ii = e / rem, cc = e - ii * rem;
-            if (cc <= ii) {
-                const int i = j + 1 + ii, c = j + 1 + cc;
-                A[i * ldA + c] -= A[i * ldA + j] * A[c * ldA + j];
+    double* Ys = sm;                      // [MT][MT+1]  Y = L^-1 B
+    double* Ls = Ys + MT * LDS_;          // [MT][MT+1]  L^-1
+    double* bc = Ls + MT * LDS_;          // [2][3][MT]  per-step broadcast (column of A, rows of B and V)
+    const int tid = threadIdx.x;
+    const int c = tid % MT, rg = tid / MT;
+    double a[R], b[R], v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { a[r] = 0.0; b[r] = 0.0; v[r] = (8 * r + rg == c) ? 1.0 : 0.0; }
+#pragma unroll
+    for (int s = 0; s < CS_NSPLIT; ++s)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = 8 * r + rg;
+            if (i < Mt && c < Mt) {
+                const double* row = Cpart + (size_t)s * pstride + (size_t)i * 2 * Mt;
+                a[r] += row[c];
+                b[r] += row[Mt + c];
             }
         }
-        __syncthreads();
-    }
-    // triangular solves: 8 threads per right-hand-side column, 64 columns per pass
-    const int q = tid & 7, cl = tid >> 3, cper = nt >> 3;
-    for (int c0 = 0; c0 < Mt; c0 += cper) {
-        const int c = c0 + cl;
-        const bool on = c < Mt;
-        for (int i = 0; i < Mt; ++i) {
-            double s = 0.0;
-            if (on) for (int p = q; p < i; p += 8) s += A[i * ldA + p] * B[p * ldA + c];
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 8);
-            if (on && q == 0) B[i * ldA + c] = (B[i * ldA + c] - s) / A[i * ldA + i];
-            __syncwarp();
-        }
-        for (int i = Mt - 1; i >= 0; --i) {
-            double s = 0.0;
-            if (on) for (int p = i + 1 + q; p < Mt; p += 8) s += A[p * ldA + i] * B[p * ldA + c];
+    for (int r = 0; r < R; ++r) {
+        const int i = 8 * r + rg;
+        if (i == c) a[r] = (i < Mt) ? a[r] + shift : 1.0;
+    }
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 8);
-            if (on && q == 0) B[i * ldA + c] = (B[i * ldA + c] - s) / A[i * ldA + i];
-            __syncwarp();
+    for (int pb = 0; pb < R; ++pb) {
+        for (int pr = 0; pr < 8; ++pr) {
+            const int j = 8 * pb + pr;
+            double* cb = bc + (j & 1) * 3 * MT;
+            double* brow = cb + MT;
+            double* vrow = cb + 2 * MT;
+            if (c == j) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) cb[8 * r + rg] = a[r];       // rows < j carry junk that nobody reads
+            }
+            if (rg == pr) { brow[c] = b[pb]; vrow[c] = v[pb]; }
+            __syncthreads();
+            double d = cb[j];
+            if (!(d > 0.0)) { if (tid == 0) *info = j + 1; d = 1.0; }
+            const double rs = rsqrt(d), rs2 = rs * rs;
+            const double bj = brow[c], vj = vrow[c];
+            if (rg == pr) { b[pb] = bj * rs; v[pb] = vj * rs; }
+            const double fb = bj * rs2, fv = vj * rs2, fa = c > j ? cb[c] * rs2 : 0.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = 8 * r + rg;
+                if (r > pb || (r == pb && rg > pr)) {                    // i > j
+                    const double l = cb[i];
+                    b[r] -= l * fb;
+                    v[r] -= l * fv;
+                    if (i >= c) a[r] -= l * fa;
+                }
+            }
         }
     }
+#pragma unroll
+    for (int r = 0; r < R; ++r) { const int i = 8 * r + rg; Ys[i * LDS_ + c] = b[r]; Ls[i * LDS_ + c] = v[r]; }
     __syncthreads();
-    for (int e = tid; e < Mt * Mt; e += nt) Z[e] = B[(e / Mt) * ldA + (e % Mt)];
+    // Z[i][c] = sum_p L^-1[p][i] Y[p][c]
+    double z[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) z[r] = 0.0;
+    for (int p = 0; p < MT; ++p) {
+        const double y = Ys[p * LDS_ + c];
+        const double* lp = Ls + p * LDS_ + rg;
+#pragma unroll
+        for (int r = 0; r < R; ++r) z[r] += lp[8 * r] * y;
+    }
+    if (c < Mt) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) { const int i = 8 * r + rg; if (i < Mt) Z[(size_t)i * Mt + c] = z[r]; }
+    }
 }
 
-// W[k][c] = Y_dz[k][c] - sum_j Y_HA[k][j] Z[j][c]      (Y rows are [Y_HA | Y_dz], 2*Mt doubles)
-__global__ void __launch_bounds__(256)
-woodbury_w_kernel(const double* __restrict__ Y, const double* __restrict__ Z, int m, int Mt, double* __restrict__ W)
-{
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= m * Mt) return;
-    const int k = gid / Mt, c = gid - k * Mt;
-    const double* y = Y + (size_t)k * 2 * Mt;
-    double s = y[Mt + c];
-    for (int j = 0; j < Mt; ++j) s -= y[j] * Z[(size_t)j * Mt + c];
-    W[gid] = s;
-}
+// ---- ensemble transform applied to the state ------------------------------------------------------
+// gain[k][c] = sum_j (Xall[k][j] - mean_k) T[j][c]  for this shard's columns c, written to G and added to
+// O in place (da.py:126, o_t_next += gain); the inflow part of _apply_gain follows in inflow_gain_kernel.
+// FP64 tensor cores (DMMA m8n8k4).  A warp owns 16 rows (two 8-row MMA tiles): its anomalies of one
+// 64-member k chunk live in registers as A fragments (32 doubles per lane), the matching 64 x 64 block
+// of T is staged in shared memory and every B fragment read feeds two MMAs.  The k index of a fragment
+// is permuted (lane t holds members 8j+2t, 8j+2t+1 for k steps 2j, 2j+1) so that a lane fetches its two
+// members of a row with one 128-bit load; T is read with the same permutation.
+constexpr int EU_WARPS = 8, EU_ROWS = 16 * EU_WARPS, EU_LDT = 66;
 
-// G[k][c] = sum_m (X[k][m] - mean_k) T[m][c]  for the shard's columns c: the ensemble transform
-// applied to every reach.  CTA = 4 warps, 32 rows per CTA; T staged in shared memory once; each
-// warp owns 8 rows and walks the 8x8 output tiles with FP64 tensor-core MMAs.
-// Xall: [n][ldx] rows with Mtot members (the gathered ensemble, or the state itself when Mtot == Mloc)
-constexpr int EG_ROWS = 32;
-
-__global__ void __launch_bounds__(128)
-enkf_gain_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const double* __restrict__ mean,
-                 const double* __restrict__ T, int ldt, int Mloc, double* __restrict__ G, int ldg, long long n)
+__global__ void __launch_bounds__(EU_WARPS * 32)
+enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const double* __restrict__ mean,
+                   const double* __restrict__ T, int ldt, int Mloc, double* __restrict__ O, double* __restrict__ G,
+                   int ld, long long n, const int32_t* __restrict__ gauge_of_pos, const double* __restrict__ qs,
+                   const double* __restrict__ W, int col0)
 {
-    extern __shared__ double smem[];
-    const int Kp = (Mtot + 3) & ~3;            // K padded to the MMA depth
-    const int Np = (Mloc + 7) & ~7;            // N padded to the MMA width
-    double* sT = smem;                          // [Kp][Np + 1]
-    double* sX = smem + (size_t)Kp * (Np + 1);  // [EG_ROWS][Kp + 1]
+    __shared__ double sT[64 * EU_LDT];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    for (int e = tid; e < Kp * Np; e += 128) {
-        const int k = e / Np, c = e - k * Np;
-        sT[k * (Np + 1) + c] = (k < Mtot && c < Mloc) ? T[(size_t)k * ldt + c] : 0.0;
-    }
-    for (long long r0 = (long long)blockIdx.x * EG_ROWS; r0 < n; r0 += (long long)gridDim.x * EG_ROWS) {
-        __syncthreads();
-        for (int e = tid; e < EG_ROWS * Kp; e += 128) {
-            const int r = e / Kp, k = e - r * Kp;
-            const long long row = r0 + r;
-            sX[r * (Kp + 1) + k] = (row < n && k < Mtot) ? Xall[(size_t)row * ldx + k] - mean[row] : 0.0;
-        }
-        __syncthreads();
-        const int rw = warp * 8;
-        for (int c0 = 0; c0 < Np; c0 += 8) {
-            double c0v = 0.0, c1v = 0.0;
-            for (int k0 = 0; k0 < Kp; k0 += 4)
-                dmma8x8x4(c0v, c1v, sX[(rw + g) * (Kp + 1) + k0 + t], sT[(k0 + t) * (Np + 1) + c0 + g]);
-            const long long row = r0 + rw + g;
-            const int col = c0 + 2 * t;
-            if (row < n) {
-                if (col < Mloc) G[(size_t)row * ldg + col] = c0v;
-                if (col + 1 < Mloc) G[(size_t)row * ldg + col + 1] = c1v;
+    const bool vec = (ldx & 1) == 0;
+    const int nkc = (Mtot + 63) / 64, ncg = (ld + 63) / 64;
+    for (long long r0 = (long long)blockIdx.x * EU_ROWS; r0 < n; r0 += (long long)gridDim.x * EU_ROWS) {
+        const long long rw = r0 + warp * 16;
+        const long long row0 = rw + g, row1 = rw + 8 + g;
+        const double mu0 = row0 < n ? mean[row0] : 0.0, mu1 = row1 < n ? mean[row1] : 0.0;
+        for (int cg = 0; cg < ncg; ++cg) {
+            double acc[2][8][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int kc = 0; kc < nkc; ++kc) {
+                if (nkc * ncg > 1 || r0 == (long long)blockIdx.x * EU_ROWS) {
+                    // stage T[kc*64 .. +64][cg*64 .. +64] (zero outside the matrix); with a single block it
+                    // is staged once per CTA
+                    __syncthreads();
+                    for (int e = tid; e < 64 * 64; e += EU_WARPS * 32) {
+                        const int k = e >> 6, c = e & 63;
+                        const int gk = kc * 64 + k, gc = cg * 64 + c;
+                        sT[k * EU_LDT + c] = (gk < Mtot && gc < Mloc) ? T[(size_t)gk * ldt + gc] : 0.0;
+                    }
+                    __syncthreads();
+                }
+                // A fragments: a[i][2j], a[i][2j+1] = anomalies of members kc*64 + 8j + 2t, +1
+                double a[2][16];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const long long row = i ? row1 : row0;
+                    const double mu = i ? mu1 : mu0;
+                    const double* xr = Xall + (size_t)(row < n ? row : 0) * ldx;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = kc * 64 + 8 * j + 2 * t;
+                        double x0 = mu, x1 = mu;
+                        if (row < n) {
+                            if (vec && k + 1 < Mtot) {
+                                const double2 v = *reinterpret_cast<const double2*>(xr + k);
+                                x0 = v.x; x1 = v.y;
+                            } else {
+                                if (k < Mtot) x0 = xr[k];
+                                if (k + 1 < Mtot) x1 = xr[k + 1];
+                            }
+                        }
+                        a[i][2 * j] = x0 - mu; a[i][2 * j + 1] = x1 - mu;
+                    }
+                }
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) {
+                    const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
+                    const double* bt = sT + k * EU_LDT + g;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double b = bt[8 * j];
+                        dmma8x8x4(acc[0][j][0], acc[0][j][1], a[0][ks], b);
+                        dmma8x8x4(acc[1][j][0], acc[1][j][1], a[1][ks], b);
+                    }
+                }
+            }
+            // epilogue: G = gain, O += gain (row-local, so in place is safe); gauged rows add the Q[:, s]
+            // term of the gain, qs[g] * W[g][col0 + c] (da.py:117-121)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const long long row = i ? row1 : row0;
+                if (row >= n) continue;
+                const int gi = gauge_of_pos[row];
+                const double qg = gi >= 0 ? qs[gi] : 0.0;
+                const double* wr = W + (size_t)(gi >= 0 ? gi : 0) * Mtot + col0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = cg * 64 + 8 * j + 2 * t;
+                    if (col >= ld) continue;
+                    double2 gn = make_double2(acc[i][j][0], col + 1 < Mloc ? acc[i][j][1] : 0.0);
+                    if (col >= Mloc) gn.x = 0.0;
+                    if (gi >= 0) {
+                        if (col < Mloc) gn.x += qg * wr[col];
+                        if (col + 1 < Mloc) gn.y += qg * wr[col + 1];
+                    }
+                    if (O) {
+                        double2* op = reinterpret_cast<double2*>(O + (size_t)row * ld + col);
+                        double2 o = *op;
+                        o.x += gn.x; o.y += gn.y;
+                        *op = o;
+                    }
+                    *reinterpret_cast<double2*>(G + (size_t)row * ld + col) = gn;
+                }
             }
         }
     }
 }
 
-// gauge rows: G[pos_k][c] += qs[k] * W[k][col0 + c]      (the Q[:, s] term of the gain, da.py:117-121)
+// inflow part of _apply_gain (nutils.py:116-134, da.py:125): I[k] += sum of the gains of the reaches
+// draining into k (self-loops excluded).  One thread per (row, member pair).
 __global__ void __launch_bounds__(256)
-enkf_gauge_term_kernel(const int32_t* __restrict__ obs_pos, const double* __restrict__ qs, const double* __restrict__ W,
-                       int m, int Mtot, int col0, int Mloc, double* __restrict__ G, int ldg)
+inflow_gain_kernel(const int32_t* __restrict__ up_off, const int32_t* __restrict__ up_pos, const double* __restrict__ G,
+                   double* __restrict__ I, long long n, int ld)
 {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= m * Mloc) return;
-    const int k = gid / Mloc, c = gid - k * Mloc;
-    G[(size_t)obs_pos[k] * ldg + c] += qs[k] * W[(size_t)k * Mtot + col0 + c];
+    const int half = ld >> 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n * half) return;
+    const long long k = gid / half;
+    const int col = (int)(gid - k * half) * 2;
+    const int u0 = up_off[k], u1 = up_off[k + 1];
+    if (u0 == u1) return;
+    double2 s = make_double2(0.0, 0.0);
+    for (int u = u0; u < u1; ++u) {
+        const double2 v = *reinterpret_cast<const double2*>(G + (size_t)up_pos[u] * ld + col);
+        s.x += v.x; s.y += v.y;
+    }
+    double2* ip = reinterpret_cast<double2*>(I + (size_t)k * ld + col);
+    double2 i = *ip;
+    i.x += s.x; i.y += s.y;
+    *ip = i;
 }
 
 __global__ void __launch_bounds__(256)
@@ -430,7 +545,21 @@ cudaError_t launch_dgemm(int transA, int transB, int M, int N, int K, double alp
 {
     if (M <= 0 || N <= 0) return cudaSuccess;
     dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M);
-    dgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K > 0 ? K : 1, 0);
+    dgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K > 0 ? K : 1, 0,
+                                       C, ldc);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// C = alpha op(A) op(B) + beta Cin   (Cin may differ from C)
+cudaError_t launch_dgemm_ex(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
+                            const double* B, int ldb, double beta, const double* Cin, int ldcin, double* C, int ldc,
+                            cudaStream_t st)
+{
+    if (M <= 0 || N <= 0) return cudaSuccess;
+    dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M);
+    dgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K > 0 ? K : 1, 0,
+                                       Cin, ldcin);
     count_launch();
     return cudaGetLastError();
 }
@@ -442,7 +571,8 @@ cudaError_t launch_dgemm_splitk(int transA, int transB, int M, int N, int K, con
     int kchunk = (K + nsplit - 1) / nsplit;
     kchunk = (kchunk + GB_K - 1) / GB_K * GB_K;
     dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M, nsplit);
-    dgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, 1.0, A, lda, B, ldb, 0.0, Cpart, ldc, kchunk, pstride);
+    dgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, 1.0, A, lda, B, ldb, 0.0, Cpart, ldc, kchunk, pstride,
+                                       Cpart, ldc);
     count_launch();
     return cudaGetLastError();
 }
@@ -458,24 +588,27 @@ cudaError_t launch_innovation_cat(const double* HX, const double* Zp, const doub
 cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long pstride, int Mt, double shift, double* Z,
                                     int* info, cudaStream_t st)
 {
-    const size_t smem = 2 * (size_t)Mt * (Mt + 1) * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(chol_solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    chol_solve_small_kernel<<<1, 512, smem, st>>>(Cpart, nsplit, pstride, Mt, shift, Z, info);
+    if (nsplit != CS_NSPLIT || Mt > 96) return cudaErrorInvalidValue;
+    const int MT = Mt <= 64 ? 64 : 96;
+    const size_t smem = (2 * (size_t)MT * (MT + 1) + 6 * MT) * sizeof(double);
+    cudaError_t e;
+    if (MT == 64) {
+        e = cudaFuncSetAttribute(chol_solve_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        chol_solve_small_kernel<64><<<1, 8 * 64, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
+    } else {
+        e = cudaFuncSetAttribute(chol_solve_small_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        chol_solve_small_kernel<96><<<1, 8 * 96, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
+    }
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_woodbury_w(const double* Y, const double* Z, int m, int Mt, double* W, cudaStream_t st)
+cudaError_t launch_enkf_stats(const double* X, int ld, int M, int64_t n, double scale, const int32_t* gauge_of_pos,
+                              double* rowsum, double* HX, cudaStream_t st)
 {
-    woodbury_w_kernel<<<nblk((long long)m * Mt, 256), 256, 0, st>>>(Y, Z, m, Mt, W);
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_rowsum(const double* X, int ld, int M, int64_t n, double* rowsum, cudaStream_t st)
-{
-    rowsum_kernel<<<nblk(n, 8), 256, 0, st>>>(X, ld, M, n, rowsum);
+    enkf_stats_kernel<<<nblk(n, 8), 256, 0, st>>>(X, ld, M, n, scale, gauge_of_pos, rowsum, HX);
     count_launch();
     return cudaGetLastError();
 }
@@ -509,24 +642,22 @@ cudaError_t launch_inverse(double* A, double* W, int m, int* info, cudaStream_t 
     return cudaGetLastError();
 }
 
-cudaError_t launch_enkf_gain(const double* Xall, int ldx, int Mtot, const double* mean, const double* T, int ldt, int Mloc,
-                             double* G, int ldg, int64_t n, int num_sms, cudaStream_t st)
+cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const double* mean, const double* T, int ldt,
+                               int Mloc, double* O, double* G, int ld, int64_t n, const int32_t* gauge_of_pos,
+                               const double* qs, const double* W, int col0, int num_sms, cudaStream_t st)
 {
-    const int Kp = (Mtot + 3) & ~3, Np = (Mloc + 7) & ~7;
-    const size_t smem = ((size_t)Kp * (Np + 1) + (size_t)EG_ROWS * (Kp + 1)) * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(enkf_gain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    long long tiles = (n + EG_ROWS - 1) / EG_ROWS;
-    long long grid = tiles < (long long)num_sms * 4 ? tiles : (long long)num_sms * 4;
-    enkf_gain_kernel<<<(unsigned)grid, 128, smem, st>>>(Xall, ldx, Mtot, mean, T, ldt, Mloc, G, ldg, n);
+    long long tiles = (n + EU_ROWS - 1) / EU_ROWS;
+    long long grid = tiles < (long long)num_sms ? tiles : (long long)num_sms;
+    enkf_update_kernel<<<(unsigned)grid, EU_WARPS * 32, 0, st>>>(Xall, ldx, Mtot, mean, T, ldt, Mloc, O, G, ld, n,
+                                                                 gauge_of_pos, qs, W, col0);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_enkf_gauge_term(const int32_t* obs_pos, const double* qs, const double* W, int m, int Mtot, int col0,
-                                   int Mloc, double* G, int ldg, cudaStream_t st)
+cudaError_t launch_inflow_gain(const int32_t* up_off, const int32_t* up_pos, const double* G, double* I, int64_t n,
+                               int ld, cudaStream_t st)
 {
-    enkf_gauge_term_kernel<<<nblk((long long)m * Mloc, 256), 256, 0, st>>>(obs_pos, qs, W, m, Mtot, col0, Mloc, G, ldg);
+    inflow_gain_kernel<<<nblk(n * (ld >> 1), 256), 256, 0, st>>>(up_off, up_pos, G, I, n, ld);
     count_launch();
     return cudaGetLastError();
 }

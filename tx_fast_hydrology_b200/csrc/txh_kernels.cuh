@@ -57,6 +57,12 @@ struct InitArgs {
     unsigned long long* queue;
     unsigned long long* q_head;
     int32_t n_tasks, n_mblocks, n_init;
+    long long queue_entries;              // slots of the ready queue to clear (pairs * steps of this launch)
+    // forcing interpolation of this launch's steps, resolved on the device (nullptr times = skip)
+    const double* times;                  // [R] float64 ns since epoch
+    StepInterp* steps_out;                // [nsteps]
+    long long t0_ns, dt_ns, step_base;
+    int32_t R, nsteps, method;
 };
 
 struct LevelArgs {
@@ -102,17 +108,21 @@ cudaError_t launch_innovation_cat(const double* HX, const double* Zp, const doub
                                   const double* dinv_diag, int m, int Mt, double* Bc, double* Y, cudaStream_t st);
 cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long pstride, int Mt, double shift, double* Z,
                                     int* info, cudaStream_t st);
-cudaError_t launch_woodbury_w(const double* Y, const double* Z, int m, int Mt, double* W, cudaStream_t st);
-cudaError_t launch_rowsum(const double* X, int ld, int M, int64_t n, double* rowsum, cudaStream_t st);
+cudaError_t launch_dgemm_ex(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
+                            const double* B, int ldb, double beta, const double* Cin, int ldcin, double* C, int ldc,
+                            cudaStream_t st);
+cudaError_t launch_enkf_stats(const double* X, int ld, int M, int64_t n, double scale, const int32_t* gauge_of_pos,
+                              double* rowsum, double* HX, cudaStream_t st);
 cudaError_t launch_innovation(const double* HX, const double* Zp, const double* mean_obs, int m, int M, double* HA,
                               double* dz, cudaStream_t st);
 cudaError_t launch_innov_cov_finish(double* S, const double* qs, const double* R, int m, double scale, cudaStream_t st);
 cudaError_t launch_spd_solve(double* S, double* B, int m, int k, int* info, cudaStream_t st);
 cudaError_t launch_inverse(double* A, double* W, int m, int* info, cudaStream_t st);
-cudaError_t launch_enkf_gain(const double* Xall, int ldx, int Mtot, const double* mean, const double* T, int ldt, int Mloc,
-                             double* G, int ldg, int64_t n, int num_sms, cudaStream_t st);
-cudaError_t launch_enkf_gauge_term(const int32_t* obs_pos, const double* qs, const double* W, int m, int Mtot, int col0,
-                                   int Mloc, double* G, int ldg, cudaStream_t st);
+cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const double* mean, const double* T, int ldt,
+                               int Mloc, double* O, double* G, int ld, int64_t n, const int32_t* gauge_of_pos,
+                               const double* qs, const double* W, int col0, int num_sms, cudaStream_t st);
+cudaError_t launch_inflow_gain(const int32_t* up_off, const int32_t* up_pos, const double* G, double* I, int64_t n,
+                               int ld, cudaStream_t st);
 cudaError_t launch_scale(double* X, int64_t count, double s, cudaStream_t st);
 cudaError_t launch_gather_cols(const double* P, int n, const int32_t* idx, int m, double* out, cudaStream_t st);
 cudaError_t launch_gather_rows_dense(const double* P, int ncols, const int32_t* idx, int m, double* out, cudaStream_t st);

@@ -386,20 +386,52 @@ __device__ __forceinline__ void run_fix(const RouteArgs& a, const TaskDesc& td, 
     cp_async_wait_all();
 }
 
-// Prepares the dataflow runtime for one launch: dependency counters and the ready queue seeded
-// with every task that has no same-step producer.  Queue entry = (step << 32) | (pair + 1).
+// Prepares the dataflow runtime for one launch: the ready queue cleared and seeded with every task that
+// has no same-step producer, the dependency counters, and the forcing interpolation of every step of the
+// launch -- nutils.py:21-34 evaluated in float64 exactly as the reference does (searchsorted-left,
+// clamped ends; x = float(next_timestep.value), muskingum.py:528-530).  Queue entry = (step << 32) | (pair + 1).
 __global__ void __launch_bounds__(256) dataflow_init_kernel(const InitArgs a)
 {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int pairs = a.n_tasks * a.n_mblocks;
-    if (gid < pairs) a.pending[gid] = a.tasks[gid / a.n_mblocks].need0;
-    if (gid < a.n_init * a.n_mblocks) {
-        const int t = a.init_ready[gid / a.n_mblocks];
-        a.queue[gid] = (unsigned long long)(t * a.n_mblocks + gid % a.n_mblocks) + 1ull;
+    const long long gid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long pairs = (long long)a.n_tasks * a.n_mblocks;
+    const long long seeded = (long long)a.n_init * a.n_mblocks;
+    for (long long gid = gid0; gid < a.queue_entries; gid += stride) {
+        unsigned long long e = 0ull;
+        if (gid < seeded) {
+            const int t = a.init_ready[gid / a.n_mblocks];
+            e = (unsigned long long)(t * a.n_mblocks + gid % a.n_mblocks) + 1ull;
+        }
+        a.queue[gid] = e;
     }
-    if (gid == 0) {
+    for (long long gid = gid0; gid < pairs; gid += stride) a.pending[gid] = a.tasks[gid / a.n_mblocks].need0;
+    if (a.times) {
+        for (long long s = gid0; s < a.nsteps; s += stride) {
+            const double x = (double)(a.t0_ns + (a.step_base + s + 1) * a.dt_ns);
+            int lo = 0, hi = a.R;                                   // np.searchsorted(xp, x), side='left'
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (a.times[mid] < x) lo = mid + 1; else hi = mid;
+            }
+            StepInterp si;
+            if (lo == 0) { si.r0 = 0; si.r1 = 0; si.w0 = 1.0; si.w1 = 0.0; }
+            else if (lo >= a.R) { si.r0 = a.R - 1; si.r1 = a.R - 1; si.w0 = 1.0; si.w1 = 0.0; }
+            else {
+                const double dx_0 = __dsub_rn(x, a.times[lo - 1]), dx_1 = __dsub_rn(a.times[lo], x);
+                if (a.method == 1) {
+                    const double frac = __ddiv_rn(dx_0, __dadd_rn(dx_0, dx_1));
+                    si.r0 = lo - 1; si.r1 = lo; si.w0 = __dsub_rn(1.0, frac); si.w1 = frac;
+                } else {
+                    const int r = fabs(dx_0) <= fabs(dx_1) ? lo - 1 : lo;
+                    si.r0 = r; si.r1 = r; si.w0 = 1.0; si.w1 = 0.0;
+                }
+            }
+            a.steps_out[s] = si;
+        }
+    }
+    if (gid0 == 0) {
         a.q_head[0] = 0ull;
-        a.q_head[1] = (unsigned long long)a.n_init * a.n_mblocks;
+        a.q_head[1] = (unsigned long long)seeded;
         a.q_head[2] = 0ull;     // completed tasks
     }
 }
@@ -712,8 +744,11 @@ inline unsigned blocks_for(long long work, int threads) { return (unsigned)((wor
 
 cudaError_t launch_dataflow_init(const InitArgs& a, cudaStream_t st)
 {
-    const int pairs = a.n_tasks * a.n_mblocks;
-    dataflow_init_kernel<<<blocks_for(pairs, 256), 256, 0, st>>>(a);
+    long long work = (long long)a.n_tasks * a.n_mblocks;
+    if (a.queue_entries > work) work = a.queue_entries;
+    unsigned blocks = blocks_for(work, 256);
+    if (blocks > 1184u) blocks = 1184u;                       // grid-stride beyond 8 CTAs per SM
+    dataflow_init_kernel<<<blocks, 256, 0, st>>>(a);
     g_launches++;
     return cudaGetLastError();
 }

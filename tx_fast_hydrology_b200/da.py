@@ -275,18 +275,19 @@ class EnsembleKalmanFilter(BaseCallback):
         if Zp_dev is None:
             Zp_dev = torch.as_tensor(self.perturbed_observations(mdl.datetime), device='cuda')
         dist = torch.distributed
-        net.enkf_stats(O, M, self.reach_indices, self._rowsum, self._HX)
+        # one pass over the state: row sums (already the mean when the ensemble is not sharded) + gauge rows
+        net.enkf_stats(O, M, self.reach_indices, self._rowsum, self._HX, scale=1.0 / Mt if self.world == 1 else 1.0)
         Xall, ldx = None, 0
+        mean = self._rowsum
         if self.world > 1:
             # ensemble mean over all shards (all-reduce) + every shard's gauge rows (all-gather)
-            self._rowsum, self._HXall = combine_statistics(self._rowsum, self._HX, 1, group=self.group)
+            mean, self._HXall = combine_statistics(self._rowsum, self._HX, Mt, group=self.group)
             ld = net.row_stride(M)
             if self._Xall is None:
                 self._Xall = torch.empty((self.world, mdl.n, ld), dtype=torch.float64, device='cuda')
             dist.all_gather_into_tensor(self._Xall, O, group=self.group)     # anomalies of every shard
             Xall = self._Xall.permute(1, 0, 2)[:, :, :M].reshape(mdl.n, Mt).contiguous()
             ldx = Mt
-        mean = self._rowsum.mul_(1.0 / Mt)
         net.enkf_solve(m, Mt, self._HXall, Zp_dev, mean, self.reach_indices, self._qs, self._R, self._work,
                        self._W, self._T, self._Dinv, self._dinv_kind)
         net.enkf_apply(O, I, M, Xall, ldx, Mt, self.rank * M, mean, self._T, self.reach_indices, self._qs,

@@ -233,10 +233,10 @@ class RiverNetwork:
                                          _stream_ptr()))
 
     # ---- assimilation ----------------------------------------------------------------------
-    def enkf_stats(self, O, Mloc, obs_reach, rowsum, HX):
+    def enkf_stats(self, O, Mloc, obs_reach, rowsum, HX, scale=1.0):
         idx = L.as_i64(obs_reach)
         L.check(self._lib.txh_enkf_stats(self.handle, _cuda_ptr(O), int(Mloc), L.ptr_i64(idx), idx.size,
-                                         _cuda_ptr(rowsum), _cuda_ptr(HX), _stream_ptr()))
+                                         float(scale), _cuda_ptr(rowsum), _cuda_ptr(HX), _stream_ptr()))
 
     @staticmethod
     def enkf_work_size(m, Mtot):
