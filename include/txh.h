@@ -72,6 +72,13 @@ int txh_get_schedule_info(const txh_net* net, int64_t info[10]);
 int txh_get_schedule(const txh_net* net, int64_t* pos_of_reach /*[n]*/, int32_t* task_desc /*[n_tasks*12]*/,
                      int32_t* notify, uint32_t* hdr /*[n]*/, uint32_t* inw);
 
+/* window-mode schedule (route_window_kernel): info = {n_tasks, n_slots, max_len, max_words, max_producers,
+ * n_input_words, n_producer_entries, cp_tasks}; task rows are 12 int32: begin, len, kind, in_off, n_words,
+ * prod_off, n_prod, out_slot, n_in, pad x3 */
+int txh_get_window_info(const txh_net* net, int64_t info[8]);
+int txh_get_window_schedule(const txh_net* net, int32_t* wtask_desc, uint32_t* whdr /*[n]*/, uint32_t* winw,
+                            int32_t* wprod);
+
 /* ---- coefficients ----------------------------------------------------------------
  * txh_compute_coeffs replaces Muskingum.compute_muskingum_coeffs (muskingum.py:332-360):
  * host arithmetic in the reference's operation order; results returned in reach order

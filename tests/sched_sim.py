@@ -115,3 +115,84 @@ def simulate(sched, coef, O, I, q_of_step, nsteps, seed=0, order="random"):
                 ready.append(t)
     assert (stepno == nsteps).all(), "not every task ran every step"
     return executed
+
+
+WIN_SLOT, WIN_OWN = 0x80000000, 0x40000000
+WPOCKET, WSEG = 0, 1
+
+
+def simulate_window(w, coef, O, I, q_of_step, nsteps):
+    """Test-only CPU interpreter of the WINDOW-mode descriptors (`txh_get_window_schedule`): every task
+    keeps its rows locally for all `nsteps` steps and exchanges rows through the slot ring, exactly as
+    route_window_kernel does; tasks run one after another in descriptor order (producers first).
+    coef [n][4], O/I [n] schedule order (updated in place).  Returns #task-steps executed."""
+    tasks, hdr, inw, prod = w["tasks"], w["hdr"], w["inw"], w["prod"]
+    nt = tasks.shape[0]
+    ring = np.full((nsteps, max(1, w["n_slots"])), np.nan)
+    done = np.zeros(nt, dtype=bool)
+    cumA = np.empty(O.size)
+    for p in range(O.size):
+        cumA[p] = cumA[p - 1] * coef[p][0] if (p > 0 and (int(hdr[p]) & 1)) else coef[p][0]
+    qs = [q_of_step(s) for s in range(nsteps)]
+    executed = 0
+    for k in range(nt):
+        begin, ln, kind, in_off, nwords, prod_off, nprod, out_slot, n_in = (int(x) for x in tasks[k, :9])
+        for pr in prod[prod_off:prod_off + nprod]:
+            assert pr < k and done[pr], "producer not ordered before its consumer"
+        Ol = O[begin:begin + ln].copy(); Il = I[begin:begin + ln].copy()
+        for s in range(nsteps):
+            q = qs[s]
+            wv = in_off
+            if kind == WPOCKET:
+                scratch = np.full(32, np.nan)
+                acc = 0.0
+                for r in range(ln):
+                    p = begin + r
+                    h = int(hdr[p]); infl = acc if (h & 1) else 0.0
+                    for _ in range((h >> 6) & 0x1ffffff):
+                        x = int(inw[wv]); wv += 1
+                        if x & WIN_SLOT:
+                            v = ring[s, x & 0x3fffffff]; assert not np.isnan(v); infl += v
+                        elif x & WIN_OWN:
+                            assert (x & 0x3fffffff) < r; infl += Ol[x & 0x3fffffff]
+                        else:
+                            assert not np.isnan(scratch[x]); infl += scratch[x]; scratch[x] = np.nan
+                    a, b, c, g = coef[p]
+                    on = a * infl + (b * Il[r] + c * Ol[r] + g * q[p])
+                    Il[r] = infl; Ol[r] = on
+                    if h >> 31:
+                        ring[s, int(inw[wv])] = on; wv += 1
+                    sl = (h >> 1) & 31
+                    if sl:
+                        scratch[sl - 1] = on
+                    acc = on
+            else:
+                ent = [int(inw[wv + t]) for t in range(n_in)]; wv += n_in
+                B = 0.0
+                for r in range(ln):                                   # PRE
+                    p = begin + r
+                    h = int(hdr[p]); side = 0.0
+                    for _ in range((h >> 6) & 0x1fff):
+                        x = int(inw[wv]); wv += 1
+                        assert x & WIN_SLOT
+                        v = ring[s, x & 0x3fffffff]; assert not np.isnan(v); side += v
+                    a, b, c, g = coef[p]
+                    infl = side + (B if (h & 1) else 0.0)
+                    B = a * infl + (b * Il[r] + c * Ol[r] + g * q[p])
+                    Il[r] = side; Ol[r] = B
+                oin = 0.0                                             # hop
+                for x in ent:
+                    v = ring[s, x & 0x3fffffff]; assert not np.isnan(v); oin += v
+                out = cumA[begin + ln - 1] * oin + Ol[ln - 1]
+                ring[s, out_slot] = out
+                op = oin                                              # FIX
+                for r in range(ln):
+                    on = out if r == ln - 1 else cumA[begin + r] * oin + Ol[r]
+                    Ol[r] = on
+                    Il[r] = op + Il[r]
+                    op = on
+            assert wv == in_off + nwords, "input stream not consumed exactly"
+            executed += 1
+        O[begin:begin + ln] = Ol; I[begin:begin + ln] = Il
+        done[k] = True
+    return executed

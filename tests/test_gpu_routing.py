@@ -111,12 +111,16 @@ def test_golden_model_c1(torch_cuda, libtxh, golden_dir):
     assert relerr(net.unpack_host(I, 1)[:, 0], g["I"][-1]) < RTOL
 
 
+@pytest.mark.parametrize("kernel", ["window", "dataflow"])
 @pytest.mark.parametrize("n,seed,M,sched", [
     (1000, 1, 1, None), (1000, 1, 3, None), (2500, 6, 64, None), (2500, 6, 70, None),
     (1500, 9, 130, None), (3000, 4, 5, (8, 4, 6, 3)), (300, 5, 2, (4, 8, 8, 1)), (7, 12, 2, None),
-    (1, 13, 1, None)])
-def test_members_vs_oracle(torch_cuda, libtxh, oracle, n, seed, M, sched):
-    """Member-batched multi-step run == _ax_bu looped per member."""
+    (1, 13, 1, None), (4000, 21, 8, (16, 8, 12, 2, 4))])
+def test_members_vs_oracle(torch_cuda, libtxh, oracle, monkeypatch, n, seed, M, sched, kernel):
+    """Member-batched multi-step run == _ax_bu looped per member, through both device
+    paths: the window-resident kernel (state in shared memory across the steps of a launch) and the
+    dataflow kernel (state streamed every step)."""
+    monkeypatch.setenv("TXH_ROUTE_KERNEL", kernel)
     torch = torch_cuda
     from tx_fast_hydrology_b200 import synthetic as S
     from tx_fast_hydrology_b200.network import Forcing

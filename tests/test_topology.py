@@ -100,6 +100,14 @@ def test_schedule_protocol(libtxh, oracle, n, seed, sp, order):
         Ir, Or = O._ax_bu(sn[ind == 0], en, a, b, c, g, Ir, Or, qs[s], ind)
     assert np.abs(Os[pos] - Or).max() <= 1e-12 * np.abs(Or).max()
     assert np.abs(Is[pos] - Ir).max() <= 1e-12 * np.abs(Ir).max()
+    # the window-mode descriptors over the same row layout (route_window_kernel)
+    win = rn.window_schedule()
+    assert win["tasks"][:, 1].sum() == n and (np.diff(np.sort(win["tasks"][:, 0])) > 0).all()
+    Ow = o0[rop].copy(); Iw = i0[rop].copy()
+    exw = sched_sim.simulate_window(win, coef, Ow, Iw, lambda s: qs[s][rop], T)
+    assert exw == T * win["n_tasks"]
+    assert np.abs(Ow[pos] - Or).max() <= 1e-12 * np.abs(Or).max()
+    assert np.abs(Iw[pos] - Ir).max() <= 1e-12 * np.abs(Ir).max()
 
 
 def test_texas_scale_schedule(libtxh):

@@ -73,6 +73,13 @@ struct txh_net {
     std::vector<int64_t> obs_cached;    // gauge list whose positions are resident in d_obs
     int32_t* d_obs = nullptr; size_t obs_cap = 0;
     int32_t* d_gauge_of_pos = nullptr;  // [n] gauge index of each schedule position, or -1
+    // window-mode kernel
+    WTaskDesc* d_wtasks = nullptr;
+    uint32_t *d_whdr = nullptr, *d_winw = nullptr;
+    int32_t* d_wprod = nullptr;
+    double* d_ring = nullptr; size_t ring_cap = 0;
+    int32_t* d_prog = nullptr; size_t prog_cap = 0;
+    int route_kernel = 0;               // 0 auto (window unless recording), 1 dataflow, 2 window
 };
 
 struct txh_forcing {
@@ -111,6 +118,14 @@ int ensure_device(txh_net* net)
     if ((rc = upload(&net->d_reach_of_pos, s.reach_of_pos))) return rc;
     if ((rc = upload(&net->d_pos_of_reach, s.pos_of_reach))) return rc;
     if ((rc = upload(&net->d_outlet, s.is_outlet_pos))) return rc;
+    if ((rc = upload(&net->d_wtasks, s.wtasks))) return rc;
+    if ((rc = upload(&net->d_whdr, s.whdr))) return rc;
+    if ((rc = upload(&net->d_winw, s.winw))) return rc;
+    if ((rc = upload(&net->d_wprod, s.wprod))) return rc;
+    if (const char* k = getenv("TXH_ROUTE_KERNEL")) {
+        if (!strcmp(k, "dataflow")) net->route_kernel = 1;
+        else if (!strcmp(k, "window")) net->route_kernel = 2;
+    }
     CU(cudaMalloc((void**)&net->d_coef, sizeof(double) * (5 * net->topo.n + net->sched.link_last.size() + 1)));
     CU(cudaMalloc((void**)&net->d_qtmp, sizeof(double) * net->topo.n));
     CU(cudaMalloc((void**)&net->d_qctl, 64));
@@ -264,6 +279,87 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
     return TXH_OK;
 }
 
+// The window-resident kernel (txh_window.cu): state in shared memory for all steps of a launch.
+// Returns 1 when the schedule does not fit it (rows of a task x 1 KB per warp) and the caller should fall
+// back to the dataflow kernel.
+int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, const double* W, int wm_ld,
+               const StepPlan& plan, int64_t nsteps, cudaStream_t st)
+{
+    const Schedule& s = net->sched;
+    const int ld = (int)txh_row_stride(M);
+    const int nmb = (ld + kMemberBlock - 1) / kMemberBlock;
+    const size_t pairs = (size_t)s.wtasks.size() * nmb;
+    if (pairs >= (size_t(1) << 31)) return fail(TXH_E_INVALID, "too many (task, member block) pairs");
+    WinArgs a{};
+    auto up16 = [](int x) { return (x + 15) & ~15; };
+    const int rc = std::max(1, s.w_max_len), slots = std::max(1, s.slots_used);
+    a.off_O = rc * 512;
+    a.off_scr = 2 * rc * 512;
+    a.off_in = a.off_scr + slots * 512;
+    a.off_coef = a.off_in + 8 * 512;
+    a.off_cum = a.off_coef + rc * 32;
+    a.off_f0 = a.off_cum + up16(rc * 8);
+    a.off_f1 = a.off_f0 + up16(rc * 8);
+    a.off_hdr = a.off_f1 + up16(rc * 8);
+    a.off_words = a.off_hdr + up16(rc * 4);
+    a.off_prod = a.off_words + up16(std::max(1, s.w_max_words) * 4);
+    a.off_list = a.off_prod + up16(std::max(1, s.w_max_prod) * 4);
+    a.smem_per_warp = a.off_list + up16(std::max(1, s.w_max_words) * 4);
+    const int smem_max = 227 * 1024;
+    int wpc = std::min(8, smem_max / a.smem_per_warp);
+    if (wpc < 2) return 1;
+    // ring[step][slot][ld]: one launch covers at most 16 steps (and at most ~1 GiB of ring)
+    const size_t slot_row = (size_t)std::max(1, s.n_wslots) * ld;
+    int64_t spl = std::min<int64_t>(16, nsteps);
+    while (spl > 1 && slot_row * spl * sizeof(double) > (size_t(1) << 30)) --spl;
+    if (slot_row * spl > net->ring_cap) {
+        if (net->d_ring) CU(cudaFree(net->d_ring));
+        CU(cudaMalloc((void**)&net->d_ring, slot_row * spl * sizeof(double)));
+        net->ring_cap = slot_row * spl;
+    }
+    if (pairs > net->prog_cap) {
+        if (net->d_prog) CU(cudaFree(net->d_prog));
+        CU(cudaMalloc((void**)&net->d_prog, pairs * sizeof(int32_t)));
+        net->prog_cap = pairs;
+    }
+    const StepInterp* d_steps = net->d_unit_step;
+    if (plan.times) {
+        if ((size_t)spl > net->steps_cap) {
+            if (net->d_steps) CU(cudaFree(net->d_steps));
+            CU(cudaMalloc((void**)&net->d_steps, sizeof(StepInterp) * spl));
+            net->steps_cap = spl;
+        }
+        d_steps = net->d_steps;
+    }
+    for (int64_t s0 = 0; s0 < nsteps; s0 += spl) {
+        const int64_t ns = std::min<int64_t>(spl, nsteps - s0);
+        InitArgs ia{};
+        ia.times = plan.times; ia.steps_out = net->d_steps; ia.t0_ns = plan.t0_ns; ia.dt_ns = plan.dt_ns;
+        ia.step_base = s0; ia.R = (int32_t)plan.R; ia.nsteps = (int32_t)ns; ia.method = plan.method;
+        CU(launch_window_init(ia, net->d_prog, (long long)pairs, net->d_qctl + 3, st));
+        a.tasks = net->d_wtasks; a.hdr = net->d_whdr; a.inw = net->d_winw; a.prod = net->d_wprod;
+        a.coef = net->d_coef; a.cumA = net->d_coef + 4 * net->topo.n;
+        a.O = O; a.I = I; a.ring = net->d_ring; a.prog = net->d_prog; a.ticket = net->d_qctl + 3;
+        a.F = F; a.steps = d_steps; a.Wmul = W; a.status = net->d_status; a.watchdog_ns = net->watchdog_ns;
+        a.n = net->topo.n; a.n_tasks = (int32_t)s.wtasks.size(); a.n_mblocks = nmb; a.nsteps = (int32_t)ns;
+        a.n_slots = std::max(1, s.n_wslots); a.ld = ld; a.M = (int32_t)M; a.wm_ld = wm_ld;
+        CU(launch_route_window(a, wpc, net->num_sms, st));
+    }
+    return TXH_OK;
+}
+
+// routing entry: the window kernel unless recording was asked for (or the environment says otherwise)
+int run_routing(txh_net* net, double* O, double* I, int64_t M, const double* F, const double* W, int wm_ld,
+                const StepPlan& plan, int64_t nsteps, const int32_t* rec_slot, double* rec_out, int rec_every,
+                int rec_count, cudaStream_t st)
+{
+    if (net->route_kernel != 1 && !rec_slot) {
+        const int rc = run_window(net, O, I, M, F, W, wm_ld, plan, nsteps, st);
+        if (rc != 1) return rc;
+    }
+    return run_dataflow(net, O, I, M, F, W, wm_ld, plan, nsteps, rec_slot, rec_out, rec_every, rec_count, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -309,6 +405,9 @@ void txh_destroy(txh_net* net)
         if (net->d_tmp_idx) cudaFree(net->d_tmp_idx);
         if (net->d_obs) cudaFree(net->d_obs);
         if (net->d_gauge_of_pos) cudaFree(net->d_gauge_of_pos);
+        cudaFree(net->d_wtasks); cudaFree(net->d_whdr); cudaFree(net->d_winw); cudaFree(net->d_wprod);
+        if (net->d_ring) cudaFree(net->d_ring);
+        if (net->d_prog) cudaFree(net->d_prog);
         if (net->h_status) cudaFreeHost(net->h_status);
     }
     delete net;
@@ -374,6 +473,25 @@ int txh_get_schedule(const txh_net* net, int64_t* pos_of_reach, int32_t* task_de
     if (notify) std::memcpy(notify, s.notify.data(), s.notify.size() * sizeof(int32_t));
     if (hdr) std::memcpy(hdr, s.hdr.data(), s.hdr.size() * sizeof(uint32_t));
     if (inw) std::memcpy(inw, s.inw.data(), s.inw.size() * sizeof(uint32_t));
+    return TXH_OK;
+}
+
+int txh_get_window_info(const txh_net* net, int64_t info[8])
+{
+    if (!net || !info) return fail(TXH_E_INVALID, "null argument");
+    const Schedule& s = net->sched;
+    info[0] = (int64_t)s.wtasks.size(); info[1] = s.n_wslots; info[2] = s.w_max_len; info[3] = s.w_max_words;
+    info[4] = s.w_max_prod; info[5] = (int64_t)s.winw.size(); info[6] = (int64_t)s.wprod.size(); info[7] = s.w_cp_tasks;
+    return TXH_OK;
+}
+int txh_get_window_schedule(const txh_net* net, int32_t* wtask_desc, uint32_t* whdr, uint32_t* winw, int32_t* wprod)
+{
+    if (!net) return fail(TXH_E_INVALID, "null argument");
+    const Schedule& s = net->sched;
+    if (wtask_desc) std::memcpy(wtask_desc, s.wtasks.data(), s.wtasks.size() * sizeof(WTaskDesc));
+    if (whdr) std::memcpy(whdr, s.whdr.data(), s.whdr.size() * sizeof(uint32_t));
+    if (winw) std::memcpy(winw, s.winw.data(), s.winw.size() * sizeof(uint32_t));
+    if (wprod) std::memcpy(wprod, s.wprod.data(), s.wprod.size() * sizeof(int32_t));
     return TXH_OK;
 }
 
@@ -572,8 +690,8 @@ int txh_route_run(txh_net* net, double* O, double* I, int64_t M, const txh_forci
         CU(cudaStreamSynchronize(st));
         rec_slot = net->d_rec_slot;
     }
-    return run_dataflow(net, O, I, M, fo ? fo->d_F : nullptr, fo ? fo->d_W : nullptr, fo ? (int)fo->M : 0,
-                        plan, nsteps, rec_slot, rec_out, (int)rec_every, (int)rec_count, st);
+    return run_routing(net, O, I, M, fo ? fo->d_F : nullptr, fo ? fo->d_W : nullptr, fo ? (int)fo->M : 0,
+                       plan, nsteps, rec_slot, rec_out, (int)rec_every, (int)rec_count, st);
 }
 
 int txh_route_step(txh_net* net, double* O, double* I, int64_t M, const double* q, void* stream)

@@ -65,6 +65,30 @@ struct InitArgs {
     int32_t R, nsteps, method;
 };
 
+// route_window_kernel (txh_window.cu)
+struct WinArgs {
+    const WTaskDesc* tasks;
+    const uint32_t* hdr;                  // window headers per position
+    const uint32_t* inw;
+    const int32_t* prod;
+    const double* coef;                   // [n][4]
+    const double* cumA;                   // [n]
+    double* O;
+    double* I;
+    double* ring;                         // [nsteps][n_slots][ld] rows handed between tasks
+    int32_t* prog;                        // [n_tasks * n_mblocks] steps published by each (task, member block)
+    unsigned long long* ticket;
+    const double* F;                      // [R][n] schedule order, or nullptr
+    const StepInterp* steps;              // [nsteps]
+    const double* Wmul;                   // [R][wm_ld] or nullptr
+    int32_t* status;
+    unsigned long long watchdog_ns;
+    int64_t n;
+    int32_t n_tasks, n_mblocks, nsteps, n_slots, ld, M, wm_ld;
+    // per-warp shared memory (bytes): [I rows][O rows][scratch slots][input ring][coef][cumA][f0][f1][hdr][words][producers][slot list]
+    int32_t smem_per_warp, off_O, off_scr, off_in, off_coef, off_cum, off_f0, off_f1, off_hdr, off_words, off_prod, off_list;
+};
+
 struct LevelArgs {
     const int32_t* lvl_pos;               // positions of this level
     int32_t count;
@@ -80,6 +104,9 @@ struct LevelArgs {
 cudaError_t launch_dataflow_init(const InitArgs& a, cudaStream_t st);
 cudaError_t launch_route_dataflow(const RouteArgs& a, int num_sms, cudaStream_t st);
 cudaError_t launch_route_level(const LevelArgs& a, cudaStream_t st);
+cudaError_t launch_window_init(const InitArgs& a, int32_t* prog, long long n_prog, unsigned long long* ticket,
+                               cudaStream_t st);
+cudaError_t launch_route_window(const WinArgs& a, int warps_per_cta, int num_sms, cudaStream_t st);
 cudaError_t launch_init_inflows(const int32_t* up_off, const int32_t* up_pos, const uint8_t* is_outlet,
                                 const double* O, double* I, int64_t n, int ld, int M, cudaStream_t st);
 cudaError_t launch_apply_gain(const int32_t* up_off, const int32_t* up_pos, const double* G, double* O,

@@ -494,6 +494,149 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
         }
     }
 
+    // ---- window-mode tasks over the same groups -------------------------------------------
+    // One task per row group.  Rows read across tasks travel through slots of a ring: every pocket
+    // root read by another task, and the last row of every segment.
+    {
+        const int32_t ng = (int32_t)g_begin.size();
+        std::vector<int32_t> grp_of(n, -1);
+        for (int32_t g = 0; g < ng; ++g)
+            for (int32_t e = g_begin[g]; e < g_begin[g] + g_len[g]; ++e) grp_of[rows[e]] = g;
+        std::vector<int32_t> unit_pocket(ng, -1), unit_pre(ng, -1);
+        for (int32_t u = 0; u < nu; ++u) {
+            if (units[u].kind == TASK_POCKET) unit_pocket[units[u].grp] = u;
+            if (units[u].kind == TASK_PRE) unit_pre[units[u].grp] = u;
+        }
+        std::vector<int32_t> slot_of_reach(n, -1);
+        n_wslots = 0;
+        auto slot_for = [&](int32_t c) { if (slot_of_reach[c] < 0) slot_of_reach[c] = n_wslots++; return slot_of_reach[c]; };
+        struct WU { std::vector<uint32_t> words; std::vector<int32_t> prod, prod_in; int32_t n_in = 0, out_slot = -1, kind = 0; };
+        std::vector<WU> wu(ng);
+        std::vector<uint32_t> ghdr(rhdr);                                  // window headers, group-row order
+        for (int32_t g = 0; g < ng; ++g) {
+            WU& W = wu[g];
+            if (unit_pocket[g] >= 0) {
+                W.kind = WTASK_POCKET;
+                const Unit& U = units[unit_pocket[g]];
+                size_t w = 0;
+                for (int32_t e = g_begin[g]; e < g_begin[g] + g_len[g]; ++e) {
+                    const uint32_t h = rhdr[e];
+                    const uint32_t nin = (h >> 6) & 0x1ffffffu;
+                    for (uint32_t q = 0; q < nin; ++q, ++w) {
+                        const uint32_t x = U.ins[w];
+                        if (!(x & INW_ROW)) { W.words.push_back(x); continue; }
+                        const int32_t c = (int32_t)(x & ~INW_ROW);
+                        if (grp_of[c] == g) {                              // a row of this task (scratch fallback)
+                            int32_t k = -1;
+                            for (int32_t e2 = g_begin[g]; e2 < e; ++e2) if (rows[e2] == c) { k = e2 - g_begin[g]; break; }
+                            if (k < 0) { err = "internal: own-row input not yet evaluated"; return false; }
+                            W.words.push_back(WIN_OWN | (uint32_t)k);
+                        } else {
+                            W.words.push_back(WIN_SLOT | (uint32_t)slot_for(c));
+                            W.prod.push_back(grp_of[c]);
+                        }
+                    }
+                    if (h & HDR_PUSH) ++w;                                 // the dataflow side-buffer row: unused here
+                }
+                if (w != U.ins.size()) { err = "internal: pocket stream mismatch"; return false; }
+            } else {
+                W.kind = WTASK_SEG;
+                const Unit& P = units[unit_pre[g]];
+                const Unit& F = units[unit_pre[g] + 1];
+                for (uint32_t x : F.ins) {                                 // rows entering the segment
+                    const int32_t c = (int32_t)(x & ~INW_ROW);
+                    W.words.push_back(WIN_SLOT | (uint32_t)slot_for(c));
+                    W.prod_in.push_back(grp_of[c]);
+                    ++W.n_in;
+                }
+                for (uint32_t x : P.ins) {                                 // pocket roots, in row order
+                    const int32_t c = (int32_t)(x & ~INW_ROW);
+                    W.words.push_back(WIN_SLOT | (uint32_t)slot_for(c));
+                    W.prod.push_back(grp_of[c]);
+                }
+                W.out_slot = slot_for(rows[g_begin[g] + g_len[g] - 1]);
+            }
+            sort_unique(W.prod);
+        }
+        // publishing rows: pocket rows with a slot get HDR_PUSH (+ the slot word after their inputs)
+        for (int32_t g = 0; g < ng; ++g) {
+            if (wu[g].kind != WTASK_POCKET) continue;
+            std::vector<uint32_t> out;
+            size_t w = 0;
+            for (int32_t e = g_begin[g]; e < g_begin[g] + g_len[g]; ++e) {
+                uint32_t h = rhdr[e] & ~HDR_PUSH;
+                const uint32_t nin = (h >> 6) & 0x1ffffffu;
+                for (uint32_t q = 0; q < nin; ++q) out.push_back(wu[g].words[w++]);
+                if (slot_of_reach[rows[e]] >= 0) { h |= HDR_PUSH; out.push_back((uint32_t)slot_of_reach[rows[e]]); }
+                ghdr[e] = h;
+            }
+            wu[g].words.swap(out);
+        }
+        // topological order over the producer edges, longest remaining chain first
+        std::vector<std::vector<int32_t>> cons(ng);
+        std::vector<std::vector<int32_t>> allprod(ng);
+        for (int32_t g = 0; g < ng; ++g) {
+            allprod[g] = wu[g].prod;
+            allprod[g].insert(allprod[g].end(), wu[g].prod_in.begin(), wu[g].prod_in.end());
+            sort_unique(allprod[g]);
+            for (int32_t pr : allprod[g]) cons[pr].push_back(g);
+        }
+        std::vector<int64_t> wcp(ng, 0);
+        std::vector<int32_t> wcpt(ng, 0), worder0;
+        {
+            std::vector<int32_t> pend(ng);
+            for (int32_t g = 0; g < ng; ++g) { pend[g] = (int32_t)allprod[g].size(); if (!pend[g]) worder0.push_back(g); }
+            for (size_t k = 0; k < worder0.size(); ++k)
+                for (int32_t c : cons[worder0[k]]) if (--pend[c] == 0) worder0.push_back(c);
+            if ((int32_t)worder0.size() != ng) { err = "internal: window task graph has a cycle"; return false; }
+            for (int32_t k = ng - 1; k >= 0; --k) {
+                const int32_t g = worder0[k];
+                int64_t best = 0; int32_t bt = 0;
+                for (int32_t c : cons[g]) { best = std::max(best, wcp[c]); bt = std::max(bt, wcpt[c]); }
+                wcp[g] = best + 8 + g_len[g];
+                wcpt[g] = bt + 1;
+            }
+        }
+        std::vector<int32_t> worder; worder.reserve(ng);
+        {
+            auto cmp = [&](int32_t a, int32_t b) { return wcp[a] != wcp[b] ? wcp[a] < wcp[b] : a > b; };
+            std::priority_queue<int32_t, std::vector<int32_t>, decltype(cmp)> pq(cmp);
+            std::vector<int32_t> pend(ng);
+            for (int32_t g = 0; g < ng; ++g) { pend[g] = (int32_t)allprod[g].size(); if (!pend[g]) pq.push(g); }
+            while (!pq.empty()) {
+                const int32_t g = pq.top(); pq.pop();
+                worder.push_back(g);
+                for (int32_t c : cons[g]) if (--pend[c] == 0) pq.push(c);
+            }
+        }
+        std::vector<int32_t> wrank(ng);
+        for (int32_t k = 0; k < ng; ++k) wrank[worder[k]] = k;
+        wtasks.assign(ng, WTaskDesc{});
+        whdr.assign(n, 0); winw.clear(); wprod.clear();
+        w_max_len = w_max_words = w_max_prod = w_cp_tasks = 0;
+        for (int32_t k = 0; k < ng; ++k) {
+            const int32_t g = worder[k];
+            const WU& W = wu[g];
+            WTaskDesc& td = wtasks[k];
+            td.begin = pos_of_reach[rows[g_begin[g]]]; td.len = g_len[g]; td.kind = W.kind;
+            td.in_off = (int32_t)winw.size(); td.n_words = (int32_t)W.words.size();
+            winw.insert(winw.end(), W.words.begin(), W.words.end());
+            td.prod_off = (int32_t)wprod.size(); td.n_prod = (int32_t)(W.prod_in.size() + W.prod.size());
+            for (const std::vector<int32_t>* lst : {&W.prod_in, &W.prod})
+                for (int32_t pr : *lst) {
+                    if (wrank[pr] >= k) { err = "internal: window producer ordered after consumer"; return false; }
+                    wprod.push_back(wrank[pr]);
+                }
+            td.out_slot = W.out_slot; td.n_in = W.n_in;
+            for (int32_t e = 0; e < g_len[g]; ++e) {
+                if (pos_of_reach[rows[g_begin[g] + e]] != td.begin + e) { err = "internal: group rows not contiguous"; return false; }
+                whdr[td.begin + e] = ghdr[g_begin[g] + e];
+            }
+            w_max_len = std::max(w_max_len, td.len); w_max_words = std::max(w_max_words, td.n_words);
+            w_max_prod = std::max(w_max_prod, td.n_prod); w_cp_tasks = std::max(w_cp_tasks, wcpt[g]);
+        }
+    }
+
     // ---- position-space CSR of upstream rows + level lists -------------------------------
     up_off.assign(n + 1, 0); up_pos.resize(t.child.size());
     is_outlet_pos.assign(n, 0);

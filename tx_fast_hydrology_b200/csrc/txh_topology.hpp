@@ -39,9 +39,9 @@ struct Topology {
 
 struct SchedParams {
     int long_path_min = 32;   // paths at least this long become spines
-    int spine_cap = 32;       // reaches per spine segment (a PRE and a FIX task each)
-    int pocket_cap = 48;      // reaches per pocket task (bundled side subtrees)
-    int max_slots = 12;       // shared-memory scratch rows per warp
+    int spine_cap = 16;       // reaches per spine segment (a PRE and a FIX task each; one window task)
+    int pocket_cap = 20;      // reaches per pocket task (bundled side subtrees)
+    int max_slots = 8;        // shared-memory scratch rows per warp
     int link_cap = 8;         // segments per LINK task (blocks chained along the path)
 };
 
@@ -92,6 +92,27 @@ struct TaskDesc {
     int32_t pad_;
 };
 
+// Window task (route_window_kernel): one warp owns the task's rows in shared memory for every step of
+// a launch and exchanges single rows with other tasks through the slot ring.
+//   WPOCKET : a pocket (bundled side subtrees), evaluated depth-first each step
+//   WSEG    : one spine segment; per step the PRE recurrence, the hop
+//             out = A_last * o_in + B_last published to its own slot, then the FIX pass
+// Input word (window mode): bit 31 -> slot of the ring, bit 30 -> row of this task, else scratch slot.
+// Stream of a WPOCKET: the words of its rows in order (a row whose header has HDR_PUSH is followed by
+// the slot it publishes).  Stream of a WSEG: [n_in entering slots][side slots of the rows in order].
+constexpr uint32_t WIN_SLOT = 0x80000000u, WIN_OWN = 0x40000000u;
+constexpr int WTASK_POCKET = 0, WTASK_SEG = 1;
+struct WTaskDesc {
+    int32_t begin, len;      // rows [begin, begin + len)
+    int32_t kind;
+    int32_t in_off, n_words; // input stream
+    int32_t prod_off, n_prod;// producer tasks (indices in window-task order, all smaller than this task's): first the
+                             // n_in owners of the entering slots (same order), then the distinct other producers
+    int32_t out_slot;        // WSEG: slot of the segment's outflow; -1 otherwise
+    int32_t n_in;            // WSEG: number of entering slots at the head of the stream
+    int32_t pad_[3];
+};
+
 struct Schedule {
     SchedParams prm;
     std::vector<int32_t> pos_of_reach, reach_of_pos;
@@ -111,6 +132,11 @@ struct Schedule {
     int32_t max_link_len = 0;               // longest LINK task (segments)
     int32_t max_words = 0, max_link_words = 0;   // longest input streams (walking tasks / LINK)
     int32_t n_side = 0;                     // rows of the side buffer
+    // window-mode descriptors over the same row layout
+    std::vector<WTaskDesc> wtasks;          // in a topological, critical-path-first order
+    std::vector<uint32_t> whdr, winw;       // per-position headers / input streams of the window tasks
+    std::vector<int32_t> wprod;
+    int32_t n_wslots = 0, w_max_len = 0, w_max_words = 0, w_max_prod = 0, w_cp_tasks = 0;
     int32_t cp_tasks = 0;                   // tasks on the longest same-step dependent chain
     int64_t cp_cost = 0;
 

@@ -154,6 +154,36 @@ class RiverNetwork:
         return {"pos_of_reach": pos, "tasks": tasks, "notify": deps[:info["n_notify"]], "hdr": hdr,
                 "inw": inw[:info["n_input_words"]]}
 
+    def window_schedule(self):
+        info = np.zeros(8, dtype=np.int64)
+        L.check(self._lib.txh_get_window_info(self.handle, L.ptr_i64(info)))
+        keys = ["n_tasks", "n_slots", "max_len", "max_words", "max_prod", "n_words", "n_prod", "cp_tasks"]
+        d = dict(zip(keys, (int(x) for x in info)))
+        tasks = np.empty((d["n_tasks"], 12), dtype=np.int32)
+        hdr = np.empty(self.n, dtype=np.uint32)
+        inw = np.empty(max(1, d["n_words"]), dtype=np.uint32)
+        prod = np.empty(max(1, d["n_prod"]), dtype=np.int32)
+        L.check(self._lib.txh_get_window_schedule(
+            self.handle, tasks.ctypes.data_as(L.p_i32), hdr.ctypes.data_as(L.p_u32), inw.ctypes.data_as(L.p_u32),
+            prod.ctypes.data_as(L.p_i32)))
+        d.update(tasks=tasks, hdr=hdr, inw=inw[:d["n_words"]], prod=prod[:d["n_prod"]])
+        return d
+
+    def window_schedule(self):
+        info = np.zeros(8, dtype=np.int64)
+        L.check(self._lib.txh_get_window_info(self.handle, L.ptr_i64(info)))
+        keys = ["n_tasks", "n_slots", "max_len", "max_words", "max_prod", "n_words", "n_prod", "cp_tasks"]
+        d = dict(zip(keys, (int(x) for x in info)))
+        tasks = np.empty((d["n_tasks"], 12), dtype=np.int32)
+        hdr = np.empty(self.n, dtype=np.uint32)
+        inw = np.empty(max(1, d["n_words"]), dtype=np.uint32)
+        prod = np.empty(max(1, d["n_prod"]), dtype=np.int32)
+        L.check(self._lib.txh_get_window_schedule(
+            self.handle, tasks.ctypes.data_as(L.p_i32), hdr.ctypes.data_as(L.p_u32), inw.ctypes.data_as(L.p_u32),
+            prod.ctypes.data_as(L.p_i32)))
+        d.update(tasks=tasks, hdr=hdr, inw=inw[:d["n_words"]], prod=prod[:d["n_prod"]])
+        return d
+
     # ---- coefficients ---------------------------------------------------------------------
     def compute_coeffs(self, K, X, dt):
         K = L.as_f64(K); X = L.as_f64(X)
