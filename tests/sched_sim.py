@@ -152,7 +152,7 @@ def simulate_window(w, coef, O, I, q_of_step, nsteps):
                     for _ in range((h >> 6) & 0x1ffffff):
                         x = int(inw[wv]); wv += 1
                         if x & WIN_SLOT:
-                            v = ring[s, x & 0x3fffffff]; assert not np.isnan(v); infl += v
+                            v = ring[s, x & 0x3fffffff]; assert not np.isnan(v); infl += v; ring[s, x & 0x3fffffff] = np.nan
                         elif x & WIN_OWN:
                             assert (x & 0x3fffffff) < r; infl += Ol[x & 0x3fffffff]
                         else:
@@ -175,16 +175,17 @@ def simulate_window(w, coef, O, I, q_of_step, nsteps):
                     for _ in range((h >> 6) & 0x1fff):
                         x = int(inw[wv]); wv += 1
                         assert x & WIN_SLOT
-                        v = ring[s, x & 0x3fffffff]; assert not np.isnan(v); side += v
+                        v = ring[s, x & 0x3fffffff]; assert not np.isnan(v); side += v; ring[s, x & 0x3fffffff] = np.nan
                     a, b, c, g = coef[p]
                     infl = side + (B if (h & 1) else 0.0)
                     B = a * infl + (b * Il[r] + c * Ol[r] + g * q[p])
                     Il[r] = side; Ol[r] = B
                 oin = 0.0                                             # hop
                 for x in ent:
-                    v = ring[s, x & 0x3fffffff]; assert not np.isnan(v); oin += v
+                    v = ring[s, x & 0x3fffffff]; assert not np.isnan(v); oin += v; ring[s, x & 0x3fffffff] = np.nan
                 out = cumA[begin + ln - 1] * oin + Ol[ln - 1]
-                ring[s, out_slot] = out
+                if out_slot >= 0:
+                    ring[s, out_slot] = out
                 op = oin                                              # FIX
                 for r in range(ln):
                     on = out if r == ln - 1 else cumA[begin + r] * oin + Ol[r]
@@ -195,4 +196,5 @@ def simulate_window(w, coef, O, I, q_of_step, nsteps):
             executed += 1
         O[begin:begin + ln] = Ol; I[begin:begin + ln] = Il
         done[k] = True
+    assert np.isnan(ring).all(), "a published row was never consumed (the ring would not be clean for the next launch)"
     return executed

@@ -77,8 +77,7 @@ struct txh_net {
     WTaskDesc* d_wtasks = nullptr;
     uint32_t *d_whdr = nullptr, *d_winw = nullptr;
     int32_t* d_wprod = nullptr;
-    double* d_ring = nullptr; size_t ring_cap = 0;
-    int32_t* d_prog = nullptr; size_t prog_cap = 0;
+    double* d_ring = nullptr; size_t ring_cap = 0; int ring_ld = 0;
     int route_kernel = 0;               // 0 auto (window unless recording), 1 dataflow, 2 window
 };
 
@@ -126,7 +125,7 @@ int ensure_device(txh_net* net)
         if (!strcmp(k, "dataflow")) net->route_kernel = 1;
         else if (!strcmp(k, "window")) net->route_kernel = 2;
     }
-    CU(cudaMalloc((void**)&net->d_coef, sizeof(double) * (5 * net->topo.n + net->sched.link_last.size() + 1)));
+    CU(cudaMalloc((void**)&net->d_coef, sizeof(double) * (6 * net->topo.n + net->sched.link_last.size() + 1)));
     CU(cudaMalloc((void**)&net->d_qtmp, sizeof(double) * net->topo.n));
     CU(cudaMalloc((void**)&net->d_qctl, 64));
     net->d_status = reinterpret_cast<int32_t*>(net->d_qctl + 4);
@@ -293,34 +292,34 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     WinArgs a{};
     auto up16 = [](int x) { return (x + 15) & ~15; };
     const int rc = std::max(1, s.w_max_len), slots = std::max(1, s.slots_used);
-    a.off_O = rc * 512;
-    a.off_scr = 2 * rc * 512;
+    a.off_scr = rc * 512;
     a.off_in = a.off_scr + slots * 512;
-    a.off_coef = a.off_in + 8 * 512;
+    a.off_coef = a.off_in + std::max(4, 8 - slots) * 512;     // segments stream through [scratch | ring]: >= 8 rows
     a.off_cum = a.off_coef + rc * 32;
-    a.off_f0 = a.off_cum + up16(rc * 8);
+    a.off_cumc = a.off_cum + up16(rc * 8);
+    a.off_f0 = a.off_cumc + up16(rc * 8);
     a.off_f1 = a.off_f0 + up16(rc * 8);
     a.off_hdr = a.off_f1 + up16(rc * 8);
     a.off_words = a.off_hdr + up16(rc * 4);
-    a.off_prod = a.off_words + up16(std::max(1, s.w_max_words) * 4);
-    a.off_list = a.off_prod + up16(std::max(1, s.w_max_prod) * 4);
-    a.smem_per_warp = a.off_list + up16(std::max(1, s.w_max_words) * 4);
+    a.off_list = a.off_words + up16(std::max(1, s.w_max_words) * 4);
+    a.off_steps = a.off_list + up16(std::max(1, s.w_max_words) * 4);
+    a.smem_per_warp = a.off_steps + 16 * 24;                  // StepInterp records of one launch (<= 16 steps)
     const int smem_max = 227 * 1024;
-    int wpc = std::min(8, smem_max / a.smem_per_warp);
-    if (wpc < 2) return 1;
+    int wpc = std::min(16, (smem_max - 1024) / a.smem_per_warp);
+    if (wpc < 2 || s.w_n_own > 0) return 1;
     // ring[step][slot][ld]: one launch covers at most 16 steps (and at most ~1 GiB of ring)
     const size_t slot_row = (size_t)std::max(1, s.n_wslots) * ld;
     int64_t spl = std::min<int64_t>(16, nsteps);
     while (spl > 1 && slot_row * spl * sizeof(double) > (size_t(1) << 30)) --spl;
-    if (slot_row * spl > net->ring_cap) {
-        if (net->d_ring) CU(cudaFree(net->d_ring));
-        CU(cudaMalloc((void**)&net->d_ring, slot_row * spl * sizeof(double)));
-        net->ring_cap = slot_row * spl;
-    }
-    if (pairs > net->prog_cap) {
-        if (net->d_prog) CU(cudaFree(net->d_prog));
-        CU(cudaMalloc((void**)&net->d_prog, pairs * sizeof(int32_t)));
-        net->prog_cap = pairs;
+    if (slot_row * spl > net->ring_cap || ld != net->ring_ld) {
+        // every cell starts EMPTY (all bits set); consumers put EMPTY back, so a finished launch leaves it clean
+        if (slot_row * spl > net->ring_cap) {
+            if (net->d_ring) CU(cudaFree(net->d_ring));
+            CU(cudaMalloc((void**)&net->d_ring, slot_row * spl * sizeof(double)));
+            net->ring_cap = slot_row * spl;
+        }
+        CU(cudaMemsetAsync(net->d_ring, 0xff, net->ring_cap * sizeof(double), st));
+        net->ring_ld = ld;
     }
     const StepInterp* d_steps = net->d_unit_step;
     if (plan.times) {
@@ -336,14 +335,37 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
         InitArgs ia{};
         ia.times = plan.times; ia.steps_out = net->d_steps; ia.t0_ns = plan.t0_ns; ia.dt_ns = plan.dt_ns;
         ia.step_base = s0; ia.R = (int32_t)plan.R; ia.nsteps = (int32_t)ns; ia.method = plan.method;
-        CU(launch_window_init(ia, net->d_prog, (long long)pairs, net->d_qctl + 3, st));
+        CU(launch_window_init(ia, net->d_qctl + 3, st));
         a.tasks = net->d_wtasks; a.hdr = net->d_whdr; a.inw = net->d_winw; a.prod = net->d_wprod;
         a.coef = net->d_coef; a.cumA = net->d_coef + 4 * net->topo.n;
-        a.O = O; a.I = I; a.ring = net->d_ring; a.prog = net->d_prog; a.ticket = net->d_qctl + 3;
+        a.cumC = net->d_coef + 5 * net->topo.n + s.link_last.size();
+        a.O = O; a.I = I; a.ring = net->d_ring; a.ticket = net->d_qctl + 3;
         a.F = F; a.steps = d_steps; a.Wmul = W; a.status = net->d_status; a.watchdog_ns = net->watchdog_ns;
         a.n = net->topo.n; a.n_tasks = (int32_t)s.wtasks.size(); a.n_mblocks = nmb; a.nsteps = (int32_t)ns;
         a.n_slots = std::max(1, s.n_wslots); a.ld = ld; a.M = (int32_t)M; a.wm_ld = wm_ld;
+        a.trace = nullptr;
+        const char* trace_file = getenv("TXH_TRACE_FILE");
+        unsigned long long* d_trace = nullptr;
+        const size_t trace_words = pairs * (size_t)(4 + ns);
+        if (trace_file && *trace_file) {
+            CU(cudaMalloc((void**)&d_trace, trace_words * sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(d_trace, 0, trace_words * sizeof(unsigned long long), st));
+            a.trace = d_trace;
+        }
         CU(launch_route_window(a, wpc, net->num_sms, st));
+        if (d_trace) {
+            // development aid: dump the per-task timeline of this launch (synchronous)
+            std::vector<unsigned long long> h(trace_words);
+            CU(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            CU(cudaFree(d_trace));
+            if (FILE* fp = fopen(trace_file, "wb")) {
+                const long long hd[4] = {(long long)pairs, (long long)ns, (long long)s.wtasks.size(), -(long long)nmb};
+                fwrite(hd, sizeof(hd), 1, fp);
+                fwrite(h.data(), sizeof(unsigned long long), h.size(), fp);
+                fclose(fp);
+            }
+        }
     }
     return TXH_OK;
 }
@@ -407,7 +429,6 @@ void txh_destroy(txh_net* net)
         if (net->d_gauge_of_pos) cudaFree(net->d_gauge_of_pos);
         cudaFree(net->d_wtasks); cudaFree(net->d_whdr); cudaFree(net->d_winw); cudaFree(net->d_wprod);
         if (net->d_ring) cudaFree(net->d_ring);
-        if (net->d_prog) cudaFree(net->d_prog);
         if (net->h_status) cudaFreeHost(net->h_status);
     }
     delete net;
@@ -500,7 +521,7 @@ int txh_set_coeffs(txh_net* net, const double* al, const double* be, const doubl
     if (!net || !al || !be || !ch || !ga) return fail(TXH_E_INVALID, "null argument");
     const int64_t n = net->topo.n;
     const Schedule& sc = net->sched;
-    net->coef_host.resize(5 * n + sc.link_last.size());
+    net->coef_host.resize(6 * n + sc.link_last.size());
     double* cum = net->coef_host.data() + 4 * n;
     for (int64_t k = 0; k < n; ++k) {
         const int32_t j = sc.reach_of_pos[k];
@@ -510,6 +531,13 @@ int txh_set_coeffs(txh_net* net, const double* al, const double* be, const doubl
         cum[k] = (k > 0 && (sc.hdr[k] & HDR_ACC)) ? cum[k - 1] * al[j] : al[j];
     }
     for (size_t e = 0; e < sc.link_last.size(); ++e) net->coef_host[5 * n + e] = cum[sc.link_last[e]];
+    // window kernel: p_k' = P0_k + C_k o_in along a segment, C_k = beta_k A_{k-1} + chi_k A_k, A_{-1} = 1
+    double* cumc = net->coef_host.data() + 5 * n + sc.link_last.size();
+    for (int64_t k = 0; k < n; ++k) {
+        const int32_t j = sc.reach_of_pos[k];
+        const double aprev = (k > 0 && (sc.hdr[k] & HDR_ACC)) ? cum[k - 1] : 1.0;
+        cumc[k] = be[j] * aprev + ch[j] * cum[k];
+    }
     net->have_coef = true; net->coef_dirty = true;
     return TXH_OK;
 }

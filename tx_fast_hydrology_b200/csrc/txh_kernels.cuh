@@ -72,11 +72,11 @@ struct WinArgs {
     const uint32_t* inw;
     const int32_t* prod;
     const double* coef;                   // [n][4]
-    const double* cumA;                   // [n]
+    const double* cumA;                   // [n] prefix product of alpha along the segment
+    const double* cumC;                   // [n] beta_k A_{k-1} + chi_k A_k (see route_window_kernel)
     double* O;
     double* I;
-    double* ring;                         // [nsteps][n_slots][ld] rows handed between tasks
-    int32_t* prog;                        // [n_tasks * n_mblocks] steps published by each (task, member block)
+    double* ring;                         // [nsteps][n_slots][ld] rows handed between tasks; EMPTY (all bits set) when idle
     unsigned long long* ticket;
     const double* F;                      // [R][n] schedule order, or nullptr
     const StepInterp* steps;              // [nsteps]
@@ -85,8 +85,10 @@ struct WinArgs {
     unsigned long long watchdog_ns;
     int64_t n;
     int32_t n_tasks, n_mblocks, nsteps, n_slots, ld, M, wm_ld;
-    // per-warp shared memory (bytes): [I rows][O rows][scratch slots][input ring][coef][cumA][f0][f1][hdr][words][producers][slot list]
-    int32_t smem_per_warp, off_O, off_scr, off_in, off_coef, off_cum, off_f0, off_f1, off_hdr, off_words, off_prod, off_list;
+    // per-warp shared memory (bytes): [p rows][scratch slots][input ring][coef][cumA][cumC][f0][f1][hdr][words][producers][slot list][steps]
+    int32_t smem_per_warp, off_scr, off_in, off_coef, off_cum, off_cumc, off_f0, off_f1, off_hdr, off_words, off_list,
+        off_steps;
+    unsigned long long* trace;            // optional [pairs][4 + nsteps] timeline (claim, loaded, end, kind|smid, publish per step)
 };
 
 struct LevelArgs {
@@ -104,8 +106,7 @@ struct LevelArgs {
 cudaError_t launch_dataflow_init(const InitArgs& a, cudaStream_t st);
 cudaError_t launch_route_dataflow(const RouteArgs& a, int num_sms, cudaStream_t st);
 cudaError_t launch_route_level(const LevelArgs& a, cudaStream_t st);
-cudaError_t launch_window_init(const InitArgs& a, int32_t* prog, long long n_prog, unsigned long long* ticket,
-                               cudaStream_t st);
+cudaError_t launch_window_init(const InitArgs& a, unsigned long long* ticket, cudaStream_t st);
 cudaError_t launch_route_window(const WinArgs& a, int warps_per_cta, int num_sms, cudaStream_t st);
 cudaError_t launch_init_inflows(const int32_t* up_off, const int32_t* up_pos, const uint8_t* is_outlet,
                                 const double* O, double* I, int64_t n, int ld, int M, cudaStream_t st);

@@ -554,10 +554,12 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
                     W.words.push_back(WIN_SLOT | (uint32_t)slot_for(c));
                     W.prod.push_back(grp_of[c]);
                 }
-                W.out_slot = slot_for(rows[g_begin[g] + g_len[g] - 1]);
             }
             sort_unique(W.prod);
         }
+        // a segment publishes its outflow only when some task reads it (every slot has exactly one reader)
+        for (int32_t g = 0; g < ng; ++g)
+            if (wu[g].kind == WTASK_SEG) wu[g].out_slot = slot_of_reach[rows[g_begin[g] + g_len[g] - 1]];
         // publishing rows: pocket rows with a slot get HDR_PUSH (+ the slot word after their inputs)
         for (int32_t g = 0; g < ng; ++g) {
             if (wu[g].kind != WTASK_POCKET) continue;
@@ -613,7 +615,7 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
         for (int32_t k = 0; k < ng; ++k) wrank[worder[k]] = k;
         wtasks.assign(ng, WTaskDesc{});
         whdr.assign(n, 0); winw.clear(); wprod.clear();
-        w_max_len = w_max_words = w_max_prod = w_cp_tasks = 0;
+        w_max_len = w_max_words = w_max_prod = w_cp_tasks = w_n_own = 0;
         for (int32_t k = 0; k < ng; ++k) {
             const int32_t g = worder[k];
             const WU& W = wu[g];
@@ -628,6 +630,12 @@ bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
                     wprod.push_back(wrank[pr]);
                 }
             td.out_slot = W.out_slot; td.n_in = W.n_in;
+            td.n_out = W.kind == WTASK_SEG ? 1 : 0;
+            td.n_own = 0;
+            for (uint32_t x : W.words) if (!(x & WIN_SLOT) && (x & WIN_OWN)) td.n_own += 1;
+            w_n_own += td.n_own;
+            if (W.kind == WTASK_POCKET)
+                for (int32_t e = 0; e < g_len[g]; ++e) if (ghdr[g_begin[g] + e] & HDR_PUSH) td.n_out += 1;
             for (int32_t e = 0; e < g_len[g]; ++e) {
                 if (pos_of_reach[rows[g_begin[g] + e]] != td.begin + e) { err = "internal: group rows not contiguous"; return false; }
                 whdr[td.begin + e] = ghdr[g_begin[g] + e];

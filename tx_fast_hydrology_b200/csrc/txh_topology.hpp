@@ -110,7 +110,9 @@ struct WTaskDesc {
                              // n_in owners of the entering slots (same order), then the distinct other producers
     int32_t out_slot;        // WSEG: slot of the segment's outflow; -1 otherwise
     int32_t n_in;            // WSEG: number of entering slots at the head of the stream
-    int32_t pad_[3];
+    int32_t n_out;           // rows this task publishes per step (0: nobody waits for it)
+    int32_t n_own;           // input words that read a row of the task itself (scratch-slot fallback)
+    int32_t pad_;
 };
 
 struct Schedule {
@@ -136,7 +138,7 @@ struct Schedule {
     std::vector<WTaskDesc> wtasks;          // in a topological, critical-path-first order
     std::vector<uint32_t> whdr, winw;       // per-position headers / input streams of the window tasks
     std::vector<int32_t> wprod;
-    int32_t n_wslots = 0, w_max_len = 0, w_max_words = 0, w_max_prod = 0, w_cp_tasks = 0;
+    int32_t n_wslots = 0, w_max_len = 0, w_max_words = 0, w_max_prod = 0, w_cp_tasks = 0, w_n_own = 0;
     int32_t cp_tasks = 0;                   // tasks on the longest same-step dependent chain
     int64_t cp_cost = 0;
 

@@ -76,6 +76,10 @@ __device__ __forceinline__ double lds_f64(unsigned sa)
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sa));
     return v;
 }
+__device__ __forceinline__ void sts_f64(unsigned sa, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(sa), "d"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u32(unsigned sa)
 {
     uint32_t v;
@@ -87,33 +91,94 @@ __device__ __forceinline__ void sts_u32(unsigned sa, uint32_t v)
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
 }
 
-constexpr int kInRing = 8;                 // rows of other tasks in flight per warp (cp.async ring)
+constexpr int kInRing = 4;                 // pockets: rows of other tasks in flight per warp (cp.async ring)
+constexpr int kSegRing = 8;                // segments: the ring also takes the (unused) scratch slots
+constexpr int kWinThreads = 512;           // one CTA per SM, up to 16 warps
 constexpr uint32_t kIdMask = 0x3fffffffu;
 
-// Waits until every listed producer has published at least `need` steps; returns the smallest progress seen
-// (>= need), or -1 when the launch is being abandoned (watchdog / poisoned handle).
-__device__ __forceinline__ int wait_producers(const WinArgs& a, unsigned list_sa, int cnt, int mb, int need, int lane)
+// Hand-over protocol: a ring cell that has not been written holds the EMPTY pattern (all bits set -- a NaN no
+// arithmetic produces).  The producer just stores its row; the consumer polls the 16 bytes of its own two
+// member columns until neither is EMPTY, and puts EMPTY back (every cell has exactly one reader), so the
+// ring is clean again when the launch ends.  No flags, no fences: a lane only ever depends on the cell the
+// same lane of the producer wrote.
+__device__ __forceinline__ bool cell_full(double2 v)
 {
+    return __double_as_longlong(v.x) != -1ll && __double_as_longlong(v.y) != -1ll;
+}
+__device__ __forceinline__ double2 ld_cell_relaxed(const double* p)
+{
+    double2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 empty_cell()
+{
+    return make_double2(__longlong_as_double(-1ll), __longlong_as_double(-1ll));
+}
+
+// Polls `cell` (this lane's 16 bytes of a ring row) until it is full; `v` is what an earlier read saw.
+// Returns false when the launch is being abandoned (watchdog / poisoned handle).
+__device__ __forceinline__ bool wait_cell(const WinArgs& a, const double* cell, bool active, double2& v, int lane)
+{
+    bool ok = !active || cell_full(v);
+    if (__all_sync(0xffffffffu, ok)) return true;
     unsigned spins = 0, nap = 32;
     unsigned long long t0 = 0;
     for (;;) {
-        int mn = 0x7fffffff;
-        for (int i = lane; i < cnt; i += 32) {
-            const int p = (int)lds_u32(list_sa + 4u * i);
-            mn = min(mn, ld_relaxed_s32(a.prog + (size_t)p * a.n_mblocks + mb));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        if (mn >= need) { fence_acq_rel(); return mn; }          // acquire: the producers' rows are visible
+        if (!ok) { v = ld_cell_relaxed(cell); ok = cell_full(v); }
+        if (__all_sync(0xffffffffu, ok)) return true;
         if ((++spins & 15u) == 0) {
-            if (ld_relaxed_s32(a.status) != 0) return -1;
+            if (ld_relaxed_s32(a.status) != 0) return false;
             const unsigned long long now = globaltimer_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > a.watchdog_ns) { if (lane == 0) atomicExch(a.status, 1); return -1; }
+            else if (now - t0 > a.watchdog_ns) { if (lane == 0) atomicExch(a.status, 1); return false; }
         }
         __nanosleep(nap);
         if (nap < 256u) nap <<= 1;
     }
+}
+
+// Rows handed over by other tasks, consumed in a fixed order every step: a continuous stream (step, index)
+// prefetched D rows ahead through a shared-memory ring, across step boundaries.  One cp.async group per row.
+// A prefetch that came too early sees EMPTY and the consumer falls back to polling the cell itself.
+struct InStream {
+    int issued, consumed;      // rows
+    int ps, pi;                // next (step, index) to issue
+    int cs, cidx;              // next (step, index) to consume
+    int slot_i, slot_c;        // ring cells of the next issue / next consume
+};
+
+template <int D>
+__device__ __forceinline__ void stream_fill(InStream& st, const WinArgs& a, unsigned ring_sa, unsigned list_sa, int nL,
+                                            int ccol, bool active, bool one)
+{
+    while (st.issued - st.consumed < D && nL > 0 && st.ps < a.nsteps) {
+        if (active)
+            cp_async16(ring_sa + st.slot_i * 512u,
+                       a.ring + ((size_t)st.ps * a.n_slots + lds_u32(list_sa + 4u * st.pi)) * a.ld + ccol);
+        cp_async_commit();
+        st.slot_i = st.slot_i + 1 == D ? 0 : st.slot_i + 1;
+        ++st.issued;
+        if (++st.pi == nL) { st.pi = 0; ++st.ps; }
+        if (one) break;
+    }
+}
+
+template <int D>
+__device__ __forceinline__ bool stream_next(InStream& st, const WinArgs& a, unsigned ring_sa, unsigned list_sa, int nL,
+                                            int ccol, bool active, int lane, double2& v)
+{
+    if (st.issued - st.consumed >= D) cp_async_wait_group<D - 1>();     // the oldest of D rows in flight
+    else cp_async_wait_all();
+    v = lds_row(ring_sa + st.slot_c * 512u);
+    double* cell = a.ring + ((size_t)st.cs * a.n_slots + lds_u32(list_sa + 4u * st.cidx)) * a.ld + ccol;
+    if (!wait_cell(a, cell, active, v, lane)) return false;
+    if (active) st_row(cell, empty_cell());
+    st.slot_c = st.slot_c + 1 == D ? 0 : st.slot_c + 1;
+    ++st.consumed;
+    if (++st.cidx == nL) { st.cidx = 0; ++st.cs; }
+    stream_fill<D>(st, a, ring_sa, list_sa, nL, ccol, active, true);
+    return true;
 }
 
 struct FCtx {
@@ -121,6 +186,7 @@ struct FCtx {
     double2 wm0, wm1;
 };
 
+// gamma*q of this lane's two members; the staged rows already carry gamma
 template <bool HAS_F, bool HAS_W>
 __device__ __forceinline__ double2 forcing_q(const FCtx& c, unsigned f0, unsigned f1, int r)
 {
@@ -133,18 +199,22 @@ __device__ __forceinline__ double2 forcing_q(const FCtx& c, unsigned f0, unsigne
     return q;
 }
 
+// Shared-memory state of a task: ONE row per reach, p = beta*i + chi*o, the part of the next update that
+// depends on the old state (o' = alpha*inflow + (gamma*q + p)); the outflows and inflows themselves only
+// exist in registers, and are written to global memory in the last step of the launch.
 template <bool HAS_F, bool HAS_W>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kWinThreads, 1)
 route_window_kernel(const WinArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_all[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned sb = (unsigned)__cvta_generic_to_shared(smem_all + (size_t)warp * a.smem_per_warp);
-    const unsigned sI = sb + lane * 16u, sO = sb + a.off_O + lane * 16u;
+    const unsigned sP = sb + lane * 16u;
     const unsigned sScr = sb + a.off_scr + lane * 16u, sIn = sb + a.off_in + lane * 16u;
-    const unsigned sCoef = sb + a.off_coef, sCum = sb + a.off_cum, sF0 = sb + a.off_f0, sF1 = sb + a.off_f1;
-    const unsigned sHdr = sb + a.off_hdr, sWords = sb + a.off_words, sProd = sb + a.off_prod, sList = sb + a.off_list;
+    const unsigned sCoef = sb + a.off_coef, sCum = sb + a.off_cum, sCumC = sb + a.off_cumc, sF0 = sb + a.off_f0, sF1 = sb + a.off_f1;
+    const unsigned sHdr = sb + a.off_hdr, sWords = sb + a.off_words, sList = sb + a.off_list;
+    const unsigned sSteps = sb + a.off_steps;
     const int nmb = a.n_mblocks, ld = a.ld;
     const long long total = (long long)a.n_tasks * nmb;
 
@@ -157,6 +227,8 @@ route_window_kernel(const WinArgs a)
         const int task = (int)(t / nmb);
         const int mb = (int)(t - (long long)task * nmb);
         const WTaskDesc td = a.tasks[task];
+        unsigned long long* tr = a.trace ? a.trace + (size_t)t * (4 + a.nsteps) : nullptr;
+        if (tr && lane == 0) tr[0] = globaltimer_ns();
         const int len = td.len;
         const int col = mb * kMemberBlock + lane * 2;
         const bool active = col < ld;
@@ -164,25 +236,38 @@ route_window_kernel(const WinArgs a)
         double* Og = a.O + (size_t)td.begin * ld + ccol;
         double* Ig = a.I + (size_t)td.begin * ld + ccol;
 
-        // ---- load the task: its rows of I and O, per-row metadata, input stream, producer list ----
-        if (active)
-            for (int r = 0; r < len; ++r) {
-                cp_async16(sI + r * 512u, Ig + (size_t)r * ld);
-                cp_async16(sO + r * 512u, Og + (size_t)r * ld);
-            }
+        // ---- load the task: per-row metadata, input stream, producer list; rows of I and O -> p ----
         {
             const double* gc = a.coef + 4 * (size_t)td.begin;
             for (int i = lane; i < 2 * len; i += 32) cp_async16(sCoef + 16u * i, gc + 2 * i);
             for (int i = lane; i < len; i += 32) {
                 cp_async8(sCum + 8u * i, a.cumA + td.begin + i);
+                cp_async8(sCumC + 8u * i, a.cumC + td.begin + i);
                 cp_async4(sHdr + 4u * i, a.hdr + td.begin + i);
             }
             for (int i = lane; i < td.n_words; i += 32) cp_async4(sWords + 4u * i, a.inw + td.in_off + i);
-            for (int i = lane; i < td.n_prod; i += 32) cp_async4(sProd + 4u * i, a.prod + td.prod_off + i);
+            if (HAS_F)                                             // the launch's interpolation records (24 B each)
+                for (int i = lane; i < 6 * a.nsteps; i += 32) cp_async4(sSteps + 4u * i, reinterpret_cast<const uint32_t*>(a.steps) + i);
         }
         cp_async_commit();
-        cp_async_wait_all();
-        __syncwarp();
+        // rows: the loads of a batch are all in flight before the first is used
+        for (int r0 = 0; r0 < len; r0 += 4) {
+            double2 io[4], oo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (active && r0 + u < len) { io[u] = ld_row(Ig + (size_t)(r0 + u) * ld); oo[u] = ld_row(Og + (size_t)(r0 + u) * ld); }
+                else { io[u] = make_double2(0.0, 0.0); oo[u] = io[u]; }
+            if (r0 == 0) { cp_async_wait_all(); __syncwarp(); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + u < len) {
+                    const double be = lds_f64(sCoef + 32u * (r0 + u) + 8u), ch = lds_f64(sCoef + 32u * (r0 + u) + 16u);
+                    double2 p;
+                    p.x = be * io[u].x + ch * oo[u].x;
+                    p.y = be * io[u].y + ch * oo[u].y;
+                    sts_row(sP + (r0 + u) * 512u, p);
+                }
+        }
         // rows of other tasks consumed through the input ring, in consumption order
         int nL = 0;
         for (int base = 0; base < td.n_words; base += 32) {
@@ -194,88 +279,86 @@ route_window_kernel(const WinArgs a)
             nL += __popc(m);
         }
         __syncwarp();
-        const int n_side_prod = td.n_prod - td.n_in;
-        int have = n_side_prod > 0 ? 0 : 0x7fffffff;            // side producers are known to have published `have` steps
-        int have_in = td.n_in > 0 ? 0 : 0x7fffffff;
         int cur_r0 = -1, cur_r1 = -1;
         bool dead = false;
+        if (tr && lane == 0) tr[1] = globaltimer_ns();
+        // per-step forcing weights of this lane's two members: (w0*mul[r0][m], w1*mul[r1][m]), muskingum.py:528-531
+        auto load_fctx = [&](int s) -> FCtx {
+            FCtx c;
+            c.w0 = c.w1 = 0.0; c.wm0 = c.wm1 = make_double2(0.0, 0.0);
+            if (HAS_F) {
+                const int r0 = (int)lds_u32(sSteps + 24u * s), r1 = (int)lds_u32(sSteps + 24u * s + 4u);
+                c.w0 = lds_f64(sSteps + 24u * s + 8u); c.w1 = lds_f64(sSteps + 24u * s + 16u);
+                if (HAS_W) {
+                    const int c0 = min(col, a.wm_ld - 1), c1 = min(col + 1, a.wm_ld - 1);
+                    const double* m0 = a.Wmul + (size_t)r0 * a.wm_ld;
+                    const double* m1 = a.Wmul + (size_t)r1 * a.wm_ld;
+                    c.wm0 = make_double2(c.w0 * __ldg(m0 + c0), c.w0 * __ldg(m0 + c1));
+                    c.wm1 = make_double2(c.w1 * __ldg(m1 + c0), c.w1 * __ldg(m1 + c1));
+                }
+            }
+            return c;
+        };
+        FCtx fc_next = load_fctx(0);
+        InStream ist;
+        ist.issued = ist.consumed = ist.ps = ist.pi = ist.cs = ist.cidx = ist.slot_i = ist.slot_c = 0;
 
         for (int s = 0; s < a.nsteps && !dead; ++s) {
+            const bool last = s + 1 == a.nsteps;                   // outflows and inflows go to global memory
             double* ringS = a.ring + (size_t)s * a.n_slots * ld + ccol;
-            FCtx fc;
-            fc.w0 = fc.w1 = 0.0; fc.wm0 = fc.wm1 = make_double2(0.0, 0.0);
+            FCtx fc = fc_next;
             if (HAS_F) {
-                const StepInterp si = a.steps[s];
-                if (si.r0 != cur_r0 || si.r1 != cur_r1) {      // a new bracket of the forcing table
-                    const double* F0 = a.F + (size_t)si.r0 * a.n + td.begin;
-                    const double* F1 = a.F + (size_t)si.r1 * a.n + td.begin;
+                const int r0 = (int)lds_u32(sSteps + 24u * s), r1 = (int)lds_u32(sSteps + 24u * s + 4u);
+                if (r0 != cur_r0 || r1 != cur_r1) {              // a new bracket of the forcing table
+                    const double* F0 = a.F + (size_t)r0 * a.n + td.begin;
+                    const double* F1 = a.F + (size_t)r1 * a.n + td.begin;
                     __syncwarp();
-                    for (int i = lane; i < len; i += 32) { cp_async8(sF0 + 8u * i, F0 + i); cp_async8(sF1 + 8u * i, F1 + i); }
-                    cur_r0 = si.r0; cur_r1 = si.r1;
+                    // the rows are stored multiplied by gamma: o' = alpha*inflow + (p + c0*(gamma f0) + c1*(gamma f1))
+                    for (int i = lane; i < len; i += 32) {
+                        const double ga = lds_f64(sCoef + 32u * i + 24u);
+                        sts_f64(sF0 + 8u * i, ga * __ldg(F0 + i));
+                        sts_f64(sF1 + 8u * i, ga * __ldg(F1 + i));
+                    }
+                    __syncwarp();
+                    cur_r0 = r0; cur_r1 = r1;
                 }
-                fc.w0 = si.w0; fc.w1 = si.w1;
-                if (HAS_W) {
-                    // member m sees (w0*mul[r0][m]) * F[r0] + (w1*mul[r1][m]) * F[r1]
-                    const int c0 = min(col, a.wm_ld - 1), c1 = min(col + 1, a.wm_ld - 1);
-                    const double* m0 = a.Wmul + (size_t)si.r0 * a.wm_ld;
-                    const double* m1 = a.Wmul + (size_t)si.r1 * a.wm_ld;
-                    fc.wm0 = make_double2(si.w0 * __ldg(m0 + c0), si.w0 * __ldg(m0 + c1));
-                    fc.wm1 = make_double2(si.w1 * __ldg(m1 + c0), si.w1 * __ldg(m1 + c1));
-                }
+                if (!last) fc_next = load_fctx(s + 1);           // in flight during this step
             }
-            cp_async_commit();
-            if (s >= have) {
-                have = wait_producers(a, sProd + 4u * td.n_in, n_side_prod, mb, s + 1, lane);
-                if (have < 0) { dead = true; break; }
-            }
-            // input ring prologue: the first kInRing rows of this step, one cp.async group per row
-            int li = 0, ci = 0;
-#pragma unroll
-            for (int j = 0; j < kInRing; ++j) {
-                if (li < nL) {
-                    if (active) cp_async16(sIn + (li & (kInRing - 1)) * 512u, ringS + (size_t)lds_u32(sList + 4u * li) * ld);
-                    ++li;
-                }
-                cp_async_commit();
-            }
-            cp_async_wait_group<kInRing>();                       // the forcing rows (older than the ring groups)
-            __syncwarp();
-            auto next_input = [&]() -> double2 {
-                cp_async_wait_group<kInRing - 1>();
-                const double2 v = lds_row(sIn + (ci & (kInRing - 1)) * 512u);
-                ++ci;
-                if (li < nL) {
-                    if (active) cp_async16(sIn + (li & (kInRing - 1)) * 512u, ringS + (size_t)lds_u32(sList + 4u * li) * ld);
-                    ++li;
-                }
-                cp_async_commit();
-                return v;
-            };
+            const bool seg = td.kind == WTASK_SEG;
+            if (seg) stream_fill<kSegRing>(ist, a, sScr, sList, nL, ccol, active, false);
+            else stream_fill<kInRing>(ist, a, sIn, sList, nL, ccol, active, false);
 
             if (td.kind == WTASK_POCKET) {
                 int wi = 0;
                 double2 acc = make_double2(0.0, 0.0);
                 for (int r = 0; r < len; ++r) {
                     const uint32_t h = lds_u32(sHdr + 4u * r);
-                    const double2 io = lds_row(sI + r * 512u), oo = lds_row(sO + r * 512u);
+                    const double2 p = lds_row(sP + r * 512u);
                     const double al = lds_f64(sCoef + 32u * r), be = lds_f64(sCoef + 32u * r + 8u);
-                    const double ch = lds_f64(sCoef + 32u * r + 16u), ga = lds_f64(sCoef + 32u * r + 24u);
+                    const double ch = lds_f64(sCoef + 32u * r + 16u);
                     double2 inflow = (h & HDR_ACC) ? acc : make_double2(0.0, 0.0);
                     const int nin = (int)((h >> 6) & 0x1ffffffu);
                     for (int k = 0; k < nin; ++k) {
                         const uint32_t w = lds_u32(sWords + 4u * wi++);
                         double2 v;
-                        if (w & WIN_SLOT) v = next_input();
-                        else if (w & WIN_OWN) v = lds_row(sO + (w & kIdMask) * 512u);
+                        if (w & WIN_SLOT) { if (!stream_next<kInRing>(ist, a, sIn, sList, nL, ccol, active, lane, v)) { dead = true; break; } }
                         else v = lds_row(sScr + w * 512u);
                         inflow.x += v.x; inflow.y += v.y;
                     }
+                    if (dead) break;
                     const double2 q = forcing_q<HAS_F, HAS_W>(fc, sF0, sF1, r);
                     double2 on;
-                    on.x = al * inflow.x + (be * io.x + ch * oo.x + ga * q.x);
-                    on.y = al * inflow.y + (be * io.y + ch * oo.y + ga * q.y);
-                    sts_row(sI + r * 512u, inflow);
-                    sts_row(sO + r * 512u, on);
+                    on.x = al * inflow.x + (p.x + q.x);
+                    on.y = al * inflow.y + (p.y + q.y);
+                    if (!last) {
+                        double2 pn;
+                        pn.x = be * inflow.x + ch * on.x;
+                        pn.y = be * inflow.y + ch * on.y;
+                        sts_row(sP + r * 512u, pn);
+                    } else if (active) {
+                        st_row(Ig + (size_t)r * ld, inflow);
+                        st_row(Og + (size_t)r * ld, on);
+                    }
                     if (h & HDR_PUSH) {                              // read by another task: publish
                         const uint32_t slot = lds_u32(sWords + 4u * wi++);
                         if (active) st_row(ringS + (size_t)slot * ld, on);
@@ -284,86 +367,105 @@ route_window_kernel(const WinArgs a)
                     if (sl) sts_row(sScr + (sl - 1) * 512u, on);
                     acc = on;
                 }
-                __syncwarp();
-                if (lane == 0) st_release_s32(a.prog + t, s + 1);
+                if (tr && lane == 0) tr[4 + s] = globaltimer_ns();
             } else {
-                // PRE: side_k = pocket roots joining reach k; r_k from the old state; B_k = the recurrence with
-                // nothing entering the segment.  (side_k, B_k) replace (i_k, o_k) in shared memory.
+                // PRE: side_k = pocket roots joining reach k; B_k = the recurrence with nothing entering the
+                // segment; what the NEXT step needs of this one is affine in the flow o_in entering the segment:
+                //   p_k' = beta_k i_k + chi_k o_k = P0_k + C_k o_in,   P0_k = beta_k (side_k + B_{k-1}) + chi_k B_k,
+                //   C_k = beta_k A_{k-1} + chi_k A_k  (A = prefix product of alpha, A_{-1} = 1; precomputed).
+                // In the last step (side_k, B_k) are parked in the global I / O rows for the final fix-up.
                 double2 B = make_double2(0.0, 0.0);
                 for (int r = 0; r < len; ++r) {
                     const uint32_t h = lds_u32(sHdr + 4u * r);
-                    const double2 io = lds_row(sI + r * 512u), oo = lds_row(sO + r * 512u);
+                    const double2 p = lds_row(sP + r * 512u);
                     const double al = lds_f64(sCoef + 32u * r), be = lds_f64(sCoef + 32u * r + 8u);
-                    const double ch = lds_f64(sCoef + 32u * r + 16u), ga = lds_f64(sCoef + 32u * r + 24u);
+                    const double ch = lds_f64(sCoef + 32u * r + 16u);
                     const int nin = (int)((h >> 6) & 0x1fffu);
                     double2 side = make_double2(0.0, 0.0);
-                    for (int k = 0; k < nin; ++k) { const double2 v = next_input(); side.x += v.x; side.y += v.y; }
+                    for (int k = 0; k < nin; ++k) {
+                        double2 v;
+                        if (!stream_next<kSegRing>(ist, a, sScr, sList, nL, ccol, active, lane, v)) { dead = true; break; }
+                        side.x += v.x; side.y += v.y;
+                    }
+                    if (dead) break;
                     const double2 q = forcing_q<HAS_F, HAS_W>(fc, sF0, sF1, r);
-                    double2 inflow = side;
+                    double2 inflow = side;                           // side_k + B_{k-1}
                     if (h & HDR_ACC) { inflow.x += B.x; inflow.y += B.y; }
-                    B.x = al * inflow.x + (be * io.x + ch * oo.x + ga * q.x);
-                    B.y = al * inflow.y + (be * io.y + ch * oo.y + ga * q.y);
-                    sts_row(sI + r * 512u, side);
-                    sts_row(sO + r * 512u, B);
+                    B.x = al * inflow.x + (p.x + q.x);
+                    B.y = al * inflow.y + (p.y + q.y);
+                    if (!last) {
+                        double2 p0;
+                        p0.x = be * inflow.x + ch * B.x;
+                        p0.y = be * inflow.y + ch * B.y;
+                        sts_row(sP + r * 512u, p0);
+                    } else if (active) {
+                        st_row(Ig + (size_t)r * ld, side);
+                        st_row(Og + (size_t)r * ld, B);
+                    }
                 }
                 // hop: out = A_last * o_in + B_last, o_in = the rows entering the segment
+                if (dead) break;
                 double2 oin = make_double2(0.0, 0.0);
-                if (td.n_in > 0) {
-                    if (s >= have_in) {
-                        have_in = wait_producers(a, sProd, td.n_in, mb, s + 1, lane);
-                        if (have_in < 0) { dead = true; break; }
-                    }
-                    for (int k = 0; k < td.n_in; ++k) {
-                        const double2 v = active ? ld_row(ringS + (size_t)(lds_u32(sWords + 4u * k) & kIdMask) * ld)
-                                                 : make_double2(0.0, 0.0);
-                        oin.x += v.x; oin.y += v.y;
-                    }
+                for (int k = 0; k < td.n_in; ++k) {
+                    double* cell = ringS + (size_t)(lds_u32(sWords + 4u * k) & kIdMask) * ld;
+                    double2 v = active ? ld_cell_relaxed(cell) : make_double2(0.0, 0.0);
+                    if (!wait_cell(a, cell, active, v, lane)) { dead = true; break; }
+                    if (active) st_row(cell, empty_cell());
+                    oin.x += v.x; oin.y += v.y;
                 }
+                if (dead) break;
                 const double Al = lds_f64(sCum + 8u * (len - 1));
                 double2 out;
                 out.x = Al * oin.x + B.x;
                 out.y = Al * oin.y + B.y;
-                if (active) st_row(ringS + (size_t)td.out_slot * ld, out);
-                __syncwarp();
-                if (lane == 0) st_release_s32(a.prog + t, s + 1);
-                // FIX: o_k = B_k + A_k o_in, i_k = o_{k-1} + side_k
-                double2 op = oin;
-                for (int r = 0; r < len; ++r) {
-                    const double2 side = lds_row(sI + r * 512u), Bk = lds_row(sO + r * 512u);
-                    double2 on = out;
-                    if (r + 1 < len) {
-                        const double A = lds_f64(sCum + 8u * r);
-                        on.x = A * oin.x + Bk.x;
-                        on.y = A * oin.y + Bk.y;
+                if (active && td.out_slot >= 0) st_row(ringS + (size_t)td.out_slot * ld, out);
+                if (tr && lane == 0) tr[4 + s] = globaltimer_ns();
+                if (!last) {
+                    // FIX, folded: p_k' = P0_k + C_k o_in
+                    for (int r = 0; r < len; ++r) {
+                        const double C = lds_f64(sCumC + 8u * r);
+                        double2 p0 = lds_row(sP + r * 512u);
+                        p0.x = C * oin.x + p0.x;
+                        p0.y = C * oin.y + p0.y;
+                        sts_row(sP + r * 512u, p0);
                     }
-                    double2 it;
-                    it.x = op.x + side.x;
-                    it.y = op.y + side.y;
-                    sts_row(sO + r * 512u, on);
-                    sts_row(sI + r * 512u, it);
-                    op = on;
+                } else if (active) {
+                    // final FIX: o_k = B_k + A_k o_in, i_k = o_{k-1} + side_k (each lane re-reads its own cells)
+                    double2 op = oin;
+                    for (int r = 0; r < len; ++r) {
+                        const double2 side = ld_row(Ig + (size_t)r * ld), Bk = ld_row(Og + (size_t)r * ld);
+                        double2 on = out;
+                        if (r + 1 < len) {
+                            const double A = lds_f64(sCum + 8u * r);
+                            on.x = A * oin.x + Bk.x;
+                            on.y = A * oin.y + Bk.y;
+                        }
+                        double2 it;
+                        it.x = op.x + side.x;
+                        it.y = op.y + side.y;
+                        st_row(Og + (size_t)r * ld, on);
+                        st_row(Ig + (size_t)r * ld, it);
+                        op = on;
+                    }
                 }
             }
-            cp_async_wait_all();
         }
         cp_async_wait_all();
-        // ---- write the task's rows back ----
-        if (active && !dead)
-            for (int r = 0; r < len; ++r) {
-                st_row(Ig + (size_t)r * ld, lds_row(sI + r * 512u));
-                st_row(Og + (size_t)r * ld, lds_row(sO + r * 512u));
-            }
+        if (tr && lane == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            tr[2] = globaltimer_ns();
+            tr[3] = ((unsigned long long)smid << 8) | (unsigned)td.kind;
+        }
         __syncwarp();
     }
 }
 
-// ticket, progress words and the forcing interpolation of the launch's steps (see dataflow_init_kernel)
-__global__ void __launch_bounds__(256) window_init_kernel(const InitArgs a, int32_t* prog, long long n_prog,
-                                                          unsigned long long* ticket)
+// ticket and the forcing interpolation of the launch's steps (see dataflow_init_kernel)
+__global__ void __launch_bounds__(256) window_init_kernel(const InitArgs a, unsigned long long* ticket)
 {
     const long long gid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long g = gid0; g < n_prog; g += stride) prog[g] = 0;
     if (gid0 == 0) *ticket = 0ull;
     if (a.times) {
         for (long long s = gid0; s < a.nsteps; s += stride) {
@@ -393,13 +495,9 @@ __global__ void __launch_bounds__(256) window_init_kernel(const InitArgs a, int3
 
 }  // namespace
 
-cudaError_t launch_window_init(const InitArgs& a, int32_t* prog, long long n_prog, unsigned long long* ticket,
-                               cudaStream_t st)
+cudaError_t launch_window_init(const InitArgs& a, unsigned long long* ticket, cudaStream_t st)
 {
-    long long blocks = (n_prog + 255) / 256;
-    if (blocks < 1) blocks = 1;
-    if (blocks > 1184) blocks = 1184;
-    window_init_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, prog, n_prog, ticket);
+    window_init_kernel<<<1, 256, 0, st>>>(a, ticket);
     count_launch();
     return cudaGetLastError();
 }
@@ -417,6 +515,7 @@ cudaError_t launch_route_window(const WinArgs& a, int warps_per_cta, int num_sms
     const long long pairs = (long long)a.n_tasks * a.n_mblocks;
     long long want = (pairs + warps_per_cta - 1) / warps_per_cta;
     const unsigned grid = (unsigned)(want < num_sms ? (want < 1 ? 1 : want) : num_sms);   // one resident CTA per SM
+    (void)want;
     kern<<<grid, warps_per_cta * 32, smem, st>>>(a);
     count_launch();
     return cudaGetLastError();
