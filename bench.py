@@ -14,7 +14,7 @@ One bench "step" is one whole 7-day run.  The metric is reach*timestep*member up
   e2e   : the same run through the public Python API from PINNED HOST buffers: initial ensemble,
           forcing table, member multipliers and observations copied host->device and the final
           ensemble copied device->host inside the timed region
-  roofline : route_dataflow_kernel (the persistent routing kernel, one launch per hourly window),
+  roofline : route_window_kernel (the window-resident routing kernel, one launch per hourly window),
           algorithmic bytes per launch / its mean CUDA-event duration / measured HBM copy bandwidth
   cpu_baseline : the CPU oracle (C/OpenMP restatement of the reference kernels, members over host
           threads + numpy EnKF) on a bounded sample of the same workload, rank 0 at N=1 only
@@ -330,14 +330,28 @@ def gpu_arm(a):
         mdl._datetime = t_start
         mdl.run_assimilating(forcing, nsteps, enkf, every, Zp_dev, timers=timers)
 
+    e2e_parts = {}
+
     def e2e_run():
+        def lap(key, t0):
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            e2e_parts[key] = e2e_parts.get(key, 0.0) + (t1 - t0)
+            return t1
+        t = time.perf_counter()
         mdl.upload_state(o0_pin)                                                     # H2D
+        t = lap("upload_state_ms", t)
         f = mdl.make_forcing(times_ns=wl.times, table=table_pin, member_mul=mul_pin)  # H2D
+        t = lap("forcing_ms", t)
         Zp_dev.copy_(Zp_pin, non_blocking=True)                                      # H2D
+        t = lap("observations_ms", t)
         mdl._datetime = t_start
         mdl.run_assimilating(f, nsteps, enkf, every, Zp_dev)
+        t = lap("run_ms", t)
         mdl.download_state(out_o=out_pin)                                            # D2H (synchronises)
+        t = lap("download_ms", t)
         f.close()
+        lap("free_ms", t)
 
     h2d = o0_pin.numel() * 8 + table_pin.numel() * 8 + mul_pin.numel() * 8 + Zp_pin.numel() * 8
     d2h = out_pin.numel() * 8
@@ -397,10 +411,10 @@ def gpu_arm(a):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as ft:
-            traffic = json.load(ft).get("route_dataflow_kernel_dram_bytes_per_launch")
+            traffic = json.load(ft).get("route_window_kernel_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "route_dataflow_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "route_window_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": k_ms,
                 "launches_timed": len(timers), "bytes_per_update": ab,
@@ -410,6 +424,7 @@ def gpu_arm(a):
     e2e = None
     if not a.no_e2e:
         e2e_run()                                         # warm-up (allocations)
+        e2e_parts.clear()
         barrier()
         t0 = time.perf_counter()
         reps = max(1, min(a.steps, 3))
@@ -418,7 +433,8 @@ def gpu_arm(a):
         barrier()
         s_e2e = max_over_ranks((time.perf_counter() - t0) / reps)
         e2e = {"value": wl.updates_per_run() / s_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * s_e2e, "runs": reps}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * s_e2e, "runs": reps,
+               "breakdown_ms": {k: round(1e3 * v / reps, 3) for k, v in e2e_parts.items()}}
 
     # ---- CPU baseline (rank 0, single GPU only) -------------------------------------------------------
     cpu = None

@@ -136,8 +136,12 @@ void sort_unique(std::vector<int32_t>& v)
 
 }  // namespace
 
-bool Schedule::build(const Topology& t, const SchedParams& p, std::string& err)
+bool Schedule::build(const Topology& t, const SchedParams& p_in, std::string& err)
 {
+    SchedParams p = p_in;
+    // Short segments keep the per-step work of a segment (serial in one warp) small; long networks need
+    // longer ones so that the hop chain along the main stem stays short: about 128 hops along the deepest path.
+    if (p.spine_cap <= 0) p.spine_cap = std::min(16, std::max(6, t.nlevels / 128));
     prm = p;
     const int64_t n = t.n;
     if (p.spine_cap < 1 || p.spine_cap > 4096 || p.pocket_cap < 1 || p.pocket_cap > 4096 ||

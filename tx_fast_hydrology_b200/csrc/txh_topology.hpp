@@ -38,11 +38,11 @@ struct Topology {
 };
 
 struct SchedParams {
-    int long_path_min = 32;   // paths at least this long become spines
-    int spine_cap = 16;       // reaches per spine segment (a PRE and a FIX task each; one window task)
-    int pocket_cap = 20;      // reaches per pocket task (bundled side subtrees)
+    int long_path_min = 64;   // paths at least this long become spines
+    int spine_cap = 0;        // reaches per spine segment; 0 = chosen from the depth of the network (6..16)
+    int pocket_cap = 16;      // reaches per pocket task (bundled side subtrees)
     int max_slots = 8;        // shared-memory scratch rows per warp
-    int link_cap = 8;         // segments per LINK task (blocks chained along the path)
+    int link_cap = 8;         // segments per LINK task (dataflow kernel: blocks chained along the path)
 };
 
 // Per-reach header word consumed by the routing kernel.
