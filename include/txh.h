@@ -159,6 +159,11 @@ int txh_apply_gain(txh_net* net, const double* G_dev, double* O_dev, double* I_d
 int txh_enkf_stats(txh_net* net, const double* O_dev, int64_t Mloc, const int64_t* obs_reach_host, int64_t m,
                    double scale /* rowsum = scale * sum; 1/Mtot gives the mean of an unsharded ensemble */,
                    double* rowsum_dev /*[n] schedule order*/, double* HX_dev /*[m][Mloc]*/, void* stream);
+/* Every later routing call on the handle also leaves rowsum[pos] = scale * (sum over the members of the final
+ * outflow of the reach at schedule position pos) in rowsum_dev [n] -- the first half of txh_enkf_stats, fused
+ * into the last step of the launch.  NULL switches it off.  txh_enkf_stats with rowsum_dev == NULL then only
+ * gathers the gauge rows. */
+int txh_set_stats_output(txh_net* net, double* rowsum_dev, double scale);
 /* doubles of workspace txh_enkf_solve needs */
 int64_t txh_enkf_work_size(int64_t m, int64_t Mtot);
 /* Dinv (optional): the inverse of D = R + diag(qs), which is constant between updates -- dinv_kind 1: its

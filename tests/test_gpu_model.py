@@ -191,3 +191,51 @@ def test_enkf_update_vs_oracle(oracle, n, M, m, seed, diag):
     O_ref, I_ref, _ = oracle.enkf_update(ref_net, O_f, I_f, gidx, Zp, q, R)
     assert relerr(mdl.o_t_next, O_ref) < RTOL
     assert relerr(mdl.i_t_next, I_ref) < RTOL
+
+
+@pytest.mark.parametrize("n,M,m,seed", [(2000, 64, 50, 7), (1200, 20, 30, 8), (900, 70, 40, 9)])
+def test_run_assimilating_vs_oracle(oracle, n, M, m, seed):
+    """The device-resident loop of the headline benchmark -- `every` routing steps in one window launch, the
+    ensemble row sums riding on its last step, then one EnKF update, repeated -- equals the CPU oracle's
+    routing (nutils.py:64-89 per member) + ensemble update (da.py:112-126) loop."""
+    import torch
+    from tx_fast_hydrology_b200 import synthetic as S
+    from tx_fast_hydrology_b200.muskingum import Muskingum
+    from tx_fast_hydrology_b200.da import EnsembleKalmanFilter
+    every, nwin = 6, 3
+    net_d = S.make_network(n, seed)
+    prm = S.make_params(n, seed, well_posed=True)
+    rng = np.random.default_rng(seed)
+    o0 = prm["o_t"][:, None] * rng.uniform(0.5, 1.5, size=(n, M))
+    d = S.model_dict(net_d, prm, dt_s=300.0)
+    d["o_t"] = o0
+    mdl = Muskingum(d, members=M)
+    t0 = int(mdl.datetime.value)
+    times, table = S.make_forcing(n, every * nwin, 300.0, seed, t0_ns=t0, rows_every=4)
+    mul = S.make_member_multipliers(times.size, M, seed)
+    gidx = S.make_gauges(net_d["endnodes"], m, seed=seed)
+    mt = t0 + (np.arange(nwin, dtype=np.int64) + 1) * int(every * 300e9)
+    meas = rng.uniform(0.5, 8.0, size=(nwin, m))
+    mdf = frame(mt, meas, [d["reach_ids"][j] for j in gidx])
+    R = 1e-2 * np.eye(m)
+    q = rng.uniform(0.5, 2.0, size=n)
+    enkf = EnsembleKalmanFilter(mdl, mdf, q, R)
+    Zp = meas[:, :, None] + 0.1 * rng.standard_normal((nwin, m, M))
+    f = mdl.make_forcing(times_ns=times, table=table, member_mul=mul)
+    mdl.run_assimilating(f, every * nwin, enkf, every, torch.as_tensor(Zp, device="cuda"))
+    mdl.network.check()
+    assert enkf.n_updates == nwin and mdl.datetime.value == t0 + int(every * nwin * 300e9)
+    ind = oracle.compute_indegree(net_d["startnodes"], net_d["endnodes"])
+    al, be, ch, ga = oracle.compute_coeffs(prm["K"], prm["X"], 300.0)
+    onet = {"startnodes": net_d["startnodes"], "endnodes": net_d["endnodes"], "indegree": ind,
+            "alpha": al, "beta": be, "chi": ch, "gamma": ga}
+    o = np.ascontiguousarray(o0.T)
+    i = np.stack([oracle.init_states(net_d["startnodes"], net_d["endnodes"], x) for x in o])
+    t = float(t0)
+    for k in range(nwin):
+        oracle.run_members(onet, o, i, every, times.astype(np.float64), table, t, 300e9, wmul=mul)
+        t += every * 300e9
+        Op, Ip, _ = oracle.enkf_update(onet, o.T, i.T, gidx, Zp[k], q, R)
+        o = np.ascontiguousarray(Op.T); i = np.ascontiguousarray(Ip.T)
+    assert relerr(mdl.o_t_next, o.T) < RTOL
+    assert relerr(mdl.i_t_next, i.T) < RTOL

@@ -58,6 +58,7 @@ SIGNATURES = {
     "txh_route_apply": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "txh_apply_gain": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "txh_enkf_stats": (ctypes.c_int, [c_vp, c_vp, c_i64, p_i64, c_i64, c_f64, c_vp, c_vp, c_vp]),
+    "txh_set_stats_output": (ctypes.c_int, [c_vp, c_vp, c_f64]),
     "txh_enkf_work_size": (c_i64, [c_i64, c_i64]),
     "txh_enkf_solve": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, p_i64, c_vp, c_vp, c_vp, ctypes.c_int,
                                       c_vp, c_vp, c_vp, c_vp]),

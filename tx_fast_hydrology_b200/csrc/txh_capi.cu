@@ -79,6 +79,8 @@ struct txh_net {
     int32_t* d_wprod = nullptr;
     double* d_ring = nullptr; size_t ring_cap = 0; int ring_ld = 0;
     int route_kernel = 0;               // 0 auto (window unless recording), 1 dataflow, 2 window
+    double* stats_rowsum = nullptr;     // txh_set_stats_output: row sums of the final outflows of every routing call
+    double stats_scale = 1.0;
 };
 
 struct txh_forcing {
@@ -343,6 +345,9 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
         a.F = F; a.steps = d_steps; a.Wmul = W; a.status = net->d_status; a.watchdog_ns = net->watchdog_ns;
         a.n = net->topo.n; a.n_tasks = (int32_t)s.wtasks.size(); a.n_mblocks = nmb; a.nsteps = (int32_t)ns;
         a.n_slots = std::max(1, s.n_wslots); a.ld = ld; a.M = (int32_t)M; a.wm_ld = wm_ld;
+        // the row sums ride on the last step of the call when one warp covers all members of a row
+        a.rowsum = (net->stats_rowsum && nmb == 1 && s0 + ns == nsteps) ? net->stats_rowsum : nullptr;
+        a.rowsum_scale = net->stats_scale;
         a.trace = nullptr;
         const char* trace_file = getenv("TXH_TRACE_FILE");
         unsigned long long* d_trace = nullptr;
@@ -375,11 +380,17 @@ int run_routing(txh_net* net, double* O, double* I, int64_t M, const double* F, 
                 const StepPlan& plan, int64_t nsteps, const int32_t* rec_slot, double* rec_out, int rec_every,
                 int rec_count, cudaStream_t st)
 {
+    const int ld = (int)txh_row_stride(M);
     if (net->route_kernel != 1 && !rec_slot) {
         const int rc = run_window(net, O, I, M, F, W, wm_ld, plan, nsteps, st);
+        if (rc == TXH_OK && net->stats_rowsum && ld > kMemberBlock)
+            CU(launch_enkf_stats(O, ld, (int)M, net->topo.n, net->stats_scale, nullptr, net->stats_rowsum, nullptr, st));
         if (rc != 1) return rc;
     }
-    return run_dataflow(net, O, I, M, F, W, wm_ld, plan, nsteps, rec_slot, rec_out, rec_every, rec_count, st);
+    const int rc = run_dataflow(net, O, I, M, F, W, wm_ld, plan, nsteps, rec_slot, rec_out, rec_every, rec_count, st);
+    if (rc == TXH_OK && net->stats_rowsum)
+        CU(launch_enkf_stats(O, ld, (int)M, net->topo.n, net->stats_scale, nullptr, net->stats_rowsum, nullptr, st));
+    return rc;
 }
 
 }  // namespace
@@ -821,17 +832,25 @@ int* info_word(txh_net* net) { return net->d_status + 1; }
 
 extern "C" {
 
+int txh_set_stats_output(txh_net* net, double* rowsum, double scale)
+{
+    if (!net) return fail(TXH_E_INVALID, "null argument");
+    net->stats_rowsum = rowsum; net->stats_scale = scale;
+    return TXH_OK;
+}
+
 int txh_enkf_stats(txh_net* net, const double* O, int64_t Mloc, const int64_t* obs, int64_t m, double scale,
                    double* rowsum, double* HX, void* stream)
 {
-    if (!net || !O || !obs || !rowsum || !HX || m < 1) return fail(TXH_E_INVALID, "bad argument");
+    if (!net || !O || !obs || !HX || m < 1) return fail(TXH_E_INVALID, "bad argument");
     int rc;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = check_M(Mloc)) || (rc = ensure_device(net))) return rc;
     int32_t* d_pos = nullptr;
     if ((rc = obs_positions(net, obs, m, st, &d_pos))) return rc;
     const int ld = (int)txh_row_stride(Mloc);
-    CU(launch_enkf_stats(O, ld, (int)Mloc, net->topo.n, scale, net->d_gauge_of_pos, rowsum, HX, st));
+    if (rowsum) CU(launch_enkf_stats(O, ld, (int)Mloc, net->topo.n, scale, net->d_gauge_of_pos, rowsum, HX, st));
+    else CU(launch_gather_rows(d_pos, m, O, ld, (int)Mloc, HX, st));       // the sums came with the routing launch
     return TXH_OK;
 }
 

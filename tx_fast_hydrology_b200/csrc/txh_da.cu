@@ -122,7 +122,7 @@ enkf_stats_kernel(const double* __restrict__ X, int ld, int M, long long n, doub
     const int lane = threadIdx.x & 31;
     if (row >= n) return;
     const double* p = X + (size_t)row * ld;
-    const int gi = gauge_of_pos[row];
+    const int gi = gauge_of_pos ? gauge_of_pos[row] : -1;
     double s = 0.0;
     for (int m = 2 * lane; m < M; m += 64) {
         const double2 v = *reinterpret_cast<const double2*>(p + m);

@@ -89,6 +89,8 @@ struct WinArgs {
     int32_t smem_per_warp, off_scr, off_in, off_coef, off_cum, off_cumc, off_f0, off_f1, off_hdr, off_words, off_list,
         off_steps;
     unsigned long long* trace;            // optional [pairs][4 + nsteps] timeline (claim, loaded, end, kind|smid, publish per step)
+    double* rowsum;                       // optional [n]: scale * sum over the members of the final outflows (n_mblocks == 1)
+    double rowsum_scale;
 };
 
 struct LevelArgs {

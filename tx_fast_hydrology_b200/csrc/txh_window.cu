@@ -176,6 +176,15 @@ __device__ __forceinline__ bool stream_next(InStream& st, const WinArgs& a, unsi
     return true;
 }
 
+// scale * (sum of this row over the members of the warp's block), lane 0 stores it (last step of a launch)
+__device__ __forceinline__ void emit_rowsum(const WinArgs& a, int pos, int col, double2 on, int lane)
+{
+    double v = (col < a.M ? on.x : 0.0) + (col + 1 < a.M ? on.y : 0.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) a.rowsum[pos] = v * a.rowsum_scale;
+}
+
 struct FCtx {
     double w0, w1;
     double2 wm0, wm1;
@@ -350,9 +359,9 @@ route_window_kernel(const WinArgs a)
                         pn.x = be * inflow.x + ch * on.x;
                         pn.y = be * inflow.y + ch * on.y;
                         sts_row(sP + r * 512u, pn);
-                    } else if (active) {
-                        st_row(Ig + (size_t)r * ld, inflow);
-                        st_row(Og + (size_t)r * ld, on);
+                    } else {
+                        if (active) { st_row(Ig + (size_t)r * ld, inflow); st_row(Og + (size_t)r * ld, on); }
+                        if (a.rowsum) emit_rowsum(a, td.begin + r, col, on, lane);
                     }
                     if (h & HDR_PUSH) {                              // read by another task: publish
                         const uint32_t slot = lds_u32(sWords + 4u * wi++);
@@ -424,11 +433,12 @@ route_window_kernel(const WinArgs a)
                         p0.y = C * oin.y + p0.y;
                         sts_row(sP + r * 512u, p0);
                     }
-                } else if (active) {
+                } else {
                     // final FIX: o_k = B_k + A_k o_in, i_k = o_{k-1} + side_k (each lane re-reads its own cells)
                     double2 op = oin;
                     for (int r = 0; r < len; ++r) {
-                        const double2 side = ld_row(Ig + (size_t)r * ld), Bk = ld_row(Og + (size_t)r * ld);
+                        double2 side = make_double2(0.0, 0.0), Bk = side;
+                        if (active) { side = ld_row(Ig + (size_t)r * ld); Bk = ld_row(Og + (size_t)r * ld); }
                         double2 on = out;
                         if (r + 1 < len) {
                             const double A = lds_f64(sCum + 8u * r);
@@ -438,8 +448,8 @@ route_window_kernel(const WinArgs a)
                         double2 it;
                         it.x = op.x + side.x;
                         it.y = op.y + side.y;
-                        st_row(Og + (size_t)r * ld, on);
-                        st_row(Ig + (size_t)r * ld, it);
+                        if (active) { st_row(Og + (size_t)r * ld, on); st_row(Ig + (size_t)r * ld, it); }
+                        if (a.rowsum) emit_rowsum(a, td.begin + r, col, on, lane);
                         op = on;
                     }
                 }

@@ -264,9 +264,13 @@ class EnsembleKalmanFilter(BaseCallback):
             Zp = Zp + interpolate_sample(x, self._meas_times, flat).reshape(Z.size, self.Mtot)
         return np.ascontiguousarray(Zp)
 
-    def filter(self, Zp_dev=None):
+    def stats_scale(self):
+        return 1.0 / self.Mtot if self.world == 1 else 1.0
+
+    def filter(self, Zp_dev=None, stats_fresh=False):
         """One ensemble update on the device.  `Zp_dev` ([m][Mtot] CUDA tensor) overrides the
-        interpolated observations (used by the fast path that pre-stages them)."""
+        interpolated observations (used by the fast path that pre-stages them).  `stats_fresh`: the row
+        sums of the forecast are already in `self._rowsum` (written by the routing launch)."""
         torch = self._torch
         mdl = self.model
         net = mdl.network
@@ -276,7 +280,8 @@ class EnsembleKalmanFilter(BaseCallback):
             Zp_dev = torch.as_tensor(self.perturbed_observations(mdl.datetime), device='cuda')
         dist = torch.distributed
         # one pass over the state: row sums (already the mean when the ensemble is not sharded) + gauge rows
-        net.enkf_stats(O, M, self.reach_indices, self._rowsum, self._HX, scale=1.0 / Mt if self.world == 1 else 1.0)
+        net.enkf_stats(O, M, self.reach_indices, None if stats_fresh else self._rowsum, self._HX,
+                       scale=self.stats_scale())
         Xall, ldx = None, 0
         mean = self._rowsum
         if self.world > 1:

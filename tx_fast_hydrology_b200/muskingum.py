@@ -396,24 +396,28 @@ class Muskingum:
         CUDA tensor of per-member observations for the k-th update), repeated; nothing returns to
         the host in between.  Mirrors simulate + a KalmanFilter callback gated to every `every`-th
         step (the reference filters every step, da.py:56-61; SURVEY.md section 8c iv).
-        `timers`: optional list that receives a (start, end) CUDA-event pair around every routing launch."""
+        `timers`: optional list that receives a (start, end) CUDA-event pair around every 8th routing launch."""
         torch = self._ensure_device()
         self._sync_coeffs()
         d, net, M = self._dev, self.network, self.members
         step_ns = int(self.timedelta.value)
         t = int(self.datetime.value)
         nwin = nsteps // every
+        # the ensemble row sums ride on the last step of every routing launch
+        net.set_stats_output(enkf._rowsum, enkf.stats_scale())
         for k in range(nwin):
-            if timers is not None:
+            timed = timers is not None and k % 8 == 0      # events cost a few microseconds: sample every 8th launch
+            if timed:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
             net.route_run(d['O'], d['I'], M, forcing, t, step_ns, every)
-            if timers is not None:
+            if timed:
                 e1.record()
                 timers.append((e0, e1))
             t += every * step_ns
             self._datetime = pd.Timestamp(t, tz='UTC')
-            enkf.filter(observations[k])
+            enkf.filter(observations[k], stats_fresh=True)
+        net.set_stats_output(None)
         rest = nsteps - nwin * every
         if rest:
             net.route_run(d['O'], d['I'], M, forcing, t, step_ns, rest)

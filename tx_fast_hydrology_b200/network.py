@@ -263,10 +263,18 @@ class RiverNetwork:
                                          _stream_ptr()))
 
     # ---- assimilation ----------------------------------------------------------------------
+    def set_stats_output(self, rowsum=None, scale=1.0):
+        """Routing calls also leave scale * (member sum of the final outflows) in `rowsum` [n]; None = off."""
+        self._stats_keep = rowsum
+        L.check(self._lib.txh_set_stats_output(self.handle, _cuda_ptr(rowsum) if rowsum is not None else None,
+                                               float(scale)))
+
     def enkf_stats(self, O, Mloc, obs_reach, rowsum, HX, scale=1.0):
+        """`rowsum` None: the sums came with the routing launch (set_stats_output); only gather the gauge rows."""
         idx = L.as_i64(obs_reach)
         L.check(self._lib.txh_enkf_stats(self.handle, _cuda_ptr(O), int(Mloc), L.ptr_i64(idx), idx.size,
-                                         float(scale), _cuda_ptr(rowsum), _cuda_ptr(HX), _stream_ptr()))
+                                         float(scale), _cuda_ptr(rowsum) if rowsum is not None else None,
+                                         _cuda_ptr(HX), _stream_ptr()))
 
     @staticmethod
     def enkf_work_size(m, Mtot):
