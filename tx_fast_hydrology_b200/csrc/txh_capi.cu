@@ -296,16 +296,14 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     const int rc = std::max(1, s.w_max_len), slots = std::max(1, s.slots_used);
     a.off_scr = rc * 512;
     a.off_in = a.off_scr + slots * 512;
-    a.off_coef = a.off_in + std::max(4, 8 - slots) * 512;     // segments stream through [scratch | ring]: >= 8 rows
-    a.off_cum = a.off_coef + rc * 32;
+    a.off_rec = a.off_in + std::max(4, 8 - slots) * 512;      // segments stream through [scratch | ring]: >= 8 rows
+    a.off_cum = a.off_rec + rc * 48;
     a.off_cumc = a.off_cum + up16(rc * 8);
-    a.off_f0 = a.off_cumc + up16(rc * 8);
-    a.off_f1 = a.off_f0 + up16(rc * 8);
-    a.off_hdr = a.off_f1 + up16(rc * 8);
-    a.off_words = a.off_hdr + up16(rc * 4);
+    a.off_words = a.off_cumc + up16(rc * 8);
     a.off_list = a.off_words + up16(std::max(1, s.w_max_words) * 4);
     a.off_steps = a.off_list + up16(std::max(1, s.w_max_words) * 4);
     a.smem_per_warp = a.off_steps + 16 * 24;                  // StepInterp records of one launch (<= 16 steps)
+    if ((size_t)std::max(1, s.n_wslots) * ld * sizeof(double) >= (size_t(1) << 32)) return 1;   // 32-bit slot offsets
     const int smem_max = 227 * 1024;
     int wpc = std::min(16, (smem_max - 1024) / a.smem_per_warp);
     if (wpc < 2 || s.w_n_own > 0) return 1;

@@ -284,13 +284,14 @@ innovation_cat_kernel(const double* __restrict__ HX, const double* __restrict__ 
 }
 
 // (sum of the split-K partials of C) -> A = C0 + shift*I, B = C1, then (C0 + shift I) Z = C1 by Cholesky.
-// One CTA of 8*MT threads; the matrices live in REGISTERS: thread (rg, c) = (tid / MT, tid % MT) owns rows
-// {8r + rg} of column c of A (lower triangle), of the right-hand sides B and of V (starts as the identity).
-// The forward substitutions ride on the factorisation, so a step is one shared-memory broadcast and ONE
-// barrier: at step j the owners publish column j of A (unscaled) and row j of B and V; with r = 1/sqrt(d_j)
-// everyone applies   A[i][c] -= A[i][j] A[c][j] r^2,   B[i][c] -= A[i][j] B[j][c] r^2,   V likewise,
-// and row j becomes final:  Y[j] = B[j] r,  L^-1[j] = V[j] r.  After MT steps Y = L^-1 B and V = L^-1, and
-// the backward substitution is the product Z = (L^-1)^T Y -- no second sequential sweep.
+// The vector FP64 pipe of one SM is the bound of this small solve, so the right-hand sides are split over
+// MT/8 CTAs (8 columns each); every CTA factors A itself (8*MT threads, the lower triangle in REGISTERS:
+// thread (rg, c) = (tid / MT, tid % MT) owns rows {8r + rg} of column c) and carries its slice of B along:
+//   step j : the owners publish column j of A (unscaled) and row j of B; with r = 1/sqrt(d_j) everyone applies
+//            A[i][c] -= A[i][j] A[c][j] r^2,  B[i][c] -= A[i][j] B[j][c] r^2;  row j becomes Y[j] = B[j] r and
+//            L[:, j] = A[:, j] r is parked in shared memory -- one barrier per column, the forward substitution
+//            rides on the factorisation;
+//   then the backward substitution L^T Z = Y, one barrier per row.
 // The system is padded with the identity up to MT (64 or 96) so that all register indices are static.
 constexpr int CS_NSPLIT = 8;
 
@@ -299,80 +300,80 @@ __global__ void __launch_bounds__(8 * MT)
 chol_solve_small_kernel(const double* __restrict__ Cpart, long long pstride, int Mt, double shift,
                         double* __restrict__ Z, int* __restrict__ info)
 {
-    constexpr int R = MT / 8, LDS_ = MT + 1;
+    constexpr int R = MT / 8, LDU = MT + 1;
     extern __shared__ double sm[];
-    double* Ys = sm;                      // [MT][MT+1]  Y = L^-1 B
-    double* Ls = Ys + MT * LDS_;          // [MT][MT+1]  L^-1
-    double* bc = Ls + MT * LDS_;          // [2][3][MT]  per-step broadcast (column of A, rows of B and V)
+    double* U = sm;                       // [MT][MT+1]  U[j][i] = L[i][j], i > j
+    double* bc = U + MT * LDU;            // [2][MT + 9] per-step broadcast (column of A, row of B, 1/sqrt(pivot))
+    double* invd = bc + 2 * (MT + 9);     // [MT]        1 / L[j][j]
     const int tid = threadIdx.x;
-    const int c = tid % MT, rg = tid / MT;
-    double a[R], b[R], v[R];
+    const int c = tid % MT, rg = tid / MT;            // A: rows {8r + rg} of column c
+    const int bi = tid >> 3, bcol = tid & 7;          // B: one element, row bi of this CTA's column bcol
+    const int gcol = blockIdx.x * 8 + bcol;
+    const int warp0 = (tid & ~31) % MT;               // first column of this warp's 32 columns
+    double a[R], b = 0.0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) { a[r] = 0.0; b[r] = 0.0; v[r] = (8 * r + rg == c) ? 1.0 : 0.0; }
+    for (int r = 0; r < R; ++r) a[r] = 0.0;
 #pragma unroll
-    for (int s = 0; s < CS_NSPLIT; ++s)
+    for (int s = 0; s < CS_NSPLIT; ++s) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int i = 8 * r + rg;
-            if (i < Mt && c < Mt) {
-                const double* row = Cpart + (size_t)s * pstride + (size_t)i * 2 * Mt;
-                a[r] += row[c];
-                b[r] += row[Mt + c];
-            }
+            if (i < Mt && c < Mt) a[r] += Cpart[(size_t)s * pstride + (size_t)i * 2 * Mt + c];
         }
+        if (bi < Mt && gcol < Mt) b += Cpart[(size_t)s * pstride + (size_t)bi * 2 * Mt + Mt + gcol];
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int i = 8 * r + rg;
         if (i == c) a[r] = (i < Mt) ? a[r] + shift : 1.0;
     }
+    // ---- factor + forward substitution ----
 #pragma unroll
     for (int pb = 0; pb < R; ++pb) {
         for (int pr = 0; pr < 8; ++pr) {
             const int j = 8 * pb + pr;
-            double* cb = bc + (j & 1) * 3 * MT;
+            double* cb = bc + (j & 1) * (MT + 9);
             double* brow = cb + MT;
-            double* vrow = cb + 2 * MT;
             if (c == j) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) cb[8 * r + rg] = a[r];       // rows < j carry junk that nobody reads
+                if (rg == pr) {
+                    // the pivot's owner alone takes the reciprocal square root (the FP64 pipe is narrow: sixteen
+                    // warps repeating it would cost more than the barrier)
+                    double d = a[pb];
+                    if (!(d > 0.0)) { if (blockIdx.x == 0) *info = j + 1; d = 1.0; }
+                    const double r1 = rsqrt(d);
+                    cb[MT + 8] = r1; invd[j] = r1;
+                }
             }
-            if (rg == pr) { brow[c] = b[pb]; vrow[c] = v[pb]; }
+            if (bi == j) brow[bcol] = b;
             __syncthreads();
-            double d = cb[j];
-            if (!(d > 0.0)) { if (tid == 0) *info = j + 1; d = 1.0; }
-            const double rs = rsqrt(d), rs2 = rs * rs;
-            const double bj = brow[c], vj = vrow[c];
-            if (rg == pr) { b[pb] = bj * rs; v[pb] = vj * rs; }
-            const double fb = bj * rs2, fv = vj * rs2, fa = c > j ? cb[c] * rs2 : 0.0;
+            const double rs = cb[MT + 8], rs2 = rs * rs;
+            if (bi == j) b *= rs;
+            else if (bi > j) b -= cb[bi] * (brow[bcol] * rs2);
+            if (c == j) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int i = 8 * r + rg;
-                if (r > pb || (r == pb && rg > pr)) {                    // i > j
-                    const double l = cb[i];
-                    b[r] -= l * fb;
-                    v[r] -= l * fv;
-                    if (i >= c) a[r] -= l * fa;
+                for (int r = 0; r < R; ++r) { const int i = 8 * r + rg; if (i > j) U[j * LDU + i] = a[r] * rs; }
+            }
+            if (warp0 + 31 > j) {                                        // some column of this warp is right of j
+                const double fa = c > j ? cb[c] * rs2 : 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = 8 * r + rg;
+                    if ((r > pb || (r == pb && rg > pr)) && i >= c) a[r] -= cb[i] * fa;
                 }
             }
         }
     }
-#pragma unroll
-    for (int r = 0; r < R; ++r) { const int i = 8 * r + rg; Ys[i * LDS_ + c] = b[r]; Ls[i * LDS_ + c] = v[r]; }
     __syncthreads();
-    // Z[i][c] = sum_p L^-1[p][i] Y[p][c]
-    double z[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) z[r] = 0.0;
-    for (int p = 0; p < MT; ++p) {
-        const double y = Ys[p * LDS_ + c];
-        const double* lp = Ls + p * LDS_ + rg;
-#pragma unroll
-        for (int r = 0; r < R; ++r) z[r] += lp[8 * r] * y;
+    // ---- backward: L^T Z = Y ----
+    for (int p = MT - 1; p >= 0; --p) {
+        double* zrow = bc + (p & 1) * (MT + 9) + MT;
+        if (bi == p) { b *= invd[p]; zrow[bcol] = b; }
+        __syncthreads();
+        if (bi < p) b -= U[bi * LDU + p] * zrow[bcol];
     }
-    if (c < Mt) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) { const int i = 8 * r + rg; if (i < Mt) Z[(size_t)i * Mt + c] = z[r]; }
-    }
+    if (bi < Mt && gcol < Mt) Z[(size_t)bi * Mt + gcol] = b;
 }
 
 // ---- ensemble transform applied to the state ------------------------------------------------------
@@ -590,16 +591,17 @@ cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long p
 {
     if (nsplit != CS_NSPLIT || Mt > 96) return cudaErrorInvalidValue;
     const int MT = Mt <= 64 ? 64 : 96;
-    const size_t smem = (2 * (size_t)MT * (MT + 1) + 6 * MT) * sizeof(double);
+    const size_t smem = ((size_t)MT * (MT + 1) + 2 * (MT + 9) + MT) * sizeof(double);
+    const int ncta = (Mt + 7) / 8;                      // 8 right-hand-side columns per CTA
     cudaError_t e;
     if (MT == 64) {
         e = cudaFuncSetAttribute(chol_solve_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        chol_solve_small_kernel<64><<<1, 8 * 64, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
+        chol_solve_small_kernel<64><<<ncta, 8 * 64, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
     } else {
         e = cudaFuncSetAttribute(chol_solve_small_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        chol_solve_small_kernel<96><<<1, 8 * 96, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
+        chol_solve_small_kernel<96><<<ncta, 8 * 96, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
     }
     count_launch();
     return cudaGetLastError();

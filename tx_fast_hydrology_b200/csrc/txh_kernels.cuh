@@ -85,9 +85,8 @@ struct WinArgs {
     unsigned long long watchdog_ns;
     int64_t n;
     int32_t n_tasks, n_mblocks, nsteps, n_slots, ld, M, wm_ld;
-    // per-warp shared memory (bytes): [p rows][scratch slots][input ring][coef][cumA][cumC][f0][f1][hdr][words][producers][slot list][steps]
-    int32_t smem_per_warp, off_scr, off_in, off_coef, off_cum, off_cumc, off_f0, off_f1, off_hdr, off_words, off_list,
-        off_steps;
+    // per-warp shared memory (bytes): [p rows][scratch slots][input ring][row records][cumA][cumC][words][slot list][steps]
+    int32_t smem_per_warp, off_scr, off_in, off_rec, off_cum, off_cumc, off_words, off_list, off_steps;
     unsigned long long* trace;            // optional [pairs][4 + nsteps] timeline (claim, loaded, end, kind|smid, publish per step)
     double* rowsum;                       // optional [n]: scale * sum over the members of the final outflows (n_mblocks == 1)
     double rowsum_scale;

@@ -43,10 +43,6 @@ __device__ __forceinline__ void cp_async4(unsigned sa, const void* g)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(g) : "memory");
 }
-__device__ __forceinline__ void cp_async8(unsigned sa, const void* g)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(g) : "memory");
-}
 __device__ __forceinline__ void cp_async16(unsigned sa, const void* g)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
@@ -136,44 +132,43 @@ __device__ __forceinline__ bool wait_cell(const WinArgs& a, const double* cell, 
 // Rows handed over by other tasks, consumed in a fixed order every step: a continuous stream (step, index)
 // prefetched D rows ahead through a shared-memory ring, across step boundaries.  One cp.async group per row.
 // A prefetch that came too early sees EMPTY and the consumer falls back to polling the cell itself.
+// The list holds byte offsets of the slots inside one step of the ring.
 struct InStream {
-    int issued, consumed;      // rows
-    int ps, pi;                // next (step, index) to issue
-    int cs, cidx;              // next (step, index) to consume
-    int slot_i, slot_c;        // ring cells of the next issue / next consume
+    int in_flight;             // rows issued and not yet consumed
+    int pi, ci;                // index of the next row to issue / consume within its step
+    int psteps;                // steps left to issue (including the current one)
+    unsigned slot_i, slot_c;   // byte offsets of the ring cells of the next issue / next consume
+    char* pbase;               // this lane's columns of the ring step being issued / consumed
+    char* cbase;
+    bool dead;                 // the launch is being abandoned: stop waiting
 };
 
 template <int D>
-__device__ __forceinline__ void stream_fill(InStream& st, const WinArgs& a, unsigned ring_sa, unsigned list_sa, int nL,
-                                            int ccol, bool active, bool one)
+__device__ __forceinline__ void stream_issue(InStream& st, const WinArgs& a, unsigned ring_sa, unsigned list_sa, int nL,
+                                             size_t step_bytes, bool active)
 {
-    while (st.issued - st.consumed < D && nL > 0 && st.ps < a.nsteps) {
-        if (active)
-            cp_async16(ring_sa + st.slot_i * 512u,
-                       a.ring + ((size_t)st.ps * a.n_slots + lds_u32(list_sa + 4u * st.pi)) * a.ld + ccol);
-        cp_async_commit();
-        st.slot_i = st.slot_i + 1 == D ? 0 : st.slot_i + 1;
-        ++st.issued;
-        if (++st.pi == nL) { st.pi = 0; ++st.ps; }
-        if (one) break;
-    }
+    if (active) cp_async16(ring_sa + st.slot_i, st.pbase + lds_u32(list_sa + 4u * st.pi));
+    cp_async_commit();
+    st.slot_i = st.slot_i + 512u == D * 512u ? 0u : st.slot_i + 512u;
+    ++st.in_flight;
+    if (++st.pi == nL) { st.pi = 0; --st.psteps; st.pbase += step_bytes; }
 }
 
 template <int D>
-__device__ __forceinline__ bool stream_next(InStream& st, const WinArgs& a, unsigned ring_sa, unsigned list_sa, int nL,
-                                            int ccol, bool active, int lane, double2& v)
+__device__ __forceinline__ double2 stream_next(InStream& st, const WinArgs& a, unsigned ring_sa, unsigned list_sa, int nL,
+                                               size_t step_bytes, bool active, int lane)
 {
-    if (st.issued - st.consumed >= D) cp_async_wait_group<D - 1>();     // the oldest of D rows in flight
+    if (st.in_flight >= D) cp_async_wait_group<D - 1>();                // the oldest of D rows in flight
     else cp_async_wait_all();
-    v = lds_row(ring_sa + st.slot_c * 512u);
-    double* cell = a.ring + ((size_t)st.cs * a.n_slots + lds_u32(list_sa + 4u * st.cidx)) * a.ld + ccol;
-    if (!wait_cell(a, cell, active, v, lane)) return false;
+    double2 v = lds_row(ring_sa + st.slot_c);
+    double* cell = reinterpret_cast<double*>(st.cbase + lds_u32(list_sa + 4u * st.ci));
+    if (!st.dead && !wait_cell(a, cell, active, v, lane)) st.dead = true;
     if (active) st_row(cell, empty_cell());
-    st.slot_c = st.slot_c + 1 == D ? 0 : st.slot_c + 1;
-    ++st.consumed;
-    if (++st.cidx == nL) { st.cidx = 0; ++st.cs; }
-    stream_fill<D>(st, a, ring_sa, list_sa, nL, ccol, active, true);
-    return true;
+    st.slot_c = st.slot_c + 512u == D * 512u ? 0u : st.slot_c + 512u;
+    --st.in_flight;
+    if (++st.ci == nL) { st.ci = 0; st.cbase += step_bytes; }
+    if (st.psteps > 0) stream_issue<D>(st, a, ring_sa, list_sa, nL, step_bytes, active);
+    return v;
 }
 
 // scale * (sum of this row over the members of the warp's block), lane 0 stores it (last step of a launch)
@@ -185,6 +180,26 @@ __device__ __forceinline__ void emit_rowsum(const WinArgs& a, int pos, int col, 
     if (lane == 0) a.rowsum[pos] = v * a.rowsum_scale;
 }
 
+// Per-row record in shared memory (48 bytes): everything a row update needs besides its state row, read with
+// three 128-bit loads one row ahead of the arithmetic.
+//   +0 header word   +8 alpha   +16 beta   +24 chi   +32 gamma*F[r0]   +40 gamma*F[r1]
+constexpr unsigned kRec = 48u;
+struct RowIn {
+    uint32_t h;
+    double al, be, ch, g0, g1;
+    double2 p;
+};
+__device__ __forceinline__ RowIn load_rowin(unsigned rec_sa, unsigned p_sa)
+{
+    RowIn x;
+    x.h = lds_u32(rec_sa);
+    x.al = lds_f64(rec_sa + 8u);
+    const double2 bc = lds_row(rec_sa + 16u), g = lds_row(rec_sa + 32u);
+    x.be = bc.x; x.ch = bc.y; x.g0 = g.x; x.g1 = g.y;
+    x.p = lds_row(p_sa);
+    return x;
+}
+
 struct FCtx {
     double w0, w1;
     double2 wm0, wm1;
@@ -192,15 +207,163 @@ struct FCtx {
 
 // gamma*q of this lane's two members; the staged rows already carry gamma
 template <bool HAS_F, bool HAS_W>
-__device__ __forceinline__ double2 forcing_q(const FCtx& c, unsigned f0, unsigned f1, int r)
+__device__ __forceinline__ double2 forcing_q(const FCtx& c, double g0, double g1)
 {
     double2 q = make_double2(0.0, 0.0);
     if (HAS_F) {
-        const double a0 = lds_f64(f0 + 8u * r), a1 = lds_f64(f1 + 8u * r);
-        if (HAS_W) { q.x = c.wm0.x * a0 + c.wm1.x * a1; q.y = c.wm0.y * a0 + c.wm1.y * a1; }
-        else { q.x = c.w0 * a0 + c.w1 * a1; q.y = q.x; }
+        if (HAS_W) { q.x = c.wm0.x * g0 + c.wm1.x * g1; q.y = c.wm0.y * g0 + c.wm1.y * g1; }
+        else { q.x = c.w0 * g0 + c.w1 * g1; q.y = q.x; }
     }
     return q;
+}
+
+// per-task context
+struct Tk {
+    unsigned sP, sScr, sIn, sRec, sCum, sCumC, sWords, sList;
+    int len, n_in, nL, col, lane, begin, ld;
+    bool active;
+    double* Ig;
+    double* Og;
+    size_t step_bytes;
+};
+
+// One step of a pocket: depth-first walk, o' = alpha*inflow + (p + gamma q), p' = beta*inflow + chi*o'.
+template <bool LAST, bool HAS_F, bool HAS_W>
+__device__ __forceinline__ void pocket_step(const WinArgs& a, const Tk& tk, InStream& ist, const FCtx& fc, char* ringS)
+{
+    unsigned aRec = tk.sRec, aP = tk.sP, aW = tk.sWords;
+    double* ig = tk.Ig;
+    double* og = tk.Og;
+    double2 acc = make_double2(0.0, 0.0);
+    RowIn nx = load_rowin(aRec, aP);
+    for (int r = 0; r < tk.len; ++r) {
+        const RowIn x = nx;
+        if (r + 1 < tk.len) nx = load_rowin(aRec + kRec, aP + 512u);
+        const uint32_t h = x.h;
+        double2 inflow = (h & HDR_ACC) ? acc : make_double2(0.0, 0.0);
+        for (uint32_t k = (h >> 6) & 0x1ffffffu; k > 0; --k) {
+            const uint32_t w = lds_u32(aW);
+            aW += 4u;
+            const double2 v = (w & WIN_SLOT) ? stream_next<kInRing>(ist, a, tk.sIn, tk.sList, tk.nL, tk.step_bytes, tk.active, tk.lane)
+                                             : lds_row(tk.sScr + (w << 9));
+            inflow.x += v.x; inflow.y += v.y;
+        }
+        const double2 q = forcing_q<HAS_F, HAS_W>(fc, x.g0, x.g1);
+        double2 on;
+        on.x = x.al * inflow.x + (x.p.x + q.x);
+        on.y = x.al * inflow.y + (x.p.y + q.y);
+        if (!LAST) {
+            double2 pn;
+            pn.x = x.be * inflow.x + x.ch * on.x;
+            pn.y = x.be * inflow.y + x.ch * on.y;
+            sts_row(aP, pn);
+        } else {
+            if (tk.active) { st_row(ig, inflow); st_row(og, on); }
+            if (a.rowsum) emit_rowsum(a, tk.begin + r, tk.col, on, tk.lane);
+            ig += tk.ld; og += tk.ld;
+        }
+        if (h & (HDR_PUSH | 0x3eu)) {                               // published and / or parked in a scratch row
+            if (h & HDR_PUSH) {
+                const uint32_t slot = lds_u32(aW);
+                aW += 4u;
+                if (tk.active) st_row(reinterpret_cast<double*>(ringS + (size_t)slot * tk.ld * sizeof(double)), on);
+            }
+            const uint32_t sl = (h >> 1) & 31u;
+            if (sl) sts_row(tk.sScr + ((sl - 1u) << 9), on);
+        }
+        acc = on;
+        aRec += kRec; aP += 512u;
+    }
+}
+
+// One step of a segment.  PRE: side_k = pocket roots joining reach k; B_k = the recurrence with nothing entering
+// the segment; what the NEXT step needs of this one is affine in the flow o_in entering the segment:
+//   p_k' = beta_k i_k + chi_k o_k = P0_k + C_k o_in,   P0_k = beta_k (side_k + B_{k-1}) + chi_k B_k,
+//   C_k = beta_k A_{k-1} + chi_k A_k  (A = prefix product of alpha, A_{-1} = 1; precomputed).
+// Hop: out = A_last * o_in + B_last, handed on before anything else.  In the last step (side_k, B_k) are
+// parked in the global I / O rows for the final fix-up o_k = B_k + A_k o_in, i_k = o_{k-1} + side_k.
+template <bool LAST, bool HAS_F, bool HAS_W>
+__device__ __forceinline__ void segment_step(const WinArgs& a, const Tk& tk, InStream& ist, const FCtx& fc, char* ringS,
+                                             int out_slot, unsigned long long* trs)
+{
+    unsigned aRec = tk.sRec, aP = tk.sP;
+    double* ig = tk.Ig;
+    double* og = tk.Og;
+    double2 B = make_double2(0.0, 0.0);
+    RowIn nx = load_rowin(aRec, aP);
+    for (int r = 0; r < tk.len; ++r) {
+        const RowIn x = nx;
+        if (r + 1 < tk.len) nx = load_rowin(aRec + kRec, aP + 512u);
+        const uint32_t h = x.h;
+        double2 inflow = (h & HDR_ACC) ? B : make_double2(0.0, 0.0);   // side_k + B_{k-1}
+        double2 side = make_double2(0.0, 0.0);
+        for (uint32_t k = (h >> 6) & 0x1fffu; k > 0; --k) {
+            const double2 v = stream_next<kSegRing>(ist, a, tk.sScr, tk.sList, tk.nL, tk.step_bytes, tk.active, tk.lane);
+            side.x += v.x; side.y += v.y;
+        }
+        inflow.x += side.x; inflow.y += side.y;
+        const double2 q = forcing_q<HAS_F, HAS_W>(fc, x.g0, x.g1);
+        B.x = x.al * inflow.x + (x.p.x + q.x);
+        B.y = x.al * inflow.y + (x.p.y + q.y);
+        if (!LAST) {
+            double2 p0;
+            p0.x = x.be * inflow.x + x.ch * B.x;
+            p0.y = x.be * inflow.y + x.ch * B.y;
+            sts_row(aP, p0);
+        } else {
+            if (tk.active) { st_row(ig, side); st_row(og, B); }
+            ig += tk.ld; og += tk.ld;
+        }
+        aRec += kRec; aP += 512u;
+    }
+    // hop
+    double2 oin = make_double2(0.0, 0.0);
+    for (int k = 0; k < tk.n_in; ++k) {
+        double* cell = reinterpret_cast<double*>(ringS + (size_t)(lds_u32(tk.sWords + 4u * k) & kIdMask) * tk.ld * sizeof(double));
+        double2 v = tk.active ? ld_cell_relaxed(cell) : make_double2(0.0, 0.0);
+        if (!ist.dead && !wait_cell(a, cell, tk.active, v, tk.lane)) ist.dead = true;
+        if (tk.active) st_row(cell, empty_cell());
+        oin.x += v.x; oin.y += v.y;
+    }
+    const double Al = lds_f64(tk.sCum + 8u * (tk.len - 1));
+    double2 out;
+    out.x = Al * oin.x + B.x;
+    out.y = Al * oin.y + B.y;
+    if (tk.active && out_slot >= 0) st_row(reinterpret_cast<double*>(ringS + (size_t)out_slot * tk.ld * sizeof(double)), out);
+    if (trs && tk.lane == 0) *trs = globaltimer_ns();
+    if (!LAST) {
+        // FIX, folded into the next state: p_k' = P0_k + C_k o_in
+        unsigned aQ = tk.sP, aC = tk.sCumC;
+        for (int r = 0; r < tk.len; ++r) {
+            const double C = lds_f64(aC);
+            double2 p0 = lds_row(aQ);
+            p0.x = C * oin.x + p0.x;
+            p0.y = C * oin.y + p0.y;
+            sts_row(aQ, p0);
+            aQ += 512u; aC += 8u;
+        }
+    } else {
+        // final FIX (each lane re-reads its own cells of the parked rows)
+        double2 op = oin;
+        ig = tk.Ig; og = tk.Og;
+        for (int r = 0; r < tk.len; ++r) {
+            double2 side = make_double2(0.0, 0.0), Bk = side;
+            if (tk.active) { side = ld_row(ig); Bk = ld_row(og); }
+            double2 on = out;
+            if (r + 1 < tk.len) {
+                const double A = lds_f64(tk.sCum + 8u * r);
+                on.x = A * oin.x + Bk.x;
+                on.y = A * oin.y + Bk.y;
+            }
+            double2 it;
+            it.x = op.x + side.x;
+            it.y = op.y + side.y;
+            if (tk.active) { st_row(og, on); st_row(ig, it); }
+            if (a.rowsum) emit_rowsum(a, tk.begin + r, tk.col, on, tk.lane);
+            op = on;
+            ig += tk.ld; og += tk.ld;
+        }
+    }
 }
 
 // Shared-memory state of a task: ONE row per reach, p = beta*i + chi*o, the part of the next update that
@@ -214,13 +377,15 @@ route_window_kernel(const WinArgs a)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned sb = (unsigned)__cvta_generic_to_shared(smem_all + (size_t)warp * a.smem_per_warp);
-    const unsigned sP = sb + lane * 16u;
-    const unsigned sScr = sb + a.off_scr + lane * 16u, sIn = sb + a.off_in + lane * 16u;
-    const unsigned sCoef = sb + a.off_coef, sCum = sb + a.off_cum, sCumC = sb + a.off_cumc, sF0 = sb + a.off_f0, sF1 = sb + a.off_f1;
-    const unsigned sHdr = sb + a.off_hdr, sWords = sb + a.off_words, sList = sb + a.off_list;
     const unsigned sSteps = sb + a.off_steps;
     const int nmb = a.n_mblocks, ld = a.ld;
     const long long total = (long long)a.n_tasks * nmb;
+    Tk tk;
+    tk.sP = sb + lane * 16u; tk.sScr = sb + a.off_scr + lane * 16u; tk.sIn = sb + a.off_in + lane * 16u;
+    tk.sRec = sb + a.off_rec; tk.sCum = sb + a.off_cum; tk.sCumC = sb + a.off_cumc;
+    tk.sWords = sb + a.off_words; tk.sList = sb + a.off_list;
+    tk.lane = lane; tk.ld = ld;
+    tk.step_bytes = (size_t)a.n_slots * ld * sizeof(double);
 
     for (;;) {
         long long t = 0;
@@ -237,54 +402,57 @@ route_window_kernel(const WinArgs a)
         const int col = mb * kMemberBlock + lane * 2;
         const bool active = col < ld;
         const int ccol = active ? col : 0;
-        double* Og = a.O + (size_t)td.begin * ld + ccol;
-        double* Ig = a.I + (size_t)td.begin * ld + ccol;
+        tk.len = len; tk.n_in = td.n_in; tk.col = col; tk.active = active; tk.begin = td.begin;
+        tk.Og = a.O + (size_t)td.begin * ld + ccol;
+        tk.Ig = a.I + (size_t)td.begin * ld + ccol;
 
-        // ---- load the task: per-row metadata, input stream, producer list; rows of I and O -> p ----
-        {
-            const double* gc = a.coef + 4 * (size_t)td.begin;
-            for (int i = lane; i < 2 * len; i += 32) cp_async16(sCoef + 16u * i, gc + 2 * i);
-            for (int i = lane; i < len; i += 32) {
-                cp_async8(sCum + 8u * i, a.cumA + td.begin + i);
-                cp_async8(sCumC + 8u * i, a.cumC + td.begin + i);
-                cp_async4(sHdr + 4u * i, a.hdr + td.begin + i);
-            }
-            for (int i = lane; i < td.n_words; i += 32) cp_async4(sWords + 4u * i, a.inw + td.in_off + i);
-            if (HAS_F)                                             // the launch's interpolation records (24 B each)
-                for (int i = lane; i < 6 * a.nsteps; i += 32) cp_async4(sSteps + 4u * i, reinterpret_cast<const uint32_t*>(a.steps) + i);
-        }
+        // ---- load the task: input stream, step records, per-row records; rows of I and O -> p ----
+        for (int i = lane; i < td.n_words; i += 32) cp_async4(tk.sWords + 4u * i, a.inw + td.in_off + i);
+        if (HAS_F)                                             // the launch's interpolation records (24 B each)
+            for (int i = lane; i < 6 * a.nsteps; i += 32) cp_async4(sSteps + 4u * i, reinterpret_cast<const uint32_t*>(a.steps) + i);
         cp_async_commit();
+        for (int i = lane; i < len; i += 32) {
+            const double2 ab = *reinterpret_cast<const double2*>(a.coef + 4 * (size_t)(td.begin + i));
+            const double2 cg = *reinterpret_cast<const double2*>(a.coef + 4 * (size_t)(td.begin + i) + 2);
+            const unsigned rec = tk.sRec + kRec * i;
+            sts_u32(rec, a.hdr[td.begin + i]);
+            sts_f64(rec + 8u, ab.x);
+            sts_row(rec + 16u, make_double2(ab.y, cg.x));
+            sts_row(rec + 32u, make_double2(0.0, 0.0));
+            sts_f64(tk.sCum + 8u * i, a.cumA[td.begin + i]);
+            sts_f64(tk.sCumC + 8u * i, a.cumC[td.begin + i]);
+        }
         // rows: the loads of a batch are all in flight before the first is used
         for (int r0 = 0; r0 < len; r0 += 4) {
             double2 io[4], oo[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (active && r0 + u < len) { io[u] = ld_row(Ig + (size_t)(r0 + u) * ld); oo[u] = ld_row(Og + (size_t)(r0 + u) * ld); }
+                if (active && r0 + u < len) { io[u] = ld_row(tk.Ig + (size_t)(r0 + u) * ld); oo[u] = ld_row(tk.Og + (size_t)(r0 + u) * ld); }
                 else { io[u] = make_double2(0.0, 0.0); oo[u] = io[u]; }
             if (r0 == 0) { cp_async_wait_all(); __syncwarp(); }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if (r0 + u < len) {
-                    const double be = lds_f64(sCoef + 32u * (r0 + u) + 8u), ch = lds_f64(sCoef + 32u * (r0 + u) + 16u);
+                    const double2 bc = lds_row(tk.sRec + kRec * (r0 + u) + 16u);
                     double2 p;
-                    p.x = be * io[u].x + ch * oo[u].x;
-                    p.y = be * io[u].y + ch * oo[u].y;
-                    sts_row(sP + (r0 + u) * 512u, p);
+                    p.x = bc.x * io[u].x + bc.y * oo[u].x;
+                    p.y = bc.x * io[u].y + bc.y * oo[u].y;
+                    sts_row(tk.sP + (r0 + u) * 512u, p);
                 }
         }
-        // rows of other tasks consumed through the input ring, in consumption order
+        // rows of other tasks consumed through the input ring, in consumption order: byte offsets of their slots
         int nL = 0;
         for (int base = 0; base < td.n_words; base += 32) {
             const int i = base + lane;
-            const uint32_t w = i < td.n_words ? lds_u32(sWords + 4u * i) : 0u;
+            const uint32_t w = i < td.n_words ? lds_u32(tk.sWords + 4u * i) : 0u;
             const bool is = (w & WIN_SLOT) != 0u && i >= td.n_in;
             const unsigned m = __ballot_sync(0xffffffffu, is);
-            if (is) sts_u32(sList + 4u * (nL + __popc(m & ((1u << lane) - 1u))), w & kIdMask);
+            if (is) sts_u32(tk.sList + 4u * (nL + __popc(m & ((1u << lane) - 1u))), (w & kIdMask) * (unsigned)(ld * sizeof(double)));
             nL += __popc(m);
         }
         __syncwarp();
+        tk.nL = nL;
         int cur_r0 = -1, cur_r1 = -1;
-        bool dead = false;
         if (tr && lane == 0) tr[1] = globaltimer_ns();
         // per-step forcing weights of this lane's two members: (w0*mul[r0][m], w1*mul[r1][m]), muskingum.py:528-531
         auto load_fctx = [&](int s) -> FCtx {
@@ -304,13 +472,22 @@ route_window_kernel(const WinArgs a)
             return c;
         };
         FCtx fc_next = load_fctx(0);
+        const bool seg = td.kind == WTASK_SEG;
+        const unsigned ring_sa = seg ? tk.sScr : tk.sIn;
         InStream ist;
-        ist.issued = ist.consumed = ist.ps = ist.pi = ist.cs = ist.cidx = ist.slot_i = ist.slot_c = 0;
+        ist.in_flight = 0; ist.pi = ist.ci = 0; ist.slot_i = ist.slot_c = 0u; ist.dead = false;
+        ist.psteps = nL > 0 ? a.nsteps : 0;
+        ist.pbase = reinterpret_cast<char*>(a.ring + ccol);
+        ist.cbase = ist.pbase;
+        for (int j = 0; j < (seg ? kSegRing : kInRing) && ist.psteps > 0; ++j) {
+            if (seg) stream_issue<kSegRing>(ist, a, ring_sa, tk.sList, nL, tk.step_bytes, active);
+            else stream_issue<kInRing>(ist, a, ring_sa, tk.sList, nL, tk.step_bytes, active);
+        }
 
-        for (int s = 0; s < a.nsteps && !dead; ++s) {
+        for (int s = 0; s < a.nsteps; ++s) {
             const bool last = s + 1 == a.nsteps;                   // outflows and inflows go to global memory
-            double* ringS = a.ring + (size_t)s * a.n_slots * ld + ccol;
-            FCtx fc = fc_next;
+            char* ringS = reinterpret_cast<char*>(a.ring + ccol) + (size_t)s * tk.step_bytes;
+            const FCtx fc = fc_next;
             if (HAS_F) {
                 const int r0 = (int)lds_u32(sSteps + 24u * s), r1 = (int)lds_u32(sSteps + 24u * s + 4u);
                 if (r0 != cur_r0 || r1 != cur_r1) {              // a new bracket of the forcing table
@@ -319,141 +496,24 @@ route_window_kernel(const WinArgs a)
                     __syncwarp();
                     // the rows are stored multiplied by gamma: o' = alpha*inflow + (p + c0*(gamma f0) + c1*(gamma f1))
                     for (int i = lane; i < len; i += 32) {
-                        const double ga = lds_f64(sCoef + 32u * i + 24u);
-                        sts_f64(sF0 + 8u * i, ga * __ldg(F0 + i));
-                        sts_f64(sF1 + 8u * i, ga * __ldg(F1 + i));
+                        const double ga = a.coef[4 * (size_t)(td.begin + i) + 3];
+                        sts_row(tk.sRec + kRec * i + 32u, make_double2(ga * __ldg(F0 + i), ga * __ldg(F1 + i)));
                     }
                     __syncwarp();
                     cur_r0 = r0; cur_r1 = r1;
                 }
                 if (!last) fc_next = load_fctx(s + 1);           // in flight during this step
             }
-            const bool seg = td.kind == WTASK_SEG;
-            if (seg) stream_fill<kSegRing>(ist, a, sScr, sList, nL, ccol, active, false);
-            else stream_fill<kInRing>(ist, a, sIn, sList, nL, ccol, active, false);
-
-            if (td.kind == WTASK_POCKET) {
-                int wi = 0;
-                double2 acc = make_double2(0.0, 0.0);
-                for (int r = 0; r < len; ++r) {
-                    const uint32_t h = lds_u32(sHdr + 4u * r);
-                    const double2 p = lds_row(sP + r * 512u);
-                    const double al = lds_f64(sCoef + 32u * r), be = lds_f64(sCoef + 32u * r + 8u);
-                    const double ch = lds_f64(sCoef + 32u * r + 16u);
-                    double2 inflow = (h & HDR_ACC) ? acc : make_double2(0.0, 0.0);
-                    const int nin = (int)((h >> 6) & 0x1ffffffu);
-                    for (int k = 0; k < nin; ++k) {
-                        const uint32_t w = lds_u32(sWords + 4u * wi++);
-                        double2 v;
-                        if (w & WIN_SLOT) { if (!stream_next<kInRing>(ist, a, sIn, sList, nL, ccol, active, lane, v)) { dead = true; break; } }
-                        else v = lds_row(sScr + w * 512u);
-                        inflow.x += v.x; inflow.y += v.y;
-                    }
-                    if (dead) break;
-                    const double2 q = forcing_q<HAS_F, HAS_W>(fc, sF0, sF1, r);
-                    double2 on;
-                    on.x = al * inflow.x + (p.x + q.x);
-                    on.y = al * inflow.y + (p.y + q.y);
-                    if (!last) {
-                        double2 pn;
-                        pn.x = be * inflow.x + ch * on.x;
-                        pn.y = be * inflow.y + ch * on.y;
-                        sts_row(sP + r * 512u, pn);
-                    } else {
-                        if (active) { st_row(Ig + (size_t)r * ld, inflow); st_row(Og + (size_t)r * ld, on); }
-                        if (a.rowsum) emit_rowsum(a, td.begin + r, col, on, lane);
-                    }
-                    if (h & HDR_PUSH) {                              // read by another task: publish
-                        const uint32_t slot = lds_u32(sWords + 4u * wi++);
-                        if (active) st_row(ringS + (size_t)slot * ld, on);
-                    }
-                    const uint32_t sl = (h >> 1) & 31u;
-                    if (sl) sts_row(sScr + (sl - 1) * 512u, on);
-                    acc = on;
-                }
+            if (!seg) {
+                if (last) pocket_step<true, HAS_F, HAS_W>(a, tk, ist, fc, ringS);
+                else pocket_step<false, HAS_F, HAS_W>(a, tk, ist, fc, ringS);
                 if (tr && lane == 0) tr[4 + s] = globaltimer_ns();
             } else {
-                // PRE: side_k = pocket roots joining reach k; B_k = the recurrence with nothing entering the
-                // segment; what the NEXT step needs of this one is affine in the flow o_in entering the segment:
-                //   p_k' = beta_k i_k + chi_k o_k = P0_k + C_k o_in,   P0_k = beta_k (side_k + B_{k-1}) + chi_k B_k,
-                //   C_k = beta_k A_{k-1} + chi_k A_k  (A = prefix product of alpha, A_{-1} = 1; precomputed).
-                // In the last step (side_k, B_k) are parked in the global I / O rows for the final fix-up.
-                double2 B = make_double2(0.0, 0.0);
-                for (int r = 0; r < len; ++r) {
-                    const uint32_t h = lds_u32(sHdr + 4u * r);
-                    const double2 p = lds_row(sP + r * 512u);
-                    const double al = lds_f64(sCoef + 32u * r), be = lds_f64(sCoef + 32u * r + 8u);
-                    const double ch = lds_f64(sCoef + 32u * r + 16u);
-                    const int nin = (int)((h >> 6) & 0x1fffu);
-                    double2 side = make_double2(0.0, 0.0);
-                    for (int k = 0; k < nin; ++k) {
-                        double2 v;
-                        if (!stream_next<kSegRing>(ist, a, sScr, sList, nL, ccol, active, lane, v)) { dead = true; break; }
-                        side.x += v.x; side.y += v.y;
-                    }
-                    if (dead) break;
-                    const double2 q = forcing_q<HAS_F, HAS_W>(fc, sF0, sF1, r);
-                    double2 inflow = side;                           // side_k + B_{k-1}
-                    if (h & HDR_ACC) { inflow.x += B.x; inflow.y += B.y; }
-                    B.x = al * inflow.x + (p.x + q.x);
-                    B.y = al * inflow.y + (p.y + q.y);
-                    if (!last) {
-                        double2 p0;
-                        p0.x = be * inflow.x + ch * B.x;
-                        p0.y = be * inflow.y + ch * B.y;
-                        sts_row(sP + r * 512u, p0);
-                    } else if (active) {
-                        st_row(Ig + (size_t)r * ld, side);
-                        st_row(Og + (size_t)r * ld, B);
-                    }
-                }
-                // hop: out = A_last * o_in + B_last, o_in = the rows entering the segment
-                if (dead) break;
-                double2 oin = make_double2(0.0, 0.0);
-                for (int k = 0; k < td.n_in; ++k) {
-                    double* cell = ringS + (size_t)(lds_u32(sWords + 4u * k) & kIdMask) * ld;
-                    double2 v = active ? ld_cell_relaxed(cell) : make_double2(0.0, 0.0);
-                    if (!wait_cell(a, cell, active, v, lane)) { dead = true; break; }
-                    if (active) st_row(cell, empty_cell());
-                    oin.x += v.x; oin.y += v.y;
-                }
-                if (dead) break;
-                const double Al = lds_f64(sCum + 8u * (len - 1));
-                double2 out;
-                out.x = Al * oin.x + B.x;
-                out.y = Al * oin.y + B.y;
-                if (active && td.out_slot >= 0) st_row(ringS + (size_t)td.out_slot * ld, out);
-                if (tr && lane == 0) tr[4 + s] = globaltimer_ns();
-                if (!last) {
-                    // FIX, folded: p_k' = P0_k + C_k o_in
-                    for (int r = 0; r < len; ++r) {
-                        const double C = lds_f64(sCumC + 8u * r);
-                        double2 p0 = lds_row(sP + r * 512u);
-                        p0.x = C * oin.x + p0.x;
-                        p0.y = C * oin.y + p0.y;
-                        sts_row(sP + r * 512u, p0);
-                    }
-                } else {
-                    // final FIX: o_k = B_k + A_k o_in, i_k = o_{k-1} + side_k (each lane re-reads its own cells)
-                    double2 op = oin;
-                    for (int r = 0; r < len; ++r) {
-                        double2 side = make_double2(0.0, 0.0), Bk = side;
-                        if (active) { side = ld_row(Ig + (size_t)r * ld); Bk = ld_row(Og + (size_t)r * ld); }
-                        double2 on = out;
-                        if (r + 1 < len) {
-                            const double A = lds_f64(sCum + 8u * r);
-                            on.x = A * oin.x + Bk.x;
-                            on.y = A * oin.y + Bk.y;
-                        }
-                        double2 it;
-                        it.x = op.x + side.x;
-                        it.y = op.y + side.y;
-                        if (active) { st_row(Og + (size_t)r * ld, on); st_row(Ig + (size_t)r * ld, it); }
-                        if (a.rowsum) emit_rowsum(a, td.begin + r, col, on, lane);
-                        op = on;
-                    }
-                }
+                unsigned long long* trs = tr ? tr + 4 + s : nullptr;
+                if (last) segment_step<true, HAS_F, HAS_W>(a, tk, ist, fc, ringS, td.out_slot, trs);
+                else segment_step<false, HAS_F, HAS_W>(a, tk, ist, fc, ringS, td.out_slot, trs);
             }
+            if (ist.dead) break;
         }
         cp_async_wait_all();
         if (tr && lane == 0) {
