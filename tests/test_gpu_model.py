@@ -157,7 +157,8 @@ def test_dense_linear_algebra():
 
 @pytest.mark.parametrize("n,M,m,seed,diag", [(400, 16, 12, 1, False), (1500, 64, 40, 2, False), (900, 10, 25, 3, False),
                                              (2000, 64, 100, 4, True), (1200, 32, 80, 5, False),
-                                             (1000, 96, 130, 6, True)])
+                                             (1000, 96, 130, 6, True), (1500, 128, 200, 10, True),
+                                             (1200, 160, 100, 11, False), (800, 200, 330, 12, False)])
 def test_enkf_update_vs_oracle(oracle, n, M, m, seed, diag):
     """Ensemble update == da.py:112-126 applied to the sample covariance (oracle.enkf_update).  Covers the
     direct m x m solve (M >= m) and the ensemble-space solve (M < m) with diagonal and dense R."""

@@ -216,6 +216,108 @@ spd_solve_kernel(double* __restrict__ S, double* __restrict__ B, int m, int k, i
     }
 }
 
+// ---- blocked Cholesky solve for systems too large for one CTA (S [m][m] row-major, B [m][k]) -------------
+constexpr int PB = 32;
+
+// factor the diagonal block S[j0:j0+nb, j0:j0+nb] in shared memory (every CTA repeats it), then by CTA:
+//   0            : write the factor back
+//   1..nslab     : a 64-row slab of the panel below, L21 = A21 L11^-T (one thread per row)
+//   nslab+1..    : a 64-column slab of the right-hand sides, Y1 = L11^-1 B1 (one thread per column)
+__global__ void __launch_bounds__(64)
+chol_panel_kernel(double* __restrict__ S, int m, double* __restrict__ B, int k, int j0, int nb, int nslab,
+                  int* __restrict__ info)
+{
+    __shared__ double D[PB][PB + 1];
+    __shared__ double invd[PB];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < PB * PB; e += 64) {
+        const int i = e / PB, c = e - i * PB;
+        D[i][c] = (i < nb && c < nb) ? S[(size_t)(j0 + i) * m + j0 + c] : (i == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {
+        double d = D[j][j];
+        if (!(d > 0.0)) { if (tid == 0 && blockIdx.x == 0) *info = j0 + j + 1; d = 1.0; }
+        const double rs = rsqrt(d);
+        __syncthreads();
+        if (tid == 0) { D[j][j] = d * rs; invd[j] = rs; }
+        if (tid > j && tid < nb) D[tid][j] *= rs;
+        __syncthreads();
+        if (tid > j && tid < nb) {
+            const double l = D[tid][j];
+            for (int c = j + 1; c <= tid; ++c) D[tid][c] -= l * D[c][j];
+        }
+        __syncthreads();
+    }
+    const int b = blockIdx.x;
+    if (b == 0) {
+        for (int e = tid; e < nb * nb; e += 64) {
+            const int i = e / nb, c = e - i * nb;
+            if (c <= i) S[(size_t)(j0 + i) * m + j0 + c] = D[i][c];
+        }
+    } else if (b <= nslab) {
+        const int i = j0 + nb + (b - 1) * 64 + tid;
+        if (i < m) {
+            double* row = S + (size_t)i * m + j0;
+            double x[PB];
+#pragma unroll
+            for (int c = 0; c < PB; ++c) {
+                if (c < nb) {
+                    double v = row[c];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) v -= x[q] * D[c][q];
+                    x[c] = v * invd[c];
+                } else x[c] = 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < PB; ++c) if (c < nb) row[c] = x[c];
+        }
+    } else {
+        const int col = (b - nslab - 1) * 64 + tid;
+        if (col < k) {
+            double y[PB];
+#pragma unroll
+            for (int r = 0; r < PB; ++r) {
+                if (r < nb) {
+                    double v = B[(size_t)(j0 + r) * k + col];
+#pragma unroll
+                    for (int q = 0; q < r; ++q) v -= D[r][q] * y[q];
+                    y[r] = v * invd[r];
+                } else y[r] = 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < PB; ++r) if (r < nb) B[(size_t)(j0 + r) * k + col] = y[r];
+        }
+    }
+}
+
+// Z1 = L11^-T Y1 for one diagonal block (one thread per right-hand-side column)
+__global__ void __launch_bounds__(64)
+chol_back_kernel(const double* __restrict__ S, int m, double* __restrict__ B, int k, int j0, int nb)
+{
+    __shared__ double D[PB][PB + 1];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < PB * PB; e += 64) {
+        const int i = e / PB, c = e - i * PB;
+        D[i][c] = (i < nb && c <= i) ? S[(size_t)(j0 + i) * m + j0 + c] : (i == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int col = blockIdx.x * 64 + tid;
+    if (col >= k) return;
+    double z[PB];
+#pragma unroll
+    for (int r = PB - 1; r >= 0; --r) {
+        if (r < nb) {
+            double v = B[(size_t)(j0 + r) * k + col];
+#pragma unroll
+            for (int q = PB - 1; q > r; --q) if (q < nb) v -= D[q][r] * z[q];
+            z[r] = v / D[r][r];
+        } else z[r] = 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < PB; ++r) if (r < nb) B[(size_t)(j0 + r) * k + col] = z[r];
+}
+
 // Gauss-Jordan inverse with partial pivoting (np.linalg.inv of da.py:119), one CTA, in place:
 // A <- inv(A); `work` [m][m] receives the running inverse.
 __global__ void __launch_bounds__(1024)
@@ -374,6 +476,20 @@ chol_solve_small_kernel(const double* __restrict__ Cpart, long long pstride, int
         if (bi < p) b -= U[bi * LDU + p] * zrow[bcol];
     }
     if (bi < Mt && gcol < Mt) Z[(size_t)bi * Mt + gcol] = b;
+}
+
+// sum of the split-K partials of C = [C0 | C1] -> Cf = C0 + shift*I and C1 as two dense Mt x Mt matrices
+__global__ void __launch_bounds__(256)
+woodbury_assemble_kernel(const double* __restrict__ Cpart, int nsplit, long long pstride, int Mt, double shift,
+                         double* __restrict__ Cf, double* __restrict__ C1)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= Mt * 2 * Mt) return;
+    const int i = gid / (2 * Mt), j = gid - i * 2 * Mt;
+    double v = 0.0;
+    for (int s = 0; s < nsplit; ++s) v += Cpart[(size_t)s * pstride + gid];
+    if (j < Mt) Cf[(size_t)i * Mt + j] = v + (i == j ? shift : 0.0);
+    else C1[(size_t)i * Mt + (j - Mt)] = v;
 }
 
 // ---- ensemble transform applied to the state ------------------------------------------------------
@@ -607,6 +723,14 @@ cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long p
     return cudaGetLastError();
 }
 
+cudaError_t launch_woodbury_assemble(const double* Cpart, int nsplit, long long pstride, int Mt, double shift, double* Cf,
+                                     double* C1, cudaStream_t st)
+{
+    woodbury_assemble_kernel<<<nblk((long long)Mt * 2 * Mt, 256), 256, 0, st>>>(Cpart, nsplit, pstride, Mt, shift, Cf, C1);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_enkf_stats(const double* X, int ld, int M, int64_t n, double scale, const int32_t* gauge_of_pos,
                               double* rowsum, double* HX, cudaStream_t st)
 {
@@ -632,9 +756,41 @@ cudaError_t launch_innov_cov_finish(double* S, const double* qs, const double* R
 
 cudaError_t launch_spd_solve(double* S, double* B, int m, int k, int* info, cudaStream_t st)
 {
-    spd_solve_kernel<<<1, 1024, 0, st>>>(S, B, m, k, info);
-    count_launch();
-    return cudaGetLastError();
+    if (m <= 48) {
+        spd_solve_kernel<<<1, 1024, 0, st>>>(S, B, m, k, info);
+        count_launch();
+        return cudaGetLastError();
+    }
+    // blocked right-looking Cholesky, panels of PB columns: factor the diagonal block, solve the panel below
+    // and the matching rows of B, update the trailing matrix and the rest of B on the tensor cores
+    cudaError_t e;
+    for (int j0 = 0; j0 < m; j0 += PB) {
+        const int nb = m - j0 < PB ? m - j0 : PB;
+        const int below = m - j0 - nb;
+        const int nslab = (below + 63) / 64, ncol = (k + 63) / 64;
+        chol_panel_kernel<<<1 + nslab + ncol, 64, 0, st>>>(S, m, B, k, j0, nb, nslab, info);
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (below > 0) {
+            const double* L21 = S + (size_t)(j0 + nb) * m + j0;
+            double* S22 = S + (size_t)(j0 + nb) * m + (j0 + nb);
+            if ((e = launch_dgemm(0, 1, below, below, nb, -1.0, L21, m, L21, m, 1.0, S22, m, st)) != cudaSuccess) return e;
+            if ((e = launch_dgemm(0, 0, below, k, nb, -1.0, L21, m, B + (size_t)j0 * k, k, 1.0, B + (size_t)(j0 + nb) * k, k, st)) != cudaSuccess) return e;
+        }
+    }
+    // backward substitution L^T X = Y, panels from the bottom: solve the block, then update the rows above
+    const int last0 = ((m - 1) / PB) * PB;
+    for (int j0 = last0; j0 >= 0; j0 -= PB) {
+        const int nb = m - j0 < PB ? m - j0 : PB;
+        chol_back_kernel<<<(k + 63) / 64, 64, 0, st>>>(S, m, B, k, j0, nb);
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (j0 > 0) {
+            // Y[0:j0] -= L[j0:j0+nb, 0:j0]^T Z1
+            if ((e = launch_dgemm(1, 0, j0, k, nb, -1.0, S + (size_t)j0 * m, m, B + (size_t)j0 * k, k, 1.0, B, k, st)) != cudaSuccess) return e;
+        }
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_inverse(double* A, double* W, int m, int* info, cudaStream_t st)

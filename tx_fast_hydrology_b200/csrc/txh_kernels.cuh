@@ -140,6 +140,8 @@ cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long p
 cudaError_t launch_dgemm_ex(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
                             const double* B, int ldb, double beta, const double* Cin, int ldcin, double* C, int ldc,
                             cudaStream_t st);
+cudaError_t launch_woodbury_assemble(const double* Cpart, int nsplit, long long pstride, int Mt, double shift, double* Cf,
+                                     double* C1, cudaStream_t st);
 cudaError_t launch_enkf_stats(const double* X, int ld, int M, int64_t n, double scale, const int32_t* gauge_of_pos,
                               double* rowsum, double* HX, cudaStream_t st);
 cudaError_t launch_innovation(const double* HX, const double* Zp, const double* mean_obs, int m, int M, double* HA,
