@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--assim-every", type=int, default=12, help="routing steps between EnKF updates")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--cpu-windows", type=int, default=3, help="hourly windows in the CPU sample")
+    ap.add_argument("--sharding", default="basins", choices=["basins", "members"],
+                    help="N > 1: one independent basin (network + ensemble + gauges) per GPU, no collective; or the "
+                         "members of ONE network's ensemble over the GPUs, EnKF statistics combined with NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -77,19 +80,27 @@ class Workload:
         self.M = M = a.members
         self.Mtot = M * world
         self.rank, self.world = rank, world
+        self.by_basin = a.sharding == "basins" and world > 1
+        if self.by_basin:
+            # basin sharding: every rank owns an independent basin of the same size with its own ensemble
+            # and gauges (the reference's app runs one Kalman filter per sub-basin model, app.py:130-141)
+            self.Mtot = M
+        seed = a.seed + (1000 * rank if self.by_basin else 0)
+        self.seed = seed
         self.nsteps = int(round(a.days * 86400.0 / DT_S))
         self.every = a.assim_every
         self.nwin = self.nsteps // self.every
-        self.net = S.make_network(n, a.seed)
-        self.params = S.make_params(n, a.seed)
+        self.net = S.make_network(n, seed)
+        self.params = S.make_params(n, seed)
         import pandas as pd
         self.t0_ns = int(pd.Timestamp(T0).value)
-        self.times, self.table = S.make_forcing(n, self.nsteps, DT_S, a.seed, t0_ns=self.t0_ns, rows_every=12)
-        mul_all = S.make_member_multipliers(self.times.size, self.Mtot, a.seed)
-        self.mul = np.ascontiguousarray(mul_all[:, rank * M:(rank + 1) * M])
-        rng = np.random.default_rng(a.seed + 7)
+        self.times, self.table = S.make_forcing(n, self.nsteps, DT_S, seed, t0_ns=self.t0_ns, rows_every=12)
+        mul_all = S.make_member_multipliers(self.times.size, self.Mtot, seed)
+        c0 = 0 if self.by_basin else rank * M
+        self.mul = np.ascontiguousarray(mul_all[:, c0:c0 + M])
+        rng = np.random.default_rng(seed + 7)
         spread = rng.uniform(0.5, 1.5, size=(n, self.Mtot))
-        self.o0 = np.ascontiguousarray(self.params["o_t"][:, None] * spread[:, rank * M:(rank + 1) * M])
+        self.o0 = np.ascontiguousarray(self.params["o_t"][:, None] * spread[:, c0:c0 + M])
         self.gauges = S.make_gauges(self.net["endnodes"], a.gauges, seed=4)
         self.m = self.gauges.size
         self.R = 1e-2 * np.eye(self.m)             # app.py:137-138 values
@@ -99,7 +110,7 @@ class Workload:
 
     def make_observations(self, truth):
         """truth [nwin][m] -> per-member perturbed observations [nwin][m][Mtot] (all ranks identical)."""
-        rng = np.random.default_rng(self.a.seed + 11)
+        rng = np.random.default_rng(self.seed + 11)
         obs = truth + 0.1 * rng.standard_normal(truth.shape)                 # N(0, R), R = 1e-2 I
         noise = 0.1 * rng.standard_normal((truth.shape[0], self.m, self.Mtot))
         self.obs = obs
@@ -107,7 +118,8 @@ class Workload:
         return self.Zp
 
     def updates_per_run(self):
-        return float(self.n) * self.Mtot * self.nsteps
+        """whole job: all ranks"""
+        return float(self.n) * self.M * self.world * self.nsteps
 
 
 # ------------------------------------------------------------------------------------------------
@@ -249,10 +261,14 @@ def workload_config(wl, a, world):
     return {
         "workload": "C3: synthetic Texas-scale network, 64-member ensemble per GPU, 7-day run at a 5-min step, "
                     "hourly EnKF of 500 gauges (BASELINE.json configs[2])",
-        "reaches": wl.n, "levels": 1000, "members_per_gpu": wl.M, "members_total": wl.M * world,
+        "reaches": wl.n * (world if wl.by_basin else 1), "reaches_per_gpu": wl.n, "levels": 1000,
+        "members_per_gpu": wl.M, "members_per_ensemble": wl.Mtot,
         "routing_steps": wl.nsteps, "dt_s": DT_S, "gauges": wl.m, "enkf_updates": wl.nwin,
         "assimilate_every_steps": wl.every, "seed": a.seed,
-        "sharding": "ensemble members over ranks (network replicated); EnKF statistics combined with NCCL",
+        "sharding": ("single GPU" if world == 1 else
+                     "independent basins, one per GPU, each with its own ensemble, gauges and EnKF; no collective"
+                     if wl.by_basin else
+                     "ensemble members of one network over ranks (network replicated); EnKF statistics combined with NCCL"),
         "l2": "256 MiB buffer written between bench steps (inside the timed region); per-run inputs "
               "(forcing 135 MB + observations + 102 MB state) exceed the 126 MB L2",
     }
@@ -301,7 +317,8 @@ def gpu_arm(a):
     idx = pd.DatetimeIndex(pd.to_datetime(wl.t0_ns + (np.arange(nwin, dtype=np.int64) + 1) * int(every * DT_S * 1e9),
                                           unit="ns", utc=True)).as_unit("ns")
     meas = pd.DataFrame(wl.obs, index=idx, columns=[d["reach_ids"][j] for j in wl.gauges])
-    enkf = EnsembleKalmanFilter(mdl, meas, wl.Q, wl.R, every=pd.Timedelta(seconds=every * DT_S))
+    enkf = EnsembleKalmanFilter(mdl, meas, wl.Q, wl.R, every=pd.Timedelta(seconds=every * DT_S),
+                                group=False if (wl.by_basin or world == 1) else None)
     assert enkf.Mtot == wl.Mtot
 
     # pinned host inputs / outputs of the end-to-end arm

@@ -79,6 +79,7 @@ struct txh_net {
     int32_t* d_wprod = nullptr;
     double* d_ring = nullptr; size_t ring_cap = 0; int ring_ld = 0;
     int route_kernel = 0;               // 0 auto (window unless recording), 1 dataflow, 2 window
+    double* d_stage = nullptr; size_t stage_cap = 0;   // reach-order staging of txh_pack_host / txh_unpack_host
     double* stats_rowsum = nullptr;     // txh_set_stats_output: row sums of the final outflows of every routing call
     double stats_scale = 1.0;
 };
@@ -156,6 +157,18 @@ int ensure_coef(txh_net* net, cudaStream_t st)
         CU(cudaStreamSynchronize(st));
         net->coef_dirty = false;
     }
+    return TXH_OK;
+}
+
+// grow-only device staging buffer in reach order (stream-ordered reuse: one stream per handle)
+int stage_buffer(txh_net* net, size_t doubles, cudaStream_t st, double** out)
+{
+    if (doubles > net->stage_cap) {
+        if (net->d_stage) { CU(cudaStreamSynchronize(st)); CU(cudaFree(net->d_stage)); net->d_stage = nullptr; }
+        CU(cudaMalloc((void**)&net->d_stage, doubles * sizeof(double)));
+        net->stage_cap = doubles;
+    }
+    *out = net->d_stage;
     return TXH_OK;
 }
 
@@ -438,6 +451,7 @@ void txh_destroy(txh_net* net)
         if (net->d_gauge_of_pos) cudaFree(net->d_gauge_of_pos);
         cudaFree(net->d_wtasks); cudaFree(net->d_whdr); cudaFree(net->d_winw); cudaFree(net->d_wprod);
         if (net->d_ring) cudaFree(net->d_ring);
+        if (net->d_stage) cudaFree(net->d_stage);
         if (net->h_status) cudaFreeHost(net->h_status);
     }
     delete net;
@@ -580,10 +594,9 @@ int txh_pack_host(txh_net* net, const double* src, int64_t M, int layout, double
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = net->topo.n;
     double* tmp = nullptr;
-    CU(cudaMallocAsync((void**)&tmp, sizeof(double) * n * M, st));
+    if ((rc = stage_buffer(net, (size_t)n * M, st, &tmp))) return rc;
     CU(cudaMemcpyAsync(tmp, src, sizeof(double) * n * M, cudaMemcpyHostToDevice, st));
     CU(launch_pack(net->d_reach_of_pos, tmp, dst, n, (int)M, (int)txh_row_stride(M), layout, st));
-    CU(cudaFreeAsync(tmp, st));
     return TXH_OK;
 }
 
@@ -595,10 +608,9 @@ int txh_unpack_host(txh_net* net, const double* src, int64_t M, int layout, doub
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = net->topo.n;
     double* tmp = nullptr;
-    CU(cudaMallocAsync((void**)&tmp, sizeof(double) * n * M, st));
+    if ((rc = stage_buffer(net, (size_t)n * M, st, &tmp))) return rc;
     CU(launch_unpack(net->d_reach_of_pos, src, tmp, n, (int)M, (int)txh_row_stride(M), layout, st));
     CU(cudaMemcpyAsync(dst, tmp, sizeof(double) * n * M, cudaMemcpyDeviceToHost, st));
-    CU(cudaFreeAsync(tmp, st));
     CU(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (*net->h_status != 0) return fail(TXH_E_WATCHDOG, "a routing launch bailed out on its dataflow watchdog");

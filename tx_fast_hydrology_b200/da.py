@@ -187,7 +187,8 @@ class EnsembleKalmanFilter(BaseCallback):
                    zeros if omitted (deterministic ensemble update)
     every        : pd.Timedelta cadence (e.g. hourly); None = every step as the reference (da.py:56-61)
     group        : torch.distributed process group when members are sharded over ranks (this rank
-                   holds columns [rank*M, (rank+1)*M) of the global ensemble)
+                   holds columns [rank*M, (rank+1)*M) of the global ensemble); None = the default group
+                   if torch.distributed is initialised; False = never sharded (independent ensembles)
     """
 
     def __init__(self, model, measurements, Q_diag, R_cov, obs_noise=None, every=None, group=None):
@@ -202,7 +203,9 @@ class EnsembleKalmanFilter(BaseCallback):
         self.every = every
         self.group = group
         self.rank, self.world = 0, 1
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if group is False:                     # this rank's ensemble is whole (e.g. one independent basin per rank)
+            self.group = group = None
+        elif group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.rank = torch.distributed.get_rank(group)
             self.world = torch.distributed.get_world_size(group)
         self.M = model.members
