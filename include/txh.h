@@ -114,6 +114,9 @@ int txh_init_inflows(txh_net* net, const double* O_dev, double* I_dev, int64_t M
  * member_mul (optional, host [R][M]): member m sees table[r][j]*member_mul[r][m]. */
 int txh_forcing_create(txh_net* net, int64_t R, const double* times, const double* table_host,
                        int64_t M, const double* member_mul_host, void* stream, txh_forcing** out);
+/* new values for an existing table of the same shape (a new forecast cycle): no allocation, one H2D copy */
+int txh_forcing_update(txh_forcing* f, const double* times, const double* table_host, const double* member_mul_host,
+                       void* stream);
 void txh_forcing_destroy(txh_forcing* f);
 
 /* ---- routing ---------------------------------------------------------------------------

@@ -214,3 +214,31 @@ def test_no_coeffs_is_an_error(torch_cuda, libtxh):
     O = net.alloc_state(1); I = net.alloc_state(1)
     with pytest.raises(TxhError):
         net.route_step(O, I, 1, None)
+
+
+def test_forcing_update_in_place(torch_cuda, libtxh):
+    """txh_forcing_update refreshes a resident table: the run equals one with a freshly created forcing."""
+    torch = torch_cuda
+    from tx_fast_hydrology_b200 import synthetic as S
+    from tx_fast_hydrology_b200.network import Forcing
+    n, seed, M, T = 3000, 17, 6, 20
+    net_d = S.make_network(n, seed)
+    prm = S.make_params(n, seed)
+    net, _ = _setup(net_d["endnodes"], prm["K"], prm["X"], 300.0)
+    t0 = 1_700_000_000 * 10**9
+    times, table = S.make_forcing(n, T, 300.0, seed, t0_ns=t0, rows_every=4)
+    mul = S.make_member_multipliers(times.size, M, seed)
+    rng = np.random.default_rng(seed)
+    o0 = prm["o_t"][:, None] * rng.uniform(0.5, 1.5, size=(n, M))
+    i0 = np.zeros_like(o0)
+    f = Forcing(net, times, 0.5 * table, 2.0 * mul)
+    f.update(times, table, mul)
+    O, I = _upload(torch, net, o0, i0, M)
+    net.route_run(O, I, M, f, t0, int(300e9), T)
+    g = Forcing(net, times, table, mul)
+    O2, I2 = _upload(torch, net, o0, i0, M)
+    net.route_run(O2, I2, M, g, t0, int(300e9), T)
+    net.check()
+    assert torch.equal(O, O2) and torch.equal(I, I2)
+    with pytest.raises(ValueError):
+        f.update(times[:-1], table[:-1], mul[:-1])

@@ -683,24 +683,44 @@ int txh_forcing_create(txh_net* net, int64_t R, const double* times, const doubl
     if (!f) return fail(TXH_E_INVALID, "out of memory");
     f->net = net; f->R = R; f->M = mul ? M : 0;
     f->times.assign(times, times + R);
-    // one H2D copy of the table as given (pinned or pageable), columns permuted into schedule
-    // order on the device
+    // one H2D copy of the table as given (pinned or pageable) into the handle's staging buffer, columns
+    // permuted into schedule order on the device
     double* tmp = nullptr;
+    if ((rc = stage_buffer(net, (size_t)R * n, st, &tmp))) { delete f; return rc; }
     cudaError_t e = cudaMalloc((void**)&f->d_F, sizeof(double) * R * n);
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_times, sizeof(double) * R);
     if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_times, f->times.data(), sizeof(double) * R, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&tmp, sizeof(double) * R * n);
     if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, table, sizeof(double) * R * n, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = launch_permute_rows(net->d_reach_of_pos, tmp, f->d_F, n, R, st);
     if (e == cudaSuccess && mul) {
-        if (M < 1) { cudaFree(f->d_F); cudaFree(f->d_times); cudaFree(tmp); delete f; return fail(TXH_E_INVALID, "member multipliers need M >= 1"); }
+        if (M < 1) { cudaFree(f->d_F); cudaFree(f->d_times); delete f; return fail(TXH_E_INVALID, "member multipliers need M >= 1"); }
         e = cudaMalloc((void**)&f->d_W, sizeof(double) * R * M);
         if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_W, mul, sizeof(double) * R * M, cudaMemcpyHostToDevice, st);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(tmp);
     if (e != cudaSuccess) { cudaFree(f->d_F); cudaFree(f->d_W); cudaFree(f->d_times); delete f; return cuda_fail(e, "forcing upload"); }
     *out = f;
+    return TXH_OK;
+}
+
+int txh_forcing_update(txh_forcing* f, const double* times, const double* table, const double* mul, void* stream)
+{
+    if (!f || !times || !table) return fail(TXH_E_INVALID, "null argument");
+    if ((mul != nullptr) != (f->d_W != nullptr)) return fail(TXH_E_INVALID, "member multipliers must stay present / absent");
+    txh_net* net = f->net;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = net->topo.n, R = f->R;
+    for (int64_t r = 1; r < R; ++r)
+        if (!(times[r] >= times[r - 1])) return fail(TXH_E_INVALID, "forcing times must be sorted ascending");
+    int rc;
+    double* tmp = nullptr;
+    if ((rc = stage_buffer(net, (size_t)R * n, st, &tmp))) return rc;
+    f->times.assign(times, times + R);
+    CU(cudaMemcpyAsync(f->d_times, f->times.data(), sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(tmp, table, sizeof(double) * R * n, cudaMemcpyHostToDevice, st));
+    CU(launch_permute_rows(net->d_reach_of_pos, tmp, f->d_F, n, R, st));
+    if (mul) CU(cudaMemcpyAsync(f->d_W, mul, sizeof(double) * R * f->M, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));          // `times` and pageable sources may be reused by the caller
     return TXH_OK;
 }
 

@@ -397,71 +397,84 @@ innovation_cat_kernel(const double* __restrict__ HX, const double* __restrict__ 
 // The system is padded with the identity up to MT (64 or 96) so that all register indices are static.
 constexpr int CS_NSPLIT = 8;
 
-template <int MT>
-__global__ void __launch_bounds__(8 * MT)
+template <int MT, int RG>
+__global__ void __launch_bounds__(RG * MT)
 chol_solve_small_kernel(const double* __restrict__ Cpart, long long pstride, int Mt, double shift,
                         double* __restrict__ Z, int* __restrict__ info)
 {
-    constexpr int R = MT / 8, LDU = MT + 1;
+    // thread (rg, c) = (tid / MT, tid % MT) owns rows {RG*r + rg} of column c of A; NB elements of this CTA's
+    // 8 columns of B: element u is row (tid + u*NT) / 8, column (tid + u*NT) % 8
+    constexpr int R = MT / RG, LDU = MT + 1, NT = RG * MT, NB = 8 / RG;
     extern __shared__ double sm[];
     double* U = sm;                       // [MT][MT+1]  U[j][i] = L[i][j], i > j
     double* bc = U + MT * LDU;            // [2][MT + 9] per-step broadcast (column of A, row of B, 1/sqrt(pivot))
     double* invd = bc + 2 * (MT + 9);     // [MT]        1 / L[j][j]
     const int tid = threadIdx.x;
-    const int c = tid % MT, rg = tid / MT;            // A: rows {8r + rg} of column c
-    const int bi = tid >> 3, bcol = tid & 7;          // B: one element, row bi of this CTA's column bcol
+    const int c = tid % MT, rg = tid / MT;
+    const int bcol = tid & 7;
     const int gcol = blockIdx.x * 8 + bcol;
     const int warp0 = (tid & ~31) % MT;               // first column of this warp's 32 columns
-    double a[R], b = 0.0;
+    double a[R], b[NB];
 #pragma unroll
     for (int r = 0; r < R; ++r) a[r] = 0.0;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) b[u] = 0.0;
 #pragma unroll
     for (int s = 0; s < CS_NSPLIT; ++s) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int i = 8 * r + rg;
+            const int i = RG * r + rg;
             if (i < Mt && c < Mt) a[r] += Cpart[(size_t)s * pstride + (size_t)i * 2 * Mt + c];
         }
-        if (bi < Mt && gcol < Mt) b += Cpart[(size_t)s * pstride + (size_t)bi * 2 * Mt + Mt + gcol];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int bi = (tid + u * NT) >> 3;
+            if (bi < Mt && gcol < Mt) b[u] += Cpart[(size_t)s * pstride + (size_t)bi * 2 * Mt + Mt + gcol];
+        }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int i = 8 * r + rg;
+        const int i = RG * r + rg;
         if (i == c) a[r] = (i < Mt) ? a[r] + shift : 1.0;
     }
     // ---- factor + forward substitution ----
 #pragma unroll
     for (int pb = 0; pb < R; ++pb) {
-        for (int pr = 0; pr < 8; ++pr) {
-            const int j = 8 * pb + pr;
+        for (int pr = 0; pr < RG; ++pr) {
+            const int j = RG * pb + pr;
             double* cb = bc + (j & 1) * (MT + 9);
             double* brow = cb + MT;
             if (c == j) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) cb[8 * r + rg] = a[r];       // rows < j carry junk that nobody reads
+                for (int r = 0; r < R; ++r) cb[RG * r + rg] = a[r];      // rows < j carry junk that nobody reads
                 if (rg == pr) {
-                    // the pivot's owner alone takes the reciprocal square root (the FP64 pipe is narrow: sixteen
-                    // warps repeating it would cost more than the barrier)
+                    // the pivot's owner alone takes the reciprocal square root
                     double d = a[pb];
                     if (!(d > 0.0)) { if (blockIdx.x == 0) *info = j + 1; d = 1.0; }
                     const double r1 = rsqrt(d);
                     cb[MT + 8] = r1; invd[j] = r1;
                 }
             }
-            if (bi == j) brow[bcol] = b;
+#pragma unroll
+            for (int u = 0; u < NB; ++u) if (((tid + u * NT) >> 3) == j) brow[bcol] = b[u];
             __syncthreads();
             const double rs = cb[MT + 8], rs2 = rs * rs;
-            if (bi == j) b *= rs;
-            else if (bi > j) b -= cb[bi] * (brow[bcol] * rs2);
+            const double bj = brow[bcol] * rs2;
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int bi = (tid + u * NT) >> 3;
+                if (bi == j) b[u] *= rs;
+                else if (bi > j) b[u] -= cb[bi] * bj;
+            }
             if (c == j) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) { const int i = 8 * r + rg; if (i > j) U[j * LDU + i] = a[r] * rs; }
+                for (int r = 0; r < R; ++r) { const int i = RG * r + rg; if (i > j) U[j * LDU + i] = a[r] * rs; }
             }
             if (warp0 + 31 > j) {                                        // some column of this warp is right of j
                 const double fa = c > j ? cb[c] * rs2 : 0.0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const int i = 8 * r + rg;
+                    const int i = RG * r + rg;
                     if ((r > pb || (r == pb && rg > pr)) && i >= c) a[r] -= cb[i] * fa;
                 }
             }
@@ -471,11 +484,21 @@ chol_solve_small_kernel(const double* __restrict__ Cpart, long long pstride, int
     // ---- backward: L^T Z = Y ----
     for (int p = MT - 1; p >= 0; --p) {
         double* zrow = bc + (p & 1) * (MT + 9) + MT;
-        if (bi == p) { b *= invd[p]; zrow[bcol] = b; }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) if (((tid + u * NT) >> 3) == p) { b[u] *= invd[p]; zrow[bcol] = b[u]; }
         __syncthreads();
-        if (bi < p) b -= U[bi * LDU + p] * zrow[bcol];
+        const double z = zrow[bcol];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int bi = (tid + u * NT) >> 3;
+            if (bi < p) b[u] -= U[bi * LDU + p] * z;
+        }
     }
-    if (bi < Mt && gcol < Mt) Z[(size_t)bi * Mt + gcol] = b;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        const int bi = (tid + u * NT) >> 3;
+        if (bi < Mt && gcol < Mt) Z[(size_t)bi * Mt + gcol] = b[u];
+    }
 }
 
 // sum of the split-K partials of C = [C0 | C1] -> Cf = C0 + shift*I and C1 as two dense Mt x Mt matrices
@@ -602,6 +625,128 @@ enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const dou
     }
 }
 
+// The common case of the above -- the whole ensemble is this shard's (Xall == O's layout, Mtot = Mloc <= 64):
+// T is staged once per CTA; every warp streams its 16-row tiles through a double-buffered shared-memory
+// stage (cp.async, the next tile in flight while the tensor cores work on the current one) and reads both
+// the A fragments and, in the epilogue, the old outflows from it, so O is read from global memory once.
+constexpr int EU_RS = 576;                       // bytes per staged row: 512 + 64, conflict-free 128-bit reads
+constexpr int EU64_SMEM = 64 * EU_LDT * 8 + EU_WARPS * 2 * 16 * EU_RS;
+
+__global__ void __launch_bounds__(EU_WARPS * 32, 1)
+enkf_update64_kernel(const double* __restrict__ X, int M, const double* __restrict__ mean, const double* __restrict__ T,
+                     int ldt, double* __restrict__ O, double* __restrict__ G, int ld, long long n,
+                     const int32_t* __restrict__ gauge_of_pos, const double* __restrict__ qs,
+                     const double* __restrict__ W)
+{
+    extern __shared__ __align__(16) unsigned char eu_smem[];
+    double* sT = reinterpret_cast<double*>(eu_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const unsigned stage0 = (unsigned)__cvta_generic_to_shared(eu_smem + 64 * EU_LDT * 8 + warp * 2 * 16 * EU_RS);
+    const long long ntiles = (n + 15) / 16;
+    const long long tstride = (long long)gridDim.x * EU_WARPS;
+    long long tile = (long long)blockIdx.x * EU_WARPS + warp;
+    auto prefetch = [&](long long tl, int buf) {
+        if (tl < ntiles && 2 * lane < ld) {
+            const long long r0 = tl * 16;
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (r0 + r < n) {
+                    const unsigned sa = stage0 + (buf * 16 + r) * EU_RS + lane * 16;
+                    const double* gp = X + (size_t)(r0 + r) * ld + 2 * lane;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gp) : "memory");
+                }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(tile, 0);
+    {
+        // all 16 loads of a thread are in flight before the first store
+        double tv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int e = tid + u * EU_WARPS * 32;
+            const int k = e >> 6, c = e & 63;
+            tv[u] = (k < M && c < M) ? __ldg(T + (size_t)k * ldt + c) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int e = tid + u * EU_WARPS * 32;
+            sT[(e >> 6) * EU_LDT + (e & 63)] = tv[u];
+        }
+    }
+    __syncthreads();
+    int buf = 0;
+    for (; tile < ntiles; tile += tstride, buf ^= 1) {
+        prefetch(tile + tstride, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const long long rw = tile * 16;
+        const long long rows[2] = {rw + g, rw + 8 + g};
+        double mu[2];
+        int gi[2];
+        double a[2][16];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const bool ok = rows[i] < n;
+            mu[i] = ok ? mean[rows[i]] : 0.0;
+            gi[i] = ok ? gauge_of_pos[rows[i]] : -1;
+            const unsigned ra = stage0 + (buf * 16 + 8 * i + g) * EU_RS + t * 16;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = 8 * j + 2 * t;
+                double2 v = make_double2(0.0, 0.0);
+                if (ok && k < ld) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ra + j * 64));
+                a[i][2 * j] = (ok && k < M) ? v.x - mu[i] : 0.0;
+                a[i][2 * j + 1] = (ok && k + 1 < M) ? v.y - mu[i] : 0.0;
+            }
+        }
+        double acc[2][8][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+            const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
+            const double* bt = sT + k * EU_LDT + g;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double b = bt[8 * j];
+                dmma8x8x4(acc[0][j][0], acc[0][j][1], a[0][ks], b);
+                dmma8x8x4(acc[1][j][0], acc[1][j][1], a[1][ks], b);
+            }
+        }
+        // epilogue: G = gain (+ the Q[:, s] term on gauged rows, da.py:117-121), O = old outflow + gain
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (rows[i] >= n) continue;
+            const double qg = gi[i] >= 0 ? qs[gi[i]] : 0.0;
+            const double* wr = W + (size_t)(gi[i] >= 0 ? gi[i] : 0) * M;
+            const unsigned ra = stage0 + (buf * 16 + 8 * i + g) * EU_RS + t * 16;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = 8 * j + 2 * t;
+                if (col >= ld) continue;
+                double2 gn = make_double2(col < M ? acc[i][j][0] : 0.0, col + 1 < M ? acc[i][j][1] : 0.0);
+                if (gi[i] >= 0) {
+                    if (col < M) gn.x += qg * wr[col];
+                    if (col + 1 < M) gn.y += qg * wr[col + 1];
+                }
+                if (O) {
+                    double2 o;
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o.x), "=d"(o.y) : "r"(ra + j * 64));
+                    o.x += gn.x; o.y += gn.y;
+                    *reinterpret_cast<double2*>(O + (size_t)rows[i] * ld + col) = o;
+                }
+                *reinterpret_cast<double2*>(G + (size_t)rows[i] * ld + col) = gn;
+            }
+        }
+        __syncwarp();                                 // everyone is done with this buffer before it is refilled
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // inflow part of _apply_gain (nutils.py:116-134, da.py:125): I[k] += sum of the gains of the reaches
 // draining into k (self-loops excluded).  One thread per (row, member pair).
 __global__ void __launch_bounds__(256)
@@ -710,14 +855,15 @@ cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long p
     const size_t smem = ((size_t)MT * (MT + 1) + 2 * (MT + 9) + MT) * sizeof(double);
     const int ncta = (Mt + 7) / 8;                      // 8 right-hand-side columns per CTA
     cudaError_t e;
+    constexpr int RG = 8;                               // 8*MT threads (4*MT measured slower: 76 vs 58 us at MT = 64)
     if (MT == 64) {
-        e = cudaFuncSetAttribute(chol_solve_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(chol_solve_small_kernel<64, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        chol_solve_small_kernel<64><<<ncta, 8 * 64, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
+        chol_solve_small_kernel<64, RG><<<ncta, RG * 64, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
     } else {
-        e = cudaFuncSetAttribute(chol_solve_small_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(chol_solve_small_kernel<96, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        chol_solve_small_kernel<96><<<ncta, 8 * 96, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
+        chol_solve_small_kernel<96, RG><<<ncta, RG * 96, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
     }
     count_launch();
     return cudaGetLastError();
@@ -805,6 +951,15 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
                                const double* qs, const double* W, int col0, int num_sms, cudaStream_t st)
 {
     long long tiles = (n + EU_ROWS - 1) / EU_ROWS;
+    if (Mtot == Mloc && Mtot <= 64 && ld <= 64 && ldx == ld && col0 == 0) {
+        cudaError_t e = cudaFuncSetAttribute(enkf_update64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EU64_SMEM);
+        if (e != cudaSuccess) return e;
+        const long long grid2 = tiles < (long long)num_sms ? tiles : (long long)num_sms;
+        enkf_update64_kernel<<<(unsigned)grid2, EU_WARPS * 32, EU64_SMEM, st>>>(Xall, Mtot, mean, T, ldt, O, G, ld, n,
+                                                                               gauge_of_pos, qs, W);
+        count_launch();
+        return cudaGetLastError();
+    }
     long long grid = tiles < (long long)num_sms ? tiles : (long long)num_sms;
     enkf_update_kernel<<<(unsigned)grid, EU_WARPS * 32, 0, st>>>(Xall, ldx, Mtot, mean, T, ldt, Mloc, O, G, ld, n,
                                                                  gauge_of_pos, qs, W, col0);

@@ -54,6 +54,19 @@ class Forcing:
         a = L.as_f64(a)
         return ctypes.c_void_p(a.ctypes.data), a.shape, a
 
+    def update(self, times_ns, table, member_mul=None):
+        """New values for the resident table (same shape): one host->device copy, no allocation."""
+        times = L.as_f64(np.asarray(times_ns).astype(np.float64))
+        tptr, tshape, keep_t = self._host_ptr(table)
+        if tshape != (self.R, self.net.n) or times.size != self.R:
+            raise ValueError("forcing update must keep the table shape")
+        mp, keep_m = None, None
+        if member_mul is not None:
+            mp, mshape, keep_m = self._host_ptr(member_mul)
+            if mshape != (self.R, self.M):
+                raise ValueError("member multipliers must keep their shape")
+        L.check(L.load().txh_forcing_update(self.handle, L.ptr_f64(times), tptr, mp, _stream_ptr()))
+
     def close(self):
         if getattr(self, "handle", None):
             L.load().txh_forcing_destroy(self.handle)
