@@ -240,3 +240,64 @@ def test_run_assimilating_vs_oracle(oracle, n, M, m, seed):
         o = np.ascontiguousarray(Op.T); i = np.ascontiguousarray(Ip.T)
     assert relerr(mdl.o_t_next, o.T) < RTOL
     assert relerr(mdl.i_t_next, i.T) < RTOL
+
+
+def test_headline_window_full_size(oracle):
+    """BASELINE.json configs[2] at FULL size -- 100,000 reaches, 64 members, 500 gauges: one hourly window
+    (12 routing steps in one window launch) and one EnKF update against the CPU oracle, plus two
+    size-independent properties of the update: observations equal to the forecast leave the ensemble
+    unchanged, and the update commutes with a permutation of the members."""
+    import torch
+    from tx_fast_hydrology_b200 import synthetic as S
+    from tx_fast_hydrology_b200.muskingum import Muskingum
+    from tx_fast_hydrology_b200.da import EnsembleKalmanFilter
+    n, M, m, seed, every = 100_000, 64, 500, 2, 12
+    net_d = S.make_network(n, seed)
+    prm = S.make_params(n, seed)
+    rng = np.random.default_rng(seed + 7)
+    o0 = prm["o_t"][:, None] * rng.uniform(0.5, 1.5, size=(n, M))
+    d = S.model_dict(net_d, prm, dt_s=300.0)
+    d["o_t"] = o0
+    mdl = Muskingum(d, members=M)
+    t0 = int(mdl.datetime.value)
+    times, table = S.make_forcing(n, every, 300.0, seed, t0_ns=t0)
+    mul = S.make_member_multipliers(times.size, M, seed)
+    gidx = S.make_gauges(net_d["endnodes"], m, seed=4)
+    mdf = frame(np.array([t0 + int(every * 300e9)], dtype=np.int64), rng.uniform(0.5, 8.0, size=(1, m)),
+                [d["reach_ids"][j] for j in gidx])
+    R = 1e-2 * np.eye(m)
+    enkf = EnsembleKalmanFilter(mdl, mdf, 2.0, R)
+    f = mdl.make_forcing(times_ns=times, table=table, member_mul=mul)
+    # forecast on both sides
+    mdl.run(f, every)
+    mdl.network.check()
+    ind = oracle.compute_indegree(net_d["startnodes"], net_d["endnodes"])
+    al, be, ch, ga = oracle.compute_coeffs(prm["K"], prm["X"], 300.0)
+    onet = {"startnodes": net_d["startnodes"], "endnodes": net_d["endnodes"], "indegree": ind,
+            "alpha": al, "beta": be, "chi": ch, "gamma": ga}
+    o = np.ascontiguousarray(o0.T)
+    i = np.stack([oracle.init_states(net_d["startnodes"], net_d["endnodes"], x) for x in o])
+    oracle.run_members(onet, o, i, every, times.astype(np.float64), table, float(t0), 300e9, wmul=mul)
+    assert relerr(mdl.o_t_next, o.T) < RTOL and relerr(mdl.i_t_next, i.T) < RTOL
+    O_d, I_d = mdl.device_state
+    Of, If = O_d.clone(), I_d.clone()
+    # (a) zero innovation: Zp == H x  ->  nothing moves
+    HX = torch.as_tensor(np.ascontiguousarray(o.T[gidx]), device="cuda")
+    enkf.filter(HX)
+    mdl.network.check()
+    assert (O_d - Of).abs().max().item() <= 1e-12 * Of.abs().max().item()
+    assert (I_d - If).abs().max().item() <= 1e-12 * If.abs().max().item()
+    # (b) the real update vs the oracle
+    mdl.upload_state(np.ascontiguousarray(o.T), np.ascontiguousarray(i.T))
+    Zp = np.ascontiguousarray(mdf.values[0][:, None] + 0.1 * rng.standard_normal((m, M)))
+    enkf.filter(torch.as_tensor(Zp, device="cuda"))
+    mdl.network.check()
+    Op, Ip, _ = oracle.enkf_update(onet, o.T, i.T, gidx, Zp, np.full(n, 2.0), R)
+    o_gpu, i_gpu = mdl.o_t_next.copy(), mdl.i_t_next.copy()
+    assert relerr(o_gpu, Op) < RTOL and relerr(i_gpu, Ip) < RTOL
+    # (c) member permutation: update(P x, P z) == P update(x, z)
+    perm = rng.permutation(M)
+    mdl.upload_state(np.ascontiguousarray(o.T[:, perm]), np.ascontiguousarray(i.T[:, perm]))
+    enkf.filter(torch.as_tensor(np.ascontiguousarray(Zp[:, perm]), device="cuda"))
+    mdl.network.check()
+    assert relerr(mdl.o_t_next, o_gpu[:, perm]) < 1e-10

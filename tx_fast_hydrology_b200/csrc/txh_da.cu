@@ -501,6 +501,172 @@ chol_solve_small_kernel(const double* __restrict__ Cpart, long long pstride, int
     }
 }
 
+// Blocked variant of the small solve, the one in use: the matrix lives in shared memory, panels of 8 columns.
+//   panel   : warp 0 keeps the panel rows in registers (lane l owns rows j0+l, j0+l+32, ...) and factors the 8
+//             columns with shuffles -- no barrier inside a panel -- then solves the 8 matching rows of B;
+//   trailing: every warp takes 8x8 tiles of the lower triangle (and of B) and applies the rank-8 update with
+//             two FP64 tensor-core MMAs per tile;
+// two barriers per panel instead of one per column; the backward substitution is blocked the same way.
+// Right-hand sides are split over CTAs, 8 columns each (every CTA repeats the factorisation).
+template <int MT>
+__global__ void __launch_bounds__(256)
+chol_solve_blocked_kernel(const double* __restrict__ Cpart, long long pstride, int Mt, double shift,
+                          double* __restrict__ Z, int* __restrict__ info)
+{
+    constexpr int LD = MT + 1, NT = MT / 8, RPL = MT / 32, LDB = 9;
+    extern __shared__ double sm[];
+    double* A = sm;                       // [MT][MT+1], lower triangle: working matrix, then L
+    double* Bs = A + MT * LD;             // [MT][9]     this CTA's 8 right-hand-side columns
+    double* invd = Bs + MT * LDB;         // [MT]        1 / L[j][j]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int gc0 = blockIdx.x * 8;
+    // 4 elements x 8 partials in flight per thread
+    for (int e0 = 0; e0 < MT * MT; e0 += 4 * 256) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * 256 + tid;
+            const int i = e / MT, c = e - i * MT;
+            v[u] = (i == c) ? 1.0 : 0.0;
+            if (e < MT * MT && i < Mt && c < Mt) {
+                v[u] = (i == c) ? shift : 0.0;
+#pragma unroll
+                for (int s = 0; s < CS_NSPLIT; ++s) v[u] += Cpart[(size_t)s * pstride + (size_t)i * 2 * Mt + c];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * 256 + tid;
+            if (e < MT * MT) A[(e / MT) * LD + (e % MT)] = v[u];
+        }
+    }
+    for (int e = tid; e < MT * 8; e += 256) {
+        const int i = e >> 3, cl = e & 7;
+        double v = 0.0;
+        if (i < Mt && gc0 + cl < Mt) {
+#pragma unroll
+            for (int s = 0; s < CS_NSPLIT; ++s) v += Cpart[(size_t)s * pstride + (size_t)i * 2 * Mt + Mt + gc0 + cl];
+        }
+        Bs[i * LDB + cl] = v;
+    }
+    __syncthreads();
+    // ---- factorisation + forward substitution, panel by panel ----
+    for (int p = 0; p < NT; ++p) {
+        const int j0 = 8 * p;
+        if (warp == 0) {
+            double x[RPL][8];
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) {
+                const int i = j0 + lane + 32 * q;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) x[q][cc] = i < MT ? A[i * LD + j0 + cc] : 0.0;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                double d = __shfl_sync(0xffffffffu, x[0][jj], jj);              // pivot: row j0+jj lives in lane jj
+                if (!(d > 0.0)) { if (lane == 0 && blockIdx.x == 0) *info = j0 + jj + 1; d = 1.0; }
+                const double rs = rsqrt(d);
+                if (lane == 0) invd[j0 + jj] = rs;
+                double l[RPL];
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    l[q] = x[q][jj] * rs;
+                    if (lane + 32 * q >= jj) x[q][jj] = l[q];                    // rows at or below the pivot
+                }
+#pragma unroll
+                for (int cc = jj + 1; cc < 8; ++cc) {
+                    const double lc = __shfl_sync(0xffffffffu, l[0], cc);        // L[j0+cc][j0+jj]
+#pragma unroll
+                    for (int q = 0; q < RPL; ++q)
+                        if (lane + 32 * q >= cc) x[q][cc] -= l[q] * lc;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) {
+                const int i = j0 + lane + 32 * q;
+                if (i < MT)
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc)
+                        if (lane + 32 * q >= cc) A[i * LD + j0 + cc] = x[q][cc];
+            }
+            __syncwarp();
+            // the 8 matching rows of B: Y = L11^-1 B1 (lane cl < 8 owns column cl)
+            if (lane < 8) {
+                double y[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    double v = Bs[(j0 + jj) * LDB + lane];
+#pragma unroll
+                    for (int k = 0; k < jj; ++k) v -= A[(j0 + jj) * LD + j0 + k] * y[k];
+                    y[jj] = v * invd[j0 + jj];
+                }
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) Bs[(j0 + jj) * LDB + lane] = y[jj];
+            }
+        }
+        __syncthreads();
+        // trailing update: tiles (it, ct), p < ct <= it < NT, of A, then one tile per it of B
+        const int Tn = NT - p - 1;
+        const int ntile = Tn * (Tn + 1) / 2 + Tn;
+        for (int e = warp; e < ntile; e += 8) {
+            int it, ct;
+            bool isB = false;
+            if (e < Tn * (Tn + 1) / 2) {
+                it = 0;
+                int rem = e;
+                while (rem > it) { rem -= it + 1; ++it; }                        // row it has it+1 tiles
+                ct = p + 1 + rem; it = p + 1 + it;
+            } else { it = p + 1 + (e - Tn * (Tn + 1) / 2); ct = 0; isB = true; }
+            double c0, c1;
+            double* cp = isB ? Bs + (8 * it + g) * LDB + 2 * t : A + (8 * it + g) * LD + 8 * ct + 2 * t;
+            c0 = cp[0]; c1 = cp[1];
+#pragma unroll
+            for (int kk = 0; kk < 8; kk += 4) {
+                const double af = -A[(8 * it + g) * LD + j0 + kk + t];
+                const double bf = isB ? Bs[(j0 + kk + t) * LDB + g] : A[(8 * ct + g) * LD + j0 + kk + t];
+                dmma8x8x4(c0, c1, af, bf);
+            }
+            cp[0] = c0; cp[1] = c1;
+        }
+        __syncthreads();
+    }
+    // ---- backward substitution L^T Z = Y ----
+    for (int p = NT - 1; p >= 0; --p) {
+        const int j0 = 8 * p;
+        if (warp == 0 && lane < 8) {
+            double z[8];
+#pragma unroll
+            for (int jj = 7; jj >= 0; --jj) {
+                double v = Bs[(j0 + jj) * LDB + lane];
+#pragma unroll
+                for (int k = 7; k > jj; --k) v -= A[(j0 + k) * LD + j0 + jj] * z[k];
+                z[jj] = v * invd[j0 + jj];
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) Bs[(j0 + jj) * LDB + lane] = z[jj];
+        }
+        __syncthreads();
+        // rows above: B[it] -= L[p][it]^T Z[p]
+        for (int it = warp; it < p; it += 8) {
+            double* cp = Bs + (8 * it + g) * LDB + 2 * t;
+            double c0 = cp[0], c1 = cp[1];
+#pragma unroll
+            for (int kk = 0; kk < 8; kk += 4) {
+                const double af = -A[(j0 + kk + t) * LD + 8 * it + g];
+                const double bf = Bs[(j0 + kk + t) * LDB + g];
+                dmma8x8x4(c0, c1, af, bf);
+            }
+            cp[0] = c0; cp[1] = c1;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < MT * 8; e += 256) {
+        const int i = e >> 3, cl = e & 7;
+        if (i < Mt && gc0 + cl < Mt) Z[(size_t)i * Mt + gc0 + cl] = Bs[i * LDB + cl];
+    }
+}
+
 // sum of the split-K partials of C = [C0 | C1] -> Cf = C0 + shift*I and C1 as two dense Mt x Mt matrices
 __global__ void __launch_bounds__(256)
 woodbury_assemble_kernel(const double* __restrict__ Cpart, int nsplit, long long pstride, int Mt, double shift,
@@ -855,15 +1021,16 @@ cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long p
     const size_t smem = ((size_t)MT * (MT + 1) + 2 * (MT + 9) + MT) * sizeof(double);
     const int ncta = (Mt + 7) / 8;                      // 8 right-hand-side columns per CTA
     cudaError_t e;
-    constexpr int RG = 8;                               // 8*MT threads (4*MT measured slower: 76 vs 58 us at MT = 64)
+    const size_t smem_b = ((size_t)MT * (MT + 1) + (size_t)MT * 9 + MT) * sizeof(double);
+    (void)smem;
     if (MT == 64) {
-        e = cudaFuncSetAttribute(chol_solve_small_kernel<64, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(chol_solve_blocked_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
         if (e != cudaSuccess) return e;
-        chol_solve_small_kernel<64, RG><<<ncta, RG * 64, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
+        chol_solve_blocked_kernel<64><<<ncta, 256, smem_b, st>>>(Cpart, pstride, Mt, shift, Z, info);
     } else {
-        e = cudaFuncSetAttribute(chol_solve_small_kernel<96, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(chol_solve_blocked_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
         if (e != cudaSuccess) return e;
-        chol_solve_small_kernel<96, RG><<<ncta, RG * 96, smem, st>>>(Cpart, pstride, Mt, shift, Z, info);
+        chol_solve_blocked_kernel<96><<<ncta, 256, smem_b, st>>>(Cpart, pstride, Mt, shift, Z, info);
     }
     count_launch();
     return cudaGetLastError();
