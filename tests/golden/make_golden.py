@@ -167,7 +167,57 @@ def checkpoint():
     print("checkpoint_n80.npz ok")
 
 
+def split_collection():
+    """Muskingum.split + AsyncSimulation (muskingum.py:607-714, simulation.py:94-166): a network cut at
+    three reaches, hourly step with forcing rows aligned 1:1 with the steps, the sub-models'
+    hydrographs, and the un-split run they must reproduce."""
+    import asyncio
+    from tx_fast_hydrology.simulation import AsyncSimulation
+    n, T, seed = 300, 24, 31
+    net = S.make_network(n, seed)
+    prm = S.make_params(n, seed)
+    d = S.model_dict(net, prm, dt_s=3600.0, t0=T0)
+    d["dx"] = np.ones(n)
+    d["paths"] = [[0.0] for _ in range(n)]
+    mdl = Muskingum(d)
+    t0_ns = mdl.datetime.value
+    rng = np.random.default_rng(seed + 3)
+    times = t0_ns + (np.arange(T, dtype=np.int64) + 1) * int(3600e9)
+    table = rng.gamma(0.5, 2.0, size=(T, n))
+    df = frame(times, table, d["reach_ids"])
+    # cut at three non-outlet reaches with a decent subtree above them
+    order = np.argsort(-np.bincount(net["endnodes"], minlength=n) - rng.uniform(0, 0.5, n))
+    cuts = [int(j) for j in order if net["endnodes"][j] != j][:3]
+    mc = mdl.split(cuts, create_state_space=False)
+    names = list(mc.models.keys())
+    sub_reach = {k: np.asarray([int(r) for r in mc.models[k].reach_ids]) for k in names}
+    sub_i0 = {k: mc.models[k].i_t_next.copy() for k in names}
+    sub_indeg = {k: mc.models[k].indegree.copy() for k in names}
+    conns = []
+    for k in names:
+        for c in mc.models[k].sinks:
+            conns.append([int(c.upstream_model.name), int(c.downstream_model.name), int(c.upstream_index),
+                          int(c.downstream_index)])
+    sim = AsyncSimulation(mc, df)
+    outputs = asyncio.run(sim.simulate())
+    # un-split run
+    ref = Muskingum(d)
+    whole = [ref.o_t_next.copy()]
+    for state in ref.simulate(df):
+        whole.append(state.o_t_next.copy())
+    out = dict(endnodes=mdl.endnodes, K=mdl.K, X=mdl.X, o_init=prm["o_t"], dt=3600.0, t0_ns=t0_ns, times=times,
+               table=table, cuts=np.asarray(cuts), n_models=len(names), connections=np.asarray(sorted(conns)),
+               whole=np.stack(whole))
+    for k in names:
+        out[f"reach_{k}"] = sub_reach[k]; out[f"i0_{k}"] = sub_i0[k]; out[f"indegree_{k}"] = sub_indeg[k]
+        out[f"out_{k}"] = outputs[k].values
+        out[f"out_times_{k}"] = outputs[k].index.astype("int64").values
+    np.savez_compressed(os.path.join(HERE, "split_n300.npz"), **out)
+    print("split_n300.npz ok", len(names), "models", conns)
+
+
 if __name__ == "__main__":
+    split_collection()
     kernels(60, 7, "kernels_n60.npz")
     kernels(160, 8, "kernels_n160.npz")
     model_c1()

@@ -1,0 +1,85 @@
+"""`Muskingum.split` / `ModelCollection` / `AsyncSimulation` against the golden
+vectors of the unmodified reference (tests/golden/split_n300.npz, made by make_golden.split_collection)."""
+import asyncio
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+RTOL = 1e-9
+
+
+def relerr(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max()) / max(1e-300, float(np.abs(b).max()))
+
+
+def _model(g):
+    from tx_fast_hydrology_b200.muskingum import Muskingum
+    n = g["endnodes"].size
+    d = {"name": "golden", "datetime": pd.Timestamp(int(g["t0_ns"]), tz="UTC"),
+         "timedelta": pd.to_timedelta(float(g["dt"]), unit="s"), "reach_ids": [str(i) for i in range(n)],
+         "startnodes": np.arange(n, dtype=np.int64), "endnodes": g["endnodes"].astype(np.int64),
+         "K": g["K"].astype(np.float64), "X": g["X"].astype(np.float64), "o_t": g["o_init"].astype(np.float64),
+         "dx": np.ones(n), "paths": [[0.0] for _ in range(n)]}
+    return Muskingum(d), d
+
+
+def _frame(g, cols):
+    idx = pd.DatetimeIndex(pd.to_datetime(g["times"], unit="ns", utc=True)).as_unit("ns")
+    return pd.DataFrame(g["table"], index=idx, columns=cols)
+
+
+def test_split_structure(libtxh, golden_dir, tmp_path):
+    """Components, their numbering, reach membership, inflow correction and connections (host only)."""
+    from tx_fast_hydrology_b200.muskingum import ModelCollection
+    g = np.load(os.path.join(golden_dir, "split_n300.npz"))
+    mdl, d = _model(g)
+    mc = mdl.split([int(c) for c in g["cuts"]])
+    assert list(mc.models.keys()) == [str(k) for k in range(int(g["n_models"]))]
+    conns = []
+    for k, sub in mc.models.items():
+        assert ([int(r) for r in sub.reach_ids] == g[f"reach_{k}"]).all()
+        assert (sub.indegree == g[f"indegree_{k}"]).all()                   # exact integers
+        assert relerr(sub.i_t_next, g[f"i0_{k}"]) < 1e-15
+        assert (sub.startnodes == np.arange(sub.n)).all()
+        for c in sub.sinks:
+            conns.append([int(c.upstream_model.name), int(c.downstream_model.name), int(c.upstream_index),
+                          int(c.downstream_index)])
+    assert (np.asarray(sorted(conns)) == g["connections"]).all()
+    assert mc.datetime == mdl.datetime and mc.timedelta == mdl.timedelta
+    # JSON round trip of the collection keeps models and wiring
+    path = str(tmp_path / "collection.json")
+    mc.dump_model_collection(path)
+    mc2 = ModelCollection.from_file(path)
+    assert list(mc2.models.keys()) == list(mc.models.keys())
+    for k in mc.models:
+        assert (mc2.models[k].K == mc.models[k].K).all() and mc2.models[k].reach_ids == mc.models[k].reach_ids
+        assert len(mc2.models[k].sinks) == len(mc.models[k].sinks)
+        assert len(mc2.models[k].sources) == len(mc.models[k].sources)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_callback", [False, True])
+def test_async_simulation_matches_reference(libtxh, golden_dir, with_callback):
+    """Sub-model hydrographs == the reference's AsyncSimulation, and together == the un-split run; once through
+    the device-resident fast path and once through the per-step path (a callback bound to every sub-model)."""
+    from tx_fast_hydrology_b200.simulation import AsyncSimulation, CheckPoint
+    g = np.load(os.path.join(golden_dir, "split_n300.npz"))
+    mdl, d = _model(g)
+    df = _frame(g, d["reach_ids"])
+    mc = mdl.split([int(c) for c in g["cuts"]])
+    if with_callback:
+        for sub in mc.models.values():
+            sub.bind_callback(CheckPoint(sub, timedelta=7200), key="checkpoint")
+    sim = AsyncSimulation(mc, df)
+    outputs = asyncio.run(sim.simulate())
+    whole = np.empty_like(g["whole"])
+    for k, sub in mc.models.items():
+        out = outputs[k]
+        # the reference's frame carries a microsecond index (pandas 3 default unit); compare instants
+        assert (out.index.as_unit("ns").astype("int64").values == g[f"out_times_{k}"] * 1000).all()
+        assert relerr(out.values, g[f"out_{k}"]) < RTOL
+        whole[:, g[f"reach_{k}"]] = out.values
+    assert relerr(whole, g["whole"]) < RTOL
+    assert mc.datetime.value == int(g["times"][-1])

@@ -488,6 +488,166 @@ class Muskingum:
         return new
 
 
+    def split(self, indices, name=None, create_state_space=False):
+        """Cut the network at the reaches `indices` (muskingum.py:607-714): every weakly connected piece of
+        the cut forest becomes its own model (named "0", "1", ... in component order), wired by one-way
+        `Connection`s.  The downstream model loses the cut reach's contribution to its inflow state, so the
+        collection stepped with `AsyncSimulation` reproduces the un-split run.  Returns a `ModelCollection`."""
+        from scipy.sparse import coo_matrix, csgraph
+        if create_state_space:
+            raise NotImplementedError('dense state-space matrices are not built by the GPU drop-in')
+        if self.members != 1:
+            raise ValueError('split() needs a single-member model')
+        n = self.n
+        end = self.endnodes.copy()
+        cut = np.asarray(indices, dtype=np.int64).reshape(-1)
+        if cut.size and (cut.min() < 0 or cut.max() >= n):
+            raise ValueError('split index out of range')
+        cut_down = end[cut].copy()                       # the reach each cut reach used to drain into
+        end[cut] = cut                                   # cut reaches become outlets
+        adj = coo_matrix((np.ones(n, dtype=np.int8), (end, np.arange(n))), shape=(n, n))
+        n_comp, labels = csgraph.connected_components(adj)
+        o_next, i_next = self.o_t_next, self.i_t_next
+        o_prev, i_prev = self.o_t_prev, self.i_t_prev
+        models, local_index = [], np.empty(n, dtype=np.int64)
+        for comp in range(n_comp):
+            sel = np.flatnonzero(labels == comp)
+            local_index[sel] = np.arange(sel.size)
+            d = {'name': str(comp), 'datetime': self.datetime, 'timedelta': self.timedelta,
+                 'reach_ids': [self.reach_ids[j] for j in sel],
+                 'startnodes': np.arange(sel.size, dtype=np.int64), 'endnodes': local_index[end[sel]].astype(np.int64),
+                 'K': self.K[sel].copy(), 'X': self.X[sel].copy(), 'o_t': np.array(o_next[sel], dtype=np.float64),
+                 'dx': None if self.dx is None else np.asarray(self.dx)[sel],
+                 'paths': [self.paths[j] for j in sel] if len(self.paths) == n else []}
+            sub = type(self)(d, sched_params=self._sched_params)
+            sub.alpha[:], sub.beta[:], sub.chi[:], sub.gamma[:] = (self.alpha[sel], self.beta[sel], self.chi[sel],
+                                                                   self.gamma[sel])
+            sub.init_states(o_t_next=o_next[sel], i_t_next=i_next[sel])
+            sub.o_t_prev = np.array(o_prev[sel]); sub.i_t_prev = np.array(i_prev[sel])
+            models.append(sub)
+        for u, dwn in zip(cut, cut_down):
+            if dwn == u:
+                continue                                  # cutting at an outlet separates nothing
+            up_model, dn_model = models[labels[u]], models[labels[dwn]]
+            ui, di = int(local_index[u]), int(local_index[dwn])
+            i_dn = dn_model.i_t_next
+            i_dn[di] -= up_model.o_t_next[ui]             # muskingum.py:690
+            dn_model.i_t_next = i_dn
+            connection = Connection(up_model, dn_model, ui, di)
+            up_model.sinks.append(connection)
+            dn_model.sources.append(connection)
+        for sub in models:
+            sub.save_state()
+        return ModelCollection(models, name=name)
+
+
+class Connection:
+    """One-way link between two sub-models (muskingum.py:716-726): reach `upstream_index` of
+    `upstream_model` drains into reach `downstream_index` of `downstream_model`."""
+
+    def __init__(self, upstream_model, downstream_model, upstream_index, downstream_index, name=None):
+        self.upstream_model = upstream_model
+        self.downstream_model = downstream_model
+        self.upstream_index = upstream_index
+        self.downstream_index = downstream_index
+        self.name = str(uuid.uuid4()) if name is None else name
+
+
+class ModelCollection:
+    """A forest of sub-models (muskingum.py:728-836)."""
+
+    def __init__(self, models, name=None):
+        self.models = {model.name: model for model in models}
+        self.name = str(uuid.uuid4()) if name is None else name
+
+    @property
+    def info(self):
+        return {}
+
+    def _common(self, attr, what):
+        values = set(getattr(model, attr) for model in self.models.values())
+        if len(values) != 1:
+            raise ValueError(f'Models must all have the same {what}')
+        return values.pop()
+
+    @property
+    def datetime(self):
+        return pd.to_datetime(self._common('datetime', 'datetime'))
+
+    @property
+    def timedelta(self):
+        return pd.to_timedelta(self._common('timedelta', 'timedelta'))
+
+    def load_states(self):
+        for model in self.models.values():
+            model.load_state()
+
+    def save_states(self):
+        for model in self.models.values():
+            model.save_state()
+
+    def set_datetime(self, timestamp):
+        for model in self.models.values():
+            model.datetime = timestamp
+
+    def init_states(self, streamflow):
+        for model in self.models.values():
+            model.init_states(o_t_next=np.asarray(streamflow[model.reach_ids], dtype=np.float64))
+
+    def connections(self):
+        seen = {}
+        for model in self.models.values():
+            for c in list(model.sinks) + list(model.sources):
+                seen.setdefault(c.name, c)
+        return seen
+
+    def dump_model_collection(self, file_path, model_file_paths={}, dump_optional=True):
+        connections = {name: {'upstream_model': c.upstream_model.name, 'downstream_model': c.downstream_model.name,
+                              'upstream_index': int(c.upstream_index), 'downstream_index': int(c.downstream_index)}
+                       for name, c in self.connections().items()}
+        keys = _REQUIRED + (_OPTIONAL if dump_optional else ())
+        models = {name: {'model': {k: model.info[k] for k in keys},
+                         'sinks': [c.name for c in model.sinks], 'sources': [c.name for c in model.sources]}
+                  for name, model in self.models.items()}
+        with open(file_path, 'w') as f:
+            json.dump({'models': models, 'connections': connections}, f, cls=_Encoder)
+
+    @classmethod
+    def from_file(cls, file_path, load_optional=True, **kwargs):
+        return cls(load_model_collection(file_path, load_optional=load_optional), **kwargs)
+
+
+def _decode_model(obj, load_optional=True):
+    for key, dtype in (('startnodes', np.int64), ('endnodes', np.int64), ('K', np.float64),
+                       ('X', np.float64), ('o_t', np.float64), ('dx', np.float64)):
+        if obj.get(key) is not None:
+            obj[key] = np.asarray(obj[key], dtype=dtype)
+    if 'datetime' in obj:
+        obj['datetime'] = pd.Timestamp(obj['datetime'])
+    if 'timedelta' in obj:
+        obj['timedelta'] = pd.Timedelta(obj['timedelta'])
+    if not load_optional:
+        obj.pop('dx', None)
+        obj.pop('paths', None)
+    return obj
+
+
+def load_model_collection(file_path, load_optional=True):
+    """Collection JSON -> list of wired models (muskingum.py:920-944)."""
+    with open(file_path) as f:
+        info = json.load(f)
+    models = {}
+    for _, model_info in info['models'].items():
+        model = Muskingum(_decode_model(model_info['model'], load_optional), load_optional=load_optional)
+        models[model.name] = model
+    for name, c in info['connections'].items():
+        connection = Connection(models[c['upstream_model']], models[c['downstream_model']],
+                                c['upstream_index'], c['downstream_index'], name=name)
+        connection.upstream_model.sinks.append(connection)
+        connection.downstream_model.sources.append(connection)
+    return list(models.values())
+
+
 # ---------------------------------------------------------------------- JSON I/O
 class _Encoder(json.JSONEncoder):
     def default(self, obj):

@@ -1,13 +1,118 @@
-"""`CheckPoint` callback (tx_fast_hydrology/simulation.py:169-211): saves the model state once
-when `model.datetime >= checkpoint_time` and fans save/load out to sibling callbacks.  The
-sub-basin orchestration of simulation.py (`AsyncSimulation`) is host glue outside the routing hot
-path and is not rebuilt here."""
+"""Orchestration of a forest of sub-models and the `CheckPoint` callback
+(tx_fast_hydrology/simulation.py).
+
+`AsyncSimulation` (simulation.py:94-166) runs the sub-models of a `ModelCollection` in dependency order:
+a sub-model starts once every sub-model draining into it has finished its whole run, and the hydrograph of
+the upstream exit reach enters the downstream entry reach as extra lateral inflow,
+(alpha*i_next + beta*i_prev)/gamma -- which reproduces the un-split update exactly.  A sub-model without
+callbacks runs its whole span in device-resident launches with the trajectory recorded on the GPU
+(`Muskingum.run`); one with callbacks (a Kalman filter per sub-basin, as app.py:130-141 binds them) steps
+through `simulate_iter` so that every hook fires as in the reference.
+
+`CheckPoint` (simulation.py:169-211) saves the model state once when `model.datetime >= checkpoint_time`
+and fans save/load out to sibling callbacks."""
+import asyncio
 import datetime
 import logging
+
+import numpy as np
+import pandas as pd
 
 from .callbacks import BaseCallback
 
 logger = logging.getLogger(__name__)
+
+
+class Simulation:
+    def __init__(self, model_collection, inputs):
+        self.model_collection = model_collection
+        self.models = model_collection.models
+        self.inputs = self.load_inputs(inputs)
+        self.outputs = {}
+
+    def load_inputs(self, inputs):
+        return {name: inputs[model.reach_ids].copy() for name, model in self.models.items()}
+
+    def simulate(self):
+        raise NotImplementedError
+
+    @property
+    def datetime(self):
+        return self.model_collection.datetime
+
+    def load_states(self):
+        self.model_collection.load_states()
+
+    def save_states(self):
+        self.model_collection.save_states()
+
+    def init_states(self, streamflow):
+        self.model_collection.init_states(streamflow)
+
+    def set_datetime(self, timestamp):
+        self.model_collection.set_datetime(timestamp)
+
+
+class AsyncSimulation(Simulation):
+    async def simulate(self):
+        """Awaitable like the reference's (simulation.py:98-108); `run()` is the plain-call form."""
+        return self.run()
+
+    def run(self):
+        pending = {name: len(model.sources) for name, model in self.models.items()}
+        ready = [name for name, k in pending.items() if k == 0]
+        done = 0
+        while ready:
+            name = ready.pop(0)
+            model = self.models[name]
+            outputs = self._simulate(model, self.inputs[name])
+            self.outputs[name] = outputs
+            done += 1
+            for connection in model.sinks:
+                down = connection.downstream_model
+                if down.name == name:
+                    continue
+                self._accumulate(outputs, model, connection)
+                pending[down.name] -= 1
+                if pending[down.name] == 0:
+                    ready.append(down.name)
+        if done != len(self.models):
+            raise ValueError('sub-model connections contain a cycle')
+        return self.outputs
+
+    def _simulate(self, model, inputs):
+        """Whole run of one sub-model; rows = start time + every step, columns = reach ids."""
+        logger.debug(f'Started job for sub-watershed {model.name}')
+        start, dt = model.datetime, model.timedelta
+        first = np.array(model.o_t_next, dtype=np.float64)
+        end_time = inputs.index.max()
+        nsteps = 0 if not end_time > start else int(-((start - end_time) // dt))      # steps while datetime < end
+        whole = dt.value == int(round(model.dt * 1e9))
+        if model.callbacks or nsteps == 0 or not whole:
+            rows, times = [first], [start]
+            for state in model.simulate_iter(inputs):
+                rows.append(np.array(state.o_t_next, dtype=np.float64)); times.append(state.datetime)
+            values = np.stack(rows)
+        else:
+            assert isinstance(inputs.index, pd.DatetimeIndex) and str(inputs.index.tz) == 'UTC'
+            forcing = model.make_forcing(dataframe=inputs)
+            rec = model.run(forcing, nsteps, record_reaches=np.arange(model.n), record_every=1)
+            model.network.check()
+            values = np.concatenate([first[None, :], rec.cpu().numpy()[:, :, 0]], axis=0)
+            times = [start + k * dt for k in range(nsteps + 1)]
+            forcing.close()
+        outputs = pd.DataFrame(values, index=pd.to_datetime(times, utc=True), columns=inputs.columns)
+        return outputs
+
+    def _accumulate(self, outputs, upstream_model, connection):
+        """simulation.py:137-166: the exit hydrograph becomes lateral inflow of the entry reach."""
+        down = connection.downstream_model
+        inputs = self.inputs[down.name]
+        o = outputs[upstream_model.reach_ids[connection.upstream_index]].values
+        i_t_prev, i_t_next = o[:-1], o[1:]
+        k = connection.downstream_index
+        inputs.loc[:, down.reach_ids[k]] += (down.alpha[k] * i_t_next / down.gamma[k]
+                                             + down.beta[k] * i_t_prev / down.gamma[k])
 
 
 class CheckPoint(BaseCallback):
