@@ -216,7 +216,41 @@ def split_collection():
     print("split_n300.npz ok", len(names), "models", conns)
 
 
+def smoother():
+    """KalmanSmoother (da.py:139-264): forward filter with stored covariances + RTS backward pass."""
+    from tx_fast_hydrology.da import KalmanSmoother
+    n, m, T, seed = 60, 6, 10, 41
+    net = S.make_network(n, seed)
+    prm = S.make_params(n, seed, well_posed=True)
+    d = S.model_dict(net, prm, dt_s=300.0, t0=T0)
+    mdl = Muskingum(d)
+    t0_ns = mdl.datetime.value
+    times, table = S.make_forcing(n, T, 300.0, seed, t0_ns=t0_ns, rows_every=5)
+    df = frame(times, table, d["reach_ids"])
+    gidx = np.sort(S.make_gauges(net["endnodes"], m, seed=seed))
+    rng = np.random.default_rng(seed + 5)
+    mt = t0_ns + np.arange(0, T + 1, dtype=np.int64) * int(300e9)        # a measurement at every model time
+    meas = rng.uniform(0.5, 8.0, size=(mt.size, m))
+    mdf = frame(mt, meas, [d["reach_ids"][j] for j in gidx])
+    Rm = rng.standard_normal((m, m)); R = 1e-2 * np.eye(m) + 1e-3 * (Rm @ Rm.T)
+    Q = 0.5 * np.eye(n); P0 = Q.copy()
+    ks = KalmanSmoother(mdl, mdf, Q, R, P0)
+    mdl.bind_callback(ks, key="ks")
+    for state in mdl.simulate(df):
+        pass
+    ts = sorted(ks.o_hat_s.index)
+    np.savez_compressed(
+        os.path.join(HERE, "smoother_n60.npz"), endnodes=mdl.endnodes, K=mdl.K, X=mdl.X, o_init=prm["o_t"], dt=300.0,
+        t0_ns=t0_ns, times=times, table=table, gauge_idx=gidx, meas_times=mt, meas=meas, R=R, Q=Q, P0=P0,
+        o_final=mdl.o_t_next, i_final=mdl.i_t_next,
+        o_hat_s=ks.o_hat_s.loc[ts].values, i_hat_s=ks.i_hat_s.loc[ts].values,
+        smooth_times=np.asarray([pd.Timestamp(t).value for t in ts]),
+        P_s_first=ks.P_s[ts[0]], P_f_last=ks.P_f[ts[-1]], n_times=len(ks.datetimes))
+    print("smoother_n60.npz ok", len(ks.datetimes))
+
+
 if __name__ == "__main__":
+    smoother()
     split_collection()
     kernels(60, 7, "kernels_n60.npz")
     kernels(160, 8, "kernels_n160.npz")

@@ -87,6 +87,27 @@ def test_kalman_filter_matches_reference(golden_dir):
     assert relerr(kf.P_t_next, g["P_final"]) < RTOL and relerr(kf.K, g["K_final"]) < RTOL
 
 
+def test_kalman_smoother_matches_reference(golden_dir):
+    """KalmanSmoother (da.py:139-264): forward filter at exact measurement times + RTS backward pass."""
+    from tx_fast_hydrology_b200.da import KalmanSmoother
+    g = np.load(os.path.join(golden_dir, "smoother_n60.npz"))
+    mdl, d = model_from(g)
+    df = frame(g["times"], g["table"], d["reach_ids"])
+    mdf = frame(g["meas_times"], g["meas"], [d["reach_ids"][j] for j in g["gauge_idx"]])
+    ks = KalmanSmoother(mdl, mdf, g["Q"], g["R"], g["P0"])
+    mdl.bind_callback(ks, key="ks")
+    for _ in mdl.simulate(df):
+        pass
+    assert len(ks.datetimes) == int(g["n_times"])
+    assert relerr(mdl.o_t_next, g["o_final"]) < RTOL and relerr(mdl.i_t_next, g["i_final"]) < RTOL
+    ts = sorted(ks.o_hat_s.index)
+    assert [pd.Timestamp(t).value for t in ts] == [int(x) for x in g["smooth_times"]]
+    assert relerr(ks.o_hat_s.loc[ts].values, g["o_hat_s"]) < 1e-8
+    assert relerr(ks.i_hat_s.loc[ts].values, g["i_hat_s"]) < 1e-8
+    assert relerr(ks.P_f[ts[-1]].cpu().numpy(), g["P_f_last"]) < RTOL
+    assert relerr(ks.P_s[ts[0]].cpu().numpy(), g["P_s_first"]) < 1e-7     # ten solves with P_p deep
+
+
 def test_checkpoint_rewind(golden_dir):
     """CheckPoint + save_state / load_state (simulation.py:169-211, muskingum.py:573-588)."""
     from tx_fast_hydrology_b200.simulation import CheckPoint

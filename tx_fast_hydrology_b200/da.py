@@ -176,6 +176,119 @@ class KalmanFilter(BaseCallback):
         self.datetime = mdl.datetime
 
 
+class KalmanSmoother(KalmanFilter):
+    """Rauch-Tung-Striebel smoother callback (tx_fast_hydrology/da.py:139-264): the forward pass is the dense
+    filter with every prior / posterior covariance kept ON THE DEVICE, the backward pass
+    J = (P_p[t+1]^-1 A P_f[t])^T,  x_s[t] = x_f[t] + J (x_s[t+1] - x_p[t+1]),  P_s[t] = P_f[t] + J (P_s[t+1] - P_p[t+1])
+    runs at simulation end with the operator product as a member-batched routing launch and the dense
+    products on the FP64 tensor cores.  Kept quirks: measurements are looked up at the exact model time
+    (da.py:190), states are rebound rather than updated in place (da.py:205-206), the covariance recursion has
+    no trailing J^T (da.py:257)."""
+
+    def __init__(self, model, measurements, Q_cov, R_cov, P_t_init):
+        super().__init__(model, measurements, Q_cov, R_cov, P_t_init)
+        self.N = len(measurements) - 1
+        t = model.datetime
+        self.datetimes = [t]
+        self.P_f = {t: self._P.clone()}
+        self.P_p = {t: self._P.clone()}
+        self.i_hat_f = {t: model.i_t_next.copy()}
+        self.o_hat_f = {t: model.o_t_next.copy()}
+        self.i_hat_p = {t: model.i_t_next.copy()}
+        self.o_hat_p = {t: model.o_t_next.copy()}
+        self.i_hat_s = None
+        self.o_hat_s = None
+        self.P_s = None
+
+    def __on_simulation_end__(self):
+        return self.smooth()
+
+    def _ap(self, P):
+        """nutils.py:157-169 (`_ap_par`): A P, the columns of P routed as members."""
+        torch = self._torch
+        net, n = self.model.network, self.model.n
+        self.model._sync_coeffs()
+        X = net.alloc_state(n)
+        scr = net.alloc_state(n)
+        out = torch.empty((n, n), dtype=torch.float64, device='cuda')
+        net.pack_dev(P.contiguous(), n, X)
+        net.route_apply(X, scr, n)
+        net.unpack_dev(X, n, out)
+        return out
+
+    def filter(self):
+        """da.py:170-219."""
+        torch = self._torch
+        mdl = self.model
+        n, m = mdl.n, self.num_measurements
+        t = mdl.datetime
+        i_prior = mdl.i_t_next
+        o_prior = mdl.o_t_next
+        Z = self.measurements.loc[t].values                                  # exact time, no interpolation
+        dz = Z - o_prior[self.s]
+        P_prev = self._P
+        P_prior = self._aqat(P_prev)
+        P_prior += self._Q
+        Ps = P_prior.index_select(1, self._idx).contiguous()
+        S = Ps.index_select(0, self._idx).contiguous() + self._R
+        Sinv = inverse(S)
+        K = torch.empty((n, m), dtype=torch.float64, device='cuda')
+        dgemm(Ps, Sinv, K)
+        gain_d = torch.empty((n, 1), dtype=torch.float64, device='cuda')
+        dgemm(K, torch.as_tensor(dz, device='cuda').reshape(m, 1).contiguous(), gain_d)
+        Prow = P_prior.index_select(0, self._idx).contiguous()
+        P_next = P_prior.clone()
+        dgemm(K, Prow, P_next, alpha=-1.0, beta=1.0)
+        gain = gain_d.cpu().numpy()[:, 0]
+        i_gain = np.zeros(n)
+        nz = mdl.endnodes != mdl.startnodes
+        np.add.at(i_gain, mdl.endnodes[nz], gain[nz])
+        i_next = i_prior + i_gain                                            # fresh arrays (da.py:203-206)
+        o_next = o_prior + gain
+        mdl.i_t_next = i_next
+        mdl.o_t_next = o_next
+        self._P_prev = P_prev
+        self._P = P_next
+        self.K = K.cpu().numpy(); self.dz = dz; self.gain = gain
+        self.i_hat_f[t] = i_next; self.i_hat_p[t] = np.array(i_prior)
+        self.o_hat_f[t] = o_next; self.o_hat_p[t] = np.array(o_prior)
+        self.P_p[t] = P_prior; self.P_f[t] = P_next
+        self.datetimes.append(t)
+        self.datetime = t
+
+    def smooth(self):
+        """da.py:221-264, backward pass on the device."""
+        torch = self._torch
+        n = self.model.n
+        ts = self.datetimes
+        N = len(ts) - 1
+        last = self.datetime
+        P_s = {last: self.P_f[last]}
+        dev = dict(dtype=torch.float64, device='cuda')
+        x_s = torch.as_tensor(np.stack([self.i_hat_f[last], self.o_hat_f[last]], axis=1), **dev).contiguous()
+        i_hat_s, o_hat_s = {last: self.i_hat_f[last]}, {last: self.o_hat_f[last]}
+        for k in reversed(range(N)):
+            t, tp1 = ts[k], ts[k + 1]
+            A_Pf = self._ap(self.P_f[t])
+            J = torch.empty((n, n), **dev)
+            dgemm(A_Pf, inverse(self.P_p[tp1].clone()), J, transA=True, transB=True)     # (P_p^-1 A P_f)^T
+            x_f = torch.as_tensor(np.stack([self.i_hat_f[t], self.o_hat_f[t]], axis=1), **dev).contiguous()
+            x_p = torch.as_tensor(np.stack([self.i_hat_p[tp1], self.o_hat_p[tp1]], axis=1), **dev).contiguous()
+            x_new = x_f.clone()
+            dgemm(J, (x_s - x_p).contiguous(), x_new, alpha=1.0, beta=1.0)
+            P = self.P_f[t].clone()
+            dgemm(J, (P_s[tp1] - self.P_p[tp1]).contiguous(), P, alpha=1.0, beta=1.0)
+            x_s = x_new
+            xs_host = x_new.cpu().numpy()
+            i_hat_s[t] = xs_host[:, 0].copy(); o_hat_s[t] = xs_host[:, 1].copy()
+            P_s[t] = P
+        self.i_hat_s = pd.DataFrame.from_dict(i_hat_s, orient='index')
+        self.i_hat_s.columns = self.model.reach_ids
+        self.o_hat_s = pd.DataFrame.from_dict(o_hat_s, orient='index')
+        self.o_hat_s.columns = self.model.reach_ids
+        self.P_s = P_s
+
+
 class EnsembleKalmanFilter(BaseCallback):
     """Ensemble Kalman update of a member-batched `Muskingum(members=M)`.
 
