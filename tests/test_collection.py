@@ -83,3 +83,24 @@ def test_async_simulation_matches_reference(libtxh, golden_dir, with_callback):
         whole[:, g[f"reach_{k}"]] = out.values
     assert relerr(whole, g["whole"]) < RTOL
     assert mc.datetime.value == int(g["times"][-1])
+
+
+def test_load_nhd_geojson(libtxh, tmp_path):
+    """muskingum.py:877-917: COMID/toCOMID -> indices, missing downstream id -> self-loop outlet, defaults."""
+    import json
+    from tx_fast_hydrology_b200.muskingum import Muskingum, load_nhd_geojson
+    comid = [501, 77, 9001, 12, 345, 60]
+    to = [77, 12, 12, 999999, 501, 345]                  # 999999 is not a feature: reach 12 is the outlet
+    feats = [{"attributes": {"COMID": c, "toCOMID": t, "Shape_Length": 1.5 + k},
+              "geometry": {"paths": [[[0.0, 1.0 * k], [1.0, 1.0 * k]]]}} for k, (c, t) in enumerate(zip(comid, to))]
+    path = str(tmp_path / "nhd.json")
+    with open(path, "w") as f:
+        json.dump({"features": feats}, f)
+    obj = load_nhd_geojson(path)
+    assert obj["reach_ids"] == [str(c) for c in comid]
+    assert (obj["startnodes"] == np.arange(6)).all()
+    assert (obj["endnodes"] == np.array([1, 3, 3, 3, 0, 4])).all()
+    assert (obj["K"] == 3600.0).all() and (obj["X"] == 0.29).all() and (obj["o_t"] == 1e-3).all()
+    assert (obj["dx"] == 1.5 + np.arange(6)).all() and len(obj["paths"]) == 6
+    mdl = Muskingum(obj)
+    assert (mdl.indegree == np.array([1, 1, 0, 2, 1, 0])).all()

@@ -676,6 +676,35 @@ def load_model_file(file_path, load_optional=True):
     return obj
 
 
+def load_nhd_geojson(file_path):
+    """NHD flowline GeoJSON -> the dict `Muskingum` takes (muskingum.py:877-917): reach = feature, COMID /
+    toCOMID give the downstream link (a missing toCOMID makes the reach an outlet, i.e. a self-loop), defaults
+    K = 3600 s, X = 0.29, o_t = 1e-3.  The id -> index join is one sort + searchsorted instead of a per-feature
+    loop, so CONUS-size files do not spend their time here."""
+    with open(file_path) as f:
+        features = json.load(f)['features']
+    attrs = [ft['attributes'] for ft in features]
+    comid = np.asarray([a['COMID'] for a in attrs])
+    to_comid = np.asarray([a['toCOMID'] for a in attrs])
+    n = comid.size
+    order = np.argsort(comid, kind='stable')
+    sorted_ids = comid[order]
+    # first occurrence wins, as a pandas index lookup on unique ids does
+    pos = np.searchsorted(sorted_ids, to_comid)
+    pos_c = np.minimum(pos, max(n - 1, 0))
+    found = (pos < n) & (sorted_ids[pos_c] == to_comid) if n else np.zeros(0, dtype=bool)
+    startnodes = np.arange(n, dtype=np.int64)
+    endnodes = np.where(found, order[pos_c], startnodes).astype(np.int64)
+    return {
+        'name': str(uuid.uuid4()), 'datetime': DEFAULT_START_TIME, 'timedelta': DEFAULT_TIMEDELTA,
+        'reach_ids': [str(x) for x in comid.tolist()], 'startnodes': startnodes, 'endnodes': endnodes,
+        'K': 3600 * np.ones(n, dtype=np.float64), 'X': 0.29 * np.ones(n, dtype=np.float64),
+        'o_t': 1e-3 * np.ones(n, dtype=np.float64),
+        'dx': np.asarray([a['Shape_Length'] for a in attrs]),
+        'paths': [np.asarray(ft['geometry']['paths']) for ft in features],
+    }
+
+
 def dump_model_file(obj, file_path, dump_optional=True):
     keys = _REQUIRED + (_OPTIONAL if dump_optional else ())
     with open(file_path, 'w') as f:
