@@ -428,6 +428,8 @@ int txh_create(int64_t n, const int64_t* endnodes, const int32_t* sp, txh_net** 
     if (!net->topo.build(n, endnodes, err)) { delete net; return fail(TXH_E_TOPOLOGY, err); }
     SchedParams p;
     if (sp) { p.long_path_min = sp[0]; p.spine_cap = sp[1]; p.pocket_cap = sp[2]; p.max_slots = sp[3]; p.link_cap = sp[4]; }
+    if (const char* lw = getenv("TXH_LEN_WEIGHT")) p.len_weight = atoi(lw);
+    if (const char* sc = getenv("TXH_SIDE_CAP")) p.side_cap = std::max(1, atoi(sc));
     if (!net->sched.build(net->topo, p, err)) { delete net; return fail(TXH_E_INVALID, err); }
     *out = net;
     return TXH_OK;

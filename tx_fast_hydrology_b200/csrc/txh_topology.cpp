@@ -140,8 +140,8 @@ bool Schedule::build(const Topology& t, const SchedParams& p_in, std::string& er
 {
     SchedParams p = p_in;
     // Short segments keep the per-step work of a segment (serial in one warp) small; long networks need
-    // longer ones so that the hop chain along the main stem stays short: about 128 hops along the deepest path.
-    if (p.spine_cap <= 0) p.spine_cap = std::min(16, std::max(6, t.nlevels / 128));
+    // longer ones so that the hop chain along the main stem stays short: about 100 hops along the deepest path.
+    if (p.spine_cap <= 0) p.spine_cap = std::min(16, std::max(6, t.nlevels / 100));
     prm = p;
     const int64_t n = t.n;
     if (p.spine_cap < 1 || p.spine_cap > 4096 || p.pocket_cap < 1 || p.pocket_cap > 4096 ||
@@ -182,12 +182,23 @@ bool Schedule::build(const Topology& t, const SchedParams& p_in, std::string& er
                     if (t.child[c] != t.main_child[j] && is_long[t.child[c]]) { forced.push_back(k); break; }
             }
             forced.push_back(len);
+            // a segment ends when it has spine_cap reaches or side_cap pocket roots joining it: the serial work of
+            // a segment per step (rows + rows handed over by other tasks) paces the whole chain downstream
             cuts.clear();
             for (size_t f = 0; f + 1 < forced.size(); ++f) {
                 const int32_t a0 = forced[f], a1 = forced[f + 1];
-                const int32_t nseg = (a1 - a0 + p.spine_cap - 1) / p.spine_cap;
-                const int32_t seglen = (a1 - a0 + nseg - 1) / nseg;
-                for (int32_t s0 = a0; s0 < a1; s0 += seglen) cuts.push_back(s0);
+                int32_t s0 = a0, nrows = 0, nsides = 0;
+                cuts.push_back(a0);
+                for (int32_t k = a0; k < a1; ++k) {
+                    const int32_t j = member[poff[q] + k];
+                    int32_t sk = 0;
+                    for (int32_t c = t.child_off[j]; c < t.child_off[j + 1]; ++c)
+                        if (t.child[c] != t.main_child[j] && !is_long[t.child[c]]) ++sk;
+                    if (k > s0 && (nrows + 1 > p.spine_cap || nsides + sk > p.side_cap)) {
+                        cuts.push_back(k); s0 = k; nrows = 0; nsides = 0;
+                    }
+                    ++nrows; nsides += sk;
+                }
             }
             cuts.push_back(len);
             int32_t link_u = -1, prev_last = -1;
@@ -605,7 +616,11 @@ bool Schedule::build(const Topology& t, const SchedParams& p_in, std::string& er
         }
         std::vector<int32_t> worder; worder.reserve(ng);
         {
-            auto cmp = [&](int32_t a, int32_t b) { return wcp[a] != wcp[b] ? wcp[a] < wcp[b] : a > b; };
+            // longest remaining chain first; among equals (and to shorten the ramp-down at the end of a launch,
+            // where the last tasks claimed decide when it ends) the tasks with more rows first
+            std::vector<int64_t> prio(ng);
+            for (int32_t g = 0; g < ng; ++g) prio[g] = wcp[g] + (int64_t)p.len_weight * g_len[g];
+            auto cmp = [&](int32_t a, int32_t b) { return prio[a] != prio[b] ? prio[a] < prio[b] : a > b; };
             std::priority_queue<int32_t, std::vector<int32_t>, decltype(cmp)> pq(cmp);
             std::vector<int32_t> pend(ng);
             for (int32_t g = 0; g < ng; ++g) { pend[g] = (int32_t)allprod[g].size(); if (!pend[g]) pq.push(g); }
