@@ -889,7 +889,7 @@ int txh_enkf_stats(txh_net* net, const double* O, int64_t Mloc, const int64_t* o
 int64_t txh_enkf_work_size(int64_t m, int64_t Mtot)
 {
     const int64_t direct = m * m + 2 * m * Mtot + m;
-    const int64_t nsplit = Mtot <= 96 ? 8 : 1;
+    const int64_t nsplit = Mtot <= 128 ? 8 : 1;
     const int64_t woodbury = 4 * m * Mtot + nsplit * 2 * Mtot * Mtot + Mtot * Mtot;
     return std::max(direct, woodbury);
 }
@@ -908,7 +908,7 @@ int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, cons
     if ((rc = obs_positions(net, obs, m, st, &d_pos))) return rc;
     if (dinv_kind != 0 && Mtot < m) {
         // ensemble-space form (txh_da.cu): the Mtot x Mtot system replaces the m x m one and T is its solution
-        const int Mt = (int)Mtot, nsplit = Mtot <= 96 ? 8 : 1;
+        const int Mt = (int)Mtot, nsplit = Mtot <= 128 ? 8 : 1;
         double* Bc = work;                                  // [m][2Mt] = [HA | dz]
         double* Y = Bc + 2 * m * Mtot;                      // [m][2Mt] = D^-1 Bc
         double* Cp = Y + 2 * m * Mtot;                      // [nsplit][Mt][2Mt] split-K partials of HA^T Y
@@ -917,7 +917,7 @@ int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, cons
             CU(launch_dgemm(0, 0, (int)m, 2 * Mt, (int)m, 1.0, Dinv, (int)m, Bc, 2 * Mt, 0.0, Y, 2 * Mt, st));
         CU(launch_dgemm_splitk(1, 0, Mt, 2 * Mt, (int)m, Bc, 2 * Mt, Y, 2 * Mt, Cp, 2 * Mt, nsplit,
                                (long long)Mt * 2 * Mt, st));
-        if (Mt <= 96) {
+        if (Mt <= 128) {
             CU(launch_chol_solve_small(Cp, nsplit, (long long)Mt * 2 * Mt, Mt, (double)(Mtot - 1), T, info_word(net), st));
         } else {
             double* Cf = Cp + (size_t)nsplit * 2 * Mt * Mt;  // blocked Cholesky: (C0 + (Mt-1) I) Z = C1, Z in place in T

@@ -386,122 +386,11 @@ innovation_cat_kernel(const double* __restrict__ HX, const double* __restrict__ 
 }
 
 // (sum of the split-K partials of C) -> A = C0 + shift*I, B = C1, then (C0 + shift I) Z = C1 by Cholesky.
-// The vector FP64 pipe of one SM is the bound of this small solve, so the right-hand sides are split over
-// MT/8 CTAs (8 columns each); every CTA factors A itself (8*MT threads, the lower triangle in REGISTERS:
-// thread (rg, c) = (tid / MT, tid % MT) owns rows {8r + rg} of column c) and carries its slice of B along:
-//   step j : the owners publish column j of A (unscaled) and row j of B; with r = 1/sqrt(d_j) everyone applies
-//            A[i][c] -= A[i][j] A[c][j] r^2,  B[i][c] -= A[i][j] B[j][c] r^2;  row j becomes Y[j] = B[j] r and
-//            L[:, j] = A[:, j] r is parked in shared memory -- one barrier per column, the forward substitution
-//            rides on the factorisation;
-//   then the backward substitution L^T Z = Y, one barrier per row.
-// The system is padded with the identity up to MT (64 or 96) so that all register indices are static.
+// (A register-resident column-by-column variant with one barrier per column measured 58 us at 64 members; the
+// blocked one below 31 us.)
 constexpr int CS_NSPLIT = 8;
 
-template <int MT, int RG>
-__global__ void __launch_bounds__(RG * MT)
-chol_solve_small_kernel(const double* __restrict__ Cpart, long long pstride, int Mt, double shift,
-                        double* __restrict__ Z, int* __restrict__ info)
-{
-    // thread (rg, c) = (tid / MT, tid % MT) owns rows {RG*r + rg} of column c of A; NB elements of this CTA's
-    // 8 columns of B: element u is row (tid + u*NT) / 8, column (tid + u*NT) % 8
-    constexpr int R = MT / RG, LDU = MT + 1, NT = RG * MT, NB = 8 / RG;
-    extern __shared__ double sm[];
-    double* U = sm;                       // [MT][MT+1]  U[j][i] = L[i][j], i > j
-    double* bc = U + MT * LDU;            // [2][MT + 9] per-step broadcast (column of A, row of B, 1/sqrt(pivot))
-    double* invd = bc + 2 * (MT + 9);     // [MT]        1 / L[j][j]
-    const int tid = threadIdx.x;
-    const int c = tid % MT, rg = tid / MT;
-    const int bcol = tid & 7;
-    const int gcol = blockIdx.x * 8 + bcol;
-    const int warp0 = (tid & ~31) % MT;               // first column of this warp's 32 columns
-    double a[R], b[NB];
-#pragma unroll
-    for (int r = 0; r < R; ++r) a[r] = 0.0;
-#pragma unroll
-    for (int u = 0; u < NB; ++u) b[u] = 0.0;
-#pragma unroll
-    for (int s = 0; s < CS_NSPLIT; ++s) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int i = RG * r + rg;
-            if (i < Mt && c < Mt) a[r] += Cpart[(size_t)s * pstride + (size_t)i * 2 * Mt + c];
-        }
-#pragma unroll
-        for (int u = 0; u < NB; ++u) {
-            const int bi = (tid + u * NT) >> 3;
-            if (bi < Mt && gcol < Mt) b[u] += Cpart[(size_t)s * pstride + (size_t)bi * 2 * Mt + Mt + gcol];
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int i = RG * r + rg;
-        if (i == c) a[r] = (i < Mt) ? a[r] + shift : 1.0;
-    }
-    // ---- factor + forward substitution ----
-#pragma unroll
-    for (int pb = 0; pb < R; ++pb) {
-        for (int pr = 0; pr < RG; ++pr) {
-            const int j = RG * pb + pr;
-            double* cb = bc + (j & 1) * (MT + 9);
-            double* brow = cb + MT;
-            if (c == j) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) cb[RG * r + rg] = a[r];      // rows < j carry junk that nobody reads
-                if (rg == pr) {
-                    // the pivot's owner alone takes the reciprocal square root
-                    double d = a[pb];
-                    if (!(d > 0.0)) { if (blockIdx.x == 0) *info = j + 1; d = 1.0; }
-                    const double r1 = rsqrt(d);
-                    cb[MT + 8] = r1; invd[j] = r1;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < NB; ++u) if (((tid + u * NT) >> 3) == j) brow[bcol] = b[u];
-            __syncthreads();
-            const double rs = cb[MT + 8], rs2 = rs * rs;
-            const double bj = brow[bcol] * rs2;
-#pragma unroll
-            for (int u = 0; u < NB; ++u) {
-                const int bi = (tid + u * NT) >> 3;
-                if (bi == j) b[u] *= rs;
-                else if (bi > j) b[u] -= cb[bi] * bj;
-            }
-            if (c == j) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) { const int i = RG * r + rg; if (i > j) U[j * LDU + i] = a[r] * rs; }
-            }
-            if (warp0 + 31 > j) {                                        // some column of this warp is right of j
-                const double fa = c > j ? cb[c] * rs2 : 0.0;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int i = RG * r + rg;
-                    if ((r > pb || (r == pb && rg > pr)) && i >= c) a[r] -= cb[i] * fa;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    // ---- backward: L^T Z = Y ----
-    for (int p = MT - 1; p >= 0; --p) {
-        double* zrow = bc + (p & 1) * (MT + 9) + MT;
-#pragma unroll
-        for (int u = 0; u < NB; ++u) if (((tid + u * NT) >> 3) == p) { b[u] *= invd[p]; zrow[bcol] = b[u]; }
-        __syncthreads();
-        const double z = zrow[bcol];
-#pragma unroll
-        for (int u = 0; u < NB; ++u) {
-            const int bi = (tid + u * NT) >> 3;
-            if (bi < p) b[u] -= U[bi * LDU + p] * z;
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < NB; ++u) {
-        const int bi = (tid + u * NT) >> 3;
-        if (bi < Mt && gcol < Mt) Z[(size_t)bi * Mt + gcol] = b[u];
-    }
-}
-
-// Blocked variant of the small solve, the one in use: the matrix lives in shared memory, panels of 8 columns.
+// Blocked small solve: the matrix lives in shared memory, panels of 8 columns.
 //   panel   : warp 0 keeps the panel rows in registers (lane l owns rows j0+l, j0+l+32, ...) and factors the 8
 //             columns with shuffles -- no barrier inside a panel -- then solves the 8 matching rows of B;
 //   trailing: every warp takes 8x8 tiles of the lower triangle (and of B) and applies the rank-8 update with
@@ -695,9 +584,11 @@ __global__ void __launch_bounds__(EU_WARPS * 32)
 enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const double* __restrict__ mean,
                    const double* __restrict__ T, int ldt, int Mloc, double* __restrict__ O, double* __restrict__ G,
                    int ld, long long n, const int32_t* __restrict__ gauge_of_pos, const double* __restrict__ qs,
-                   const double* __restrict__ W, int col0)
+                   const double* __restrict__ W, int col0, int resident)
 {
-    __shared__ double sT[64 * EU_LDT];
+    // `resident`: every 64-member k chunk of T has its own block of shared memory and is staged once per CTA
+    // (single column group); otherwise one block is restaged for every (row tile, chunk)
+    extern __shared__ double sT_all[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const bool vec = (ldx & 1) == 0;
@@ -713,7 +604,8 @@ enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const dou
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
             for (int kc = 0; kc < nkc; ++kc) {
-                if (nkc * ncg > 1 || r0 == (long long)blockIdx.x * EU_ROWS) {
+                double* sT = sT_all + (resident ? kc * 64 * EU_LDT : 0);
+                if ((!resident && nkc * ncg > 1) || r0 == (long long)blockIdx.x * EU_ROWS) {
                     // stage T[kc*64 .. +64][cg*64 .. +64] (zero outside the matrix); with a single block it
                     // is staged once per CTA
                     __syncthreads();
@@ -937,33 +829,6 @@ inflow_gain_kernel(const int32_t* __restrict__ up_off, const int32_t* __restrict
     *ip = i;
 }
 
-__global__ void __launch_bounds__(256)
-scale_kernel(double* __restrict__ X, long long count, double s)
-{
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid < count) X[gid] *= s;
-}
-
-// dense filter helpers: P += Q ;  Ps = P[:, s] (columns) ; Pss = P[s][:, s]
-__global__ void __launch_bounds__(256)
-gather_cols_kernel(const double* __restrict__ P, int n, const int32_t* __restrict__ idx, int m, double* __restrict__ out)
-{
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)n * m) return;
-    const int i = (int)(gid / m), k = (int)(gid - (long long)i * m);
-    out[gid] = P[(size_t)i * n + idx[k]];
-}
-
-__global__ void __launch_bounds__(256)
-gather_rows_dense_kernel(const double* __restrict__ P, int ncols, const int32_t* __restrict__ idx, int m,
-                         double* __restrict__ out)
-{
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)m * ncols) return;
-    const int k = (int)(gid / ncols), c = (int)(gid - (long long)k * ncols);
-    out[gid] = P[(size_t)idx[k] * ncols + c];
-}
-
 inline unsigned nblk(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
 
 }  // namespace
@@ -1016,22 +881,15 @@ cudaError_t launch_innovation_cat(const double* HX, const double* Zp, const doub
 cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long pstride, int Mt, double shift, double* Z,
                                     int* info, cudaStream_t st)
 {
-    if (nsplit != CS_NSPLIT || Mt > 96) return cudaErrorInvalidValue;
-    const int MT = Mt <= 64 ? 64 : 96;
-    const size_t smem = ((size_t)MT * (MT + 1) + 2 * (MT + 9) + MT) * sizeof(double);
+    if (nsplit != CS_NSPLIT || Mt > 128) return cudaErrorInvalidValue;
+    const int MT = Mt <= 64 ? 64 : (Mt <= 96 ? 96 : 128);
     const int ncta = (Mt + 7) / 8;                      // 8 right-hand-side columns per CTA
-    cudaError_t e;
     const size_t smem_b = ((size_t)MT * (MT + 1) + (size_t)MT * 9 + MT) * sizeof(double);
-    (void)smem;
-    if (MT == 64) {
-        e = cudaFuncSetAttribute(chol_solve_blocked_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-        if (e != cudaSuccess) return e;
-        chol_solve_blocked_kernel<64><<<ncta, 256, smem_b, st>>>(Cpart, pstride, Mt, shift, Z, info);
-    } else {
-        e = cudaFuncSetAttribute(chol_solve_blocked_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-        if (e != cudaSuccess) return e;
-        chol_solve_blocked_kernel<96><<<ncta, 256, smem_b, st>>>(Cpart, pstride, Mt, shift, Z, info);
-    }
+    void (*kern)(const double*, long long, int, double, double*, int*) =
+        MT == 64 ? chol_solve_blocked_kernel<64> : (MT == 96 ? chol_solve_blocked_kernel<96> : chol_solve_blocked_kernel<128>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    if (e != cudaSuccess) return e;
+    kern<<<ncta, 256, smem_b, st>>>(Cpart, pstride, Mt, shift, Z, info);
     count_launch();
     return cudaGetLastError();
 }
@@ -1128,8 +986,13 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
         return cudaGetLastError();
     }
     long long grid = tiles < (long long)num_sms ? tiles : (long long)num_sms;
-    enkf_update_kernel<<<(unsigned)grid, EU_WARPS * 32, 0, st>>>(Xall, ldx, Mtot, mean, T, ldt, Mloc, O, G, ld, n,
-                                                                 gauge_of_pos, qs, W, col0);
+    const int nkc = (Mtot + 63) / 64;
+    const int resident = (ld <= 64 && nkc <= 6) ? 1 : 0;
+    const size_t smem = (size_t)(resident ? nkc : 1) * 64 * EU_LDT * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(enkf_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    enkf_update_kernel<<<(unsigned)grid, EU_WARPS * 32, smem, st>>>(Xall, ldx, Mtot, mean, T, ldt, Mloc, O, G, ld, n,
+                                                                    gauge_of_pos, qs, W, col0, resident);
     count_launch();
     return cudaGetLastError();
 }
@@ -1138,27 +1001,6 @@ cudaError_t launch_inflow_gain(const int32_t* up_off, const int32_t* up_pos, con
                                int ld, cudaStream_t st)
 {
     inflow_gain_kernel<<<nblk(n * (ld >> 1), 256), 256, 0, st>>>(up_off, up_pos, G, I, n, ld);
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_scale(double* X, int64_t count, double s, cudaStream_t st)
-{
-    scale_kernel<<<nblk(count, 256), 256, 0, st>>>(X, count, s);
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_gather_cols(const double* P, int n, const int32_t* idx, int m, double* out, cudaStream_t st)
-{
-    gather_cols_kernel<<<nblk((long long)n * m, 256), 256, 0, st>>>(P, n, idx, m, out);
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_gather_rows_dense(const double* P, int ncols, const int32_t* idx, int m, double* out, cudaStream_t st)
-{
-    gather_rows_dense_kernel<<<nblk((long long)m * ncols, 256), 256, 0, st>>>(P, ncols, idx, m, out);
     count_launch();
     return cudaGetLastError();
 }

@@ -154,8 +154,5 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
                                const double* qs, const double* W, int col0, int num_sms, cudaStream_t st);
 cudaError_t launch_inflow_gain(const int32_t* up_off, const int32_t* up_pos, const double* G, double* I, int64_t n,
                                int ld, cudaStream_t st);
-cudaError_t launch_scale(double* X, int64_t count, double s, cudaStream_t st);
-cudaError_t launch_gather_cols(const double* P, int n, const int32_t* idx, int m, double* out, cudaStream_t st);
-cudaError_t launch_gather_rows_dense(const double* P, int ncols, const int32_t* idx, int m, double* out, cudaStream_t st);
 
 }  // namespace txh
