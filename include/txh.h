@@ -79,6 +79,11 @@ int txh_get_window_info(const txh_net* net, int64_t info[8]);
 int txh_get_window_schedule(const txh_net* net, int32_t* wtask_desc, uint32_t* whdr /*[n]*/, uint32_t* winw,
                             int32_t* wprod);
 
+/* depth-first sweep order of small networks (route_sweep_kernel; header bits in txh_topology.hpp): the reach of
+ * every sweep row, its header word, and the number of scratch slots a warp needs.  TXH_E_INVALID if the
+ * network has no sweep order (a reach with > 256 upstream reaches, or a park stack deeper than 126). */
+int txh_get_sweep(const txh_net* net, int64_t* reach_of_row /*[n]*/, uint32_t* hdr /*[n]*/, int64_t* slots);
+
 /* ---- coefficients ----------------------------------------------------------------
  * txh_compute_coeffs replaces Muskingum.compute_muskingum_coeffs (muskingum.py:332-360):
  * host arithmetic in the reference's operation order; results returned in reach order
@@ -193,6 +198,21 @@ int txh_dgemm(int transA, int transB, int64_t M, int64_t N, int64_t K, double al
 int txh_spd_solve(int64_t m, int64_t k, double* S_dev, double* B_dev, void* stream);
 /* A <- inv(A) by Gauss-Jordan with partial pivoting (np.linalg.inv, da.py:119); work [m][m]. Synchronous. */
 int txh_inverse(int64_t m, double* A_dev, double* work_dev, void* stream);
+
+/* ---- dense Kalman filter of a single-member model: KalmanFilter.filter, da.py:91-136 ------------
+ * One update as a chain of launches with no host round trip (the measurement vector is the only host input):
+ *   P- = A P A^T + Q  (_aqat_par, nutils.py:194-214: the columns of P ride as members of two routing
+ *   launches), K = P-[:, s] inv(P-[s][:, s] + R), gain = K (z - o[s]), P+ = P- - K P-[s], then
+ *   o += gain and i += sum of upstream gains (_apply_gain, nutils.py:116-134) in place on the state rows.
+ * P_in [n][n] (posterior of the previous update), P_out [n][n] (may alias P_in), P_prior nullable [n][n],
+ * Q [n][n], R [m][m] in ascending gauge order (da.py:36-44), all device, row-major, reach order.
+ * obs_host [m] ascending reach indices, z_host [m].  O, I: state rows of the model (M = 1).
+ * K [n][m], gain [n] (reach order), dz [m]: device outputs.  work: txh_kf_work_size(net, m) doubles.
+ * Asynchronous; a singular innovation covariance is reported by txh_check. */
+int64_t txh_kf_work_size(const txh_net* net, int64_t m);
+int txh_kf_filter(txh_net* net, const double* P_in, double* P_out, double* P_prior, const double* Q_dev,
+                  const double* R_dev, const int64_t* obs_host, int64_t m, const double* z_host, double* O,
+                  double* I, double* K_dev, double* gain_dev, double* dz_dev, double* work_dev, void* stream);
 
 /* Synchronise `stream` and report a poisoned launch (TXH_E_WATCHDOG), an innovation covariance that was
  * not positive definite in an earlier txh_enkf_solve (TXH_E_INVALID), or a CUDA fault. */

@@ -40,6 +40,7 @@ SIGNATURES = {
     "txh_get_schedule": (ctypes.c_int, [c_vp, p_i64, p_i32, p_i32, p_u32, p_u32]),
     "txh_get_window_info": (ctypes.c_int, [c_vp, p_i64]),
     "txh_get_window_schedule": (ctypes.c_int, [c_vp, p_i32, p_u32, p_u32, p_i32]),
+    "txh_get_sweep": (ctypes.c_int, [c_vp, p_i64, p_u32, p_i64]),
     "txh_compute_coeffs": (ctypes.c_int, [c_vp, p_f64, p_f64, c_f64, p_f64, p_f64, p_f64, p_f64]),
     "txh_set_coeffs": (ctypes.c_int, [c_vp, p_f64, p_f64, p_f64, p_f64]),
     "txh_row_stride": (c_i64, [c_i64]),
@@ -69,6 +70,9 @@ SIGNATURES = {
                                  c_f64, c_vp, c_i64, c_vp]),
     "txh_spd_solve": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, c_vp]),
     "txh_inverse": (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp]),
+    "txh_kf_work_size": (c_i64, [c_vp, c_i64]),
+    "txh_kf_filter": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, p_i64, c_i64, p_f64, c_vp, c_vp, c_vp,
+                                     c_vp, c_vp, c_vp, c_vp]),
     "txh_check": (ctypes.c_int, [c_vp, c_vp]),
     "txh_launch_count": (c_i64, []),
 }

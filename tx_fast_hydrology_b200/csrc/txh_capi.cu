@@ -82,6 +82,13 @@ struct txh_net {
     double* d_stage = nullptr; size_t stage_cap = 0;   // reach-order staging of txh_pack_host / txh_unpack_host
     double* stats_rowsum = nullptr;     // txh_set_stats_output: row sums of the final outflows of every routing call
     double stats_scale = 1.0;
+    // depth-first sweep of small networks (txh_sweep.cu), built on first use
+    Sweep sweep;
+    int sweep_state = 0;                // 0 not tried, 1 usable, -1 not usable for this network
+    unsigned char* d_sweep_rec = nullptr;
+    uint32_t* d_sweep_hdr = nullptr;
+    int32_t* d_sweep_row = nullptr;
+    bool sweep_rec_stale = true;        // records carry the coefficients: rebuilt after every coefficient upload
 };
 
 struct txh_forcing {
@@ -127,6 +134,7 @@ int ensure_device(txh_net* net)
     if (const char* k = getenv("TXH_ROUTE_KERNEL")) {
         if (!strcmp(k, "dataflow")) net->route_kernel = 1;
         else if (!strcmp(k, "window")) net->route_kernel = 2;
+        else if (!strcmp(k, "sweep")) net->route_kernel = 3;
     }
     CU(cudaMalloc((void**)&net->d_coef, sizeof(double) * (6 * net->topo.n + net->sched.link_last.size() + 1)));
     CU(cudaMalloc((void**)&net->d_qtmp, sizeof(double) * net->topo.n));
@@ -156,7 +164,40 @@ int ensure_coef(txh_net* net, cudaStream_t st)
                            cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));
         net->coef_dirty = false;
+        net->sweep_rec_stale = true;
     }
+    return TXH_OK;
+}
+
+// Single steps of small networks go to the sweep kernel: one warp per 32 member columns walks every reach, so
+// its time is n * ~25 ns whatever M is (up to the ~50k columns the SMs hold at once).
+
+int sweep_ready(txh_net* net, int64_t M, cudaStream_t st, bool* use)
+{
+    *use = false;
+    (void)M;
+    if (net->route_kernel != 3) return TXH_OK;            // opt-in (TXH_ROUTE_KERNEL=sweep): see DESIGN.md section 4.4
+    if (net->sweep_state == 0) {
+        net->sweep_state = -1;
+        if (net->sweep.build(net->topo) && sweep_smem_bytes(net->sweep.slots) <= 200 * 1024) {
+            std::vector<int32_t> row(net->topo.n);
+            for (int64_t k = 0; k < net->topo.n; ++k) row[k] = net->sched.pos_of_reach[net->sweep.reach_of_row[k]];
+            int rc;
+            if ((rc = upload(&net->d_sweep_hdr, net->sweep.hdr)) || (rc = upload(&net->d_sweep_row, row))) return rc;
+            CU(cudaMalloc((void**)&net->d_sweep_rec, sweep_record_bytes(net->topo.n)));
+            net->sweep_state = 1;
+            net->sweep_rec_stale = true;
+        }
+    }
+    if (net->sweep_state != 1) {
+        if (net->route_kernel == 3) return fail(TXH_E_INVALID, "TXH_ROUTE_KERNEL=sweep: this network has no sweep order");
+        return TXH_OK;
+    }
+    if (net->sweep_rec_stale) {
+        CU(launch_sweep_records(net->d_sweep_hdr, net->d_sweep_row, net->d_coef, (int)net->topo.n, net->d_sweep_rec, st));
+        net->sweep_rec_stale = false;
+    }
+    *use = true;
     return TXH_OK;
 }
 
@@ -324,16 +365,15 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     const size_t slot_row = (size_t)std::max(1, s.n_wslots) * ld;
     int64_t spl = std::min<int64_t>(16, nsteps);
     while (spl > 1 && slot_row * spl * sizeof(double) > (size_t(1) << 30)) --spl;
-    if (slot_row * spl > net->ring_cap || ld != net->ring_ld) {
-        // every cell starts EMPTY (all bits set); consumers put EMPTY back, so a finished launch leaves it clean
-        if (slot_row * spl > net->ring_cap) {
-            if (net->d_ring) CU(cudaFree(net->d_ring));
-            CU(cudaMalloc((void**)&net->d_ring, slot_row * spl * sizeof(double)));
-            net->ring_cap = slot_row * spl;
-        }
+    if (slot_row * spl > net->ring_cap) {
+        // every cell starts EMPTY (all bits set); consumers put EMPTY back, so a finished launch leaves the whole
+        // ring EMPTY again whatever row stride the next launch lays over it
+        if (net->d_ring) CU(cudaFree(net->d_ring));
+        CU(cudaMalloc((void**)&net->d_ring, slot_row * spl * sizeof(double)));
+        net->ring_cap = slot_row * spl;
         CU(cudaMemsetAsync(net->d_ring, 0xff, net->ring_cap * sizeof(double), st));
-        net->ring_ld = ld;
     }
+    net->ring_ld = ld;
     const StepInterp* d_steps = net->d_unit_step;
     if (plan.times) {
         if ((size_t)spl > net->steps_cap) {
@@ -404,6 +444,16 @@ int run_routing(txh_net* net, double* O, double* I, int64_t M, const double* F, 
     return rc;
 }
 
+// one step without a forcing table (q: [n] schedule order or nullptr): window kernel first, dataflow otherwise
+int run_one_step(txh_net* net, double* O, double* I, int64_t M, const double* q, cudaStream_t st)
+{
+    if (net->route_kernel != 1) {
+        const int rc = run_window(net, O, I, M, q, nullptr, 0, StepPlan(), 1, st);
+        if (rc != 1) return rc;
+    }
+    return run_dataflow(net, O, I, M, q, nullptr, 0, StepPlan(), 1, nullptr, nullptr, 1, 0, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -440,6 +490,7 @@ void txh_destroy(txh_net* net)
     if (!net) return;
     if (net->dev_ready) {
         cudaFree(net->d_tasks); cudaFree(net->d_notify); cudaFree(net->d_init_ready); cudaFree(net->d_hdr); cudaFree(net->d_inw);
+        cudaFree(net->d_sweep_rec); cudaFree(net->d_sweep_hdr); cudaFree(net->d_sweep_row);
         cudaFree(net->d_up_off); cudaFree(net->d_up_pos); cudaFree(net->d_lvl_pos);
         cudaFree(net->d_reach_of_pos); cudaFree(net->d_pos_of_reach); cudaFree(net->d_outlet);
         cudaFree(net->d_coef); cudaFree(net->d_qtmp); cudaFree(net->d_qctl); cudaFree(net->d_rec_slot);
@@ -538,6 +589,17 @@ int txh_get_window_schedule(const txh_net* net, int32_t* wtask_desc, uint32_t* w
     if (whdr) std::memcpy(whdr, s.whdr.data(), s.whdr.size() * sizeof(uint32_t));
     if (winw) std::memcpy(winw, s.winw.data(), s.winw.size() * sizeof(uint32_t));
     if (wprod) std::memcpy(wprod, s.wprod.data(), s.wprod.size() * sizeof(int32_t));
+    return TXH_OK;
+}
+
+int txh_get_sweep(const txh_net* net, int64_t* reach_of_row, uint32_t* hdr, int64_t* slots)
+{
+    if (!net || !reach_of_row || !hdr || !slots) return fail(TXH_E_INVALID, "null argument");
+    Sweep sw;
+    if (!sw.build(net->topo)) return fail(TXH_E_INVALID, "this network has no sweep order");
+    widen(sw.reach_of_row, reach_of_row);
+    std::copy(sw.hdr.begin(), sw.hdr.end(), hdr);
+    *slots = sw.slots;
     return TXH_OK;
 }
 
@@ -772,8 +834,14 @@ int txh_route_step(txh_net* net, double* O, double* I, int64_t M, const double* 
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = check_M(M)) || (rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
     if (q) CU(launch_permute_vec(net->d_reach_of_pos, q, net->d_qtmp, net->topo.n, st));
-    return run_dataflow(net, O, I, M, q ? net->d_qtmp : nullptr, nullptr, 0, StepPlan(), 1, nullptr,
-                        nullptr, 1, 0, st);
+    bool sweep = false;
+    if ((rc = sweep_ready(net, M, st, &sweep))) return rc;
+    if (sweep) {
+        CU(launch_route_sweep(net->d_sweep_rec, (int)net->topo.n, net->sweep.slots, O, I, q ? net->d_qtmp : nullptr,
+                              (int)txh_row_stride(M), (int)M, false, st));
+        return TXH_OK;
+    }
+    return run_one_step(net, O, I, M, q ? net->d_qtmp : nullptr, st);
 }
 
 int txh_route_step_levels(txh_net* net, double* O, double* I, int64_t M, const double* q, void* stream)
@@ -801,9 +869,16 @@ int txh_route_apply(txh_net* net, double* X, double* Iscr, int64_t M, void* stre
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = check_M(M)) || (rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
     // nutils.py:148-154: i_prev = init_inflows(o_prev) (self-loop included), then _ax
+    bool sweep = false;
+    if ((rc = sweep_ready(net, M, st, &sweep))) return rc;
+    if (sweep) {
+        CU(launch_route_sweep(net->d_sweep_rec, (int)net->topo.n, net->sweep.slots, X, nullptr, nullptr,
+                              (int)txh_row_stride(M), (int)M, true, st));
+        return TXH_OK;
+    }
     CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, X, Iscr, net->topo.n,
                            (int)txh_row_stride(M), (int)M, st));
-    return run_dataflow(net, X, Iscr, M, nullptr, nullptr, 0, StepPlan(), 1, nullptr, nullptr, 1, 0, st);
+    return run_one_step(net, X, Iscr, M, nullptr, st);
 }
 
 int txh_apply_gain(txh_net* net, const double* G, double* O, double* I, int64_t M, void* stream)
@@ -1008,6 +1083,69 @@ int txh_inverse(int64_t m, double* A, double* work, void* stream)
     CU(cudaStreamSynchronize(st));
     cudaFree(d_info);
     if (info != 0) return fail(TXH_E_INVALID, "matrix is singular");
+    return TXH_OK;
+}
+
+static inline int64_t up4(int64_t x) { return (x + 3) & ~int64_t(3); }
+
+int64_t txh_kf_work_size(const txh_net* net, int64_t m)
+{
+    if (!net || m < 1) return 0;
+    const int64_t n = net->topo.n, ld = txh_row_stride(n);
+    return 2 * n * ld + up4(n * n) + 2 * up4(n * m) + 2 * up4(m * m) + up4(2 * n) + up4(m) + 16;
+}
+
+int txh_kf_filter(txh_net* net, const double* P_in, double* P_out, double* P_prior, const double* Q, const double* R,
+                  const int64_t* obs, int64_t m, const double* z, double* O, double* I, double* K, double* gain,
+                  double* dz, double* work, void* stream)
+{
+    if (!net || !P_in || !P_out || !Q || !R || !obs || !z || !O || !I || !K || !gain || !dz || !work || m < 1)
+        return fail(TXH_E_INVALID, "bad argument");
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = net->topo.n;
+    if ((rc = check_M(n)) || (rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
+    if (m > n) return fail(TXH_E_INVALID, "more gauges than reaches");
+    int32_t* d_pos = nullptr;
+    if ((rc = obs_positions(net, obs, m, st, &d_pos))) return rc;
+    const int ld = (int)txh_row_stride(n), ld1 = (int)txh_row_stride(1);
+    double* X = work;
+    double* X2 = X + n * ld;
+    double* Pm = P_prior ? P_prior : X2 + n * ld;
+    double* Ps = X2 + n * ld + up4(n * n);
+    double* Prow = Ps + up4(n * m);
+    double* S = Prow + up4(n * m);
+    double* Sw = S + up4(m * m);
+    double* Gp = Sw + up4(m * m);
+    double* zd = Gp + up4(2 * n);
+    CU(cudaMemcpyAsync(zd, z, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    // P- = A (A P)^T + Q, nutils.py:194-214 (X2 doubles as the inflow scratch of the first pass and vice versa)
+    bool sweep = false;
+    if ((rc = sweep_ready(net, n, st, &sweep))) return rc;
+    CU(launch_pack(net->d_reach_of_pos, P_in, X, n, (int)n, ld, 0, st));
+    if (sweep) {
+        CU(launch_route_sweep(net->d_sweep_rec, (int)n, net->sweep.slots, X, nullptr, nullptr, ld, (int)n, true, st));
+    } else {
+        CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, X, X2, n, ld, (int)n, st));
+        if ((rc = run_one_step(net, X, X2, n, nullptr, st))) return rc;
+    }
+    CU(launch_kf_repack_transposed(net->d_reach_of_pos, net->d_pos_of_reach, X, X2, (int)n, ld, st));
+    if (sweep) {
+        CU(launch_route_sweep(net->d_sweep_rec, (int)n, net->sweep.slots, X2, nullptr, nullptr, ld, (int)n, true, st));
+    } else {
+        CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, X2, X, n, ld, (int)n, st));
+        if ((rc = run_one_step(net, X2, X, n, nullptr, st))) return rc;
+    }
+    CU(launch_kf_prior_finish(net->d_reach_of_pos, net->d_pos_of_reach, net->d_gauge_of_pos, X2, ld, Q, R, (int)n, (int)m,
+                              Pm, Ps, Prow, S, st));
+    // K = P-[:, s] inv(P-[s][:, s] + R)   (da.py:119)
+    CU(launch_inverse(S, Sw, (int)m, info_word(net), st));
+    CU(launch_dgemm(0, 0, (int)n, (int)m, (int)m, 1.0, Ps, (int)m, S, (int)m, 0.0, K, (int)m, st));
+    // dz = z - o[s], gain = K dz (da.py:112, 121), P+ = P- - K P-[s] (da.py:122)
+    CU(launch_kf_gain(net->d_reach_of_pos, d_pos, zd, O, ld1, K, (int)n, (int)m, dz, gain, Gp, st));
+    CU(launch_dgemm_ex(0, 0, (int)n, (int)n, (int)m, -1.0, K, (int)m, Prow, (int)n, 1.0, Pm, (int)n, P_out, (int)n, st));
+    // da.py:124-126
+    CU(launch_apply_gain(net->d_up_off, net->d_up_pos, Gp, O, I, n, ld1, 1, st));
     return TXH_OK;
 }
 

@@ -318,50 +318,6 @@ chol_back_kernel(const double* __restrict__ S, int m, double* __restrict__ B, in
     for (int r = 0; r < PB; ++r) if (r < nb) B[(size_t)(j0 + r) * k + col] = z[r];
 }
 
-// Gauss-Jordan inverse with partial pivoting (np.linalg.inv of da.py:119), one CTA, in place:
-// A <- inv(A); `work` [m][m] receives the running inverse.
-__global__ void __launch_bounds__(1024)
-inverse_kernel(double* __restrict__ A, double* __restrict__ W, int m, int* __restrict__ info)
-{
-    const int tid = threadIdx.x;
-    __shared__ int piv;
-    __shared__ double pval;
-    for (int e = tid; e < m * m; e += blockDim.x) W[e] = (e / m == e % m) ? 1.0 : 0.0;
-    __syncthreads();
-    for (int j = 0; j < m; ++j) {
-        if (tid == 0) {
-            int best = j; double bv = fabs(A[(size_t)j * m + j]);
-            for (int i = j + 1; i < m; ++i) { const double v = fabs(A[(size_t)i * m + j]); if (v > bv) { bv = v; best = i; } }
-            piv = best; pval = A[(size_t)best * m + j];
-            if (bv == 0.0) { *info = j + 1; pval = 1.0; }
-        }
-        __syncthreads();
-        const int pr = piv;
-        if (pr != j)
-            for (int c = tid; c < m; c += blockDim.x) {
-                double x = A[(size_t)j * m + c]; A[(size_t)j * m + c] = A[(size_t)pr * m + c]; A[(size_t)pr * m + c] = x;
-                x = W[(size_t)j * m + c]; W[(size_t)j * m + c] = W[(size_t)pr * m + c]; W[(size_t)pr * m + c] = x;
-            }
-        __syncthreads();
-        const double inv = 1.0 / pval;
-        for (int c = tid; c < m; c += blockDim.x) { A[(size_t)j * m + c] *= inv; W[(size_t)j * m + c] *= inv; }
-        __syncthreads();
-        // eliminate column j from every other row; each thread owns (row, column-chunk) pairs
-        for (int e = tid; e < m * m; e += blockDim.x) {
-            const int i = e / m, c = e - i * m;
-            if (i == j) continue;
-            const double f = A[(size_t)i * m + j];
-            if (f != 0.0 && c != j) A[e] -= f * A[(size_t)j * m + c];
-            W[e] -= f * W[(size_t)j * m + c];
-        }
-        __syncthreads();
-        for (int i = tid; i < m; i += blockDim.x) if (i != j) A[(size_t)i * m + j] = 0.0;
-        __syncthreads();
-    }
-    for (int e = tid; e < m * m; e += blockDim.x) A[e] = W[e];
-}
-
-
 // ---- ensemble-space (Woodbury) form of the innovation solve ----------------------------------------
 // With D = R + diag(Q[s,s]) constant between updates and its inverse precomputed, the m x m system
 // S W = dz,  S = HA HA^T/(Mt-1) + D,  collapses to an Mt x Mt one:
@@ -962,13 +918,6 @@ cudaError_t launch_spd_solve(double* S, double* B, int m, int k, int* info, cuda
         }
     }
     return cudaSuccess;
-}
-
-cudaError_t launch_inverse(double* A, double* W, int m, int* info, cudaStream_t st)
-{
-    inverse_kernel<<<1, 1024, 0, st>>>(A, W, m, info);
-    count_launch();
-    return cudaGetLastError();
 }
 
 cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const double* mean, const double* T, int ldt,

@@ -64,6 +64,7 @@ class KalmanFilter(BaseCallback):
         self.R_cov = np.asarray(R_cov, dtype=np.float64)[perm, :][:, perm]
         self._meas_times = self.measurements.index.astype(int).astype(float).values
         self._meas_values = np.ascontiguousarray(self.measurements.values, dtype=np.float64)
+        self.reach_indices = np.ascontiguousarray(self.reach_indices, dtype=np.int64)
         # device-resident matrices
         self._torch = torch
         dev = 'cuda'
@@ -72,7 +73,8 @@ class KalmanFilter(BaseCallback):
         self._R = torch.as_tensor(self.R_cov, device=dev)
         self._idx = torch.as_tensor(self.reach_indices, device=dev)
         self._P_prev = self._P
-        self.K = self.dz = self.gain = None
+        self._K_d = self._dz_d = self._gain_d = None
+        self._work = None
         self.saved_states = {}
         self.save_state()
 
@@ -137,42 +139,41 @@ class KalmanFilter(BaseCallback):
         net.unpack_dev(X, n, out)
         return out
 
-    def filter(self):
-        """da.py:91-136 on the device; model state is updated in place through its host views."""
+    # K, dz, gain of the last update stay on the device until somebody looks at them
+    K = property(lambda self: None if self._K_d is None else self._K_d.cpu().numpy())
+    dz = property(lambda self: None if self._dz_d is None else self._dz_d.cpu().numpy())
+    gain = property(lambda self: None if self._gain_d is None else self._gain_d.cpu().numpy())
+
+    def _device_filter(self, Z, keep_prior=False):
+        """One `txh_kf_filter` chain: covariance propagation, gain, covariance update and the in-place
+        state correction (da.py:112-126), no host round trip besides the measurement vector."""
         torch = self._torch
         mdl = self.model
         n, m = mdl.n, self.num_measurements
+        mdl._ensure_device()
+        mdl._sync_coeffs()
+        net, d = mdl.network, mdl._dev
+        if self._work is None:
+            self._work = torch.empty(net.kf_work_size(m), dtype=torch.float64, device='cuda')
+        f64 = dict(dtype=torch.float64, device='cuda')
+        P_prev = self._P if self._P.is_contiguous() else self._P.contiguous()
+        P_next = torch.empty((n, n), **f64)
+        P_prior = torch.empty((n, n), **f64) if keep_prior else None
+        K = torch.empty((n, m), **f64)
+        gain = torch.empty(n, **f64)
+        dz = torch.empty(m, **f64)
+        net.kf_filter(P_prev, P_next, P_prior, self._Q, self._R, self.reach_indices, Z, d['O'], d['I'], K, gain, dz,
+                      self._work)
+        mdl._device_advanced()
+        self._P, self._P_prev = P_next, P_prev
+        self._K_d, self._gain_d, self._dz_d = K, gain, dz
+        return P_prior
+
+    def filter(self):
+        """da.py:91-136 on the device; the model state is corrected in place in HBM."""
+        mdl = self.model
         Z = self.interpolate_input(mdl.datetime)
-        o_t_next = mdl.o_t_next
-        i_t_next = mdl.i_t_next
-        dz = Z - o_t_next[self.s]                                            # da.py:112
-        P_prev = self._P
-        P = self._aqat(P_prev)                                               # da.py:115
-        P += self._Q                                                         # da.py:117
-        Ps = P.index_select(1, self._idx).contiguous()                       # P[:, s]      n x m
-        S = Ps.index_select(0, self._idx).contiguous() + self._R             # P[s][:, s] + R
-        Sinv = inverse(S)                                                    # da.py:119
-        K = torch.empty((n, m), dtype=torch.float64, device='cuda')
-        dgemm(Ps, Sinv, K)                                                   # K = P[:, s] @ inv(...)
-        dz_d = torch.as_tensor(dz, device='cuda').reshape(m, 1).contiguous()
-        gain_d = torch.empty((n, 1), dtype=torch.float64, device='cuda')
-        dgemm(K, dz_d, gain_d)                                               # da.py:121
-        Prow = P.index_select(0, self._idx).contiguous()                     # P[s]         m x n
-        dgemm(K, Prow, P, alpha=-1.0, beta=1.0)                              # da.py:122: P - K @ P[s]
-        gain = gain_d.cpu().numpy()[:, 0]
-        # _apply_gain (nutils.py:116-134): o_gain = gain, i_gain[j] = sum of upstream gains
-        i_gain = np.zeros(n)
-        nz = mdl.endnodes != mdl.startnodes
-        np.add.at(i_gain, mdl.endnodes[nz], gain[nz])
-        i_t_next += i_gain                                                   # da.py:125 (in place)
-        o_t_next += gain                                                     # da.py:126
-        mdl.i_t_next = i_t_next
-        mdl.o_t_next = o_t_next
-        self._P = P
-        self._P_prev = P_prev
-        self.K = K.cpu().numpy()
-        self.dz = dz
-        self.gain = gain
+        self._device_filter(Z)
         self.datetime = mdl.datetime
 
 
@@ -218,41 +219,17 @@ class KalmanSmoother(KalmanFilter):
 
     def filter(self):
         """da.py:170-219."""
-        torch = self._torch
         mdl = self.model
-        n, m = mdl.n, self.num_measurements
         t = mdl.datetime
-        i_prior = mdl.i_t_next
-        o_prior = mdl.o_t_next
+        i_prior = mdl._peek_state('i_t_next')
+        o_prior = mdl._peek_state('o_t_next')
         Z = self.measurements.loc[t].values                                  # exact time, no interpolation
-        dz = Z - o_prior[self.s]
-        P_prev = self._P
-        P_prior = self._aqat(P_prev)
-        P_prior += self._Q
-        Ps = P_prior.index_select(1, self._idx).contiguous()
-        S = Ps.index_select(0, self._idx).contiguous() + self._R
-        Sinv = inverse(S)
-        K = torch.empty((n, m), dtype=torch.float64, device='cuda')
-        dgemm(Ps, Sinv, K)
-        gain_d = torch.empty((n, 1), dtype=torch.float64, device='cuda')
-        dgemm(K, torch.as_tensor(dz, device='cuda').reshape(m, 1).contiguous(), gain_d)
-        Prow = P_prior.index_select(0, self._idx).contiguous()
-        P_next = P_prior.clone()
-        dgemm(K, Prow, P_next, alpha=-1.0, beta=1.0)
-        gain = gain_d.cpu().numpy()[:, 0]
-        i_gain = np.zeros(n)
-        nz = mdl.endnodes != mdl.startnodes
-        np.add.at(i_gain, mdl.endnodes[nz], gain[nz])
-        i_next = i_prior + i_gain                                            # fresh arrays (da.py:203-206)
-        o_next = o_prior + gain
-        mdl.i_t_next = i_next
-        mdl.o_t_next = o_next
-        self._P_prev = P_prev
-        self._P = P_next
-        self.K = K.cpu().numpy(); self.dz = dz; self.gain = gain
-        self.i_hat_f[t] = i_next; self.i_hat_p[t] = np.array(i_prior)
-        self.o_hat_f[t] = o_next; self.o_hat_p[t] = np.array(o_prior)
-        self.P_p[t] = P_prior; self.P_f[t] = P_next
+        P_prior = self._device_filter(Z, keep_prior=True)
+        i_next = mdl._peek_state('i_t_next')                                 # fresh arrays (da.py:203-206)
+        o_next = mdl._peek_state('o_t_next')
+        self.i_hat_f[t] = i_next; self.i_hat_p[t] = i_prior
+        self.o_hat_f[t] = o_next; self.o_hat_p[t] = o_prior
+        self.P_p[t] = P_prior; self.P_f[t] = self._P
         self.datetimes.append(t)
         self.datetime = t
 
@@ -313,6 +290,7 @@ class EnsembleKalmanFilter(BaseCallback):
         self.num_measurements = m = self.measurements.shape[1]
         self._meas_times = self.measurements.index.astype(int).astype(float).values
         self._meas_values = np.ascontiguousarray(self.measurements.values, dtype=np.float64)
+        self.reach_indices = np.ascontiguousarray(self.reach_indices, dtype=np.int64)
         self.every = every
         self.group = group
         self.rank, self.world = 0, 1

@@ -149,6 +149,13 @@ class Muskingum:
     def _state_get(self, key):
         return self._materialise()[key]
 
+    def _peek_state(self, key):
+        """A private copy of a state array that leaves the device copy authoritative."""
+        dirty = self._host_dirty
+        v = np.array(self._materialise()[key])
+        self._host_dirty = dirty
+        return v
+
     def _state_set(self, key, value):
         h = self._materialise()
         h[key] = value

@@ -15,8 +15,18 @@ def _cuda_ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_raw_stream = None
+
+
 def _stream_ptr():
+    """The current torch stream as a cudaStream_t (the raw getter: `current_stream()` builds a Python
+    Stream object on every call, 15 us -- more than a launch)."""
+    global _raw_stream
     import torch
+    if _raw_stream is None:
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", False)
+    if _raw_stream:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -182,20 +192,13 @@ class RiverNetwork:
         d.update(tasks=tasks, hdr=hdr, inw=inw[:d["n_words"]], prod=prod[:d["n_prod"]])
         return d
 
-    def window_schedule(self):
-        info = np.zeros(8, dtype=np.int64)
-        L.check(self._lib.txh_get_window_info(self.handle, L.ptr_i64(info)))
-        keys = ["n_tasks", "n_slots", "max_len", "max_words", "max_prod", "n_words", "n_prod", "cp_tasks"]
-        d = dict(zip(keys, (int(x) for x in info)))
-        tasks = np.empty((d["n_tasks"], 12), dtype=np.int32)
+    def sweep_order(self):
+        """Depth-first order of the small-network kernel: (reach_of_row [n], hdr [n], slots)."""
+        rows = np.empty(self.n, dtype=np.int64)
         hdr = np.empty(self.n, dtype=np.uint32)
-        inw = np.empty(max(1, d["n_words"]), dtype=np.uint32)
-        prod = np.empty(max(1, d["n_prod"]), dtype=np.int32)
-        L.check(self._lib.txh_get_window_schedule(
-            self.handle, tasks.ctypes.data_as(L.p_i32), hdr.ctypes.data_as(L.p_u32), inw.ctypes.data_as(L.p_u32),
-            prod.ctypes.data_as(L.p_i32)))
-        d.update(tasks=tasks, hdr=hdr, inw=inw[:d["n_words"]], prod=prod[:d["n_prod"]])
-        return d
+        slots = np.zeros(1, dtype=np.int64)
+        L.check(self._lib.txh_get_sweep(self.handle, L.ptr_i64(rows), hdr.ctypes.data_as(L.p_u32), L.ptr_i64(slots)))
+        return rows, hdr, int(slots[0])
 
     # ---- coefficients ---------------------------------------------------------------------
     def compute_coeffs(self, K, X, dt):
@@ -288,6 +291,19 @@ class RiverNetwork:
         L.check(self._lib.txh_enkf_stats(self.handle, _cuda_ptr(O), int(Mloc), L.ptr_i64(idx), idx.size,
                                          float(scale), _cuda_ptr(rowsum) if rowsum is not None else None,
                                          _cuda_ptr(HX), _stream_ptr()))
+
+    def kf_work_size(self, m):
+        return int(self._lib.txh_kf_work_size(self.handle, int(m)))
+
+    def kf_filter(self, P_in, P_out, P_prior, Q, R, obs_reach, z, O, I, K, gain, dz, work):
+        """KalmanFilter.filter (da.py:91-136) as one chain of launches; `z` is the host measurement vector."""
+        idx = L.as_i64(obs_reach)
+        zz = L.as_f64(z)
+        L.check(self._lib.txh_kf_filter(self.handle, _cuda_ptr(P_in), _cuda_ptr(P_out),
+                                        _cuda_ptr(P_prior) if P_prior is not None else None, _cuda_ptr(Q),
+                                        _cuda_ptr(R), L.ptr_i64(idx), idx.size, L.ptr_f64(zz), _cuda_ptr(O),
+                                        _cuda_ptr(I), _cuda_ptr(K), _cuda_ptr(gain), _cuda_ptr(dz), _cuda_ptr(work),
+                                        _stream_ptr()))
 
     @staticmethod
     def enkf_work_size(m, Mtot):
