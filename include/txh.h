@@ -79,11 +79,6 @@ int txh_get_window_info(const txh_net* net, int64_t info[8]);
 int txh_get_window_schedule(const txh_net* net, int32_t* wtask_desc, uint32_t* whdr /*[n]*/, uint32_t* winw,
                             int32_t* wprod);
 
-/* depth-first sweep order of small networks (route_sweep_kernel; header bits in txh_topology.hpp): the reach of
- * every sweep row, its header word, and the number of scratch slots a warp needs.  TXH_E_INVALID if the
- * network has no sweep order (a reach with > 256 upstream reaches, or a park stack deeper than 126). */
-int txh_get_sweep(const txh_net* net, int64_t* reach_of_row /*[n]*/, uint32_t* hdr /*[n]*/, int64_t* slots);
-
 /* ---- coefficients ----------------------------------------------------------------
  * txh_compute_coeffs replaces Muskingum.compute_muskingum_coeffs (muskingum.py:332-360):
  * host arithmetic in the reference's operation order; results returned in reach order

@@ -198,46 +198,3 @@ def simulate_window(w, coef, O, I, q_of_step, nsteps):
         done[k] = True
     assert np.isnan(ring).all(), "a published row was never consumed (the ring would not be clean for the next launch)"
     return executed
-
-
-def simulate_sweep(rows, hdr, slots, end, coef, o, i=None, q=None):
-    """Test-only CPU interpreter of the depth-first sweep (`txh_get_sweep`, route_sweep_kernel): one pass over
-    the rows with an accumulator and a stack of parked rows, exactly the reads and writes the kernel does.
-    coef [n][4] in reach order.  i is None: the homogeneous operator of nutils.py:148-154 (i_prev rebuilt from
-    the old upstream outflows, self-loop included); else one step of _ax_bu.  Returns (i_new, o_new)."""
-    n = rows.size
-    o_new = np.full(n, np.nan); i_new = np.full(n, np.nan)
-    park_old = np.full(max(1, slots), np.nan); park_new = np.full(max(1, slots), np.nan)
-    acc_old = acc_new = np.nan
-    seen = np.zeros(n, dtype=bool)
-    for k in range(n):
-        r = int(rows[k]); h = int(hdr[k])
-        in_new = acc_new if h & 1 else 0.0
-        in_old = acc_old if h & 1 else 0.0
-        base, cnt = (h >> 8) & 127, (h >> 15) & 255
-        for s in range(base, base + cnt):
-            assert not np.isnan(park_new[s]), "reads a slot nobody parked in"
-            in_old += park_old[s]; in_new += park_new[s]
-            park_old[s] = park_new[s] = np.nan
-        # the rows summed must be exactly the upstream reaches, each already evaluated
-        ups = np.flatnonzero((end == r) & (np.arange(n) != r))
-        assert seen[ups].all() and (1 if h & 1 else 0) + cnt == ups.size
-        if h & 1:
-            assert end[rows[k - 1]] == r
-        assert bool(h >> 31) == (end[r] == r)
-        a, b, c, g = coef[r]
-        if i is None:
-            if h >> 31:
-                in_old += o[r]
-            on = a * in_new + (b * in_old + c * o[r])
-        else:
-            on = a * in_new + (b * i[r] + (c * o[r] + g * (q[r] if q is not None else 0.0)))
-        o_new[r] = on; i_new[r] = in_new
-        ps = (h >> 1) & 127
-        if ps:
-            assert ps - 1 < slots and np.isnan(park_new[ps - 1]), "parks on top of a live slot"
-            park_old[ps - 1] = o[r]; park_new[ps - 1] = on
-        acc_old, acc_new = o[r], on
-        seen[r] = True
-    assert seen.all() and np.isnan(park_new).all()
-    return i_new, o_new

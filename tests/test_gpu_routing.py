@@ -42,11 +42,11 @@ def _upload(torch, net, o, i, M):
     return O, I
 
 
-@pytest.mark.parametrize("kernel", ["window", "sweep", "dataflow"])
+@pytest.mark.parametrize("kernel", ["window", "dataflow"])
 @pytest.mark.parametrize("fname", ["kernels_n60.npz", "kernels_n160.npz"])
 def test_golden_kernels(torch_cuda, libtxh, golden_dir, monkeypatch, fname, kernel):
     """Outputs of the unmodified reference's kernels; single steps and operator applications run on the
-    window kernel (the default), the depth-first sweep kernel and the dataflow kernel."""
+    window kernel (the default) and on the dataflow kernel."""
     monkeypatch.setenv("TXH_ROUTE_KERNEL", kernel)
     torch = torch_cuda
     g = np.load(os.path.join(golden_dir, fname))
@@ -152,43 +152,6 @@ def test_members_vs_oracle(torch_cuda, libtxh, oracle, monkeypatch, n, seed, M, 
     assert relerr(i_gpu, i_ref.T) < RTOL
     # member-major download agrees with reach-major
     assert (net.unpack_host(O, M, member_major=True) == o_gpu.T).all()
-
-
-@pytest.mark.parametrize("n,seed,M,basins", [(1, 13, 1, 1), (7, 12, 2, 1), (40, 3, 33, 1), (1000, 1, 1, 3),
-                                              (3000, 4, 70, 2), (8000, 6, 5, 1), (500, 9, 500, 1)])
-def test_sweep_vs_oracle(torch_cuda, libtxh, oracle, monkeypatch, n, seed, M, basins):
-    """route_sweep_kernel (one warp per 32 member columns walks the network depth first): three forced steps
-    == _ax_bu per member (nutils.py:64-89), and one operator application == a column of _ap
-    (nutils.py:143-155, self-loop inflow included), bit-compatible to FP64 round-off."""
-    monkeypatch.setenv("TXH_ROUTE_KERNEL", "sweep")
-    torch = torch_cuda
-    from tx_fast_hydrology_b200 import synthetic as S
-    net_d = S.make_network(n, seed, n_basins=basins)
-    prm = S.make_params(n, seed)
-    net, (al, be, ch, ga) = _setup(net_d["endnodes"], prm["K"], prm["X"], 300.0)
-    sn, en = net_d["startnodes"], net_d["endnodes"]
-    ind = oracle.compute_indegree(sn, en)
-    rng = np.random.default_rng(seed)
-    o0 = prm["o_t"][:, None] * rng.uniform(0.5, 1.5, size=(n, M))
-    i0 = np.stack([oracle.init_states(sn, en, o0[:, k]) for k in range(M)], 1)
-    O, I = _upload(torch, net, o0, i0, M)
-    o_ref, i_ref = o0.copy(), i0.copy()
-    for s in range(3):
-        q = rng.gamma(0.5, 2.0, n)
-        net.route_step(O, I, M, torch.from_numpy(q).cuda())
-        for k in range(M):
-            i_ref[:, k], o_ref[:, k] = oracle._ax_bu(sn[ind == 0], en, al, be, ch, ga, np.ascontiguousarray(i_ref[:, k]),
-                                                     np.ascontiguousarray(o_ref[:, k]), q, ind)
-    net.check()
-    assert relerr(net.unpack_host(O, M), o_ref) < RTOL and relerr(net.unpack_host(I, M), i_ref) < RTOL
-    X, _ = _upload(torch, net, o0, i0, M)
-    net.route_apply(X, net.alloc_state(M), M)
-    a_ref = np.empty_like(o0)
-    for k in range(M):
-        ip = np.zeros(n); oracle.numba_init_inflows(ip, en, np.ascontiguousarray(o0[:, k]))
-        _, a_ref[:, k] = oracle._ax(sn[ind == 0], en, al, be, ch, ip, np.ascontiguousarray(o0[:, k]), ind)
-    net.check()
-    assert relerr(net.unpack_host(X, M), a_ref) < RTOL
 
 
 def test_texas_scale_short(torch_cuda, libtxh, oracle):

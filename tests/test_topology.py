@@ -110,32 +110,6 @@ def test_schedule_protocol(libtxh, oracle, n, seed, sp, order):
     assert np.abs(Iw[pos] - Ir).max() <= 1e-12 * np.abs(Ir).max()
 
 
-@pytest.mark.parametrize("n,seed,basins", [(1, 1, 1), (2, 2, 1), (60, 3, 1), (1000, 4, 3), (5000, 5, 1)])
-def test_sweep_order(libtxh, oracle, n, seed, basins):
-    """The depth-first order of the small-network kernel (route_sweep_kernel): interpreted on the CPU it is
-    one _ax_bu step / one column of _ap (nutils.py:64-89, 143-155), every upstream reach comes before its
-    downstream one, parked rows form a stack no deeper than the slot count says."""
-    O = oracle
-    net = S.make_network(n, seed, n_basins=basins)
-    prm = S.make_params(n, seed)
-    rn = _net(libtxh, net["endnodes"])
-    en, sn = net["endnodes"], net["startnodes"]
-    rows, hdr, slots = rn.sweep_order()
-    assert sorted(rows.tolist()) == list(range(n)) and slots <= 2 * int(np.log2(n + 1)) + 2
-    a, b, c, g = rn.compute_coeffs(prm["K"], prm["X"], 300.0)
-    coef = np.stack([a, b, c, g], 1)
-    ind = O.compute_indegree(sn, en)
-    o0 = prm["o_t"]; i0 = O.init_states(sn, en, o0)
-    q = np.random.default_rng(seed).gamma(0.5, 2.0, n)
-    i1, o1 = sched_sim.simulate_sweep(rows, hdr, slots, en, coef, o0, i0, q)
-    Ir, Or = O._ax_bu(sn[ind == 0], en, a, b, c, g, i0, o0, q, ind)
-    assert np.abs(o1 - Or).max() <= 1e-13 * np.abs(Or).max() and np.abs(i1 - Ir).max() <= 1e-13 * np.abs(Ir).max()
-    _, o2 = sched_sim.simulate_sweep(rows, hdr, slots, en, coef, o0)
-    ip = np.zeros(n); O.numba_init_inflows(ip, en, o0)
-    _, Oa = O._ax(sn[ind == 0], en, a, b, c, ip, o0, ind)
-    assert np.abs(o2 - Oa).max() <= 1e-13 * np.abs(Oa).max()
-
-
 def test_texas_scale_schedule(libtxh):
     """BASELINE.json configs[1] network: ~100k reaches, ~1k levels; schedule statistics are sane."""
     net = S.make_network(100_000, 2)

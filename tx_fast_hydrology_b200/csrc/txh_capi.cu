@@ -82,13 +82,6 @@ struct txh_net {
     double* d_stage = nullptr; size_t stage_cap = 0;   // reach-order staging of txh_pack_host / txh_unpack_host
     double* stats_rowsum = nullptr;     // txh_set_stats_output: row sums of the final outflows of every routing call
     double stats_scale = 1.0;
-    // depth-first sweep of small networks (txh_sweep.cu), built on first use
-    Sweep sweep;
-    int sweep_state = 0;                // 0 not tried, 1 usable, -1 not usable for this network
-    unsigned char* d_sweep_rec = nullptr;
-    uint32_t* d_sweep_hdr = nullptr;
-    int32_t* d_sweep_row = nullptr;
-    bool sweep_rec_stale = true;        // records carry the coefficients: rebuilt after every coefficient upload
 };
 
 struct txh_forcing {
@@ -134,7 +127,6 @@ int ensure_device(txh_net* net)
     if (const char* k = getenv("TXH_ROUTE_KERNEL")) {
         if (!strcmp(k, "dataflow")) net->route_kernel = 1;
         else if (!strcmp(k, "window")) net->route_kernel = 2;
-        else if (!strcmp(k, "sweep")) net->route_kernel = 3;
     }
     CU(cudaMalloc((void**)&net->d_coef, sizeof(double) * (6 * net->topo.n + net->sched.link_last.size() + 1)));
     CU(cudaMalloc((void**)&net->d_qtmp, sizeof(double) * net->topo.n));
@@ -164,40 +156,7 @@ int ensure_coef(txh_net* net, cudaStream_t st)
                            cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));
         net->coef_dirty = false;
-        net->sweep_rec_stale = true;
     }
-    return TXH_OK;
-}
-
-// Single steps of small networks go to the sweep kernel: one warp per 32 member columns walks every reach, so
-// its time is n * ~25 ns whatever M is (up to the ~50k columns the SMs hold at once).
-
-int sweep_ready(txh_net* net, int64_t M, cudaStream_t st, bool* use)
-{
-    *use = false;
-    (void)M;
-    if (net->route_kernel != 3) return TXH_OK;            // opt-in (TXH_ROUTE_KERNEL=sweep): see DESIGN.md section 4.4
-    if (net->sweep_state == 0) {
-        net->sweep_state = -1;
-        if (net->sweep.build(net->topo) && sweep_smem_bytes(net->sweep.slots) <= 200 * 1024) {
-            std::vector<int32_t> row(net->topo.n);
-            for (int64_t k = 0; k < net->topo.n; ++k) row[k] = net->sched.pos_of_reach[net->sweep.reach_of_row[k]];
-            int rc;
-            if ((rc = upload(&net->d_sweep_hdr, net->sweep.hdr)) || (rc = upload(&net->d_sweep_row, row))) return rc;
-            CU(cudaMalloc((void**)&net->d_sweep_rec, sweep_record_bytes(net->topo.n)));
-            net->sweep_state = 1;
-            net->sweep_rec_stale = true;
-        }
-    }
-    if (net->sweep_state != 1) {
-        if (net->route_kernel == 3) return fail(TXH_E_INVALID, "TXH_ROUTE_KERNEL=sweep: this network has no sweep order");
-        return TXH_OK;
-    }
-    if (net->sweep_rec_stale) {
-        CU(launch_sweep_records(net->d_sweep_hdr, net->d_sweep_row, net->d_coef, (int)net->topo.n, net->d_sweep_rec, st));
-        net->sweep_rec_stale = false;
-    }
-    *use = true;
     return TXH_OK;
 }
 
@@ -490,7 +449,6 @@ void txh_destroy(txh_net* net)
     if (!net) return;
     if (net->dev_ready) {
         cudaFree(net->d_tasks); cudaFree(net->d_notify); cudaFree(net->d_init_ready); cudaFree(net->d_hdr); cudaFree(net->d_inw);
-        cudaFree(net->d_sweep_rec); cudaFree(net->d_sweep_hdr); cudaFree(net->d_sweep_row);
         cudaFree(net->d_up_off); cudaFree(net->d_up_pos); cudaFree(net->d_lvl_pos);
         cudaFree(net->d_reach_of_pos); cudaFree(net->d_pos_of_reach); cudaFree(net->d_outlet);
         cudaFree(net->d_coef); cudaFree(net->d_qtmp); cudaFree(net->d_qctl); cudaFree(net->d_rec_slot);
@@ -589,17 +547,6 @@ int txh_get_window_schedule(const txh_net* net, int32_t* wtask_desc, uint32_t* w
     if (whdr) std::memcpy(whdr, s.whdr.data(), s.whdr.size() * sizeof(uint32_t));
     if (winw) std::memcpy(winw, s.winw.data(), s.winw.size() * sizeof(uint32_t));
     if (wprod) std::memcpy(wprod, s.wprod.data(), s.wprod.size() * sizeof(int32_t));
-    return TXH_OK;
-}
-
-int txh_get_sweep(const txh_net* net, int64_t* reach_of_row, uint32_t* hdr, int64_t* slots)
-{
-    if (!net || !reach_of_row || !hdr || !slots) return fail(TXH_E_INVALID, "null argument");
-    Sweep sw;
-    if (!sw.build(net->topo)) return fail(TXH_E_INVALID, "this network has no sweep order");
-    widen(sw.reach_of_row, reach_of_row);
-    std::copy(sw.hdr.begin(), sw.hdr.end(), hdr);
-    *slots = sw.slots;
     return TXH_OK;
 }
 
@@ -834,13 +781,6 @@ int txh_route_step(txh_net* net, double* O, double* I, int64_t M, const double* 
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = check_M(M)) || (rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
     if (q) CU(launch_permute_vec(net->d_reach_of_pos, q, net->d_qtmp, net->topo.n, st));
-    bool sweep = false;
-    if ((rc = sweep_ready(net, M, st, &sweep))) return rc;
-    if (sweep) {
-        CU(launch_route_sweep(net->d_sweep_rec, (int)net->topo.n, net->sweep.slots, O, I, q ? net->d_qtmp : nullptr,
-                              (int)txh_row_stride(M), (int)M, false, st));
-        return TXH_OK;
-    }
     return run_one_step(net, O, I, M, q ? net->d_qtmp : nullptr, st);
 }
 
@@ -869,13 +809,6 @@ int txh_route_apply(txh_net* net, double* X, double* Iscr, int64_t M, void* stre
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = check_M(M)) || (rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
     // nutils.py:148-154: i_prev = init_inflows(o_prev) (self-loop included), then _ax
-    bool sweep = false;
-    if ((rc = sweep_ready(net, M, st, &sweep))) return rc;
-    if (sweep) {
-        CU(launch_route_sweep(net->d_sweep_rec, (int)net->topo.n, net->sweep.slots, X, nullptr, nullptr,
-                              (int)txh_row_stride(M), (int)M, true, st));
-        return TXH_OK;
-    }
     CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, X, Iscr, net->topo.n,
                            (int)txh_row_stride(M), (int)M, st));
     return run_one_step(net, X, Iscr, M, nullptr, st);
@@ -1120,22 +1053,12 @@ int txh_kf_filter(txh_net* net, const double* P_in, double* P_out, double* P_pri
     double* zd = Gp + up4(2 * n);
     CU(cudaMemcpyAsync(zd, z, sizeof(double) * m, cudaMemcpyHostToDevice, st));
     // P- = A (A P)^T + Q, nutils.py:194-214 (X2 doubles as the inflow scratch of the first pass and vice versa)
-    bool sweep = false;
-    if ((rc = sweep_ready(net, n, st, &sweep))) return rc;
     CU(launch_pack(net->d_reach_of_pos, P_in, X, n, (int)n, ld, 0, st));
-    if (sweep) {
-        CU(launch_route_sweep(net->d_sweep_rec, (int)n, net->sweep.slots, X, nullptr, nullptr, ld, (int)n, true, st));
-    } else {
-        CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, X, X2, n, ld, (int)n, st));
-        if ((rc = run_one_step(net, X, X2, n, nullptr, st))) return rc;
-    }
+    CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, X, X2, n, ld, (int)n, st));
+    if ((rc = run_one_step(net, X, X2, n, nullptr, st))) return rc;
     CU(launch_kf_repack_transposed(net->d_reach_of_pos, net->d_pos_of_reach, X, X2, (int)n, ld, st));
-    if (sweep) {
-        CU(launch_route_sweep(net->d_sweep_rec, (int)n, net->sweep.slots, X2, nullptr, nullptr, ld, (int)n, true, st));
-    } else {
-        CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, X2, X, n, ld, (int)n, st));
-        if ((rc = run_one_step(net, X2, X, n, nullptr, st))) return rc;
-    }
+    CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, X2, X, n, ld, (int)n, st));
+    if ((rc = run_one_step(net, X2, X, n, nullptr, st))) return rc;
     CU(launch_kf_prior_finish(net->d_reach_of_pos, net->d_pos_of_reach, net->d_gauge_of_pos, X2, ld, Q, R, (int)n, (int)m,
                               Pm, Ps, Prow, S, st));
     // K = P-[:, s] inv(P-[s][:, s] + R)   (da.py:119)

@@ -155,14 +155,6 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
 cudaError_t launch_inflow_gain(const int32_t* up_off, const int32_t* up_pos, const double* G, double* I, int64_t n,
                                int ld, cudaStream_t st);
 
-// ---- depth-first sweep of a small network, one warp per 32 member columns (txh_sweep.cu) -------------
-size_t sweep_record_bytes(int64_t n);
-size_t sweep_smem_bytes(int slots);
-cudaError_t launch_sweep_records(const uint32_t* hdr, const int32_t* row, const double* coef, int n, unsigned char* rec,
-                                 cudaStream_t st);
-cudaError_t launch_route_sweep(const unsigned char* rec, int n, int slots, double* X, double* I, const double* q, int ld,
-                               int M, bool apply, cudaStream_t st);
-
 // ---- dense per-sub-basin filter glue (txh_kf.cu) ---------------------------------------------------
 cudaError_t launch_kf_repack_transposed(const int32_t* reach_of_pos, const int32_t* pos_of_reach, const double* X,
                                         double* X2, int n, int ld, cudaStream_t st);

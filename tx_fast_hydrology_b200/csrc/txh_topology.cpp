@@ -683,53 +683,4 @@ bool Schedule::build(const Topology& t, const SchedParams& p_in, std::string& er
     return true;
 }
 
-bool Sweep::build(const Topology& t)
-{
-    const int32_t n = (int32_t)t.n;
-    reach_of_row.clear(); hdr.clear(); slots = 0;
-    reach_of_row.reserve(n); hdr.reserve(n);
-    // slots the subtree of a reach needs while it is evaluated: its i-th upstream reach (0-based) is walked
-    // with i earlier ones parked, so walk them in decreasing order of their own need
-    std::vector<int32_t> need(n, 0), ord(t.child);
-    for (int32_t idx = 0; idx < n; ++idx) {
-        const int32_t j = t.topo[idx];
-        int32_t* b = ord.data() + t.child_off[j];
-        int32_t* e = ord.data() + t.child_off[j + 1];
-        std::stable_sort(b, e, [&](int32_t x, int32_t y) { return need[x] > need[y]; });
-        int32_t nd = 0;
-        for (int32_t i = 0; b + i < e; ++i) nd = std::max(nd, i + need[b[i]]);
-        need[j] = nd;
-        if (e - b > 256) return false;
-    }
-    struct Frame { int32_t node, base, idx; };
-    std::vector<Frame> st;
-    std::vector<int32_t> park(n, -1);
-    for (int32_t root = 0; root < n; ++root) {
-        if (t.end[root] != root) continue;
-        st.push_back({root, 0, 0});
-        while (!st.empty()) {
-            Frame& f = st.back();
-            const int32_t off = t.child_off[f.node], nc = t.child_off[f.node + 1] - off;
-            if (f.idx < nc) {
-                const int32_t c = ord[off + f.idx], cb = f.base + f.idx;
-                park[c] = f.idx < nc - 1 ? cb : -1;
-                ++f.idx;
-                st.push_back({c, cb, 0});
-                continue;
-            }
-            const int32_t parked = nc > 0 ? nc - 1 : 0;
-            if (parked > 0) slots = std::max(slots, f.base + parked);
-            if (f.base + parked > 126) return false;
-            uint32_t h = (nc > 0 ? 1u : 0u) | ((uint32_t)(park[f.node] + 1) << 1) | ((uint32_t)f.base << 8) |
-                         ((uint32_t)parked << 15);
-            if (t.end[f.node] == f.node) h |= SWEEP_OUTLET;
-            reach_of_row.push_back(f.node);
-            hdr.push_back(h);
-            st.pop_back();
-        }
-    }
-    return (int32_t)reach_of_row.size() == n;
-}
-
-
 }  // namespace txh

@@ -147,24 +147,4 @@ struct Schedule {
     bool build(const Topology& t, const SchedParams& p, std::string& err);
 };
 
-// Depth-first sweep of the whole network by ONE warp per block of member columns (route_sweep_kernel): the
-// latency-optimal order for small networks (per-sub-basin models of 10^2..10^4 reaches, the reference's
-// operational case, app/app.py:121-166), where cross-SM hand-overs would cost more than walking every reach.
-// Post-order: every reach comes after everything upstream of it and directly after its LAST upstream
-// reach, whose outflow it takes from the running accumulator; the other upstream reaches were parked in
-// scratch slots, allocated as a stack (upstream reaches are visited in decreasing order of the slots their
-// own subtrees need, so the stack stays within ~log2(n) rows).
-//   hdr bit 0       inflow starts from the accumulator (the previous row is an upstream reach)
-//       bits 1..7   (slot + 1) the outflow is parked in, 0 = none
-//       bits 8..14  first slot holding a parked upstream reach
-//       bits 15..22 number of parked upstream reaches (consecutive slots)
-//       bit 31      outlet (self-loop)
-constexpr uint32_t SWEEP_OUTLET = 0x80000000u;
-struct Sweep {
-    std::vector<int32_t> reach_of_row;
-    std::vector<uint32_t> hdr;
-    int32_t slots = 0;
-    bool build(const Topology& t);          // false: a reach has too many upstream reaches / too deep a stack
-};
-
 }  // namespace txh

@@ -192,14 +192,6 @@ class RiverNetwork:
         d.update(tasks=tasks, hdr=hdr, inw=inw[:d["n_words"]], prod=prod[:d["n_prod"]])
         return d
 
-    def sweep_order(self):
-        """Depth-first order of the small-network kernel: (reach_of_row [n], hdr [n], slots)."""
-        rows = np.empty(self.n, dtype=np.int64)
-        hdr = np.empty(self.n, dtype=np.uint32)
-        slots = np.zeros(1, dtype=np.int64)
-        L.check(self._lib.txh_get_sweep(self.handle, L.ptr_i64(rows), hdr.ctypes.data_as(L.p_u32), L.ptr_i64(slots)))
-        return rows, hdr, int(slots[0])
-
     # ---- coefficients ---------------------------------------------------------------------
     def compute_coeffs(self, K, X, dt):
         K = L.as_f64(K); X = L.as_f64(X)
