@@ -179,7 +179,9 @@ int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX_dev /
                    double* work_dev /* txh_enkf_work_size(m, Mtot) doubles */,
                    double* W_dev /*[m][Mtot] out*/, double* T_dev /*[Mtot][Mtot] out*/, void* stream);
 int txh_enkf_apply(txh_net* net, double* O_dev, double* I_dev, int64_t Mloc, const double* Xall_dev /* [n][ldx] gathered
-                   ensemble in schedule order, or NULL to use O_dev (Mtot == Mloc) */, int64_t ldx, int64_t Mtot,
+                   ensemble in schedule order, or NULL to use O_dev (Mtot == Mloc) */, int64_t ldx,
+                   int64_t x_block_stride /* 0: one [n][ldx] matrix; else Xall is Mtot/Mloc blocks of [n][ldx], this
+                   many doubles apart, block b = the state rows of shard b (an all-gather of O_dev) */, int64_t Mtot,
                    int64_t col0 /* first global member of this shard */, const double* mean_dev, const double* T_dev,
                    const int64_t* obs_reach_host, int64_t m, const double* qs_dev, const double* W_dev,
                    double* G_dev /* scratch, same shape as O_dev */, void* stream);

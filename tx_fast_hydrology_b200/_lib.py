@@ -63,7 +63,7 @@ SIGNATURES = {
     "txh_enkf_work_size": (c_i64, [c_i64, c_i64]),
     "txh_enkf_solve": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, p_i64, c_vp, c_vp, c_vp, ctypes.c_int,
                                       c_vp, c_vp, c_vp, c_vp]),
-    "txh_enkf_apply": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, p_i64, c_i64,
+    "txh_enkf_apply": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, p_i64, c_i64,
                                       c_vp, c_vp, c_vp, c_vp]),
     "txh_dgemm": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_i64, c_i64, c_i64, c_f64, c_vp, c_i64, c_vp, c_i64,
                                  c_f64, c_vp, c_i64, c_vp]),

@@ -950,8 +950,8 @@ int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, cons
     return TXH_OK;
 }
 
-int txh_enkf_apply(txh_net* net, double* O, double* I, int64_t Mloc, const double* Xall, int64_t ldx, int64_t Mtot,
-                   int64_t col0, const double* mean, const double* T, const int64_t* obs, int64_t m, const double* qs,
+int txh_enkf_apply(txh_net* net, double* O, double* I, int64_t Mloc, const double* Xall, int64_t ldx,
+                   int64_t x_block_stride, int64_t Mtot, int64_t col0, const double* mean, const double* T, const int64_t* obs, int64_t m, const double* qs,
                    const double* W, double* G, void* stream)
 {
     if (!net || !O || !I || !mean || !T || !obs || !qs || !W || !G) return fail(TXH_E_INVALID, "null argument");
@@ -962,14 +962,17 @@ int txh_enkf_apply(txh_net* net, double* O, double* I, int64_t Mloc, const doubl
     int32_t* d_pos = nullptr;
     if ((rc = obs_positions(net, obs, m, st, &d_pos))) return rc;
     const int ld = (int)txh_row_stride(Mloc);
-    if (!Xall) { if (Mtot != Mloc) return fail(TXH_E_INVALID, "gathered ensemble missing"); Xall = O; ldx = ld; }
+    if (!Xall) { if (Mtot != Mloc) return fail(TXH_E_INVALID, "gathered ensemble missing"); Xall = O; ldx = ld; x_block_stride = 0; }
+    if (x_block_stride != 0 && (Mtot % Mloc != 0 || ldx < Mloc)) return fail(TXH_E_INVALID, "bad gathered-ensemble layout");
+    const int Mb = x_block_stride != 0 ? (int)Mloc : (int)Mtot;
     // O += gain and G = gain (tensor cores), gauge rows, then I += sum of the upstream gains.  The in-place
     // update of O is row-local; when the ensemble being transformed IS O and a row spans several 64-column
     // groups, a later group would read members an earlier one has already updated: then O is updated from G
     // afterwards instead.
     const bool fuse_o = Xall != O || ld <= 64;
     CU(launch_enkf_update(Xall, (int)ldx, (int)Mtot, mean, T + col0, (int)Mtot, (int)Mloc, fuse_o ? O : nullptr, G, ld,
-                          net->topo.n, net->d_gauge_of_pos, qs, W, (int)col0, net->num_sms, st));
+                          net->topo.n, net->d_gauge_of_pos, qs, W, (int)col0, net->num_sms, Mb, (long long)x_block_stride,
+                          st));
     if (fuse_o) CU(launch_inflow_gain(net->d_up_off, net->d_up_pos, G, I, net->topo.n, ld, st));
     else CU(launch_apply_gain(net->d_up_off, net->d_up_pos, G, O, I, net->topo.n, ld, (int)Mloc, st));
     return TXH_OK;

@@ -540,14 +540,16 @@ __global__ void __launch_bounds__(EU_WARPS * 32)
 enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const double* __restrict__ mean,
                    const double* __restrict__ T, int ldt, int Mloc, double* __restrict__ O, double* __restrict__ G,
                    int ld, long long n, const int32_t* __restrict__ gauge_of_pos, const double* __restrict__ qs,
-                   const double* __restrict__ W, int col0, int resident)
+                   const double* __restrict__ W, int col0, int resident, int Mb, long long blk_stride)
 {
+    // Xall: Mtot / Mb blocks of [n][ldx], block b holding members b*Mb .. (b+1)*Mb - 1 (what an all-gather of
+    // the shards' state rows produces); Mb == Mtot: one matrix
     // `resident`: every 64-member k chunk of T has its own block of shared memory and is staged once per CTA
     // (single column group); otherwise one block is restaged for every (row tile, chunk)
     extern __shared__ double sT_all[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const bool vec = (ldx & 1) == 0;
+    const bool vec = (ldx & 1) == 0 && (Mb & 1) == 0;
     const int nkc = (Mtot + 63) / 64, ncg = (ld + 63) / 64;
     for (long long r0 = (long long)blockIdx.x * EU_ROWS; r0 < n; r0 += (long long)gridDim.x * EU_ROWS) {
         const long long rw = r0 + warp * 16;
@@ -578,18 +580,20 @@ enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const dou
                 for (int i = 0; i < 2; ++i) {
                     const long long row = i ? row1 : row0;
                     const double mu = i ? mu1 : mu0;
-                    const double* xr = Xall + (size_t)(row < n ? row : 0) * ldx;
+                    const double* xrow = Xall + (size_t)(row < n ? row : 0) * ldx;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int k = kc * 64 + 8 * j + 2 * t;
                         double x0 = mu, x1 = mu;
                         if (row < n) {
+                            const int b = k / Mb, kk = k - b * Mb;
+                            const double* xr = xrow + (size_t)b * blk_stride + kk;
                             if (vec && k + 1 < Mtot) {
-                                const double2 v = *reinterpret_cast<const double2*>(xr + k);
+                                const double2 v = *reinterpret_cast<const double2*>(xr);
                                 x0 = v.x; x1 = v.y;
                             } else {
-                                if (k < Mtot) x0 = xr[k];
-                                if (k + 1 < Mtot) x1 = xr[k + 1];
+                                if (k < Mtot) x0 = xr[0];
+                                if (k + 1 < Mtot) x1 = (kk + 1 < Mb) ? xr[1] : xrow[(size_t)(b + 1) * blk_stride];
                             }
                         }
                         a[i][2 * j] = x0 - mu; a[i][2 * j + 1] = x1 - mu;
@@ -922,7 +926,8 @@ cudaError_t launch_spd_solve(double* S, double* B, int m, int k, int* info, cuda
 
 cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const double* mean, const double* T, int ldt,
                                int Mloc, double* O, double* G, int ld, int64_t n, const int32_t* gauge_of_pos,
-                               const double* qs, const double* W, int col0, int num_sms, cudaStream_t st)
+                               const double* qs, const double* W, int col0, int num_sms, int Mb, long long blk_stride,
+                               cudaStream_t st)
 {
     long long tiles = (n + EU_ROWS - 1) / EU_ROWS;
     if (Mtot == Mloc && Mtot <= 64 && ld <= 64 && ldx == ld && col0 == 0) {
@@ -941,7 +946,7 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
     cudaError_t e = cudaFuncSetAttribute(enkf_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     enkf_update_kernel<<<(unsigned)grid, EU_WARPS * 32, smem, st>>>(Xall, ldx, Mtot, mean, T, ldt, Mloc, O, G, ld, n,
-                                                                    gauge_of_pos, qs, W, col0, resident);
+                                                                    gauge_of_pos, qs, W, col0, resident, Mb, blk_stride);
     count_launch();
     return cudaGetLastError();
 }

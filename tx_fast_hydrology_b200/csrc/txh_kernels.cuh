@@ -151,7 +151,8 @@ cudaError_t launch_spd_solve(double* S, double* B, int m, int k, int* info, cuda
 cudaError_t launch_inverse(double* A, double* W, int m, int* info, cudaStream_t st);
 cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const double* mean, const double* T, int ldt,
                                int Mloc, double* O, double* G, int ld, int64_t n, const int32_t* gauge_of_pos,
-                               const double* qs, const double* W, int col0, int num_sms, cudaStream_t st);
+                               const double* qs, const double* W, int col0, int num_sms, int Mb, long long blk_stride,
+                               cudaStream_t st);
 cudaError_t launch_inflow_gain(const int32_t* up_off, const int32_t* up_pos, const double* G, double* I, int64_t n,
                                int ld, cudaStream_t st);
 

@@ -376,21 +376,23 @@ class EnsembleKalmanFilter(BaseCallback):
         # one pass over the state: row sums (already the mean when the ensemble is not sharded) + gauge rows
         net.enkf_stats(O, M, self.reach_indices, None if stats_fresh else self._rowsum, self._HX,
                        scale=self.stats_scale())
-        Xall, ldx = None, 0
+        Xall, ldx, xstride, gather = None, 0, 0, None
         mean = self._rowsum
         if self.world > 1:
-            # ensemble mean over all shards (all-reduce) + every shard's gauge rows (all-gather)
+            # ensemble mean over all shards (all-reduce) + every shard's gauge rows (all-gather); the state rows
+            # of every shard follow on the collective stream while the small system is solved
             mean, self._HXall = combine_statistics(self._rowsum, self._HX, Mt, group=self.group)
             ld = net.row_stride(M)
             if self._Xall is None:
                 self._Xall = torch.empty((self.world, mdl.n, ld), dtype=torch.float64, device='cuda')
-            dist.all_gather_into_tensor(self._Xall, O, group=self.group)     # anomalies of every shard
-            Xall = self._Xall.permute(1, 0, 2)[:, :, :M].reshape(mdl.n, Mt).contiguous()
-            ldx = Mt
+            gather = dist.all_gather_into_tensor(self._Xall, O, group=self.group, async_op=True)
+            Xall, ldx, xstride = self._Xall, ld, mdl.n * ld
         net.enkf_solve(m, Mt, self._HXall, Zp_dev, mean, self.reach_indices, self._qs, self._R, self._work,
                        self._W, self._T, self._Dinv, self._dinv_kind)
+        if gather is not None:
+            gather.wait()
         net.enkf_apply(O, I, M, Xall, ldx, Mt, self.rank * M, mean, self._T, self.reach_indices, self._qs,
-                       self._W, self._G)
+                       self._W, self._G, x_block_stride=xstride)
         mdl._device_advanced()
         self.n_updates += 1
         self.datetime = mdl.datetime

@@ -308,10 +308,12 @@ class RiverNetwork:
                                          _cuda_ptr(Dinv) if Dinv is not None else None, int(dinv_kind),
                                          _cuda_ptr(work), _cuda_ptr(W), _cuda_ptr(T), _stream_ptr()))
 
-    def enkf_apply(self, O, I, Mloc, Xall, ldx, Mtot, col0, mean, T, obs_reach, qs, W, G):
+    def enkf_apply(self, O, I, Mloc, Xall, ldx, Mtot, col0, mean, T, obs_reach, qs, W, G, x_block_stride=0):
+        """`x_block_stride` != 0: Xall is the all-gather of the shards' state rows, [world][n][ldx]."""
         idx = L.as_i64(obs_reach)
         L.check(self._lib.txh_enkf_apply(self.handle, _cuda_ptr(O), _cuda_ptr(I), int(Mloc),
-                                         _cuda_ptr(Xall) if Xall is not None else None, int(ldx), int(Mtot),
+                                         _cuda_ptr(Xall) if Xall is not None else None, int(ldx),
+                                         int(x_block_stride), int(Mtot),
                                          int(col0), _cuda_ptr(mean), _cuda_ptr(T), L.ptr_i64(idx), idx.size,
                                          _cuda_ptr(qs), _cuda_ptr(W), _cuda_ptr(G), _stream_ptr()))
 
