@@ -320,9 +320,11 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     const int smem_max = 227 * 1024;
     int wpc = std::min(16, (smem_max - 1024) / a.smem_per_warp);
     if (wpc < 2 || s.w_n_own > 0) return 1;
-    // ring[step][slot][ld]: one launch covers at most 16 steps (and at most ~1 GiB of ring)
+    // ring[step][slot][ld]: one launch covers 16 steps, up to 64 while the ring stays below 64 MiB (few members):
+    // a launch costs the critical path of one step before its pipeline is full, so longer launches amortise it
     const size_t slot_row = (size_t)std::max(1, s.n_wslots) * ld;
-    int64_t spl = std::min<int64_t>(16, nsteps);
+    const int64_t spl_max = std::min<int64_t>(64, std::max<int64_t>(16, (int64_t)((size_t(64) << 20) / (slot_row * sizeof(double)))));
+    int64_t spl = std::min<int64_t>(spl_max, nsteps);
     while (spl > 1 && slot_row * spl * sizeof(double) > (size_t(1) << 30)) --spl;
     if (slot_row * spl > net->ring_cap) {
         // every cell starts EMPTY (all bits set); consumers put EMPTY back, so a finished launch leaves the whole

@@ -84,6 +84,7 @@ __device__ __forceinline__ void sts_u32(unsigned sa, uint32_t v)
 
 constexpr int kInRing = 4;                 // pockets: rows of other tasks in flight per warp (cp.async ring)
 constexpr int kSegRing = 8;                // segments: the ring also takes the (unused) scratch slots
+constexpr int kStepsStaged = 16;            // interpolation records of a launch kept in shared memory
 constexpr int kWinThreads = 512;           // one CTA per SM, up to 16 warps
 constexpr uint32_t kIdMask = 0x3fffffffu;
 
@@ -408,7 +409,17 @@ route_window_kernel(const WinArgs a)
 
         // ---- load the task: input stream, step records, per-row records; rows of I and O -> p ----
         for (int i = lane; i < td.n_words; i += 32) cp_async4(tk.sWords + 4u * i, a.inw + td.in_off + i);
-        if (HAS_F)                                             // the launch's interpolation records (24 B each)
+        // the launch's interpolation records (24 B each): staged when they fit (<= kStepsStaged), else read in place
+        const bool steps_staged = a.nsteps <= kStepsStaged;
+        auto step_rows = [&](int s) -> int2 {
+            if (steps_staged) return make_int2((int)lds_u32(sSteps + 24u * s), (int)lds_u32(sSteps + 24u * s + 4u));
+            return make_int2(__ldg(&a.steps[s].r0), __ldg(&a.steps[s].r1));
+        };
+        auto step_weights = [&](int s) -> double2 {
+            if (steps_staged) return make_double2(lds_f64(sSteps + 24u * s + 8u), lds_f64(sSteps + 24u * s + 16u));
+            return make_double2(__ldg(&a.steps[s].w0), __ldg(&a.steps[s].w1));
+        };
+        if (HAS_F && steps_staged)
             for (int i = lane; i < 6 * a.nsteps; i += 32) cp_async4(sSteps + 4u * i, reinterpret_cast<const uint32_t*>(a.steps) + i);
         cp_async_commit();
         for (int i = lane; i < len; i += 32) {
@@ -459,8 +470,10 @@ route_window_kernel(const WinArgs a)
             FCtx c;
             c.w0 = c.w1 = 0.0; c.wm0 = c.wm1 = make_double2(0.0, 0.0);
             if (HAS_F) {
-                const int r0 = (int)lds_u32(sSteps + 24u * s), r1 = (int)lds_u32(sSteps + 24u * s + 4u);
-                c.w0 = lds_f64(sSteps + 24u * s + 8u); c.w1 = lds_f64(sSteps + 24u * s + 16u);
+                const int2 rr = step_rows(s);
+                const int r0 = rr.x, r1 = rr.y;
+                const double2 ww = step_weights(s);
+                c.w0 = ww.x; c.w1 = ww.y;
                 if (HAS_W) {
                     const int c0 = min(col, a.wm_ld - 1), c1 = min(col + 1, a.wm_ld - 1);
                     const double* m0 = a.Wmul + (size_t)r0 * a.wm_ld;
@@ -489,7 +502,8 @@ route_window_kernel(const WinArgs a)
             char* ringS = reinterpret_cast<char*>(a.ring + ccol) + (size_t)s * tk.step_bytes;
             const FCtx fc = fc_next;
             if (HAS_F) {
-                const int r0 = (int)lds_u32(sSteps + 24u * s), r1 = (int)lds_u32(sSteps + 24u * s + 4u);
+                const int2 rr = step_rows(s);
+                const int r0 = rr.x, r1 = rr.y;
                 if (r0 != cur_r0 || r1 != cur_r1) {              // a new bracket of the forcing table
                     const double* F0 = a.F + (size_t)r0 * a.n + td.begin;
                     const double* F1 = a.F + (size_t)r1 * a.n + td.begin;
