@@ -421,6 +421,13 @@ route_window_kernel(const WinArgs a)
         };
         if (HAS_F && steps_staged)
             for (int i = lane; i < 6 * a.nsteps; i += 32) cp_async4(sSteps + 4u * i, reinterpret_cast<const uint32_t*>(a.steps) + i);
+        // rows of O straight into their p slots, rows of I (eight at a time) into the scratch / ring area: every
+        // load of the task is in flight before the first is waited for
+        if (active)
+            for (int r = 0; r < len; ++r) {
+                cp_async16(tk.sP + 512u * r, tk.Og + (size_t)r * ld);
+                if (r < 8) cp_async16(tk.sScr + 512u * r, tk.Ig + (size_t)r * ld);
+            }
         cp_async_commit();
         for (int i = lane; i < len; i += 32) {
             const double2 ab = *reinterpret_cast<const double2*>(a.coef + 4 * (size_t)(td.begin + i));
@@ -433,23 +440,24 @@ route_window_kernel(const WinArgs a)
             sts_f64(tk.sCum + 8u * i, a.cumA[td.begin + i]);
             sts_f64(tk.sCumC + 8u * i, a.cumC[td.begin + i]);
         }
-        // rows: the loads of a batch are all in flight before the first is used
-        for (int r0 = 0; r0 < len; r0 += 4) {
-            double2 io[4], oo[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (active && r0 + u < len) { io[u] = ld_row(tk.Ig + (size_t)(r0 + u) * ld); oo[u] = ld_row(tk.Og + (size_t)(r0 + u) * ld); }
-                else { io[u] = make_double2(0.0, 0.0); oo[u] = io[u]; }
-            if (r0 == 0) { cp_async_wait_all(); __syncwarp(); }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (r0 + u < len) {
-                    const double2 bc = lds_row(tk.sRec + kRec * (r0 + u) + 16u);
-                    double2 p;
-                    p.x = bc.x * io[u].x + bc.y * oo[u].x;
-                    p.y = bc.x * io[u].y + bc.y * oo[u].y;
-                    sts_row(tk.sP + (r0 + u) * 512u, p);
+        for (int r0 = 0; r0 < len; r0 += 8) {
+            if (r0 > 0) {
+                if (active)
+                    for (int r = r0; r < len && r < r0 + 8; ++r) cp_async16(tk.sScr + 512u * (r - r0), tk.Ig + (size_t)r * ld);
+                cp_async_commit();
+            }
+            cp_async_wait_all();
+            __syncwarp();
+            for (int r = r0; r < len && r < r0 + 8; ++r) {
+                const double2 bc = lds_row(tk.sRec + kRec * r + 16u);
+                double2 p = make_double2(0.0, 0.0);
+                if (active) {
+                    const double2 oo = lds_row(tk.sP + 512u * r), io = lds_row(tk.sScr + 512u * (r - r0));
+                    p.x = bc.x * io.x + bc.y * oo.x;
+                    p.y = bc.x * io.y + bc.y * oo.y;
                 }
+                sts_row(tk.sP + 512u * r, p);
+            }
         }
         // rows of other tasks consumed through the input ring, in consumption order: byte offsets of their slots
         int nL = 0;
