@@ -186,6 +186,21 @@ int txh_enkf_apply(txh_net* net, double* O_dev, double* I_dev, int64_t Mloc, con
                    const int64_t* obs_reach_host, int64_t m, const double* qs_dev, const double* W_dev,
                    double* G_dev /* scratch, same shape as O_dev */, void* stream);
 
+/* The whole assimilating run of an unsharded ensemble in one call: `every` routing steps per launch (the row
+ * sums ride on its last step), then one ensemble update with Zp_dev[k] ([m][M], the k-th update's per-member
+ * observations), nsteps / every times, then the remaining steps -- the loop of simulate + a filter callback
+ * gated to every `every`-th step (muskingum.py:527-536, da.py:56-61), with the host out of it.
+ * time_every > 0: every time_every-th routing launch is bracketed by CUDA events on `stream` (kept over
+ * calls, at most 4096); txh_get_route_timings synchronises them, returns their durations (ms) and, when
+ * `capacity` covers them all, releases them (capacity 0: just count). */
+int txh_run_assimilating(txh_net* net, double* O_dev, double* I_dev, int64_t M, const txh_forcing* forcing,
+                         int64_t t0_ns, int64_t dt_ns, int64_t nsteps, int64_t every, int method,
+                         const int64_t* obs_reach_host, int64_t m, const double* Zp_dev /*[nsteps/every][m][M]*/,
+                         const double* qs_dev, const double* R_dev, const double* Dinv_dev, int dinv_kind,
+                         double* rowsum_dev /*[n]*/, double* HX_dev /*[m][M]*/, double* work_dev, double* W_dev,
+                         double* T_dev, double* G_dev, int64_t time_every, void* stream);
+int txh_get_route_timings(txh_net* net, double* ms_out, int64_t capacity, int64_t* count);
+
 /* Dense products of KalmanFilter.filter for small n (da.py:115-122): C = alpha op(A) op(B) + beta C,
  * row-major FP64 on the tensor cores (mma.sync m8n8k4 = DMMA). */
 int txh_dgemm(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha, const double* A_dev,

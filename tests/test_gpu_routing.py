@@ -154,6 +154,34 @@ def test_members_vs_oracle(torch_cuda, libtxh, oracle, monkeypatch, n, seed, M, 
     assert (net.unpack_host(O, M, member_major=True) == o_gpu.T).all()
 
 
+@pytest.mark.parametrize("n,seed,M,T", [(600, 31, 2, 150), (2000, 32, 1, 70)])
+def test_long_launches_vs_oracle(torch_cuda, libtxh, oracle, n, seed, M, T):
+    """Runs longer than one launch holds: with few members a launch covers up to 64 steps (interpolation records
+    read in place instead of staged), and the run continues in the next launch from the state in HBM."""
+    torch = torch_cuda
+    from tx_fast_hydrology_b200 import synthetic as S
+    from tx_fast_hydrology_b200.network import Forcing
+    net_d = S.make_network(n, seed)
+    prm = S.make_params(n, seed)
+    net, (al, be, ch, ga) = _setup(net_d["endnodes"], prm["K"], prm["X"], 300.0)
+    t0 = 1_700_000_000 * 10**9
+    times, table = S.make_forcing(n, T, 300.0, seed, t0_ns=t0, rows_every=5)
+    mul = S.make_member_multipliers(times.size, M, seed) if M > 1 else None
+    rng = np.random.default_rng(seed)
+    o0 = prm["o_t"][:, None] * rng.uniform(0.5, 1.5, size=(n, M))
+    i0 = np.stack([oracle.init_states(net_d["startnodes"], net_d["endnodes"], o0[:, k]) for k in range(M)], 1)
+    O, I = _upload(torch, net, o0, i0, M)
+    net.route_run(O, I, M, Forcing(net, times, table, mul), t0, int(300e9), T)
+    net.check()
+    ref = {"startnodes": net_d["startnodes"], "endnodes": net_d["endnodes"],
+           "indegree": oracle.compute_indegree(net_d["startnodes"], net_d["endnodes"]),
+           "alpha": al, "beta": be, "chi": ch, "gamma": ga}
+    o_ref = np.ascontiguousarray(o0.T); i_ref = np.ascontiguousarray(i0.T)
+    oracle.run_members(ref, o_ref, i_ref, T, times.astype(np.float64), table, float(t0), 300e9, wmul=mul)
+    assert relerr(net.unpack_host(O, M), o_ref.T) < RTOL
+    assert relerr(net.unpack_host(I, M), i_ref.T) < RTOL
+
+
 def test_texas_scale_short(torch_cuda, libtxh, oracle):
     """~100k reaches, ~1k levels (BASELINE.json configs[1] network), 24 steps, 2 members."""
     torch = torch_cuda

@@ -82,6 +82,7 @@ struct txh_net {
     double* d_stage = nullptr; size_t stage_cap = 0;   // reach-order staging of txh_pack_host / txh_unpack_host
     double* stats_rowsum = nullptr;     // txh_set_stats_output: row sums of the final outflows of every routing call
     double stats_scale = 1.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> route_events;   // txh_run_assimilating(time_every > 0)
 };
 
 struct txh_forcing {
@@ -451,6 +452,7 @@ void txh_destroy(txh_net* net)
     if (!net) return;
     if (net->dev_ready) {
         cudaFree(net->d_tasks); cudaFree(net->d_notify); cudaFree(net->d_init_ready); cudaFree(net->d_hdr); cudaFree(net->d_inw);
+        for (auto& ev : net->route_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
         cudaFree(net->d_up_off); cudaFree(net->d_up_pos); cudaFree(net->d_lvl_pos);
         cudaFree(net->d_reach_of_pos); cudaFree(net->d_pos_of_reach); cudaFree(net->d_outlet);
         cudaFree(net->d_coef); cudaFree(net->d_qtmp); cudaFree(net->d_qctl); cudaFree(net->d_rec_slot);
@@ -977,6 +979,55 @@ int txh_enkf_apply(txh_net* net, double* O, double* I, int64_t Mloc, const doubl
                           st));
     if (fuse_o) CU(launch_inflow_gain(net->d_up_off, net->d_up_pos, G, I, net->topo.n, ld, st));
     else CU(launch_apply_gain(net->d_up_off, net->d_up_pos, G, O, I, net->topo.n, ld, (int)Mloc, st));
+    return TXH_OK;
+}
+
+int txh_run_assimilating(txh_net* net, double* O, double* I, int64_t M, const txh_forcing* fo, int64_t t0_ns,
+                         int64_t dt_ns, int64_t nsteps, int64_t every, int method, const int64_t* obs, int64_t m,
+                         const double* Zp, const double* qs, const double* R, const double* Dinv, int dinv_kind,
+                         double* rowsum, double* HX, double* work, double* W, double* T, double* G, int64_t time_every,
+                         void* stream)
+{
+    if (!net || !O || !I || !obs || !Zp || !qs || !R || !rowsum || !HX || !work || !W || !T || !G || every < 1 || m < 1)
+        return fail(TXH_E_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* const rowsum_before = net->stats_rowsum;
+    const double scale_before = net->stats_scale;
+    int rc = txh_set_stats_output(net, rowsum, 1.0 / (double)M);
+    const int64_t nwin = nsteps / every;
+    int64_t t = t0_ns;
+    for (int64_t k = 0; k < nwin && rc == TXH_OK; ++k) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        const bool timed = time_every > 0 && k % time_every == 0 && net->route_events.size() < 4096;
+        if (timed) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, st)); }
+        rc = txh_route_run(net, O, I, M, fo, t, dt_ns, every, method, nullptr, 0, 1, nullptr, stream);
+        if (timed) { CU(cudaEventRecord(e1, st)); net->route_events.emplace_back(e0, e1); }
+        t += every * dt_ns;
+        if (rc == TXH_OK) rc = txh_enkf_stats(net, O, M, obs, m, 1.0 / (double)M, nullptr, HX, stream);
+        if (rc == TXH_OK) rc = txh_enkf_solve(net, m, M, HX, Zp + (size_t)k * m * M, rowsum, obs, qs, R, Dinv, dinv_kind, work, W, T, stream);
+        if (rc == TXH_OK) rc = txh_enkf_apply(net, O, I, M, nullptr, 0, 0, M, 0, rowsum, T, obs, m, qs, W, G, stream);
+    }
+    net->stats_rowsum = nullptr;
+    if (rc == TXH_OK && nsteps > nwin * every)
+        rc = txh_route_run(net, O, I, M, fo, t, dt_ns, nsteps - nwin * every, method, nullptr, 0, 1, nullptr, stream);
+    net->stats_rowsum = rowsum_before; net->stats_scale = scale_before;
+    return rc;
+}
+
+int txh_get_route_timings(txh_net* net, double* ms_out, int64_t capacity, int64_t* count)
+{
+    if (!net || !count || (capacity > 0 && !ms_out)) return fail(TXH_E_INVALID, "null argument");
+    *count = (int64_t)net->route_events.size();
+    for (int64_t i = 0; i < *count && i < capacity; ++i) {
+        float ms = 0.f;
+        CU(cudaEventSynchronize(net->route_events[i].second));
+        CU(cudaEventElapsedTime(&ms, net->route_events[i].first, net->route_events[i].second));
+        ms_out[i] = ms;
+    }
+    if (capacity >= *count) {                                  // read out: the events are done with
+        for (auto& ev : net->route_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+        net->route_events.clear();
+    }
     return TXH_OK;
 }
 

@@ -403,13 +403,26 @@ class Muskingum:
         CUDA tensor of per-member observations for the k-th update), repeated; nothing returns to
         the host in between.  Mirrors simulate + a KalmanFilter callback gated to every `every`-th
         step (the reference filters every step, da.py:56-61; SURVEY.md section 8c iv).
-        `timers`: optional list that receives a (start, end) CUDA-event pair around every 8th routing launch."""
+        `timers`: optional list; every 8th routing launch is bracketed by CUDA events -- the unsharded path
+        keeps them in the library (`network.route_timings()` returns their durations), the sharded one appends
+        (start, end) torch event pairs."""
         torch = self._ensure_device()
         self._sync_coeffs()
         d, net, M = self._dev, self.network, self.members
         step_ns = int(self.timedelta.value)
         t = int(self.datetime.value)
         nwin = nsteps // every
+        if (enkf.world == 1 and torch.is_tensor(observations) and observations.is_cuda and observations.is_contiguous()
+                and observations.shape[0] >= nwin and observations.dtype == torch.float64):
+            # one call: the loop below, in the library (txh_run_assimilating)
+            net.run_assimilating(d['O'], d['I'], M, forcing, t, step_ns, nsteps, every, enkf.reach_indices,
+                                 observations, enkf._qs, enkf._R, enkf._Dinv, enkf._dinv_kind, enkf._rowsum, enkf._HX,
+                                 enkf._work, enkf._W, enkf._T, enkf._G, time_every=8 if timers is not None else 0)
+            enkf.n_updates += nwin
+            self._datetime = pd.Timestamp(t + nsteps * step_ns, tz='UTC')
+            enkf.datetime = self._datetime
+            self._device_advanced()
+            return
         # the ensemble row sums ride on the last step of every routing launch
         net.set_stats_output(enkf._rowsum, enkf.stats_scale())
         for k in range(nwin):

@@ -258,6 +258,25 @@ class RiverNetwork:
                                         int(dt_ns), int(nsteps), int(method), rp, rc, int(rec_every), ro,
                                         _stream_ptr()))
 
+    def run_assimilating(self, O, I, M, forcing, t0_ns, dt_ns, nsteps, every, obs_reach, Zp, qs, R, Dinv, dinv_kind,
+                         rowsum, HX, work, W, T, G, method=1, time_every=0):
+        """`txh_run_assimilating`: routing windows + ensemble updates of an unsharded ensemble, host out of the loop."""
+        idx = L.as_i64(obs_reach)
+        L.check(self._lib.txh_run_assimilating(
+            self.handle, _cuda_ptr(O), _cuda_ptr(I), int(M), forcing.handle if forcing is not None else None,
+            int(t0_ns), int(dt_ns), int(nsteps), int(every), int(method), L.ptr_i64(idx), idx.size, _cuda_ptr(Zp),
+            _cuda_ptr(qs), _cuda_ptr(R), _cuda_ptr(Dinv) if Dinv is not None else None, int(dinv_kind),
+            _cuda_ptr(rowsum), _cuda_ptr(HX), _cuda_ptr(work), _cuda_ptr(W), _cuda_ptr(T), _cuda_ptr(G),
+            int(time_every), _stream_ptr()))
+
+    def route_timings(self):
+        """Durations (ms) of the routing launches `run_assimilating(time_every=...)` bracketed; synchronises."""
+        cnt = np.zeros(1, dtype=np.int64)
+        L.check(self._lib.txh_get_route_timings(self.handle, L.p_f64(), 0, L.ptr_i64(cnt)))
+        out = np.zeros(max(1, int(cnt[0])))
+        L.check(self._lib.txh_get_route_timings(self.handle, L.ptr_f64(out), int(cnt[0]), L.ptr_i64(cnt)))
+        return out[:int(cnt[0])]
+
     def route_step(self, O, I, M, q_dev=None, levels=False):
         fn = self._lib.txh_route_step_levels if levels else self._lib.txh_route_step
         L.check(fn(self.handle, _cuda_ptr(O), _cuda_ptr(I), int(M),
