@@ -216,10 +216,12 @@ def test_enkf_update_vs_oracle(oracle, n, M, m, seed, diag):
 
 
 @pytest.mark.parametrize("n,M,m,seed", [(2000, 64, 50, 7), (1200, 20, 30, 8), (900, 70, 40, 9)])
-def test_run_assimilating_vs_oracle(oracle, n, M, m, seed):
+@pytest.mark.parametrize("in_library", [True, False])
+def test_run_assimilating_vs_oracle(oracle, n, M, m, seed, in_library):
     """The device-resident loop of the headline benchmark -- `every` routing steps in one window launch, the
     ensemble row sums riding on its last step, then one EnKF update, repeated -- equals the CPU oracle's
-    routing (nutils.py:64-89 per member) + ensemble update (da.py:112-126) loop."""
+    routing (nutils.py:64-89 per member) + ensemble update (da.py:112-126) loop.  `in_library`: the loop runs
+    inside libtxh (txh_run_assimilating, observations as one CUDA tensor) or in Python (a list of tensors)."""
     import torch
     from tx_fast_hydrology_b200 import synthetic as S
     from tx_fast_hydrology_b200.muskingum import Muskingum
@@ -244,7 +246,8 @@ def test_run_assimilating_vs_oracle(oracle, n, M, m, seed):
     enkf = EnsembleKalmanFilter(mdl, mdf, q, R)
     Zp = meas[:, :, None] + 0.1 * rng.standard_normal((nwin, m, M))
     f = mdl.make_forcing(times_ns=times, table=table, member_mul=mul)
-    mdl.run_assimilating(f, every * nwin, enkf, every, torch.as_tensor(Zp, device="cuda"))
+    Zd = torch.as_tensor(Zp, device="cuda")
+    mdl.run_assimilating(f, every * nwin, enkf, every, Zd if in_library else list(Zd))
     mdl.network.check()
     assert enkf.n_updates == nwin and mdl.datetime.value == t0 + int(every * nwin * 300e9)
     ind = oracle.compute_indegree(net_d["startnodes"], net_d["endnodes"])
