@@ -117,6 +117,13 @@ int txh_forcing_create(txh_net* net, int64_t R, const double* times, const doubl
 /* new values for an existing table of the same shape (a new forecast cycle): no allocation, one H2D copy */
 int txh_forcing_update(txh_forcing* f, const double* times, const double* table_host, const double* member_mul_host,
                        void* stream);
+/* The same without waiting for the copy: the table (PINNED host memory, untouched until txh_forcing_wait or the
+ * end of the run that reads it) arrives in row chunks on a copy stream owned by the handle, and every later
+ * txh_route_run / txh_run_assimilating makes its stream wait only for the chunks its steps interpolate in -- the
+ * upload overlaps the routing of the earlier hours. */
+int txh_forcing_update_async(txh_forcing* f, const double* times, const double* table_host,
+                             const double* member_mul_host, void* stream);
+int txh_forcing_wait(txh_forcing* f);
 void txh_forcing_destroy(txh_forcing* f);
 
 /* ---- routing ---------------------------------------------------------------------------

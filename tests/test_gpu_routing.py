@@ -274,3 +274,36 @@ def test_forcing_update_in_place(torch_cuda, libtxh):
     assert torch.equal(O, O2) and torch.equal(I, I2)
     with pytest.raises(ValueError):
         f.update(times[:-1], table[:-1], mul[:-1])
+
+
+def test_forcing_update_overlapped(torch_cuda, libtxh):
+    """txh_forcing_update_async: the table arrives in row chunks on the handle's copy stream while routing calls
+    that read only its first hours already run; window by window the result equals the synchronous upload.
+    (A 40 MB table: several chunks.)"""
+    torch = torch_cuda
+    from tx_fast_hydrology_b200 import synthetic as S
+    from tx_fast_hydrology_b200.network import Forcing
+    n, seed, M, every, nwin = 60000, 19, 2, 12, 80
+    net_d = S.make_network(n, seed)
+    prm = S.make_params(n, seed)
+    net, _ = _setup(net_d["endnodes"], prm["K"], prm["X"], 300.0)
+    t0 = 1_700_000_000 * 10**9
+    times, table = S.make_forcing(n, every * nwin, 300.0, seed, t0_ns=t0)
+    mul = S.make_member_multipliers(times.size, M, seed)
+    tp = torch.from_numpy(np.ascontiguousarray(table)).pin_memory()
+    mp = torch.from_numpy(np.ascontiguousarray(mul)).pin_memory()
+    rng = np.random.default_rng(seed)
+    o0 = prm["o_t"][:, None] * rng.uniform(0.5, 1.5, size=(n, M))
+    f = Forcing(net, times, torch.zeros_like(tp), torch.ones_like(mp))
+    g = Forcing(net, times, tp, mp)
+    for rep in range(2):                                   # the second pass re-uses the table while it may be in use
+        O, I = _upload(torch, net, o0, np.zeros_like(o0), M)
+        O2, I2 = _upload(torch, net, o0, np.zeros_like(o0), M)
+        f.update(times, tp, mp, overlap=True)
+        for k in range(nwin):
+            net.route_run(O, I, M, f, t0 + k * every * int(300e9), int(300e9), every)
+        for k in range(nwin):
+            net.route_run(O2, I2, M, g, t0 + k * every * int(300e9), int(300e9), every)
+        net.check()
+        assert torch.equal(O, O2) and torch.equal(I, I2)
+    f.wait()

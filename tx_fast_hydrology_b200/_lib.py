@@ -51,6 +51,8 @@ SIGNATURES = {
     "txh_init_inflows": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "txh_forcing_create": (ctypes.c_int, [c_vp, c_i64, p_f64, c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "txh_forcing_update": (ctypes.c_int, [c_vp, p_f64, c_vp, c_vp, c_vp]),
+    "txh_forcing_update_async": (ctypes.c_int, [c_vp, p_f64, c_vp, c_vp, c_vp]),
+    "txh_forcing_wait": (ctypes.c_int, [c_vp]),
     "txh_forcing_destroy": (None, [c_vp]),
     "txh_route_run": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, ctypes.c_int,
                                      p_i64, c_i64, c_i64, c_vp, c_vp]),

@@ -92,6 +92,14 @@ struct txh_forcing {
     double* d_times = nullptr;          // [R] the same on the device
     double* d_F = nullptr;              // [R][n] schedule order
     double* d_W = nullptr;              // [R][M] or nullptr
+    // txh_forcing_update_async: the table arrives in row chunks on a copy stream of its own; a routing call waits
+    // (on its stream) for the chunks its steps read
+    cudaStream_t copy_stream = nullptr;
+    double* d_stage = nullptr;          // [R][n] reach order, private to the handle
+    cudaEvent_t reuse_ev = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
+    std::vector<int64_t> chunk_begin;   // first row of each chunk
+    size_t waited = 0;                  // chunks the routing stream has been made to wait for
 };
 
 namespace {
@@ -728,6 +736,7 @@ int txh_forcing_update(txh_forcing* f, const double* times, const double* table,
     for (int64_t r = 1; r < R; ++r)
         if (!(times[r] >= times[r - 1])) return fail(TXH_E_INVALID, "forcing times must be sorted ascending");
     int rc;
+    if ((rc = txh_forcing_wait(f))) return rc;
     double* tmp = nullptr;
     if ((rc = stage_buffer(net, (size_t)R * n, st, &tmp))) return rc;
     f->times.assign(times, times + R);
@@ -739,9 +748,60 @@ int txh_forcing_update(txh_forcing* f, const double* times, const double* table,
     return TXH_OK;
 }
 
+int txh_forcing_update_async(txh_forcing* f, const double* times, const double* table, const double* mul, void* stream)
+{
+    if (!f || !times || !table) return fail(TXH_E_INVALID, "null argument");
+    if ((mul != nullptr) != (f->d_W != nullptr)) return fail(TXH_E_INVALID, "member multipliers must stay present / absent");
+    txh_net* net = f->net;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = net->topo.n, R = f->R;
+    for (int64_t r = 1; r < R; ++r)
+        if (!(times[r] >= times[r - 1])) return fail(TXH_E_INVALID, "forcing times must be sorted ascending");
+    if (!f->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&f->reuse_ev, cudaEventDisableTiming));
+        CU(cudaMalloc((void**)&f->d_stage, sizeof(double) * R * n));
+        // a first chunk small enough that routing starts at once, then ~16 MiB pieces
+        const int64_t rows_per = std::max<int64_t>(1, (int64_t)((size_t(16) << 20) / (sizeof(double) * n)));
+        for (int64_t r = 0; r < R; r += (r == 0 ? std::min<int64_t>(2, rows_per) : rows_per)) f->chunk_begin.push_back(r);
+        f->chunk_ev.resize(f->chunk_begin.size());
+        for (cudaEvent_t& e : f->chunk_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    f->times.assign(times, times + R);
+    CU(cudaMemcpyAsync(f->d_times, f->times.data(), sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    if (mul) CU(cudaMemcpyAsync(f->d_W, mul, sizeof(double) * R * f->M, cudaMemcpyHostToDevice, st));
+    // the table may still be read by launches already queued on `st`
+    CU(cudaEventRecord(f->reuse_ev, st));
+    CU(cudaStreamWaitEvent(f->copy_stream, f->reuse_ev, 0));
+    for (size_t c = 0; c < f->chunk_begin.size(); ++c) {
+        const int64_t r0 = f->chunk_begin[c], r1 = c + 1 < f->chunk_begin.size() ? f->chunk_begin[c + 1] : R;
+        CU(cudaMemcpyAsync(f->d_stage + r0 * n, table + r0 * n, sizeof(double) * (r1 - r0) * n, cudaMemcpyHostToDevice,
+                           f->copy_stream));
+        CU(launch_permute_rows(net->d_reach_of_pos, f->d_stage + r0 * n, f->d_F + r0 * n, n, r1 - r0, f->copy_stream));
+        CU(cudaEventRecord(f->chunk_ev[c], f->copy_stream));
+    }
+    f->waited = 0;
+    return TXH_OK;
+}
+
+int txh_forcing_wait(txh_forcing* f)
+{
+    if (!f) return fail(TXH_E_INVALID, "null argument");
+    if (f->copy_stream) CU(cudaStreamSynchronize(f->copy_stream));
+    f->waited = f->chunk_ev.size();
+    return TXH_OK;
+}
+
 void txh_forcing_destroy(txh_forcing* f)
 {
     if (!f) return;
+    if (f->copy_stream) {
+        cudaStreamSynchronize(f->copy_stream);
+        for (cudaEvent_t e : f->chunk_ev) cudaEventDestroy(e);
+        cudaEventDestroy(f->reuse_ev);
+        cudaStreamDestroy(f->copy_stream);
+        cudaFree(f->d_stage);
+    }
     cudaFree(f->d_F);
     if (f->d_times) cudaFree(f->d_times);
     if (f->d_W) cudaFree(f->d_W);
@@ -763,6 +823,16 @@ int txh_route_run(txh_net* net, double* O, double* I, int64_t M, const txh_forci
     if (nsteps == 0) return TXH_OK;
     StepPlan plan;
     if (fo) { plan.times = fo->d_times; plan.R = fo->R; plan.t0_ns = t0_ns; plan.dt_ns = dt_ns; plan.method = method; }
+    if (fo && fo->waited < fo->chunk_ev.size()) {
+        // a table still arriving (txh_forcing_update_async): wait for the row chunks these steps interpolate in
+        txh_forcing* fw = const_cast<txh_forcing*>(fo);
+        const double x_end = (double)(t0_ns + nsteps * dt_ns);
+        const int64_t need = std::min<int64_t>(fo->R - 1, std::lower_bound(fo->times.begin(), fo->times.end(), x_end) - fo->times.begin());
+        while (fw->waited < fw->chunk_ev.size() && fw->chunk_begin[fw->waited] <= need) {
+            CU(cudaStreamWaitEvent(st, fw->chunk_ev[fw->waited], 0));
+            ++fw->waited;
+        }
+    }
     const int32_t* rec_slot = nullptr;
     if (rec_count > 0) {
         std::vector<int32_t> slot(net->topo.n, -1);

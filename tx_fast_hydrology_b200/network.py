@@ -64,8 +64,11 @@ class Forcing:
         a = L.as_f64(a)
         return ctypes.c_void_p(a.ctypes.data), a.shape, a
 
-    def update(self, times_ns, table, member_mul=None):
-        """New values for the resident table (same shape): one host->device copy, no allocation."""
+    def update(self, times_ns, table, member_mul=None, overlap=False):
+        """New values for the resident table (same shape): one host->device copy, no allocation.
+        `overlap` (pinned CPU torch tensors only): return at once; the table arrives in row chunks on a copy
+        stream and later routing calls wait only for the rows their steps read -- do not touch the buffers
+        until the run that uses them has finished (or call `wait()`)."""
         times = L.as_f64(np.asarray(times_ns).astype(np.float64))
         tptr, tshape, keep_t = self._host_ptr(table)
         if tshape != (self.R, self.net.n) or times.size != self.R:
@@ -75,7 +78,16 @@ class Forcing:
             mp, mshape, keep_m = self._host_ptr(member_mul)
             if mshape != (self.R, self.M):
                 raise ValueError("member multipliers must keep their shape")
-        L.check(L.load().txh_forcing_update(self.handle, L.ptr_f64(times), tptr, mp, _stream_ptr()))
+        pinned = all(hasattr(x, "is_pinned") and x.is_pinned() for x in (table, member_mul) if x is not None)
+        if overlap and pinned:
+            self._keep_t, self._keep_m = keep_t, keep_m
+            L.check(L.load().txh_forcing_update_async(self.handle, L.ptr_f64(times), tptr, mp, _stream_ptr()))
+        else:
+            L.check(L.load().txh_forcing_update(self.handle, L.ptr_f64(times), tptr, mp, _stream_ptr()))
+
+    def wait(self):
+        """Block until an overlapped `update` has landed."""
+        L.check(L.load().txh_forcing_wait(self.handle))
 
     def close(self):
         if getattr(self, "handle", None):
