@@ -355,15 +355,22 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     }
     for (int64_t s0 = 0; s0 < nsteps; s0 += spl) {
         const int64_t ns = std::min<int64_t>(spl, nsteps - s0);
-        InitArgs ia{};
-        ia.times = plan.times; ia.steps_out = net->d_steps; ia.t0_ns = plan.t0_ns; ia.dt_ns = plan.dt_ns;
-        ia.step_base = s0; ia.R = (int32_t)plan.R; ia.nsteps = (int32_t)ns; ia.method = plan.method;
-        CU(launch_window_init(ia, net->d_qctl + 3, st));
+        // up to 16 steps every warp resolves the forcing interpolation itself (no init launch: the kernel re-arms
+        // its own ticket); longer launches read the records an init kernel leaves in global memory
+        const bool own_steps = ns <= 16;
+        if (!own_steps) {
+            InitArgs ia{};
+            ia.times = plan.times; ia.steps_out = net->d_steps; ia.t0_ns = plan.t0_ns; ia.dt_ns = plan.dt_ns;
+            ia.step_base = s0; ia.R = (int32_t)plan.R; ia.nsteps = (int32_t)ns; ia.method = plan.method;
+            CU(launch_window_init(ia, net->d_qctl + 3, st));
+        }
+        a.times = plan.times; a.t0_ns = plan.t0_ns; a.dt_ns = plan.dt_ns; a.step_base = s0; a.R = (int32_t)plan.R;
+        a.method = plan.method; a.done = net->d_qctl + 5;
         a.tasks = net->d_wtasks; a.hdr = net->d_whdr; a.inw = net->d_winw; a.prod = net->d_wprod;
         a.coef = net->d_coef; a.cumA = net->d_coef + 4 * net->topo.n;
         a.cumC = net->d_coef + 5 * net->topo.n + s.link_last.size();
         a.O = O; a.I = I; a.ring = net->d_ring; a.ticket = net->d_qctl + 3;
-        a.F = F; a.steps = d_steps; a.Wmul = W; a.status = net->d_status; a.watchdog_ns = net->watchdog_ns;
+        a.F = F; a.steps = (own_steps && plan.times) ? nullptr : d_steps; a.Wmul = W; a.status = net->d_status; a.watchdog_ns = net->watchdog_ns;
         a.n = net->topo.n; a.n_tasks = (int32_t)s.wtasks.size(); a.n_mblocks = nmb; a.nsteps = (int32_t)ns;
         a.n_slots = std::max(1, s.n_wslots); a.ld = ld; a.M = (int32_t)M; a.wm_ld = wm_ld;
         // the row sums ride on the last step of the call when one warp covers all members of a row

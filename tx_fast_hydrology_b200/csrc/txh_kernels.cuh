@@ -77,9 +77,13 @@ struct WinArgs {
     double* O;
     double* I;
     double* ring;                         // [nsteps][n_slots][ld] rows handed between tasks; EMPTY (all bits set) when idle
-    unsigned long long* ticket;
+    unsigned long long* ticket;           // zero at launch; the last warp to leave the kernel zeroes it again
+    unsigned long long* done;             // warps that have left the kernel
     const double* F;                      // [R][n] schedule order, or nullptr
-    const StepInterp* steps;              // [nsteps]
+    const StepInterp* steps;              // [nsteps] interpolation records, or nullptr: every warp resolves them itself
+    const double* times;                  // ... from the forcing times [R] (steps == nullptr)
+    long long t0_ns, dt_ns, step_base;    // step s of the launch ends at t0_ns + (step_base + s + 1) * dt_ns
+    int32_t R, method;
     const double* Wmul;                   // [R][wm_ld] or nullptr
     int32_t* status;
     unsigned long long watchdog_ns;

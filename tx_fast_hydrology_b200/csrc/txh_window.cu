@@ -367,6 +367,30 @@ __device__ __forceinline__ void segment_step(const WinArgs& a, const Tk& tk, InS
     }
 }
 
+// nutils.py:21-34: np.searchsorted(xp, x) (side='left'), clamped ends, linear weights or the nearer row
+__device__ __forceinline__ StepInterp interp_step(const double* __restrict__ times, int R, double x, int method)
+{
+    int lo = 0, hi = R;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (times[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    StepInterp si;
+    if (lo == 0) { si.r0 = 0; si.r1 = 0; si.w0 = 1.0; si.w1 = 0.0; }
+    else if (lo >= R) { si.r0 = R - 1; si.r1 = R - 1; si.w0 = 1.0; si.w1 = 0.0; }
+    else {
+        const double dx_0 = __dsub_rn(x, times[lo - 1]), dx_1 = __dsub_rn(times[lo], x);
+        if (method == 1) {
+            const double frac = __ddiv_rn(dx_0, __dadd_rn(dx_0, dx_1));
+            si.r0 = lo - 1; si.r1 = lo; si.w0 = __dsub_rn(1.0, frac); si.w1 = frac;
+        } else {
+            const int r = fabs(dx_0) <= fabs(dx_1) ? lo - 1 : lo;
+            si.r0 = r; si.r1 = r; si.w0 = 1.0; si.w1 = 0.0;
+        }
+    }
+    return si;
+}
+
 // Shared-memory state of a task: ONE row per reach, p = beta*i + chi*o, the part of the next update that
 // depends on the old state (o' = alpha*inflow + (gamma*q + p)); the outflows and inflows themselves only
 // exist in registers, and are written to global memory in the last step of the launch.
@@ -419,8 +443,15 @@ route_window_kernel(const WinArgs a)
             if (steps_staged) return make_double2(lds_f64(sSteps + 24u * s + 8u), lds_f64(sSteps + 24u * s + 16u));
             return make_double2(__ldg(&a.steps[s].w0), __ldg(&a.steps[s].w1));
         };
-        if (HAS_F && steps_staged)
-            for (int i = lane; i < 6 * a.nsteps; i += 32) cp_async4(sSteps + 4u * i, reinterpret_cast<const uint32_t*>(a.steps) + i);
+        if (HAS_F && steps_staged) {
+            if (a.steps != nullptr) {
+                for (int i = lane; i < 6 * a.nsteps; i += 32) cp_async4(sSteps + 4u * i, reinterpret_cast<const uint32_t*>(a.steps) + i);
+            } else if (lane < a.nsteps) {                      // no init kernel: resolved here, one step per lane
+                const StepInterp si = interp_step(a.times, a.R, (double)(a.t0_ns + (a.step_base + lane + 1) * a.dt_ns), a.method);
+                sts_u32(sSteps + 24u * lane, (uint32_t)si.r0); sts_u32(sSteps + 24u * lane + 4u, (uint32_t)si.r1);
+                sts_f64(sSteps + 24u * lane + 8u, si.w0); sts_f64(sSteps + 24u * lane + 16u, si.w1);
+            }
+        }
         // rows of O straight into their p slots, rows of I (eight at a time) into the scratch / ring area: every
         // load of the task is in flight before the first is waited for
         if (active)
@@ -546,6 +577,14 @@ route_window_kernel(const WinArgs a)
         }
         __syncwarp();
     }
+    // the last warp to leave re-arms the ticket for the next launch on this handle
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(a.done, 1ull) + 1ull == (unsigned long long)gridDim.x * (blockDim.x >> 5)) {
+            *a.done = 0ull;
+            *a.ticket = 0ull;
+        }
+    }
 }
 
 // ticket and the forcing interpolation of the launch's steps (see dataflow_init_kernel)
@@ -556,25 +595,7 @@ __global__ void __launch_bounds__(256) window_init_kernel(const InitArgs a, unsi
     if (gid0 == 0) *ticket = 0ull;
     if (a.times) {
         for (long long s = gid0; s < a.nsteps; s += stride) {
-            const double x = (double)(a.t0_ns + (a.step_base + s + 1) * a.dt_ns);
-            int lo = 0, hi = a.R;                                   // np.searchsorted(xp, x), side='left'
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (a.times[mid] < x) lo = mid + 1; else hi = mid;
-            }
-            StepInterp si;
-            if (lo == 0) { si.r0 = 0; si.r1 = 0; si.w0 = 1.0; si.w1 = 0.0; }
-            else if (lo >= a.R) { si.r0 = a.R - 1; si.r1 = a.R - 1; si.w0 = 1.0; si.w1 = 0.0; }
-            else {
-                const double dx_0 = __dsub_rn(x, a.times[lo - 1]), dx_1 = __dsub_rn(a.times[lo], x);
-                if (a.method == 1) {
-                    const double frac = __ddiv_rn(dx_0, __dadd_rn(dx_0, dx_1));
-                    si.r0 = lo - 1; si.r1 = lo; si.w0 = __dsub_rn(1.0, frac); si.w1 = frac;
-                } else {
-                    const int r = fabs(dx_0) <= fabs(dx_1) ? lo - 1 : lo;
-                    si.r0 = r; si.r1 = r; si.w0 = 1.0; si.w1 = 0.0;
-                }
-            }
+            const StepInterp si = interp_step(a.times, a.R, (double)(a.t0_ns + (a.step_base + s + 1) * a.dt_ns), a.method);
             a.steps_out[s] = si;
         }
     }
