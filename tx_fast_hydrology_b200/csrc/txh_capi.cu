@@ -58,6 +58,7 @@ struct txh_net {
             *d_reach_of_pos = nullptr, *d_pos_of_reach = nullptr;
     uint32_t *d_hdr = nullptr, *d_inw = nullptr;
     uint8_t* d_outlet = nullptr;
+    int32_t* d_inner = nullptr; int64_t n_inner = 0;   // schedule positions that have upstream reaches
     double* d_coef = nullptr;           // same layout as coef_host
     double* d_qtmp = nullptr;           // [n] schedule-order scratch for txh_route_step
     int32_t* d_pending = nullptr; size_t pairs_cap = 0;
@@ -125,6 +126,12 @@ int ensure_device(txh_net* net)
     if ((rc = upload(&net->d_inw, s.inw))) return rc;
     if ((rc = upload(&net->d_up_off, s.up_off))) return rc;
     if ((rc = upload(&net->d_up_pos, s.up_pos))) return rc;
+    {
+        std::vector<int32_t> inner;                            // rows with upstream reaches (inflow_gain_kernel)
+        for (int64_t k = 0; k < net->topo.n; ++k) if (s.up_off[k + 1] > s.up_off[k]) inner.push_back((int32_t)k);
+        net->n_inner = (int64_t)inner.size();
+        if ((rc = upload(&net->d_inner, inner))) return rc;
+    }
     if ((rc = upload(&net->d_lvl_pos, s.lvl_pos))) return rc;
     if ((rc = upload(&net->d_reach_of_pos, s.reach_of_pos))) return rc;
     if ((rc = upload(&net->d_pos_of_reach, s.pos_of_reach))) return rc;
@@ -468,7 +475,7 @@ void txh_destroy(txh_net* net)
     if (net->dev_ready) {
         cudaFree(net->d_tasks); cudaFree(net->d_notify); cudaFree(net->d_init_ready); cudaFree(net->d_hdr); cudaFree(net->d_inw);
         for (auto& ev : net->route_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-        cudaFree(net->d_up_off); cudaFree(net->d_up_pos); cudaFree(net->d_lvl_pos);
+        cudaFree(net->d_up_off); cudaFree(net->d_up_pos); cudaFree(net->d_lvl_pos); cudaFree(net->d_inner);
         cudaFree(net->d_reach_of_pos); cudaFree(net->d_pos_of_reach); cudaFree(net->d_outlet);
         cudaFree(net->d_coef); cudaFree(net->d_qtmp); cudaFree(net->d_qctl); cudaFree(net->d_rec_slot);
         cudaFree(net->d_unit_step);
@@ -1054,7 +1061,7 @@ int txh_enkf_apply(txh_net* net, double* O, double* I, int64_t Mloc, const doubl
     CU(launch_enkf_update(Xall, (int)ldx, (int)Mtot, mean, T + col0, (int)Mtot, (int)Mloc, fuse_o ? O : nullptr, G, ld,
                           net->topo.n, net->d_gauge_of_pos, qs, W, (int)col0, net->num_sms, Mb, (long long)x_block_stride,
                           st));
-    if (fuse_o) CU(launch_inflow_gain(net->d_up_off, net->d_up_pos, G, I, net->topo.n, ld, st));
+    if (fuse_o) CU(launch_inflow_gain(net->d_inner, net->n_inner, net->d_up_off, net->d_up_pos, G, I, ld, st));
     else CU(launch_apply_gain(net->d_up_off, net->d_up_pos, G, O, I, net->topo.n, ld, (int)Mloc, st));
     return TXH_OK;
 }

@@ -695,20 +695,33 @@ enkf_update64_kernel(const double* __restrict__ X, int M, const double* __restri
     }
     __syncthreads();
     int buf = 0;
+    // mean and gauge index of this lane's two rows, fetched one tile ahead (a global round trip otherwise
+    // exposed at the head of every tile)
+    auto row_meta = [&](long long tl, double* mu_o, int* gi_o) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const long long row = tl * 16 + 8 * i + g;
+            const bool ok = tl < ntiles && row < n;
+            mu_o[i] = ok ? __ldg(mean + row) : 0.0;
+            gi_o[i] = ok ? __ldg(gauge_of_pos + row) : -1;
+        }
+    };
+    double mu_n[2];
+    int gi_n[2];
+    row_meta(tile, mu_n, gi_n);
     for (; tile < ntiles; tile += tstride, buf ^= 1) {
         prefetch(tile + tstride, buf ^ 1);
+        const double mu[2] = {mu_n[0], mu_n[1]};
+        const int gi[2] = {gi_n[0], gi_n[1]};
+        row_meta(tile + tstride, mu_n, gi_n);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         const long long rw = tile * 16;
         const long long rows[2] = {rw + g, rw + 8 + g};
-        double mu[2];
-        int gi[2];
         double a[2][16];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const bool ok = rows[i] < n;
-            mu[i] = ok ? mean[rows[i]] : 0.0;
-            gi[i] = ok ? gauge_of_pos[rows[i]] : -1;
             const unsigned ra = stage0 + (buf * 16 + 8 * i + g) * EU_RS + t * 16;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -766,25 +779,26 @@ enkf_update64_kernel(const double* __restrict__ X, int M, const double* __restri
 }
 
 // inflow part of _apply_gain (nutils.py:116-134, da.py:125): I[k] += sum of the gains of the reaches
-// draining into k (self-loops excluded).  One thread per (row, member pair).
+// draining into k (self-loops excluded).  One thread per (row with upstream reaches, member pair): `inner` lists
+// those rows, so no thread is spent on a headwater (half of a river network).
 __global__ void __launch_bounds__(256)
-inflow_gain_kernel(const int32_t* __restrict__ up_off, const int32_t* __restrict__ up_pos, const double* __restrict__ G,
-                   double* __restrict__ I, long long n, int ld)
+inflow_gain_kernel(const int32_t* __restrict__ inner, long long n_inner, const int32_t* __restrict__ up_off,
+                   const int32_t* __restrict__ up_pos, const double* __restrict__ G, double* __restrict__ I, int ld)
 {
     const int half = ld >> 1;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n * half) return;
-    const long long k = gid / half;
-    const int col = (int)(gid - k * half) * 2;
+    if (gid >= n_inner * half) return;
+    const long long e = gid / half;
+    const int col = (int)(gid - e * half) * 2;
+    const long long k = inner[e];
     const int u0 = up_off[k], u1 = up_off[k + 1];
-    if (u0 == u1) return;
+    double2* ip = reinterpret_cast<double2*>(I + (size_t)k * ld + col);
+    double2 i = *ip;
     double2 s = make_double2(0.0, 0.0);
     for (int u = u0; u < u1; ++u) {
         const double2 v = *reinterpret_cast<const double2*>(G + (size_t)up_pos[u] * ld + col);
         s.x += v.x; s.y += v.y;
     }
-    double2* ip = reinterpret_cast<double2*>(I + (size_t)k * ld + col);
-    double2 i = *ip;
     i.x += s.x; i.y += s.y;
     *ip = i;
 }
@@ -951,10 +965,11 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
     return cudaGetLastError();
 }
 
-cudaError_t launch_inflow_gain(const int32_t* up_off, const int32_t* up_pos, const double* G, double* I, int64_t n,
-                               int ld, cudaStream_t st)
+cudaError_t launch_inflow_gain(const int32_t* inner, int64_t n_inner, const int32_t* up_off, const int32_t* up_pos,
+                               const double* G, double* I, int ld, cudaStream_t st)
 {
-    inflow_gain_kernel<<<nblk(n * (ld >> 1), 256), 256, 0, st>>>(up_off, up_pos, G, I, n, ld);
+    if (n_inner == 0) return cudaSuccess;
+    inflow_gain_kernel<<<nblk(n_inner * (ld >> 1), 256), 256, 0, st>>>(inner, n_inner, up_off, up_pos, G, I, ld);
     count_launch();
     return cudaGetLastError();
 }
