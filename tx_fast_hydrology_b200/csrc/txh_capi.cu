@@ -990,9 +990,14 @@ int64_t txh_enkf_work_size(int64_t m, int64_t Mtot)
     return std::max(direct, woodbury);
 }
 
-int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, const double* Zp, const double* mean,
-                   const int64_t* obs, const double* qs, const double* R, const double* Dinv, int dinv_kind,
-                   double* work, double* W, double* T, void* stream)
+}  // extern "C"
+
+namespace {
+// txh_enkf_solve; with O_gather the gauge rows HX are gathered from the state (unsharded ensemble, ld = row stride of
+// Mtot members) inside the first kernel instead of by a launch of their own
+int enkf_solve_impl(txh_net* net, int64_t m, int64_t Mtot, double* HX, const double* O_gather, const double* Zp,
+                    const double* mean, const int64_t* obs, const double* qs, const double* R, const double* Dinv,
+                    int dinv_kind, double* work, double* W, double* T, void* stream)
 {
     if (!net || !HX || !Zp || !mean || !obs || !qs || !R || !work || !W || !T || m < 1 || Mtot < 2)
         return fail(TXH_E_INVALID, "bad argument");
@@ -1008,7 +1013,8 @@ int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, cons
         double* Bc = work;                                  // [m][2Mt] = [HA | dz]
         double* Y = Bc + 2 * m * Mtot;                      // [m][2Mt] = D^-1 Bc
         double* Cp = Y + 2 * m * Mtot;                      // [nsplit][Mt][2Mt] split-K partials of HA^T Y
-        CU(launch_innovation_cat(HX, Zp, mean, d_pos, dinv_kind == 1 ? Dinv : nullptr, (int)m, Mt, Bc, Y, st));
+        CU(launch_innovation_cat(HX, O_gather, (int)txh_row_stride(Mtot), Zp, mean, d_pos, dinv_kind == 1 ? Dinv : nullptr,
+                                 (int)m, Mt, Bc, Y, st));
         if (dinv_kind == 2)
             CU(launch_dgemm(0, 0, (int)m, 2 * Mt, (int)m, 1.0, Dinv, (int)m, Bc, 2 * Mt, 0.0, Y, 2 * Mt, st));
         CU(launch_dgemm_splitk(1, 0, Mt, 2 * Mt, (int)m, Bc, 2 * Mt, Y, 2 * Mt, Cp, 2 * Mt, nsplit,
@@ -1023,6 +1029,7 @@ int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, cons
         // W = Y_dz - Y_HA Z
         CU(launch_dgemm_ex(0, 0, (int)m, Mt, Mt, -1.0, Y, 2 * Mt, T, Mt, 1.0, Y + Mt, 2 * Mt, W, Mt, st));
     } else {
+        if (O_gather) CU(launch_gather_rows(d_pos, m, O_gather, (int)txh_row_stride(Mtot), (int)Mtot, HX, st));
         double* S = work;
         double* HA = S + m * m;
         double* mean_obs = HA + m * Mtot;
@@ -1036,6 +1043,17 @@ int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, cons
     }
     // asynchronous: a failed factorisation leaves a non-zero info word that txh_check reports
     return TXH_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int txh_enkf_solve(txh_net* net, int64_t m, int64_t Mtot, const double* HX, const double* Zp, const double* mean,
+                   const int64_t* obs, const double* qs, const double* R, const double* Dinv, int dinv_kind,
+                   double* work, double* W, double* T, void* stream)
+{
+    return enkf_solve_impl(net, m, Mtot, const_cast<double*>(HX), nullptr, Zp, mean, obs, qs, R, Dinv, dinv_kind, work, W, T,
+                           stream);
 }
 
 int txh_enkf_apply(txh_net* net, double* O, double* I, int64_t Mloc, const double* Xall, int64_t ldx,
@@ -1087,8 +1105,8 @@ int txh_run_assimilating(txh_net* net, double* O, double* I, int64_t M, const tx
         rc = txh_route_run(net, O, I, M, fo, t, dt_ns, every, method, nullptr, 0, 1, nullptr, stream);
         if (timed) { CU(cudaEventRecord(e1, st)); net->route_events.emplace_back(e0, e1); }
         t += every * dt_ns;
-        if (rc == TXH_OK) rc = txh_enkf_stats(net, O, M, obs, m, 1.0 / (double)M, nullptr, HX, stream);
-        if (rc == TXH_OK) rc = txh_enkf_solve(net, m, M, HX, Zp + (size_t)k * m * M, rowsum, obs, qs, R, Dinv, dinv_kind, work, W, T, stream);
+        if (rc == TXH_OK) rc = check_M(M);
+        if (rc == TXH_OK) rc = enkf_solve_impl(net, m, M, HX, O, Zp + (size_t)k * m * M, rowsum, obs, qs, R, Dinv, dinv_kind, work, W, T, stream);
         if (rc == TXH_OK) rc = txh_enkf_apply(net, O, I, M, nullptr, 0, 0, M, 0, rowsum, T, obs, m, qs, W, G, stream);
     }
     net->stats_rowsum = nullptr;

@@ -327,14 +327,16 @@ chol_back_kernel(const double* __restrict__ S, int m, double* __restrict__ B, in
 
 // Bc[k] = [HA_k | dz_k] (2*Mt doubles per gauge); Y = dinv_k * Bc when D is diagonal.
 __global__ void __launch_bounds__(256)
-innovation_cat_kernel(const double* __restrict__ HX, const double* __restrict__ Zp, const double* __restrict__ mean,
-                      const int32_t* __restrict__ obs_pos, const double* __restrict__ dinv_diag, int m, int Mt,
-                      double* __restrict__ Bc, double* __restrict__ Y)
+innovation_cat_kernel(double* __restrict__ HX, const double* __restrict__ O, int ldo, const double* __restrict__ Zp,
+                      const double* __restrict__ mean, const int32_t* __restrict__ obs_pos,
+                      const double* __restrict__ dinv_diag, int m, int Mt, double* __restrict__ Bc, double* __restrict__ Y)
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= m * Mt) return;
     const int k = gid / Mt, c = gid - k * Mt;
-    const double hx = HX[gid];
+    double hx;
+    if (O) { hx = O[(size_t)obs_pos[k] * ldo + c]; HX[gid] = hx; }      // the gauge rows gathered on the way
+    else hx = HX[gid];
     const double ha = hx - mean[obs_pos[k]], dz = Zp[gid] - hx;
     const size_t o = (size_t)k * 2 * Mt + c;
     Bc[o] = ha; Bc[o + Mt] = dz;
@@ -844,10 +846,11 @@ cudaError_t launch_dgemm_splitk(int transA, int transB, int M, int N, int K, con
     return cudaGetLastError();
 }
 
-cudaError_t launch_innovation_cat(const double* HX, const double* Zp, const double* mean, const int32_t* obs_pos,
-                                  const double* dinv_diag, int m, int Mt, double* Bc, double* Y, cudaStream_t st)
+cudaError_t launch_innovation_cat(double* HX, const double* O, int ldo, const double* Zp, const double* mean,
+                                  const int32_t* obs_pos, const double* dinv_diag, int m, int Mt, double* Bc, double* Y,
+                                  cudaStream_t st)
 {
-    innovation_cat_kernel<<<nblk((long long)m * Mt, 256), 256, 0, st>>>(HX, Zp, mean, obs_pos, dinv_diag, m, Mt, Bc, Y);
+    innovation_cat_kernel<<<nblk((long long)m * Mt, 256), 256, 0, st>>>(HX, O, ldo, Zp, mean, obs_pos, dinv_diag, m, Mt, Bc, Y);
     count_launch();
     return cudaGetLastError();
 }

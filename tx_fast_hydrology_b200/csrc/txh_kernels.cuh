@@ -137,8 +137,10 @@ cudaError_t launch_dgemm(int transA, int transB, int M, int N, int K, double alp
                          const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t st);
 cudaError_t launch_dgemm_splitk(int transA, int transB, int M, int N, int K, const double* A, int lda, const double* B,
                                 int ldb, double* Cpart, int ldc, int nsplit, long long pstride, cudaStream_t st);
-cudaError_t launch_innovation_cat(const double* HX, const double* Zp, const double* mean, const int32_t* obs_pos,
-                                  const double* dinv_diag, int m, int Mt, double* Bc, double* Y, cudaStream_t st);
+// O != nullptr: HX is gathered from the gauge rows of O on the way (and written out)
+cudaError_t launch_innovation_cat(double* HX, const double* O, int ldo, const double* Zp, const double* mean,
+                                  const int32_t* obs_pos, const double* dinv_diag, int m, int Mt, double* Bc, double* Y,
+                                  cudaStream_t st);
 cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long pstride, int Mt, double shift, double* Z,
                                     int* info, cudaStream_t st);
 cudaError_t launch_dgemm_ex(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
