@@ -368,34 +368,52 @@ chol_solve_blocked_kernel(const double* __restrict__ Cpart, long long pstride, i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int gc0 = blockIdx.x * 8;
-    // 4 elements x 8 partials in flight per thread
-    for (int e0 = 0; e0 < MT * MT; e0 += 4 * 256) {
-        double v[4];
+    // the split-K partials are summed on the way in: 8 elements x 8 partials in flight per thread, lower triangle
+    // only (the upper one is never read)
+    for (int e0 = 0; e0 < MT * MT; e0 += 8 * 256) {
+        double part[8][CS_NSPLIT];
+        // unconditional loads (an element that is not needed reads element 0): all 64 are issued before the first add
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const int e = e0 + u * 256 + tid;
             const int i = e / MT, c = e - i * MT;
-            v[u] = (i == c) ? 1.0 : 0.0;
-            if (e < MT * MT && i < Mt && c < Mt) {
-                v[u] = (i == c) ? shift : 0.0;
+            const bool need = e < MT * MT && i < Mt && c <= i;
+            const double* src = Cpart + (need ? (size_t)i * 2 * Mt + c : 0);
 #pragma unroll
-                for (int s = 0; s < CS_NSPLIT; ++s) v[u] += Cpart[(size_t)s * pstride + (size_t)i * 2 * Mt + c];
-            }
+            for (int s = 0; s < CS_NSPLIT; ++s) part[u][s] = __ldg(src + (size_t)s * pstride);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const int e = e0 + u * 256 + tid;
-            if (e < MT * MT) A[(e / MT) * LD + (e % MT)] = v[u];
+            const int i = e / MT, c = e - i * MT;
+            const bool need = e < MT * MT && i < Mt && c <= i;
+            double acc = (i == c) ? shift : 0.0;
+#pragma unroll
+            for (int s = 0; s < CS_NSPLIT; ++s) acc += part[u][s];
+            if (e < MT * MT) A[i * LD + c] = need ? acc : ((i == c) ? 1.0 : 0.0);
         }
     }
-    for (int e = tid; e < MT * 8; e += 256) {
-        const int i = e >> 3, cl = e & 7;
-        double v = 0.0;
-        if (i < Mt && gc0 + cl < Mt) {
+    {
+        constexpr int NB = MT * 8 / 256;                       // right-hand-side elements per thread
+        double part[NB][CS_NSPLIT];
 #pragma unroll
-            for (int s = 0; s < CS_NSPLIT; ++s) v += Cpart[(size_t)s * pstride + (size_t)i * 2 * Mt + Mt + gc0 + cl];
+        for (int u = 0; u < NB; ++u) {
+            const int e = tid + u * 256;
+            const int i = e >> 3, cl = e & 7;
+            const bool need = i < Mt && gc0 + cl < Mt;
+            const double* src = Cpart + (need ? (size_t)i * 2 * Mt + Mt + gc0 + cl : 0);
+#pragma unroll
+            for (int s = 0; s < CS_NSPLIT; ++s) part[u][s] = __ldg(src + (size_t)s * pstride);
         }
-        Bs[i * LDB + cl] = v;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int e = tid + u * 256;
+            const int i = e >> 3, cl = e & 7;
+            double v = 0.0;
+#pragma unroll
+            for (int s = 0; s < CS_NSPLIT; ++s) v += part[u][s];
+            Bs[i * LDB + cl] = (i < Mt && gc0 + cl < Mt) ? v : 0.0;
+        }
     }
     __syncthreads();
     // ---- factorisation + forward substitution, panel by panel ----
