@@ -348,6 +348,8 @@ def gpu_arm(a):
         mdl.run_assimilating(forcing, nsteps, enkf, every, Zp_dev, timers=timers)
 
     e2e_parts = {}
+    copy_stream = torch.cuda.Stream()
+    obs_ready = torch.cuda.Event()
 
     def e2e_run():
         def lap(key, t0, sync=True):
@@ -364,10 +366,12 @@ def gpu_arm(a):
         forcing.update(wl.times, table_pin, mul_pin, overlap=True)
         f = forcing
         t = lap("forcing_enqueue_ms", t, sync=False)
-        Zp_dev.copy_(Zp_pin, non_blocking=True)                                      # H2D
+        with torch.cuda.stream(copy_stream):                                         # H2D beside the first window
+            Zp_dev.copy_(Zp_pin, non_blocking=True)
+            obs_ready.record(copy_stream)
         t = lap("observations_enqueue_ms", t, sync=False)
         mdl._datetime = t_start
-        mdl.run_assimilating(f, nsteps, enkf, every, Zp_dev)
+        mdl.run_assimilating(f, nsteps, enkf, every, Zp_dev, observations_ready=obs_ready)
         t = lap("run_ms", t)
         mdl.download_state(out_o=out_pin)                                            # D2H (synchronises)
         lap("download_ms", t)

@@ -205,7 +205,9 @@ int txh_run_assimilating(txh_net* net, double* O_dev, double* I_dev, int64_t M, 
                          const int64_t* obs_reach_host, int64_t m, const double* Zp_dev /*[nsteps/every][m][M]*/,
                          const double* qs_dev, const double* R_dev, const double* Dinv_dev, int dinv_kind,
                          double* rowsum_dev /*[n]*/, double* HX_dev /*[m][M]*/, double* work_dev, double* W_dev,
-                         double* T_dev, double* G_dev, int64_t time_every, void* stream);
+                         double* T_dev, double* G_dev, int64_t time_every,
+                         void* obs_ready_event /* cudaEvent_t or NULL: Zp_dev is complete once it has fired (an upload
+                         on another stream); only the first update waits for it */, void* stream);
 int txh_get_route_timings(txh_net* net, double* ms_out, int64_t capacity, int64_t* count);
 
 /* Dense products of KalmanFilter.filter for small n (da.py:115-122): C = alpha op(A) op(B) + beta C,

@@ -246,8 +246,14 @@ def test_run_assimilating_vs_oracle(oracle, n, M, m, seed, in_library):
     enkf = EnsembleKalmanFilter(mdl, mdf, q, R)
     Zp = meas[:, :, None] + 0.1 * rng.standard_normal((nwin, m, M))
     f = mdl.make_forcing(times_ns=times, table=table, member_mul=mul)
-    Zd = torch.as_tensor(Zp, device="cuda")
-    mdl.run_assimilating(f, every * nwin, enkf, every, Zd if in_library else list(Zd))
+    # the observations travel on a side stream; the first update waits for the event, the first window does not
+    Zh = torch.from_numpy(np.ascontiguousarray(Zp)).pin_memory()
+    Zd = torch.empty(Zh.shape, dtype=torch.float64, device="cuda")
+    side, ready = torch.cuda.Stream(), torch.cuda.Event()
+    with torch.cuda.stream(side):
+        Zd.copy_(Zh, non_blocking=True)
+        ready.record(side)
+    mdl.run_assimilating(f, every * nwin, enkf, every, Zd if in_library else list(Zd), observations_ready=ready)
     mdl.network.check()
     assert enkf.n_updates == nwin and mdl.datetime.value == t0 + int(every * nwin * 300e9)
     ind = oracle.compute_indegree(net_d["startnodes"], net_d["endnodes"])

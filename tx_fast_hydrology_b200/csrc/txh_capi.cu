@@ -1088,7 +1088,7 @@ int txh_run_assimilating(txh_net* net, double* O, double* I, int64_t M, const tx
                          int64_t dt_ns, int64_t nsteps, int64_t every, int method, const int64_t* obs, int64_t m,
                          const double* Zp, const double* qs, const double* R, const double* Dinv, int dinv_kind,
                          double* rowsum, double* HX, double* work, double* W, double* T, double* G, int64_t time_every,
-                         void* stream)
+                         void* obs_ready_event, void* stream)
 {
     if (!net || !O || !I || !obs || !Zp || !qs || !R || !rowsum || !HX || !work || !W || !T || !G || every < 1 || m < 1)
         return fail(TXH_E_INVALID, "bad argument");
@@ -1105,6 +1105,9 @@ int txh_run_assimilating(txh_net* net, double* O, double* I, int64_t M, const tx
         rc = txh_route_run(net, O, I, M, fo, t, dt_ns, every, method, nullptr, 0, 1, nullptr, stream);
         if (timed) { CU(cudaEventRecord(e1, st)); net->route_events.emplace_back(e0, e1); }
         t += every * dt_ns;
+        // observations still on their way (copied on another stream): the first update waits for them, the first
+        // window does not
+        if (k == 0 && obs_ready_event) CU(cudaStreamWaitEvent(st, (cudaEvent_t)obs_ready_event, 0));
         if (rc == TXH_OK) rc = check_M(M);
         if (rc == TXH_OK) rc = enkf_solve_impl(net, m, M, HX, O, Zp + (size_t)k * m * M, rowsum, obs, qs, R, Dinv, dinv_kind, work, W, T, stream);
         if (rc == TXH_OK) rc = txh_enkf_apply(net, O, I, M, nullptr, 0, 0, M, 0, rowsum, T, obs, m, qs, W, G, stream);

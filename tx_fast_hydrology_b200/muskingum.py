@@ -397,7 +397,7 @@ class Muskingum:
         self.datetime = self.datetime + nsteps * self.timedelta
         return rec
 
-    def run_assimilating(self, forcing, nsteps, enkf, every, observations, timers=None):
+    def run_assimilating(self, forcing, nsteps, enkf, every, observations, timers=None, observations_ready=None):
         """Device-resident run with periodic ensemble assimilation: `every` routing steps in one
         persistent launch, then one `EnsembleKalmanFilter` update with `observations[k]` ([m][Mtot]
         CUDA tensor of per-member observations for the k-th update), repeated; nothing returns to
@@ -405,7 +405,9 @@ class Muskingum:
         step (the reference filters every step, da.py:56-61; SURVEY.md section 8c iv).
         `timers`: optional list; every 8th routing launch is bracketed by CUDA events -- the unsharded path
         keeps them in the library (`network.route_timings()` returns their durations), the sharded one appends
-        (start, end) torch event pairs."""
+        (start, end) torch event pairs.
+        `observations_ready`: optional `torch.cuda.Event` recorded after an upload of `observations` on another
+        stream; the first update waits for it (the first routing window does not)."""
         torch = self._ensure_device()
         self._sync_coeffs()
         d, net, M = self._dev, self.network, self.members
@@ -417,12 +419,15 @@ class Muskingum:
             # one call: the loop below, in the library (txh_run_assimilating)
             net.run_assimilating(d['O'], d['I'], M, forcing, t, step_ns, nsteps, every, enkf.reach_indices,
                                  observations, enkf._qs, enkf._R, enkf._Dinv, enkf._dinv_kind, enkf._rowsum, enkf._HX,
-                                 enkf._work, enkf._W, enkf._T, enkf._G, time_every=8 if timers is not None else 0)
+                                 enkf._work, enkf._W, enkf._T, enkf._G, time_every=8 if timers is not None else 0,
+                                 obs_ready=observations_ready)
             enkf.n_updates += nwin
             self._datetime = pd.Timestamp(t + nsteps * step_ns, tz='UTC')
             enkf.datetime = self._datetime
             self._device_advanced()
             return
+        if observations_ready is not None:
+            torch.cuda.current_stream().wait_event(observations_ready)
         # the ensemble row sums ride on the last step of every routing launch
         net.set_stats_output(enkf._rowsum, enkf.stats_scale())
         for k in range(nwin):

@@ -271,7 +271,7 @@ class RiverNetwork:
                                         _stream_ptr()))
 
     def run_assimilating(self, O, I, M, forcing, t0_ns, dt_ns, nsteps, every, obs_reach, Zp, qs, R, Dinv, dinv_kind,
-                         rowsum, HX, work, W, T, G, method=1, time_every=0):
+                         rowsum, HX, work, W, T, G, method=1, time_every=0, obs_ready=None):
         """`txh_run_assimilating`: routing windows + ensemble updates of an unsharded ensemble, host out of the loop."""
         idx = L.as_i64(obs_reach)
         L.check(self._lib.txh_run_assimilating(
@@ -279,7 +279,7 @@ class RiverNetwork:
             int(t0_ns), int(dt_ns), int(nsteps), int(every), int(method), L.ptr_i64(idx), idx.size, _cuda_ptr(Zp),
             _cuda_ptr(qs), _cuda_ptr(R), _cuda_ptr(Dinv) if Dinv is not None else None, int(dinv_kind),
             _cuda_ptr(rowsum), _cuda_ptr(HX), _cuda_ptr(work), _cuda_ptr(W), _cuda_ptr(T), _cuda_ptr(G),
-            int(time_every), _stream_ptr()))
+            int(time_every), ctypes.c_void_p(obs_ready.cuda_event) if obs_ready is not None else None, _stream_ptr()))
 
     def route_timings(self):
         """Durations (ms) of the routing launches `run_assimilating(time_every=...)` bracketed; synchronises."""
