@@ -667,10 +667,12 @@ enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const dou
 // T is staged once per CTA; every warp streams its 16-row tiles through a double-buffered shared-memory
 // stage (cp.async, the next tile in flight while the tensor cores work on the current one) and reads both
 // the A fragments and, in the epilogue, the old outflows from it, so O is read from global memory once.
+constexpr int EU64_RT = 1;                        // row tiles per warp (see enkf_update64_kernel)
 constexpr int EU_RS = 576;                       // bytes per staged row: 512 + 64, conflict-free 128-bit reads
-constexpr int EU64_SMEM = 64 * EU_LDT * 8 + EU_WARPS * 2 * 16 * EU_RS;
+constexpr int EU64_SMEM = 64 * EU_LDT * 8 + 16 * 2 * 8 * EU_RS;   // the same for 8 warps x 16 rows and 16 warps x 8 rows
 
-__global__ void __launch_bounds__(EU_WARPS * 32, 1)
+template <int RT>                                 // 8-row MMA tiles per warp: 2 (8 warps per CTA) or 1 (16 warps)
+__global__ void __launch_bounds__(512 / RT * 1, 1)
 enkf_update64_kernel(const double* __restrict__ X, int M, const double* __restrict__ mean, const double* __restrict__ T,
                      int ldt, double* __restrict__ O, double* __restrict__ G, int ld, long long n,
                      const int32_t* __restrict__ gauge_of_pos, const double* __restrict__ qs,
@@ -680,17 +682,18 @@ enkf_update64_kernel(const double* __restrict__ X, int M, const double* __restri
     double* sT = reinterpret_cast<double*>(eu_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const unsigned stage0 = (unsigned)__cvta_generic_to_shared(eu_smem + 64 * EU_LDT * 8 + warp * 2 * 16 * EU_RS);
-    const long long ntiles = (n + 15) / 16;
-    const long long tstride = (long long)gridDim.x * EU_WARPS;
-    long long tile = (long long)blockIdx.x * EU_WARPS + warp;
+    constexpr int NW = 16 / RT, TR = 8 * RT;          // warps per CTA, rows per warp tile
+    const unsigned stage0 = (unsigned)__cvta_generic_to_shared(eu_smem + 64 * EU_LDT * 8 + warp * 2 * TR * EU_RS);
+    const long long ntiles = (n + TR - 1) / TR;
+    const long long tstride = (long long)gridDim.x * NW;
+    long long tile = (long long)blockIdx.x * NW + warp;
     auto prefetch = [&](long long tl, int buf) {
         if (tl < ntiles && 2 * lane < ld) {
-            const long long r0 = tl * 16;
+            const long long r0 = tl * TR;
 #pragma unroll
-            for (int r = 0; r < 16; ++r)
+            for (int r = 0; r < TR; ++r)
                 if (r0 + r < n) {
-                    const unsigned sa = stage0 + (buf * 16 + r) * EU_RS + lane * 16;
+                    const unsigned sa = stage0 + (buf * TR + r) * EU_RS + lane * 16;
                     const double* gp = X + (size_t)(r0 + r) * ld + 2 * lane;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gp) : "memory");
                 }
@@ -700,16 +703,16 @@ enkf_update64_kernel(const double* __restrict__ X, int M, const double* __restri
     prefetch(tile, 0);
     {
         // all 16 loads of a thread are in flight before the first store
-        double tv[16];
+        double tv[8 * RT];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int e = tid + u * EU_WARPS * 32;
+        for (int u = 0; u < 8 * RT; ++u) {
+            const int e = tid + u * NW * 32;
             const int k = e >> 6, c = e & 63;
             tv[u] = (k < M && c < M) ? __ldg(T + (size_t)k * ldt + c) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int e = tid + u * EU_WARPS * 32;
+        for (int u = 0; u < 8 * RT; ++u) {
+            const int e = tid + u * NW * 32;
             sT[(e >> 6) * EU_LDT + (e & 63)] = tv[u];
         }
     }
@@ -719,30 +722,34 @@ enkf_update64_kernel(const double* __restrict__ X, int M, const double* __restri
     // exposed at the head of every tile)
     auto row_meta = [&](long long tl, double* mu_o, int* gi_o) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const long long row = tl * 16 + 8 * i + g;
+        for (int i = 0; i < RT; ++i) {
+            const long long row = tl * TR + 8 * i + g;
             const bool ok = tl < ntiles && row < n;
             mu_o[i] = ok ? __ldg(mean + row) : 0.0;
             gi_o[i] = ok ? __ldg(gauge_of_pos + row) : -1;
         }
     };
-    double mu_n[2];
-    int gi_n[2];
+    double mu_n[RT];
+    int gi_n[RT];
     row_meta(tile, mu_n, gi_n);
     for (; tile < ntiles; tile += tstride, buf ^= 1) {
         prefetch(tile + tstride, buf ^ 1);
-        const double mu[2] = {mu_n[0], mu_n[1]};
-        const int gi[2] = {gi_n[0], gi_n[1]};
+        double mu[RT];
+        int gi[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) { mu[i] = mu_n[i]; gi[i] = gi_n[i]; }
         row_meta(tile + tstride, mu_n, gi_n);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
-        const long long rw = tile * 16;
-        const long long rows[2] = {rw + g, rw + 8 + g};
-        double a[2][16];
+        const long long rw = tile * TR;
+        long long rows[RT];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < RT; ++i) rows[i] = rw + 8 * i + g;
+        double a[RT][16];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
             const bool ok = rows[i] < n;
-            const unsigned ra = stage0 + (buf * 16 + 8 * i + g) * EU_RS + t * 16;
+            const unsigned ra = stage0 + (buf * TR + 8 * i + g) * EU_RS + t * 16;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int k = 8 * j + 2 * t;
@@ -752,9 +759,9 @@ enkf_update64_kernel(const double* __restrict__ X, int M, const double* __restri
                 a[i][2 * j + 1] = (ok && k + 1 < M) ? v.y - mu[i] : 0.0;
             }
         }
-        double acc[2][8][2];
+        double acc[RT][8][2];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < RT; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 #pragma unroll
@@ -764,17 +771,17 @@ enkf_update64_kernel(const double* __restrict__ X, int M, const double* __restri
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const double b = bt[8 * j];
-                dmma8x8x4(acc[0][j][0], acc[0][j][1], a[0][ks], b);
-                dmma8x8x4(acc[1][j][0], acc[1][j][1], a[1][ks], b);
+#pragma unroll
+                for (int i = 0; i < RT; ++i) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i][ks], b);
             }
         }
         // epilogue: G = gain (+ the Q[:, s] term on gauged rows, da.py:117-121), O = old outflow + gain
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < RT; ++i) {
             if (rows[i] >= n) continue;
             const double qg = gi[i] >= 0 ? qs[gi[i]] : 0.0;
             const double* wr = W + (size_t)(gi[i] >= 0 ? gi[i] : 0) * M;
-            const unsigned ra = stage0 + (buf * 16 + 8 * i + g) * EU_RS + t * 16;
+            const unsigned ra = stage0 + (buf * TR + 8 * i + g) * EU_RS + t * 16;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int col = 8 * j + 2 * t;
@@ -966,10 +973,13 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
 {
     long long tiles = (n + EU_ROWS - 1) / EU_ROWS;
     if (Mtot == Mloc && Mtot <= 64 && ld <= 64 && ldx == ld && col0 == 0) {
-        cudaError_t e = cudaFuncSetAttribute(enkf_update64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EU64_SMEM);
+        constexpr int RT = EU64_RT;
+        tiles = (n + 8 * RT - 1) / (8 * RT);
+        tiles = (tiles + 16 / RT - 1) / (16 / RT);             // CTAs' worth of warp tiles
+        cudaError_t e = cudaFuncSetAttribute(enkf_update64_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, EU64_SMEM);
         if (e != cudaSuccess) return e;
         const long long grid2 = tiles < (long long)num_sms ? tiles : (long long)num_sms;
-        enkf_update64_kernel<<<(unsigned)grid2, EU_WARPS * 32, EU64_SMEM, st>>>(Xall, Mtot, mean, T, ldt, O, G, ld, n,
+        enkf_update64_kernel<RT><<<(unsigned)grid2, 512 / RT, EU64_SMEM, st>>>(Xall, Mtot, mean, T, ldt, O, G, ld, n,
                                                                                gauge_of_pos, qs, W);
         count_launch();
         return cudaGetLastError();
