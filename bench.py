@@ -470,6 +470,10 @@ def gpu_arm(a):
         best = min(cs.run()[0] for _ in range(2))
         cpu = {"value": cs.updates / best, "unit": UNIT, "cores": cs.threads, "kind": "port",
                "sample": cs.describe()}
+        # the same on ONE core, one window (SURVEY.md section 8d asks for both)
+        c1 = CpuSample(wl, 1)
+        c1.threads = 1
+        cpu["value_1core"] = c1.updates / c1.run()[0]
 
     if rank == 0:
         line = {
