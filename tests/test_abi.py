@@ -40,6 +40,14 @@ def test_no_cpu_fallback(libtxh):
     buf = (ctypes.c_double * 8)()
     rc = libtxh.txh_route_step(net.handle, buf, buf, 1, None, None)
     assert rc == -4 and b"no CPU fallback" in libtxh.txh_last_error()
+    # ... and so do the fused entry points (dense filter chain, in-library assimilation loop)
+    obs = (ctypes.c_int64 * 1)(1)
+    z = (ctypes.c_double * 1)(0.0)
+    rc = libtxh.txh_kf_filter(net.handle, buf, buf, None, buf, buf, obs, 1, z, buf, buf, buf, buf, buf, buf, None)
+    assert rc == -4
+    rc = libtxh.txh_run_assimilating(net.handle, buf, buf, 1, None, 0, 1, 2, 1, 1, obs, 1, buf, buf, buf, buf, 1,
+                                     buf, buf, buf, buf, buf, buf, 0, None, None)
+    assert rc == -4
     with pytest.raises((TxhError, RuntimeError)):
         from tx_fast_hydrology_b200.muskingum import Muskingum
         from tx_fast_hydrology_b200 import synthetic as S
