@@ -79,6 +79,16 @@ int txh_get_window_info(const txh_net* net, int64_t info[8]);
 int txh_get_window_schedule(const txh_net* net, int32_t* wtask_desc, uint32_t* whdr /*[n]*/, uint32_t* winw,
                             int32_t* wprod);
 
+/* lane schedule (route_lane_kernel, ensembles of up to 16 members: lanes are reaches, regions of the network run
+ * time-skewed in shared memory).  Host only.  cap_rows > 0 overrides the rows per region for schedules not yet
+ * in use.  info = {n_regions, n_row_entries, n_child_entries, n_slots, max_real, max_virt, max_extra, member_tile};
+ * regions rows are 8 int32: row_off, n_real, n_virt, child_off, n_child, n_extra, height, pad; rows are 4 int32
+ * per entry: reach (-1: virtual row or the sentinel closing a region), skew offset, first child (relative to the
+ * region's child_off), slot (real: stream published, virtual: stream mirrored; -1 none); child: region-local rows.
+ * Replaces the implicit ordering of the reference's headwater walk (nutils.py:72-88) for M <= 16. */
+int txh_get_lane_info(txh_net* net, int64_t M, int64_t cap_rows, int64_t info[8]);
+int txh_get_lane_schedule(txh_net* net, int64_t M, int32_t* regions, int32_t* rows, int32_t* child);
+
 /* ---- coefficients ----------------------------------------------------------------
  * txh_compute_coeffs replaces Muskingum.compute_muskingum_coeffs (muskingum.py:332-360):
  * host arithmetic in the reference's operation order; results returned in reach order

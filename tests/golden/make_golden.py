@@ -6,7 +6,8 @@ Run in the build container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py
 
 Outputs (committed): kernels_n60.npz, kernels_n160.npz, model_c1.npz,
-kalman_n120.npz, checkpoint_n80.npz.  Every file stores its inputs next to the
+kalman_n120.npz, checkpoint_n80.npz, split_n300.npz, smoother_n60.npz, quirks_n90.npz,
+checkpoint_kf_n70.npz.  Every file stores its inputs next to the
 reference's outputs, so replaying it needs neither the reference nor the
 generator.
 """
@@ -249,7 +250,104 @@ def smoother():
     print("smoother_n60.npz ok", len(ks.datetimes))
 
 
+def quirks():
+    """User-mutated coefficients and the variable-timestep quirk, through the reference's step():
+    set_transmissive_boundary (muskingum.py:567-571) in the middle of a run, and step(p, timedelta=dt2)
+    followed by default steps (muskingum.py:447-449: the second call sees dt == self.dt and keeps the
+    coefficients of the 600 s call)."""
+    n, seed = 90, 23
+    net = S.make_network(n, seed)
+    prm = S.make_params(n, seed)
+    d = S.model_dict(net, prm, dt_s=300.0, t0=T0)
+    rng = np.random.default_rng(seed)
+    q = rng.gamma(0.5, 2.0, size=(16, n))
+    # (a) transmissive boundary installed after 5 steps
+    mdl = Muskingum(d)
+    for s in range(5):
+        mdl.step(q[s])
+    o_a5, i_a5 = mdl.o_t_next.copy(), mdl.i_t_next.copy()
+    tb = np.sort(rng.choice(n, size=6, replace=False))
+    mdl.set_transmissive_boundary(tb)
+    for s in range(5, 10):
+        mdl.step(q[s])
+    o_a10, i_a10 = mdl.o_t_next.copy(), mdl.i_t_next.copy()
+    coef_a = np.stack([mdl.alpha, mdl.beta, mdl.chi, mdl.gamma])
+    # (b) variable timestep
+    mdl = Muskingum(dict(d))
+    mdl.step(q[0])
+    mdl.step(q[1], timedelta=pd.to_timedelta(600, unit="s"))
+    o_b2, t_b2 = mdl.o_t_next.copy(), mdl.datetime.value
+    coef_b2 = np.stack([mdl.alpha, mdl.beta, mdl.chi, mdl.gamma])
+    mdl.step(q[2])                                   # default timedelta: runs on the 600 s coefficients
+    mdl.step(q[3])
+    o_b4, i_b4, t_b4 = mdl.o_t_next.copy(), mdl.i_t_next.copy(), mdl.datetime.value
+    coef_b4 = np.stack([mdl.alpha, mdl.beta, mdl.chi, mdl.gamma])
+    np.savez_compressed(
+        os.path.join(HERE, "quirks_n90.npz"), endnodes=mdl.endnodes, K=mdl.K, X=mdl.X, o_init=prm["o_t"],
+        dt=300.0, t0_ns=pd.Timestamp(T0).value, q=q, tb=tb, o_a5=o_a5, i_a5=i_a5, o_a10=o_a10, i_a10=i_a10,
+        coef_a=coef_a, o_b2=o_b2, t_b2=t_b2, coef_b2=coef_b2, o_b4=o_b4, i_b4=i_b4, t_b4=t_b4, coef_b4=coef_b4)
+    print("quirks_n90.npz ok")
+
+
+def checkpoint_kf():
+    """The operational cycle of app.py:56-80,125-141: 'checkpoint' bound before 'kf' (SURVEY.md A.7), a run,
+    load_state (model state, clock and the filter's covariance rewind: simulation.py:196-206, da.py:83-89),
+    the measurement table REASSIGNED (app.py:75-80), and a second run from the checkpoint."""
+    n, m, T, seed = 70, 6, 30, 29
+    net = S.make_network(n, seed)
+    prm = S.make_params(n, seed, well_posed=True)
+    d = S.model_dict(net, prm, dt_s=300.0, t0=T0)
+    mdl = Muskingum(d)
+    t0_ns = mdl.datetime.value
+    times, table = S.make_forcing(n, 2 * T, 300.0, seed, t0_ns=t0_ns, rows_every=6)
+    cols = d["reach_ids"]
+    df1 = frame(times[times <= t0_ns + T * int(300e9)], table[times <= t0_ns + T * int(300e9)], cols)
+    gidx = S.make_gauges(net["endnodes"], m, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    gcols = rng.permutation(gidx)
+    mt1 = t0_ns + np.arange(0, T + 1, 3, dtype=np.int64) * int(300e9)
+    meas1 = rng.uniform(0.5, 8.0, size=(mt1.size, m))
+    mdf1 = frame(mt1, meas1, [cols[j] for j in gcols])
+    R = 1e-2 * np.eye(m); Q = 2.0 * np.eye(n); P0 = Q.copy()
+    cp = CheckPoint(mdl, timedelta=3600)
+    mdl.bind_callback(cp, key="checkpoint")
+    kf = KalmanFilter(mdl, mdf1, Q, R, P0)
+    mdl.bind_callback(kf, key="kf")
+    for state in mdl.simulate(df1):
+        pass
+    o_end, t_end = mdl.o_t_next.copy(), mdl.datetime.value
+    P_end = kf.P_t_next.copy()
+    saved_o, saved_i = mdl.saved_states["o_t_next"].copy(), mdl.saved_states["i_t_next"].copy()
+    saved_t = mdl.saved_states["datetime"].value
+    saved_P = kf.saved_states["P_t_next"].copy()
+    mdl.load_state()
+    o_loaded, t_loaded, P_loaded = mdl.o_t_next.copy(), mdl.datetime.value, kf.P_t_next.copy()
+    # a new forecast cycle: new forcing frame, new measurement frame (different rows, same gauges)
+    t1 = mdl.datetime.value
+    sel = (times >= t1) & (times <= t1 + T * int(300e9))
+    df2 = frame(times[sel], table[sel], cols)
+    mt2 = t1 + np.arange(0, T + 1, 2, dtype=np.int64) * int(300e9)
+    meas2 = rng.uniform(0.5, 8.0, size=(mt2.size, m))
+    kf.measurements = frame(mt2, meas2, [cols[j] for j in gcols]).iloc[:, np.argsort(gcols)]
+    O2 = []
+    for state in mdl.simulate(df2):
+        O2.append(state.o_t_next.copy())
+    np.savez_compressed(
+        os.path.join(HERE, "checkpoint_kf_n70.npz"), endnodes=mdl.endnodes, K=mdl.K, X=mdl.X, o_init=prm["o_t"],
+        dt=300.0, t0_ns=t0_ns, times=times, table=table, T=T, gauge_cols=gcols, meas_times1=mt1, meas1=meas1,
+        meas_times2=mt2, meas2=meas2, R=R, Q=Q, P0=P0, o_end=o_end, t_end=t_end, P_end=P_end, saved_o=saved_o,
+        saved_i=saved_i, saved_t=saved_t, saved_P=saved_P, o_loaded=o_loaded, t_loaded=t_loaded, P_loaded=P_loaded,
+        O2=np.stack(O2), o_end2=mdl.o_t_next.copy(), i_end2=mdl.i_t_next.copy(), t_end2=mdl.datetime.value,
+        P_end2=kf.P_t_next.copy(), saved_t2=mdl.saved_states["datetime"].value)
+    print("checkpoint_kf_n70.npz ok")
+
+
 if __name__ == "__main__":
+    only = set(sys.argv[1:])
+    if only:                                  # e.g. `make_golden.py quirks checkpoint_kf`: just these fixtures
+        for name in only:
+            globals()[name]()
+        sys.exit(0)
     smoother()
     split_collection()
     kernels(60, 7, "kernels_n60.npz")

@@ -9,10 +9,13 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9
+# placeholders until the first GPU measurement of this round calibrates them (see tests/perf/kf_error_budget.py)
+GAIN_TOL = 1e-8
+SMOOTH_X_TOL = 1e-8
+SMOOTH_P_TOL = 1e-7
 
 
-def relerr(a, b):
-    return float(np.abs(np.asarray(a) - np.asarray(b)).max()) / max(1e-300, float(np.abs(b).max()))
+from parity import relerr, normerr        # element-wise with a floor / max-norm (dense matrices)
 
 
 def frame(times_ns, table, cols):
@@ -82,9 +85,9 @@ def test_kalman_filter_matches_reference(golden_dir):
         O.append(state.o_t_next.copy()); I.append(state.i_t_next.copy())
         Pd.append(np.diag(kf.P_t_next).copy()); gains.append(kf.gain.copy())
     assert relerr(np.stack(O), g["O"]) < RTOL and relerr(np.stack(I), g["I"]) < RTOL
-    assert relerr(np.stack(Pd), g["P_diag"]) < RTOL
-    assert relerr(np.stack(gains), g["gains"]) < 1e-8      # gains are differences of O(1) numbers
-    assert relerr(kf.P_t_next, g["P_final"]) < RTOL and relerr(kf.K, g["K_final"]) < RTOL
+    assert normerr(np.stack(Pd), g["P_diag"]) < RTOL
+    assert normerr(np.stack(gains), g["gains"]) < GAIN_TOL
+    assert normerr(kf.P_t_next, g["P_final"]) < RTOL and normerr(kf.K, g["K_final"]) < RTOL
 
 
 def test_kalman_smoother_matches_reference(golden_dir):
@@ -102,10 +105,10 @@ def test_kalman_smoother_matches_reference(golden_dir):
     assert relerr(mdl.o_t_next, g["o_final"]) < RTOL and relerr(mdl.i_t_next, g["i_final"]) < RTOL
     ts = sorted(ks.o_hat_s.index)
     assert [pd.Timestamp(t).value for t in ts] == [int(x) for x in g["smooth_times"]]
-    assert relerr(ks.o_hat_s.loc[ts].values, g["o_hat_s"]) < 1e-8
-    assert relerr(ks.i_hat_s.loc[ts].values, g["i_hat_s"]) < 1e-8
-    assert relerr(ks.P_f[ts[-1]].cpu().numpy(), g["P_f_last"]) < RTOL
-    assert relerr(ks.P_s[ts[0]].cpu().numpy(), g["P_s_first"]) < 1e-7     # ten solves with P_p deep
+    assert normerr(ks.o_hat_s.loc[ts].values, g["o_hat_s"]) < SMOOTH_X_TOL
+    assert normerr(ks.i_hat_s.loc[ts].values, g["i_hat_s"]) < SMOOTH_X_TOL
+    assert normerr(ks.P_f[ts[-1]].cpu().numpy(), g["P_f_last"]) < RTOL
+    assert normerr(ks.P_s[ts[0]].cpu().numpy(), g["P_s_first"]) < SMOOTH_P_TOL
 
 
 def test_checkpoint_rewind(golden_dir):
@@ -127,6 +130,118 @@ def test_checkpoint_rewind(golden_dir):
         pass
     assert relerr(mdl.o_t_next, g["o_end2"]) < RTOL and mdl.datetime.value == int(g["t_end2"])
     assert mdl.saved_states["datetime"].value == int(g["saved_t2"])
+
+
+def test_transmissive_boundary_and_variable_timestep(golden_dir):
+    """User-mutated coefficients (set_transmissive_boundary, muskingum.py:567-571) reach the device copies in the
+    middle of a run, and step(p, timedelta=dt2) followed by default steps keeps the dt2 coefficients
+    (muskingum.py:447-449) -- both against the unmodified reference."""
+    g = np.load(os.path.join(golden_dir, "quirks_n90.npz"))
+    q = g["q"]
+    mdl, d = model_from(g)
+    for s in range(5):
+        mdl.step(q[s])
+    assert relerr(mdl.o_t_next, g["o_a5"]) < RTOL and relerr(mdl.i_t_next, g["i_a5"]) < RTOL
+    mdl.set_transmissive_boundary(g["tb"])
+    for s in range(5, 10):
+        mdl.step(q[s])
+    assert (np.stack([mdl.alpha, mdl.beta, mdl.chi, mdl.gamma]) == g["coef_a"]).all()
+    assert relerr(mdl.o_t_next, g["o_a10"]) < RTOL and relerr(mdl.i_t_next, g["i_a10"]) < RTOL
+    # a pass-through reach hands its inflow on unchanged
+    assert relerr(mdl.o_t_next[g["tb"]], mdl.i_t_next[g["tb"]]) < 1e-15
+    # the device fast path sees the mutated coefficients too: 3 more steps through run() == 3 step() calls
+    twin = mdl.copy()
+    for s in range(10, 13):
+        mdl.step(q[s])
+    times = int(g["t0_ns"]) + np.arange(11, 14, dtype=np.int64) * int(300e9)      # sampled at the END of a step
+    f = twin.make_forcing(times_ns=times, table=np.ascontiguousarray(q[10:13]))
+    twin.run(f, 3)
+    assert relerr(twin.o_t_next, mdl.o_t_next) < 1e-13 and twin.datetime == mdl.datetime
+
+    mdl, d = model_from(g)
+    mdl.step(q[0])
+    mdl.step(q[1], timedelta=pd.to_timedelta(600, unit="s"))
+    assert mdl.datetime.value == int(g["t_b2"]) and relerr(mdl.o_t_next, g["o_b2"]) < RTOL
+    assert (np.stack([mdl.alpha, mdl.beta, mdl.chi, mdl.gamma]) == g["coef_b2"]).all()
+    mdl.step(q[2]); mdl.step(q[3])
+    assert mdl.datetime.value == int(g["t_b4"])
+    assert (np.stack([mdl.alpha, mdl.beta, mdl.chi, mdl.gamma]) == g["coef_b4"]).all()
+    assert relerr(mdl.o_t_next, g["o_b4"]) < RTOL and relerr(mdl.i_t_next, g["i_b4"]) < RTOL
+
+
+def test_checkpoint_with_kalman_filter_and_new_measurements(golden_dir):
+    """The service loop of app/app.py:56-80,125-141 against the unmodified reference: 'checkpoint' bound before
+    'kf' (SURVEY.md A.7), a run, load_state -- model state, clock AND the filter's covariance rewind through
+    CheckPoint's fan-out (simulation.py:196-206, da.py:83-89) -- then the measurement table is REASSIGNED
+    (app.py:75-80) and the next cycle must assimilate the new frame, not the one the filter was built with."""
+    from tx_fast_hydrology_b200.da import KalmanFilter
+    from tx_fast_hydrology_b200.simulation import CheckPoint
+    g = np.load(os.path.join(golden_dir, "checkpoint_kf_n70.npz"))
+    mdl, d = model_from(g)
+    cols = d["reach_ids"]
+    T, t0 = int(g["T"]), int(g["t0_ns"])
+    times, table = g["times"], g["table"]
+    sel = times <= t0 + T * int(300e9)
+    df1 = frame(times[sel], table[sel], cols)
+    gcols = g["gauge_cols"]
+    mdf1 = frame(g["meas_times1"], g["meas1"], [cols[j] for j in gcols])
+    mdl.bind_callback(CheckPoint(mdl, timedelta=3600), key="checkpoint")
+    kf = KalmanFilter(mdl, mdf1, g["Q"], g["R"], g["P0"])
+    mdl.bind_callback(kf, key="kf")
+    for _ in mdl.simulate(df1):
+        pass
+    assert mdl.datetime.value == int(g["t_end"]) and relerr(mdl.o_t_next, g["o_end"]) < RTOL
+    # covariances: max-norm (entries between far-apart reaches are differences of O(1) products)
+    assert normerr(kf.P_t_next, g["P_end"]) < RTOL
+    assert mdl.saved_states["datetime"].value == int(g["saved_t"])
+    assert relerr(mdl.saved_states["o_t_next"], g["saved_o"]) < RTOL
+    assert relerr(mdl.saved_states["i_t_next"], g["saved_i"]) < RTOL
+    assert normerr(kf.saved_states["P_t_next"].cpu().numpy(), g["saved_P"]) < RTOL
+    mdl.load_state()
+    assert mdl.datetime.value == int(g["t_loaded"]) and relerr(mdl.o_t_next, g["o_loaded"]) < RTOL
+    assert normerr(kf.P_t_next, g["P_loaded"]) < RTOL
+    t1 = mdl.datetime.value
+    sel = (times >= t1) & (times <= t1 + T * int(300e9))
+    df2 = frame(times[sel], table[sel], cols)
+    new = frame(g["meas_times2"], g["meas2"], [cols[j] for j in gcols])
+    kf.measurements = new                      # columns in the caller's order: re-ordered by label
+    assert list(kf.measurements.columns) == [cols[j] for j in np.sort(gcols)]
+    assert kf.latest_timestamp.value == int(g["meas_times2"][-1])
+    O2 = [state.o_t_next.copy() for state in mdl.simulate(df2)]
+    assert relerr(np.stack(O2), g["O2"]) < RTOL
+    assert relerr(mdl.o_t_next, g["o_end2"]) < RTOL and relerr(mdl.i_t_next, g["i_end2"]) < RTOL
+    assert mdl.datetime.value == int(g["t_end2"]) and mdl.saved_states["datetime"].value == int(g["saved_t2"])
+    assert normerr(kf.P_t_next, g["P_end2"]) < RTOL
+    with pytest.raises(ValueError):
+        kf.measurements = new.iloc[:, :-1]
+
+
+def test_bad_shapes_are_rejected_before_the_c_abi(golden_dir):
+    """Raw pointers cross the boundary: sizes are checked on the Python side (no out-of-bounds device reads)."""
+    from tx_fast_hydrology_b200.da import KalmanFilter
+    g = np.load(os.path.join(golden_dir, "checkpoint_kf_n70.npz"))
+    mdl, d = model_from(g)
+    cols = d["reach_ids"]
+    n, m = mdl.n, g["gauge_cols"].size
+    mdf = frame(g["meas_times1"], g["meas1"], [cols[j] for j in g["gauge_cols"]])
+    with pytest.raises(ValueError):
+        mdl.step(np.zeros(n - 1))
+    with pytest.raises(ValueError):
+        KalmanFilter(mdl, mdf, g["Q"], g["R"][:-1, :-1], g["P0"])
+    with pytest.raises(ValueError):
+        KalmanFilter(mdl, mdf, g["Q"], g["R"], g["P0"][:-1])
+    with pytest.raises(ValueError):
+        KalmanFilter(mdl, mdf, np.ones(n - 1), g["R"], g["P0"])
+    # what the reference accepts through numpy broadcasting (da.py:115-116) is accepted here: scalar Q
+    kf = KalmanFilter(mdl, mdf, 2.0, g["R"], g["P0"])
+    mdl.bind_callback(kf, key="kf")
+    kf.filter()
+    ref_mdl, _ = model_from(g)
+    kf2 = KalmanFilter(ref_mdl, mdf, 2.0 * np.ones((n, n)), g["R"], g["P0"])
+    kf2.filter()
+    assert (kf.P_t_next == kf2.P_t_next).all() and (mdl.o_t_next == ref_mdl.o_t_next).all()
+    with pytest.raises(ValueError):
+        mdl.network.unpack_host(mdl.device_state[0], 1, out=np.empty(n - 1))
 
 
 def test_nutils_names(golden_dir):

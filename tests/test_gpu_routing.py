@@ -1,9 +1,9 @@
 """GPU parity tests of the routing kernels, through the C ABI (libtxh.so), against the
 CPU oracle and the golden vectors produced by the unmodified reference.
 
-Tolerance: FP64, max relative error <= 1e-9 (BASELINE.json north_star); the kernels
-re-associate the confluence sums and contract to FMA, so results are not bit-identical
-(observed ~1e-15).  Integer artefacts are compared exactly elsewhere (test_topology.py).
+Tolerance: FP64, element-wise relative error <= 1e-9 with an absolute floor of 1e-12 of the largest
+element (tests/parity.py; BASELINE.json north_star); the kernels re-associate the confluence sums and
+contract to FMA, so results are not bit-identical (observed ~1e-15).  Integer artefacts are compared exactly elsewhere (test_topology.py).
 """
 import os
 
@@ -15,9 +15,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
-def relerr(a, b):
-    scale = max(1e-300, float(np.abs(b).max()))
-    return float(np.abs(a - b).max()) / scale
+from parity import relerr        # element-wise |a-b| / max(|b|, 1e-12 max|b|)
 
 
 @pytest.fixture(scope="module")
@@ -42,7 +40,7 @@ def _upload(torch, net, o, i, M):
     return O, I
 
 
-@pytest.mark.parametrize("kernel", ["window", "dataflow"])
+@pytest.mark.parametrize("kernel", ["lane", "window", "dataflow"])
 @pytest.mark.parametrize("fname", ["kernels_n60.npz", "kernels_n160.npz"])
 def test_golden_kernels(torch_cuda, libtxh, golden_dir, monkeypatch, fname, kernel):
     """Outputs of the unmodified reference's kernels; single steps and operator applications run on the
@@ -115,7 +113,7 @@ def test_golden_model_c1(torch_cuda, libtxh, golden_dir):
     assert relerr(net.unpack_host(I, 1)[:, 0], g["I"][-1]) < RTOL
 
 
-@pytest.mark.parametrize("kernel", ["window", "dataflow"])
+@pytest.mark.parametrize("kernel", ["lane", "window", "dataflow"])
 @pytest.mark.parametrize("n,seed,M,sched", [
     (1000, 1, 1, None), (1000, 1, 3, None), (2500, 6, 64, None), (2500, 6, 70, None),
     (1500, 9, 130, None), (3000, 4, 5, (8, 4, 6, 3)), (300, 5, 2, (4, 8, 8, 1)), (7, 12, 2, None),

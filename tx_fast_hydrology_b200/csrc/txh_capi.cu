@@ -79,7 +79,20 @@ struct txh_net {
     uint32_t *d_whdr = nullptr, *d_winw = nullptr;
     int32_t* d_wprod = nullptr;
     double* d_ring = nullptr; size_t ring_cap = 0; int ring_ld = 0;
-    int route_kernel = 0;               // 0 auto (window unless recording), 1 dataflow, 2 window
+    int route_kernel = 0;               // 0 auto (lane for small ensembles, else window; dataflow when recording
+                                        // a large ensemble), 1 dataflow, 2 window, 3 lane
+    // lane kernel (txh_lane.cu): one schedule per member tile, built on first use
+    struct LaneDev {
+        LaneSchedule sched;
+        bool built = false, ok = false, on_dev = false;
+        LaneRegionDesc* d_regions = nullptr;
+        int4* d_meta = nullptr;
+        uint16_t* d_child = nullptr;
+    };
+    LaneDev lane[5];                    // member tiles 1, 2, 4, 8, 16
+    int lane_max_members = 8;           // ensembles up to this size take the lane kernel
+    int lane_cap_rows = 0;              // rows per region; 0 = from the size of the network and the SM count
+    double* d_lring = nullptr; size_t lring_cap = 0;
     double* d_stage = nullptr; size_t stage_cap = 0;   // reach-order staging of txh_pack_host / txh_unpack_host
     double* stats_rowsum = nullptr;     // txh_set_stats_output: row sums of the final outflows of every routing call
     double stats_scale = 1.0;
@@ -143,7 +156,10 @@ int ensure_device(txh_net* net)
     if (const char* k = getenv("TXH_ROUTE_KERNEL")) {
         if (!strcmp(k, "dataflow")) net->route_kernel = 1;
         else if (!strcmp(k, "window")) net->route_kernel = 2;
+        else if (!strcmp(k, "lane")) net->route_kernel = 3;
     }
+    if (const char* k = getenv("TXH_LANE_MAX_M")) net->lane_max_members = std::max(0, std::min(16, atoi(k)));
+    if (const char* k = getenv("TXH_LANE_CAP")) net->lane_cap_rows = std::max(0, atoi(k));
     CU(cudaMalloc((void**)&net->d_coef, sizeof(double) * (6 * net->topo.n + net->sched.link_last.size() + 1)));
     CU(cudaMalloc((void**)&net->d_qtmp, sizeof(double) * net->topo.n));
     CU(cudaMalloc((void**)&net->d_qctl, 64));
@@ -186,6 +202,34 @@ int stage_buffer(txh_net* net, size_t doubles, cudaStream_t st, double** out)
     }
     *out = net->d_stage;
     return TXH_OK;
+}
+
+// Synchronise `st` and report what the device recorded since the last report: a watchdog bail-out (status word)
+// or a failed factorisation (info word).  Both words are cleared once reported, so the handle is usable again
+// after the caller has re-uploaded a sane state; the rings of the persistent kernels are re-armed with them
+// (an abandoned launch leaves cells behind).
+int report_status(txh_net* net, cudaStream_t st)
+{
+    CU(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int32_t status = net->h_status[0], info = net->h_status[1];
+    if (status == 0 && info == 0) return TXH_OK;
+    CU(cudaMemsetAsync(net->d_status, 0, 2 * sizeof(int32_t), st));
+    if (status != 0) {
+        if (net->d_ring) CU(cudaMemsetAsync(net->d_ring, 0xff, net->ring_cap * sizeof(double), st));
+        if (net->d_lring) CU(cudaMemsetAsync(net->d_lring, 0xff, net->lring_cap * sizeof(double), st));
+        CU(cudaMemsetAsync(net->d_qctl, 0, 32, st));                    // queue cursors, tickets
+        CU(cudaMemsetAsync(net->d_qctl + 5, 0, 24, st));                // done counters, lane ticket
+        CU(cudaStreamSynchronize(st));
+        return fail(TXH_E_WATCHDOG, "a routing launch bailed out on its dataflow watchdog (a wait for another task "
+                                    "exceeded TXH_WATCHDOG_MS; the state arrays of that call are undefined)");
+    }
+    CU(cudaStreamSynchronize(st));
+    if (info > 0)
+        return fail(TXH_E_INVALID, "an ensemble innovation covariance was not positive definite (Cholesky pivot " +
+                                   std::to_string(info) + ")");
+    return fail(TXH_E_INVALID, "a Kalman innovation covariance P[s][:,s] + R was singular (Gauss-Jordan pivot " +
+                               std::to_string(-info) + ")");
 }
 
 int check_M(int64_t M)
@@ -410,12 +454,144 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     return TXH_OK;
 }
 
-// routing entry: the window kernel unless recording was asked for (or the environment says otherwise)
+// ---- lane kernel (txh_lane.cu): lanes = reaches, for deterministic runs and small ensembles --------------
+constexpr size_t kLaneSmemBudget = 200 * 1024;
+
+int lane_tile_index(int64_t M) { return M <= 1 ? 0 : M <= 2 ? 1 : M <= 4 ? 2 : M <= 8 ? 3 : 4; }
+
+// host side only: the schedule for member tile index `ti` (built once per handle).  Without an explicit cap the
+// rows per region follow from the size of the network: one region per SM while that keeps a region within two
+// passes of a CTA's threads (all regions are then resident at once and run as one pipeline).
+txh_net::LaneDev* lane_schedule(txh_net* net, int ti, int num_sms)
+{
+    txh_net::LaneDev& L = net->lane[ti];
+    if (!L.built) {
+        std::string err;
+        int side_min = 32;
+        if (const char* k = getenv("TXH_LANE_SIDE_MIN")) side_min = atoi(k);
+        if (net->lane_cap_rows > 0) {
+            L.ok = L.sched.build(net->topo, net->sched.pos_of_reach, 1 << ti, net->lane_cap_rows, kLaneSmemBudget, side_min, err);
+        } else {
+            const int64_t per_sm = (net->topo.n + num_sms - 1) / std::max(1, num_sms);
+            int cap = (int)std::min<int64_t>(2048, std::max<int64_t>(320, per_sm + per_sm / 50));
+            for (;;) {
+                L.ok = L.sched.build(net->topo, net->sched.pos_of_reach, 1 << ti, cap, kLaneSmemBudget, side_min, err);
+                if (!L.ok || (int)L.sched.regions.size() <= num_sms || cap >= 2048) break;
+                cap = std::min(2048, cap + std::max(8, cap / 12));
+            }
+        }
+        L.built = true;
+        if (!L.ok) g_err = err;
+    }
+    return &L;
+}
+
+// Returns 1 when the lane schedule cannot be built for this network (the caller falls back).
+int run_lane(txh_net* net, double* O, double* I, int64_t M, const double* F, const double* W, int wm_ld,
+             const StepPlan& plan, int64_t nsteps, const int32_t* rec_slot, double* rec_out, int rec_every,
+             int rec_count, cudaStream_t st)
+{
+    const int ti = lane_tile_index(M), mt = 1 << ti;
+    if (M > 16) return 1;
+    txh_net::LaneDev* L = lane_schedule(net, ti, net->num_sms);
+    if (!L->ok) return 1;
+    const LaneSchedule& s = L->sched;
+    if (!L->on_dev) {
+        std::vector<int4> meta(s.row_reach.size());
+        for (size_t i = 0; i < meta.size(); ++i) {
+            const int32_t j = s.row_reach[i];
+            meta[i] = make_int4(j >= 0 ? net->sched.pos_of_reach[j] : -1, s.row_off[i], s.row_cbeg[i], s.row_slot[i]);
+        }
+        int rc;
+        if ((rc = upload(&L->d_regions, s.regions))) return rc;
+        if ((rc = upload(&L->d_meta, meta))) return rc;
+        if ((rc = upload(&L->d_child, s.child))) return rc;
+        L->on_dev = true;
+    }
+    const int ld = (int)txh_row_stride(M);
+    // streams ring[slot][member][step]: one launch covers as many steps as fit 128 MiB
+    const size_t streams = (size_t)std::max(1, s.n_slots) * (size_t)M;
+    int64_t spl = std::min<int64_t>(nsteps, 4096);
+    if (const char* k = getenv("TXH_LANE_SPL")) { const long v = atol(k); if (v > 0) spl = std::min<int64_t>(spl, v); }
+    while (spl > 16 && streams * (size_t)((spl + 15) & ~int64_t(15)) * sizeof(double) > (size_t(128) << 20)) spl = (spl + 1) / 2;
+    if (rec_slot && rec_every > 1 && spl < nsteps) spl = std::max<int64_t>(rec_every, spl / rec_every * rec_every);
+    const size_t ring_need = streams * (size_t)((spl + 15) & ~int64_t(15));
+    if (ring_need > net->lring_cap) {
+        if (net->d_lring) { CU(cudaStreamSynchronize(st)); CU(cudaFree(net->d_lring)); }
+        CU(cudaMalloc((void**)&net->d_lring, ring_need * sizeof(double)));
+        net->lring_cap = ring_need;
+        CU(cudaMemsetAsync(net->d_lring, 0xff, ring_need * sizeof(double), st));   // every cell starts EMPTY
+    }
+    const StepInterp* d_steps = net->d_unit_step;
+    if (plan.times) {
+        if ((size_t)spl > net->steps_cap) {
+            if (net->d_steps) { CU(cudaStreamSynchronize(st)); CU(cudaFree(net->d_steps)); }
+            CU(cudaMalloc((void**)&net->d_steps, sizeof(StepInterp) * spl));
+            net->steps_cap = spl;
+        }
+        d_steps = net->d_steps;
+    } else if (nsteps != 1) {
+        return fail(TXH_E_INVALID, "internal: a launch without a forcing table covers one step");
+    }
+    // shared-memory layout
+    LaneArgs a{};
+    auto up16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    const size_t rr = (size_t)std::max(1, s.max_real), rvs = rr + (size_t)s.max_virt;
+    a.rr_stride = (int32_t)rr; a.rv_stride = (int32_t)rvs;
+    size_t off = up16(16 * (rvs + 1));
+    a.off_coef = (int32_t)off; off += 64 * rr;
+    a.off_p = (int32_t)off; off += 8 * (size_t)mt * rr;
+    a.off_obuf = (int32_t)off; off += 16 * (size_t)mt * rvs;
+    a.off_ext = (int32_t)off; off += 256 * (size_t)mt * (size_t)s.max_virt;
+    a.off_child = (int32_t)off; off += up16(2 * (size_t)std::max(1, s.max_child));
+    const size_t smem = off;
+    if (smem > 227 * 1024) return 1;
+    const int tv = s.max_virt > 0 ? std::min(256, (s.max_virt + 31) / 32 * 32) : 0;
+    const int tr = std::min(1024 - tv, (s.max_real + 31) / 32 * 32);
+    a.TR = tr;
+    const int threads = tr + tv;
+    const int grid = std::min<int>(net->num_sms, (int)s.regions.size());
+    for (int64_t s0 = 0; s0 < nsteps; s0 += spl) {
+        const int64_t ns = std::min<int64_t>(spl, nsteps - s0);
+        if (plan.times) {
+            InitArgs ia{};
+            ia.times = plan.times; ia.steps_out = net->d_steps; ia.t0_ns = plan.t0_ns; ia.dt_ns = plan.dt_ns;
+            ia.step_base = s0; ia.R = (int32_t)plan.R; ia.nsteps = (int32_t)ns; ia.method = plan.method;
+            CU(launch_window_init(ia, net->d_qctl + 6, st));
+        }
+        a.regions = L->d_regions; a.meta = L->d_meta; a.child = L->d_child;
+        a.coef = net->d_coef; a.O = O; a.I = I; a.F = F; a.steps = d_steps; a.Wmul = W;
+        a.ring = net->d_lring; a.ticket = net->d_qctl + 6; a.done = net->d_qctl + 7;
+        a.status = net->d_status; a.watchdog_ns = net->watchdog_ns;
+        a.rec_slot = rec_slot; a.rec_out = rec_out; a.rec_step_base = s0;
+        a.rec_every = std::max(1, rec_every); a.rec_count = rec_count;
+        a.n = net->topo.n; a.n_regions = (int32_t)s.regions.size(); a.nsteps = (int32_t)ns;
+        a.splp = (int32_t)((ns + 15) & ~int64_t(15)); a.ld = ld; a.M = (int32_t)M; a.wm_ld = wm_ld;
+        a.R = plan.times ? (int32_t)plan.R : 1;
+        CU(launch_route_lane(a, mt, threads, smem, grid, st));
+    }
+    return TXH_OK;
+}
+
+bool lane_wanted(const txh_net* net, int64_t M)
+{
+    if (net->route_kernel == 3) return M <= 16;
+    return net->route_kernel == 0 && M <= net->lane_max_members;
+}
+
+// routing entry: the lane kernel for small ensembles, else the window kernel unless recording was asked for
+// (or the environment says otherwise)
 int run_routing(txh_net* net, double* O, double* I, int64_t M, const double* F, const double* W, int wm_ld,
                 const StepPlan& plan, int64_t nsteps, const int32_t* rec_slot, double* rec_out, int rec_every,
                 int rec_count, cudaStream_t st)
 {
     const int ld = (int)txh_row_stride(M);
+    if (lane_wanted(net, M)) {
+        const int rc = run_lane(net, O, I, M, F, W, wm_ld, plan, nsteps, rec_slot, rec_out, rec_every, rec_count, st);
+        if (rc == TXH_OK && net->stats_rowsum)
+            CU(launch_enkf_stats(O, ld, (int)M, net->topo.n, net->stats_scale, nullptr, net->stats_rowsum, nullptr, st));
+        if (rc != 1) return rc;
+    }
     if (net->route_kernel != 1 && !rec_slot) {
         const int rc = run_window(net, O, I, M, F, W, wm_ld, plan, nsteps, st);
         if (rc == TXH_OK && net->stats_rowsum && ld > kMemberBlock)
@@ -431,6 +607,10 @@ int run_routing(txh_net* net, double* O, double* I, int64_t M, const double* F, 
 // one step without a forcing table (q: [n] schedule order or nullptr): window kernel first, dataflow otherwise
 int run_one_step(txh_net* net, double* O, double* I, int64_t M, const double* q, cudaStream_t st)
 {
+    if (lane_wanted(net, M)) {
+        const int rc = run_lane(net, O, I, M, q, nullptr, 0, StepPlan(), 1, nullptr, nullptr, 1, 0, st);
+        if (rc != 1) return rc;
+    }
     if (net->route_kernel != 1) {
         const int rc = run_window(net, O, I, M, q, nullptr, 0, StepPlan(), 1, st);
         if (rc != 1) return rc;
@@ -488,6 +668,8 @@ void txh_destroy(txh_net* net)
         if (net->d_gauge_of_pos) cudaFree(net->d_gauge_of_pos);
         cudaFree(net->d_wtasks); cudaFree(net->d_whdr); cudaFree(net->d_winw); cudaFree(net->d_wprod);
         if (net->d_ring) cudaFree(net->d_ring);
+        if (net->d_lring) cudaFree(net->d_lring);
+        for (auto& L : net->lane) { cudaFree(L.d_regions); cudaFree(L.d_meta); cudaFree(L.d_child); }
         if (net->d_stage) cudaFree(net->d_stage);
         if (net->h_status) cudaFreeHost(net->h_status);
     }
@@ -576,6 +758,35 @@ int txh_get_window_schedule(const txh_net* net, int32_t* wtask_desc, uint32_t* w
     return TXH_OK;
 }
 
+int txh_get_lane_info(txh_net* net, int64_t M, int64_t cap_rows, int64_t info[8])
+{
+    if (!net || !info || M < 1 || M > 16) return fail(TXH_E_INVALID, "bad argument");
+    if (cap_rows > 0) {
+        if (net->lane_cap_rows != (int)cap_rows) for (auto& L : net->lane) if (!L.on_dev) L.built = false;
+        net->lane_cap_rows = (int)cap_rows;
+    }
+    txh_net::LaneDev* L = lane_schedule(net, lane_tile_index(M), net->num_sms > 0 ? net->num_sms : 148);
+    if (!L->ok) return fail(TXH_E_INVALID, g_err);
+    const LaneSchedule& s = L->sched;
+    info[0] = (int64_t)s.regions.size(); info[1] = (int64_t)s.row_reach.size(); info[2] = (int64_t)s.child.size();
+    info[3] = s.n_slots; info[4] = s.max_real; info[5] = s.max_virt; info[6] = s.max_extra; info[7] = s.mt;
+    return TXH_OK;
+}
+int txh_get_lane_schedule(txh_net* net, int64_t M, int32_t* regions, int32_t* rows, int32_t* child)
+{
+    if (!net || M < 1 || M > 16) return fail(TXH_E_INVALID, "bad argument");
+    txh_net::LaneDev* L = lane_schedule(net, lane_tile_index(M), net->num_sms > 0 ? net->num_sms : 148);
+    if (!L->ok) return fail(TXH_E_INVALID, g_err);
+    const LaneSchedule& s = L->sched;
+    if (regions) std::memcpy(regions, s.regions.data(), s.regions.size() * sizeof(LaneRegionDesc));
+    if (rows)
+        for (size_t i = 0; i < s.row_reach.size(); ++i) {
+            rows[4 * i] = s.row_reach[i]; rows[4 * i + 1] = s.row_off[i]; rows[4 * i + 2] = s.row_cbeg[i]; rows[4 * i + 3] = s.row_slot[i];
+        }
+    if (child) for (size_t i = 0; i < s.child.size(); ++i) child[i] = s.child[i];
+    return TXH_OK;
+}
+
 int txh_set_coeffs(txh_net* net, const double* al, const double* be, const double* ch, const double* ga)
 {
     if (!net || !al || !be || !ch || !ga) return fail(TXH_E_INVALID, "null argument");
@@ -648,10 +859,7 @@ int txh_unpack_host(txh_net* net, const double* src, int64_t M, int layout, doub
     if ((rc = stage_buffer(net, (size_t)n * M, st, &tmp))) return rc;
     CU(launch_unpack(net->d_reach_of_pos, src, tmp, n, (int)M, (int)txh_row_stride(M), layout, st));
     CU(cudaMemcpyAsync(dst, tmp, sizeof(double) * n * M, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (*net->h_status != 0) return fail(TXH_E_WATCHDOG, "a routing launch bailed out on its dataflow watchdog");
-    return TXH_OK;
+    return report_status(net, st);
 }
 
 int txh_pack_dev(txh_net* net, const double* src, int64_t M, double* dst, void* stream)
@@ -917,11 +1125,7 @@ int txh_check(txh_net* net, void* stream)
     if (!net) return fail(TXH_E_INVALID, "null argument");
     if (!net->dev_ready) return TXH_OK;
     // the status word (watchdog) and the solver info word travel only here: launches stay back to back
-    CU(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CU(cudaStreamSynchronize((cudaStream_t)stream));
-    if (net->h_status[0] != 0) return fail(TXH_E_WATCHDOG, "a routing launch bailed out on its dataflow watchdog");
-    if (net->h_status[1] != 0) return fail(TXH_E_INVALID, "an innovation covariance was not positive definite");
-    return TXH_OK;
+    return report_status(net, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -96,6 +96,32 @@ struct WinArgs {
     double rowsum_scale;
 };
 
+// route_lane_kernel (txh_lane.cu): lanes = reaches, time-skewed regions, state in shared memory
+struct LaneArgs {
+    const LaneRegionDesc* regions;        // ticket order
+    const int4* meta;                     // per row: {position (-1: virtual), skew offset, first child, slot}
+    const uint16_t* child;
+    const double* coef;                   // [n][4]
+    double* O;
+    double* I;
+    const double* F;                      // [R][n] schedule order, or nullptr
+    const StepInterp* steps;              // [nsteps] interpolation records of this launch
+    const double* Wmul;                   // [R][wm_ld] or nullptr
+    double* ring;                         // [n_slots][M][splp] streams between regions; EMPTY (all bits set) when idle
+    unsigned long long* ticket;           // zero at launch; the last CTA to leave zeroes it again
+    unsigned long long* done;
+    int32_t* status;
+    unsigned long long watchdog_ns;
+    const int32_t* rec_slot;              // [n] recording slot of each position or -1; nullptr = off
+    double* rec_out;                      // [steps recorded][rec_count][M]
+    long long rec_step_base;              // steps of the call before this launch
+    int64_t n;
+    int32_t n_regions, nsteps, splp, ld, M, wm_ld, R, rec_every, rec_count;
+    int32_t TR;                           // threads [0, TR) own real rows, the rest the virtual rows
+    int32_t rr_stride, rv_stride;         // row strides of the p / outflow arrays
+    int32_t off_coef, off_p, off_obuf, off_ext, off_child;   // shared-memory layout (bytes)
+};
+
 struct LevelArgs {
     const int32_t* lvl_pos;               // positions of this level
     int32_t count;
@@ -113,6 +139,7 @@ cudaError_t launch_route_dataflow(const RouteArgs& a, int num_sms, cudaStream_t 
 cudaError_t launch_route_level(const LevelArgs& a, cudaStream_t st);
 cudaError_t launch_window_init(const InitArgs& a, unsigned long long* ticket, cudaStream_t st);
 cudaError_t launch_route_window(const WinArgs& a, int warps_per_cta, int num_sms, cudaStream_t st);
+cudaError_t launch_route_lane(const LaneArgs& a, int mt, int threads, size_t smem, int grid, cudaStream_t st);
 cudaError_t launch_init_inflows(const int32_t* up_off, const int32_t* up_pos, const uint8_t* is_outlet,
                                 const double* O, double* I, int64_t n, int ld, int M, cudaStream_t st);
 cudaError_t launch_apply_gain(const int32_t* up_off, const int32_t* up_pos, const double* G, double* O,

@@ -117,7 +117,7 @@ inverse_smem_kernel(double* __restrict__ A, int m, int in_smem, int* __restrict_
         }
         const int pr = bi;
         double inv = 1.0;
-        if (bv > 0.0) inv = 1.0 / cv[pr]; else if (tid == 0) *info = j + 1;
+        if (bv > 0.0) inv = 1.0 / cv[pr]; else if (tid == 0) *info = -(j + 1);   // negative: Gauss-Jordan pivot (txh_check)
         // swap rows j <-> pr, a[j][j] := 1, scale the pivot row
         for (int c = tid; c < m; c += nt) {
             const double vp = a[(size_t)pr * m + c];

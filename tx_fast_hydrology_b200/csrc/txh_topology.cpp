@@ -684,3 +684,179 @@ bool Schedule::build(const Topology& t, const SchedParams& p_in, std::string& er
 }
 
 }  // namespace txh
+
+// ---------------------------------------------------------------------------
+// Lane schedule (route_lane_kernel)
+// ---------------------------------------------------------------------------
+namespace txh {
+
+size_t LaneSchedule::region_bytes(size_t real, size_t virt, size_t nchild, int mt)
+{
+    auto up16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    return 16 * (real + virt + 1)          // row records
+           + 64 * real                     // alpha beta chi gamma f0 f1 fn aux
+           + 8 * (size_t)mt * real         // p = beta i + chi o
+           + 16 * (size_t)mt * (real + virt)   // outflows of this and the previous iteration
+           + 256 * (size_t)mt * virt       // 32 steps of every incoming stream
+           + up16(2 * nchild);
+}
+
+bool LaneSchedule::build(const Topology& t, const std::vector<int32_t>& pos_of_reach, int mt_, int cap_rows_,
+                         size_t smem_budget_, int side_min, std::string& err)
+{
+    mt = mt_; cap_rows = cap_rows_; smem_budget = smem_budget_;
+    side_min = std::max(2, side_min);
+    const int64_t n = t.n;
+    if (mt < 1 || mt > 16 || (mt & (mt - 1))) { err = "lane schedule: member tile must be 1, 2, 4, 8 or 16"; return false; }
+    if (cap_rows < 1) { err = "lane schedule: bad row cap"; return false; }
+    cap_rows = std::min(cap_rows, 60000);                                   // 16-bit local indices
+    // weights in bytes: a real row with ~one child entry, a virtual row
+    const int64_t wr = 16 + 64 + 24 * (int64_t)mt + 2, wv = 16 + 272 * (int64_t)mt + 2;
+    const int64_t cap_bytes = (int64_t)smem_budget - 256;               // sentinel record, alignment of the parts
+    if (wr + wv > cap_bytes) { err = "lane schedule: shared-memory budget too small"; return false; }
+
+    // ---- clusters: greedy bottom-up cut of the forest into sub-trees that fit one CTA -------------------
+    // The deepest child (the longest path continues through it) stays with its downstream reach as long as
+    // the caps allow; side tributaries of `side_min` rows or more are always cut off -- they become clusters of
+    // their own, bundled with others of the same height -- so that the chain of regions along a long path
+    // (every link costs a trip through L2) stays short.
+    std::vector<int64_t> open_w(n, 0);
+    std::vector<int32_t> open_r(n, 0);
+    std::vector<uint8_t> closed(n, 0);
+    {
+        std::vector<std::pair<int64_t, int32_t>> kids;
+        for (int32_t j : t.topo) {
+            int64_t W = wr; int32_t R = 1;
+            kids.clear();
+            const int32_t mainc = t.main_child[j];
+            for (int32_t c = t.child_off[j]; c < t.child_off[j + 1]; ++c) {
+                const int32_t ch = t.child[c];
+                if (!closed[ch] && ch != mainc && open_r[ch] >= side_min) closed[ch] = 1;
+                if (closed[ch]) W += wv;
+                else { W += open_w[ch]; R += open_r[ch]; if (ch != mainc) kids.emplace_back(open_w[ch], ch); }
+            }
+            if (W > cap_bytes || R > cap_rows) {
+                std::sort(kids.begin(), kids.end(), [](auto& a, auto& b) {
+                    return a.first != b.first ? a.first > b.first : a.second < b.second; });
+                if (mainc >= 0 && !closed[mainc]) kids.emplace_back(open_w[mainc], mainc);   // the path itself: last
+                for (auto& kv : kids) {
+                    if (W <= cap_bytes && R <= cap_rows) break;
+                    closed[kv.second] = 1;
+                    W -= kv.first - wv; R -= open_r[kv.second];
+                }
+                if (W > cap_bytes) { err = "lane schedule: a confluence is too wide for one region"; return false; }
+            }
+            open_w[j] = W; open_r[j] = R;
+            if (t.end[j] == j) closed[j] = 1;
+        }
+    }
+    // cluster of every reach, distance to the cluster's exit
+    std::vector<int32_t> cl_of(n, -1), dist(n, 0), cl_root;
+    for (int64_t k = n - 1; k >= 0; --k) {
+        const int32_t j = t.topo[k];
+        if (closed[j]) { cl_of[j] = (int32_t)cl_root.size(); cl_root.push_back(j); dist[j] = 0; }
+        else { cl_of[j] = cl_of[t.end[j]]; dist[j] = dist[t.end[j]] + 1; }
+    }
+    const int32_t ncl = (int32_t)cl_root.size();
+    // per cluster: rows, virtual rows, children entries, depth (virtual leaves included), height in the cluster graph
+    std::vector<int32_t> cl_real(ncl, 0), cl_virt(ncl, 0), cl_child(ncl, 0), cl_depth(ncl, 0), cl_h(ncl, 0);
+    for (int32_t j : t.topo) {                                              // upstream first: heights are final at the root
+        const int32_t c = cl_of[j];
+        cl_real[c] += 1;
+        cl_child[c] += t.child_off[j + 1] - t.child_off[j];
+        cl_depth[c] = std::max(cl_depth[c], dist[j]);
+        for (int32_t e = t.child_off[j]; e < t.child_off[j + 1]; ++e) {
+            const int32_t ch = t.child[e];
+            if (!closed[ch]) continue;
+            cl_virt[c] += 1;
+            cl_depth[c] = std::max(cl_depth[c], dist[j] + 1);
+            cl_h[c] = std::max(cl_h[c], cl_h[cl_of[ch]] + 1);
+        }
+    }
+    // ---- regions: clusters of equal height bundled up to the caps; ticket order = height ascending ----------
+    std::vector<int32_t> cl_order(ncl);
+    std::iota(cl_order.begin(), cl_order.end(), 0);
+    // among equal heights: deep clusters first (they pace their consumers), then by root id
+    std::stable_sort(cl_order.begin(), cl_order.end(), [&](int32_t a, int32_t b) {
+        if (cl_h[a] != cl_h[b]) return cl_h[a] < cl_h[b];
+        if (cl_depth[a] != cl_depth[b]) return cl_depth[a] > cl_depth[b];
+        return cl_root[a] < cl_root[b]; });
+    std::vector<int32_t> reg_of_cl(ncl, -1);
+    std::vector<std::vector<int32_t>> reg_cls;
+    {
+        size_t real = 0, virt = 0, nch = 0; int32_t cur_h = -1;
+        for (int32_t c : cl_order) {
+            const bool fits = !reg_cls.empty() && cl_h[c] == cur_h && real + cl_real[c] <= (size_t)cap_rows &&
+                              real + virt + cl_real[c] + cl_virt[c] < 65000 &&
+                              region_bytes(real + cl_real[c], virt + cl_virt[c], nch + cl_child[c], mt) <= smem_budget;
+            if (!fits) {
+                reg_cls.emplace_back(); real = virt = nch = 0; cur_h = cl_h[c];
+                if (region_bytes(cl_real[c], cl_virt[c], cl_child[c], mt) > smem_budget) {
+                    err = "lane schedule: a cluster exceeds the shared-memory budget"; return false;
+                }
+            }
+            reg_cls.back().push_back(c);
+            reg_of_cl[c] = (int32_t)reg_cls.size() - 1;
+            real += cl_real[c]; virt += cl_virt[c]; nch += cl_child[c];
+        }
+    }
+    // ---- slots: one stream per cluster root that drains into another cluster -------------------------------
+    std::vector<int32_t> slot_of(n, -1);
+    n_slots = 0;
+    for (int32_t c = 0; c < ncl; ++c) {
+        const int32_t r = cl_root[c];
+        if (t.end[r] != r) slot_of[r] = n_slots++;
+    }
+    // ---- rows of every region ---------------------------------------------------------------------------
+    const int32_t nreg = (int32_t)reg_cls.size();
+    std::vector<std::vector<int32_t>> reg_rows(nreg);
+    for (int64_t j = 0; j < n; ++j) reg_rows[reg_of_cl[cl_of[j]]].push_back((int32_t)j);
+    regions.assign(nreg, LaneRegionDesc{});
+    row_reach.clear(); row_off.clear(); row_cbeg.clear(); row_slot.clear(); child.clear();
+    max_real = max_virt = max_child = max_extra = 0;
+    std::vector<int32_t> local(n, -1);
+    for (int32_t g = 0; g < nreg; ++g) {
+        std::vector<int32_t>& rows = reg_rows[g];
+        std::sort(rows.begin(), rows.end(), [&](int32_t a, int32_t b) { return pos_of_reach[a] < pos_of_reach[b]; });
+        LaneRegionDesc& rd = regions[g];
+        rd.row_off = (int32_t)row_reach.size();
+        rd.n_real = (int32_t)rows.size();
+        rd.child_off = (int32_t)child.size();
+        rd.height = cl_h[reg_cls[g].front()];
+        for (int32_t i = 0; i < rd.n_real; ++i) local[rows[i]] = i;
+        int32_t nv = 0, extra = 0;
+        std::vector<int32_t> v_off, v_slot;
+        for (int32_t i = 0; i < rd.n_real; ++i) {
+            const int32_t j = rows[i], c = cl_of[j];
+            const int32_t off = cl_depth[c] - dist[j];
+            row_reach.push_back(j); row_off.push_back(off);
+            row_cbeg.push_back((int32_t)child.size() - rd.child_off);
+            row_slot.push_back(slot_of[j]);
+            extra = std::max(extra, off + 1);
+            for (int32_t e = t.child_off[j]; e < t.child_off[j + 1]; ++e) {
+                const int32_t ch = t.child[e];
+                if (!closed[ch]) child.push_back((uint16_t)local[ch]);      // rows are sorted by position, not by id:
+                else {                                                      // local[] of every row was set above
+                    child.push_back((uint16_t)(rd.n_real + nv));
+                    v_off.push_back(off - 1); v_slot.push_back(slot_of[ch]);
+                    ++nv;
+                }
+            }
+        }
+        rd.n_virt = nv;
+        rd.n_child = (int32_t)child.size() - rd.child_off;
+        for (int32_t v = 0; v < nv; ++v) {
+            if (v_off[v] < 0) { err = "internal: lane skew offset below zero"; return false; }
+            row_reach.push_back(-1); row_off.push_back(v_off[v]); row_cbeg.push_back(rd.n_child); row_slot.push_back(v_slot[v]);
+        }
+        // sentinel closing the children list of the last row
+        row_reach.push_back(-1); row_off.push_back(0); row_cbeg.push_back(rd.n_child); row_slot.push_back(-1);
+        rd.n_extra = extra;
+        max_real = std::max(max_real, rd.n_real); max_virt = std::max(max_virt, rd.n_virt);
+        max_child = std::max(max_child, rd.n_child); max_extra = std::max(max_extra, rd.n_extra);
+        if (region_bytes(rd.n_real, rd.n_virt, rd.n_child, mt) > smem_budget) { err = "internal: lane region over budget"; return false; }
+    }
+    return true;
+}
+
+}  // namespace txh

@@ -117,6 +117,49 @@ struct WTaskDesc {
     int32_t pad_;
 };
 
+// ---------------------------------------------------------------------------------------------------
+// Lane schedule (route_lane_kernel, small ensembles): lanes are REACHES, not members.
+//
+// The network is cut into regions (unions of sub-trees); one CTA owns a region for every step of a launch
+// with its state in shared memory.  Inside a region every row (reach) has a skew offset
+//   off = D - d,   d = distance (in reaches) to the exit of its sub-tree, D = the sub-tree's largest d,
+// and evaluates timestep s in iteration k = s + off of the CTA's loop.  An edge u -> j inside a region then
+// has off[u] = off[j] - 1: what a row reads in iteration k was written in iteration k - 1, one barrier apart,
+// so ALL rows of a region are busy in every iteration, each on its own timestep (time skewing, SURVEY.md
+// appendix B).  Outflows that cross regions travel through per-(slot, member) streams in global memory,
+// ring[slot][member][step]; the consuming region mirrors every stream as a VIRTUAL row (a leaf one skew level
+// above its consumer) whose thread copies the stream into the row buffer, prefetching 16 steps ahead.
+// Regions are claimed in a topological order of the region graph (producers first).
+struct LaneRegionDesc {
+    int32_t row_off;      // first entry of this region in the row arrays (real rows, then virtual rows)
+    int32_t n_real;
+    int32_t n_virt;
+    int32_t child_off;    // first entry in `child`
+    int32_t n_child;
+    int32_t n_extra;      // largest skew offset + 1: iterations of a launch = nsteps + n_extra - 1
+    int32_t height;       // level of the region in the region graph (0: depends on no other region)
+    int32_t pad_;
+};
+
+struct LaneSchedule {
+    int mt = 0;                             // member tile the regions were sized for (1, 2, 4, 8, 16)
+    int cap_rows = 0;
+    size_t smem_budget = 0;
+    std::vector<LaneRegionDesc> regions;    // ticket order
+    // per row (region-local order): reach id (-1: virtual), skew offset, first child (relative to the region's
+    // child_off; row r's children are [cbeg[r], cbeg[r+1]), the entry after the last real row closes the list),
+    // slot (real: stream the outflow is published to, or -1; virtual: stream it mirrors)
+    std::vector<int32_t> row_reach, row_off, row_cbeg, row_slot;
+    std::vector<uint16_t> child;            // region-local row indices
+    int32_t n_slots = 0, max_real = 0, max_virt = 0, max_child = 0, max_extra = 0;
+
+    // bytes of shared memory a region of (real, virt, child) rows needs at member tile mt
+    static size_t region_bytes(size_t real, size_t virt, size_t nchild, int mt);
+    // side_min: side tributaries of at least this many rows always become clusters of their own
+    bool build(const Topology& t, const std::vector<int32_t>& pos_of_reach, int mt, int cap_rows, size_t smem_budget,
+               int side_min, std::string& err);
+};
+
 struct Schedule {
     SchedParams prm;
     std::vector<int32_t> pos_of_reach, reach_of_pos;

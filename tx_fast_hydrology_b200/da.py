@@ -45,7 +45,33 @@ def _gauge_setup(model, measurements):
     return reach_indices[permutations], permutations
 
 
-class KalmanFilter(BaseCallback):
+class _MeasurementTable:
+    """`measurements` is a live attribute in the reference: the service loop reassigns it on every forecast
+    cycle (app/app.py:75-80) and `interpolate_input` / `latest_timestamp` read it on every call (da.py:63-81).
+    The drop-in keeps float64 copies of the index and the values for the device path, rebuilt on assignment.
+    A frame whose columns are the filter's gauges in another order is re-ordered by label (the reference would
+    silently pair gauges with the wrong reaches); another column set is an error."""
+
+    @property
+    def measurements(self):
+        return self._measurements
+
+    @measurements.setter
+    def measurements(self, frame):
+        assert isinstance(frame.index, pd.DatetimeIndex)
+        assert (frame.index.tz == _dt.timezone.utc)
+        known = getattr(self, '_measurements', None)
+        if known is not None:
+            if frame.shape[1] != known.shape[1] or set(frame.columns) != set(known.columns):
+                raise ValueError('new measurements must carry the same gauge columns as the filter was built with')
+            if list(frame.columns) != list(known.columns):
+                frame = frame[known.columns]
+        self._measurements = frame
+        self._meas_times = frame.index.astype(int).astype(float).values
+        self._meas_values = np.ascontiguousarray(frame.values, dtype=np.float64)
+
+
+class KalmanFilter(_MeasurementTable, BaseCallback):
     def __init__(self, model, measurements, Q_cov, R_cov, P_t_init):
         import torch
         self.model = model
@@ -61,16 +87,28 @@ class KalmanFilter(BaseCallback):
         s[self.reach_indices] = True
         self.s = s
         self.measurements = measurements.iloc[:, perm]
-        self.R_cov = np.asarray(R_cov, dtype=np.float64)[perm, :][:, perm]
-        self._meas_times = self.measurements.index.astype(int).astype(float).values
-        self._meas_values = np.ascontiguousarray(self.measurements.values, dtype=np.float64)
+        n, m = model.n, self.num_measurements
+        R_full = np.asarray(R_cov, dtype=np.float64)
+        if R_full.shape != (m, m):
+            raise ValueError(f'`R_cov` must be ({m}, {m}), got {R_full.shape}')
+        self.R_cov = R_full[perm, :][:, perm]
         self.reach_indices = np.ascontiguousarray(self.reach_indices, dtype=np.int64)
+        # The reference adds Q_cov with numpy broadcasting (da.py:115-116), so a scalar or a row vector works
+        # there; the device chain reads dense n x n / m x m matrices through raw pointers, so the shapes are
+        # settled here, before anything crosses the C ABI.
+        try:
+            Q_full = np.ascontiguousarray(np.broadcast_to(np.asarray(Q_cov, dtype=np.float64), (n, n)))
+        except ValueError:
+            raise ValueError(f'`Q_cov` must broadcast to ({n}, {n}), got {np.shape(Q_cov)}')
+        P_full = np.ascontiguousarray(P_t_init, dtype=np.float64)
+        if P_full.shape != (n, n):
+            raise ValueError(f'`P_t_init` must be ({n}, {n}), got {P_full.shape}')
         # device-resident matrices
         self._torch = torch
         dev = 'cuda'
-        self._P = torch.as_tensor(np.ascontiguousarray(P_t_init, dtype=np.float64), device=dev).clone()
-        self._Q = torch.as_tensor(np.ascontiguousarray(Q_cov, dtype=np.float64), device=dev)
-        self._R = torch.as_tensor(self.R_cov, device=dev)
+        self._P = torch.as_tensor(P_full, device=dev).clone()
+        self._Q = torch.as_tensor(Q_full, device=dev)
+        self._R = torch.as_tensor(np.ascontiguousarray(self.R_cov), device=dev)
         self._idx = torch.as_tensor(self.reach_indices, device=dev)
         self._P_prev = self._P
         self._K_d = self._dz_d = self._gain_d = None
@@ -85,7 +123,10 @@ class KalmanFilter(BaseCallback):
 
     @P_t_next.setter
     def P_t_next(self, value):
-        self._P = self._torch.as_tensor(np.ascontiguousarray(value, dtype=np.float64), device='cuda').clone()
+        value = np.ascontiguousarray(value, dtype=np.float64)
+        if value.shape != (self.model.n, self.model.n):
+            raise ValueError(f'`P_t_next` must be ({self.model.n}, {self.model.n}), got {value.shape}')
+        self._P = self._torch.as_tensor(value, device='cuda').clone()
 
     @property
     def P_t_prev(self):
@@ -266,7 +307,7 @@ class KalmanSmoother(KalmanFilter):
         self.P_s = P_s
 
 
-class EnsembleKalmanFilter(BaseCallback):
+class EnsembleKalmanFilter(_MeasurementTable, BaseCallback):
     """Ensemble Kalman update of a member-batched `Muskingum(members=M)`.
 
     measurements : DataFrame [times x gauges], columns are reach ids (as for KalmanFilter)
@@ -288,8 +329,8 @@ class EnsembleKalmanFilter(BaseCallback):
         self.reach_indices, perm = _gauge_setup(model, measurements)
         self.measurements = measurements.iloc[:, perm]
         self.num_measurements = m = self.measurements.shape[1]
-        self._meas_times = self.measurements.index.astype(int).astype(float).values
-        self._meas_values = np.ascontiguousarray(self.measurements.values, dtype=np.float64)
+        if np.shape(R_cov) != (m, m):
+            raise ValueError(f'`R_cov` must be ({m}, {m}), got {np.shape(R_cov)}')
         self.reach_indices = np.ascontiguousarray(self.reach_indices, dtype=np.int64)
         self.every = every
         self.group = group

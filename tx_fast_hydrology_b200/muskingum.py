@@ -73,6 +73,7 @@ class Muskingum:
         self._coef_seen = None
         self._dev = None                 # device tensors, created on first use
         self._dev_valid = False
+        self._host_ref = {}
         shape = (n,) if self.members == 1 else (n, self.members)
         o0 = np.asarray(self._o_t_initial, dtype=np.float64)
         if o0.shape != shape:
@@ -142,6 +143,9 @@ class Muskingum:
                 'o_t_prev': net.unpack_host(d['Op'], M).reshape(shape),
                 'i_t_prev': net.unpack_host(d['Ip'], M).reshape(shape),
             }
+            # what the device holds: an array handed out and still equal to this at the next launch is not
+            # uploaded again (callbacks that only READ the state cost no PCIe traffic)
+            self._host_ref = {k: v.copy() for k, v in self._host.items()}
         # a caller holding these arrays may write into them (da.py:125-126 does)
         self._host_dirty = True
         return self._host
@@ -159,6 +163,7 @@ class Muskingum:
     def _state_set(self, key, value):
         h = self._materialise()
         h[key] = value
+        self._host_ref.pop(key, None)
         self._host_dirty = True
 
     o_t_next = property(lambda self: self._state_get('o_t_next'),
@@ -273,14 +278,23 @@ class Muskingum:
             self._dev_valid = False
         if self._host and (self._host_dirty or not self._dev_valid):
             h, d = self._host, self._dev
+            ref = self._host_ref if self._dev_valid else {}
             for hk, dk in (('o_t_next', 'O'), ('i_t_next', 'I'), ('o_t_prev', 'Op'), ('i_t_prev', 'Ip')):
-                net.pack_host(np.asarray(h[hk], dtype=np.float64).reshape(self.n, M), M, d[dk])
+                v = np.asarray(h[hk], dtype=np.float64)
+                if v.size != self.n * M:
+                    raise ValueError(f'`{hk}` must hold {self.n} x {M} values, got shape {np.shape(h[hk])}')
+                if hk in ref and ref[hk].shape == v.shape and np.array_equal(ref[hk], v):
+                    continue                                   # untouched since it was downloaded
+                net.pack_host(v.reshape(self.n, M), M, d[dk])
+                ref[hk] = v.copy()
+            self._host_ref = ref
         self._dev_valid = True
         self._host_dirty = False
         return torch
 
     def _device_advanced(self):
         self._host = {}
+        self._host_ref = {}
         self._host_dirty = False
 
     def init_states(self, o_t_next=None, i_t_next=None):
@@ -300,6 +314,7 @@ class Muskingum:
         for k in ('o_t_prev', 'i_t_prev'):
             if k not in h or np.shape(h[k]) != full:
                 h[k] = np.zeros(full)
+        self._host_ref = {}
         self._host_dirty = True
 
     # ------------------------------------------------------------------ stepping
@@ -320,7 +335,10 @@ class Muskingum:
         d, net, M = self._dev, self.network, self.members
         d['Op'].copy_(d['O'])
         d['Ip'].copy_(d['I'])
-        q = torch.from_numpy(np.ascontiguousarray(p_t_next, dtype=np.float64)).cuda()
+        q_host = np.ascontiguousarray(p_t_next, dtype=np.float64)
+        if q_host.shape != (self.n,):
+            raise ValueError(f'`p_t_next` must be a vector of {self.n} lateral inflows, got shape {q_host.shape}')
+        q = torch.from_numpy(q_host).cuda()
         net.route_step(d['O'], d['I'], M, q)
         self._device_advanced()
         self.datetime += timedelta
@@ -414,6 +432,10 @@ class Muskingum:
         step_ns = int(self.timedelta.value)
         t = int(self.datetime.value)
         nwin = nsteps // every
+        if torch.is_tensor(observations) or isinstance(observations, np.ndarray):
+            want = (enkf.num_measurements, enkf.Mtot)
+            if observations.ndim != 3 or observations.shape[0] < nwin or tuple(observations.shape[1:]) != want:
+                raise ValueError(f'`observations` must be [>= {nwin}][{want[0]}][{want[1]}], got {tuple(observations.shape)}')
         if (enkf.world == 1 and torch.is_tensor(observations) and observations.is_cuda and observations.is_contiguous()
                 and observations.shape[0] >= nwin and observations.dtype == torch.float64):
             # one call: the loop below, in the library (txh_run_assimilating)
@@ -482,8 +504,8 @@ class Muskingum:
         """muskingum.py:573-580: snapshot (copies) + callback fan-out."""
         self.logger.info(f'Saving state for model {self.name} at time {self.datetime}...')
         self.saved_states['datetime'] = self.datetime
-        self.saved_states['i_t_next'] = self.i_t_next.copy()
-        self.saved_states['o_t_next'] = self.o_t_next.copy()
+        self.saved_states['i_t_next'] = self._peek_state('i_t_next')
+        self.saved_states['o_t_next'] = self._peek_state('o_t_next')
         for _, callback in self.callbacks.items():
             callback.__on_save_state__()
 
@@ -504,13 +526,23 @@ class Muskingum:
         return self.callbacks.pop(key)
 
     def copy(self):
-        """Independent model with the same parameters, state and clock (callbacks are not copied)."""
+        """Independent model with the same parameters, state (current and previous step), saved state and
+        clock -- what `copy.deepcopy` gives on the reference object, minus the callbacks, sinks and sources,
+        which hold references to other objects and are left unbound."""
         d = {k: _copy.deepcopy(v) for k, v in self.info.items()}
-        d['o_t'] = np.array(self.o_t_next)
+        d['o_t'] = np.array(self._peek_state('o_t_next'))
         new = type(self)(d, members=self.members, sched_params=self._sched_params)
-        new.init_states(o_t_next=self.o_t_next, i_t_next=self.i_t_next)
+        new.init_states(o_t_next=self._peek_state('o_t_next'), i_t_next=self._peek_state('i_t_next'))
+        new.o_t_prev = self._peek_state('o_t_prev')
+        new.i_t_prev = self._peek_state('i_t_prev')
         new.alpha[:], new.beta[:], new.chi[:], new.gamma[:] = self.alpha, self.beta, self.chi, self.gamma
+        new.saved_states = {k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in self.saved_states.items()}
         return new
+
+    @classmethod
+    def from_nhd_geojson(cls, file_path, **kwargs):
+        """muskingum.py:877-917 as the reference exposes it (a classmethod around the loader)."""
+        return cls(load_nhd_geojson(file_path), **kwargs)
 
 
     def split(self, indices, name=None, create_state_space=False):

@@ -204,6 +204,20 @@ class RiverNetwork:
         d.update(tasks=tasks, hdr=hdr, inw=inw[:d["n_words"]], prod=prod[:d["n_prod"]])
         return d
 
+    def lane_schedule(self, M=1, cap_rows=0):
+        """The reach-parallel schedule route_lane_kernel runs for ensembles of M <= 16 members (host only)."""
+        info = np.zeros(8, dtype=np.int64)
+        L.check(self._lib.txh_get_lane_info(self.handle, int(M), int(cap_rows), L.ptr_i64(info)))
+        keys = ["n_regions", "n_rows", "n_child", "n_slots", "max_real", "max_virt", "max_extra", "member_tile"]
+        d = dict(zip(keys, (int(x) for x in info)))
+        regions = np.empty((d["n_regions"], 8), dtype=np.int32)
+        rows = np.empty((max(1, d["n_rows"]), 4), dtype=np.int32)
+        child = np.empty(max(1, d["n_child"]), dtype=np.int32)
+        L.check(self._lib.txh_get_lane_schedule(self.handle, int(M), regions.ctypes.data_as(L.p_i32),
+                                                rows.ctypes.data_as(L.p_i32), child.ctypes.data_as(L.p_i32)))
+        d.update(regions=regions, rows=rows[:d["n_rows"]], child=child[:d["n_child"]])
+        return d
+
     # ---- coefficients ---------------------------------------------------------------------
     def compute_coeffs(self, K, X, dt):
         K = L.as_f64(K); X = L.as_f64(X)
@@ -227,7 +241,11 @@ class RiverNetwork:
 
     def pack_host(self, src, M, dst, member_major=False):
         """Host array (numpy, or a pinned CPU torch tensor) in reach order -> device schedule order."""
-        ptr, _, keep = Forcing._host_ptr(src)
+        ptr, shape, keep = Forcing._host_ptr(src)
+        if int(np.prod(shape)) != self.n * int(M):
+            raise ValueError(f"pack_host: source must hold {self.n} x {M} doubles, got shape {tuple(shape)}")
+        if tuple(dst.shape) != (self.n, self.row_stride(M)) or not dst.is_contiguous():
+            raise ValueError("pack_host: destination must be a contiguous alloc_state(M) tensor")
         L.check(self._lib.txh_pack_host(self.handle, ctypes.cast(ptr, L.p_f64), int(M), int(member_major),
                                         _cuda_ptr(dst), _stream_ptr()))
         del keep
@@ -238,7 +256,19 @@ class RiverNetwork:
             out = np.empty((M, self.n) if member_major else (self.n, M), dtype=np.float64)
             optr = L.ptr_f64(out)
         else:
-            optr = ctypes.cast(ctypes.c_void_p(out.data_ptr()), L.p_f64)
+            # a caller buffer crosses the C ABI as a raw pointer: settle size, type and layout here
+            if hasattr(out, "data_ptr"):
+                ok = (out.numel() == self.n * int(M) and out.element_size() == 8 and out.dtype.is_floating_point
+                      and out.is_contiguous() and not out.is_cuda)
+                optr = ctypes.cast(ctypes.c_void_p(out.data_ptr()), L.p_f64)
+            else:
+                ok = (isinstance(out, np.ndarray) and out.size == self.n * int(M) and out.dtype == np.float64
+                      and out.flags.c_contiguous)
+                optr = L.ptr_f64(out) if ok else None
+            if not ok:
+                raise ValueError(f"unpack_host: `out` must be a contiguous float64 host buffer of {self.n} x {M} values")
+        if tuple(src.shape) != (self.n, self.row_stride(M)) or not src.is_contiguous():
+            raise ValueError("unpack_host: source must be a contiguous alloc_state(M) tensor")
         L.check(self._lib.txh_unpack_host(self.handle, _cuda_ptr(src), int(M), int(member_major), optr,
                                           _stream_ptr()))
         return out

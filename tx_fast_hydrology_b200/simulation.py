@@ -84,14 +84,14 @@ class AsyncSimulation(Simulation):
         """Whole run of one sub-model; rows = start time + every step, columns = reach ids."""
         logger.debug(f'Started job for sub-watershed {model.name}')
         start, dt = model.datetime, model.timedelta
-        first = np.array(model.o_t_next, dtype=np.float64)
+        first = model._peek_state('o_t_next')
         end_time = inputs.index.max()
         nsteps = 0 if not end_time > start else int(-((start - end_time) // dt))      # steps while datetime < end
         whole = dt.value == int(round(model.dt * 1e9))
         if model.callbacks or nsteps == 0 or not whole:
             rows, times = [first], [start]
             for state in model.simulate_iter(inputs):
-                rows.append(np.array(state.o_t_next, dtype=np.float64)); times.append(state.datetime)
+                rows.append(state._peek_state('o_t_next')); times.append(state.datetime)
             values = np.stack(rows)
         else:
             assert isinstance(inputs.index, pd.DatetimeIndex) and str(inputs.index.tz) == 'UTC'
