@@ -16,11 +16,18 @@ One bench "step" is one whole 7-day run.  The metric is reach*timestep*member up
           ensemble copied device->host inside the timed region
   roofline : route_window_kernel (the window-resident routing kernel, one launch per hourly window),
           algorithmic bytes per launch / its mean CUDA-event duration / measured HBM copy bandwidth
-  cpu_baseline : the CPU oracle (C/OpenMP restatement of the reference kernels, members over host
-          threads + numpy EnKF) on a bounded sample of the same workload, rank 0 at N=1 only
+  cpu_baseline : the reference's own numba kernels (oracle/_ref: `_ax_bu` + `interpolate_sample`, nutils.py,
+          members fanned out over one process per host core) + the numpy ensemble update, on a bounded
+          sample of the same workload; `port_value` = the C/OpenMP restatement (oracle/txh_oracle.c) beside
+          it; rank 0 at N=1 only.  Without oracle/_ref the port alone is timed (kind "port").
+  parity_max_rel_err : element-wise relative error (floor 1e-12 of the largest element) of the GPU ensemble
+          against that CPU sample after its windows (routing + EnKF updates), same inputs
+  members / c4_basins (N > 1): the member-sharded form of the same C3 run (one 64-member ensemble over the
+          ranks, EnKF statistics combined over NVLink) and BASELINE.json configs[3] (2.7M reaches partitioned
+          by independent basins over the ranks, no collective), each timed like `value`
 
---impl reference times the oracle port alone (the reference is numba/Python and cannot travel to
-the GPU box; its kernels are restated in oracle/txh_oracle.c and pinned against it by the goldens).
+--impl reference times the CPU arm alone: the reference's kernels from oracle/_ref when present, else the
+port, on all the host cores of the box, on the same workload configuration the GPU arm reports at --gpus N.
 """
 import argparse
 import json
@@ -59,6 +66,8 @@ def parse_args():
                     help="N > 1: one independent basin (network + ensemble + gauges) per GPU, no collective; or the "
                          "members of ONE network's ensemble over the GPUs, EnKF statistics combined with NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C4 (basin-partitioned) and member-sharded arms")
+    ap.add_argument("--c4-reaches", type=int, default=2_700_000)
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -231,12 +240,130 @@ class CpuSample:
                 f"oracle/txh_oracle.c over {self.threads} OpenMP threads + numpy")
 
 
+# state shared with the forked workers of RefSample (set before the pool is created)
+_REF = {}
+
+
+def _ref_worker(job):
+    """One worker = a slice of the members: `every` steps of the reference's simulate loop (muskingum.py:527-533:
+    interpolate the forcing at t + dt, then `_ax_bu`, nutils.py:64-89) on the shared state arrays."""
+    lo, hi, t_ns = job
+    R = _REF
+    nu, xp, table, mul = R["nutils"], R["xp"], R["table"], R["mul"]
+    o, i = R["o"], R["i"]
+    for m in range(lo, hi):
+        t = t_ns
+        om, im = o[m].copy(), i[m].copy()
+        for _ in range(R["every"]):
+            t += R["step_ns"]
+            # member m sees table[r] * mul[r][m]; the bracket weights come from the reference's own
+            # interpolate_sample (nutils.py:5-39) applied to a table whose row r is the unit vector e_(r mod 2)
+            ix = int(np.searchsorted(xp, t))
+            if ix == 0:
+                q = table[0] * mul[0, m]
+            elif ix >= xp.size:
+                q = table[-1] * mul[-1, m]
+            else:
+                w = nu.interpolate_sample(t, xp, R["unit"])
+                q = (w[(ix - 1) % 2] * mul[ix - 1, m]) * table[ix - 1] + (w[ix % 2] * mul[ix, m]) * table[ix]
+            im, om = nu._ax_bu(R["heads"], R["end"], R["alpha"], R["beta"], R["chi"], R["gamma"], im, om, q, R["indegree"])
+        o[m] = om; i[m] = im
+    return hi - lo
+
+
+class RefSample:
+    """The same bounded sample on the UNMODIFIED reference kernels (oracle/_ref, numba): one process per host core,
+    each routing a slice of the members with `_ax_bu`; the ensemble update (which the reference does not have) is
+    the oracle's numpy restatement of da.py:112-126 in the parent."""
+
+    def __init__(self, wl, windows, nutils):
+        import multiprocessing as mp
+        from oracle import oracle as O
+        self.O, self.wl, self.windows = O, wl, windows
+        net = wl.net
+        ind = O.compute_indegree(net["startnodes"], net["endnodes"])
+        al, be, ch, ga = O.compute_coeffs(wl.params["K"], wl.params["X"], DT_S)
+        self.net = {"startnodes": net["startnodes"], "endnodes": net["endnodes"], "indegree": ind,
+                    "alpha": al, "beta": be, "chi": ch, "gamma": ga}
+        M, n = wl.M, wl.n
+        self.cores = min(O.max_threads(), M)
+        shm_o = np.frombuffer(mp.RawArray("d", M * n), dtype=np.float64).reshape(M, n)
+        shm_i = np.frombuffer(mp.RawArray("d", M * n), dtype=np.float64).reshape(M, n)
+        self.o, self.i = shm_o, shm_i
+        self.o_init = np.ascontiguousarray(wl.o0.T)
+        self.i_init = np.stack([O.init_states(net["startnodes"], net["endnodes"], o) for o in self.o_init])
+        R = wl.times.size
+        unit = np.zeros((R, 2)); unit[0::2, 0] = 1.0; unit[1::2, 1] = 1.0     # row r -> e_(r mod 2): weights of a bracket
+        _REF.update(nutils=nutils, xp=wl.times.astype(np.float64), table=wl.table, mul=wl.mul, o=shm_o, i=shm_i,
+                    every=wl.every, step_ns=DT_S * 1e9, heads=net["startnodes"][ind == 0], end=net["endnodes"],
+                    alpha=al, beta=be, chi=ch, gamma=ga, indegree=ind, unit=unit)
+        # JIT in the parent, so the forked workers inherit the compiled kernels
+        nutils._ax_bu(_REF["heads"], _REF["end"], al, be, ch, ga, self.i_init[0], self.o_init[0], wl.table[0], ind)
+        nutils.interpolate_sample(float(wl.times[0]) + 1.0, _REF["xp"], unit)
+        self.pool = mp.get_context("fork").Pool(self.cores)
+        self.q_diag = np.full(n, wl.Q)
+        if wl.Zp is None:
+            rng = np.random.default_rng(5)
+            self.Zp = wl.params["o_t"][wl.gauges][None, :, None] + 0.1 * rng.standard_normal((windows, wl.m, M))
+        else:
+            self.Zp = wl.Zp[:windows, :, :M]
+        self.updates = float(n) * M * wl.every * windows
+        bounds = np.linspace(0, M, self.cores + 1).astype(int)
+        self.slices = [(int(bounds[k]), int(bounds[k + 1])) for k in range(self.cores) if bounds[k + 1] > bounds[k]]
+
+    def run(self):
+        O, wl = self.O, self.wl
+        self.o[:] = self.o_init; self.i[:] = self.i_init
+        t = float(wl.t0_ns)
+        t0 = time.perf_counter()
+        for k in range(self.windows):
+            self.pool.map(_ref_worker, [(lo, hi, t) for lo, hi in self.slices])
+            t += wl.every * DT_S * 1e9
+            Op, Ip, _ = O.enkf_update(self.net, self.o.T, self.i.T, wl.gauges, self.Zp[k], self.q_diag, wl.R)
+            self.o[:] = Op.T; self.i[:] = Ip.T
+        return time.perf_counter() - t0, np.array(self.o)
+
+    def close(self):
+        self.pool.close(); self.pool.join()
+
+    def describe(self):
+        wl = self.wl
+        return (f"{self.windows} hourly windows of the workload: {wl.every * self.windows} routing steps x {wl.M} members x "
+                f"{wl.n} reaches on the reference's numba _ax_bu + interpolate_sample (oracle/_ref/tx_fast_hydrology/"
+                f"nutils.py), members over {self.cores} processes, + {self.windows} EnKF updates of {wl.m} gauges (numpy "
+                f"restatement of da.py:112-126; the reference has no ensemble filter)")
+
+
+def cpu_samples(wl, windows):
+    """(reference sample or None, port sample)"""
+    from oracle import oracle as O
+    nu = O.reference_nutils()
+    ref = None
+    if nu is not None:
+        try:
+            ref = RefSample(wl, windows, nu)
+        except Exception as e:                       # numba missing or fork refused: the port still runs
+            print(f"bench.py: reference kernels unavailable ({e}); timing the port", file=sys.stderr)
+    return ref, CpuSample(wl, windows)
+
+
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
-    wl = Workload(a)
-    cs = CpuSample(wl, a.cpu_windows)
+    # the same workload description the GPU arm prints at --gpus N: with basin sharding every GPU owns one basin of
+    # this size; the CPU routes them one after another, so its throughput is that of one basin (rank 0's)
+    a_cfg = argparse.Namespace(**vars(a))
+    wl = Workload(a, 0, 1)
+    try:
+        from threadpoolctl import threadpool_limits
+        from oracle import oracle as O
+        threadpool_limits(limits=O.max_threads())    # numpy's BLAS too (torchrun exports OMP_NUM_THREADS=1)
+    except Exception:
+        pass
+    ref, port = cpu_samples(wl, a.cpu_windows)
+    cs = ref if ref is not None else port
     for _ in range(max(1, a.warmup)):
         cs.run()
     tot = 0.0
@@ -244,12 +371,22 @@ def reference_arm(a):
         dt, _ = cs.run()
         tot += dt
     val = cs.updates * a.steps / tot
+    cores = cs.cores if ref is not None else cs.threads
+    cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "reference" if ref is not None else "port",
+           "sample": cs.describe()}
+    if ref is not None:
+        port.run()
+        cpu["port_value"] = port.updates / min(port.run()[0] for _ in range(2))
+        cpu["port_cores"] = port.threads
+        ref.close()
+    n_gpus = max(a.gpus, world)
+    cfg_wl = wl
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(wl, a, 1),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cs.threads, "kind": "port", "sample": cs.describe()},
+        "config": workload_config(cfg_wl, a_cfg, n_gpus, by_basin=(n_gpus > 1 and a.sharding == "basins")),
+        "cpu_baseline": cpu,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -257,17 +394,21 @@ def reference_arm(a):
     return 0
 
 
-def workload_config(wl, a, world):
+def workload_config(wl, a, world, by_basin=None):
+    by_basin = wl.by_basin if by_basin is None else by_basin
     return {
-        "workload": "C3: synthetic Texas-scale network, 64-member ensemble per GPU, 7-day run at a 5-min step, "
-                    "hourly EnKF of 500 gauges (BASELINE.json configs[2])",
-        "reaches": wl.n * (world if wl.by_basin else 1), "reaches_per_gpu": wl.n, "levels": 1000,
+        "workload": (f"C3: synthetic Texas-scale network, ONE {wl.Mtot}-member ensemble with its members sharded over "
+                     f"{world} GPUs ({wl.M} per GPU), 7-day run at a 5-min step, hourly EnKF of 500 gauges "
+                     "(BASELINE.json configs[2])" if (world > 1 and not by_basin) else
+                     "C3: synthetic Texas-scale network, 64-member ensemble per GPU, 7-day run at a 5-min step, "
+                     "hourly EnKF of 500 gauges (BASELINE.json configs[2])"),
+        "reaches": wl.n * (world if by_basin else 1), "reaches_per_gpu": wl.n, "levels": 1000,
         "members_per_gpu": wl.M, "members_per_ensemble": wl.Mtot,
         "routing_steps": wl.nsteps, "dt_s": DT_S, "gauges": wl.m, "enkf_updates": wl.nwin,
         "assimilate_every_steps": wl.every, "seed": a.seed,
         "sharding": ("single GPU" if world == 1 else
                      "independent basins, one per GPU, each with its own ensemble, gauges and EnKF; no collective"
-                     if wl.by_basin else
+                     if by_basin else
                      "ensemble members of one network over ranks (network replicated); EnKF statistics combined with NCCL"),
         "l2": "256 MiB buffer written between bench steps (inside the timed region); per-run inputs "
               "(forcing 135 MB + observations + 102 MB state) exceed the 126 MB L2",
@@ -289,8 +430,114 @@ def gpu_arm(a):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from tx_fast_hydrology_b200 import build, _lib
+    from tx_fast_hydrology_b200 import build
     build.build_lib()
+    # the headline line: C3 on one GPU, or one independent C3 basin per GPU (weak scaling, no collective)
+    line = c3_arm(a, rank, world, local, full=True)
+    if world > 1 and not a.no_extras and a.sharding == "basins":
+        # BASELINE.json configs[2] as written: ONE 64-member ensemble with its members sharded over the ranks
+        # (strong scaling: 64 / N members per GPU), EnKF statistics combined over NVLink
+        if a.members % world == 0:
+            am = argparse.Namespace(**vars(a))
+            am.sharding, am.members = "members", a.members // world
+            sub = c3_arm(am, rank, world, local, full=False)
+            if rank == 0:
+                line["members"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "scaling", "config", "gpu_launches",
+                                                       "roofline", "update_path")}
+    if not a.no_extras:
+        c4 = c4_arm(a, rank, world, local)
+        if rank == 0:
+            line["c4_basins"] = c4
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def c4_arm(a, rank, world, local):
+    """BASELINE.json configs[3]: the CONUS-scale forest (2.7M reaches, 64 independent basins, seed 3), deterministic,
+    24 hours at a 5-min step (288 steps), whole basins bin-packed over the ranks (sharding.shard_basins) and routed
+    with no collective: strong scaling of a fixed forest.  Device-resident timing like `value`."""
+    import torch
+    import torch.distributed as dist
+    import pandas as pd
+    from tx_fast_hydrology_b200 import synthetic as S
+    from tx_fast_hydrology_b200.muskingum import Muskingum
+    from tx_fast_hydrology_b200.sharding import shard_basins, extract_shard
+    dev = torch.device("cuda", local)
+    n_total, nsteps, seed = a.c4_reaches, 288, 3
+    net = S.make_network(n_total, seed, n_basins=64)
+    parts = shard_basins(net["basin"], world)
+    sub_end, idx = extract_shard(net["endnodes"], net["basin"], parts[rank])
+    prm = S.make_params(n_total, seed)
+    t0_ns = int(pd.Timestamp(T0).value)
+    times, table = S.make_forcing(n_total, nsteps, DT_S, seed, t0_ns=t0_ns, rows_every=12)
+    n = idx.size
+    sub_net = {"startnodes": np.arange(n, dtype=np.int64), "endnodes": sub_end}
+    sub_prm = {k: np.ascontiguousarray(v[idx]) for k, v in prm.items()}
+    t_topo = time.perf_counter()
+    mdl = Muskingum(S.model_dict(sub_net, sub_prm, dt_s=DT_S, t0=T0), members=1)
+    t_topo = time.perf_counter() - t_topo
+    f = mdl.make_forcing(times_ns=times, table=np.ascontiguousarray(table[:, idx]))
+    del table
+    O, I = mdl.device_state
+    O0, I0 = O.clone(), I.clone()
+    t_start = pd.Timestamp(T0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def run():
+        flush.fill_(1)
+        O.copy_(O0); I.copy_(I0)
+        mdl._datetime = t_start
+        mdl.run(f, nsteps)
+
+    for _ in range(max(3, a.warmup)):
+        run()
+    mdl.network.check()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(a.steps):
+        run()
+    ev1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    mdl.network.check()
+    ms = ev0.elapsed_time(ev1) / a.steps
+    counts = [n]
+    if world > 1:
+        t = torch.tensor([ms, float(n)], dtype=torch.float64, device=dev)
+        allv = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        ms = max(float(x[0]) for x in allv)
+        counts = [int(x[1]) for x in allv]
+    o_fin = mdl.download_state()[0]
+    ok = bool(np.isfinite(o_fin).all())
+    f.close()
+    del mdl, O0, I0, flush
+    torch.cuda.empty_cache()
+    upd = float(n_total) * nsteps
+    ab = algorithmic_bytes_per_update(1)
+    return {"workload": "C4: CONUS-scale synthetic forest, 64 independent basins, deterministic, 24-hour run at a 5-min "
+                        "step (BASELINE.json configs[3]); whole basins bin-packed over the ranks, no collective",
+            "value": upd / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "scaling": "strong", "reaches": n_total,
+            "routing_steps": nsteps, "members": 1, "reaches_per_rank": counts,
+            "load_imbalance": max(counts) / (sum(counts) / len(counts)), "topology_pass_s_rank0": round(t_topo, 3),
+            "algorithmic_GBps": upd * ab / (ms * 1e-3) / 1e9, "finite": ok,
+            "l2": "256 MiB buffer written between bench steps (inside the timed region)"}
+
+
+def c3_arm(a, rank, world, local, full):
+    """One C3 measurement (see the module docstring).  `full`: also the end-to-end arm, the CPU baseline and the
+    in-run parity number (rank 0, single GPU).  Returns the JSON line as a dict (meaningful on rank 0)."""
+    import torch
+    import torch.distributed as dist
+    from tx_fast_hydrology_b200 import _lib
     lib = _lib.load()
     import pandas as pd
     from tx_fast_hydrology_b200.muskingum import Muskingum
@@ -343,7 +590,8 @@ def gpu_arm(a):
 
     def resident_run(timers=None):
         flush.fill_(1)                                   # L2 flush between bench steps
-        O.copy_(O0); I.copy_(I0)
+        Oc, Ic = mdl.device_state                        # (a member-sharded filter alternates two state buffers)
+        Oc.copy_(O0); Ic.copy_(I0)
         mdl._datetime = t_start
         mdl.run_assimilating(forcing, nsteps, enkf, every, Zp_dev, timers=timers)
 
@@ -440,15 +688,23 @@ def gpu_arm(a):
             traffic = json.load(ft).get("route_window_kernel_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "route_window_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kernel = "route_lane_kernel" if M <= 8 else "route_window_kernel"
+    if kernel != "route_window_kernel":
+        traffic = None
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": k_ms,
                 "launches_timed": len(k_list), "bytes_per_update": ab,
                 "routing_share_of_step": k_ms * nwin / ms_step if ms_step > 0 else None}
+    if traffic:
+        # The state stays in shared memory for the 12 steps of a window, so the kernel moves ~10x fewer bytes than
+        # the algorithmic figure: what it physically does to HBM, and the floor that traffic sets for a launch
+        roofline["physical"] = {"dram_bytes_per_launch": traffic, "achieved": traffic / (k_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                "frac": traffic / (k_ms * 1e-3) / 1e9 / peak, "floor_ms_per_launch": traffic / (peak * 1e9) * 1e3}
 
     # ---- end to end through the public API, host buffers in and out --------------------------------
     e2e = None
-    if not a.no_e2e:
+    if full and not a.no_e2e:
         e2e_run()                                         # warm-up (allocations)
         e2e_parts.clear()
         barrier()
@@ -463,32 +719,56 @@ def gpu_arm(a):
                "breakdown_ms": {k: round(1e3 * v / reps, 3) for k, v in e2e_parts.items()}}
 
     # ---- CPU baseline (rank 0, single GPU only) -------------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cs = CpuSample(wl, a.cpu_windows)
-        cs.run()                                          # warm-up (page faults, OpenMP pool)
-        best = min(cs.run()[0] for _ in range(2))
-        cpu = {"value": cs.updates / best, "unit": UNIT, "cores": cs.threads, "kind": "port",
-               "sample": cs.describe()}
+    cpu, parity = None, None
+    if full and rank == 0 and world == 1 and not a.no_cpu_baseline:
+        ref, port = cpu_samples(wl, a.cpu_windows)
+        port.run()                                        # warm-up (page faults, OpenMP pool)
+        runs = [port.run() for _ in range(2)]
+        best = min(r[0] for r in runs)
+        o_cpu = runs[-1][1]                               # [M][n] after the sample's windows
+        cpu = {"value": port.updates / best, "unit": UNIT, "cores": port.threads, "kind": "port",
+               "sample": port.describe()}
+        if ref is not None:
+            ref.run()
+            rruns = [ref.run() for _ in range(2)]
+            cpu = {"value": ref.updates / min(r[0] for r in rruns), "unit": UNIT, "cores": ref.cores, "kind": "reference",
+                   "sample": ref.describe(), "port_value": port.updates / best, "port_cores": port.threads}
+            o_cpu = rruns[-1][1]
+            ref.close()
         # the same on ONE core, one window (SURVEY.md section 8d asks for both)
         c1 = CpuSample(wl, 1)
         c1.threads = 1
-        cpu["value_1core"] = c1.updates / c1.run()[0]
+        cpu["port_value_1core"] = c1.updates / c1.run()[0]
+        # ---- parity of THIS run: the GPU ensemble after the sample's windows against the CPU sample --------
+        Oc, Ic = mdl.device_state
+        Oc.copy_(O0); Ic.copy_(I0)
+        mdl._datetime = t_start
+        mdl.run_assimilating(forcing, a.cpu_windows * every, enkf, every, Zp_dev)
+        mdl.network.check()
+        o_gpu = mdl.download_state()[0]
+        ref_o = o_cpu.T
+        scale = float(np.abs(ref_o).max())
+        parity = {"max_rel_err": float((np.abs(o_gpu - ref_o) / np.maximum(np.abs(ref_o), 1e-12 * scale)).max()),
+                  "metric": "element-wise |gpu - cpu| / max(|cpu|, 1e-12 max|cpu|) over the ensemble outflows",
+                  "after": f"{a.cpu_windows} windows ({a.cpu_windows * every} routing steps + {a.cpu_windows} EnKF updates)",
+                  "against": cpu["kind"], "tolerance": 1e-9}
+        parity["ok"] = parity["max_rel_err"] <= 1e-9
 
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(wl, a, world),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clk, "wall_s_timed_region": wall,
-            "roofline_whole_step": {"achieved": value * ab / 1e9, "unit": "GB/s", "frac": value * ab / 1e9 / peak / world},
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    sharded = world > 1 and not wl.by_basin
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(wl, a, world),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "parity_max_rel_err": None if parity is None else parity["max_rel_err"], "parity": parity,
+        "clocks": clk, "wall_s_timed_region": wall,
+        "roofline_whole_step": {"achieved": value * ab / 1e9, "unit": "GB/s", "frac": value * ab / 1e9 / peak / world},
+        "update_path": getattr(enkf, "update_path", None),
+    }
+    forcing.close()
+    del mdl, enkf, O0, I0, flush, Zp_dev
+    torch.cuda.empty_cache()
+    return line
 
 
 def main():

@@ -82,9 +82,11 @@ int txh_get_window_schedule(const txh_net* net, int32_t* wtask_desc, uint32_t* w
 /* lane schedule (route_lane_kernel, ensembles of up to 16 members: lanes are reaches, regions of the network run
  * time-skewed in shared memory).  Host only.  cap_rows > 0 overrides the rows per region for schedules not yet
  * in use.  info = {n_regions, n_row_entries, n_child_entries, n_slots, max_real, max_virt, max_extra, member_tile};
- * regions rows are 8 int32: row_off, n_real, n_virt, child_off, n_child, n_extra, height, pad; rows are 4 int32
- * per entry: reach (-1: virtual row or the sentinel closing a region), skew offset, first child (relative to the
- * region's child_off), slot (real: stream published, virtual: stream mirrored; -1 none); child: region-local rows.
+ * regions rows are 8 int32: row_off, n_real, n_virt, child_off, n_child, n_extra, height, pad; rows are 6 int32
+ * per entry: reach (-1: virtual row), skew offset, the first two children c0 | c1 << 16 (region-local rows; a
+ * missing child is the region's zero row, n_real + n_virt), number of further children, their first entry in
+ * `child` (relative to the region's child_off), slot (real: stream published, virtual: stream mirrored; -1
+ * none); child: region-local rows.
  * Replaces the implicit ordering of the reference's headwater walk (nutils.py:72-88) for M <= 16. */
 int txh_get_lane_info(txh_net* net, int64_t M, int64_t cap_rows, int64_t info[8]);
 int txh_get_lane_schedule(txh_net* net, int64_t M, int32_t* regions, int32_t* rows, int32_t* child);
@@ -202,6 +204,18 @@ int txh_enkf_apply(txh_net* net, double* O_dev, double* I_dev, int64_t Mloc, con
                    int64_t col0 /* first global member of this shard */, const double* mean_dev, const double* T_dev,
                    const int64_t* obs_reach_host, int64_t m, const double* qs_dev, const double* W_dev,
                    double* G_dev /* scratch, same shape as O_dev */, void* stream);
+
+/* txh_enkf_apply for a member-sharded ensemble whose shards are read IN PLACE: shard_ptrs[b] (host array of `world`
+ * device pointers) is the state matrix [n][row_stride(Mloc)] of shard b -- this GPU's own (== O_in for b = rank) or a
+ * peer GPU's buffer mapped into this process (CUDA IPC / symmetric memory over NVLink).  The transform kernel loads
+ * the peers' rows tile by tile while it multiplies (no all-gather in front of it) and writes the posterior of this
+ * shard to O_out, a different buffer than O_in: peers may still be reading O_in.  The caller orders the launches
+ * across GPUs (every shard's forecast complete before any transform starts, e.g. by the all-reduce of the row sums)
+ * and alternates the two buffers.  nutils.py:157-169 shards the same loop over columns with prange. */
+int txh_enkf_apply_peers(txh_net* net, const double* O_in_dev, double* O_out_dev, double* I_dev, int64_t Mloc,
+                         const double* const* shard_ptrs_host, int64_t world, int64_t Mtot, int64_t col0,
+                         const double* mean_dev, const double* T_dev, const int64_t* obs_reach_host, int64_t m,
+                         const double* qs_dev, const double* W_dev, double* G_dev, void* stream);
 
 /* The whole assimilating run of an unsharded ensemble in one call: `every` routing steps per launch (the row
  * sums ride on its last step), then one ensemble update with Zp_dev[k] ([m][M], the k-th update's per-member

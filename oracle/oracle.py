@@ -40,6 +40,33 @@ def build(force=False):
     return so
 
 
+def build_ref():
+    """Copy the unmodified reference package into oracle/_ref/ (only where /root/reference exists: the build
+    container).  Returns the directory, or None when there is no copy."""
+    subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=False, stdout=subprocess.DEVNULL)
+    return ref_dir()
+
+
+def ref_dir():
+    d = os.path.join(_HERE, "_ref")
+    return d if os.path.exists(os.path.join(d, "tx_fast_hydrology", "nutils.py")) else None
+
+
+def reference_nutils():
+    """The reference's own `tx_fast_hydrology.nutils` (numba kernels) from oracle/_ref, or None."""
+    import importlib
+    import sys
+    d = ref_dir()
+    if d is None:
+        return None
+    try:
+        if d not in sys.path:
+            sys.path.insert(0, d)
+        return importlib.import_module("tx_fast_hydrology.nutils")
+    except Exception:
+        return None
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -61,7 +88,12 @@ def _f(a):
 
 
 def max_threads():
-    return int(lib().txo_max_threads())
+    """Host threads this process may use: its CPU affinity (launchers such as torchrun export OMP_NUM_THREADS=1,
+    which would otherwise pin the oracle to one core; every parallel region here names its thread count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, int(lib().txo_max_threads()))
 
 
 # --------------------------------------------------------------------------

@@ -60,7 +60,8 @@ def run(name, net_d, M, nsteps, seed, parity_steps, parity_members, chunk=None):
     tc = time.time() - tc
     eo = float(np.abs(og - o_ref.T).max() / np.abs(o_ref).max()); ei = float(np.abs(ig - i_ref.T).max() / np.abs(i_ref).max())
     upd = float(n) * M * nsteps
-    out = {"config": name, "reaches": n, "levels": nlev, "members": M, "steps": nsteps, "topology_pass_s": round(tb, 3),
+    extra = {k: os.environ[k] for k in ("TXH_ROUTE_KERNEL", "TXH_LANE_CAP", "TXH_LANE_SIDE_MIN", "TXH_LANE_MAX_M") if k in os.environ}
+    out = {"config": name, "env": extra, "reaches": n, "levels": nlev, "members": M, "steps": nsteps, "topology_pass_s": round(tb, 3),
            "gpu_ms": round(ms, 3), "updates_per_s": upd / (ms * 1e-3),
            "algorithmic_GBps": upd * (32 + 44.0 / M) / (ms * 1e-3) / 1e9,
            "parity": {"steps": parity_steps, "members": parity_members, "max_rel_err_o": eo, "max_rel_err_i": ei,
@@ -80,6 +81,9 @@ def main():
     if "c4" in which:
         run("C4: CONUS-scale forest of 64 independent basins (2.7M reaches) on ONE GPU, 24-hour run",
             S.make_network(2_700_000, 3, n_basins=64), 1, 288, 3, 48, 1)
+    if "c2w" in which:      # hourly windows (12 steps per call) on the Texas-scale network, small ensembles
+        for M in (1, 2, 4, 8, 16):
+            run(f"C2-net, {M} members, 168 windows of 12 steps", S.make_network(100000, 2), M, 2016, 2, 24, min(M, 2), chunk=12)
     if "c5" in which:
         run("C5: long-chain stress (10k-reach main stem + tributaries), 1024 members, 288 steps",
             S.make_longchain_network(), 1024, 288, 5, 12, 32)

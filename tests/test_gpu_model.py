@@ -9,13 +9,16 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9
-# placeholders until the first GPU measurement of this round calibrates them (see tests/perf/kf_error_budget.py)
-GAIN_TOL = 1e-8
-SMOOTH_X_TOL = 1e-8
-SMOOTH_P_TOL = 1e-7
+# Dense filter / smoother quantities are held to the same 1e-9 as the states.  Measured on B200 against the
+# reference goldens (tests/perf/kf_error_budget.py, profiles/r02_kf_error_budget.json): gains 6e-16, P 2.4e-16,
+# K 4.4e-16, smoothed states 8e-16, smoothed covariance 7e-16 (max-norm); cond(P[s][:,s] + R) = 3.7 and
+# cond(P_p) <= 12.3 in these fixtures, so nothing here needs a looser bound.
+GAIN_TOL = RTOL
+SMOOTH_X_TOL = RTOL
+SMOOTH_P_TOL = RTOL
 
 
-from parity import relerr, normerr        # element-wise with a floor / max-norm (dense matrices)
+from parity import relerr, normerr, enkf_tolerance        # element-wise with a floor / max-norm (dense matrices)
 
 
 def frame(times_ns, table, cols):
@@ -280,15 +283,15 @@ def test_dense_linear_algebra():
         ref = 0.5 * (A.T if ta else A) @ (B.T if tb else B) - 2.0 * C0
         C = torch.as_tensor(C0, device="cuda").clone()
         dgemm(torch.as_tensor(A, device="cuda"), torch.as_tensor(B, device="cuda"), C, ta, tb, 0.5, -2.0)
-        assert relerr(C.cpu().numpy(), ref) < 1e-13
+        assert normerr(C.cpu().numpy(), ref) < 1e-13       # matrix results: max-norm (backward-stable, not element-wise)
     for m, k in [(7, 3), (130, 64), (500, 64)]:
         X = rng.standard_normal((m, m)); S = X @ X.T + m * np.eye(m); B = rng.standard_normal((m, k))
         Sd = torch.as_tensor(S, device="cuda").clone(); Bd = torch.as_tensor(B, device="cuda").clone()
         spd_solve(Sd, Bd)
-        assert relerr(Bd.cpu().numpy(), np.linalg.solve(S, B)) < 1e-11
+        assert normerr(Bd.cpu().numpy(), np.linalg.solve(S, B)) < 1e-11
         Ad = torch.as_tensor(S + 0.1 * X, device="cuda").clone()
         inverse(Ad)
-        assert relerr(Ad.cpu().numpy(), np.linalg.inv(S + 0.1 * X)) < 1e-10
+        assert normerr(Ad.cpu().numpy(), np.linalg.inv(S + 0.1 * X)) < 1e-10
 
 
 @pytest.mark.parametrize("n,M,m,seed,diag", [(400, 16, 12, 1, False), (1500, 64, 40, 2, False), (900, 10, 25, 3, False),
@@ -378,13 +381,18 @@ def test_run_assimilating_vs_oracle(oracle, n, M, m, seed, in_library):
     o = np.ascontiguousarray(o0.T)
     i = np.stack([oracle.init_states(net_d["startnodes"], net_d["endnodes"], x) for x in o])
     t = float(t0)
+    tol = RTOL
+    so, si = np.zeros((n, M)), np.zeros((n, M))                   # magnitudes of the forecasts the updates started from
     for k in range(nwin):
         oracle.run_members(onet, o, i, every, times.astype(np.float64), table, t, 300e9, wmul=mul)
         t += every * 300e9
+        tol = max(tol, enkf_tolerance(o.T, gidx, q, R))          # eps * cond(S) of this update (tests/parity.py)
+        so = np.maximum(so, np.abs(o.T)); si = np.maximum(si, np.abs(i.T))
         Op, Ip, _ = oracle.enkf_update(onet, o.T, i.T, gidx, Zp[k], q, R)
         o = np.ascontiguousarray(Op.T); i = np.ascontiguousarray(Ip.T)
-    assert relerr(mdl.o_t_next, o.T) < RTOL
-    assert relerr(mdl.i_t_next, i.T) < RTOL
+    # element-wise, relative to max(|posterior|, |forecast|): o + gain cancels on some reaches (tests/parity.py)
+    assert relerr(mdl.o_t_next, o.T, scale=so) < tol
+    assert relerr(mdl.i_t_next, i.T, scale=si) < tol
 
 
 def test_headline_window_full_size(oracle):
@@ -439,10 +447,13 @@ def test_headline_window_full_size(oracle):
     mdl.network.check()
     Op, Ip, _ = oracle.enkf_update(onet, o.T, i.T, gidx, Zp, np.full(n, 2.0), R)
     o_gpu, i_gpu = mdl.o_t_next.copy(), mdl.i_t_next.copy()
-    assert relerr(o_gpu, Op) < RTOL and relerr(i_gpu, Ip) < RTOL
+    tol = enkf_tolerance(o.T, gidx, 2.0, R)                      # max(1e-9, 64 eps cond(S)), tests/parity.py
+    # element-wise, relative to max(|posterior|, |forecast|): o + gain cancels on some reaches (tests/parity.py)
+    assert relerr(o_gpu, Op, scale=o.T) < tol and relerr(i_gpu, Ip, scale=i.T) < tol
+    assert normerr(o_gpu, Op) < RTOL and normerr(i_gpu, Ip) < RTOL
     # (c) member permutation: update(P x, P z) == P update(x, z)
     perm = rng.permutation(M)
     mdl.upload_state(np.ascontiguousarray(o.T[:, perm]), np.ascontiguousarray(i.T[:, perm]))
     enkf.filter(torch.as_tensor(np.ascontiguousarray(Zp[:, perm]), device="cuda"))
     mdl.network.check()
-    assert relerr(mdl.o_t_next, o_gpu[:, perm]) < 1e-10
+    assert relerr(mdl.o_t_next, o_gpu[:, perm], scale=o.T[:, perm]) < tol and normerr(mdl.o_t_next, o_gpu[:, perm]) < 1e-10

@@ -69,6 +69,8 @@ SIGNATURES = {
                                       c_vp, c_vp, c_vp, c_vp]),
     "txh_enkf_apply": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, p_i64, c_i64,
                                       c_vp, c_vp, c_vp, c_vp]),
+    "txh_enkf_apply_peers": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_vp), c_i64, c_i64, c_i64, c_vp,
+                                            c_vp, p_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "txh_run_assimilating": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_int,
                                             p_i64, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp,
                                             c_vp, c_vp, c_i64, c_vp, c_vp]),

@@ -87,8 +87,11 @@ struct txh_net {
         bool built = false, ok = false, on_dev = false;
         LaneRegionDesc* d_regions = nullptr;
         int4* d_meta = nullptr;
+        int32_t* d_xbeg = nullptr;
         uint16_t* d_child = nullptr;
     };
+    LaneStep* d_lsteps = nullptr; size_t lsteps_cap = 0;
+    LaneStep* d_unit_lstep = nullptr;
     LaneDev lane[5];                    // member tiles 1, 2, 4, 8, 16
     int lane_max_members = 8;           // ensembles up to this size take the lane kernel
     int lane_cap_rows = 0;              // rows per region; 0 = from the size of the network and the SM count
@@ -473,11 +476,11 @@ txh_net::LaneDev* lane_schedule(txh_net* net, int ti, int num_sms)
             L.ok = L.sched.build(net->topo, net->sched.pos_of_reach, 1 << ti, net->lane_cap_rows, kLaneSmemBudget, side_min, err);
         } else {
             const int64_t per_sm = (net->topo.n + num_sms - 1) / std::max(1, num_sms);
-            int cap = (int)std::min<int64_t>(2048, std::max<int64_t>(320, per_sm + per_sm / 50));
+            int cap = (int)std::min<int64_t>(kLaneMaxRows, std::max<int64_t>(320, per_sm + per_sm / 50));
             for (;;) {
                 L.ok = L.sched.build(net->topo, net->sched.pos_of_reach, 1 << ti, cap, kLaneSmemBudget, side_min, err);
-                if (!L.ok || (int)L.sched.regions.size() <= num_sms || cap >= 2048) break;
-                cap = std::min(2048, cap + std::max(8, cap / 12));
+                if (!L.ok || (int)L.sched.regions.size() <= num_sms || cap >= kLaneMaxRows) break;
+                cap = std::min(kLaneMaxRows, cap + std::max(8, cap / 12));
             }
         }
         L.built = true;
@@ -500,13 +503,20 @@ int run_lane(txh_net* net, double* O, double* I, int64_t M, const double* F, con
         std::vector<int4> meta(s.row_reach.size());
         for (size_t i = 0; i < meta.size(); ++i) {
             const int32_t j = s.row_reach[i];
-            meta[i] = make_int4(j >= 0 ? net->sched.pos_of_reach[j] : -1, s.row_off[i], s.row_cbeg[i], s.row_slot[i]);
+            meta[i] = make_int4(j >= 0 ? net->sched.pos_of_reach[j] : -1, s.row_off[i] | (s.row_nx[i] << 16), s.row_c01[i],
+                                s.row_slot[i]);
         }
         int rc;
         if ((rc = upload(&L->d_regions, s.regions))) return rc;
         if ((rc = upload(&L->d_meta, meta))) return rc;
+        if ((rc = upload(&L->d_xbeg, s.row_xbeg))) return rc;
         if ((rc = upload(&L->d_child, s.child))) return rc;
         L->on_dev = true;
+    }
+    if (!net->d_unit_lstep) {
+        const LaneStep unit{1.0, 0.0, 0, 0, 0, 0};
+        CU(cudaMalloc((void**)&net->d_unit_lstep, sizeof(LaneStep)));
+        CU(cudaMemcpy(net->d_unit_lstep, &unit, sizeof(unit), cudaMemcpyHostToDevice));
     }
     const int ld = (int)txh_row_stride(M);
     // streams ring[slot][member][step]: one launch covers as many steps as fit 128 MiB
@@ -522,32 +532,24 @@ int run_lane(txh_net* net, double* O, double* I, int64_t M, const double* F, con
         net->lring_cap = ring_need;
         CU(cudaMemsetAsync(net->d_lring, 0xff, ring_need * sizeof(double), st));   // every cell starts EMPTY
     }
-    const StepInterp* d_steps = net->d_unit_step;
+    const LaneStep* d_steps = net->d_unit_lstep;
     if (plan.times) {
-        if ((size_t)spl > net->steps_cap) {
-            if (net->d_steps) { CU(cudaStreamSynchronize(st)); CU(cudaFree(net->d_steps)); }
-            CU(cudaMalloc((void**)&net->d_steps, sizeof(StepInterp) * spl));
-            net->steps_cap = spl;
+        if ((size_t)spl > net->lsteps_cap) {
+            if (net->d_lsteps) { CU(cudaStreamSynchronize(st)); CU(cudaFree(net->d_lsteps)); }
+            CU(cudaMalloc((void**)&net->d_lsteps, sizeof(LaneStep) * spl));
+            net->lsteps_cap = spl;
         }
-        d_steps = net->d_steps;
+        d_steps = net->d_lsteps;
     } else if (nsteps != 1) {
         return fail(TXH_E_INVALID, "internal: a launch without a forcing table covers one step");
     }
-    // shared-memory layout
+    // shared memory: the largest region (every CTA lays its region out itself, LaneSchedule::region_bytes)
     LaneArgs a{};
-    auto up16 = [](size_t x) { return (x + 15) & ~size_t(15); };
-    const size_t rr = (size_t)std::max(1, s.max_real), rvs = rr + (size_t)s.max_virt;
-    a.rr_stride = (int32_t)rr; a.rv_stride = (int32_t)rvs;
-    size_t off = up16(16 * (rvs + 1));
-    a.off_coef = (int32_t)off; off += 64 * rr;
-    a.off_p = (int32_t)off; off += 8 * (size_t)mt * rr;
-    a.off_obuf = (int32_t)off; off += 16 * (size_t)mt * rvs;
-    a.off_ext = (int32_t)off; off += 256 * (size_t)mt * (size_t)s.max_virt;
-    a.off_child = (int32_t)off; off += up16(2 * (size_t)std::max(1, s.max_child));
-    const size_t smem = off;
+    const size_t smem = s.max_bytes + 16;
     if (smem > 227 * 1024) return 1;
-    const int tv = s.max_virt > 0 ? std::min(256, (s.max_virt + 31) / 32 * 32) : 0;
-    const int tr = std::min(1024 - tv, (s.max_real + 31) / 32 * 32);
+    const int tv = s.max_virt > 0 ? std::min(128, (s.max_virt + 31) / 32 * 32) : 0;
+    const int tr = (s.max_real + 31) / 32 * 32;                            // one row per thread
+    if (tr + tv > 1024) return 1;
     a.TR = tr;
     const int threads = tr + tv;
     const int grid = std::min<int>(net->num_sms, (int)s.regions.size());
@@ -557,9 +559,9 @@ int run_lane(txh_net* net, double* O, double* I, int64_t M, const double* F, con
             InitArgs ia{};
             ia.times = plan.times; ia.steps_out = net->d_steps; ia.t0_ns = plan.t0_ns; ia.dt_ns = plan.dt_ns;
             ia.step_base = s0; ia.R = (int32_t)plan.R; ia.nsteps = (int32_t)ns; ia.method = plan.method;
-            CU(launch_window_init(ia, net->d_qctl + 6, st));
+            CU(launch_lane_init(ia, net->d_lsteps, net->d_qctl + 6, st));
         }
-        a.regions = L->d_regions; a.meta = L->d_meta; a.child = L->d_child;
+        a.regions = L->d_regions; a.meta = L->d_meta; a.xbeg = L->d_xbeg; a.child = L->d_child;
         a.coef = net->d_coef; a.O = O; a.I = I; a.F = F; a.steps = d_steps; a.Wmul = W;
         a.ring = net->d_lring; a.ticket = net->d_qctl + 6; a.done = net->d_qctl + 7;
         a.status = net->d_status; a.watchdog_ns = net->watchdog_ns;
@@ -669,7 +671,9 @@ void txh_destroy(txh_net* net)
         cudaFree(net->d_wtasks); cudaFree(net->d_whdr); cudaFree(net->d_winw); cudaFree(net->d_wprod);
         if (net->d_ring) cudaFree(net->d_ring);
         if (net->d_lring) cudaFree(net->d_lring);
-        for (auto& L : net->lane) { cudaFree(L.d_regions); cudaFree(L.d_meta); cudaFree(L.d_child); }
+        for (auto& L : net->lane) { cudaFree(L.d_regions); cudaFree(L.d_meta); cudaFree(L.d_xbeg); cudaFree(L.d_child); }
+        if (net->d_lsteps) cudaFree(net->d_lsteps);
+        if (net->d_unit_lstep) cudaFree(net->d_unit_lstep);
         if (net->d_stage) cudaFree(net->d_stage);
         if (net->h_status) cudaFreeHost(net->h_status);
     }
@@ -781,7 +785,8 @@ int txh_get_lane_schedule(txh_net* net, int64_t M, int32_t* regions, int32_t* ro
     if (regions) std::memcpy(regions, s.regions.data(), s.regions.size() * sizeof(LaneRegionDesc));
     if (rows)
         for (size_t i = 0; i < s.row_reach.size(); ++i) {
-            rows[4 * i] = s.row_reach[i]; rows[4 * i + 1] = s.row_off[i]; rows[4 * i + 2] = s.row_cbeg[i]; rows[4 * i + 3] = s.row_slot[i];
+            rows[6 * i] = s.row_reach[i]; rows[6 * i + 1] = s.row_off[i]; rows[6 * i + 2] = s.row_c01[i];
+            rows[6 * i + 3] = s.row_nx[i]; rows[6 * i + 4] = s.row_xbeg[i]; rows[6 * i + 5] = s.row_slot[i];
         }
     if (child) for (size_t i = 0; i < s.child.size(); ++i) child[i] = s.child[i];
     return TXH_OK;
@@ -1285,6 +1290,34 @@ int txh_enkf_apply(txh_net* net, double* O, double* I, int64_t Mloc, const doubl
                           st));
     if (fuse_o) CU(launch_inflow_gain(net->d_inner, net->n_inner, net->d_up_off, net->d_up_pos, G, I, ld, st));
     else CU(launch_apply_gain(net->d_up_off, net->d_up_pos, G, O, I, net->topo.n, ld, (int)Mloc, st));
+    return TXH_OK;
+}
+
+int txh_enkf_apply_peers(txh_net* net, const double* O_in, double* O_out, double* I, int64_t Mloc,
+                         const double* const* shard_ptrs, int64_t world, int64_t Mtot, int64_t col0, const double* mean,
+                         const double* T, const int64_t* obs, int64_t m, const double* qs, const double* W, double* G,
+                         void* stream)
+{
+    if (!net || !O_in || !O_out || !I || !shard_ptrs || !mean || !T || !obs || !qs || !W || !G)
+        return fail(TXH_E_INVALID, "null argument");
+    if (world < 1 || world > kMaxPeers || Mtot != Mloc * world) return fail(TXH_E_INVALID, "bad shard layout");
+    if (col0 < 0 || col0 + Mloc > Mtot) return fail(TXH_E_INVALID, "shard columns out of range");
+    if (O_in == O_out) return fail(TXH_E_INVALID, "the posterior needs a buffer of its own: peers may still read O_in");
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_M(Mloc)) || (rc = ensure_device(net))) return rc;
+    int32_t* d_pos = nullptr;
+    if ((rc = obs_positions(net, obs, m, st, &d_pos))) return rc;
+    const int ld = (int)txh_row_stride(Mloc);
+    PeerBlocks pb{};
+    pb.count = (int)world;
+    for (int64_t b = 0; b < world; ++b) {
+        if (!shard_ptrs[b]) return fail(TXH_E_INVALID, "null shard pointer");
+        pb.p[b] = shard_ptrs[b];
+    }
+    CU(launch_enkf_update(O_in, ld, (int)Mtot, mean, T + col0, (int)Mtot, (int)Mloc, const_cast<double*>(O_in), G, ld,
+                          net->topo.n, net->d_gauge_of_pos, qs, W, (int)col0, net->num_sms, (int)Mloc, 0, st, &pb, O_out));
+    CU(launch_inflow_gain(net->d_inner, net->n_inner, net->d_up_off, net->d_up_pos, G, I, ld, st));
     return TXH_OK;
 }
 

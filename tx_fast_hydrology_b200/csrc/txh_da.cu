@@ -558,10 +558,14 @@ constexpr int EU_WARPS = 8, EU_ROWS = 16 * EU_WARPS, EU_LDT = 66;
 
 __global__ void __launch_bounds__(EU_WARPS * 32)
 enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const double* __restrict__ mean,
-                   const double* __restrict__ T, int ldt, int Mloc, double* __restrict__ O, double* __restrict__ G,
+                   const double* __restrict__ T, int ldt, int Mloc, const double* O, double* Oout, double* __restrict__ G,
                    int ld, long long n, const int32_t* __restrict__ gauge_of_pos, const double* __restrict__ qs,
-                   const double* __restrict__ W, int col0, int resident, int Mb, long long blk_stride)
+                   const double* __restrict__ W, int col0, int resident, int Mb, long long blk_stride,
+                   const PeerBlocks peers)
 {
+    // peers.count > 0: block b of the ensemble is read where it lives -- peers.p[b] is the state matrix [n][ldx] of
+    // shard b, the local one or a peer GPU's mapped over NVLink (the transform overlaps the transfer tile by tile;
+    // nothing is gathered first).  The posterior then goes to Oout != O: a peer may still be reading O.
     // Xall: Mtot / Mb blocks of [n][ldx], block b holding members b*Mb .. (b+1)*Mb - 1 (what an all-gather of
     // the shards' state rows produces); Mb == Mtot: one matrix
     // `resident`: every 64-member k chunk of T has its own block of shared memory and is staged once per CTA
@@ -576,6 +580,7 @@ enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const dou
         const long long row0 = rw + g, row1 = rw + 8 + g;
         const double mu0 = row0 < n ? mean[row0] : 0.0, mu1 = row1 < n ? mean[row1] : 0.0;
         for (int cg = 0; cg < ncg; ++cg) {
+            const int njt = min(8, (Mloc - cg * 64 + 7) >> 3);
             double acc[2][8][2];
 #pragma unroll
             for (int i = 0; i < 2; ++i)
@@ -600,20 +605,23 @@ enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const dou
                 for (int i = 0; i < 2; ++i) {
                     const long long row = i ? row1 : row0;
                     const double mu = i ? mu1 : mu0;
-                    const double* xrow = Xall + (size_t)(row < n ? row : 0) * ldx;
+                    const size_t xoff = (size_t)(row < n ? row : 0) * ldx;
+                    const double* xrow = Xall + xoff;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int k = kc * 64 + 8 * j + 2 * t;
                         double x0 = mu, x1 = mu;
                         if (row < n) {
                             const int b = k / Mb, kk = k - b * Mb;
-                            const double* xr = xrow + (size_t)b * blk_stride + kk;
+                            const double* xr = (peers.count > 0 ? peers.p[b] + xoff : xrow + (size_t)b * blk_stride) + kk;
                             if (vec && k + 1 < Mtot) {
-                                const double2 v = *reinterpret_cast<const double2*>(xr);
+                                const double2 v = __ldcg(reinterpret_cast<const double2*>(xr));
                                 x0 = v.x; x1 = v.y;
                             } else {
-                                if (k < Mtot) x0 = xr[0];
-                                if (k + 1 < Mtot) x1 = (kk + 1 < Mb) ? xr[1] : xrow[(size_t)(b + 1) * blk_stride];
+                                if (k < Mtot) x0 = __ldcg(xr);
+                                if (k + 1 < Mtot)
+                                    x1 = (kk + 1 < Mb) ? __ldcg(xr + 1)
+                                                       : __ldcg(peers.count > 0 ? peers.p[b + 1] + xoff : xrow + (size_t)(b + 1) * blk_stride);
                             }
                         }
                         a[i][2 * j] = x0 - mu; a[i][2 * j + 1] = x1 - mu;
@@ -625,9 +633,11 @@ enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const dou
                     const double* bt = sT + k * EU_LDT + g;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const double b = bt[8 * j];
-                        dmma8x8x4(acc[0][j][0], acc[0][j][1], a[0][ks], b);
-                        dmma8x8x4(acc[1][j][0], acc[1][j][1], a[1][ks], b);
+                        if (j < njt) {                              // column tiles beyond this shard's members: skipped
+                            const double b = bt[8 * j];
+                            dmma8x8x4(acc[0][j][0], acc[0][j][1], a[0][ks], b);
+                            dmma8x8x4(acc[1][j][0], acc[1][j][1], a[1][ks], b);
+                        }
                     }
                 }
             }
@@ -651,10 +661,9 @@ enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const dou
                         if (col + 1 < Mloc) gn.y += qg * wr[col + 1];
                     }
                     if (O) {
-                        double2* op = reinterpret_cast<double2*>(O + (size_t)row * ld + col);
-                        double2 o = *op;
+                        double2 o = *reinterpret_cast<const double2*>(O + (size_t)row * ld + col);
                         o.x += gn.x; o.y += gn.y;
-                        *op = o;
+                        *reinterpret_cast<double2*>(Oout + (size_t)row * ld + col) = o;
                     }
                     *reinterpret_cast<double2*>(G + (size_t)row * ld + col) = gn;
                 }
@@ -969,10 +978,13 @@ cudaError_t launch_spd_solve(double* S, double* B, int m, int k, int* info, cuda
 cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const double* mean, const double* T, int ldt,
                                int Mloc, double* O, double* G, int ld, int64_t n, const int32_t* gauge_of_pos,
                                const double* qs, const double* W, int col0, int num_sms, int Mb, long long blk_stride,
-                               cudaStream_t st)
+                               cudaStream_t st, const PeerBlocks* peers, double* Oout)
 {
     long long tiles = (n + EU_ROWS - 1) / EU_ROWS;
-    if (Mtot == Mloc && Mtot <= 64 && ld <= 64 && ldx == ld && col0 == 0) {
+    PeerBlocks pb{};
+    if (peers) pb = *peers;
+    if (!Oout) Oout = O;
+    if (!peers && Mtot == Mloc && Mtot <= 64 && ld <= 64 && ldx == ld && col0 == 0) {
         constexpr int RT = EU64_RT;
         tiles = (n + 8 * RT - 1) / (8 * RT);
         tiles = (tiles + 16 / RT - 1) / (16 / RT);             // CTAs' worth of warp tiles
@@ -990,8 +1002,8 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
     const size_t smem = (size_t)(resident ? nkc : 1) * 64 * EU_LDT * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(enkf_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    enkf_update_kernel<<<(unsigned)grid, EU_WARPS * 32, smem, st>>>(Xall, ldx, Mtot, mean, T, ldt, Mloc, O, G, ld, n,
-                                                                    gauge_of_pos, qs, W, col0, resident, Mb, blk_stride);
+    enkf_update_kernel<<<(unsigned)grid, EU_WARPS * 32, smem, st>>>(Xall, ldx, Mtot, mean, T, ldt, Mloc, O, Oout, G, ld, n,
+                                                                    gauge_of_pos, qs, W, col0, resident, Mb, blk_stride, pb);
     count_launch();
     return cudaGetLastError();
 }

@@ -14,6 +14,38 @@ struct StepInterp {
     double w0, w1;
 };
 
+// nutils.py:21-34: np.searchsorted(xp, x) (side='left'), clamped ends, linear weights or the nearer row
+__device__ __forceinline__ StepInterp interp_step(const double* __restrict__ times, int R, double x, int method)
+{
+    int lo = 0, hi = R;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (times[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    StepInterp si;
+    if (lo == 0) { si.r0 = 0; si.r1 = 0; si.w0 = 1.0; si.w1 = 0.0; }
+    else if (lo >= R) { si.r0 = R - 1; si.r1 = R - 1; si.w0 = 1.0; si.w1 = 0.0; }
+    else {
+        const double dx_0 = __dsub_rn(x, times[lo - 1]), dx_1 = __dsub_rn(times[lo], x);
+        if (method == 1) {
+            const double frac = __ddiv_rn(dx_0, __dadd_rn(dx_0, dx_1));
+            si.r0 = lo - 1; si.r1 = lo; si.w0 = __dsub_rn(1.0, frac); si.w1 = frac;
+        } else {
+            const int r = fabs(dx_0) <= fabs(dx_1) ? lo - 1 : lo;
+            si.r0 = r; si.r1 = r; si.w0 = 1.0; si.w1 = 0.0;
+        }
+    }
+    return si;
+}
+
+// The same record for route_lane_kernel, 32 bytes (two 128-bit loads); bit 31 of r1 is set when the bracket
+// (r0, r1) differs from the previous step's.
+struct LaneStep {
+    double w0, w1;
+    int32_t r0, r1;
+    int32_t pad0, pad1;
+};
+
 constexpr int kWarpsPerCta = 4;
 constexpr int kMemberBlock = 64;          // members per warp: one double2 per lane
 constexpr int kRingBytes = 2 * 12 * 512;  // per-warp row ring: 2 arrays x 12 rows x 512 B (see txh_route.cu)
@@ -99,13 +131,15 @@ struct WinArgs {
 // route_lane_kernel (txh_lane.cu): lanes = reaches, time-skewed regions, state in shared memory
 struct LaneArgs {
     const LaneRegionDesc* regions;        // ticket order
-    const int4* meta;                     // per row: {position (-1: virtual), skew offset, first child, slot}
+    const int4* meta;                     // per row: {position (-1: virtual), skew offset | further children << 16,
+                                          //           first two children c0 | c1 << 16, slot}
+    const int32_t* xbeg;                  // per row: first further child (relative to the region's child_off)
     const uint16_t* child;
     const double* coef;                   // [n][4]
     double* O;
     double* I;
     const double* F;                      // [R][n] schedule order, or nullptr
-    const StepInterp* steps;              // [nsteps] interpolation records of this launch
+    const LaneStep* steps;                // [nsteps] interpolation records of this launch
     const double* Wmul;                   // [R][wm_ld] or nullptr
     double* ring;                         // [n_slots][M][splp] streams between regions; EMPTY (all bits set) when idle
     unsigned long long* ticket;           // zero at launch; the last CTA to leave zeroes it again
@@ -118,8 +152,6 @@ struct LaneArgs {
     int64_t n;
     int32_t n_regions, nsteps, splp, ld, M, wm_ld, R, rec_every, rec_count;
     int32_t TR;                           // threads [0, TR) own real rows, the rest the virtual rows
-    int32_t rr_stride, rv_stride;         // row strides of the p / outflow arrays
-    int32_t off_coef, off_p, off_obuf, off_ext, off_child;   // shared-memory layout (bytes)
 };
 
 struct LevelArgs {
@@ -140,6 +172,7 @@ cudaError_t launch_route_level(const LevelArgs& a, cudaStream_t st);
 cudaError_t launch_window_init(const InitArgs& a, unsigned long long* ticket, cudaStream_t st);
 cudaError_t launch_route_window(const WinArgs& a, int warps_per_cta, int num_sms, cudaStream_t st);
 cudaError_t launch_route_lane(const LaneArgs& a, int mt, int threads, size_t smem, int grid, cudaStream_t st);
+cudaError_t launch_lane_init(const InitArgs& a, LaneStep* out, unsigned long long* ticket, cudaStream_t st);
 cudaError_t launch_init_inflows(const int32_t* up_off, const int32_t* up_pos, const uint8_t* is_outlet,
                                 const double* O, double* I, int64_t n, int ld, int M, cudaStream_t st);
 cudaError_t launch_apply_gain(const int32_t* up_off, const int32_t* up_pos, const double* G, double* O,
@@ -182,10 +215,16 @@ cudaError_t launch_innovation(const double* HX, const double* Zp, const double* 
 cudaError_t launch_innov_cov_finish(double* S, const double* qs, const double* R, int m, double scale, cudaStream_t st);
 cudaError_t launch_spd_solve(double* S, double* B, int m, int k, int* info, cudaStream_t st);
 cudaError_t launch_inverse(double* A, double* W, int m, int* info, cudaStream_t st);
+// State matrices of the shards of a member-sharded ensemble, read in place (peer GPUs mapped over NVLink)
+constexpr int kMaxPeers = 16;
+struct PeerBlocks {
+    const double* p[kMaxPeers];
+    int count;
+};
 cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const double* mean, const double* T, int ldt,
                                int Mloc, double* O, double* G, int ld, int64_t n, const int32_t* gauge_of_pos,
                                const double* qs, const double* W, int col0, int num_sms, int Mb, long long blk_stride,
-                               cudaStream_t st);
+                               cudaStream_t st, const PeerBlocks* peers = nullptr, double* Oout = nullptr);
 cudaError_t launch_inflow_gain(const int32_t* inner, int64_t n_inner, const int32_t* up_off, const int32_t* up_pos,
                                const double* G, double* I, int ld, cudaStream_t st);
 

@@ -14,11 +14,14 @@
 //     inflow = sum of the upstream outflows               (shared-memory gathers, fixed child order)
 //     o' = alpha*inflow + (p + gamma*q),   p' = beta*inflow + chi*o'      (p = beta*i + chi*o of the old state)
 // Outflows crossing regions travel through streams ring[slot][member][step] in global memory: an unwritten
-// cell holds EMPTY (all bits set); the consumer mirrors a stream as a virtual row, prefetches it 16 steps
-// ahead with cp.async, polls a cell that is still EMPTY, and puts EMPTY back.  Regions are claimed in a
+// cell holds EMPTY (all bits set); the consumer mirrors a stream as a virtual row, stays kLag steps behind its
+// producer so that its cp.async prefetches (two 8-step batches ahead) always find data, polls a cell that is
+// still EMPTY, and puts EMPTY back.  Regions are claimed in a
 // topological order, so a region only waits for regions that are running or done (every CTA is resident).
 // The forcing is interpolated per step exactly as nutils.py:21-34 does; its bracket rows live in shared
 // memory and the next row is prefetched (cp.async) one bracket ahead.
+#include <algorithm>
+
 #include "txh_kernels.cuh"
 
 namespace txh {
@@ -45,77 +48,103 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void cp_async8(void* s, const void* g)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(s)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* s, const void* g)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(s)), "l"(g) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// wait until at most `pending` of this thread's most recent groups are still in flight
-__device__ __forceinline__ void cp_async_wait_pending(int pending)
-{
-    switch (pending) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-    }
-}
 __device__ __forceinline__ bool is_empty(double v) { return __double_as_longlong(v) == -1ll; }
 __device__ __forceinline__ double empty_cell() { return __longlong_as_double(-1ll); }
 
-constexpr int kBatch = 16;                 // steps of a stream fetched per cp.async batch (128 bytes)
-constexpr int kExtCells = 2 * kBatch;      // shared-memory window of a stream: this batch and the next
+// Streams are read in batches of kBatch steps (64 bytes), prefetched TWO batches ahead with cp.async into a
+// four-batch window in shared memory.  Producer and consumer regions advance at the same rate, so a consumer
+// that started right behind its producer would find every prefetch EMPTY and pay a trip to L2 per step; it
+// therefore waits once, before its first step, until the producer is kLag steps ahead (or done), and every
+// later prefetch lands on cells that are already written.
+constexpr int kBatch = 8;
+constexpr int kExtCells = 4 * kBatch;      // shared-memory window of a stream
+constexpr int kLag = 48;                   // steps a producer is ahead before its consumer starts
 
-// Auxiliary word pair kept in the eighth double of a row's coefficient record.
-struct RowAux { int32_t rec; int32_t issue; };
-
-// A new forcing bracket for a row: (pr0, pr1) -> (r0, r1).  The rows of the old bracket and the prefetched
-// row `pn` are in the record; anything else (irregular tables, nearest-row method jumps) is read in place.
-__device__ __forceinline__ void rotate_bracket(double* cf, const double* __restrict__ Fcol, int64_t n, int R, int pr0, int pr1,
-                                               int r0, int r1, int& groups_issued)
+// ---- shared memory through 32-bit shared-space addresses (no generic-address arithmetic in the loop) ----
+__device__ __forceinline__ int4 lds_i4(unsigned a)
 {
-    RowAux aux = *reinterpret_cast<RowAux*>(cf + 7);
-    // the prefetch this row issued at its previous rotation: groups committed since then may stay in flight
-    cp_async_wait_pending(min(7, groups_issued - aux.issue - 1 < 0 ? 0 : groups_issued - aux.issue - 1));
-    const double f0 = cf[4], f1 = cf[5], fn = cf[6];
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_d2(unsigned a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_d(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned a)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_d(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_d2(unsigned a, double2 v)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts_i4(unsigned a, int4 v)
+{
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void cp_async8_s(unsigned sa, const void* g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(unsigned sa, const void* g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+}
+
+// A new forcing bracket for a row: (pr0, pr1) -> (r0, r1).  f0, f1 are the rows of the old bracket at this reach,
+// fn the row after them, requested when the old bracket was entered (a plain load whose register is not touched
+// until now, a dozen iterations later: the latency is hidden without any wait); anything else (irregular tables,
+// jumps of the nearest-row method) is read in place.
+__device__ __forceinline__ void rotate_bracket(double& f0, double& f1, double& fn, const double* __restrict__ Fcol, int64_t n,
+                                               int R, int pr0, int pr1, int r0, int r1)
+{
     const int pn = min(max(pr0, pr1) + 1, R - 1);
     const double n0 = r0 == pr0 ? f0 : r0 == pr1 ? f1 : r0 == pn ? fn : __ldg(Fcol + (size_t)r0 * n);
     const double n1 = r1 == pr0 ? f0 : r1 == pr1 ? f1 : r1 == pn ? fn : __ldg(Fcol + (size_t)r1 * n);
-    cf[4] = n0; cf[5] = n1;
+    f0 = n0; f1 = n1;
     const int nn = min(max(r0, r1) + 1, R - 1);
-    if (nn == r0) cf[6] = n0;
-    else if (nn == r1) cf[6] = n1;
-    else cp_async8(cf + 6, Fcol + (size_t)nn * n);
-    cp_async_commit();
-    aux.issue = groups_issued++;
-    *reinterpret_cast<RowAux*>(cf + 7) = aux;
+    fn = nn == r0 ? n0 : nn == r1 ? n1 : __ldg(Fcol + (size_t)nn * n);
 }
 
+// One row (reach) per thread; everything a row needs every step -- coefficients, the forcing bracket, p = beta*i +
+// chi*o of up to four members -- lives in REGISTERS for the whole launch.  Shared memory carries only what rows
+// exchange: the outflows of this and the previous iteration (gathered by the downstream rows), the windows of the
+// incoming streams, and the lists of children beyond the first two.  (A first version kept 64-byte row records in
+// shared memory: their 128-bit loads at a 64-byte stride cost four times the ideal wavefronts and made the kernel
+// shared-memory-bandwidth bound at ~5,000 cycles per iteration; profiles/r02_lane_kernel_history.md.)
 template <int MT, bool HAS_F, bool HAS_W>
 __global__ void __launch_bounds__(1024, 1)
 route_lane_kernel(const LaneArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_all[];
     __shared__ int sRegion;
-    constexpr int MC = MT < 4 ? MT : 4;                         // members evaluated together (register tile)
-    int4* sMeta = reinterpret_cast<int4*>(smem_all);
-    double* sCoef = reinterpret_cast<double*>(smem_all + a.off_coef);     // [rr][8]
-    double* sP = reinterpret_cast<double*>(smem_all + a.off_p);           // [MT][rr]
-    double* sOb = reinterpret_cast<double*>(smem_all + a.off_obuf);       // [2][MT][rv]
-    double* sExt = reinterpret_cast<double*>(smem_all + a.off_ext);       // [virt][MT][32]
-    uint16_t* sChild = reinterpret_cast<uint16_t*>(smem_all + a.off_child);
+    constexpr bool PREG = MT <= 4;                              // p in registers (else in shared memory)
+    constexpr int MR = PREG ? MT : 1;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_all);
     const int tid = threadIdx.x;
     const int TR = a.TR, TV = (int)blockDim.x - a.TR;
-    const int rr = a.rr_stride, rv = a.rv_stride;
     const int nsteps = a.nsteps, M = a.M, ld = a.ld;
     const size_t splp = (size_t)a.splp;
     bool abandon = false;                                      // watchdog / poisoned handle: decided by a barrier vote
@@ -130,47 +159,63 @@ route_lane_kernel(const LaneArgs a)
         if (reg < 0) break;
         const LaneRegionDesc rd = a.regions[reg];
         const int nr = rd.n_real, nv = rd.n_virt;
-        // ---- load the region: row records, children, coefficients, p = beta*i + chi*o, forcing bracket of step 0 ----
-        {
-            const int4* gm = a.meta + rd.row_off;
-            for (int i = tid; i < nr + nv + 1; i += blockDim.x) sMeta[i] = gm[i];
-            const uint16_t* gc = a.child + rd.child_off;
-            for (int i = tid; i < rd.n_child; i += blockDim.x) sChild[i] = gc[i];
-        }
-        int r0s = 0, r1s = 0, rns = 0;
-        if (HAS_F) { r0s = __ldg(&a.steps[0].r0); r1s = __ldg(&a.steps[0].r1); rns = min(max(r0s, r1s) + 1, a.R - 1); }
-        if (tid < TR) {
-            for (int r = tid; r < nr; r += TR) {
-                const int pos = a.meta[rd.row_off + r].x;
-                const double2 ab = *reinterpret_cast<const double2*>(a.coef + 4 * (size_t)pos);
-                const double2 cg = *reinterpret_cast<const double2*>(a.coef + 4 * (size_t)pos + 2);
-                double* cf = sCoef + 8 * r;
-                cf[0] = ab.x; cf[1] = ab.y; cf[2] = cg.x; cf[3] = cg.y;
-                if (HAS_F) {
-                    cf[4] = __ldg(a.F + (size_t)r0s * a.n + pos);
-                    cf[5] = __ldg(a.F + (size_t)r1s * a.n + pos);
-                    cf[6] = __ldg(a.F + (size_t)rns * a.n + pos);
-                } else { cf[4] = cf[5] = cf[6] = 0.0; }
-                RowAux aux; aux.rec = a.rec_slot ? a.rec_slot[pos] : -1; aux.issue = -1;
-                *reinterpret_cast<RowAux*>(cf + 7) = aux;
-                const double* og = a.O + (size_t)pos * ld;
-                const double* ig = a.I + (size_t)pos * ld;
+        // shared-memory layout of this region (LaneSchedule::region_bytes)
+        const int rv = nr + nv + 1;                            // rows of an outflow buffer: real, virtual, ZERO
+        const unsigned sOb = sbase;                            // [2][MT][rv] outflows of this / the previous iteration
+        const unsigned sExt = sOb + 16u * MT * rv;             // [nv][MT][32] stream windows
+        const unsigned sMetaV = sExt + 256u * MT * nv;         // [nv] records of the virtual rows
+        const unsigned sChild = sMetaV + 16u * nv;             // children beyond the first two
+        const unsigned sP = sChild + (((unsigned)(2 * rd.n_child)) + 15u & ~15u);   // [MT][nr] (MT > 4 only)
+        // ---- this thread's row ----------------------------------------------------------------------------
+        const bool has_row = tid < nr;
+        int off = 0, nx = 0, slot = -1, pos = 0, rec = -1;
+        unsigned c0a = 0, c1a = 0, xa0 = 0;
+        double al = 0.0, be = 0.0, ch = 0.0, ga = 0.0, f0 = 0.0, f1 = 0.0, fn = 0.0;
+        double p[MR];
 #pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    double p = 0.0;
-                    if (m < M) p = ab.y * __ldcg(ig + m) + cg.x * __ldcg(og + m);
-                    sP[m * rr + r] = p;
-                }
+        for (int m = 0; m < MR; ++m) p[m] = 0.0;
+        if (has_row) {
+            const int4 mt = a.meta[rd.row_off + tid];
+            pos = mt.x; off = mt.y & 0xffff; nx = (int)((unsigned)mt.y >> 16); slot = mt.w;
+            c0a = 8u * ((unsigned)mt.z & 0xffffu); c1a = 8u * ((unsigned)mt.z >> 16);
+            if (nx > 0) xa0 = sChild + 2u * (unsigned)a.xbeg[rd.row_off + tid];
+            const double2 ab = *reinterpret_cast<const double2*>(a.coef + 4 * (size_t)pos);
+            const double2 cg = *reinterpret_cast<const double2*>(a.coef + 4 * (size_t)pos + 2);
+            al = ab.x; be = ab.y; ch = cg.x; ga = cg.y;
+            if (HAS_F) {
+                const int r0s = __ldg(&a.steps[0].r0), r1s = __ldg(&a.steps[0].r1) & 0x7fffffff;
+                f0 = __ldg(a.F + (size_t)r0s * a.n + pos);
+                f1 = __ldg(a.F + (size_t)r1s * a.n + pos);
+                fn = __ldg(a.F + (size_t)min(max(r0s, r1s) + 1, a.R - 1) * a.n + pos);
             }
-        } else {
-            // the first batch of every incoming stream
-            for (int v = tid - TR; v < nv; v += TV) {
-                const int slot = a.meta[rd.row_off + nr + v].w;
-                for (int m = 0; m < M; ++m) {
-                    double* ex = sExt + ((size_t)(v * MT + m) << 5);
-                    const double* g = a.ring + ((size_t)slot * M + m) * splp;
+            if (a.rec_slot) rec = a.rec_slot[pos];
+            const double* og = a.O + (size_t)pos * ld;
+            const double* ig = a.I + (size_t)pos * ld;
 #pragma unroll
-                    for (int q = 0; q < kBatch / 2; ++q) cp_async16(ex + 2 * q, g + 2 * q);
+            for (int m = 0; m < MT; ++m) {
+                double pm = 0.0;
+                if (m < M) pm = be * __ldcg(ig + m) + ch * __ldcg(og + m);
+                if (PREG) p[m < MR ? m : 0] = pm;
+                else sts_d(sP + 8u * ((unsigned)m * nr + tid), pm);
+            }
+        }
+        {
+            const int4* gm = a.meta + rd.row_off + nr;
+            for (int i = tid; i < nv; i += blockDim.x) sts_i4(sMetaV + 16u * i, gm[i]);
+            const uint16_t* gc = a.child + rd.child_off;
+            for (int i = tid; i < rd.n_child; i += blockDim.x) sts_u16(sChild + 2u * i, gc[i]);
+            // the ZERO row of both buffers: what a missing child reads
+            for (int i = tid; i < 2 * MT; i += blockDim.x) sts_d(sOb + 8u * ((unsigned)i * rv + (nr + nv)), 0.0);
+        }
+        if (tid >= TR) {
+            // the first two batches of every incoming stream (most likely still EMPTY: fetched again after the lag wait)
+            for (int v = tid - TR; v < nv; v += TV) {
+                const int vslot = a.meta[rd.row_off + nr + v].w;
+                for (int m = 0; m < M; ++m) {
+                    const unsigned ex = sExt + 256u * ((unsigned)v * MT + m);
+                    const double* g = a.ring + ((size_t)vslot * M + m) * splp;
+#pragma unroll
+                    for (int q = 0; q < kBatch; ++q) cp_async16_s(ex + 16u * q, g + 2 * q);
                 }
             }
             cp_async_commit();
@@ -178,98 +223,105 @@ route_lane_kernel(const LaneArgs a)
         __syncthreads();
 
         const int niter = nsteps + rd.n_extra - 1;
-        int groups_issued = 0;
+        const unsigned ra = 8u * (unsigned)tid;                 // this row's cell in an outflow buffer
         int dead = 0;
         for (int k = 0; k < niter; ++k) {
-            const double* obp = sOb + (size_t)((k & 1) ^ 1) * MT * rv;
-            double* obc = sOb + (size_t)(k & 1) * MT * rv;
-            if (tid < TR) {
-                for (int r = tid; r < nr; r += TR) {
-                    const int4 mt = sMeta[r];
-                    const int s = k - mt.y;
-                    if ((unsigned)s >= (unsigned)nsteps) continue;
-                    const int cb = mt.z, ce = sMeta[r + 1].z;
-                    double* cf = sCoef + 8 * r;
-                    double w0 = 0.0, w1 = 0.0;
-                    int fr0 = 0, fr1 = 0;
-                    if (HAS_F) {
-                        const StepInterp si = a.steps[s];
-                        fr0 = si.r0; fr1 = si.r1; w0 = si.w0; w1 = si.w1;
-                        if (s > 0) {
-                            const int pr0 = __ldg(&a.steps[s - 1].r0), pr1 = __ldg(&a.steps[s - 1].r1);
-                            if (pr0 != fr0 || pr1 != fr1)
-                                rotate_bracket(cf, a.F + mt.x, a.n, a.R, pr0, pr1, fr0, fr1, groups_issued);
+            const unsigned obp = sOb + 8u * (unsigned)(((k & 1) ^ 1) * MT * rv);
+            const unsigned obc = sOb + 8u * (unsigned)((k & 1) * MT * rv);
+            const int s = k - off;
+            if (has_row && (unsigned)s < (unsigned)nsteps) {
+                double w0 = 0.0, w1 = 0.0;
+                int fr0 = 0, fr1 = 0;
+                if (HAS_F) {
+                    const LaneStep* st = a.steps + s;
+                    const double2 ww = *reinterpret_cast<const double2*>(&st->w0);
+                    const int2 rr = *reinterpret_cast<const int2*>(&st->r0);
+                    w0 = ww.x; w1 = ww.y; fr0 = rr.x; fr1 = rr.y & 0x7fffffff;
+                    if (rr.y < 0)                                // the bracket differs from the previous step's
+                        rotate_bracket(f0, f1, fn, a.F + pos, a.n, a.R, __ldg(&st[-1].r0), __ldg(&st[-1].r1) & 0x7fffffff, fr0, fr1);
+                }
+                double q = 0.0;
+                if (HAS_F && !HAS_W) q = ga * (w0 * f0 + w1 * f1);
+                const bool last = s + 1 == nsteps;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const unsigned mo = 8u * (unsigned)(m * rv);
+                    double infl = lds_d(obp + mo + c0a) + lds_d(obp + mo + c1a);
+                    if (nx > 0) {                               // confluences of more than two reaches (rows sorted last)
+                        unsigned xa = xa0;
+                        for (int c = 0; c < nx; ++c, xa += 2u) infl += lds_d(obp + mo + 8u * lds_u16(xa));
+                    }
+                    double qm = q;
+                    if (HAS_W) {
+                        const int mc = min(m, a.wm_ld - 1);
+                        qm = ga * (w0 * __ldg(a.Wmul + (size_t)fr0 * a.wm_ld + mc) * f0 +
+                                   w1 * __ldg(a.Wmul + (size_t)fr1 * a.wm_ld + mc) * f1);
+                    }
+                    double pm;
+                    if (PREG) pm = p[m < MR ? m : 0];
+                    else pm = lds_d(sP + 8u * ((unsigned)m * nr + tid));
+                    const double o = al * infl + (pm + qm);
+                    pm = be * infl + ch * o;
+                    if (PREG) p[m < MR ? m : 0] = pm;
+                    else sts_d(sP + 8u * ((unsigned)m * nr + tid), pm);
+                    sts_d(obc + mo + ra, o);
+                    if ((slot >= 0 || last) && m < M) {
+                        if (slot >= 0) __stcg(a.ring + ((size_t)slot * M + m) * splp + s, o);
+                        if (last) {
+                            __stcg(a.O + (size_t)pos * ld + m, o);
+                            __stcg(a.I + (size_t)pos * ld + m, infl);
                         }
                     }
-                    const double2 ab = *reinterpret_cast<const double2*>(cf);
-                    const double2 cg = *reinterpret_cast<const double2*>(cf + 2);
-                    double q = 0.0, f0 = 0.0, f1 = 0.0;
-                    if (HAS_F) {
-                        const double2 ff = *reinterpret_cast<const double2*>(cf + 4);
-                        f0 = ff.x; f1 = ff.y;
-                        if (!HAS_W) q = cg.y * (w0 * f0 + w1 * f1);
-                    }
-                    const bool last = s + 1 == nsteps;
-#pragma unroll
-                    for (int m0 = 0; m0 < MT; m0 += MC) {
-                        double infl[MC];
-#pragma unroll
-                        for (int u = 0; u < MC; ++u) infl[u] = 0.0;
-                        for (int c = cb; c < ce; ++c) {
-                            const int ci = sChild[c];
-#pragma unroll
-                            for (int u = 0; u < MC; ++u) infl[u] += obp[(m0 + u) * rv + ci];
-                        }
-#pragma unroll
-                        for (int u = 0; u < MC; ++u) {
-                            const int m = m0 + u;
-                            double qm = q;
-                            if (HAS_W) {
-                                const int mc = min(m, a.wm_ld - 1);
-                                qm = cg.y * (w0 * __ldg(a.Wmul + (size_t)fr0 * a.wm_ld + mc) * f0 +
-                                             w1 * __ldg(a.Wmul + (size_t)fr1 * a.wm_ld + mc) * f1);
-                            }
-                            const double o = ab.x * infl[u] + (sP[m * rr + r] + qm);
-                            sP[m * rr + r] = ab.y * infl[u] + cg.x * o;
-                            obc[m * rv + r] = o;
-                            if (m < M) {
-                                if (mt.w >= 0) __stcg(a.ring + ((size_t)mt.w * M + m) * splp + s, o);
-                                if (last) {
-                                    __stcg(a.O + (size_t)mt.x * ld + m, o);
-                                    __stcg(a.I + (size_t)mt.x * ld + m, infl[u]);
-                                }
-                            }
-                        }
-                    }
-                    if (a.rec_slot) {
-                        const int rec = reinterpret_cast<const RowAux*>(cf + 7)->rec;
+                    if (rec >= 0 && m < M) {
                         const long long gs = a.rec_step_base + s + 1;
-                        if (rec >= 0 && gs % a.rec_every == 0) {
-                            double* out = a.rec_out + ((size_t)(gs / a.rec_every - 1) * a.rec_count + rec) * M;
-                            for (int m = 0; m < M; ++m) out[m] = obc[m * rv + r];
-                        }
+                        if (gs % a.rec_every == 0)
+                            a.rec_out[((size_t)(gs / a.rec_every - 1) * a.rec_count + rec) * M + m] = o;
                     }
                 }
-            } else {
+            } else if (tid >= TR) {
                 for (int v = tid - TR; v < nv; v += TV) {
-                    const int4 mt = sMeta[nr + v];
-                    const int s = k - mt.y;
-                    if ((unsigned)s >= (unsigned)nsteps) continue;
-                    if ((s & (kBatch - 1)) == 0) {
-                        cp_async_wait_all();                                 // this batch (issued 16 iterations ago)
-                        if (s + kBatch < nsteps) {
+                    const int4 mt = lds_i4(sMetaV + 16u * v);
+                    const int sv = k - (mt.y & 0xffff);
+                    if ((unsigned)sv >= (unsigned)nsteps) continue;
+                    if ((sv & (kBatch - 1)) == 0) {
+                        if (sv == 0) {
+                            // let the producer get kLag steps ahead (or finish), then fetch the first two batches anew
+                            const int need = min(nsteps, kLag) - 1;
+                            const double* g0 = a.ring + (size_t)mt.w * M * splp;
+                            unsigned spins = 0;
+                            unsigned long long t0 = 0;
+                            while (!dead && is_empty(ld_relaxed_f64(g0 + need))) {
+                                if ((++spins & 15u) == 0) {
+                                    if (ld_relaxed_s32(a.status) != 0) { dead = 1; break; }
+                                    const unsigned long long now = globaltimer_ns();
+                                    if (t0 == 0) t0 = now;
+                                    else if (now - t0 > a.watchdog_ns) { atomicExch(a.status, 1); dead = 1; break; }
+                                }
+                                __nanosleep(200);
+                            }
+                            cp_async_wait_all();
                             for (int m = 0; m < M; ++m) {
-                                double* ex = sExt + ((size_t)(v * MT + m) << 5) + ((s + kBatch) & (kExtCells - 1));
-                                const double* g = a.ring + ((size_t)mt.w * M + m) * splp + s + kBatch;
+                                const unsigned ex = sExt + 256u * ((unsigned)v * MT + m);
+                                const double* g = a.ring + ((size_t)mt.w * M + m) * splp;
 #pragma unroll
-                                for (int q = 0; q < kBatch / 2; ++q) cp_async16(ex + 2 * q, g + 2 * q);
+                                for (int q = 0; q < kBatch; ++q) cp_async16_s(ex + 16u * q, g + 2 * q);
+                            }
+                            cp_async_commit();
+                        }
+                        cp_async_wait_all();                                 // batches sv/8 and sv/8 + 1 are in the window
+                        if (sv + 2 * kBatch < nsteps) {
+                            for (int m = 0; m < M; ++m) {
+                                const unsigned ex = sExt + 256u * ((unsigned)v * MT + m) + 8u * ((sv + 2 * kBatch) & (kExtCells - 1));
+                                const double* g = a.ring + ((size_t)mt.w * M + m) * splp + sv + 2 * kBatch;
+#pragma unroll
+                                for (int q = 0; q < kBatch / 2; ++q) cp_async16_s(ex + 16u * q, g + 2 * q);
                             }
                         }
                         cp_async_commit();
                     }
                     for (int m = 0; m < M; ++m) {
-                        double* cell = a.ring + ((size_t)mt.w * M + m) * splp + s;
-                        double val = sExt[((size_t)(v * MT + m) << 5) + (s & (kExtCells - 1))];
+                        double* cell = a.ring + ((size_t)mt.w * M + m) * splp + sv;
+                        double val = lds_d(sExt + 256u * ((unsigned)v * MT + m) + 8u * (sv & (kExtCells - 1)));
                         if (is_empty(val)) {
                             // the prefetch came too early: poll the cell itself
                             unsigned spins = 0, nap = 32;
@@ -288,7 +340,7 @@ route_lane_kernel(const LaneArgs a)
                             }
                         }
                         __stcg(cell, empty_cell());
-                        obc[m * rv + nr + v] = val;
+                        sts_d(obc + 8u * ((unsigned)m * rv + nr + v), val);
                     }
                 }
             }
@@ -304,6 +356,25 @@ route_lane_kernel(const LaneArgs a)
             *a.done = 0ull;
             *a.ticket = 0ull;
         }
+    }
+}
+
+// forcing interpolation of the launch's steps (nutils.py:21-34), with the "bracket changed" mark on r1
+__global__ void __launch_bounds__(256) lane_init_kernel(const InitArgs a, LaneStep* out, unsigned long long* ticket)
+{
+    const long long gid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (gid0 == 0) *ticket = 0ull;
+    for (long long s = gid0; s < a.nsteps; s += stride) {
+        const StepInterp si = interp_step(a.times, a.R, (double)(a.t0_ns + (a.step_base + s + 1) * a.dt_ns), a.method);
+        bool changed = false;
+        if (s > 0) {
+            const StepInterp sp = interp_step(a.times, a.R, (double)(a.t0_ns + (a.step_base + s) * a.dt_ns), a.method);
+            changed = sp.r0 != si.r0 || sp.r1 != si.r1;
+        }
+        LaneStep ls;
+        ls.w0 = si.w0; ls.w1 = si.w1; ls.r0 = si.r0; ls.r1 = si.r1 | (changed ? (int)0x80000000 : 0); ls.pad0 = ls.pad1 = 0;
+        out[s] = ls;
     }
 }
 
@@ -323,6 +394,14 @@ cudaError_t launch_mt(const LaneArgs& a, int threads, size_t smem, int grid, cud
 }
 
 }  // namespace
+
+cudaError_t launch_lane_init(const InitArgs& a, LaneStep* out, unsigned long long* ticket, cudaStream_t st)
+{
+    const int blocks = (int)std::min<long long>(64, (a.nsteps + 255) / 256);
+    lane_init_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(a, out, ticket);
+    count_launch();
+    return cudaGetLastError();
+}
 
 cudaError_t launch_route_lane(const LaneArgs& a, int mt, int threads, size_t smem, int grid, cudaStream_t st)
 {

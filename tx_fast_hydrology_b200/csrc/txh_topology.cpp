@@ -693,12 +693,11 @@ namespace txh {
 size_t LaneSchedule::region_bytes(size_t real, size_t virt, size_t nchild, int mt)
 {
     auto up16 = [](size_t x) { return (x + 15) & ~size_t(15); };
-    return 16 * (real + virt + 1)          // row records
-           + 64 * real                     // alpha beta chi gamma f0 f1 fn aux
-           + 8 * (size_t)mt * real         // p = beta i + chi o
-           + 16 * (size_t)mt * (real + virt)   // outflows of this and the previous iteration
+    return 16 * (size_t)mt * (real + virt + 1)   // outflows of this and the previous iteration (+ the zero row)
            + 256 * (size_t)mt * virt       // 32 steps of every incoming stream
-           + up16(2 * nchild);
+           + 16 * virt                     // records of the virtual rows
+           + up16(2 * nchild)              // children beyond the first two of a row
+           + (mt > 4 ? up16(8 * (size_t)mt * real) : 0);   // p = beta i + chi o (in registers up to 4 members)
 }
 
 bool LaneSchedule::build(const Topology& t, const std::vector<int32_t>& pos_of_reach, int mt_, int cap_rows_,
@@ -709,9 +708,9 @@ bool LaneSchedule::build(const Topology& t, const std::vector<int32_t>& pos_of_r
     const int64_t n = t.n;
     if (mt < 1 || mt > 16 || (mt & (mt - 1))) { err = "lane schedule: member tile must be 1, 2, 4, 8 or 16"; return false; }
     if (cap_rows < 1) { err = "lane schedule: bad row cap"; return false; }
-    cap_rows = std::min(cap_rows, 60000);                                   // 16-bit local indices
+    cap_rows = std::min(cap_rows, kLaneMaxRows);                            // one row per thread
     // weights in bytes: a real row with ~one child entry, a virtual row
-    const int64_t wr = 16 + 64 + 24 * (int64_t)mt + 2, wv = 16 + 272 * (int64_t)mt + 2;
+    const int64_t wr = 16 * (int64_t)mt + (mt > 4 ? 8 * (int64_t)mt : 0) + 2, wv = 16 + 272 * (int64_t)mt + 2;
     const int64_t cap_bytes = (int64_t)smem_budget - 256;               // sentinel record, alignment of the parts
     if (wr + wv > cap_bytes) { err = "lane schedule: shared-memory budget too small"; return false; }
 
@@ -812,49 +811,63 @@ bool LaneSchedule::build(const Topology& t, const std::vector<int32_t>& pos_of_r
     std::vector<std::vector<int32_t>> reg_rows(nreg);
     for (int64_t j = 0; j < n; ++j) reg_rows[reg_of_cl[cl_of[j]]].push_back((int32_t)j);
     regions.assign(nreg, LaneRegionDesc{});
-    row_reach.clear(); row_off.clear(); row_cbeg.clear(); row_slot.clear(); child.clear();
+    row_reach.clear(); row_off.clear(); row_c01.clear(); row_nx.clear(); row_xbeg.clear(); row_slot.clear(); child.clear();
     max_real = max_virt = max_child = max_extra = 0;
-    std::vector<int32_t> local(n, -1);
+    max_bytes = 0;
+    std::vector<int32_t> local(n, -1), off_of(n, 0);
     for (int32_t g = 0; g < nreg; ++g) {
         std::vector<int32_t>& rows = reg_rows[g];
-        std::sort(rows.begin(), rows.end(), [&](int32_t a, int32_t b) { return pos_of_reach[a] < pos_of_reach[b]; });
+        for (int32_t j : rows) off_of[j] = cl_depth[cl_of[j]] - dist[j];
+        std::sort(rows.begin(), rows.end(), [&](int32_t a, int32_t b) {
+            const bool xa = t.child_off[a + 1] - t.child_off[a] > 2, xb = t.child_off[b + 1] - t.child_off[b] > 2;
+            if (xa != xb) return xb;                                        // rows with further children last
+            if (off_of[a] != off_of[b]) return off_of[a] < off_of[b];
+            return pos_of_reach[a] < pos_of_reach[b]; });
         LaneRegionDesc& rd = regions[g];
         rd.row_off = (int32_t)row_reach.size();
         rd.n_real = (int32_t)rows.size();
         rd.child_off = (int32_t)child.size();
         rd.height = cl_h[reg_cls[g].front()];
         for (int32_t i = 0; i < rd.n_real; ++i) local[rows[i]] = i;
+        // virtual rows: one per upstream reach that belongs to another cluster, in consumer-row order
         int32_t nv = 0, extra = 0;
-        std::vector<int32_t> v_off, v_slot;
-        for (int32_t i = 0; i < rd.n_real; ++i) {
-            const int32_t j = rows[i], c = cl_of[j];
-            const int32_t off = cl_depth[c] - dist[j];
-            row_reach.push_back(j); row_off.push_back(off);
-            row_cbeg.push_back((int32_t)child.size() - rd.child_off);
-            row_slot.push_back(slot_of[j]);
-            extra = std::max(extra, off + 1);
-            for (int32_t e = t.child_off[j]; e < t.child_off[j + 1]; ++e) {
-                const int32_t ch = t.child[e];
-                if (!closed[ch]) child.push_back((uint16_t)local[ch]);      // rows are sorted by position, not by id:
-                else {                                                      // local[] of every row was set above
-                    child.push_back((uint16_t)(rd.n_real + nv));
-                    v_off.push_back(off - 1); v_slot.push_back(slot_of[ch]);
-                    ++nv;
-                }
-            }
-        }
+        for (int32_t i = 0; i < rd.n_real; ++i)
+            for (int32_t e = t.child_off[rows[i]]; e < t.child_off[rows[i] + 1]; ++e) if (closed[t.child[e]]) ++nv;
         rd.n_virt = nv;
+        const int32_t zero_row = rd.n_real + nv;
+        std::vector<int32_t> v_off, v_slot;
+        int32_t vcount = 0;
+        for (int32_t i = 0; i < rd.n_real; ++i) {
+            const int32_t j = rows[i];
+            const int32_t off = off_of[j];
+            extra = std::max(extra, off + 1);
+            int32_t c01[2] = {zero_row, zero_row};
+            int32_t k = 0, nx = 0;
+            const int32_t xbeg = (int32_t)child.size() - rd.child_off;
+            for (int32_t e = t.child_off[j]; e < t.child_off[j + 1]; ++e, ++k) {
+                const int32_t ch = t.child[e];
+                int32_t idx;
+                if (!closed[ch]) idx = local[ch];
+                else { idx = rd.n_real + vcount++; v_off.push_back(off - 1); v_slot.push_back(slot_of[ch]); }
+                if (k < 2) c01[k] = idx;
+                else { child.push_back((uint16_t)idx); ++nx; }
+            }
+            row_reach.push_back(j); row_off.push_back(off);
+            row_c01.push_back(c01[0] | (c01[1] << 16));
+            row_nx.push_back(nx); row_xbeg.push_back(xbeg); row_slot.push_back(slot_of[j]);
+        }
         rd.n_child = (int32_t)child.size() - rd.child_off;
         for (int32_t v = 0; v < nv; ++v) {
             if (v_off[v] < 0) { err = "internal: lane skew offset below zero"; return false; }
-            row_reach.push_back(-1); row_off.push_back(v_off[v]); row_cbeg.push_back(rd.n_child); row_slot.push_back(v_slot[v]);
+            row_reach.push_back(-1); row_off.push_back(v_off[v]); row_c01.push_back(zero_row | (zero_row << 16));
+            row_nx.push_back(0); row_xbeg.push_back(0); row_slot.push_back(v_slot[v]);
         }
-        // sentinel closing the children list of the last row
-        row_reach.push_back(-1); row_off.push_back(0); row_cbeg.push_back(rd.n_child); row_slot.push_back(-1);
         rd.n_extra = extra;
         max_real = std::max(max_real, rd.n_real); max_virt = std::max(max_virt, rd.n_virt);
         max_child = std::max(max_child, rd.n_child); max_extra = std::max(max_extra, rd.n_extra);
-        if (region_bytes(rd.n_real, rd.n_virt, rd.n_child, mt) > smem_budget) { err = "internal: lane region over budget"; return false; }
+        const size_t bytes = region_bytes(rd.n_real, rd.n_virt, rd.n_child, mt);
+        max_bytes = std::max(max_bytes, bytes);
+        if (bytes > smem_budget || zero_row >= 65535) { err = "internal: lane region over budget"; return false; }
     }
     return true;
 }

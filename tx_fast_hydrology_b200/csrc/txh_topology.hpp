@@ -134,24 +134,29 @@ struct LaneRegionDesc {
     int32_t row_off;      // first entry of this region in the row arrays (real rows, then virtual rows)
     int32_t n_real;
     int32_t n_virt;
-    int32_t child_off;    // first entry in `child`
+    int32_t child_off;    // first entry in `child` (children beyond the two a row record carries inline)
     int32_t n_child;
     int32_t n_extra;      // largest skew offset + 1: iterations of a launch = nsteps + n_extra - 1
     int32_t height;       // level of the region in the region graph (0: depends on no other region)
     int32_t pad_;
 };
+constexpr int kLaneMaxRows = 896;    // rows of a region: one per thread of a 1,024-thread CTA, the rest mirror streams
 
 struct LaneSchedule {
     int mt = 0;                             // member tile the regions were sized for (1, 2, 4, 8, 16)
     int cap_rows = 0;
     size_t smem_budget = 0;
     std::vector<LaneRegionDesc> regions;    // ticket order
-    // per row (region-local order): reach id (-1: virtual), skew offset, first child (relative to the region's
-    // child_off; row r's children are [cbeg[r], cbeg[r+1]), the entry after the last real row closes the list),
-    // slot (real: stream the outflow is published to, or -1; virtual: stream it mirrors)
-    std::vector<int32_t> row_reach, row_off, row_cbeg, row_slot;
-    std::vector<uint16_t> child;            // region-local row indices
+    // per row (region-local order): reach id (-1: virtual), skew offset, the first two children c0 | c1 << 16
+    // (region-local rows; a missing child is the region's ZERO row, index n_real + n_virt), the number of further
+    // children and where they start in `child` (relative to the region's child_off), slot (real: stream the
+    // outflow is published to, or -1; virtual: stream it mirrors).
+    // Rows are ordered by (has further children, skew offset, position): the lanes of a warp then sit on (nearly)
+    // the same timestep, so their per-step records are one broadcast load and they change forcing bracket together.
+    std::vector<int32_t> row_reach, row_off, row_c01, row_nx, row_xbeg, row_slot;
+    std::vector<uint16_t> child;            // region-local row indices (children beyond the first two)
     int32_t n_slots = 0, max_real = 0, max_virt = 0, max_child = 0, max_extra = 0;
+    size_t max_bytes = 0;                   // shared memory of the largest region
 
     // bytes of shared memory a region of (real, virt, child) rows needs at member tile mt
     static size_t region_bytes(size_t real, size_t virt, size_t nchild, int mt);

@@ -367,30 +367,6 @@ __device__ __forceinline__ void segment_step(const WinArgs& a, const Tk& tk, InS
     }
 }
 
-// nutils.py:21-34: np.searchsorted(xp, x) (side='left'), clamped ends, linear weights or the nearer row
-__device__ __forceinline__ StepInterp interp_step(const double* __restrict__ times, int R, double x, int method)
-{
-    int lo = 0, hi = R;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (times[mid] < x) lo = mid + 1; else hi = mid;
-    }
-    StepInterp si;
-    if (lo == 0) { si.r0 = 0; si.r1 = 0; si.w0 = 1.0; si.w1 = 0.0; }
-    else if (lo >= R) { si.r0 = R - 1; si.r1 = R - 1; si.w0 = 1.0; si.w1 = 0.0; }
-    else {
-        const double dx_0 = __dsub_rn(x, times[lo - 1]), dx_1 = __dsub_rn(times[lo], x);
-        if (method == 1) {
-            const double frac = __ddiv_rn(dx_0, __dadd_rn(dx_0, dx_1));
-            si.r0 = lo - 1; si.r1 = lo; si.w0 = __dsub_rn(1.0, frac); si.w1 = frac;
-        } else {
-            const int r = fabs(dx_0) <= fabs(dx_1) ? lo - 1 : lo;
-            si.r0 = r; si.r1 = r; si.w0 = 1.0; si.w1 = 0.0;
-        }
-    }
-    return si;
-}
-
 // Shared-memory state of a task: ONE row per reach, p = beta*i + chi*o, the part of the next update that
 // depends on the old state (o' = alpha*inflow + (gamma*q + p)); the outflows and inflows themselves only
 // exist in registers, and are written to global memory in the last step of the launch.

@@ -370,6 +370,47 @@ class EnsembleKalmanFilter(_MeasurementTable, BaseCallback):
         self._Xall = None
         self.n_updates = 0
         self.datetime = copy.deepcopy(model.datetime)
+        # member-sharded ensembles: "peers" = the transform reads the other shards' state rows where they live
+        # (symmetric memory over NVLink, two buffers alternating), "allgather" = NCCL all-gather first
+        self.update_path = None
+        self._sym = None
+        if self.world > 1:
+            self.update_path = 'allgather'
+            import os
+            if os.environ.get('TXH_MEMBER_UPDATE', 'peers') == 'peers':
+                self._setup_peers()
+
+    def _setup_peers(self):
+        """Two symmetric-memory state buffers per rank (torch.distributed._symmetric_memory): every rank can load
+        from every other rank's buffers inside a kernel.  The model's outflow state moves into the first one.
+        Collective; any failure leaves the all-gather path in place."""
+        torch = self._torch
+        mdl = self.model
+        try:
+            import torch.distributed._symmetric_memory as symm
+            dist = torch.distributed
+            grp = self.group if self.group is not None else dist.group.WORLD
+            mdl._ensure_device()
+            O = mdl._dev['O']
+            bufs = []
+            for _ in range(2):
+                t = symm.empty(tuple(O.shape), dtype=torch.float64, device=O.device)
+                hdl = symm.rendezvous(t, grp)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                if len(ptrs) != self.world or ptrs[self.rank] != t.data_ptr():
+                    raise RuntimeError('unexpected symmetric-memory layout')
+                bufs.append((t, ptrs, hdl))
+            ok = torch.ones(1, device=O.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if float(ok.item()) != 1.0:
+                raise RuntimeError('a peer could not set up symmetric memory')
+            bufs[0][0].copy_(O)
+            mdl._dev['O'] = bufs[0][0]
+            self._sym, self._cur = bufs, 0
+            self.update_path = 'peers'
+        except Exception as e:                    # noqa: BLE001 -- optional fast path: report and carry on
+            logger.warning('member-sharded update falls back to all-gather: %s', e)
+            self._sym = None
 
     @property
     def latest_timestamp(self):
@@ -410,6 +451,11 @@ class EnsembleKalmanFilter(_MeasurementTable, BaseCallback):
         mdl = self.model
         net = mdl.network
         O, I = mdl.device_state
+        if self._sym is not None and O is not self._sym[self._cur][0]:
+            # the state was rebound to another tensor: bring it back into the shared buffer BEFORE the all-reduce
+            # below, which orders it ahead of every peer's transform
+            self._sym[self._cur][0].copy_(O)
+            mdl._dev['O'] = O = self._sym[self._cur][0]
         M, Mt, m = self.M, self.Mtot, self.num_measurements
         if Zp_dev is None:
             Zp_dev = torch.as_tensor(self.perturbed_observations(mdl.datetime), device='cuda')
@@ -419,6 +465,22 @@ class EnsembleKalmanFilter(_MeasurementTable, BaseCallback):
                        scale=self.stats_scale())
         Xall, ldx, xstride, gather = None, 0, 0, None
         mean = self._rowsum
+        if self.world > 1 and self._sym is not None:
+            # The all-reduce of the row sums doubles as the cross-GPU barrier: once it has completed on this
+            # rank, every rank's forecast (written before its contribution, in stream order) is final, and every
+            # rank has left the previous update, i.e. nobody reads the buffer this update is about to overwrite.
+            cur, nxt = self._sym[self._cur], self._sym[self._cur ^ 1]
+            mean, self._HXall = combine_statistics(self._rowsum, self._HX, Mt, group=self.group)
+            net.enkf_solve(m, Mt, self._HXall, Zp_dev, mean, self.reach_indices, self._qs, self._R, self._work,
+                           self._W, self._T, self._Dinv, self._dinv_kind)
+            net.enkf_apply_peers(cur[0], nxt[0], I, M, cur[1], Mt, self.rank * M, mean, self._T, self.reach_indices,
+                                 self._qs, self._W, self._G)
+            mdl._dev['O'] = nxt[0]
+            self._cur ^= 1
+            mdl._device_advanced()
+            self.n_updates += 1
+            self.datetime = mdl.datetime
+            return
         if self.world > 1:
             # ensemble mean over all shards (all-reduce) + every shard's gauge rows (all-gather); the state rows
             # of every shard follow on the collective stream while the small system is solved

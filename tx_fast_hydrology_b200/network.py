@@ -211,7 +211,7 @@ class RiverNetwork:
         keys = ["n_regions", "n_rows", "n_child", "n_slots", "max_real", "max_virt", "max_extra", "member_tile"]
         d = dict(zip(keys, (int(x) for x in info)))
         regions = np.empty((d["n_regions"], 8), dtype=np.int32)
-        rows = np.empty((max(1, d["n_rows"]), 4), dtype=np.int32)
+        rows = np.empty((max(1, d["n_rows"]), 6), dtype=np.int32)
         child = np.empty(max(1, d["n_child"]), dtype=np.int32)
         L.check(self._lib.txh_get_lane_schedule(self.handle, int(M), regions.ctypes.data_as(L.p_i32),
                                                 rows.ctypes.data_as(L.p_i32), child.ctypes.data_as(L.p_i32)))
@@ -377,6 +377,16 @@ class RiverNetwork:
                                          int(x_block_stride), int(Mtot),
                                          int(col0), _cuda_ptr(mean), _cuda_ptr(T), L.ptr_i64(idx), idx.size,
                                          _cuda_ptr(qs), _cuda_ptr(W), _cuda_ptr(G), _stream_ptr()))
+
+    def enkf_apply_peers(self, O_in, O_out, I, Mloc, shard_ptrs, Mtot, col0, mean, T, obs_reach, qs, W, G):
+        """`txh_enkf_apply_peers`: the shards' state matrices (`shard_ptrs`: device addresses, one per rank, peers
+        mapped over NVLink) are read in place; the posterior of this shard goes to `O_out`."""
+        idx = L.as_i64(obs_reach)
+        arr = (ctypes.c_void_p * len(shard_ptrs))(*[int(p) for p in shard_ptrs])
+        L.check(self._lib.txh_enkf_apply_peers(self.handle, _cuda_ptr(O_in), _cuda_ptr(O_out), _cuda_ptr(I), int(Mloc),
+                                               arr, len(shard_ptrs), int(Mtot), int(col0), _cuda_ptr(mean), _cuda_ptr(T),
+                                               L.ptr_i64(idx), idx.size, _cuda_ptr(qs), _cuda_ptr(W), _cuda_ptr(G),
+                                               _stream_ptr()))
 
     def check(self):
         L.check(self._lib.txh_check(self.handle, _stream_ptr() if self._has_cuda() else None))
