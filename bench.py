@@ -766,6 +766,10 @@ def c3_arm(a, rank, world, local, full):
         "update_path": getattr(enkf, "update_path", None),
     }
     forcing.close()
+    path = getattr(enkf, "update_path", None)
+    line["update_path"] = path
+    if hasattr(enkf, "release_peers"):
+        enkf.release_peers()                              # collective: peers may still read this rank's state buffers
     del mdl, enkf, O0, I0, flush, Zp_dev
     torch.cuda.empty_cache()
     return line

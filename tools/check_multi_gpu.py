@@ -4,14 +4,18 @@
         tools/check_multi_gpu.py
 
 Every rank routes its M members of a synthetic network for a few hourly windows with an EnKF update after each
-(statistics combined over NCCL); rank 0 also runs all N*M members unsharded and compares the gathered shards
-with it (FP64 max relative error <= 1e-9)."""
+(row sums all-reduced and gauge rows all-gathered over NCCL; the transform reads the other shards' state rows in
+place over NVLink -- TXH_MEMBER_UPDATE=peers, the default -- or after an NCCL all-gather -- =allgather); rank 0
+also runs all N*M members unsharded and compares the gathered shards with it (FP64, element-wise relative error
+<= 1e-9 with the forecast-scale floor of tests/parity.py).  Both update paths are run."""
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
@@ -45,33 +49,46 @@ def main():
     q = rng.uniform(0.5, 2.0, size=n)
     Zp = np.ascontiguousarray(meas[:, :, None] + 0.1 * rng.standard_normal((nwin, m, Mt)))
 
+    from parity import relerr
+
     def run(cols, group):
         d = dict(d0); d["o_t"] = np.ascontiguousarray(o_all[:, cols])
         mdl = Muskingum(d, members=len(cols))
         enkf = EnsembleKalmanFilter(mdl, mdf, q, R, group=group)
+        path = enkf.update_path
         f = mdl.make_forcing(times_ns=times, table=table, member_mul=np.ascontiguousarray(mul_all[:, cols]))
         mdl.run_assimilating(f, every * nwin, enkf, every, torch.as_tensor(Zp[:, :, :enkf.Mtot], device="cuda"))
         mdl.network.check()
-        return mdl.o_t_next.reshape(n, -1), mdl.i_t_next.reshape(n, -1)
+        enkf.release_peers()                                         # collective on the peer-read path
+        return mdl.o_t_next.reshape(n, -1), mdl.i_t_next.reshape(n, -1), path
 
-    cols = list(range(rank * M, (rank + 1) * M))
-    o_loc, i_loc = run(cols, None)                                   # sharded: default group = all ranks
-    parts = [torch.empty((n, 2 * M), dtype=torch.float64, device="cuda") for _ in range(world)] if rank == 0 else None
-    mine = torch.as_tensor(np.concatenate([o_loc, i_loc], axis=1), device="cuda")
-    dist.gather(mine, parts, dst=0)
     ok = True
+    cols = list(range(rank * M, (rank + 1) * M))
+    o_ref = i_ref = None
     if rank == 0:
-        o_ref, i_ref = run(list(range(Mt)), singles[0])             # the whole ensemble on one GPU
-        o_sh = np.concatenate([p.cpu().numpy()[:, :M] for p in parts], axis=1)
-        i_sh = np.concatenate([p.cpu().numpy()[:, M:] for p in parts], axis=1)
-        eo = float(np.abs(o_sh - o_ref).max() / np.abs(o_ref).max())
-        ei = float(np.abs(i_sh - i_ref).max() / np.abs(i_ref).max())
-        ok = eo <= 1e-9 and ei <= 1e-9
-        print(f"multi-GPU check: world={world} members={Mt} n={n}  max rel err o={eo:.2e} i={ei:.2e}  {'OK' if ok else 'FAIL'}",
-              flush=True)
-    dist.barrier()
+        o_ref, i_ref, _ = run(list(range(Mt)), singles[0])          # the whole ensemble on one GPU
+    for want in ("peers", "allgather"):
+        os.environ["TXH_MEMBER_UPDATE"] = want
+        o_loc, i_loc, path = run(cols, None)                         # sharded: default group = all ranks
+        parts = [torch.empty((n, 2 * M), dtype=torch.float64, device="cuda") for _ in range(world)] if rank == 0 else None
+        mine = torch.as_tensor(np.concatenate([o_loc, i_loc], axis=1), device="cuda")
+        dist.gather(mine, parts, dst=0)
+        if rank == 0:
+            o_sh = np.concatenate([p.cpu().numpy()[:, :M] for p in parts], axis=1)
+            i_sh = np.concatenate([p.cpu().numpy()[:, M:] for p in parts], axis=1)
+            # posterior elements are sums o + gain that may cancel: relative to max(|element|, ensemble scale of the row)
+            so = np.abs(o_ref).max(axis=1, keepdims=True) * np.ones_like(o_ref)
+            si = np.abs(i_ref).max(axis=1, keepdims=True) * np.ones_like(i_ref)
+            eo, ei = relerr(o_sh, o_ref, scale=so), relerr(i_sh, i_ref, scale=si)
+            good = eo <= 1e-9 and ei <= 1e-9 and path == want
+            ok = ok and good
+            print(f"multi-GPU check: world={world} members={Mt} n={n} update_path={path} (asked {want})  "
+                  f"max rel err o={eo:.2e} i={ei:.2e}  {'OK' if good else 'FAIL'}", flush=True)
+        dist.barrier()
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.broadcast(flag, src=0)
     dist.destroy_process_group()
-    return 0 if ok else 1
+    return 0 if float(flag.item()) == 1.0 else 1
 
 
 if __name__ == "__main__":

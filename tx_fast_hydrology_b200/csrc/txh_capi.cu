@@ -95,6 +95,7 @@ struct txh_net {
     LaneDev lane[5];                    // member tiles 1, 2, 4, 8, 16
     int lane_max_members = 8;           // ensembles up to this size take the lane kernel
     int lane_cap_rows = 0;              // rows per region; 0 = from the size of the network and the SM count
+    int lane_ctas = 4;                  // regions (CTAs) per SM the schedule is sized for
     double* d_lring = nullptr; size_t lring_cap = 0;
     double* d_stage = nullptr; size_t stage_cap = 0;   // reach-order staging of txh_pack_host / txh_unpack_host
     double* stats_rowsum = nullptr;     // txh_set_stats_output: row sums of the final outflows of every routing call
@@ -163,6 +164,7 @@ int ensure_device(txh_net* net)
     }
     if (const char* k = getenv("TXH_LANE_MAX_M")) net->lane_max_members = std::max(0, std::min(16, atoi(k)));
     if (const char* k = getenv("TXH_LANE_CAP")) net->lane_cap_rows = std::max(0, atoi(k));
+    if (const char* k = getenv("TXH_LANE_CTAS")) net->lane_ctas = std::max(1, std::min(8, atoi(k)));
     CU(cudaMalloc((void**)&net->d_coef, sizeof(double) * (6 * net->topo.n + net->sched.link_last.size() + 1)));
     CU(cudaMalloc((void**)&net->d_qtmp, sizeof(double) * net->topo.n));
     CU(cudaMalloc((void**)&net->d_qctl, 64));
@@ -475,12 +477,19 @@ txh_net::LaneDev* lane_schedule(txh_net* net, int ti, int num_sms)
         if (net->lane_cap_rows > 0) {
             L.ok = L.sched.build(net->topo, net->sched.pos_of_reach, 1 << ti, net->lane_cap_rows, kLaneSmemBudget, side_min, err);
         } else {
-            const int64_t per_sm = (net->topo.n + num_sms - 1) / std::max(1, num_sms);
-            int cap = (int)std::min<int64_t>(kLaneMaxRows, std::max<int64_t>(320, per_sm + per_sm / 50));
+            // An iteration of a region is bound by the dependent-instruction chain of one warp between two barriers
+            // (~1 us whatever the size of the region), so several small regions per SM -- independent barrier domains
+            // that overlap each other's latency -- beat one large one: lane_ctas regions per SM (default 4), all
+            // resident at once while the network is small enough.
+            const int ctas = std::max(1, net->lane_ctas);
+            const int cap_max = std::max(64, 1024 / ctas - 48);            // threads of a CTA = rows + stream mirrors
+            const int64_t slots = (int64_t)num_sms * ctas;
+            const int64_t per = (net->topo.n + slots - 1) / slots;
+            int cap = (int)std::min<int64_t>(cap_max, std::max<int64_t>(96, per + per / 50));
             for (;;) {
                 L.ok = L.sched.build(net->topo, net->sched.pos_of_reach, 1 << ti, cap, kLaneSmemBudget, side_min, err);
-                if (!L.ok || (int)L.sched.regions.size() <= num_sms || cap >= kLaneMaxRows) break;
-                cap = std::min(kLaneMaxRows, cap + std::max(8, cap / 12));
+                if (!L.ok || (int64_t)L.sched.regions.size() <= slots || cap >= cap_max) break;
+                cap = std::min(cap_max, cap + std::max(4, cap / 12));
             }
         }
         L.built = true;
@@ -545,14 +554,25 @@ int run_lane(txh_net* net, double* O, double* I, int64_t M, const double* F, con
     }
     // shared memory: the largest region (every CTA lays its region out itself, LaneSchedule::region_bytes)
     LaneArgs a{};
-    const size_t smem = s.max_bytes + 16;
+    size_t smem = (s.max_bytes + 31) & ~size_t(15);
     if (smem > 227 * 1024) return 1;
+    // the per-step interpolation records ride in shared memory too when they fit
+    if (plan.times && smem + 32 * (size_t)spl <= 200 * 1024) { a.off_steps = (int32_t)smem; smem += 32 * (size_t)spl; }
+    a.lag = 32;
+    if (const char* k = getenv("TXH_LANE_LAG")) a.lag = std::max(24, std::min(4096, atoi(k)));
+    a.vote_every = 64;
+    if (const char* k = getenv("TXH_LANE_VOTE_EVERY")) { const int v = atoi(k); if (v > 0 && (v & (v - 1)) == 0) a.vote_every = v; }
     const int tv = s.max_virt > 0 ? std::min(128, (s.max_virt + 31) / 32 * 32) : 0;
     const int tr = (s.max_real + 31) / 32 * 32;                            // one row per thread
     if (tr + tv > 1024) return 1;
     a.TR = tr;
     const int threads = tr + tv;
-    const int grid = std::min<int>(net->num_sms, (int)s.regions.size());
+    // every CTA of the grid must be resident (a region waits for regions claimed before it): ask the runtime how many
+    // CTAs of this shape fit an SM
+    int per_sm = 1;
+    CU(lane_occupancy(mt, F != nullptr, W != nullptr, threads, smem, &per_sm));
+    if (per_sm < 1) return 1;
+    const int grid = (int)std::min<int64_t>((int64_t)net->num_sms * per_sm, (int64_t)s.regions.size());
     for (int64_t s0 = 0; s0 < nsteps; s0 += spl) {
         const int64_t ns = std::min<int64_t>(spl, nsteps - s0);
         if (plan.times) {
@@ -570,7 +590,29 @@ int run_lane(txh_net* net, double* O, double* I, int64_t M, const double* F, con
         a.n = net->topo.n; a.n_regions = (int32_t)s.regions.size(); a.nsteps = (int32_t)ns;
         a.splp = (int32_t)((ns + 15) & ~int64_t(15)); a.ld = ld; a.M = (int32_t)M; a.wm_ld = wm_ld;
         a.R = plan.times ? (int32_t)plan.R : 1;
+        // development aid: TXH_LANE_TRACE=<file> dumps the region timeline of this launch (synchronous)
+        const char* trace_file = getenv("TXH_LANE_TRACE");
+        unsigned long long* d_trace = nullptr;
+        const size_t trace_words = 8 * s.regions.size();
+        if (trace_file && *trace_file) {
+            CU(cudaMalloc((void**)&d_trace, trace_words * sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(d_trace, 0, trace_words * sizeof(unsigned long long), st));
+            a.trace = d_trace;
+        }
         CU(launch_route_lane(a, mt, threads, smem, grid, st));
+        if (d_trace) {
+            std::vector<unsigned long long> h(trace_words);
+            CU(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            CU(cudaFree(d_trace));
+            if (FILE* fp = fopen(trace_file, "wb")) {
+                const long long hd[4] = {(long long)s.regions.size(), (long long)ns, (long long)threads, (long long)grid};
+                fwrite(hd, sizeof(hd), 1, fp);
+                fwrite(s.regions.data(), sizeof(LaneRegionDesc), s.regions.size(), fp);
+                fwrite(h.data(), sizeof(unsigned long long), h.size(), fp);
+                fclose(fp);
+            }
+        }
     }
     return TXH_OK;
 }

@@ -152,6 +152,11 @@ struct LaneArgs {
     int64_t n;
     int32_t n_regions, nsteps, splp, ld, M, wm_ld, R, rec_every, rec_count;
     int32_t TR;                           // threads [0, TR) own real rows, the rest the virtual rows
+    int32_t off_steps;                    // > 0: the per-step records are staged in shared memory at this offset
+    int32_t vote_every;                   // power of two: iterations between barrier votes on abandoning the launch
+    int32_t lag;                          // steps a producer region is ahead before its consumer starts / resumes
+    unsigned long long* trace;            // optional [n_regions][8]: claim, loaded, last lag wait over, end (ns), iterations,
+                                          // SM, slow-path polls, -- ; nullptr = off
 };
 
 struct LevelArgs {
@@ -172,6 +177,7 @@ cudaError_t launch_route_level(const LevelArgs& a, cudaStream_t st);
 cudaError_t launch_window_init(const InitArgs& a, unsigned long long* ticket, cudaStream_t st);
 cudaError_t launch_route_window(const WinArgs& a, int warps_per_cta, int num_sms, cudaStream_t st);
 cudaError_t launch_route_lane(const LaneArgs& a, int mt, int threads, size_t smem, int grid, cudaStream_t st);
+cudaError_t lane_occupancy(int mt, bool f, bool w, int threads, size_t smem, int* per_sm);
 cudaError_t launch_lane_init(const InitArgs& a, LaneStep* out, unsigned long long* ticket, cudaStream_t st);
 cudaError_t launch_init_inflows(const int32_t* up_off, const int32_t* up_pos, const uint8_t* is_outlet,
                                 const double* O, double* I, int64_t n, int ld, int M, cudaStream_t st);

@@ -14,9 +14,9 @@
 //     inflow = sum of the upstream outflows               (shared-memory gathers, fixed child order)
 //     o' = alpha*inflow + (p + gamma*q),   p' = beta*inflow + chi*o'      (p = beta*i + chi*o of the old state)
 // Outflows crossing regions travel through streams ring[slot][member][step] in global memory: an unwritten
-// cell holds EMPTY (all bits set); the consumer mirrors a stream as a virtual row, stays kLag steps behind its
-// producer so that its cp.async prefetches (two 8-step batches ahead) always find data, polls a cell that is
-// still EMPTY, and puts EMPTY back.  Regions are claimed in a
+// cell holds EMPTY (all bits set); the consumer mirrors a stream as a virtual row, stays `lag` steps behind its
+// producer so that its cp.async prefetches (two 8-step batches ahead) find data -- whenever it catches up it falls
+// back by `lag` steps again -- and puts EMPTY back into every cell it has consumed.  Regions are claimed in a
 // topological order, so a region only waits for regions that are running or done (every CTA is resident).
 // The forcing is interpolated per step exactly as nutils.py:21-34 does; its bracket rows live in shared
 // memory and the next row is prefetched (cp.async) one bracket ahead.
@@ -56,11 +56,10 @@ __device__ __forceinline__ double empty_cell() { return __longlong_as_double(-1l
 // Streams are read in batches of kBatch steps (64 bytes), prefetched TWO batches ahead with cp.async into a
 // four-batch window in shared memory.  Producer and consumer regions advance at the same rate, so a consumer
 // that started right behind its producer would find every prefetch EMPTY and pay a trip to L2 per step; it
-// therefore waits once, before its first step, until the producer is kLag steps ahead (or done), and every
+// therefore waits once, before its first step, until the producer is `lag` steps ahead (or done), and every
 // later prefetch lands on cells that are already written.
 constexpr int kBatch = 8;
 constexpr int kExtCells = 4 * kBatch;      // shared-memory window of a stream
-constexpr int kLag = 48;                   // steps a producer is ahead before its consumer starts
 
 // ---- shared memory through 32-bit shared-space addresses (no generic-address arithmetic in the loop) ----
 __device__ __forceinline__ int4 lds_i4(unsigned a)
@@ -148,6 +147,8 @@ route_lane_kernel(const LaneArgs a)
     const int nsteps = a.nsteps, M = a.M, ld = a.ld;
     const size_t splp = (size_t)a.splp;
     bool abandon = false;                                      // watchdog / poisoned handle: decided by a barrier vote
+    int first_region = -1;
+    const int vote_mask = a.vote_every - 1;                    // barrier votes on abandoning: every vote_every-th iteration
 
     for (;;) {
         if (tid == 0) {
@@ -157,8 +158,11 @@ route_lane_kernel(const LaneArgs a)
         __syncthreads();
         const int reg = sRegion;
         if (reg < 0) break;
+        if (first_region < 0) first_region = reg;              // the step records are staged once per CTA
         const LaneRegionDesc rd = a.regions[reg];
         const int nr = rd.n_real, nv = rd.n_virt;
+        unsigned long long* tr = a.trace ? a.trace + 8 * (size_t)reg : nullptr;    // development aid: region timeline
+        if (tr && tid == 0) tr[0] = globaltimer_ns();
         // shared-memory layout of this region (LaneSchedule::region_bytes)
         const int rv = nr + nv + 1;                            // rows of an outflow buffer: real, virtual, ZERO
         const unsigned sOb = sbase;                            // [2][MT][rv] outflows of this / the previous iteration
@@ -166,6 +170,7 @@ route_lane_kernel(const LaneArgs a)
         const unsigned sMetaV = sExt + 256u * MT * nv;         // [nv] records of the virtual rows
         const unsigned sChild = sMetaV + 16u * nv;             // children beyond the first two
         const unsigned sP = sChild + (((unsigned)(2 * rd.n_child)) + 15u & ~15u);   // [MT][nr] (MT > 4 only)
+        const unsigned sSteps = sbase + a.off_steps;           // [nsteps] per-step records (when they fit)
         // ---- this thread's row ----------------------------------------------------------------------------
         const bool has_row = tid < nr;
         int off = 0, nx = 0, slot = -1, pos = 0, rec = -1;
@@ -206,6 +211,10 @@ route_lane_kernel(const LaneArgs a)
             for (int i = tid; i < rd.n_child; i += blockDim.x) sts_u16(sChild + 2u * i, gc[i]);
             // the ZERO row of both buffers: what a missing child reads
             for (int i = tid; i < 2 * MT; i += blockDim.x) sts_d(sOb + 8u * ((unsigned)i * rv + (nr + nv)), 0.0);
+            if (HAS_F && a.off_steps > 0 && reg == first_region) {
+                const int4* gs = reinterpret_cast<const int4*>(a.steps);
+                for (int i = tid; i < 2 * nsteps; i += blockDim.x) sts_i4(sSteps + 16u * i, gs[i]);
+            }
         }
         if (tid >= TR) {
             // the first two batches of every incoming stream (most likely still EMPTY: fetched again after the lag wait)
@@ -224,6 +233,7 @@ route_lane_kernel(const LaneArgs a)
 
         const int niter = nsteps + rd.n_extra - 1;
         const unsigned ra = 8u * (unsigned)tid;                 // this row's cell in an outflow buffer
+        if (tr && tid == 0) { tr[1] = globaltimer_ns(); tr[4] = (unsigned long long)niter; tr[6] = 0ull; tr[7] = 0ull; }
         int dead = 0;
         for (int k = 0; k < niter; ++k) {
             const unsigned obp = sOb + 8u * (unsigned)(((k & 1) ^ 1) * MT * rv);
@@ -233,12 +243,24 @@ route_lane_kernel(const LaneArgs a)
                 double w0 = 0.0, w1 = 0.0;
                 int fr0 = 0, fr1 = 0;
                 if (HAS_F) {
-                    const LaneStep* st = a.steps + s;
-                    const double2 ww = *reinterpret_cast<const double2*>(&st->w0);
-                    const int2 rr = *reinterpret_cast<const int2*>(&st->r0);
-                    w0 = ww.x; w1 = ww.y; fr0 = rr.x; fr1 = rr.y & 0x7fffffff;
-                    if (rr.y < 0)                                // the bracket differs from the previous step's
-                        rotate_bracket(f0, f1, fn, a.F + pos, a.n, a.R, __ldg(&st[-1].r0), __ldg(&st[-1].r1) & 0x7fffffff, fr0, fr1);
+                    int r1f;
+                    if (a.off_steps > 0) {
+                        const double2 ww = lds_d2(sSteps + 32u * s);
+                        const int4 rr = lds_i4(sSteps + 32u * s + 16u);
+                        w0 = ww.x; w1 = ww.y; fr0 = rr.x; r1f = rr.y;
+                    } else {
+                        const LaneStep* st = a.steps + s;
+                        const double2 ww = *reinterpret_cast<const double2*>(&st->w0);
+                        const int2 rr = *reinterpret_cast<const int2*>(&st->r0);
+                        w0 = ww.x; w1 = ww.y; fr0 = rr.x; r1f = rr.y;
+                    }
+                    fr1 = r1f & 0x7fffffff;
+                    if (r1f < 0) {                               // the bracket differs from the previous step's
+                        int pr0, pr1;
+                        if (a.off_steps > 0) { const int4 pp = lds_i4(sSteps + 32u * (s - 1) + 16u); pr0 = pp.x; pr1 = pp.y; }
+                        else { pr0 = __ldg(&a.steps[s - 1].r0); pr1 = __ldg(&a.steps[s - 1].r1); }
+                        rotate_bracket(f0, f1, fn, a.F + pos, a.n, a.R, pr0, pr1 & 0x7fffffff, fr0, fr1);
+                    }
                 }
                 double q = 0.0;
                 if (HAS_F && !HAS_W) q = ga * (w0 * f0 + w1 * f1);
@@ -283,36 +305,45 @@ route_lane_kernel(const LaneArgs a)
                     const int4 mt = lds_i4(sMetaV + 16u * v);
                     const int sv = k - (mt.y & 0xffff);
                     if ((unsigned)sv >= (unsigned)nsteps) continue;
-                    if ((sv & (kBatch - 1)) == 0) {
-                        if (sv == 0) {
-                            // let the producer get kLag steps ahead (or finish), then fetch the first two batches anew
-                            const int need = min(nsteps, kLag) - 1;
-                            const double* g0 = a.ring + (size_t)mt.w * M * splp;
-                            unsigned spins = 0;
-                            unsigned long long t0 = 0;
-                            while (!dead && is_empty(ld_relaxed_f64(g0 + need))) {
-                                if ((++spins & 15u) == 0) {
-                                    if (ld_relaxed_s32(a.status) != 0) { dead = 1; break; }
-                                    const unsigned long long now = globaltimer_ns();
-                                    if (t0 == 0) t0 = now;
-                                    else if (now - t0 > a.watchdog_ns) { atomicExch(a.status, 1); dead = 1; break; }
-                                }
-                                __nanosleep(200);
+                    const double* g0 = a.ring + (size_t)mt.w * M * splp;
+                    const unsigned ex0 = sExt + 256u * ((unsigned)v * MT);
+                    // Wait until the producer is `lag` steps ahead of step `from` (or has finished), then fetch the
+                    // batch of `from` and the two after it.  Used before the first step and whenever the consumer has
+                    // caught up with its producer: consumers then advance in bursts at full speed instead of paying a
+                    // trip to L2 per step at the producer's heels (which would compound along a chain of regions).
+                    auto lag_and_fetch = [&](int from) {
+                        const int need = min(nsteps, from + a.lag) - 1;
+                        unsigned spins = 0;
+                        unsigned long long t0 = 0;
+                        while (!dead && is_empty(ld_relaxed_f64(g0 + need))) {
+                            if ((++spins & 15u) == 0) {
+                                if (ld_relaxed_s32(a.status) != 0) { dead = 1; break; }
+                                const unsigned long long now = globaltimer_ns();
+                                if (t0 == 0) t0 = now;
+                                else if (now - t0 > a.watchdog_ns) { atomicExch(a.status, 1); dead = 1; break; }
                             }
-                            cp_async_wait_all();
-                            for (int m = 0; m < M; ++m) {
-                                const unsigned ex = sExt + 256u * ((unsigned)v * MT + m);
-                                const double* g = a.ring + ((size_t)mt.w * M + m) * splp;
-#pragma unroll
-                                for (int q = 0; q < kBatch; ++q) cp_async16_s(ex + 16u * q, g + 2 * q);
-                            }
-                            cp_async_commit();
+                            __nanosleep(200);
                         }
+                        cp_async_wait_all();                                 // older prefetches must not land on top of this
+                        const int b0 = from & ~(kBatch - 1);
+                        for (int m = 0; m < M; ++m)
+#pragma unroll
+                            for (int q = 0; q < 3 * kBatch / 2; ++q) {
+                                const int c = b0 + 2 * q;
+                                if (c < (int)splp) cp_async16_s(ex0 + 256u * m + 8u * (c & (kExtCells - 1)), g0 + (size_t)m * splp + c);
+                            }
+                        cp_async_commit();
+                        cp_async_wait_all();
+                    };
+                    if (sv == 0) {
+                        lag_and_fetch(0);
+                        if (tr) atomicMax(tr + 2, globaltimer_ns());           // last first-step lag wait of the region over
+                    } else if ((sv & (kBatch - 1)) == 0) {
                         cp_async_wait_all();                                 // batches sv/8 and sv/8 + 1 are in the window
                         if (sv + 2 * kBatch < nsteps) {
                             for (int m = 0; m < M; ++m) {
-                                const unsigned ex = sExt + 256u * ((unsigned)v * MT + m) + 8u * ((sv + 2 * kBatch) & (kExtCells - 1));
-                                const double* g = a.ring + ((size_t)mt.w * M + m) * splp + sv + 2 * kBatch;
+                                const unsigned ex = ex0 + 256u * m + 8u * ((sv + 2 * kBatch) & (kExtCells - 1));
+                                const double* g = g0 + (size_t)m * splp + sv + 2 * kBatch;
 #pragma unroll
                                 for (int q = 0; q < kBatch / 2; ++q) cp_async16_s(ex + 16u * q, g + 2 * q);
                             }
@@ -321,12 +352,16 @@ route_lane_kernel(const LaneArgs a)
                     }
                     for (int m = 0; m < M; ++m) {
                         double* cell = a.ring + ((size_t)mt.w * M + m) * splp + sv;
-                        double val = lds_d(sExt + 256u * ((unsigned)v * MT + m) + 8u * (sv & (kExtCells - 1)));
+                        const unsigned ea = ex0 + 256u * m + 8u * (sv & (kExtCells - 1));
+                        double val = lds_d(ea);
                         if (is_empty(val)) {
-                            // the prefetch came too early: poll the cell itself
+                            // caught up with the producer: fall back by `lag` steps, then continue from the window
+                            if (tr) atomicAdd(tr + 6, 1ull);
+                            lag_and_fetch(sv);
+                            val = lds_d(ea);
                             unsigned spins = 0, nap = 32;
                             unsigned long long t0 = 0;
-                            for (;;) {
+                            while (is_empty(val)) {                          // (stores to different cells may land out of order)
                                 val = ld_relaxed_f64(cell);
                                 if (!is_empty(val)) break;
                                 if ((++spins & 15u) == 0) {
@@ -344,9 +379,19 @@ route_lane_kernel(const LaneArgs a)
                     }
                 }
             }
-            if (__syncthreads_or(dead)) { abandon = true; break; }   // also the barrier between two iterations
+            // the barrier between two iterations; every vote_every-th one also votes on abandoning the launch
+            if ((k & vote_mask) == vote_mask || k + 1 == niter) {
+                if (__syncthreads_or(dead)) { abandon = true; break; }
+            } else {
+                __syncthreads();
+            }
         }
         cp_async_wait_all();
+        if (tr && tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            tr[3] = globaltimer_ns(); tr[5] = smid;
+        }
         if (abandon) break;
     }
     // the last CTA to leave re-arms the ticket for the next launch on this handle
@@ -393,6 +438,35 @@ cudaError_t launch_mt(const LaneArgs& a, int threads, size_t smem, int grid, cud
     return cudaGetLastError();
 }
 
+
+
+template <int MT>
+cudaError_t occupancy_mt(bool f, bool w, int threads, size_t smem, int* per_sm)
+{
+    void (*kern)(const LaneArgs) = nullptr;
+    if (!f) kern = route_lane_kernel<MT, false, false>;
+    else if (!w) kern = route_lane_kernel<MT, true, false>;
+    else kern = route_lane_kernel<MT, true, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, threads, smem);
+}
+
+}  // namespace
+
+cudaError_t lane_occupancy(int mt, bool f, bool w, int threads, size_t smem, int* per_sm)
+{
+    switch (mt) {
+        case 1: return occupancy_mt<1>(f, w, threads, smem, per_sm);
+        case 2: return occupancy_mt<2>(f, w, threads, smem, per_sm);
+        case 4: return occupancy_mt<4>(f, w, threads, smem, per_sm);
+        case 8: return occupancy_mt<8>(f, w, threads, smem, per_sm);
+        case 16: return occupancy_mt<16>(f, w, threads, smem, per_sm);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+namespace {
 }  // namespace
 
 cudaError_t launch_lane_init(const InitArgs& a, LaneStep* out, unsigned long long* ticket, cudaStream_t st)

@@ -412,6 +412,21 @@ class EnsembleKalmanFilter(_MeasurementTable, BaseCallback):
             logger.warning('member-sharded update falls back to all-gather: %s', e)
             self._sym = None
 
+    def release_peers(self):
+        """Collective.  A member-sharded filter on the peer-read path owns buffers other ranks load from inside
+        their kernels: before it goes away every rank must have finished its last update.  Synchronises the
+        device, meets the other ranks at a barrier, and moves the state back into an ordinary tensor."""
+        if self._sym is None:
+            return
+        torch = self._torch
+        torch.cuda.synchronize()
+        torch.distributed.barrier(group=self.group)
+        mdl = self.model
+        if mdl._dev is not None:
+            mdl._dev['O'] = mdl._dev['O'].clone()
+        self._sym = None
+        self.update_path = 'allgather'
+
     @property
     def latest_timestamp(self):
         return self.measurements.index[-1]
