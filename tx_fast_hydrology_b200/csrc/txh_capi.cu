@@ -95,7 +95,7 @@ struct txh_net {
     LaneDev lane[5];                    // member tiles 1, 2, 4, 8, 16
     int lane_max_members = 8;           // ensembles up to this size take the lane kernel
     int lane_cap_rows = 0;              // rows per region; 0 = from the size of the network and the SM count
-    int lane_ctas = 4;                  // regions (CTAs) per SM the schedule is sized for
+    int lane_ctas = 1;                  // regions (CTAs) per SM the schedule is sized for (measured: 1 is best)
     double* d_lring = nullptr; size_t lring_cap = 0;
     double* d_stage = nullptr; size_t stage_cap = 0;   // reach-order staging of txh_pack_host / txh_unpack_host
     double* stats_rowsum = nullptr;     // txh_set_stats_output: row sums of the final outflows of every routing call
@@ -477,10 +477,9 @@ txh_net::LaneDev* lane_schedule(txh_net* net, int ti, int num_sms)
         if (net->lane_cap_rows > 0) {
             L.ok = L.sched.build(net->topo, net->sched.pos_of_reach, 1 << ti, net->lane_cap_rows, kLaneSmemBudget, side_min, err);
         } else {
-            // An iteration of a region is bound by the dependent-instruction chain of one warp between two barriers
-            // (~1 us whatever the size of the region), so several small regions per SM -- independent barrier domains
-            // that overlap each other's latency -- beat one large one: lane_ctas regions per SM (default 4), all
-            // resident at once while the network is small enough.
+            // lane_ctas regions per SM, all resident at once while the network is small enough.  Measured on B200
+            // (profiles/r02_lane_sweeps.jsonl): the SM's issue rate is set by warps x their dependent-instruction
+            // chains, not by the size of a barrier domain, so one large region per SM (fewest streams and hops) wins.
             const int ctas = std::max(1, net->lane_ctas);
             const int cap_max = std::max(64, 1024 / ctas - 48);            // threads of a CTA = rows + stream mirrors
             const int64_t slots = (int64_t)num_sms * ctas;
@@ -1389,7 +1388,18 @@ int txh_run_assimilating(txh_net* net, double* O, double* I, int64_t M, const tx
         if (k == 0 && obs_ready_event) CU(cudaStreamWaitEvent(st, (cudaEvent_t)obs_ready_event, 0));
         if (rc == TXH_OK) rc = check_M(M);
         if (rc == TXH_OK) rc = enkf_solve_impl(net, m, M, HX, O, Zp + (size_t)k * m * M, rowsum, obs, qs, R, Dinv, dinv_kind, work, W, T, stream);
-        if (rc == TXH_OK) rc = txh_enkf_apply(net, O, I, M, nullptr, 0, 0, M, 0, rowsum, T, obs, m, qs, W, G, stream);
+        if (rc != TXH_OK) break;
+        if (txh_row_stride(M) <= 64) {
+            // right after a routing launch the forecast inflows are exactly the sums of the upstream forecast outflows
+            // (nutils.py:84-85), so i + N gain = N (o + gain): the transform updates O in place without storing the
+            // gains, and the posterior inflows are rebuilt from the posterior outflows
+            const int ld = (int)txh_row_stride(M);
+            CU(launch_enkf_update(O, ld, (int)M, rowsum, T, (int)M, (int)M, O, nullptr, ld, net->topo.n, net->d_gauge_of_pos,
+                                  qs, W, 0, net->num_sms, (int)M, 0, st));
+            CU(launch_inflow_rebuild(net->d_inner, net->n_inner, net->d_up_off, net->d_up_pos, O, I, ld, st));
+        } else {
+            rc = txh_enkf_apply(net, O, I, M, nullptr, 0, 0, M, 0, rowsum, T, obs, m, qs, W, G, stream);
+        }
     }
     net->stats_rowsum = nullptr;
     if (rc == TXH_OK && nsteps > nwin * every)

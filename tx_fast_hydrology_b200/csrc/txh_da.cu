@@ -665,7 +665,7 @@ enkf_update_kernel(const double* __restrict__ Xall, int ldx, int Mtot, const dou
                         o.x += gn.x; o.y += gn.y;
                         *reinterpret_cast<double2*>(Oout + (size_t)row * ld + col) = o;
                     }
-                    *reinterpret_cast<double2*>(G + (size_t)row * ld + col) = gn;
+                    if (G) *reinterpret_cast<double2*>(G + (size_t)row * ld + col) = gn;
                 }
             }
         }
@@ -806,7 +806,7 @@ enkf_update64_kernel(const double* __restrict__ X, int M, const double* __restri
                     o.x += gn.x; o.y += gn.y;
                     *reinterpret_cast<double2*>(O + (size_t)rows[i] * ld + col) = o;
                 }
-                *reinterpret_cast<double2*>(G + (size_t)rows[i] * ld + col) = gn;
+                if (G) *reinterpret_cast<double2*>(G + (size_t)rows[i] * ld + col) = gn;
             }
         }
         __syncwarp();                                 // everyone is done with this buffer before it is refilled
@@ -837,6 +837,28 @@ inflow_gain_kernel(const int32_t* __restrict__ inner, long long n_inner, const i
     }
     i.x += s.x; i.y += s.y;
     *ip = i;
+}
+
+// The same update when the forecast inflows ARE the sums of the upstream forecast outflows (true right after a routing
+// step: nutils.py:84-85 builds i_t_next that way): i + N gain = N (o + gain), so the posterior inflows are rebuilt from
+// the posterior outflows and the gains never go to memory.
+__global__ void __launch_bounds__(256)
+inflow_rebuild_kernel(const int32_t* __restrict__ inner, long long n_inner, const int32_t* __restrict__ up_off,
+                      const int32_t* __restrict__ up_pos, const double* __restrict__ O, double* __restrict__ I, int ld)
+{
+    const int half = ld >> 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_inner * half) return;
+    const long long e = gid / half;
+    const int col = (int)(gid - e * half) * 2;
+    const long long k = inner[e];
+    const int u0 = up_off[k], u1 = up_off[k + 1];
+    double2 s = make_double2(0.0, 0.0);
+    for (int u = u0; u < u1; ++u) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(O + (size_t)up_pos[u] * ld + col));
+        s.x += v.x; s.y += v.y;
+    }
+    __stcg(reinterpret_cast<double2*>(I + (size_t)k * ld + col), s);
 }
 
 inline unsigned nblk(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
@@ -1004,6 +1026,15 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
     if (e != cudaSuccess) return e;
     enkf_update_kernel<<<(unsigned)grid, EU_WARPS * 32, smem, st>>>(Xall, ldx, Mtot, mean, T, ldt, Mloc, O, Oout, G, ld, n,
                                                                     gauge_of_pos, qs, W, col0, resident, Mb, blk_stride, pb);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inflow_rebuild(const int32_t* inner, int64_t n_inner, const int32_t* up_off, const int32_t* up_pos,
+                                  const double* O, double* I, int ld, cudaStream_t st)
+{
+    if (n_inner == 0) return cudaSuccess;
+    inflow_rebuild_kernel<<<nblk(n_inner * (ld >> 1), 256), 256, 0, st>>>(inner, n_inner, up_off, up_pos, O, I, ld);
     count_launch();
     return cudaGetLastError();
 }

@@ -231,6 +231,8 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
                                int Mloc, double* O, double* G, int ld, int64_t n, const int32_t* gauge_of_pos,
                                const double* qs, const double* W, int col0, int num_sms, int Mb, long long blk_stride,
                                cudaStream_t st, const PeerBlocks* peers = nullptr, double* Oout = nullptr);
+cudaError_t launch_inflow_rebuild(const int32_t* inner, int64_t n_inner, const int32_t* up_off, const int32_t* up_pos,
+                                  const double* O, double* I, int ld, cudaStream_t st);
 cudaError_t launch_inflow_gain(const int32_t* inner, int64_t n_inner, const int32_t* up_off, const int32_t* up_pos,
                                const double* G, double* I, int ld, cudaStream_t st);
 

@@ -311,11 +311,13 @@ route_lane_kernel(const LaneArgs a)
                     // batch of `from` and the two after it.  Used before the first step and whenever the consumer has
                     // caught up with its producer: consumers then advance in bursts at full speed instead of paying a
                     // trip to L2 per step at the producer's heels (which would compound along a chain of regions).
-                    auto lag_and_fetch = [&](int from) {
+                    // The wait polls the stream of member `mp`, at a cell that member has not consumed yet (cells this
+                    // thread has consumed hold EMPTY again and would never fill).
+                    auto lag_and_fetch = [&](int from, int mp) {
                         const int need = min(nsteps, from + a.lag) - 1;
                         unsigned spins = 0;
                         unsigned long long t0 = 0;
-                        while (!dead && is_empty(ld_relaxed_f64(g0 + need))) {
+                        while (!dead && is_empty(ld_relaxed_f64(g0 + (size_t)mp * splp + need))) {
                             if ((++spins & 15u) == 0) {
                                 if (ld_relaxed_s32(a.status) != 0) { dead = 1; break; }
                                 const unsigned long long now = globaltimer_ns();
@@ -336,7 +338,7 @@ route_lane_kernel(const LaneArgs a)
                         cp_async_wait_all();
                     };
                     if (sv == 0) {
-                        lag_and_fetch(0);
+                        lag_and_fetch(0, M - 1);                             // producers write their members in ascending order
                         if (tr) atomicMax(tr + 2, globaltimer_ns());           // last first-step lag wait of the region over
                     } else if ((sv & (kBatch - 1)) == 0) {
                         cp_async_wait_all();                                 // batches sv/8 and sv/8 + 1 are in the window
@@ -357,7 +359,7 @@ route_lane_kernel(const LaneArgs a)
                         if (is_empty(val)) {
                             // caught up with the producer: fall back by `lag` steps, then continue from the window
                             if (tr) atomicAdd(tr + 6, 1ull);
-                            lag_and_fetch(sv);
+                            lag_and_fetch(sv, m);
                             val = lds_d(ea);
                             unsigned spins = 0, nap = 32;
                             unsigned long long t0 = 0;
