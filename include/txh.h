@@ -91,6 +91,14 @@ int txh_get_window_schedule(const txh_net* net, int32_t* wtask_desc, uint32_t* w
 int txh_get_lane_info(txh_net* net, int64_t M, int64_t cap_rows, int64_t info[8]);
 int txh_get_lane_schedule(txh_net* net, int64_t M, int32_t* regions, int32_t* rows, int32_t* child);
 
+/* NHD flowline GeoJSON -> network arrays in ONE native pass over the file: replaces the per-feature Python loops of
+ * load_nhd_geojson (muskingum.py:877-917).  comid[i], shape_length[i] ("Shape_Length") and endnodes[i] = index of the
+ * feature whose COMID equals feature i's toCOMID, or i itself when there is none (outlet = self-loop,
+ * muskingum.py:897-902).  Geometry is skipped.  Host only.  Call with capacity = 0 to get `count`, then with arrays of
+ * that size. */
+int txh_scan_nhd_geojson(const char* path, int64_t capacity, int64_t* comid /*[capacity]*/, int64_t* endnodes,
+                         double* shape_length, int64_t* count);
+
 /* ---- coefficients ----------------------------------------------------------------
  * txh_compute_coeffs replaces Muskingum.compute_muskingum_coeffs (muskingum.py:332-360):
  * host arithmetic in the reference's operation order; results returned in reach order

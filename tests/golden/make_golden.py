@@ -342,6 +342,60 @@ def checkpoint_kf():
     print("checkpoint_kf_n70.npz ok")
 
 
+def split_kf():
+    """The product's operating mode (app/app.py:121-166): Muskingum.split, ONE dense KalmanFilter bound to every
+    sub-model that has gauges, AsyncSimulation over the collection.  Same network, cuts and forcing as
+    split_n300.npz; gauges sampled per sub-model, measurements hourly."""
+    import asyncio
+    from tx_fast_hydrology.simulation import AsyncSimulation
+    n, T, seed = 300, 24, 31
+    net = S.make_network(n, seed)
+    prm = S.make_params(n, seed, well_posed=True)
+    d = S.model_dict(net, prm, dt_s=3600.0, t0=T0)
+    d["dx"] = np.ones(n)
+    d["paths"] = [[0.0] for _ in range(n)]
+    mdl = Muskingum(d)
+    t0_ns = mdl.datetime.value
+    rng = np.random.default_rng(seed + 3)
+    times = t0_ns + (np.arange(T, dtype=np.int64) + 1) * int(3600e9)
+    table = rng.gamma(0.5, 2.0, size=(T, n))
+    df = frame(times, table, d["reach_ids"])
+    order = np.argsort(-np.bincount(net["endnodes"], minlength=n) - rng.uniform(0, 0.5, n))
+    cuts = [int(j) for j in order if net["endnodes"][j] != j][:3]
+    mc = mdl.split(cuts, create_state_space=False)
+    names = list(mc.models.keys())
+    out = dict(endnodes=mdl.endnodes, K=mdl.K, X=mdl.X, o_init=prm["o_t"], dt=3600.0, t0_ns=t0_ns, times=times,
+               table=table, cuts=np.asarray(cuts), n_models=len(names))
+    mt = t0_ns + np.arange(0, T + 1, dtype=np.int64) * int(3600e9)
+    mt = mt[mt <= t0_ns + 18 * int(3600e9)]
+    out["meas_times"] = mt
+    kfs = {}
+    for k in names:
+        sub = mc.models[k]
+        m = min(4, max(1, sub.n // 12))
+        if sub.n < 6:
+            out[f"gauges_{k}"] = np.zeros(0, dtype=np.int64)
+            continue
+        gl = np.sort(rng.choice(sub.n, size=m, replace=False))           # local gauge indices
+        meas = rng.uniform(0.5, 8.0, size=(mt.size, m))
+        mdf = frame(mt, meas, [sub.reach_ids[j] for j in gl])
+        R = 1e-2 * np.eye(m); Q = 2.0 * np.eye(sub.n); P0 = Q.copy()
+        kf = KalmanFilter(sub, mdf, Q, R, P0)
+        sub.bind_callback(kf, key="kf")
+        kfs[k] = kf
+        out[f"gauges_{k}"] = gl; out[f"meas_{k}"] = meas
+    sim = AsyncSimulation(mc, df)
+    outputs = asyncio.run(sim.simulate())
+    for k in names:
+        out[f"reach_{k}"] = np.asarray([int(r) for r in mc.models[k].reach_ids])
+        out[f"out_{k}"] = outputs[k].values
+        if k in kfs:
+            out[f"P_{k}"] = kfs[k].P_t_next
+            out[f"i_end_{k}"] = mc.models[k].i_t_next
+    np.savez_compressed(os.path.join(HERE, "split_kf_n300.npz"), **out)
+    print("split_kf_n300.npz ok", len(names), "models,", len(kfs), "filters")
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     if only:                                  # e.g. `make_golden.py quirks checkpoint_kf`: just these fixtures

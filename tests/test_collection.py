@@ -84,6 +84,36 @@ def test_async_simulation_matches_reference(libtxh, golden_dir, with_callback):
     assert mc.datetime.value == int(g["times"][-1])
 
 
+@pytest.mark.gpu
+def test_collection_with_a_kalman_filter_per_sub_model(libtxh, golden_dir):
+    """The product's operating mode (app/app.py:121-166) against the unmodified reference: the network split into
+    sub-models, ONE dense KalmanFilter bound to each, AsyncSimulation over the collection -- sub-model hydrographs,
+    final inflows and final covariances."""
+    from tx_fast_hydrology_b200.da import KalmanFilter
+    from tx_fast_hydrology_b200.simulation import AsyncSimulation
+    g = np.load(os.path.join(golden_dir, "split_kf_n300.npz"))
+    mdl, d = _model(g)
+    df = _frame(g, d["reach_ids"])
+    mc = mdl.split([int(c) for c in g["cuts"]])
+    assert len(mc.models) == int(g["n_models"])
+    idx = pd.DatetimeIndex(pd.to_datetime(g["meas_times"], unit="ns", utc=True)).as_unit("ns")
+    kfs = {}
+    for k, sub in mc.models.items():
+        gl = g[f"gauges_{k}"]
+        if gl.size == 0:
+            continue
+        mdf = pd.DataFrame(g[f"meas_{k}"], index=idx, columns=[sub.reach_ids[j] for j in gl])
+        kfs[k] = KalmanFilter(sub, mdf, 2.0 * np.eye(sub.n), 1e-2 * np.eye(gl.size), 2.0 * np.eye(sub.n))
+        sub.bind_callback(kfs[k], key="kf")
+    outputs = asyncio.run(AsyncSimulation(mc, df).simulate())
+    for k, sub in mc.models.items():
+        assert ([int(r) for r in sub.reach_ids] == g[f"reach_{k}"]).all()
+        assert relerr(outputs[k].values, g[f"out_{k}"]) < RTOL
+        if k in kfs:
+            assert relerr(sub.i_t_next, g[f"i_end_{k}"]) < RTOL
+            assert normerr(kfs[k].P_t_next, g[f"P_{k}"]) < RTOL         # covariance: max-norm (tests/parity.py)
+
+
 def test_load_nhd_geojson(libtxh, tmp_path):
     """muskingum.py:877-917: COMID/toCOMID -> indices, missing downstream id -> self-loop outlet, defaults."""
     import json
@@ -103,3 +133,48 @@ def test_load_nhd_geojson(libtxh, tmp_path):
     assert (obj["dx"] == 1.5 + np.arange(6)).all() and len(obj["paths"]) == 6
     mdl = Muskingum(obj)
     assert (mdl.indegree == np.array([1, 1, 0, 2, 1, 0])).all()
+
+
+def test_native_geojson_scanner_equals_the_reference_loader(libtxh, tmp_path):
+    """txh_scan_nhd_geojson (csrc/txh_geojson.cpp) == the reference's per-feature loops (muskingum.py:877-917,
+    restated here with json + a dict) on 40,000 features: shuffled ids, keys in varying order, null / missing /
+    unknown toCOMID, geometry with nested arrays and braces inside strings."""
+    import json
+    import time
+    from tx_fast_hydrology_b200.muskingum import load_nhd_geojson
+    rng = np.random.default_rng(5)
+    n = 40_000
+    ids = rng.permutation(np.arange(10_000_000, 10_000_000 + 3 * n))[:n]
+    down = rng.integers(0, n, size=n)
+    feats = []
+    for k in range(n):
+        r = rng.random()
+        to = None if r < 0.02 else (int(ids[down[k]]) if r < 0.95 else 777)      # null / a feature / an unknown id
+        attrs = {"COMID": int(ids[k]), "toCOMID": to, "Shape_Length": float(rng.uniform(0.1, 9.0)),
+                 "GNIS_NAME": 'a } [ \\" b'}
+        if k % 3 == 0:
+            attrs = dict(reversed(list(attrs.items())))
+        if k % 7 == 0:
+            attrs.pop("toCOMID")
+        geom = {"paths": [[[float(k), 0.5], [float(k) + 1, 1.5e-3]]], "note": "{[}"}
+        feats.append({"geometry": geom, "attributes": attrs} if k % 2 else {"attributes": attrs, "geometry": geom})
+    path = str(tmp_path / "big.json")
+    with open(path, "w") as f:
+        json.dump({"type": "x", "features": feats, "tail": [1, {"features": []}]}, f)
+    t0 = time.perf_counter()
+    obj = load_nhd_geojson(path, load_paths=False)
+    t_native = time.perf_counter() - t0
+    # the reference's logic
+    index_of = {}
+    for k in range(n):
+        index_of.setdefault(int(ids[k]), k)
+    end = np.array([index_of.get(ft["attributes"].get("toCOMID"), k) for k, ft in enumerate(feats)])
+    assert obj["reach_ids"] == [str(int(x)) for x in ids]
+    assert (obj["endnodes"] == end).all() and (obj["startnodes"] == np.arange(n)).all()
+    assert (obj["dx"] == np.array([ft["attributes"]["Shape_Length"] for ft in feats])).all()
+    assert obj["paths"] == [] and t_native < 5.0
+    with open(str(tmp_path / "bad.json"), "w") as f:
+        f.write('{"features": [{"attributes": {"toCOMID": 3, "Shape_Length": 1.0}}]}')
+    from tx_fast_hydrology_b200._lib import TxhError
+    with pytest.raises(TxhError):
+        load_nhd_geojson(str(tmp_path / "bad.json"))

@@ -42,6 +42,7 @@ SIGNATURES = {
     "txh_get_window_schedule": (ctypes.c_int, [c_vp, p_i32, p_u32, p_u32, p_i32]),
     "txh_get_lane_info": (ctypes.c_int, [c_vp, c_i64, c_i64, p_i64]),
     "txh_get_lane_schedule": (ctypes.c_int, [c_vp, c_i64, p_i32, p_i32, p_i32]),
+    "txh_scan_nhd_geojson": (ctypes.c_int, [ctypes.c_char_p, c_i64, p_i64, p_i64, p_f64, p_i64]),
     "txh_compute_coeffs": (ctypes.c_int, [c_vp, p_f64, p_f64, c_f64, p_f64, p_f64, p_f64, p_f64]),
     "txh_set_coeffs": (ctypes.c_int, [c_vp, p_f64, p_f64, p_f64, p_f64]),
     "txh_row_stride": (c_i64, [c_i64]),

@@ -663,6 +663,9 @@ int run_one_step(txh_net* net, double* O, double* I, int64_t M, const double* q,
 
 }  // namespace
 
+// error reporting for the host-only translation units (txh_geojson.cpp)
+int txh_set_error_(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+
 extern "C" {
 
 const char* txh_last_error(void) { return g_err.c_str(); }

@@ -80,12 +80,6 @@ __device__ __forceinline__ double lds_d(unsigned a)
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
     return v;
 }
-__device__ __forceinline__ int lds_s32(unsigned a)
-{
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
 __device__ __forceinline__ unsigned lds_u16(unsigned a)
 {
     unsigned short v;
@@ -93,20 +87,11 @@ __device__ __forceinline__ unsigned lds_u16(unsigned a)
     return v;
 }
 __device__ __forceinline__ void sts_d(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
-__device__ __forceinline__ void sts_d2(unsigned a, double2 v)
-{
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
-}
 __device__ __forceinline__ void sts_i4(unsigned a, int4 v)
 {
     asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
-__device__ __forceinline__ void cp_async8_s(unsigned sa, const void* g)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(g) : "memory");
-}
 __device__ __forceinline__ void cp_async16_s(unsigned sa, const void* g)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");

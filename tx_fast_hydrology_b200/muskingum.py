@@ -21,6 +21,7 @@ import copy as _copy
 import datetime as _dt
 import json
 import logging
+import os
 import uuid
 
 import numpy as np
@@ -540,9 +541,9 @@ class Muskingum:
         return new
 
     @classmethod
-    def from_nhd_geojson(cls, file_path, **kwargs):
+    def from_nhd_geojson(cls, file_path, load_paths=True, **kwargs):
         """muskingum.py:877-917 as the reference exposes it (a classmethod around the loader)."""
-        return cls(load_nhd_geojson(file_path), **kwargs)
+        return cls(load_nhd_geojson(file_path, load_paths=load_paths), **kwargs)
 
 
     def split(self, indices, name=None, create_state_space=False):
@@ -733,32 +734,33 @@ def load_model_file(file_path, load_optional=True):
     return obj
 
 
-def load_nhd_geojson(file_path):
+def load_nhd_geojson(file_path, load_paths=True):
     """NHD flowline GeoJSON -> the dict `Muskingum` takes (muskingum.py:877-917): reach = feature, COMID /
     toCOMID give the downstream link (a missing toCOMID makes the reach an outlet, i.e. a self-loop), defaults
-    K = 3600 s, X = 0.29, o_t = 1e-3.  The id -> index join is one sort + searchsorted instead of a per-feature
-    loop, so CONUS-size files do not spend their time here."""
-    with open(file_path) as f:
-        features = json.load(f)['features']
-    attrs = [ft['attributes'] for ft in features]
-    comid = np.asarray([a['COMID'] for a in attrs])
-    to_comid = np.asarray([a['toCOMID'] for a in attrs])
-    n = comid.size
-    order = np.argsort(comid, kind='stable')
-    sorted_ids = comid[order]
-    # first occurrence wins, as a pandas index lookup on unique ids does
-    pos = np.searchsorted(sorted_ids, to_comid)
-    pos_c = np.minimum(pos, max(n - 1, 0))
-    found = (pos < n) & (sorted_ids[pos_c] == to_comid) if n else np.zeros(0, dtype=bool)
-    startnodes = np.arange(n, dtype=np.int64)
-    endnodes = np.where(found, order[pos_c], startnodes).astype(np.int64)
+    K = 3600 s, X = 0.29, o_t = 1e-3.
+
+    The attributes come from ONE native pass over the file (`txh_scan_nhd_geojson`, csrc/txh_geojson.cpp): no
+    per-feature Python loop, no Python objects for the geometry, the id -> index join a sort + binary search --
+    CONUS-size files do not spend their time here.  `load_paths=True` (the reference's behaviour) additionally
+    json-loads the file for the `paths` polylines, which only plotting uses; pass False for large files."""
+    import ctypes
+    from . import _lib as L
+    lib = L.load()
+    cnt = ctypes.c_int64()
+    path = os.fsencode(file_path)
+    L.check(lib.txh_scan_nhd_geojson(path, 0, None, None, None, ctypes.byref(cnt)))
+    n = int(cnt.value)
+    comid = np.empty(n, dtype=np.int64); endnodes = np.empty(n, dtype=np.int64); dx = np.empty(n, dtype=np.float64)
+    L.check(lib.txh_scan_nhd_geojson(path, n, L.ptr_i64(comid), L.ptr_i64(endnodes), L.ptr_f64(dx), ctypes.byref(cnt)))
+    paths = []
+    if load_paths:
+        with open(file_path) as f:
+            paths = [np.asarray(ft['geometry']['paths']) for ft in json.load(f)['features']]
     return {
         'name': str(uuid.uuid4()), 'datetime': DEFAULT_START_TIME, 'timedelta': DEFAULT_TIMEDELTA,
-        'reach_ids': [str(x) for x in comid.tolist()], 'startnodes': startnodes, 'endnodes': endnodes,
+        'reach_ids': comid.astype(str).tolist(), 'startnodes': np.arange(n, dtype=np.int64), 'endnodes': endnodes,
         'K': 3600 * np.ones(n, dtype=np.float64), 'X': 0.29 * np.ones(n, dtype=np.float64),
-        'o_t': 1e-3 * np.ones(n, dtype=np.float64),
-        'dx': np.asarray([a['Shape_Length'] for a in attrs]),
-        'paths': [np.asarray(ft['geometry']['paths']) for ft in features],
+        'o_t': 1e-3 * np.ones(n, dtype=np.float64), 'dx': dx, 'paths': paths,
     }
 
 
