@@ -267,6 +267,25 @@ int txh_kf_filter(txh_net* net, const double* P_in, double* P_out, double* P_pri
                   const double* R_dev, const int64_t* obs_host, int64_t m, const double* z_host, double* O,
                   double* I, double* K_dev, double* gain_dev, double* dz_dev, double* work_dev, void* stream);
 
+/* ---- batched dense Kalman filters: ONE chain of launches for the filters of a whole generation of sub-models --------
+ * app/app.py:130-141 binds one KalmanFilter per sub-model of a split network and da.py:91-136 fires for each of them
+ * after every step.  The sub-models are disjoint forests: `union_net` is the network of all their reaches, block after
+ * block (block k: reaches [sum n_0..n_{k-1}, + n_k), local downstream links shifted accordingly).  The columns of every
+ * covariance block ride as members of the SAME two routing launches (_aqat_par, nutils.py:194-214), the m_k x m_k
+ * inverses run one CTA per block, and the gains correct the union state in place (_apply_gain, nutils.py:116-134).
+ * obs_local: the gauge reaches of every block, LOCAL indices, ascending per block, concatenated (da.py:36-44 order).
+ * which (txh_kfb_set / _get): 0 P (posterior), 1 Q, 2 R -- settable -- 3 P before the last update, 4 K [n][m], 5 dz [m],
+ * 6 gain [n]; matrices row-major in the block's local reach / gauge order.
+ * txh_kfb_filter: active[k] = 0 leaves block k alone (its filter is not due, da.py:49-61); z_host: the measurement
+ * vectors of all blocks concatenated; O, I: state rows of the UNION model (M = 1).  Asynchronous after its copies. */
+typedef struct txh_kfb txh_kfb;
+int txh_kfb_create(txh_net* union_net, int64_t nblocks, const int64_t* n_k, const int64_t* m_k, const int64_t* obs_local,
+                   txh_kfb** out);
+void txh_kfb_destroy(txh_kfb* b);
+int txh_kfb_set(txh_kfb* b, int64_t block, int which, const double* host, void* stream);
+int txh_kfb_get(txh_kfb* b, int64_t block, int which, double* host, void* stream);
+int txh_kfb_filter(txh_kfb* b, const uint8_t* active_host, const double* z_host, double* O_dev, double* I_dev, void* stream);
+
 /* Synchronise `stream` and report a poisoned launch (TXH_E_WATCHDOG), an innovation covariance that was
  * not positive definite in an earlier txh_enkf_solve (TXH_E_INVALID), or a CUDA fault. */
 int txh_check(txh_net* net, void* stream);

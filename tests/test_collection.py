@@ -85,10 +85,12 @@ def test_async_simulation_matches_reference(libtxh, golden_dir, with_callback):
 
 
 @pytest.mark.gpu
-def test_collection_with_a_kalman_filter_per_sub_model(libtxh, golden_dir):
+@pytest.mark.parametrize("batched", [True, False])
+def test_collection_with_a_kalman_filter_per_sub_model(libtxh, golden_dir, batched):
     """The product's operating mode (app/app.py:121-166) against the unmodified reference: the network split into
     sub-models, ONE dense KalmanFilter bound to each, AsyncSimulation over the collection -- sub-model hydrographs,
-    final inflows and final covariances."""
+    final inflows and final covariances.  `batched`: the filters of the sub-models that are ready together run as
+    ONE chain of launches on the union of their networks (txh_kfb_filter), or one chain per sub-model."""
     from tx_fast_hydrology_b200.da import KalmanFilter
     from tx_fast_hydrology_b200.simulation import AsyncSimulation
     g = np.load(os.path.join(golden_dir, "split_kf_n300.npz"))
@@ -105,13 +107,21 @@ def test_collection_with_a_kalman_filter_per_sub_model(libtxh, golden_dir):
         mdf = pd.DataFrame(g[f"meas_{k}"], index=idx, columns=[sub.reach_ids[j] for j in gl])
         kfs[k] = KalmanFilter(sub, mdf, 2.0 * np.eye(sub.n), 1e-2 * np.eye(gl.size), 2.0 * np.eye(sub.n))
         sub.bind_callback(kfs[k], key="kf")
-    outputs = asyncio.run(AsyncSimulation(mc, df).simulate())
+    sim = AsyncSimulation(mc, df)
+    sim.batch_filters = batched
+    from tx_fast_hydrology_b200._lib import load
+    launches = load().txh_launch_count()
+    outputs = asyncio.run(sim.simulate())
+    launches = load().txh_launch_count() - launches
+    print(f"batched={batched}: {launches} kernel launches for the collection run")
     for k, sub in mc.models.items():
         assert ([int(r) for r in sub.reach_ids] == g[f"reach_{k}"]).all()
         assert relerr(outputs[k].values, g[f"out_{k}"]) < RTOL
         if k in kfs:
             assert relerr(sub.i_t_next, g[f"i_end_{k}"]) < RTOL
             assert normerr(kfs[k].P_t_next, g[f"P_{k}"]) < RTOL         # covariance: max-norm (tests/parity.py)
+            assert kfs[k].K.shape == (sub.n, g[f"gauges_{k}"].size) and kfs[k].gain.shape == (sub.n,)
+    assert mc.datetime.value == int(g["times"][-1])
 
 
 def test_load_nhd_geojson(libtxh, tmp_path):

@@ -234,8 +234,10 @@ def test_dataflow_equals_levels(torch_cuda, libtxh):
         net.route_step(Oa, Ia, M, q)
         net.route_step(Ob, Ib, M, q, levels=True)
     net.check()
-    assert relerr(net.unpack_host(Oa, M), net.unpack_host(Ob, M)) < 1e-12
-    assert relerr(net.unpack_host(Ia, M), net.unpack_host(Ib, M)) < 1e-12
+    # (random, inconsistent o / i: elements cancel, so the tight bound is in the max-norm)
+    assert normerr(net.unpack_host(Oa, M), net.unpack_host(Ob, M)) < 1e-13
+    assert normerr(net.unpack_host(Ia, M), net.unpack_host(Ib, M)) < 1e-13
+    assert relerr(net.unpack_host(Oa, M), net.unpack_host(Ob, M)) < RTOL
 
 
 def test_no_coeffs_is_an_error(torch_cuda, libtxh):

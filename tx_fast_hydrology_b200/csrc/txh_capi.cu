@@ -93,7 +93,7 @@ struct txh_net {
     LaneStep* d_lsteps = nullptr; size_t lsteps_cap = 0;
     LaneStep* d_unit_lstep = nullptr;
     LaneDev lane[5];                    // member tiles 1, 2, 4, 8, 16
-    int lane_max_members = 8;           // ensembles up to this size take the lane kernel
+    int lane_max_members = 4;           // ensembles up to this size may take the lane kernel (row state in registers)
     int lane_cap_rows = 0;              // rows per region; 0 = from the size of the network and the SM count
     int lane_ctas = 1;                  // regions (CTAs) per SM the schedule is sized for (measured: 1 is best)
     double* d_lring = nullptr; size_t lring_cap = 0;
@@ -380,7 +380,9 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     a.off_words = a.off_cumc + up16(rc * 8);
     a.off_list = a.off_words + up16(std::max(1, s.w_max_words) * 4);
     a.off_steps = a.off_list + up16(std::max(1, s.w_max_words) * 4);
-    a.smem_per_warp = a.off_steps + 16 * 24;                  // StepInterp records of one launch (<= 16 steps)
+    a.off_mbar = a.off_steps + 16 * 24;                       // StepInterp records of one launch (<= 16 steps)
+    a.smem_per_warp = a.off_mbar + 16;                        // + the warp's mbarrier (bulk staging of the state rows)
+    if (const char* k = getenv("TXH_WINDOW_BULK")) { if (atoi(k) == 0) a.off_mbar = 0; }
     if ((size_t)std::max(1, s.n_wslots) * ld * sizeof(double) >= (size_t(1) << 32)) return 1;   // 32-bit slot offsets
     const int smem_max = 227 * 1024;
     int wpc = std::min(16, (smem_max - 1024) / a.smem_per_warp);
@@ -484,7 +486,7 @@ txh_net::LaneDev* lane_schedule(txh_net* net, int ti, int num_sms)
             const int cap_max = std::max(64, 1024 / ctas - 48);            // threads of a CTA = rows + stream mirrors
             const int64_t slots = (int64_t)num_sms * ctas;
             const int64_t per = (net->topo.n + slots - 1) / slots;
-            int cap = (int)std::min<int64_t>(cap_max, std::max<int64_t>(96, per + per / 50));
+            int cap = (int)std::min<int64_t>(cap_max, std::max<int64_t>(std::min(320, cap_max), per + per / 50));
             for (;;) {
                 L.ok = L.sched.build(net->topo, net->sched.pos_of_reach, 1 << ti, cap, kLaneSmemBudget, side_min, err);
                 if (!L.ok || (int64_t)L.sched.regions.size() <= slots || cap >= cap_max) break;
@@ -616,10 +618,25 @@ int run_lane(txh_net* net, double* O, double* I, int64_t M, const double* F, con
     return TXH_OK;
 }
 
-bool lane_wanted(const txh_net* net, int64_t M)
+// Lane kernel or window kernel?  Forced by TXH_ROUTE_KERNEL, else the lane kernel for small ensembles when the launch
+// is long enough to amortise its pipeline fill.  Measured on B200: an iteration of the lane
+// kernel costs ~1 us and a launch runs nsteps + fill iterations, fill = sum over the deepest chain of regions of
+// (internal depth + lag); the window kernel costs ~(40 + n/1000) us per launch of at most 64 steps plus
+// ~(4 + 4e-5 n) us per step (n = 100k: 138 + 8.1 us; n = 1,000: 4.5 us per step).
+bool lane_wanted(txh_net* net, int64_t M, int64_t nsteps)
 {
     if (net->route_kernel == 3) return M <= 16;
-    return net->route_kernel == 0 && M <= net->lane_max_members;
+    if (net->route_kernel != 0 || M > net->lane_max_members) return false;
+    txh_net::LaneDev* L = lane_schedule(net, lane_tile_index(M), net->num_sms);
+    if (!L->ok) return false;
+    const LaneSchedule& s = L->sched;
+    int hmax = 0; double extra = 0.0;
+    for (const LaneRegionDesc& r : s.regions) { hmax = std::max(hmax, r.height); extra += r.n_extra; }
+    extra /= std::max<size_t>(1, s.regions.size());
+    const double n = (double)net->topo.n;
+    const double t_lane = (double)nsteps + (hmax + 1) * (extra + 32.0);
+    const double t_win = std::ceil((double)nsteps / 64.0) * (40.0 + 1e-3 * n) + (double)nsteps * (4.0 + 4e-5 * n);
+    return t_lane <= t_win;
 }
 
 // routing entry: the lane kernel for small ensembles, else the window kernel unless recording was asked for
@@ -629,7 +646,7 @@ int run_routing(txh_net* net, double* O, double* I, int64_t M, const double* F, 
                 int rec_count, cudaStream_t st)
 {
     const int ld = (int)txh_row_stride(M);
-    if (lane_wanted(net, M)) {
+    if (lane_wanted(net, M, nsteps)) {
         const int rc = run_lane(net, O, I, M, F, W, wm_ld, plan, nsteps, rec_slot, rec_out, rec_every, rec_count, st);
         if (rc == TXH_OK && net->stats_rowsum)
             CU(launch_enkf_stats(O, ld, (int)M, net->topo.n, net->stats_scale, nullptr, net->stats_rowsum, nullptr, st));
@@ -650,7 +667,7 @@ int run_routing(txh_net* net, double* O, double* I, int64_t M, const double* F, 
 // one step without a forcing table (q: [n] schedule order or nullptr): window kernel first, dataflow otherwise
 int run_one_step(txh_net* net, double* O, double* I, int64_t M, const double* q, cudaStream_t st)
 {
-    if (lane_wanted(net, M)) {
+    if (lane_wanted(net, M, 1)) {
         const int rc = run_lane(net, O, I, M, q, nullptr, 0, StepPlan(), 1, nullptr, nullptr, 1, 0, st);
         if (rc != 1) return rc;
     }
@@ -1522,6 +1539,162 @@ int txh_kf_filter(txh_net* net, const double* P_in, double* P_out, double* P_pri
     CU(launch_dgemm_ex(0, 0, (int)n, (int)n, (int)m, -1.0, K, (int)m, Prow, (int)n, 1.0, Pm, (int)n, P_out, (int)n, st));
     // da.py:124-126
     CU(launch_apply_gain(net->d_up_off, net->d_up_pos, Gp, O, I, n, ld1, 1, st));
+    return TXH_OK;
+}
+
+}  // extern "C"
+
+// ---- batched dense Kalman filters of a generation of sub-models ---------------------------------------------------
+struct txh_kfb {
+    txh_net* net = nullptr;                    // the UNION network of the sub-models (reach order: block after block)
+    std::vector<KfbBlock> blocks;
+    int64_t n_u = 0, m_tot = 0, pp = 0, nm = 0, mm = 0;
+    int max_n = 0, max_m = 0, ld = 0;
+    KfbBlock* d_blocks = nullptr;
+    int32_t *d_blk_of_reach = nullptr, *d_gl_of_reach = nullptr, *d_obs_reach = nullptr;
+    double *d_P = nullptr, *d_Pprev = nullptr, *d_Q = nullptr, *d_R = nullptr, *d_Pm = nullptr, *d_Ps = nullptr, *d_Prow = nullptr,
+           *d_S = nullptr, *d_K = nullptr, *d_z = nullptr, *d_dz = nullptr, *d_gain = nullptr, *d_Gp = nullptr, *d_X = nullptr,
+           *d_X2 = nullptr;
+};
+
+extern "C" {
+
+int txh_kfb_create(txh_net* net, int64_t nblocks, const int64_t* n_k, const int64_t* m_k, const int64_t* obs_local, txh_kfb** out)
+{
+    if (!net || !n_k || !m_k || !obs_local || !out || nblocks < 1) return fail(TXH_E_INVALID, "bad argument");
+    int rc;
+    if ((rc = ensure_device(net))) return rc;
+    txh_kfb* b = new (std::nothrow) txh_kfb();
+    if (!b) return fail(TXH_E_INVALID, "out of memory");
+    b->net = net;
+    std::vector<int32_t> blk_of_reach, gl_of_reach, obs_reach;
+    int64_t row0 = 0, g0 = 0;
+    for (int64_t k = 0; k < nblocks; ++k) {
+        if (n_k[k] < 1 || m_k[k] < 1 || m_k[k] > n_k[k]) { delete b; return fail(TXH_E_INVALID, "bad block size"); }
+        KfbBlock blk{};
+        blk.n = (int32_t)n_k[k]; blk.m = (int32_t)m_k[k]; blk.row0 = (int32_t)row0; blk.g_off = (int32_t)g0; blk.active = 1;
+        blk.p_off = b->pp; blk.nm_off = b->nm; blk.mm_off = b->mm;
+        b->pp += n_k[k] * n_k[k]; b->nm += n_k[k] * m_k[k]; b->mm += m_k[k] * m_k[k];
+        b->max_n = std::max(b->max_n, blk.n); b->max_m = std::max(b->max_m, blk.m);
+        std::vector<int32_t> gl(n_k[k], -1);
+        for (int64_t g = 0; g < m_k[k]; ++g) {
+            const int64_t j = obs_local[g0 + g];
+            if (j < 0 || j >= n_k[k] || (g > 0 && j <= obs_local[g0 + g - 1])) {
+                delete b; return fail(TXH_E_INVALID, "gauge indices of a block must be strictly ascending local reaches");
+            }
+            gl[j] = (int32_t)g;
+            obs_reach.push_back((int32_t)(row0 + j));
+        }
+        for (int64_t i = 0; i < n_k[k]; ++i) blk_of_reach.push_back((int32_t)k);
+        gl_of_reach.insert(gl_of_reach.end(), gl.begin(), gl.end());
+        b->blocks.push_back(blk);
+        row0 += n_k[k]; g0 += m_k[k];
+    }
+    if (row0 != net->topo.n) { delete b; return fail(TXH_E_INVALID, "block sizes do not add up to the union network"); }
+    if ((size_t)4 * b->max_m + (size_t)b->max_m * b->max_m > 200 * 1024 / sizeof(double)) {
+        delete b; return fail(TXH_E_INVALID, "a block has too many gauges for the batched inverse");
+    }
+    b->n_u = row0; b->m_tot = g0;
+    b->ld = (int)txh_row_stride(b->max_n);
+    if ((rc = upload(&b->d_blocks, b->blocks)) || (rc = upload(&b->d_blk_of_reach, blk_of_reach)) ||
+        (rc = upload(&b->d_gl_of_reach, gl_of_reach)) || (rc = upload(&b->d_obs_reach, obs_reach))) { delete b; return rc; }
+    auto dalloc = [](double** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(double)); };
+    cudaError_t e = cudaSuccess;
+    for (auto pr : {std::make_pair(&b->d_P, (size_t)b->pp), std::make_pair(&b->d_Pprev, (size_t)b->pp), std::make_pair(&b->d_Q, (size_t)b->pp),
+                    std::make_pair(&b->d_Pm, (size_t)b->pp), std::make_pair(&b->d_R, (size_t)b->mm), std::make_pair(&b->d_S, (size_t)b->mm),
+                    std::make_pair(&b->d_Ps, (size_t)b->nm), std::make_pair(&b->d_Prow, (size_t)b->nm), std::make_pair(&b->d_K, (size_t)b->nm),
+                    std::make_pair(&b->d_z, (size_t)b->m_tot), std::make_pair(&b->d_dz, (size_t)b->m_tot),
+                    std::make_pair(&b->d_gain, (size_t)b->n_u), std::make_pair(&b->d_Gp, (size_t)b->n_u * 2),
+                    std::make_pair(&b->d_X, (size_t)b->n_u * b->ld), std::make_pair(&b->d_X2, (size_t)b->n_u * b->ld)})
+        if (e == cudaSuccess) e = dalloc(pr.first, pr.second);
+    if (e != cudaSuccess) { txh_kfb_destroy(b); return cuda_fail(e, "batched filter buffers"); }
+    *out = b;
+    return TXH_OK;
+}
+
+void txh_kfb_destroy(txh_kfb* b)
+{
+    if (!b) return;
+    cudaFree(b->d_blocks); cudaFree(b->d_blk_of_reach); cudaFree(b->d_gl_of_reach); cudaFree(b->d_obs_reach);
+    for (double* p : {b->d_P, b->d_Pprev, b->d_Q, b->d_R, b->d_Pm, b->d_Ps, b->d_Prow, b->d_S, b->d_K, b->d_z, b->d_dz, b->d_gain,
+                      b->d_Gp, b->d_X, b->d_X2})
+        cudaFree(p);
+    delete b;
+}
+
+// which: 0 P (posterior), 1 Q, 2 R, 3 P of the previous update, 4 K, 5 dz, 6 gain
+static int kfb_locate(txh_kfb* b, int64_t block, int which, double** ptr, size_t* count)
+{
+    if (!b || block < 0 || block >= (int64_t)b->blocks.size()) return fail(TXH_E_INVALID, "bad block");
+    const KfbBlock& k = b->blocks[block];
+    switch (which) {
+        case 0: *ptr = b->d_P + k.p_off; *count = (size_t)k.n * k.n; break;
+        case 1: *ptr = b->d_Q + k.p_off; *count = (size_t)k.n * k.n; break;
+        case 2: *ptr = b->d_R + k.mm_off; *count = (size_t)k.m * k.m; break;
+        case 3: *ptr = b->d_Pprev + k.p_off; *count = (size_t)k.n * k.n; break;
+        case 4: *ptr = b->d_K + k.nm_off; *count = (size_t)k.n * k.m; break;
+        case 5: *ptr = b->d_dz + k.g_off; *count = (size_t)k.m; break;
+        case 6: *ptr = b->d_gain + k.row0; *count = (size_t)k.n; break;
+        default: return fail(TXH_E_INVALID, "bad matrix selector");
+    }
+    return TXH_OK;
+}
+
+int txh_kfb_set(txh_kfb* b, int64_t block, int which, const double* host, void* stream)
+{
+    double* p; size_t c; int rc;
+    if (!host) return fail(TXH_E_INVALID, "null argument");
+    if ((rc = kfb_locate(b, block, which, &p, &c))) return rc;
+    if (which > 2) return fail(TXH_E_INVALID, "only P, Q and R can be set");
+    CU(cudaMemcpyAsync(p, host, c * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return TXH_OK;
+}
+
+int txh_kfb_get(txh_kfb* b, int64_t block, int which, double* host, void* stream)
+{
+    double* p; size_t c; int rc;
+    if (!host) return fail(TXH_E_INVALID, "null argument");
+    if ((rc = kfb_locate(b, block, which, &p, &c))) return rc;
+    CU(cudaMemcpyAsync(host, p, c * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return TXH_OK;
+}
+
+int txh_kfb_filter(txh_kfb* b, const uint8_t* active, const double* z_host, double* O, double* I, void* stream)
+{
+    if (!b || !active || !z_host || !O || !I) return fail(TXH_E_INVALID, "null argument");
+    txh_net* net = b->net;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ensure_device(net)) || (rc = ensure_coef(net, st))) return rc;
+    bool any = false, changed = false;
+    for (size_t k = 0; k < b->blocks.size(); ++k) {
+        const int32_t a = active[k] ? 1 : 0;
+        changed |= a != b->blocks[k].active;
+        b->blocks[k].active = a;
+        any |= a != 0;
+    }
+    if (!any) return TXH_OK;
+    if (changed) {
+        CU(cudaMemcpyAsync(b->d_blocks, b->blocks.data(), b->blocks.size() * sizeof(KfbBlock), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    CU(cudaMemcpyAsync(b->d_z, z_host, sizeof(double) * b->m_tot, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->d_Pprev, b->d_P, sizeof(double) * b->pp, cudaMemcpyDeviceToDevice, st));
+    const int n_u = (int)b->n_u, ld = b->ld, M = b->max_n;
+    // P- = A (A P)^T + Q for every block at once: the blocks' columns are the members of two routing launches
+    CU(launch_kfb_pack(b->d_blocks, b->d_blk_of_reach, net->d_pos_of_reach, b->d_P, b->d_X, n_u, ld, st));
+    CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, b->d_X, b->d_X2, n_u, ld, M, st));
+    if ((rc = run_one_step(net, b->d_X, b->d_X2, M, nullptr, st))) return rc;
+    CU(launch_kfb_transpose(b->d_blocks, b->d_blk_of_reach, net->d_pos_of_reach, b->d_X, b->d_X2, n_u, ld, st));
+    CU(launch_init_inflows(net->d_up_off, net->d_up_pos, net->d_outlet, b->d_X2, b->d_X, n_u, ld, M, st));
+    if ((rc = run_one_step(net, b->d_X2, b->d_X, M, nullptr, st))) return rc;
+    CU(launch_kfb_update(b->d_blocks, (int)b->blocks.size(), b->max_m, b->d_blk_of_reach, net->d_pos_of_reach, b->d_gl_of_reach,
+                         b->d_obs_reach, b->d_X2, n_u, ld, b->d_Q, b->d_R, b->d_z, O, (int)txh_row_stride(1), b->d_Pm, b->d_Ps,
+                         b->d_Prow, b->d_S, b->d_K, b->d_dz, b->d_gain, b->d_Gp, b->d_P, info_word(net), st));
+    // da.py:124-126 on the union state (inactive blocks have a zero gain)
+    CU(launch_apply_gain(net->d_up_off, net->d_up_pos, b->d_Gp, O, I, n_u, (int)txh_row_stride(1), 1, st));
     return TXH_OK;
 }
 

@@ -123,6 +123,7 @@ struct WinArgs {
     int32_t n_tasks, n_mblocks, nsteps, n_slots, ld, M, wm_ld;
     // per-warp shared memory (bytes): [p rows][scratch slots][input ring][row records][cumA][cumC][words][slot list][steps]
     int32_t smem_per_warp, off_scr, off_in, off_rec, off_cum, off_cumc, off_words, off_list, off_steps;
+    int32_t off_mbar;                     // > 0: per-warp mbarrier for the bulk (TMA) staging of the state rows
     unsigned long long* trace;            // optional [pairs][4 + nsteps] timeline (claim, loaded, end, kind|smid, publish per step)
     double* rowsum;                       // optional [n]: scale * sum over the members of the final outflows (n_mblocks == 1)
     double rowsum_scale;
@@ -235,6 +236,26 @@ cudaError_t launch_inflow_rebuild(const int32_t* inner, int64_t n_inner, const i
                                   const double* O, double* I, int ld, cudaStream_t st);
 cudaError_t launch_inflow_gain(const int32_t* inner, int64_t n_inner, const int32_t* up_off, const int32_t* up_pos,
                                const double* G, double* I, int ld, cudaStream_t st);
+
+// ---- batched dense filters of a generation of sub-models (txh_kf.cu) ------------------------------
+struct KfbBlock {
+    int32_t n, m;             // reaches / gauges of the sub-model
+    int32_t row0;             // first reach of the block in the union network
+    int32_t g_off;            // first gauge of the block in the concatenated gauge arrays
+    int32_t active;           // 0: this filter is not due, leave its block alone
+    int32_t pad_;
+    long long p_off;          // offsets (doubles) of the block in the packed [n][n], [n][m] / [m][n], [m][m] buffers
+    long long nm_off, mm_off;
+};
+cudaError_t launch_kfb_pack(const KfbBlock* blocks, const int32_t* blk_of_reach, const int32_t* pos_of_reach, const double* P,
+                            double* X, int n_u, int ld, cudaStream_t st);
+cudaError_t launch_kfb_transpose(const KfbBlock* blocks, const int32_t* blk_of_reach, const int32_t* pos_of_reach,
+                                 const double* X, double* X2, int n_u, int ld, cudaStream_t st);
+cudaError_t launch_kfb_update(const KfbBlock* blocks, int nblocks, int max_m, const int32_t* blk_of_reach,
+                              const int32_t* pos_of_reach, const int32_t* gl_of_reach, const int32_t* obs_reach,
+                              const double* X2, int n_u, int ld, const double* Q, const double* R, const double* z,
+                              const double* O, int ldo, double* Pm, double* Ps, double* Prow, double* S, double* K, double* dz,
+                              double* gain, double* Gp, double* P, int* info, cudaStream_t st);
 
 // ---- dense per-sub-basin filter glue (txh_kf.cu) ---------------------------------------------------
 cudaError_t launch_kf_repack_transposed(const int32_t* reach_of_pos, const int32_t* pos_of_reach, const double* X,

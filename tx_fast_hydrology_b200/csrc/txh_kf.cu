@@ -87,10 +87,8 @@ kf_gain_kernel(const int32_t* __restrict__ reach_of_pos, const double* __restric
 // per column: the elimination of column j also publishes column j + 1 as it will look afterwards, so every
 // warp can find the next pivot on its own; rows are swapped as the pivots are chosen and the columns swapped
 // back in reverse order at the end.
-__global__ void __launch_bounds__(1024)
-inverse_smem_kernel(double* __restrict__ A, int m, int in_smem, int* __restrict__ info)
+__device__ __forceinline__ void inverse_in_cta(double* __restrict__ A, int m, int in_smem, int* __restrict__ info, double* sm)
 {
-    extern __shared__ __align__(16) double sm[];
     double* colv = sm;                       // column j (of the rows as they are before the swap), double buffered
     double* prow = sm + 2 * m;               // scaled pivot row
     int* perm = reinterpret_cast<int*>(sm + 3 * m);
@@ -160,6 +158,131 @@ inverse_smem_kernel(double* __restrict__ A, int m, int in_smem, int* __restrict_
     if (in_smem) for (int e = tid; e < mm; e += nt) A[e] = a[e];
 }
 
+__global__ void __launch_bounds__(1024)
+inverse_smem_kernel(double* __restrict__ A, int m, int in_smem, int* __restrict__ info)
+{
+    extern __shared__ __align__(16) double sm[];
+    inverse_in_cta(A, m, in_smem, info, sm);
+}
+
+// ---- batched form: the filters of a whole generation of sub-models in ONE chain of launches ------------------
+// (app/app.py:130-141 binds one KalmanFilter per sub-model; da.py:91-136 fires for each of them after every step.)
+// The sub-models are disjoint forests, so their union is one network: the columns of every covariance block ride as
+// members of the SAME two routing launches (block k occupies the rows of its reaches and the first n_k columns), and
+// the per-block dense algebra runs with one CTA / one thread group per block.
+
+// X[pos(r)][c] = P_k[i][c]  (r = reach i of block k; zero beyond the block's columns and for inactive blocks)
+__global__ void __launch_bounds__(256)
+kfb_pack_kernel(const KfbBlock* __restrict__ blocks, const int32_t* __restrict__ blk_of_reach,
+                const int32_t* __restrict__ pos_of_reach, const double* __restrict__ P, double* __restrict__ X, int n_u, int ld)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n_u * ld) return;
+    const int r = (int)(gid / ld), c = (int)(gid - (long long)r * ld);
+    const KfbBlock b = blocks[blk_of_reach[r]];
+    double v = 0.0;
+    if (b.active && c < b.n) v = P[b.p_off + (long long)(r - b.row0) * b.n + c];
+    X[(size_t)pos_of_reach[r] * ld + c] = v;
+}
+
+// X2[pos(row0 + j)][c] = X[pos(row0 + c)][j]: the transposed block, packed again (second pass of _aqat_par)
+__global__ void __launch_bounds__(256)
+kfb_transpose_kernel(const KfbBlock* __restrict__ blocks, const int32_t* __restrict__ blk_of_reach,
+                     const int32_t* __restrict__ pos_of_reach, const double* __restrict__ X, double* __restrict__ X2, int n_u,
+                     int ld)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n_u * ld) return;
+    const int r = (int)(gid / ld), c = (int)(gid - (long long)r * ld);
+    const KfbBlock b = blocks[blk_of_reach[r]];
+    double v = 0.0;
+    if (b.active && c < b.n) v = X[(size_t)pos_of_reach[b.row0 + c] * ld + (r - b.row0)];
+    X2[(size_t)pos_of_reach[r] * ld + c] = v;
+}
+
+// P-_k[j][c] = X2[pos(row0 + j)][c] + Q_k[j][c], scattered into the gauge slices (kf_prior_finish_kernel per block)
+__global__ void __launch_bounds__(256)
+kfb_finish_kernel(const KfbBlock* __restrict__ blocks, const int32_t* __restrict__ blk_of_reach,
+                  const int32_t* __restrict__ pos_of_reach, const int32_t* __restrict__ gl_of_reach,
+                  const double* __restrict__ X2, int n_u, int ld, const double* __restrict__ Q, const double* __restrict__ R,
+                  double* __restrict__ Pm, double* __restrict__ Ps, double* __restrict__ Prow, double* __restrict__ S)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n_u * ld) return;
+    const int r = (int)(gid / ld), c = (int)(gid - (long long)r * ld);
+    const KfbBlock b = blocks[blk_of_reach[r]];
+    if (!b.active || c >= b.n) return;
+    const int j = r - b.row0;
+    const long long e = b.p_off + (long long)j * b.n + c;
+    const double v = X2[(size_t)pos_of_reach[r] * ld + c] + Q[e];
+    Pm[e] = v;
+    const int gr = gl_of_reach[r], gc = gl_of_reach[b.row0 + c];
+    if (gc >= 0) Ps[b.nm_off + (long long)j * b.m + gc] = v;
+    if (gr >= 0) {
+        Prow[b.nm_off + (long long)gr * b.n + c] = v;
+        if (gc >= 0) S[b.mm_off + (long long)gr * b.m + gc] = v + R[b.mm_off + (long long)gr * b.m + gc];
+    }
+}
+
+// S_k <- inv(S_k), one CTA per block (np.linalg.inv, da.py:119)
+__global__ void __launch_bounds__(256)
+kfb_inverse_kernel(const KfbBlock* __restrict__ blocks, double* __restrict__ S, int* __restrict__ info)
+{
+    extern __shared__ __align__(16) double sm[];
+    const KfbBlock b = blocks[blockIdx.x];
+    if (!b.active || b.m <= 0) return;
+    inverse_in_cta(S + b.mm_off, b.m, 1, info, sm);
+}
+
+// per reach: K_k[j][:] = P-_k[j, s] S_k^-1 (da.py:119), gain = K dz with dz = z - o[s] (da.py:112, 121)
+__global__ void __launch_bounds__(128)
+kfb_gain_kernel(const KfbBlock* __restrict__ blocks, const int32_t* __restrict__ blk_of_reach,
+                const int32_t* __restrict__ pos_of_reach, const int32_t* __restrict__ obs_reach, const double* __restrict__ z,
+                const double* __restrict__ O, int ldo, const double* __restrict__ Ps, const double* __restrict__ Sinv,
+                double* __restrict__ K, double* __restrict__ dz, double* __restrict__ gain, double* __restrict__ Gp, int n_u)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_u) return;
+    const KfbBlock b = blocks[blk_of_reach[r]];
+    const size_t gp = (size_t)pos_of_reach[r] * ldo;
+    double g = 0.0;
+    if (b.active) {
+        const int j = r - b.row0;
+        const double* ps = Ps + b.nm_off + (long long)j * b.m;
+        const double* si = Sinv + b.mm_off;
+        for (int q = 0; q < b.m; ++q) {
+            double kq = 0.0;
+            for (int t = 0; t < b.m; ++t) kq += ps[t] * si[(long long)t * b.m + q];
+            K[b.nm_off + (long long)j * b.m + q] = kq;
+            const double d = z[b.g_off + q] - O[(size_t)pos_of_reach[obs_reach[b.g_off + q]] * ldo];
+            if (j == 0) dz[b.g_off + q] = d;
+            g += kq * d;
+        }
+    }
+    gain[r] = g;
+    Gp[gp] = g;
+    for (int c = 1; c < ldo; ++c) Gp[gp + c] = 0.0;
+}
+
+// P+_k = P-_k - K_k P-_k[s]  (da.py:122)
+__global__ void __launch_bounds__(256)
+kfb_post_kernel(const KfbBlock* __restrict__ blocks, const int32_t* __restrict__ blk_of_reach, const double* __restrict__ Pm,
+                const double* __restrict__ K, const double* __restrict__ Prow, double* __restrict__ P, int n_u, int ld)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n_u * ld) return;
+    const int r = (int)(gid / ld), c = (int)(gid - (long long)r * ld);
+    const KfbBlock b = blocks[blk_of_reach[r]];
+    if (!b.active || c >= b.n) return;
+    const int j = r - b.row0;
+    const long long e = b.p_off + (long long)j * b.n + c;
+    double v = Pm[e];
+    const double* kr = K + b.nm_off + (long long)j * b.m;
+    const double* pr = Prow + b.nm_off + c;
+    for (int q = 0; q < b.m; ++q) v -= kr[q] * pr[(long long)q * b.n];
+    P[e] = v;
+}
+
 }  // namespace
 
 cudaError_t launch_kf_repack_transposed(const int32_t* reach_of_pos, const int32_t* pos_of_reach, const double* X,
@@ -186,6 +309,44 @@ cudaError_t launch_kf_gain(const int32_t* reach_of_pos, const int32_t* obs_pos, 
     kf_innovation_kernel<<<nblk(m, 128), 128, 0, st>>>(obs_pos, z, O, ldo, m, dz);
     count_launch();
     kf_gain_kernel<<<nblk(n, 256), 256, 0, st>>>(reach_of_pos, K, dz, n, m, ldo, gain, Gp);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kfb_pack(const KfbBlock* blocks, const int32_t* blk_of_reach, const int32_t* pos_of_reach, const double* P,
+                            double* X, int n_u, int ld, cudaStream_t st)
+{
+    kfb_pack_kernel<<<nblk((long long)n_u * ld, 256), 256, 0, st>>>(blocks, blk_of_reach, pos_of_reach, P, X, n_u, ld);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kfb_transpose(const KfbBlock* blocks, const int32_t* blk_of_reach, const int32_t* pos_of_reach,
+                                 const double* X, double* X2, int n_u, int ld, cudaStream_t st)
+{
+    kfb_transpose_kernel<<<nblk((long long)n_u * ld, 256), 256, 0, st>>>(blocks, blk_of_reach, pos_of_reach, X, X2, n_u, ld);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kfb_update(const KfbBlock* blocks, int nblocks, int max_m, const int32_t* blk_of_reach,
+                              const int32_t* pos_of_reach, const int32_t* gl_of_reach, const int32_t* obs_reach,
+                              const double* X2, int n_u, int ld, const double* Q, const double* R, const double* z,
+                              const double* O, int ldo, double* Pm, double* Ps, double* Prow, double* S, double* K, double* dz,
+                              double* gain, double* Gp, double* P, int* info, cudaStream_t st)
+{
+    kfb_finish_kernel<<<nblk((long long)n_u * ld, 256), 256, 0, st>>>(blocks, blk_of_reach, pos_of_reach, gl_of_reach, X2, n_u,
+                                                                      ld, Q, R, Pm, Ps, Prow, S);
+    count_launch();
+    const size_t smem = ((size_t)4 * max_m + (size_t)max_m * max_m) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(kfb_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kfb_inverse_kernel<<<nblocks, 256, smem, st>>>(blocks, S, info);
+    count_launch();
+    kfb_gain_kernel<<<nblk(n_u, 128), 128, 0, st>>>(blocks, blk_of_reach, pos_of_reach, obs_reach, z, O, ldo, Ps, S, K, dz, gain,
+                                                    Gp, n_u);
+    count_launch();
+    kfb_post_kernel<<<nblk((long long)n_u * ld, 256), 256, 0, st>>>(blocks, blk_of_reach, Pm, K, Prow, P, n_u, ld);
     count_launch();
     return cudaGetLastError();
 }

@@ -82,6 +82,37 @@ __device__ __forceinline__ void sts_u32(unsigned sa, uint32_t v)
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
 }
 
+// ---- TMA bulk copies (cp.async.bulk, 1-D) + mbarrier: the rows of a task are contiguous in global memory, and with
+// 64 doubles per row (one member block) their shared-memory image is contiguous too, so ONE elected lane moves all
+// outflow rows of a task with one instruction (and its inflow rows with another) instead of every lane issuing a
+// 16-byte cp.async per row.
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned phase)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
+    } while (!ok);
+}
+
 constexpr int kInRing = 4;                 // pockets: rows of other tasks in flight per warp (cp.async ring)
 constexpr int kSegRing = 8;                // segments: the ring also takes the (unused) scratch slots
 constexpr int kStepsStaged = 16;            // interpolation records of a launch kept in shared memory
@@ -387,6 +418,14 @@ route_window_kernel(const WinArgs a)
     tk.sWords = sb + a.off_words; tk.sList = sb + a.off_list;
     tk.lane = lane; tk.ld = ld;
     tk.step_bytes = (size_t)a.n_slots * ld * sizeof(double);
+    // bulk staging of the state rows (see the helpers above): one mbarrier per warp
+    const bool bulk = a.off_mbar > 0 && ld == kMemberBlock;
+    const unsigned sMbar = sb + a.off_mbar;
+    unsigned mphase = 0;
+    if (bulk) {
+        if (lane == 0) mbar_init(sMbar, 1);
+        __syncwarp();
+    }
 
     for (;;) {
         long long t = 0;
@@ -430,11 +469,22 @@ route_window_kernel(const WinArgs a)
         }
         // rows of O straight into their p slots, rows of I (eight at a time) into the scratch / ring area: every
         // load of the task is in flight before the first is waited for
-        if (active)
+        if (bulk) {
+            // the rows were last touched by this warp's ordinary stores: order them before the async proxy's writes
+            __syncwarp();
+            if (lane == 0) {
+                fence_proxy_async();
+                const unsigned bo = 512u * (unsigned)len, bi = 512u * (unsigned)(len < 8 ? len : 8);
+                mbar_expect_tx(sMbar, bo + bi);
+                bulk_g2s(sb, a.O + (size_t)td.begin * ld, bo, sMbar);
+                bulk_g2s(sb + a.off_scr, a.I + (size_t)td.begin * ld, bi, sMbar);
+            }
+        } else if (active) {
             for (int r = 0; r < len; ++r) {
                 cp_async16(tk.sP + 512u * r, tk.Og + (size_t)r * ld);
                 if (r < 8) cp_async16(tk.sScr + 512u * r, tk.Ig + (size_t)r * ld);
             }
+        }
         cp_async_commit();
         for (int i = lane; i < len; i += 32) {
             const double2 ab = *reinterpret_cast<const double2*>(a.coef + 4 * (size_t)(td.begin + i));
@@ -449,11 +499,21 @@ route_window_kernel(const WinArgs a)
         }
         for (int r0 = 0; r0 < len; r0 += 8) {
             if (r0 > 0) {
-                if (active)
+                if (bulk) {
+                    __syncwarp();                               // the previous chunk has been read by every lane
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        const unsigned bi = 512u * (unsigned)(len - r0 < 8 ? len - r0 : 8);
+                        mbar_expect_tx(sMbar, bi);
+                        bulk_g2s(sb + a.off_scr, a.I + (size_t)(td.begin + r0) * ld, bi, sMbar);
+                    }
+                } else if (active) {
                     for (int r = r0; r < len && r < r0 + 8; ++r) cp_async16(tk.sScr + 512u * (r - r0), tk.Ig + (size_t)r * ld);
+                }
                 cp_async_commit();
             }
             cp_async_wait_all();
+            if (bulk) { mbar_wait(sMbar, mphase); mphase ^= 1u; }
             __syncwarp();
             for (int r = r0; r < len && r < r0 + 8; ++r) {
                 const double2 bc = lds_row(tk.sRec + kRec * r + 16u);

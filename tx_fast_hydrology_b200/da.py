@@ -514,3 +514,145 @@ class EnsembleKalmanFilter(_MeasurementTable, BaseCallback):
         mdl._device_advanced()
         self.n_updates += 1
         self.datetime = mdl.datetime
+
+
+class BatchedKalmanFilters:
+    """The dense `KalmanFilter`s of several INDEPENDENT sub-models advanced in lockstep (the reference's operating
+    mode, app/app.py:130-141: one filter per sub-model of a split network, `filter()` after every step,
+    da.py:49-61).  The sub-models are disjoint forests, so their union is one network: one routing launch steps
+    them all, and ONE chain of launches (`txh_kfb_filter`) runs every filter -- the columns of all covariance
+    blocks ride as members of the same two routing launches (`_aqat_par`, nutils.py:194-214), the m x m inverses
+    run one CTA per block -- instead of a 14-launch chain per sub-model.
+
+    `models`: Muskingum objects whose only callback is a `KalmanFilter` under the key it was bound with, all at
+    the same `datetime` with the same `timedelta`.  `run(inputs)` does for each of them what
+    `simulate_iter(inputs[name])` + the filter's hooks do, and leaves models and filters in the state the
+    per-model path leaves them in."""
+
+    def __init__(self, models):
+        import torch
+        from . import _lib as L
+        from .muskingum import Muskingum
+        self._torch, self._L = torch, L
+        self.models = list(models)
+        self.filters = []
+        for mdl in self.models:
+            kfs = list(mdl.callbacks.values())
+            if len(kfs) != 1 or type(kfs[0]) is not KalmanFilter or mdl.members != 1:
+                raise ValueError('every model needs exactly one KalmanFilter callback and a single member')
+            self.filters.append(kfs[0])
+        t0, dt = self.models[0].datetime, self.models[0].timedelta
+        if any(m.datetime != t0 or m.timedelta != dt for m in self.models):
+            raise ValueError('models must share datetime and timedelta')
+        sizes = [m.n for m in self.models]
+        self.row0 = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        d = {'name': 'union', 'datetime': t0, 'timedelta': dt,
+             'reach_ids': [f'{k}:{r}' for k, m in enumerate(self.models) for r in m.reach_ids],
+             'startnodes': np.arange(self.row0[-1], dtype=np.int64),
+             'endnodes': np.concatenate([m.endnodes + self.row0[k] for k, m in enumerate(self.models)]).astype(np.int64),
+             'K': np.concatenate([m.K for m in self.models]), 'X': np.concatenate([m.X for m in self.models]),
+             'o_t': np.concatenate([m._peek_state('o_t_next') for m in self.models])}
+        self.union = u = Muskingum(d, load_optional=False)
+        for name in ('alpha', 'beta', 'chi', 'gamma'):                 # user-mutated coefficients travel too
+            getattr(u, name)[:] = np.concatenate([getattr(m, name) for m in self.models])
+        u.init_states(o_t_next=d['o_t'], i_t_next=np.concatenate([m._peek_state('i_t_next') for m in self.models]))
+        u.o_t_prev = np.concatenate([m._peek_state('o_t_prev') for m in self.models])
+        u.i_t_prev = np.concatenate([m._peek_state('i_t_prev') for m in self.models])
+        lib = L.load()
+        n_k = L.as_i64(sizes)
+        m_k = L.as_i64([kf.num_measurements for kf in self.filters])
+        obs = L.as_i64(np.concatenate([kf.reach_indices for kf in self.filters]))
+        self.g0 = np.concatenate([[0], np.cumsum(m_k)]).astype(np.int64)
+        import ctypes
+        h = ctypes.c_void_p()
+        L.check(lib.txh_kfb_create(u.network.handle, len(self.models), L.ptr_i64(n_k), L.ptr_i64(m_k), L.ptr_i64(obs),
+                                   ctypes.byref(h)))
+        self.handle = h
+        self._lib = lib
+        for k, kf in enumerate(self.filters):
+            for which, t in ((0, kf._P), (1, kf._Q), (2, kf._R)):
+                a = L.as_f64(t.cpu().numpy())
+                L.check(lib.txh_kfb_set(h, k, which, L.ptr_f64(a), None))
+        self.n_updates = 0
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self._lib.txh_kfb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _get(self, k, which, shape):
+        out = np.empty(shape, dtype=np.float64)
+        self._L.check(self._lib.txh_kfb_get(self.handle, k, which, self._L.ptr_f64(out), None))
+        return out
+
+    def filter(self):
+        """`KalmanFilter.filter` (da.py:91-136) of every filter that is due at the union model's time."""
+        import ctypes
+        u = self.union
+        active = np.array([u.datetime <= kf.latest_timestamp for kf in self.filters], dtype=np.uint8)
+        if not active.any():
+            return
+        z = np.concatenate([kf.interpolate_input(u.datetime) if a else np.zeros(kf.num_measurements)
+                            for kf, a in zip(self.filters, active)])
+        u._ensure_device()
+        u._sync_coeffs()
+        d = u._dev
+        from .network import _cuda_ptr, _stream_ptr
+        self._L.check(self._lib.txh_kfb_filter(self.handle, active.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                               self._L.ptr_f64(self._L.as_f64(z)), _cuda_ptr(d['O']), _cuda_ptr(d['I']),
+                                               _stream_ptr()))
+        u._device_advanced()
+        self._last_active = active
+        for kf, a in zip(self.filters, active):
+            if a:
+                kf.datetime = u.datetime
+        self.n_updates += 1
+
+    def run(self, inputs):
+        """`inputs`: {model name: forcing DataFrame} with one common index.  Returns {name: (values [steps+1][n], times)}:
+        the rows AsyncSimulation records -- row 0 is the state after the simulation-start hooks."""
+        from .nutils import interpolate_sample
+        u = self.union
+        frames = [inputs[m.name][m.reach_ids] for m in self.models]
+        index = frames[0].index
+        if any(not f.index.equals(index) for f in frames):
+            raise ValueError('the forcing frames of a batched generation must share one index')
+        times = index.astype(int).astype(float).values
+        table = np.ascontiguousarray(np.concatenate([f.values for f in frames], axis=1), dtype=np.float64)
+        end_time = index.max()
+        self._last_active = np.zeros(len(self.filters), dtype=np.uint8)
+        self.filter()                                              # __on_simulation_start__ of every filter
+        rows, stamps = [u._peek_state('o_t_next')], [u.datetime]
+        while u.datetime < end_time:
+            p = interpolate_sample(float((u.datetime + u.timedelta).value), times, table)
+            u.step_iter(p)
+            self.filter()                                          # __on_step_end__
+            rows.append(u._peek_state('o_t_next')); stamps.append(u.datetime)
+        self._write_back()
+        values = np.stack(rows)
+        return {m.name: (values[:, self.row0[k]:self.row0[k + 1]], list(stamps)) for k, m in enumerate(self.models)}
+
+    def _write_back(self):
+        """Sub-models and their filters end up where the per-model path would have left them."""
+        torch = self._torch
+        u = self.union
+        u.network.check()
+        state = {key: u._peek_state(key) for key in ('o_t_next', 'i_t_next', 'o_t_prev', 'i_t_prev')}
+        for k, (m, kf) in enumerate(zip(self.models, self.filters)):
+            sl = slice(self.row0[k], self.row0[k + 1])
+            m.init_states(o_t_next=state['o_t_next'][sl], i_t_next=state['i_t_next'][sl])
+            m.o_t_prev = np.array(state['o_t_prev'][sl]); m.i_t_prev = np.array(state['i_t_prev'][sl])
+            m.datetime = u.datetime
+            n, mm = m.n, kf.num_measurements
+            kf._P = torch.as_tensor(self._get(k, 0, (n, n)), device='cuda')
+            kf._P_prev = torch.as_tensor(self._get(k, 3, (n, n)), device='cuda')
+            if kf.datetime == u.datetime or self._last_active[k]:
+                kf._K_d = torch.as_tensor(self._get(k, 4, (n, mm)), device='cuda')
+                kf._dz_d = torch.as_tensor(self._get(k, 5, (mm,)), device='cuda')
+                kf._gain_d = torch.as_tensor(self._get(k, 6, (n,)), device='cuda')

@@ -366,6 +366,11 @@ class Muskingum:
             self.init_states(o_t_next=o_t_init)
         for _, callback in self.callbacks.items():
             callback.__on_simulation_start__()
+        if getattr(self, '_capture_start', False):
+            # AsyncSimulation's first output row is the state AFTER the simulation-start hooks: the reference stores a
+            # reference to o_t_next there and a filter bound to the model corrects that array in place
+            # (simulation.py:126-127, da.py:124-126)
+            self._start_outflow = self._peek_state('o_t_next')
         dataframe = dataframe[self.reach_ids]
         times = dataframe.index.astype(int).astype(float).values
         table = np.ascontiguousarray(dataframe.values, dtype=np.float64)

@@ -58,14 +58,16 @@ class AsyncSimulation(Simulation):
         """Awaitable like the reference's (simulation.py:98-108); `run()` is the plain-call form."""
         return self.run()
 
+    batch_filters = True      # sub-models that are ready together and carry only a KalmanFilter run as one batch
+
     def run(self):
         pending = {name: len(model.sources) for name, model in self.models.items()}
         ready = [name for name, k in pending.items() if k == 0]
         done = 0
-        while ready:
-            name = ready.pop(0)
+
+        def finished(name, outputs):
+            nonlocal done
             model = self.models[name]
-            outputs = self._simulate(model, self.inputs[name])
             self.outputs[name] = outputs
             done += 1
             for connection in model.sinks:
@@ -76,9 +78,55 @@ class AsyncSimulation(Simulation):
                 pending[down.name] -= 1
                 if pending[down.name] == 0:
                     ready.append(down.name)
+
+        while ready:
+            batch = self._batchable(ready) if self.batch_filters else []
+            if len(batch) >= 2:
+                for name in batch:
+                    ready.remove(name)
+                for name, outputs in self._simulate_batch(batch).items():
+                    finished(name, outputs)
+                continue
+            name = ready.pop(0)
+            finished(name, self._simulate(self.models[name], self.inputs[name]))
         if done != len(self.models):
             raise ValueError('sub-model connections contain a cycle')
         return self.outputs
+
+    def _batchable(self, names):
+        """The ready sub-models whose filters can run as ONE chain of launches (da.BatchedKalmanFilters): a single
+        plain KalmanFilter callback, one member, a whole-second step, the same clock and forcing index."""
+        from .da import KalmanFilter
+        out = []
+        for name in names:
+            m = self.models[name]
+            cbs = list(m.callbacks.values())
+            if len(cbs) != 1 or type(cbs[0]) is not KalmanFilter or m.members != 1:
+                continue
+            if m.timedelta.value != int(round(m.dt * 1e9)):
+                continue
+            if out:
+                first = self.models[out[0]]
+                if (m.datetime != first.datetime or m.timedelta != first.timedelta or
+                        not self.inputs[name].index.equals(self.inputs[out[0]].index)):
+                    continue
+            out.append(name)
+        return out
+
+    def _simulate_batch(self, names):
+        """One generation of independent sub-models with a Kalman filter each, stepped in lockstep on their union."""
+        from .da import BatchedKalmanFilters
+        models = [self.models[name] for name in names]
+        bkf = BatchedKalmanFilters(models)
+        try:
+            res = bkf.run({name: self.inputs[name] for name in names})
+        finally:
+            bkf.close()
+        outputs = {}
+        for name in names:
+            values, times = res[name]
+            outputs[name] = pd.DataFrame(values, index=pd.to_datetime(times, utc=True), columns=self.inputs[name].columns)
+        return outputs
 
     def _simulate(self, model, inputs):
         """Whole run of one sub-model; rows = start time + every step, columns = reach ids."""
@@ -90,8 +138,15 @@ class AsyncSimulation(Simulation):
         whole = dt.value == int(round(model.dt * 1e9))
         if model.callbacks or nsteps == 0 or not whole:
             rows, times = [first], [start]
-            for state in model.simulate_iter(inputs):
-                rows.append(state._peek_state('o_t_next')); times.append(state.datetime)
+            model._capture_start = True
+            try:
+                for state in model.simulate_iter(inputs):
+                    rows.append(state._peek_state('o_t_next')); times.append(state.datetime)
+            finally:
+                model._capture_start = False
+            # row 0 aliases o_t_next in the reference, so it shows what the simulation-start hooks (a Kalman filter's
+            # first update) did to the state (simulation.py:126-127)
+            rows[0] = getattr(model, '_start_outflow', first)
             values = np.stack(rows)
         else:
             assert isinstance(inputs.index, pd.DatetimeIndex) and str(inputs.index.tz) == 'UTC'
