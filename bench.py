@@ -428,6 +428,7 @@ def gpu_arm(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from tx_fast_hydrology_b200 import build
@@ -449,11 +450,39 @@ def gpu_arm(a):
         if rank == 0:
             line["c4_basins"] = c4
     if rank == 0:
+        line["host_affinity"] = numa
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def pin_to_gpu_numa_node(local):
+    """N ranks share the host: run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU
+    (/sys/bus/pci/devices/<bus id>/local_cpulist), so the end-to-end uploads do not cross the socket interconnect.
+    Best effort; returns what was done."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        with open(path) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-"); cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return {"pinned": False, "why": "no overlap with the allowed CPUs", "local_cpulist": spec}
+        os.sched_setaffinity(0, allowed)
+        return {"pinned": True, "cpus": len(allowed), "local_cpulist": spec}
+    except Exception as e:                           # noqa: BLE001
+        return {"pinned": False, "why": str(e)[:120]}
 
 
 def c4_arm(a, rank, world, local):

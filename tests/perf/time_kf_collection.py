@@ -26,22 +26,20 @@ def build(n, seed, ncuts, T):
     times = t0 + (np.arange(T, dtype=np.int64) + 1) * int(3600e9)
     idx = pd.DatetimeIndex(pd.to_datetime(times, unit="ns", utc=True)).as_unit("ns")
     df = pd.DataFrame(rng.gamma(0.5, 2.0, size=(T, n)), index=idx, columns=d["reach_ids"])
-    # cut at outlets-of-subtrees of comparable size: reaches whose subtree holds ~n/ncuts reaches
-    sub = np.ones(n, dtype=np.int64)
+    # balanced sub-basins (HUC-like): walking upstream -> downstream, cut wherever the not-yet-cut subtree reaches `target`
     lev, _ = mdl.network.levels()
-    for j in np.argsort(lev):
-        e = net["endnodes"][j]
-        if e != j:
-            sub[e] += sub[j]
-    target = n // ncuts
-    cuts, covered = [], np.zeros(n, dtype=bool)
-    for j in np.argsort(-lev):                       # downstream first: skip reaches inside an already cut subtree
-        pass
-    order = np.argsort(np.abs(sub - target))
-    for j in order:
-        if len(cuts) >= ncuts or net["endnodes"][j] == j:
+    end = net["endnodes"]
+    open_sz = np.ones(n, dtype=np.int64)
+    cuts = []
+    target = max(8, n // ncuts)
+    for j in np.argsort(lev, kind="stable"):
+        e = end[j]
+        if e == j:
             continue
-        cuts.append(int(j))
+        if open_sz[j] >= target:
+            cuts.append(int(j))
+        else:
+            open_sz[e] += open_sz[j]
     mc = mdl.split(cuts)
     mt = t0 + np.arange(0, T + 1, dtype=np.int64) * int(3600e9)
     midx = pd.DatetimeIndex(pd.to_datetime(mt, unit="ns", utc=True)).as_unit("ns")
@@ -59,9 +57,9 @@ def main():
     import torch
     from tx_fast_hydrology_b200._lib import load
     from tx_fast_hydrology_b200.simulation import AsyncSimulation
-    n, seed, ncuts, T = 4000, 17, 24, 12
+    n, seed, ncuts, T = 6000, 17, 40, 12
     res = {}
-    for batched in (True, False):
+    for batched in (True, False, True, False):          # the first pair warms up (module load, allocator); the second is reported
         mc, df = build(n, seed, ncuts, T)
         sim = AsyncSimulation(mc, df)
         sim.batch_filters = batched
@@ -71,6 +69,10 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         sizes = sorted(m.n for m in mc.models.values())
+        warm = batched not in res
+        if warm:
+            res[batched] = None
+            continue
         res[batched] = out
         print(json.dumps({"batched": batched, "reaches": n, "sub_models": len(mc.models), "with_filter": sum(1 for m in mc.models.values() if m.callbacks),
                           "sub_model_sizes": [sizes[0], sizes[len(sizes) // 2], sizes[-1]], "steps": T, "wall_s": round(dt, 3),

@@ -39,7 +39,7 @@ __device__ __forceinline__ StepInterp interp_step(const double* __restrict__ tim
 }
 
 // The same record for route_lane_kernel, 32 bytes (two 128-bit loads); bit 31 of r1 is set when the bracket
-// (r0, r1) differs from the previous step's.
+// (r0, r1) differs from the previous step's, bit 30 when it moved on by exactly one row.
 struct LaneStep {
     double w0, w1;
     int32_t r0, r1;

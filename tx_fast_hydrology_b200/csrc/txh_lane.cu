@@ -173,7 +173,7 @@ route_lane_kernel(const LaneArgs a)
             const double2 cg = *reinterpret_cast<const double2*>(a.coef + 4 * (size_t)pos + 2);
             al = ab.x; be = ab.y; ch = cg.x; ga = cg.y;
             if (HAS_F) {
-                const int r0s = __ldg(&a.steps[0].r0), r1s = __ldg(&a.steps[0].r1) & 0x7fffffff;
+                const int r0s = __ldg(&a.steps[0].r0), r1s = __ldg(&a.steps[0].r1) & 0x3fffffff;
                 f0 = __ldg(a.F + (size_t)r0s * a.n + pos);
                 f1 = __ldg(a.F + (size_t)r1s * a.n + pos);
                 fn = __ldg(a.F + (size_t)min(max(r0s, r1s) + 1, a.R - 1) * a.n + pos);
@@ -239,12 +239,20 @@ route_lane_kernel(const LaneArgs a)
                         const int2 rr = *reinterpret_cast<const int2*>(&st->r0);
                         w0 = ww.x; w1 = ww.y; fr0 = rr.x; r1f = rr.y;
                     }
-                    fr1 = r1f & 0x7fffffff;
+                    fr1 = r1f & 0x3fffffff;
                     if (r1f < 0) {                               // the bracket differs from the previous step's
-                        int pr0, pr1;
-                        if (a.off_steps > 0) { const int4 pp = lds_i4(sSteps + 32u * (s - 1) + 16u); pr0 = pp.x; pr1 = pp.y; }
-                        else { pr0 = __ldg(&a.steps[s - 1].r0); pr1 = __ldg(&a.steps[s - 1].r1); }
-                        rotate_bracket(f0, f1, fn, a.F + pos, a.n, a.R, pr0, pr1 & 0x7fffffff, fr0, fr1);
+                        if (r1f & 0x40000000) {
+                            // the usual case, marked by lane_init_kernel: the bracket moved on by one row -- shift, and
+                            // request the row after it (its register is not read before the next change)
+                            f0 = f1; f1 = fn;
+                            const int nn = min(fr1 + 1, a.R - 1);
+                            if (nn != fr1) fn = __ldg(a.F + (size_t)nn * a.n + pos);
+                        } else {
+                            int pr0, pr1;
+                            if (a.off_steps > 0) { const int4 pp = lds_i4(sSteps + 32u * (s - 1) + 16u); pr0 = pp.x; pr1 = pp.y; }
+                            else { pr0 = __ldg(&a.steps[s - 1].r0); pr1 = __ldg(&a.steps[s - 1].r1); }
+                            rotate_bracket(f0, f1, fn, a.F + pos, a.n, a.R, pr0, pr1 & 0x3fffffff, fr0, fr1);
+                        }
                     }
                 }
                 double q = 0.0;
@@ -391,7 +399,7 @@ route_lane_kernel(const LaneArgs a)
     }
 }
 
-// forcing interpolation of the launch's steps (nutils.py:21-34), with the "bracket changed" mark on r1
+// forcing interpolation of the launch's steps (nutils.py:21-34); bit 31 of r1: the bracket changed, bit 30: by one row
 __global__ void __launch_bounds__(256) lane_init_kernel(const InitArgs a, LaneStep* out, unsigned long long* ticket)
 {
     const long long gid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -399,13 +407,16 @@ __global__ void __launch_bounds__(256) lane_init_kernel(const InitArgs a, LaneSt
     if (gid0 == 0) *ticket = 0ull;
     for (long long s = gid0; s < a.nsteps; s += stride) {
         const StepInterp si = interp_step(a.times, a.R, (double)(a.t0_ns + (a.step_base + s + 1) * a.dt_ns), a.method);
-        bool changed = false;
+        bool changed = false, regular = false;
         if (s > 0) {
             const StepInterp sp = interp_step(a.times, a.R, (double)(a.t0_ns + (a.step_base + s) * a.dt_ns), a.method);
             changed = sp.r0 != si.r0 || sp.r1 != si.r1;
+            // regular: the new bracket is (old r1, the row the kernel prefetched after the old bracket)
+            regular = changed && si.r0 == sp.r1 && si.r1 == min(max(sp.r0, sp.r1) + 1, a.R - 1) && si.r1 != si.r0;
         }
         LaneStep ls;
-        ls.w0 = si.w0; ls.w1 = si.w1; ls.r0 = si.r0; ls.r1 = si.r1 | (changed ? (int)0x80000000 : 0); ls.pad0 = ls.pad1 = 0;
+        ls.w0 = si.w0; ls.w1 = si.w1; ls.r0 = si.r0;
+        ls.r1 = si.r1 | (changed ? (int)0x80000000 : 0) | (regular ? 0x40000000 : 0); ls.pad0 = ls.pad1 = 0;
         out[s] = ls;
     }
 }

@@ -627,16 +627,28 @@ class BatchedKalmanFilters:
         table = np.ascontiguousarray(np.concatenate([f.values for f in frames], axis=1), dtype=np.float64)
         end_time = index.max()
         self._last_active = np.zeros(len(self.filters), dtype=np.uint8)
+        torch = self._torch
+        nsteps = 0 if not end_time > u.datetime else int(-((u.datetime - end_time) // u.timedelta))
+        # the hydrographs are recorded on the device (one unpack launch per step, no host round trip in the loop)
+        rec = torch.empty((nsteps + 1, u.n, 1), dtype=torch.float64, device='cuda')
+
+        def record(row):
+            u._ensure_device()
+            u.network.unpack_dev(u._dev['O'], 1, rec[row])
+
         self.filter()                                              # __on_simulation_start__ of every filter
-        rows, stamps = [u._peek_state('o_t_next')], [u.datetime]
+        record(0)
+        stamps, k = [u.datetime], 0
         while u.datetime < end_time:
             p = interpolate_sample(float((u.datetime + u.timedelta).value), times, table)
             u.step_iter(p)
             self.filter()                                          # __on_step_end__
-            rows.append(u._peek_state('o_t_next')); stamps.append(u.datetime)
+            k += 1
+            record(k)
+            stamps.append(u.datetime)
         self._write_back()
-        values = np.stack(rows)
-        return {m.name: (values[:, self.row0[k]:self.row0[k + 1]], list(stamps)) for k, m in enumerate(self.models)}
+        values = rec[:k + 1, :, 0].cpu().numpy()
+        return {m.name: (values[:, self.row0[i]:self.row0[i + 1]], list(stamps)) for i, m in enumerate(self.models)}
 
     def _write_back(self):
         """Sub-models and their filters end up where the per-model path would have left them."""
