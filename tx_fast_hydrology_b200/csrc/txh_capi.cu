@@ -59,6 +59,7 @@ struct txh_net {
     uint32_t *d_hdr = nullptr, *d_inw = nullptr;
     uint8_t* d_outlet = nullptr;
     int32_t* d_inner = nullptr; int64_t n_inner = 0;   // schedule positions that have upstream reaches
+    int4* d_inner_rec = nullptr;        // the same rows as {row, first three upstream rows | -1}; w == -2: more in the lists
     double* d_coef = nullptr;           // same layout as coef_host
     double* d_qtmp = nullptr;           // [n] schedule-order scratch for txh_route_step
     int32_t* d_pending = nullptr; size_t pairs_cap = 0;
@@ -74,6 +75,10 @@ struct txh_net {
     std::vector<int64_t> obs_cached;    // gauge list whose positions are resident in d_obs
     int32_t* d_obs = nullptr; size_t obs_cap = 0;
     int32_t* d_gauge_of_pos = nullptr;  // [n] gauge index of each schedule position, or -1
+    // ensemble update applied by the next window launch while it loads its tasks (txh_run_assimilating, txh_window.cu)
+    int32_t* d_gfix_off = nullptr;      // [window tasks + 1] gauge terms per task, for the gauges in obs_cached
+    int2* d_gfix = nullptr; size_t gfix_cap = 0; bool gfix_ok = false;
+    struct { const double* T = nullptr; const double* W = nullptr; const double* qs = nullptr; int64_t M = 0; } pending;
     // window-mode kernel
     WTaskDesc* d_wtasks = nullptr;
     uint32_t *d_whdr = nullptr, *d_winw = nullptr;
@@ -148,6 +153,13 @@ int ensure_device(txh_net* net)
         for (int64_t k = 0; k < net->topo.n; ++k) if (s.up_off[k + 1] > s.up_off[k]) inner.push_back((int32_t)k);
         net->n_inner = (int64_t)inner.size();
         if ((rc = upload(&net->d_inner, inner))) return rc;
+        std::vector<int4> rec(inner.size());
+        for (size_t e = 0; e < inner.size(); ++e) {
+            const int32_t k = inner[e], u0 = s.up_off[k], cnt = s.up_off[k + 1] - u0;
+            // the sum keeps the order of the lists (first upstream reach first), like nutils.py:84-85 does per visit
+            rec[e] = make_int4(k, s.up_pos[u0], cnt > 1 ? s.up_pos[u0 + 1] : -1, cnt > 3 ? -2 : (cnt > 2 ? s.up_pos[u0 + 2] : -1));
+        }
+        if ((rc = upload(&net->d_inner_rec, rec))) return rc;
     }
     if ((rc = upload(&net->d_lvl_pos, s.lvl_pos))) return rc;
     if ((rc = upload(&net->d_reach_of_pos, s.reach_of_pos))) return rc;
@@ -362,7 +374,7 @@ int run_dataflow(txh_net* net, double* O, double* I, int64_t M, const double* F,
 // Returns 1 when the schedule does not fit it (rows of a task x 1 KB per warp) and the caller should fall
 // back to the dataflow kernel.
 int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, const double* W, int wm_ld,
-               const StepPlan& plan, int64_t nsteps, cudaStream_t st)
+               const StepPlan& plan, int64_t nsteps, cudaStream_t st, bool probe_only = false)
 {
     const Schedule& s = net->sched;
     const int ld = (int)txh_row_stride(M);
@@ -386,7 +398,11 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     if ((size_t)std::max(1, s.n_wslots) * ld * sizeof(double) >= (size_t(1) << 32)) return 1;   // 32-bit slot offsets
     const int smem_max = 227 * 1024;
     int wpc = std::min(16, (smem_max - 1024) / a.smem_per_warp);
+    if (const char* k = getenv("TXH_WINDOW_WARPS")) wpc = std::max(1, std::min(wpc, atoi(k)));
     if (wpc < 2 || s.w_n_own > 0) return 1;
+    // a launch that applies an ensemble update keeps the 64 x 64 transform in shared memory: fewer warps per CTA
+    const int wpc_upd = std::min(wpc, (smem_max - 1024 - 64 * 64 * (int)sizeof(double)) / a.smem_per_warp);
+    if (probe_only) return wpc_upd >= 2 ? TXH_OK : 1;
     // ring[step][slot][ld]: one launch covers 16 steps, up to 64 while the ring stays below 64 MiB (few members):
     // a launch costs the critical path of one step before its pipeline is full, so longer launches amortise it
     const size_t slot_row = (size_t)std::max(1, s.n_wslots) * ld;
@@ -434,6 +450,14 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
         // the row sums ride on the last step of the call when one warp covers all members of a row
         a.rowsum = (net->stats_rowsum && nmb == 1 && s0 + ns == nsteps) ? net->stats_rowsum : nullptr;
         a.rowsum_scale = net->stats_scale;
+        a.upT = nullptr;
+        if (s0 == 0 && net->pending.T && nmb == 1 && net->pending.M == M && wpc_upd >= 2) {
+            // the ensemble update owed to the state is applied by this launch while it loads its tasks
+            a.upT = net->pending.T; a.upW = net->pending.W; a.upQs = net->pending.qs;
+            a.gfix_off = net->d_gfix_off; a.gfix = net->d_gfix;
+            a.off_T = wpc_upd * a.smem_per_warp;
+            net->pending.T = nullptr;
+        }
         a.trace = nullptr;
         const char* trace_file = getenv("TXH_TRACE_FILE");
         unsigned long long* d_trace = nullptr;
@@ -443,7 +467,7 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
             CU(cudaMemsetAsync(d_trace, 0, trace_words * sizeof(unsigned long long), st));
             a.trace = d_trace;
         }
-        CU(launch_route_window(a, wpc, net->num_sms, st));
+        CU(launch_route_window(a, a.upT ? wpc_upd : wpc, net->num_sms, st));
         if (d_trace) {
             // development aid: dump the per-task timeline of this launch (synchronous)
             std::vector<unsigned long long> h(trace_words);
@@ -707,6 +731,7 @@ int txh_create(int64_t n, const int64_t* endnodes, const int32_t* sp, txh_net** 
     if (sp) { p.long_path_min = sp[0]; p.spine_cap = sp[1]; p.pocket_cap = sp[2]; p.max_slots = sp[3]; p.link_cap = sp[4]; }
     if (const char* lw = getenv("TXH_LEN_WEIGHT")) p.len_weight = atoi(lw);
     if (const char* sc = getenv("TXH_SIDE_CAP")) p.side_cap = std::max(1, atoi(sc));
+    if (const char* pc = getenv("TXH_POCKET_CAP")) p.pocket_cap = std::max(4, std::min(16, atoi(pc)));
     if (!net->sched.build(net->topo, p, err)) { delete net; return fail(TXH_E_INVALID, err); }
     *out = net;
     return TXH_OK;
@@ -718,7 +743,7 @@ void txh_destroy(txh_net* net)
     if (net->dev_ready) {
         cudaFree(net->d_tasks); cudaFree(net->d_notify); cudaFree(net->d_init_ready); cudaFree(net->d_hdr); cudaFree(net->d_inw);
         for (auto& ev : net->route_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-        cudaFree(net->d_up_off); cudaFree(net->d_up_pos); cudaFree(net->d_lvl_pos); cudaFree(net->d_inner);
+        cudaFree(net->d_up_off); cudaFree(net->d_up_pos); cudaFree(net->d_lvl_pos); cudaFree(net->d_inner); cudaFree(net->d_inner_rec);
         cudaFree(net->d_reach_of_pos); cudaFree(net->d_pos_of_reach); cudaFree(net->d_outlet);
         cudaFree(net->d_coef); cudaFree(net->d_qtmp); cudaFree(net->d_qctl); cudaFree(net->d_rec_slot);
         cudaFree(net->d_unit_step);
@@ -729,6 +754,7 @@ void txh_destroy(txh_net* net)
         if (net->d_tmp_idx) cudaFree(net->d_tmp_idx);
         if (net->d_obs) cudaFree(net->d_obs);
         if (net->d_gauge_of_pos) cudaFree(net->d_gauge_of_pos);
+        cudaFree(net->d_gfix_off); cudaFree(net->d_gfix);
         cudaFree(net->d_wtasks); cudaFree(net->d_whdr); cudaFree(net->d_winw); cudaFree(net->d_wprod);
         if (net->d_ring) cudaFree(net->d_ring);
         if (net->d_lring) cudaFree(net->d_lring);
@@ -1220,6 +1246,37 @@ int obs_positions(txh_net* net, const int64_t* obs, int64_t m, cudaStream_t st, 
     if (!net->d_gauge_of_pos) CU(cudaMalloc((void**)&net->d_gauge_of_pos, sizeof(int32_t) * net->topo.n));
     CU(cudaMemcpyAsync(net->d_obs, pos.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(net->d_gauge_of_pos, gop.data(), sizeof(int32_t) * net->topo.n, cudaMemcpyHostToDevice, st));
+    // gauge terms of the update per window task (route_window_kernel applies the update while it loads a task): the
+    // gauged row itself (kind 0) and the row it drains into (kind 1: its inflow takes the gain of the gauged row,
+    // nutils.py:127-134; the up lists hold no self-loops)
+    const Schedule& s = net->sched;
+    const size_t ntask = s.wtasks.size();
+    std::vector<int32_t> task_of_pos(net->topo.n, -1), down(net->topo.n, -1);
+    for (size_t k = 0; k < ntask; ++k)
+        for (int32_t r = 0; r < s.wtasks[k].len; ++r) task_of_pos[s.wtasks[k].begin + r] = (int32_t)k;
+    for (int64_t k = 0; k < net->topo.n; ++k)
+        for (int32_t u = s.up_off[k]; u < s.up_off[k + 1]; ++u) down[s.up_pos[u]] = (int32_t)k;
+    std::vector<std::vector<int2>> per_task(ntask);
+    bool fix_ok = ntask > 0;
+    for (int64_t g = 0; g < m && fix_ok; ++g) {
+        const int32_t k = pos[g], d = down[k];
+        if (task_of_pos[k] < 0 || (d >= 0 && task_of_pos[d] < 0)) { fix_ok = false; break; }
+        per_task[task_of_pos[k]].push_back(make_int2(k - s.wtasks[task_of_pos[k]].begin, (int)g));
+        if (d >= 0) per_task[task_of_pos[d]].push_back(make_int2((d - s.wtasks[task_of_pos[d]].begin) | (1 << 16), (int)g));
+    }
+    std::vector<int32_t> goff(ntask + 1, 0);
+    std::vector<int2> gfix;
+    if (fix_ok)
+        for (size_t k = 0; k < ntask; ++k) { gfix.insert(gfix.end(), per_task[k].begin(), per_task[k].end()); goff[k + 1] = (int32_t)gfix.size(); }
+    if (!net->d_gfix_off) CU(cudaMalloc((void**)&net->d_gfix_off, sizeof(int32_t) * (ntask + 1)));
+    if (gfix.size() > net->gfix_cap || !net->d_gfix) {
+        if (net->d_gfix) CU(cudaFree(net->d_gfix));
+        net->gfix_cap = std::max<size_t>(gfix.size(), 16);
+        CU(cudaMalloc((void**)&net->d_gfix, sizeof(int2) * net->gfix_cap));
+    }
+    net->gfix_ok = fix_ok;
+    CU(cudaMemcpyAsync(net->d_gfix_off, goff.data(), sizeof(int32_t) * (ntask + 1), cudaMemcpyHostToDevice, st));
+    if (!gfix.empty()) CU(cudaMemcpyAsync(net->d_gfix, gfix.data(), sizeof(int2) * gfix.size(), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
     net->obs_cached.assign(obs, obs + m);
     *d_pos = net->d_obs;
@@ -1280,6 +1337,13 @@ int enkf_solve_impl(txh_net* net, int64_t m, int64_t Mtot, double* HX, const dou
     if (dinv_kind != 0 && Mtot < m) {
         // ensemble-space form (txh_da.cu): the Mtot x Mtot system replaces the m x m one and T is its solution
         const int Mt = (int)Mtot, nsplit = Mtot <= 128 ? 8 : 1;
+        static const bool fused_ok = [] { const char* k = getenv("TXH_ENKF_FUSED"); return !(k && atoi(k) == 0); }();
+        if (fused_ok && dinv_kind == 1 && Mt <= 64) {
+            // one cluster launch: gather, split-K product, reduction, Cholesky solve and W (txh_da.cu)
+            CU(launch_enkf_small_system(HX, O_gather, (int)txh_row_stride(Mtot), Zp, mean, d_pos, Dinv, (int)m, Mt,
+                                        (double)(Mtot - 1), T, W, info_word(net), st));
+            return TXH_OK;
+        }
         double* Bc = work;                                  // [m][2Mt] = [HA | dz]
         double* Y = Bc + 2 * m * Mtot;                      // [m][2Mt] = D^-1 Bc
         double* Cp = Y + 2 * m * Mtot;                      // [nsplit][Mt][2Mt] split-K partials of HA^T Y
@@ -1396,11 +1460,38 @@ int txh_run_assimilating(txh_net* net, double* O, double* I, int64_t M, const tx
     int rc = txh_set_stats_output(net, rowsum, 1.0 / (double)M);
     const int64_t nwin = nsteps / every;
     int64_t t = t0_ns;
+    const int ld = (int)txh_row_stride(M);
+    // Right after a routing launch the forecast inflows are exactly the sums of the upstream forecast outflows
+    // (nutils.py:84-85), so i + N gain = N (o + gain): the gains are never stored.  When the window kernel routes the
+    // next window, it applies the update itself while it loads its tasks (p is linear in the state rows, txh_window.cu):
+    // the posterior state only goes to memory after the last window; otherwise the transform kernel updates O in place
+    // and the posterior inflows are rebuilt from the posterior outflows.
+    static const bool fuse_load_ok = [] { const char* k = getenv("TXH_ENKF_FUSE_LOAD"); return !(k && atoi(k) == 0); }();
+    bool fuse_load = false;
+    if (rc == TXH_OK && fuse_load_ok && ld <= kMemberBlock && (rc = ensure_device(net)) == TXH_OK)
+        fuse_load = (net->route_kernel == 0 || net->route_kernel == 2) && !lane_wanted(net, M, every) &&
+                    run_window(net, O, I, M, nullptr, nullptr, 0, StepPlan(), every, st, true) == TXH_OK;
+    bool owed = false;                                     // an update computed (T, W) but not yet applied to O, I
+    auto apply_owed = [&]() -> int {
+        CU(launch_enkf_update(O, ld, (int)M, rowsum, T, (int)M, (int)M, O, nullptr, ld, net->topo.n, net->d_gauge_of_pos,
+                              qs, W, 0, net->num_sms, (int)M, 0, st));
+        CU(launch_inflow_rebuild(net->d_inner_rec, net->n_inner, net->d_up_off, net->d_up_pos, O, I, ld, st));
+        owed = false;
+        return TXH_OK;
+    };
     for (int64_t k = 0; k < nwin && rc == TXH_OK; ++k) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         const bool timed = time_every > 0 && k % time_every == 0 && net->route_events.size() < 4096;
         if (timed) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, st)); }
-        rc = txh_route_run(net, O, I, M, fo, t, dt_ns, every, method, nullptr, 0, 1, nullptr, stream);
+        if (owed) {
+            if (net->gfix_ok) { net->pending.T = T; net->pending.W = W; net->pending.qs = qs; net->pending.M = M; }
+            else rc = apply_owed();
+        }
+        if (rc == TXH_OK) rc = txh_route_run(net, O, I, M, fo, t, dt_ns, every, method, nullptr, 0, 1, nullptr, stream);
+        if (rc == TXH_OK && owed) {
+            if (net->pending.T) { net->pending.T = nullptr; rc = fail(TXH_E_STATE, "the routing launch did not take the pending ensemble update"); }
+            owed = false;
+        }
         if (timed) { CU(cudaEventRecord(e1, st)); net->route_events.emplace_back(e0, e1); }
         t += every * dt_ns;
         // observations still on their way (copied on another stream): the first update waits for them, the first
@@ -1409,21 +1500,26 @@ int txh_run_assimilating(txh_net* net, double* O, double* I, int64_t M, const tx
         if (rc == TXH_OK) rc = check_M(M);
         if (rc == TXH_OK) rc = enkf_solve_impl(net, m, M, HX, O, Zp + (size_t)k * m * M, rowsum, obs, qs, R, Dinv, dinv_kind, work, W, T, stream);
         if (rc != TXH_OK) break;
-        if (txh_row_stride(M) <= 64) {
-            // right after a routing launch the forecast inflows are exactly the sums of the upstream forecast outflows
-            // (nutils.py:84-85), so i + N gain = N (o + gain): the transform updates O in place without storing the
-            // gains, and the posterior inflows are rebuilt from the posterior outflows
-            const int ld = (int)txh_row_stride(M);
-            CU(launch_enkf_update(O, ld, (int)M, rowsum, T, (int)M, (int)M, O, nullptr, ld, net->topo.n, net->d_gauge_of_pos,
-                                  qs, W, 0, net->num_sms, (int)M, 0, st));
-            CU(launch_inflow_rebuild(net->d_inner, net->n_inner, net->d_up_off, net->d_up_pos, O, I, ld, st));
+        if (ld <= kMemberBlock) {
+            owed = true;
+            if (!fuse_load) rc = apply_owed();
         } else {
             rc = txh_enkf_apply(net, O, I, M, nullptr, 0, 0, M, 0, rowsum, T, obs, m, qs, W, G, stream);
         }
     }
     net->stats_rowsum = nullptr;
-    if (rc == TXH_OK && nsteps > nwin * every)
-        rc = txh_route_run(net, O, I, M, fo, t, dt_ns, nsteps - nwin * every, method, nullptr, 0, 1, nullptr, stream);
+    if (rc == TXH_OK && nsteps > nwin * every) {
+        if (owed && net->gfix_ok && !lane_wanted(net, M, nsteps - nwin * every)) {
+            net->pending.T = T; net->pending.W = W; net->pending.qs = qs; net->pending.M = M;
+        } else if (owed) rc = apply_owed();
+        if (rc == TXH_OK) rc = txh_route_run(net, O, I, M, fo, t, dt_ns, nsteps - nwin * every, method, nullptr, 0, 1, nullptr, stream);
+        if (rc == TXH_OK && owed) {
+            if (net->pending.T) { net->pending.T = nullptr; rc = fail(TXH_E_STATE, "the routing launch did not take the pending ensemble update"); }
+            owed = false;
+        }
+    }
+    if (rc == TXH_OK && owed) rc = apply_owed();           // after the last window the posterior goes to memory
+    net->pending.T = nullptr;
     net->stats_rowsum = rowsum_before; net->stats_scale = scale_before;
     return rc;
 }

@@ -6,9 +6,12 @@
 // DMMA in SASS); everything else (means, gathers, the small SPD solve) is plain FP64.
 // Matrices are row-major.  State matrices are the routing layout: one row per reach (schedule
 // order), members contiguous, `ld` doubles per row.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 
 #include "txh_kernels.cuh"
 
@@ -348,74 +351,19 @@ innovation_cat_kernel(double* __restrict__ HX, const double* __restrict__ O, int
 // blocked one below 31 us.)
 constexpr int CS_NSPLIT = 8;
 
-// Blocked small solve: the matrix lives in shared memory, panels of 8 columns.
+// Factorisation A = L L^T of the MT x MT matrix in shared memory (lower triangle, leading dimension MT + 1) and the
+// solve for the CTA's 8 right-hand-side columns Bs [MT][9], in place.  256 threads; the caller has synchronised.
 //   panel   : warp 0 keeps the panel rows in registers (lane l owns rows j0+l, j0+l+32, ...) and factors the 8
 //             columns with shuffles -- no barrier inside a panel -- then solves the 8 matching rows of B;
 //   trailing: every warp takes 8x8 tiles of the lower triangle (and of B) and applies the rank-8 update with
 //             two FP64 tensor-core MMAs per tile;
 // two barriers per panel instead of one per column; the backward substitution is blocked the same way.
-// Right-hand sides are split over CTAs, 8 columns each (every CTA repeats the factorisation).
 template <int MT>
-__global__ void __launch_bounds__(256)
-chol_solve_blocked_kernel(const double* __restrict__ Cpart, long long pstride, int Mt, double shift,
-                          double* __restrict__ Z, int* __restrict__ info)
+__device__ __forceinline__ void chol_factor_solve_smem(double* A, double* Bs, double* invd, int* info, bool report)
 {
     constexpr int LD = MT + 1, NT = MT / 8, RPL = MT / 32, LDB = 9;
-    extern __shared__ double sm[];
-    double* A = sm;                       // [MT][MT+1], lower triangle: working matrix, then L
-    double* Bs = A + MT * LD;             // [MT][9]     this CTA's 8 right-hand-side columns
-    double* invd = Bs + MT * LDB;         // [MT]        1 / L[j][j]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int gc0 = blockIdx.x * 8;
-    // the split-K partials are summed on the way in: 8 elements x 8 partials in flight per thread, lower triangle
-    // only (the upper one is never read)
-    for (int e0 = 0; e0 < MT * MT; e0 += 8 * 256) {
-        double part[8][CS_NSPLIT];
-        // unconditional loads (an element that is not needed reads element 0): all 64 are issued before the first add
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * 256 + tid;
-            const int i = e / MT, c = e - i * MT;
-            const bool need = e < MT * MT && i < Mt && c <= i;
-            const double* src = Cpart + (need ? (size_t)i * 2 * Mt + c : 0);
-#pragma unroll
-            for (int s = 0; s < CS_NSPLIT; ++s) part[u][s] = __ldg(src + (size_t)s * pstride);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * 256 + tid;
-            const int i = e / MT, c = e - i * MT;
-            const bool need = e < MT * MT && i < Mt && c <= i;
-            double acc = (i == c) ? shift : 0.0;
-#pragma unroll
-            for (int s = 0; s < CS_NSPLIT; ++s) acc += part[u][s];
-            if (e < MT * MT) A[i * LD + c] = need ? acc : ((i == c) ? 1.0 : 0.0);
-        }
-    }
-    {
-        constexpr int NB = MT * 8 / 256;                       // right-hand-side elements per thread
-        double part[NB][CS_NSPLIT];
-#pragma unroll
-        for (int u = 0; u < NB; ++u) {
-            const int e = tid + u * 256;
-            const int i = e >> 3, cl = e & 7;
-            const bool need = i < Mt && gc0 + cl < Mt;
-            const double* src = Cpart + (need ? (size_t)i * 2 * Mt + Mt + gc0 + cl : 0);
-#pragma unroll
-            for (int s = 0; s < CS_NSPLIT; ++s) part[u][s] = __ldg(src + (size_t)s * pstride);
-        }
-#pragma unroll
-        for (int u = 0; u < NB; ++u) {
-            const int e = tid + u * 256;
-            const int i = e >> 3, cl = e & 7;
-            double v = 0.0;
-#pragma unroll
-            for (int s = 0; s < CS_NSPLIT; ++s) v += part[u][s];
-            Bs[i * LDB + cl] = (i < Mt && gc0 + cl < Mt) ? v : 0.0;
-        }
-    }
-    __syncthreads();
     // ---- factorisation + forward substitution, panel by panel ----
     for (int p = 0; p < NT; ++p) {
         const int j0 = 8 * p;
@@ -430,7 +378,7 @@ chol_solve_blocked_kernel(const double* __restrict__ Cpart, long long pstride, i
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
                 double d = __shfl_sync(0xffffffffu, x[0][jj], jj);              // pivot: row j0+jj lives in lane jj
-                if (!(d > 0.0)) { if (lane == 0 && blockIdx.x == 0) *info = j0 + jj + 1; d = 1.0; }
+                if (!(d > 0.0)) { if (lane == 0 && report) *info = j0 + jj + 1; d = 1.0; }
                 const double rs = rsqrt(d);
                 if (lane == 0) invd[j0 + jj] = rs;
                 double l[RPL];
@@ -526,10 +474,284 @@ chol_solve_blocked_kernel(const double* __restrict__ Cpart, long long pstride, i
         }
         __syncthreads();
     }
+}
+
+// Blocked small solve (chol_factor_solve_smem) fed by the split-K partials of a GEMM launch.
+// Right-hand sides are split over CTAs, 8 columns each (every CTA repeats the factorisation).
+template <int MT>
+__global__ void __launch_bounds__(256)
+chol_solve_blocked_kernel(const double* __restrict__ Cpart, long long pstride, int Mt, double shift,
+                          double* __restrict__ Z, int* __restrict__ info)
+{
+    constexpr int LD = MT + 1, LDB = 9;
+    extern __shared__ double sm[];
+    double* A = sm;                       // [MT][MT+1], lower triangle: working matrix, then L
+    double* Bs = A + MT * LD;             // [MT][9]     this CTA's 8 right-hand-side columns
+    double* invd = Bs + MT * LDB;         // [MT]        1 / L[j][j]
+    const int tid = threadIdx.x;
+    const int gc0 = blockIdx.x * 8;
+    // the split-K partials are summed on the way in: 8 elements x 8 partials in flight per thread, lower triangle
+    // only (the upper one is never read)
+    for (int e0 = 0; e0 < MT * MT; e0 += 8 * 256) {
+        double part[8][CS_NSPLIT];
+        // unconditional loads (an element that is not needed reads element 0): all 64 are issued before the first add
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * 256 + tid;
+            const int i = e / MT, c = e - i * MT;
+            const bool need = e < MT * MT && i < Mt && c <= i;
+            const double* src = Cpart + (need ? (size_t)i * 2 * Mt + c : 0);
+#pragma unroll
+            for (int s = 0; s < CS_NSPLIT; ++s) part[u][s] = __ldg(src + (size_t)s * pstride);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * 256 + tid;
+            const int i = e / MT, c = e - i * MT;
+            const bool need = e < MT * MT && i < Mt && c <= i;
+            double acc = (i == c) ? shift : 0.0;
+#pragma unroll
+            for (int s = 0; s < CS_NSPLIT; ++s) acc += part[u][s];
+            if (e < MT * MT) A[i * LD + c] = need ? acc : ((i == c) ? 1.0 : 0.0);
+        }
+    }
+    {
+        constexpr int NB = MT * 8 / 256;                       // right-hand-side elements per thread
+        double part[NB][CS_NSPLIT];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int e = tid + u * 256;
+            const int i = e >> 3, cl = e & 7;
+            const bool need = i < Mt && gc0 + cl < Mt;
+            const double* src = Cpart + (need ? (size_t)i * 2 * Mt + Mt + gc0 + cl : 0);
+#pragma unroll
+            for (int s = 0; s < CS_NSPLIT; ++s) part[u][s] = __ldg(src + (size_t)s * pstride);
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int e = tid + u * 256;
+            const int i = e >> 3, cl = e & 7;
+            double v = 0.0;
+#pragma unroll
+            for (int s = 0; s < CS_NSPLIT; ++s) v += part[u][s];
+            Bs[i * LDB + cl] = (i < Mt && gc0 + cl < Mt) ? v : 0.0;
+        }
+    }
+    __syncthreads();
+    chol_factor_solve_smem<MT>(A, Bs, invd, info, blockIdx.x == 0);
     for (int e = tid; e < MT * 8; e += 256) {
         const int i = e >> 3, cl = e & 7;
         if (i < Mt && gc0 + cl < Mt) Z[(size_t)i * Mt + gc0 + cl] = Bs[i * LDB + cl];
     }
+}
+
+// ---- the whole ensemble-space system in ONE launch (Mt <= 64, diagonal D) ---------------------------------------
+// A cluster of 8 CTAs replaces innovation_cat + split-K GEMM + chol_solve_blocked + GEMM (4 launches, 3 trips through
+// global memory):
+//   1. CTA r gathers its share of the gauge rows, [HA | dz] -> shared memory, and multiplies its split-K partial of
+//      C = HA^T D^-1 [HA | dz] on the FP64 tensor cores (D^-1 rides on the A fragments);
+//   2. the partials are summed over the cluster through distributed shared memory: every CTA takes the lower triangle of
+//      C0 (+ shift I) and its own 8 columns of C1;
+//   3. every CTA factors C0 + shift I (repeated, as in chol_solve_blocked_kernel) and solves its 8 columns of Z = T;
+//      the columns are scattered into every CTA's copy of Z (distributed shared memory) and written to T;
+//   4. CTA r forms W = D^-1 (dz - HA Z) for its gauges from the tile it still holds.
+constexpr int SS_NC = 8;                         // CTAs per cluster
+constexpr int SS_KT = 64;                        // gauges per shared-memory tile
+constexpr int SS_LDB = 136;                      // [HA | dz] row stride in doubles (128 + 8: conflict-free fragments)
+constexpr int SS_LDZ = 72;
+constexpr int SS_OFF_C = SS_KT * SS_LDB;                   // sC   [64][128]
+constexpr int SS_OFF_A = SS_OFF_C + 64 * 128;              // A    [64][65]
+constexpr int SS_OFF_BS = SS_OFF_A + 64 * 65;              // Bs   [64][9]
+constexpr int SS_OFF_INVD = SS_OFF_BS + 64 * 9;            // invd [64]
+constexpr int SS_OFF_Z = SS_OFF_INVD + 64;                 // sZ   [64][72]
+constexpr int SS_OFF_D = SS_OFF_Z + 64 * SS_LDZ;           // sd   [64]
+constexpr int SS_SMEM = (SS_OFF_D + SS_KT) * 8;            // 210,944 bytes
+
+__global__ void __cluster_dims__(SS_NC, 1, 1) __launch_bounds__(256, 1)
+enkf_small_system_kernel(double* __restrict__ HX, const double* __restrict__ O, int ldo, const double* __restrict__ Zp,
+                         const double* __restrict__ mean, const int32_t* __restrict__ obs_pos,
+                         const double* __restrict__ dinv, int m, int Mt, double shift, double* __restrict__ T,
+                         double* __restrict__ W, int* __restrict__ info, unsigned long long* __restrict__ trace)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    extern __shared__ double ss[];
+    double* sB = ss;
+    double* sC = ss + SS_OFF_C;
+    double* A = ss + SS_OFF_A;
+    double* Bs = ss + SS_OFF_BS;
+    double* invd = ss + SS_OFF_INVD;
+    double* sZ = ss + SS_OFF_Z;
+    double* sd = ss + SS_OFF_D;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int mc = (((m + SS_NC - 1) / SS_NC) + 3) & ~3;           // gauges per CTA
+    const int k_lo = min(m, rank * mc), k_hi = min(m, k_lo + mc);
+    auto stamp = [&](int i) {                                      // development aid (TXH_SS_TRACE): phase timeline
+        if (trace && tid == 0) {
+            unsigned long long ns;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+            trace[rank * 8 + i] = ns;
+        }
+    };
+    stamp(0);
+
+    // [HA | dz] of the gauges kt .. kt+63 -> sB (zero rows beyond k_hi), D^-1 -> sd; every load of a thread's 16
+    // elements is in flight before the first use
+    auto load_tile = [&](int kt) {
+        const int c = tid & 63;
+        int pos[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int k = kt + (tid >> 6) + 4 * u;
+            pos[u] = k < k_hi ? __ldg(obs_pos + k) : -1;
+        }
+        double hx[16], zp[16], mu[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int k = kt + (tid >> 6) + 4 * u;
+            const bool on = pos[u] >= 0 && c < Mt;
+            hx[u] = on ? (O ? __ldcg(O + (size_t)pos[u] * ldo + c) : __ldcg(HX + (size_t)k * Mt + c)) : 0.0;
+            zp[u] = on ? __ldg(Zp + (size_t)k * Mt + c) : 0.0;
+            mu[u] = on ? __ldcg(mean + pos[u]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int kk = (tid >> 6) + 4 * u, k = kt + kk;
+            const bool on = pos[u] >= 0 && c < Mt;
+            if (on && O) HX[(size_t)k * Mt + c] = hx[u];
+            sB[kk * SS_LDB + c] = hx[u] - mu[u];
+            sB[kk * SS_LDB + 64 + c] = zp[u] - hx[u];
+        }
+        if (tid < SS_KT) sd[tid] = kt + tid < k_hi ? __ldg(dinv + kt + tid) : 0.0;
+    };
+
+    // ---- 1. split-K partial of C = HA^T D^-1 [HA | dz]: warp tile 16 x 64 of the 64 x 128 product ----
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 64;
+    double acc[2][8][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kt = k_lo; kt == k_lo || kt < k_hi; kt += SS_KT) {
+        if (kt != k_lo) __syncthreads();
+        load_tile(kt);
+        __syncthreads();
+        const int nk = min(SS_KT, (max(k_hi - kt, 0) + 3) & ~3);
+        for (int kk = 0; kk < nk; kk += 4) {
+            const double* row = sB + (kk + t) * SS_LDB;
+            const double d = sd[kk + t];
+            double a[2], b[8];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) a[i] = d * row[wm + 8 * i + g];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = row[wn + 8 * j + g];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<double2*>(sC + (wm + 8 * i + g) * 128 + wn + 8 * j + 2 * t) =
+                make_double2(acc[i][j][0], acc[i][j][1]);
+    stamp(1);
+    cluster.sync();
+    stamp(2);
+
+    // ---- 2. sum over the cluster: lower triangle of C0 + shift I -> A, this CTA's 8 columns of C1 -> Bs ----
+    const double* rc[SS_NC];
+#pragma unroll
+    for (int r = 0; r < SS_NC; ++r) rc[r] = cluster.map_shared_rank(sC, r);
+    const int gc0 = rank * 8;
+    for (int e0 = 0; e0 < 64 * 64; e0 += 8 * 256) {
+        double part[8][SS_NC];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * 256 + tid;
+            const int i = e >> 6, c = e & 63;
+            const int off = c <= i ? i * 128 + c : 0;
+#pragma unroll
+            for (int r = 0; r < SS_NC; ++r) part[u][r] = rc[r][off];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * 256 + tid;
+            const int i = e >> 6, c = e & 63;
+            double v = (i == c) ? shift : 0.0;
+#pragma unroll
+            for (int r = 0; r < SS_NC; ++r) v += part[u][r];
+            A[i * 65 + c] = c <= i ? v : 0.0;
+        }
+    }
+    {
+        double part[2][SS_NC];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = tid + u * 256;
+            const int off = (e >> 3) * 128 + 64 + gc0 + (e & 7);
+#pragma unroll
+            for (int r = 0; r < SS_NC; ++r) part[u][r] = rc[r][off];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = tid + u * 256;
+            double v = 0.0;
+#pragma unroll
+            for (int r = 0; r < SS_NC; ++r) v += part[u][r];
+            Bs[(e >> 3) * 9 + (e & 7)] = v;
+        }
+    }
+    __syncthreads();
+    stamp(3);
+
+    // ---- 3. (C0 + shift I) Z = C1 for this CTA's columns; Z goes to T and into every CTA's sZ ----
+    chol_factor_solve_smem<64>(A, Bs, invd, info, rank == 0);
+    stamp(4);
+    for (int e = tid; e < 64 * 8; e += 256) {
+        const int i = e >> 3, cl = e & 7;
+        const double v = Bs[i * 9 + cl];
+        if (i < Mt && gc0 + cl < Mt) T[(size_t)i * Mt + gc0 + cl] = v;
+#pragma unroll
+        for (int r = 0; r < SS_NC; ++r) cluster.map_shared_rank(sZ, r)[i * SS_LDZ + gc0 + cl] = v;
+    }
+    cluster.sync();
+    stamp(5);
+
+    // ---- 4. W = D^-1 (dz - HA Z) for this CTA's gauges: warp tile 8 gauges x 64 columns ----
+    for (int kt = k_lo; kt < k_hi; kt += SS_KT) {
+        if (k_hi - k_lo > SS_KT) {                             // several tiles: fetch this one again (L2)
+            __syncthreads();
+            load_tile(kt);
+            __syncthreads();
+        }
+        double w[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j][0] = w[j][1] = 0.0;
+        const double* hrow = sB + (8 * warp + g) * SS_LDB;
+#pragma unroll 4
+        for (int kk = 0; kk < 64; kk += 4) {
+            const double a = hrow[kk + t];
+            const double* zr = sZ + (kk + t) * SS_LDZ + g;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dmma8x8x4(w[j][0], w[j][1], a, zr[8 * j]);
+        }
+        const int k = kt + 8 * warp + g;
+        if (k < k_hi) {
+            const double d = sd[8 * warp + g];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = 8 * j + 2 * t;
+                if (col < Mt) W[(size_t)k * Mt + col] = d * (hrow[64 + col] - w[j][0]);
+                if (col + 1 < Mt) W[(size_t)k * Mt + col + 1] = d * (hrow[64 + col + 1] - w[j][1]);
+            }
+        }
+    }
+    stamp(6);
 }
 
 // sum of the split-K partials of C = [C0 | C1] -> Cf = C0 + shift*I and C1 as two dense Mt x Mt matrices
@@ -842,23 +1064,44 @@ inflow_gain_kernel(const int32_t* __restrict__ inner, long long n_inner, const i
 // The same update when the forecast inflows ARE the sums of the upstream forecast outflows (true right after a routing
 // step: nutils.py:84-85 builds i_t_next that way): i + N gain = N (o + gain), so the posterior inflows are rebuilt from
 // the posterior outflows and the gains never go to memory.
+// `rec` packs what a row needs into one 16-byte record {row, up to three upstream rows (-1: none)} -- one load between
+// the thread and its outflow rows instead of the chain inner -> up_off -> up_pos; rec.w == -2 marks a confluence of more
+// than three reaches, which takes the lists.  Two rows per thread, all loads in flight before the first add.
 __global__ void __launch_bounds__(256)
-inflow_rebuild_kernel(const int32_t* __restrict__ inner, long long n_inner, const int32_t* __restrict__ up_off,
+inflow_rebuild_kernel(const int4* __restrict__ rec, long long n_inner, const int32_t* __restrict__ up_off,
                       const int32_t* __restrict__ up_pos, const double* __restrict__ O, double* __restrict__ I, int ld)
 {
     const int half = ld >> 1;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n_inner * half) return;
-    const long long e = gid / half;
-    const int col = (int)(gid - e * half) * 2;
-    const long long k = inner[e];
-    const int u0 = up_off[k], u1 = up_off[k + 1];
-    double2 s = make_double2(0.0, 0.0);
-    for (int u = u0; u < u1; ++u) {
-        const double2 v = __ldcg(reinterpret_cast<const double2*>(O + (size_t)up_pos[u] * ld + col));
-        s.x += v.x; s.y += v.y;
+    const long long pairs = (n_inner + 1) >> 1;
+    if (gid >= pairs * half) return;
+    const long long e0 = (gid / half) * 2;
+    const int col = (int)(gid % half) * 2;
+    int4 r[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) r[q] = e0 + q < n_inner ? __ldg(rec + e0 + q) : make_int4(-1, -1, -1, -1);
+    double2 v[2][3];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int u[3] = {r[q].y, r[q].z, r[q].w};
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            v[q][j] = u[j] >= 0 ? __ldcg(reinterpret_cast<const double2*>(O + (size_t)u[j] * ld + col)) : make_double2(0.0, 0.0);
     }
-    __stcg(reinterpret_cast<double2*>(I + (size_t)k * ld + col), s);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (r[q].x < 0) continue;
+        double2 s = v[q][0];
+        if (r[q].z >= 0) { s.x += v[q][1].x; s.y += v[q][1].y; }
+        if (r[q].w >= 0) { s.x += v[q][2].x; s.y += v[q][2].y; }
+        if (r[q].w == -2) {
+            for (int u = up_off[r[q].x] + 2; u < up_off[r[q].x + 1]; ++u) {
+                const double2 x = __ldcg(reinterpret_cast<const double2*>(O + (size_t)up_pos[u] * ld + col));
+                s.x += x.x; s.y += x.y;
+            }
+        }
+        __stcg(reinterpret_cast<double2*>(I + (size_t)r[q].x * ld + col), s);
+    }
 }
 
 inline unsigned nblk(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
@@ -925,6 +1168,44 @@ cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long p
     kern<<<ncta, 256, smem_b, st>>>(Cpart, pstride, Mt, shift, Z, info);
     count_launch();
     return cudaGetLastError();
+}
+
+// The ensemble-space system in one cluster launch (Mt <= 64, D diagonal): HX (gathered from O when O != nullptr), T, W.
+cudaError_t launch_enkf_small_system(double* HX, const double* O, int ldo, const double* Zp, const double* mean,
+                                     const int32_t* obs_pos, const double* dinv_diag, int m, int Mt, double shift,
+                                     double* T, double* W, int* info, cudaStream_t st)
+{
+    if (Mt > 64 || Mt < 1 || m < 1) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(enkf_small_system_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM);
+    if (e != cudaSuccess) return e;
+    static const char* trace_file = getenv("TXH_SS_TRACE");
+    unsigned long long* d_trace = nullptr;
+    if (trace_file && *trace_file) {
+        if ((e = cudaMalloc((void**)&d_trace, SS_NC * 8 * sizeof(unsigned long long))) != cudaSuccess) return e;
+        cudaMemsetAsync(d_trace, 0, SS_NC * 8 * sizeof(unsigned long long), st);
+    }
+    enkf_small_system_kernel<<<SS_NC, 256, SS_SMEM, st>>>(HX, O, ldo, Zp, mean, obs_pos, dinv_diag, m, Mt, shift, T, W, info,
+                                                          d_trace);
+    count_launch();
+    e = cudaGetLastError();
+    if (d_trace) {
+        // development aid: per-CTA phase stamps (ns relative to the first) appended to the file, synchronous
+        unsigned long long h[SS_NC * 8];
+        cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        cudaFree(d_trace);
+        if (FILE* fp = fopen(trace_file, "a")) {
+            unsigned long long t0 = ~0ull;
+            for (int r = 0; r < SS_NC; ++r) if (h[r * 8] && h[r * 8] < t0) t0 = h[r * 8];
+            for (int r = 0; r < SS_NC; ++r) {
+                for (int i = 0; i < 7; ++i) fprintf(fp, "%lld ", (long long)(h[r * 8 + i] - t0));
+                fprintf(fp, "\n");
+            }
+            fprintf(fp, "\n");
+            fclose(fp);
+        }
+    }
+    return e;
 }
 
 cudaError_t launch_woodbury_assemble(const double* Cpart, int nsplit, long long pstride, int Mt, double shift, double* Cf,
@@ -1030,11 +1311,11 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
     return cudaGetLastError();
 }
 
-cudaError_t launch_inflow_rebuild(const int32_t* inner, int64_t n_inner, const int32_t* up_off, const int32_t* up_pos,
+cudaError_t launch_inflow_rebuild(const int4* rec, int64_t n_inner, const int32_t* up_off, const int32_t* up_pos,
                                   const double* O, double* I, int ld, cudaStream_t st)
 {
     if (n_inner == 0) return cudaSuccess;
-    inflow_rebuild_kernel<<<nblk(n_inner * (ld >> 1), 256), 256, 0, st>>>(inner, n_inner, up_off, up_pos, O, I, ld);
+    inflow_rebuild_kernel<<<nblk(((n_inner + 1) >> 1) * (ld >> 1), 256), 256, 0, st>>>(rec, n_inner, up_off, up_pos, O, I, ld);
     count_launch();
     return cudaGetLastError();
 }

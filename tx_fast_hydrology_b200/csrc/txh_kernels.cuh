@@ -127,6 +127,14 @@ struct WinArgs {
     unsigned long long* trace;            // optional [pairs][4 + nsteps] timeline (claim, loaded, end, kind|smid, publish per step)
     double* rowsum;                       // optional [n]: scale * sum over the members of the final outflows (n_mblocks == 1)
     double rowsum_scale;
+    // optional: the ensemble update that is still owed to the state (txh_run_assimilating), applied while a task is
+    // loaded -- p+ = p + (p - mean(p)) T + gauge terms, see route_window_kernel (n_mblocks == 1)
+    const double* upT;                    // [M][M] ensemble transform, nullptr = no update pending
+    int32_t off_T;                        // CTA-wide shared-memory copy of T (32 KB, behind the per-warp areas)
+    const double* upW;                    // [gauges][M]
+    const double* upQs;                   // [gauges]
+    const int32_t* gfix_off;              // [n_tasks + 1] gauge terms per task
+    const int2* gfix;                     // {row in task | kind << 16 (0: the row's own gauge, chi; 1: an upstream gauge, beta), gauge}
 };
 
 // route_lane_kernel (txh_lane.cu): lanes = reaches, time-skewed regions, state in shared memory
@@ -210,6 +218,9 @@ cudaError_t launch_innovation_cat(double* HX, const double* O, int ldo, const do
                                   cudaStream_t st);
 cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long pstride, int Mt, double shift, double* Z,
                                     int* info, cudaStream_t st);
+cudaError_t launch_enkf_small_system(double* HX, const double* O, int ldo, const double* Zp, const double* mean,
+                                     const int32_t* obs_pos, const double* dinv_diag, int m, int Mt, double shift,
+                                     double* T, double* W, int* info, cudaStream_t st);
 cudaError_t launch_dgemm_ex(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
                             const double* B, int ldb, double beta, const double* Cin, int ldcin, double* C, int ldc,
                             cudaStream_t st);
@@ -232,7 +243,7 @@ cudaError_t launch_enkf_update(const double* Xall, int ldx, int Mtot, const doub
                                int Mloc, double* O, double* G, int ld, int64_t n, const int32_t* gauge_of_pos,
                                const double* qs, const double* W, int col0, int num_sms, int Mb, long long blk_stride,
                                cudaStream_t st, const PeerBlocks* peers = nullptr, double* Oout = nullptr);
-cudaError_t launch_inflow_rebuild(const int32_t* inner, int64_t n_inner, const int32_t* up_off, const int32_t* up_pos,
+cudaError_t launch_inflow_rebuild(const int4* rec, int64_t n_inner, const int32_t* up_off, const int32_t* up_pos,
                                   const double* O, double* I, int ld, cudaStream_t st);
 cudaError_t launch_inflow_gain(const int32_t* inner, int64_t n_inner, const int32_t* up_off, const int32_t* up_pos,
                                const double* G, double* I, int ld, cudaStream_t st);

@@ -398,10 +398,81 @@ __device__ __forceinline__ void segment_step(const WinArgs& a, const Tk& tk, InS
     }
 }
 
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor cores.  lane = 4g + t: a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1]
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// The ensemble update owed to the state, applied to the freshly loaded p rows of a task (da.py:112-126 in ensemble
+// form, see txh_da.cu).  The update acts on the member axis, o+ = o + (o - mean(o)) T (+ qs W on gauged rows), and
+// after a routing step i = sum of the upstream o, so i+ = sum of the upstream o+ = i + (i - mean(i)) T (+ the gauge
+// terms of the upstream rows); p = beta i + chi o is linear in both with per-row scalars, hence
+//     p+ = p + (p - mean(p)) T + chi qs_g W_g [row gauged] + beta sum over gauged upstream rows of qs_u W_u
+// and the posterior state never makes the trip through HBM: the next window starts from the prior rows the last one
+// wrote.  8-row tiles on the FP64 tensor cores; lane (g, t) owns row g, members 8j + 2t, 8j + 2t + 1 of a tile (the
+// k index of a fragment is permuted accordingly, as in enkf_update64_kernel).  T lives in shared memory, once per
+// CTA, zero-padded to 64 x 64 and swizzled: element (k, c) at k*64 + (((c >> 3) ^ ((k >> 1) & 3)) << 3) + (c & 7), so
+// the four rows k0, k0+2, k0+4, k0+6 a B fragment touches fall into different banks without padding.
+__device__ __forceinline__ unsigned t_swz(int k, int c) { return (unsigned)(k * 64 + ((((c >> 3) ^ ((k >> 1) & 3)) << 3) | (c & 7))) * 8u; }
+
+__device__ __noinline__ void transform_p_rows(const WinArgs& a, unsigned sb, unsigned sT, int len, int lane)
+{
+    const int g = lane >> 2, t = lane & 3, M = a.M;
+    const double invM = 1.0 / (double)M;
+    for (int r0 = 0; r0 < len; r0 += 8) {
+        const bool ok = r0 + g < len;
+        const unsigned ra = sb + (unsigned)(ok ? r0 + g : r0) * 512u + t * 16u;
+        double av[16];
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double2 v = lds_row(ra + j * 64u);
+            const int k = 8 * j + 2 * t;
+            av[2 * j] = k < M ? v.x : 0.0; av[2 * j + 1] = k + 1 < M ? v.y : 0.0;
+            s += av[2 * j] + av[2 * j + 1];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const double mu = s * invM;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = 8 * j + 2 * t;
+            av[2 * j] = (ok && k < M) ? av[2 * j] - mu : 0.0;
+            av[2 * j + 1] = (ok && k + 1 < M) ? av[2 * j + 1] - mu : 0.0;
+        }
+        // two column halves, one after the other: 8 accumulators live instead of 16 (the kernel runs at its register cap)
+#pragma unroll 1
+        for (int jh = 0; jh < 8; jh += 4) {
+            double acc[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) {
+                const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
+                double b[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = lds_f64(sT + t_swz(k, 8 * (jh + j) + g));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma8x8x4(acc[j][0], acc[j][1], av[ks], b[j]);
+            }
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double2 v = lds_row(ra + (jh + j) * 64u);
+                    v.x += acc[j][0]; v.y += acc[j][1];
+                    sts_row(ra + (jh + j) * 64u, v);
+                }
+            }
+        }
+    }
+}
+
 // Shared-memory state of a task: ONE row per reach, p = beta*i + chi*o, the part of the next update that
 // depends on the old state (o' = alpha*inflow + (gamma*q + p)); the outflows and inflows themselves only
 // exist in registers, and are written to global memory in the last step of the launch.
-template <bool HAS_F, bool HAS_W>
+template <bool HAS_F, bool HAS_W, bool UPD>
 __global__ void __launch_bounds__(kWinThreads, 1)
 route_window_kernel(const WinArgs a)
 {
@@ -425,6 +496,15 @@ route_window_kernel(const WinArgs a)
     if (bulk) {
         if (lane == 0) mbar_init(sMbar, 1);
         __syncwarp();
+    }
+    // the ensemble transform of the update this launch applies while it loads its tasks: one copy per CTA
+    const unsigned sT = (unsigned)__cvta_generic_to_shared(smem_all) + (unsigned)a.off_T;
+    if (UPD) {
+        for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+            const int k = e >> 6, c = e & 63;
+            sts_f64(sT + t_swz(k, c), (k < a.M && c < a.M) ? __ldg(a.upT + (size_t)k * a.M + c) : 0.0);
+        }
+        __syncthreads();
     }
 
     for (;;) {
@@ -525,6 +605,26 @@ route_window_kernel(const WinArgs a)
                 }
                 sts_row(tk.sP + 512u * r, p);
             }
+        }
+        if (UPD) {
+            // the update of the last window is still owed to these rows (see transform_p_rows)
+            __syncwarp();
+            transform_p_rows(a, sb, sT, len, lane);
+            __syncwarp();
+            for (int e = __ldg(a.gfix_off + task), e1 = __ldg(a.gfix_off + task + 1); e < e1; ++e) {
+                const int2 x = __ldg(a.gfix + e);
+                const int rl = x.x & 0xffff;
+                const double2 bc = lds_row(tk.sRec + kRec * rl + 16u);
+                const double q = ((x.x >> 16) ? bc.x : bc.y) * __ldg(a.upQs + x.y);
+                if (active) {
+                    const double* wr = a.upW + (size_t)x.y * a.M;
+                    double2 pv = lds_row(tk.sP + 512u * rl);
+                    if (col < a.M) pv.x += q * __ldg(wr + col);
+                    if (col + 1 < a.M) pv.y += q * __ldg(wr + col + 1);
+                    sts_row(tk.sP + 512u * rl, pv);
+                }
+            }
+            __syncwarp();
         }
         // rows of other tasks consumed through the input ring, in consumption order: byte offsets of their slots
         int nL = 0;
@@ -648,12 +748,13 @@ cudaError_t launch_window_init(const InitArgs& a, unsigned long long* ticket, cu
 
 cudaError_t launch_route_window(const WinArgs& a, int warps_per_cta, int num_sms, cudaStream_t st)
 {
-    const size_t smem = (size_t)warps_per_cta * a.smem_per_warp;
+    const size_t smem = a.upT ? (size_t)a.off_T + 64 * 64 * sizeof(double) : (size_t)warps_per_cta * a.smem_per_warp;
     void (*kern)(const WinArgs) = nullptr;
     const bool f = a.F != nullptr, w = a.Wmul != nullptr;
-    if (!f) kern = route_window_kernel<false, false>;
-    else if (!w) kern = route_window_kernel<true, false>;
-    else kern = route_window_kernel<true, true>;
+    const bool u = a.upT != nullptr;
+    if (!f) kern = u ? route_window_kernel<false, false, true> : route_window_kernel<false, false, false>;
+    else if (!w) kern = u ? route_window_kernel<true, false, true> : route_window_kernel<true, false, false>;
+    else kern = u ? route_window_kernel<true, true, true> : route_window_kernel<true, true, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long pairs = (long long)a.n_tasks * a.n_mblocks;
