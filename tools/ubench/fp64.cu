@@ -109,7 +109,7 @@ int main()
     printf("dependent DMMA m8n8k4 latency : %.1f cycles\n", (double)hc / (it * 8));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms;
-    for (int warps = 4; warps <= 32; warps *= 2) {
+    for (int warps = 1; warps <= 32; warps *= 2) {
         thr_dfma<<<p.multiProcessorCount, warps * 32>>>(d, 0.999, 0.001, it);
         cudaEventRecord(e0);
         thr_dfma<<<p.multiProcessorCount, warps * 32>>>(d, 0.999, 0.001, it);
@@ -118,7 +118,7 @@ int main()
         printf("DFMA throughput, %2d warps/SM : %.2f TFLOP/s  (%.1f FMA/clk/SM)\n", warps, 2 * fma / ms / 1e9,
                fma / (ms * 1e-3) / p.multiProcessorCount / (p.clockRate * 1e3));
     }
-    for (int warps = 4; warps <= 32; warps *= 2) {
+    for (int warps = 1; warps <= 32; warps *= 2) {
         thr_dmma<<<p.multiProcessorCount, warps * 32>>>(d, it);
         cudaEventRecord(e0);
         thr_dmma<<<p.multiProcessorCount, warps * 32>>>(d, it);

@@ -401,7 +401,7 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     if (const char* k = getenv("TXH_WINDOW_WARPS")) wpc = std::max(1, std::min(wpc, atoi(k)));
     if (wpc < 2 || s.w_n_own > 0) return 1;
     // a launch that applies an ensemble update keeps the 64 x 64 transform in shared memory: fewer warps per CTA
-    const int wpc_upd = std::min(wpc, (smem_max - 1024 - 64 * 64 * (int)sizeof(double)) / a.smem_per_warp);
+    const int wpc_upd = std::min(wpc, (smem_max - 1024 - 64 * 64 * (int)sizeof(double) - 16) / a.smem_per_warp);
     if (probe_only) return wpc_upd >= 2 ? TXH_OK : 1;
     // ring[step][slot][ld]: one launch covers 16 steps, up to 64 while the ring stays below 64 MiB (few members):
     // a launch costs the critical path of one step before its pipeline is full, so longer launches amortise it

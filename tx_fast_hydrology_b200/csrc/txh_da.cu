@@ -353,115 +353,148 @@ constexpr int CS_NSPLIT = 8;
 
 // Factorisation A = L L^T of the MT x MT matrix in shared memory (lower triangle, leading dimension MT + 1) and the
 // solve for the CTA's 8 right-hand-side columns Bs [MT][9], in place.  256 threads; the caller has synchronised.
-//   panel   : warp 0 keeps the panel rows in registers (lane l owns rows j0+l, j0+l+32, ...) and factors the 8
-//             columns with shuffles -- no barrier inside a panel -- then solves the 8 matching rows of B;
-//   trailing: every warp takes 8x8 tiles of the lower triangle (and of B) and applies the rank-8 update with
-//             two FP64 tensor-core MMAs per tile;
-// two barriers per panel instead of one per column; the backward substitution is blocked the same way.
+// Panels of 8 columns, two barriers per panel:
+//   panel   : warp 0; every lane factors the 8 x 8 diagonal block itself, in registers, and solves its own rows below the
+//             block against it (lane l owns rows j0+8+l, j0+8+l+32, ...) -- no shuffles, no barrier inside a panel (a
+//             version that exchanged the pivot column with shuffles took 283 cycles per column, this one 196).  This
+//             is the critical path (64 dependent rsqrt).  Meanwhile
+//             warp 1 inverts the diagonal block of the PREVIOUS panel (8 lanes, one column of L11^-1 each) and forms
+//             that panel's rows of the forward substitution, Y = L11^-1 B1, with two tensor-core operations;
+//   trailing: every warp takes 8x8 tiles of the lower triangle and applies the rank-8 update of the new panel, and
+//             tiles of B for the update with the previous panel's Y, two FP64 tensor-core MMAs per tile.
+// The forward substitution thus rides one panel behind the factorisation, off its critical path; the backward
+// substitution multiplies with the inverted diagonal blocks (Z1 = L11^-T Y1, two MMAs) instead of eight dependent
+// steps, one barrier per panel.  Linv: [MT/8][8][9] scratch for the inverted blocks.
 template <int MT>
-__device__ __forceinline__ void chol_factor_solve_smem(double* A, double* Bs, double* invd, int* info, bool report)
+__device__ __forceinline__ void chol_factor_solve_smem(double* A, double* Bs, double* invd, double* Linv, int* info,
+                                                       bool report)
 {
-    constexpr int LD = MT + 1, NT = MT / 8, RPL = MT / 32, LDB = 9;
+    constexpr int LD = MT + 1, NT = MT / 8, RPL = MT / 32, LDB = 9, LDI = 9;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    // ---- factorisation + forward substitution, panel by panel ----
+    // X = L_qq^-1 (lower triangular) -> Linv[q], then the rows of panel q of B: Y = X B_q   (one warp)
+    auto invert_and_forward = [&](int q) {
+        const int j0 = 8 * q;
+        double* Li = Linv + q * 8 * LDI;
+        if (lane < 8) {
+            double x[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                double v = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < r; ++k) v -= A[(j0 + r) * LD + j0 + k] * x[k];
+                x[r] = v * invd[j0 + r];
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) Li[r * LDI + lane] = x[r];
+        }
+        __syncwarp();
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 8; kk += 4) dmma8x8x4(c0, c1, Li[g * LDI + kk + t], Bs[(j0 + kk + t) * LDB + g]);
+        __syncwarp();
+        Bs[(j0 + g) * LDB + 2 * t] = c0; Bs[(j0 + g) * LDB + 2 * t + 1] = c1;
+    };
+    // ---- factorisation, the forward substitution one panel behind ----
     for (int p = 0; p < NT; ++p) {
         const int j0 = 8 * p;
         if (warp == 0) {
+            // every lane factors the 8 x 8 diagonal block itself, in registers (36 broadcast loads, no shuffles: the
+            // chain per column is rsqrt + two multiply-adds), and solves its own rows below the block against it
+            double Dm[8][8], rs[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) Dm[r][c] = A[(j0 + r) * LD + j0 + c];
             double x[RPL][8];
 #pragma unroll
             for (int q = 0; q < RPL; ++q) {
-                const int i = j0 + lane + 32 * q;
+                const int i = j0 + 8 + lane + 32 * q;
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) x[q][cc] = i < MT ? A[i * LD + j0 + cc] : 0.0;
             }
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-                double d = __shfl_sync(0xffffffffu, x[0][jj], jj);              // pivot: row j0+jj lives in lane jj
+                double d = Dm[jj][jj];
                 if (!(d > 0.0)) { if (lane == 0 && report) *info = j0 + jj + 1; d = 1.0; }
-                const double rs = rsqrt(d);
-                if (lane == 0) invd[j0 + jj] = rs;
-                double l[RPL];
+                rs[jj] = rsqrt(d);
+                Dm[jj][jj] = d * rs[jj];
+#pragma unroll
+                for (int r = jj + 1; r < 8; ++r) Dm[r][jj] *= rs[jj];
+#pragma unroll
+                for (int r = jj + 1; r < 8; ++r)
+#pragma unroll
+                    for (int c = jj + 1; c <= r; ++c) Dm[r][c] -= Dm[r][jj] * Dm[c][jj];
+                // column jj of the rows below: x = (x - sum_{k<jj} x_k L[jj][k]) / L[jj][jj]
 #pragma unroll
                 for (int q = 0; q < RPL; ++q) {
-                    l[q] = x[q][jj] * rs;
-                    if (lane + 32 * q >= jj) x[q][jj] = l[q];                    // rows at or below the pivot
-                }
+                    double v = x[q][jj];
 #pragma unroll
-                for (int cc = jj + 1; cc < 8; ++cc) {
-                    const double lc = __shfl_sync(0xffffffffu, l[0], cc);        // L[j0+cc][j0+jj]
-#pragma unroll
-                    for (int q = 0; q < RPL; ++q)
-                        if (lane + 32 * q >= cc) x[q][cc] -= l[q] * lc;
+                    for (int k = 0; k < jj; ++k) v -= x[q][k] * Dm[jj][k];
+                    x[q][jj] = v * rs[jj];
                 }
+            }
+            // every lane holds the same block: all of them store it (same value to the same address, no divergence)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                invd[j0 + r] = rs[r];
+#pragma unroll
+                for (int c = 0; c <= r; ++c) A[(j0 + r) * LD + j0 + c] = Dm[r][c];
             }
 #pragma unroll
             for (int q = 0; q < RPL; ++q) {
-                const int i = j0 + lane + 32 * q;
+                const int i = j0 + 8 + lane + 32 * q;
                 if (i < MT)
 #pragma unroll
-                    for (int cc = 0; cc < 8; ++cc)
-                        if (lane + 32 * q >= cc) A[i * LD + j0 + cc] = x[q][cc];
+                    for (int cc = 0; cc < 8; ++cc) A[i * LD + j0 + cc] = x[q][cc];
             }
-            __syncwarp();
-            // the 8 matching rows of B: Y = L11^-1 B1 (lane cl < 8 owns column cl)
-            if (lane < 8) {
-                double y[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    double v = Bs[(j0 + jj) * LDB + lane];
-#pragma unroll
-                    for (int k = 0; k < jj; ++k) v -= A[(j0 + jj) * LD + j0 + k] * y[k];
-                    y[jj] = v * invd[j0 + jj];
-                }
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) Bs[(j0 + jj) * LDB + lane] = y[jj];
-            }
+        } else if (warp == 1 && p > 0) {
+            invert_and_forward(p - 1);
         }
         __syncthreads();
-        // trailing update: tiles (it, ct), p < ct <= it < NT, of A, then one tile per it of B
+        // trailing update: tiles (it, ct), p < ct <= it < NT, of A with panel p; tiles it >= p of B with Y of panel p-1
         const int Tn = NT - p - 1;
-        const int ntile = Tn * (Tn + 1) / 2 + Tn;
-        for (int e = warp; e < ntile; e += 8) {
-            int it, ct;
-            bool isB = false;
-            if (e < Tn * (Tn + 1) / 2) {
+        const int nA = Tn * (Tn + 1) / 2, nB = p > 0 ? NT - p : 0;
+        for (int e = warp; e < nA + nB; e += 8) {
+            int it, ct = 0, k0 = j0;
+            const bool isB = e >= nA;
+            if (!isB) {
                 it = 0;
                 int rem = e;
                 while (rem > it) { rem -= it + 1; ++it; }                        // row it has it+1 tiles
                 ct = p + 1 + rem; it = p + 1 + it;
-            } else { it = p + 1 + (e - Tn * (Tn + 1) / 2); ct = 0; isB = true; }
-            double c0, c1;
+            } else { it = p + (e - nA); k0 = j0 - 8; }
             double* cp = isB ? Bs + (8 * it + g) * LDB + 2 * t : A + (8 * it + g) * LD + 8 * ct + 2 * t;
-            c0 = cp[0]; c1 = cp[1];
+            double c0 = cp[0], c1 = cp[1];
 #pragma unroll
             for (int kk = 0; kk < 8; kk += 4) {
-                const double af = -A[(8 * it + g) * LD + j0 + kk + t];
-                const double bf = isB ? Bs[(j0 + kk + t) * LDB + g] : A[(8 * ct + g) * LD + j0 + kk + t];
+                const double af = -A[(8 * it + g) * LD + k0 + kk + t];
+                const double bf = isB ? Bs[(k0 + kk + t) * LDB + g] : A[(8 * ct + g) * LD + k0 + kk + t];
                 dmma8x8x4(c0, c1, af, bf);
             }
             cp[0] = c0; cp[1] = c1;
         }
         __syncthreads();
     }
-    // ---- backward substitution L^T Z = Y ----
-    for (int p = NT - 1; p >= 0; --p) {
+    if (warp == 1) invert_and_forward(NT - 1);
+    __syncthreads();
+    // ---- backward substitution L^T Z = Y: Z_p = L_pp^-T Y_p, rows above -= L[p][it]^T Z_p ----
+    auto back_block = [&](int q) {                              // one warp: rows of panel q of Bs <- Linv[q]^T times them
+        const int j0 = 8 * q;
+        const double* Li = Linv + q * 8 * LDI;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 8; kk += 4) dmma8x8x4(c0, c1, Li[(kk + t) * LDI + g], Bs[(j0 + kk + t) * LDB + g]);
+        __syncwarp();
+        Bs[(j0 + g) * LDB + 2 * t] = c0; Bs[(j0 + g) * LDB + 2 * t + 1] = c1;
+        __syncwarp();
+    };
+    if (warp == 0) back_block(NT - 1);
+    __syncthreads();
+    for (int p = NT - 1; p > 0; --p) {
         const int j0 = 8 * p;
-        if (warp == 0 && lane < 8) {
-            double z[8];
-#pragma unroll
-            for (int jj = 7; jj >= 0; --jj) {
-                double v = Bs[(j0 + jj) * LDB + lane];
-#pragma unroll
-                for (int k = 7; k > jj; --k) v -= A[(j0 + k) * LD + j0 + jj] * z[k];
-                z[jj] = v * invd[j0 + jj];
-            }
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) Bs[(j0 + jj) * LDB + lane] = z[jj];
-        }
-        __syncthreads();
-        // rows above: B[it] -= L[p][it]^T Z[p]
-        for (int it = warp; it < p; it += 8) {
+        // warp 0 takes the tile right above and goes straight on to the next block solve; one barrier per panel
+        for (int it = p - 1 - warp; it >= 0; it -= 8) {
             double* cp = Bs + (8 * it + g) * LDB + 2 * t;
             double c0 = cp[0], c1 = cp[1];
 #pragma unroll
@@ -472,6 +505,7 @@ __device__ __forceinline__ void chol_factor_solve_smem(double* A, double* Bs, do
             }
             cp[0] = c0; cp[1] = c1;
         }
+        if (warp == 0) { __syncwarp(); back_block(p - 1); }
         __syncthreads();
     }
 }
@@ -538,7 +572,7 @@ chol_solve_blocked_kernel(const double* __restrict__ Cpart, long long pstride, i
         }
     }
     __syncthreads();
-    chol_factor_solve_smem<MT>(A, Bs, invd, info, blockIdx.x == 0);
+    chol_factor_solve_smem<MT>(A, Bs, invd, invd + MT, info, blockIdx.x == 0);
     for (int e = tid; e < MT * 8; e += 256) {
         const int i = e >> 3, cl = e & 7;
         if (i < Mt && gc0 + cl < Mt) Z[(size_t)i * Mt + gc0 + cl] = Bs[i * LDB + cl];
@@ -546,28 +580,31 @@ chol_solve_blocked_kernel(const double* __restrict__ Cpart, long long pstride, i
 }
 
 // ---- the whole ensemble-space system in ONE launch (Mt <= 64, diagonal D) ---------------------------------------
-// A cluster of 8 CTAs replaces innovation_cat + split-K GEMM + chol_solve_blocked + GEMM (4 launches, 3 trips through
-// global memory):
+// A cluster of NC = 16 (or 8) CTAs replaces innovation_cat + split-K GEMM + chol_solve_blocked + GEMM (4 launches, 3
+// trips through global memory):
 //   1. CTA r gathers its share of the gauge rows, [HA | dz] -> shared memory, and multiplies its split-K partial of
 //      C = HA^T D^-1 [HA | dz] on the FP64 tensor cores (D^-1 rides on the A fragments);
-//   2. the partials are summed over the cluster through distributed shared memory: every CTA takes the lower triangle of
-//      C0 (+ shift I) and its own 8 columns of C1;
-//   3. every CTA factors C0 + shift I (repeated, as in chol_solve_blocked_kernel) and solves its 8 columns of Z = T;
-//      the columns are scattered into every CTA's copy of Z (distributed shared memory) and written to T;
+//   2. reduce-scatter through distributed shared memory: CTA r sums slice r of C over the cluster (DSMEM moves
+//      ~20 bytes per clock and SM, so nobody reads more than 1/NC of every partial);
+//   3. the CTAs of rank < 8 collect the lower triangle of C0 (+ shift I) and their own 8 columns of C1 from the slices,
+//      factor C0 + shift I (repeated, as in chol_solve_blocked_kernel) and solve their columns of Z = T; the columns
+//      are scattered into every CTA's copy of Z (distributed shared memory) and written to T;
 //   4. CTA r forms W = D^-1 (dz - HA Z) for its gauges from the tile it still holds.
-constexpr int SS_NC = 8;                         // CTAs per cluster
 constexpr int SS_KT = 64;                        // gauges per shared-memory tile
 constexpr int SS_LDB = 136;                      // [HA | dz] row stride in doubles (128 + 8: conflict-free fragments)
 constexpr int SS_LDZ = 72;
-constexpr int SS_OFF_C = SS_KT * SS_LDB;                   // sC   [64][128]
-constexpr int SS_OFF_A = SS_OFF_C + 64 * 128;              // A    [64][65]
+constexpr int SS_OFF_C = SS_KT * SS_LDB;                   // sC   [64][128] this CTA's partial
+constexpr int SS_OFF_R = SS_OFF_C + 64 * 128;              // sR   [8192 / NC] this CTA's slice of the sum (<= 1024)
+constexpr int SS_OFF_A = SS_OFF_R + 1024;                  // A    [64][65]
 constexpr int SS_OFF_BS = SS_OFF_A + 64 * 65;              // Bs   [64][9]
 constexpr int SS_OFF_INVD = SS_OFF_BS + 64 * 9;            // invd [64]
 constexpr int SS_OFF_Z = SS_OFF_INVD + 64;                 // sZ   [64][72]
 constexpr int SS_OFF_D = SS_OFF_Z + 64 * SS_LDZ;           // sd   [64]
-constexpr int SS_SMEM = (SS_OFF_D + SS_KT) * 8;            // 210,944 bytes
+constexpr int SS_OFF_LINV = SS_OFF_D + SS_KT;              // Linv [8][8][9] inverted diagonal blocks of the factor
+constexpr int SS_SMEM = (SS_OFF_LINV + 8 * 72) * 8;        // 223,744 bytes
 
-__global__ void __cluster_dims__(SS_NC, 1, 1) __launch_bounds__(256, 1)
+template <int NC>
+__global__ void __launch_bounds__(256, 1)
 enkf_small_system_kernel(double* __restrict__ HX, const double* __restrict__ O, int ldo, const double* __restrict__ Zp,
                          const double* __restrict__ mean, const int32_t* __restrict__ obs_pos,
                          const double* __restrict__ dinv, int m, int Mt, double shift, double* __restrict__ T,
@@ -579,14 +616,16 @@ enkf_small_system_kernel(double* __restrict__ HX, const double* __restrict__ O, 
     extern __shared__ double ss[];
     double* sB = ss;
     double* sC = ss + SS_OFF_C;
+    double* sR = ss + SS_OFF_R;
     double* A = ss + SS_OFF_A;
     double* Bs = ss + SS_OFF_BS;
     double* invd = ss + SS_OFF_INVD;
     double* sZ = ss + SS_OFF_Z;
     double* sd = ss + SS_OFF_D;
+    double* Linv = ss + SS_OFF_LINV;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int mc = (((m + SS_NC - 1) / SS_NC) + 3) & ~3;           // gauges per CTA
+    const int mc = (((m + NC - 1) / NC) + 3) & ~3;                 // gauges per CTA
     const int k_lo = min(m, rank * mc), k_hi = min(m, k_lo + mc);
     auto stamp = [&](int i) {                                      // development aid (TXH_SS_TRACE): phase timeline
         if (trace && tid == 0) {
@@ -595,9 +634,14 @@ enkf_small_system_kernel(double* __restrict__ HX, const double* __restrict__ O, 
             trace[rank * 8 + i] = ns;
         }
     };
+    // programmatic dependent launch: this kernel may have started before the routing launch in front of it has
+    // finished; what it reads is final after the wait, and the routing launch behind it (which reads T and W only
+    // after a wait of its own) may start loading its tasks from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     stamp(0);
 
-    // [HA | dz] of the gauges kt .. kt+63 -> sB (zero rows beyond k_hi), D^-1 -> sd; every load of a thread's 16
+    // [HA | dz] of the gauges kt .. kt+63 -> sB (zero rows beyond k_hi), D^-1 -> sd; every load of a thread's
     // elements is in flight before the first use
     auto load_tile = [&](int kt) {
         const int c = tid & 63;
@@ -663,64 +707,72 @@ enkf_small_system_kernel(double* __restrict__ HX, const double* __restrict__ O, 
     cluster.sync();
     stamp(2);
 
-    // ---- 2. sum over the cluster: lower triangle of C0 + shift I -> A, this CTA's 8 columns of C1 -> Bs ----
-    const double* rc[SS_NC];
-#pragma unroll
-    for (int r = 0; r < SS_NC; ++r) rc[r] = cluster.map_shared_rank(sC, r);
-    const int gc0 = rank * 8;
-    for (int e0 = 0; e0 < 64 * 64; e0 += 8 * 256) {
-        double part[8][SS_NC];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * 256 + tid;
-            const int i = e >> 6, c = e & 63;
-            const int off = c <= i ? i * 128 + c : 0;
-#pragma unroll
-            for (int r = 0; r < SS_NC; ++r) part[u][r] = rc[r][off];
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * 256 + tid;
-            const int i = e >> 6, c = e & 63;
-            double v = (i == c) ? shift : 0.0;
-#pragma unroll
-            for (int r = 0; r < SS_NC; ++r) v += part[u][r];
-            A[i * 65 + c] = c <= i ? v : 0.0;
-        }
-    }
+    // ---- 2. reduce-scatter: slice `rank` of C (8192 / NC doubles), summed over the cluster in rank order ----
+    constexpr int SL = 8192 / NC;                                  // doubles per slice: 512 (NC = 16) or 1024
     {
-        double part[2][SS_NC];
+        constexpr int PT = SL / 2 / 256;                           // double2 per thread: 1 or 2
+        double2 part[PT][NC];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int e = tid + u * 256;
-            const int off = (e >> 3) * 128 + 64 + gc0 + (e & 7);
+        for (int u = 0; u < PT; ++u) {
+            const int off = rank * SL + 2 * (tid + u * 256);
 #pragma unroll
-            for (int r = 0; r < SS_NC; ++r) part[u][r] = rc[r][off];
+            for (int r = 0; r < NC; ++r) part[u][r] = *reinterpret_cast<const double2*>(cluster.map_shared_rank(sC, r) + off);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int e = tid + u * 256;
-            double v = 0.0;
+        for (int u = 0; u < PT; ++u) {
+            double2 v = part[u][0];
 #pragma unroll
-            for (int r = 0; r < SS_NC; ++r) v += part[u][r];
-            Bs[(e >> 3) * 9 + (e & 7)] = v;
+            for (int r = 1; r < NC; ++r) { v.x += part[u][r].x; v.y += part[u][r].y; }
+            *reinterpret_cast<double2*>(sR + 2 * (tid + u * 256)) = v;
         }
-    }
-    __syncthreads();
-    stamp(3);
-
-    // ---- 3. (C0 + shift I) Z = C1 for this CTA's columns; Z goes to T and into every CTA's sZ ----
-    chol_factor_solve_smem<64>(A, Bs, invd, info, rank == 0);
-    stamp(4);
-    for (int e = tid; e < 64 * 8; e += 256) {
-        const int i = e >> 3, cl = e & 7;
-        const double v = Bs[i * 9 + cl];
-        if (i < Mt && gc0 + cl < Mt) T[(size_t)i * Mt + gc0 + cl] = v;
-#pragma unroll
-        for (int r = 0; r < SS_NC; ++r) cluster.map_shared_rank(sZ, r)[i * SS_LDZ + gc0 + cl] = v;
     }
     cluster.sync();
-    stamp(5);
+    stamp(3);
+
+    // ---- 3. ranks 0..7: lower triangle of C0 + shift I -> A, 8 columns of C1 -> Bs, from the owners' slices;
+    //         (C0 + shift I) Z = C1 for these columns; Z goes to T and into every CTA's sZ ----
+    const int gc0 = rank * 8;
+    if (rank < 8) {
+        // element (i, c) of C: flat index i*128 + c, owner flat / SL
+        double2 va[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = 2 * (tid + u * 256);                     // pair (i, c), (i, c+1) of the 64 x 64 block C0
+            const int i = e >> 6, c = e & 63;
+            const int flat = i * 128 + c;
+            va[u] = c <= i ? *reinterpret_cast<const double2*>(cluster.map_shared_rank(sR, flat / SL) + flat % SL)
+                           : make_double2(0.0, 0.0);
+        }
+        double vb[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = tid + u * 256;
+            const int flat = (e >> 3) * 128 + 64 + gc0 + (e & 7);
+            vb[u] = cluster.map_shared_rank(sR, flat / SL)[flat % SL];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = 2 * (tid + u * 256);
+            const int i = e >> 6, c = e & 63;
+            A[i * 65 + c] = c <= i ? va[u].x + (i == c ? shift : 0.0) : 0.0;
+            A[i * 65 + c + 1] = c + 1 <= i ? va[u].y + (i == c + 1 ? shift : 0.0) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { const int e = tid + u * 256; Bs[(e >> 3) * 9 + (e & 7)] = vb[u]; }
+        __syncthreads();
+        stamp(4);
+        chol_factor_solve_smem<64>(A, Bs, invd, Linv, info, rank == 0);
+        stamp(5);
+        for (int e = tid; e < 64 * 8; e += 256) {
+            const int i = e >> 3, cl = e & 7;
+            const double v = Bs[i * 9 + cl];
+            if (i < Mt && gc0 + cl < Mt) T[(size_t)i * Mt + gc0 + cl] = v;
+#pragma unroll
+            for (int r = 0; r < NC; ++r) cluster.map_shared_rank(sZ, r)[i * SS_LDZ + gc0 + cl] = v;
+        }
+    }
+    cluster.sync();
+    stamp(6);
 
     // ---- 4. W = D^-1 (dz - HA Z) for this CTA's gauges: warp tile 8 gauges x 64 columns ----
     for (int kt = k_lo; kt < k_hi; kt += SS_KT) {
@@ -729,6 +781,7 @@ enkf_small_system_kernel(double* __restrict__ HX, const double* __restrict__ O, 
             load_tile(kt);
             __syncthreads();
         }
+        if (kt + 8 * warp >= k_hi) continue;                   // (warp-uniform: no gauges in this warp's rows)
         double w[8][2];
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j][0] = w[j][1] = 0.0;
@@ -751,7 +804,7 @@ enkf_small_system_kernel(double* __restrict__ HX, const double* __restrict__ O, 
             }
         }
     }
-    stamp(6);
+    stamp(7);
 }
 
 // sum of the split-K partials of C = [C0 | C1] -> Cf = C0 + shift*I and C1 as two dense Mt x Mt matrices
@@ -1160,7 +1213,7 @@ cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long p
     if (nsplit != CS_NSPLIT || Mt > 128) return cudaErrorInvalidValue;
     const int MT = Mt <= 64 ? 64 : (Mt <= 96 ? 96 : 128);
     const int ncta = (Mt + 7) / 8;                      // 8 right-hand-side columns per CTA
-    const size_t smem_b = ((size_t)MT * (MT + 1) + (size_t)MT * 9 + MT) * sizeof(double);
+    const size_t smem_b = ((size_t)MT * (MT + 1) + (size_t)MT * 9 + MT + (size_t)(MT / 8) * 72) * sizeof(double);
     void (*kern)(const double*, long long, int, double, double*, int*) =
         MT == 64 ? chol_solve_blocked_kernel<64> : (MT == 96 ? chol_solve_blocked_kernel<96> : chol_solve_blocked_kernel<128>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
@@ -1171,34 +1224,60 @@ cudaError_t launch_chol_solve_small(const double* Cpart, int nsplit, long long p
 }
 
 // The ensemble-space system in one cluster launch (Mt <= 64, D diagonal): HX (gathered from O when O != nullptr), T, W.
+// 16 CTAs per cluster where the device takes it (non-portable size), else 8.
 cudaError_t launch_enkf_small_system(double* HX, const double* O, int ldo, const double* Zp, const double* mean,
                                      const int32_t* obs_pos, const double* dinv_diag, int m, int Mt, double shift,
                                      double* T, double* W, int* info, cudaStream_t st)
 {
     if (Mt > 64 || Mt < 1 || m < 1) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(enkf_small_system_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM);
-    if (e != cudaSuccess) return e;
+    auto k16 = enkf_small_system_kernel<16>;
+    auto k8 = enkf_small_system_kernel<8>;
+    static int nc = 0;
+    cudaError_t e;
+    if (nc == 0) {
+        if ((e = cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM)) != cudaSuccess) return e;
+        nc = 8;
+        int want = 16;
+        if (const char* k = getenv("TXH_SS_CLUSTER")) want = atoi(k);
+        if (want >= 16 && cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM) == cudaSuccess &&
+            cudaFuncSetAttribute(k16, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(16); q.blockDim = dim3(256); q.dynamicSmemBytes = SS_SMEM;
+            cudaLaunchAttribute at{};
+            at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 16; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+            q.attrs = &at; q.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, k16, &q) == cudaSuccess && ncl >= 1) nc = 16;
+        }
+        cudaGetLastError();
+    }
     static const char* trace_file = getenv("TXH_SS_TRACE");
     unsigned long long* d_trace = nullptr;
     if (trace_file && *trace_file) {
-        if ((e = cudaMalloc((void**)&d_trace, SS_NC * 8 * sizeof(unsigned long long))) != cudaSuccess) return e;
-        cudaMemsetAsync(d_trace, 0, SS_NC * 8 * sizeof(unsigned long long), st);
+        if ((e = cudaMalloc((void**)&d_trace, 16 * 8 * sizeof(unsigned long long))) != cudaSuccess) return e;
+        cudaMemsetAsync(d_trace, 0, 16 * 8 * sizeof(unsigned long long), st);
     }
-    enkf_small_system_kernel<<<SS_NC, 256, SS_SMEM, st>>>(HX, O, ldo, Zp, mean, obs_pos, dinv_diag, m, Mt, shift, T, W, info,
-                                                          d_trace);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nc); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = SS_SMEM; cfg.stream = st;
+    static const bool pdl = [] { const char* k = getenv("TXH_PDL"); return !(k && atoi(k) == 0); }();
+    cudaLaunchAttribute attr[2]{};
+    attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
+    e = cudaLaunchKernelEx(&cfg, nc == 16 ? k16 : k8, HX, O, ldo, Zp, mean, obs_pos, dinv_diag, m, Mt, shift, T, W, info, d_trace);
     count_launch();
-    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (d_trace) {
         // development aid: per-CTA phase stamps (ns relative to the first) appended to the file, synchronous
-        unsigned long long h[SS_NC * 8];
+        unsigned long long h[16 * 8];
         cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         cudaFree(d_trace);
         if (FILE* fp = fopen(trace_file, "a")) {
             unsigned long long t0 = ~0ull;
-            for (int r = 0; r < SS_NC; ++r) if (h[r * 8] && h[r * 8] < t0) t0 = h[r * 8];
-            for (int r = 0; r < SS_NC; ++r) {
-                for (int i = 0; i < 7; ++i) fprintf(fp, "%lld ", (long long)(h[r * 8 + i] - t0));
+            for (int r = 0; r < nc; ++r) if (h[r * 8] && h[r * 8] < t0) t0 = h[r * 8];
+            for (int r = 0; r < nc; ++r) {
+                for (int i = 0; i < 8; ++i) fprintf(fp, "%lld ", h[r * 8 + i] ? (long long)(h[r * 8 + i] - t0) : -1ll);
                 fprintf(fp, "\n");
             }
             fprintf(fp, "\n");

@@ -17,6 +17,8 @@
 // out = A_last * o_in + B_last, before handing on -- consecutive steps ripple down the path as a
 // systolic wavefront -- and fixes its interior rows up afterwards (FIX).
 // Ensemble members are the SIMD axis: a lane owns two adjacent member columns (128-bit accesses).
+#include <cstdlib>
+
 #include "txh_kernels.cuh"
 
 namespace txh {
@@ -112,6 +114,12 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned phase)
                      : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
     } while (!ok);
 }
+
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// once every CTA of the kernel before it in the stream has executed launch_dependents (or exited); what that kernel
+// wrote is only visible after wait.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 constexpr int kInRing = 4;                 // pockets: rows of other tasks in flight per warp (cp.async ring)
 constexpr int kSegRing = 8;                // segments: the ring also takes the (unused) scratch slots
@@ -424,46 +432,40 @@ __device__ __noinline__ void transform_p_rows(const WinArgs& a, unsigned sb, uns
     for (int r0 = 0; r0 < len; r0 += 8) {
         const bool ok = r0 + g < len;
         const unsigned ra = sb + (unsigned)(ok ? r0 + g : r0) * 512u + t * 16u;
-        double av[16];
+        // row mean: the four lanes of a row hold 16 members each
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const double2 v = lds_row(ra + j * 64u);
             const int k = 8 * j + 2 * t;
-            av[2 * j] = k < M ? v.x : 0.0; av[2 * j + 1] = k + 1 < M ? v.y : 0.0;
-            s += av[2 * j] + av[2 * j + 1];
+            s += (k < M ? v.x : 0.0) + (k + 1 < M ? v.y : 0.0);
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         const double mu = s * invM;
+        // 8 independent accumulator chains (one per column tile); the k loop is a real loop, so the 8 tensor-core
+        // operations of a k step stay next to each other (fully unrolled, ptxas schedules one chain after the other
+        // and a warp then issues one DMMA per two latencies instead of one per pipe slot)
+        double acc[8][2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = 8 * j + 2 * t;
-            av[2 * j] = (ok && k < M) ? av[2 * j] - mu : 0.0;
-            av[2 * j + 1] = (ok && k + 1 < M) ? av[2 * j + 1] - mu : 0.0;
+        for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll 2
+        for (int ks = 0; ks < 16; ++ks) {
+            const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
+            const double pv = lds_f64(ra - t * 16u + (unsigned)k * 8u);
+            const double av = (ok && k < M) ? pv - mu : 0.0;
+            double b[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = lds_f64(sT + t_swz(k, 8 * j + g));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dmma8x8x4(acc[j][0], acc[j][1], av, b[j]);
         }
-        // two column halves, one after the other: 8 accumulators live instead of 16 (the kernel runs at its register cap)
-#pragma unroll 1
-        for (int jh = 0; jh < 8; jh += 4) {
-            double acc[4][2];
+        if (ok) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = 0.0;
-#pragma unroll
-            for (int ks = 0; ks < 16; ++ks) {
-                const int k = 8 * (ks >> 1) + 2 * t + (ks & 1);
-                double b[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = lds_f64(sT + t_swz(k, 8 * (jh + j) + g));
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma8x8x4(acc[j][0], acc[j][1], av[ks], b[j]);
-            }
-            if (ok) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    double2 v = lds_row(ra + (jh + j) * 64u);
-                    v.x += acc[j][0]; v.y += acc[j][1];
-                    sts_row(ra + (jh + j) * 64u, v);
-                }
+            for (int j = 0; j < 8; ++j) {
+                double2 v = lds_row(ra + j * 64u);
+                v.x += acc[j][0]; v.y += acc[j][1];
+                sts_row(ra + j * 64u, v);
             }
         }
     }
@@ -497,22 +499,42 @@ route_window_kernel(const WinArgs a)
         if (lane == 0) mbar_init(sMbar, 1);
         __syncwarp();
     }
-    // the ensemble transform of the update this launch applies while it loads its tasks: one copy per CTA
+    // The ensemble transform of the update this launch applies while it loads its tasks: one copy per CTA, behind the
+    // per-warp areas.  The launch may have started before the kernel that computes T has finished (programmatic
+    // dependent launch): every warp loads its first task, which needs nothing of that kernel, THEN waits for it, stages
+    // its share of T and waits for the other warps' shares (a counter in shared memory; a warp without a task stages
+    // its share before it leaves).
     const unsigned sT = (unsigned)__cvta_generic_to_shared(smem_all) + (unsigned)a.off_T;
+    const unsigned sTcount = sT + 64u * 64u * 8u;
+    bool t_ready = !UPD;
     if (UPD) {
-        for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
-            const int k = e >> 6, c = e & 63;
-            sts_f64(sT + t_swz(k, c), (k < a.M && c < a.M) ? __ldg(a.upT + (size_t)k * a.M + c) : 0.0);
-        }
+        if (threadIdx.x == 0) sts_u32(sTcount, 0u);
         __syncthreads();
     }
+    griddep_launch_dependents();
+    auto stage_T = [&]() {
+        griddep_wait();
+        const int nw = blockDim.x >> 5;
+        for (int e = warp * 32 + lane; e < 64 * 64; e += nw * 32) {
+            const int k = e >> 6, c = e & 63;
+            sts_f64(sT + t_swz(k, c), (k < a.M && c < a.M) ? __ldcg(a.upT + (size_t)k * a.M + c) : 0.0);
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned*>(smem_all + a.off_T + 64 * 64 * 8), 1u);
+        while (lds_u32(sTcount) < (unsigned)nw) __nanosleep(64);
+        __threadfence_block();
+        t_ready = true;
+    };
 
     for (;;) {
         long long t = 0;
         if (lane == 0) t = (long long)atomicAdd(a.ticket, 1ull);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= total) break;
-        if (ld_relaxed_s32(a.status) != 0) break;               // a launch on this handle was poisoned
+        if (t >= total || ld_relaxed_s32(a.status) != 0) {      // (status: a launch on this handle was poisoned)
+            if (!t_ready) stage_T();                             // the other warps of the CTA wait for this share
+            break;
+        }
         const int task = (int)(t / nmb);
         const int mb = (int)(t - (long long)task * nmb);
         const WTaskDesc td = a.tasks[task];
@@ -609,6 +631,7 @@ route_window_kernel(const WinArgs a)
         if (UPD) {
             // the update of the last window is still owed to these rows (see transform_p_rows)
             __syncwarp();
+            if (!t_ready) stage_T();
             transform_p_rows(a, sb, sT, len, lane);
             __syncwarp();
             for (int e = __ldg(a.gfix_off + task), e1 = __ldg(a.gfix_off + task + 1); e < e1; ++e) {
@@ -748,7 +771,8 @@ cudaError_t launch_window_init(const InitArgs& a, unsigned long long* ticket, cu
 
 cudaError_t launch_route_window(const WinArgs& a, int warps_per_cta, int num_sms, cudaStream_t st)
 {
-    const size_t smem = a.upT ? (size_t)a.off_T + 64 * 64 * sizeof(double) : (size_t)warps_per_cta * a.smem_per_warp;
+    const size_t smem = a.upT ? (size_t)a.off_T + 64 * 64 * sizeof(double) + 16 : (size_t)warps_per_cta * a.smem_per_warp;
+    static const bool pdl = [] { const char* k = getenv("TXH_PDL"); return !(k && atoi(k) == 0); }();
     void (*kern)(const WinArgs) = nullptr;
     const bool f = a.F != nullptr, w = a.Wmul != nullptr;
     const bool u = a.upT != nullptr;
@@ -761,6 +785,18 @@ cudaError_t launch_route_window(const WinArgs& a, int warps_per_cta, int num_sms
     long long want = (pairs + warps_per_cta - 1) / warps_per_cta;
     const unsigned grid = (unsigned)(want < num_sms ? (want < 1 ? 1 : want) : num_sms);   // one resident CTA per SM
     (void)want;
+    if (u) {
+        // the launch that applies an update may overlap the tail of the kernel that computes it (see stage_T)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(warps_per_cta * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, a);
+        count_launch();
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
     kern<<<grid, warps_per_cta * 32, smem, st>>>(a);
     count_launch();
     return cudaGetLastError();
