@@ -333,18 +333,14 @@ def test_enkf_update_vs_oracle(oracle, n, M, m, seed, diag):
     assert relerr(mdl.i_t_next, I_ref) < RTOL
 
 
-@pytest.mark.parametrize("n,M,m,seed", [(2000, 64, 50, 7), (1200, 20, 30, 8), (900, 70, 40, 9)])
-@pytest.mark.parametrize("in_library", [True, False])
-def test_run_assimilating_vs_oracle(oracle, n, M, m, seed, in_library):
-    """The device-resident loop of the headline benchmark -- `every` routing steps in one window launch, the
-    ensemble row sums riding on its last step, then one EnKF update, repeated -- equals the CPU oracle's
-    routing (nutils.py:64-89 per member) + ensemble update (da.py:112-126) loop.  `in_library`: the loop runs
-    inside libtxh (txh_run_assimilating, observations as one CUDA tensor) or in Python (a list of tensors)."""
+def _run_assimilating_case(oracle, n, M, m, seed, in_library, every=6, nwin=3, rest=0, gidx=None):
+    """`nwin` windows of `every` routing steps + one EnKF update each, then `rest` more routing steps, on the device
+    (through the Python API) and on the CPU oracle; returns what the assertions need."""
     import torch
     from tx_fast_hydrology_b200 import synthetic as S
     from tx_fast_hydrology_b200.muskingum import Muskingum
     from tx_fast_hydrology_b200.da import EnsembleKalmanFilter
-    every, nwin = 6, 3
+    nsteps = every * nwin + rest
     net_d = S.make_network(n, seed)
     prm = S.make_params(n, seed, well_posed=True)
     rng = np.random.default_rng(seed)
@@ -353,9 +349,12 @@ def test_run_assimilating_vs_oracle(oracle, n, M, m, seed, in_library):
     d["o_t"] = o0
     mdl = Muskingum(d, members=M)
     t0 = int(mdl.datetime.value)
-    times, table = S.make_forcing(n, every * nwin, 300.0, seed, t0_ns=t0, rows_every=4)
+    times, table = S.make_forcing(n, nsteps, 300.0, seed, t0_ns=t0, rows_every=4)
     mul = S.make_member_multipliers(times.size, M, seed)
-    gidx = S.make_gauges(net_d["endnodes"], m, seed=seed)
+    if gidx is None:
+        gidx = S.make_gauges(net_d["endnodes"], m, seed=seed)
+    gidx = np.asarray(gidx, dtype=np.int64)
+    m = gidx.size
     mt = t0 + (np.arange(nwin, dtype=np.int64) + 1) * int(every * 300e9)
     meas = rng.uniform(0.5, 8.0, size=(nwin, m))
     mdf = frame(mt, meas, [d["reach_ids"][j] for j in gidx])
@@ -371,9 +370,9 @@ def test_run_assimilating_vs_oracle(oracle, n, M, m, seed, in_library):
     with torch.cuda.stream(side):
         Zd.copy_(Zh, non_blocking=True)
         ready.record(side)
-    mdl.run_assimilating(f, every * nwin, enkf, every, Zd if in_library else list(Zd), observations_ready=ready)
+    mdl.run_assimilating(f, nsteps, enkf, every, Zd if in_library else list(Zd), observations_ready=ready)
     mdl.network.check()
-    assert enkf.n_updates == nwin and mdl.datetime.value == t0 + int(every * nwin * 300e9)
+    assert enkf.n_updates == nwin and mdl.datetime.value == t0 + int(nsteps * 300e9)
     ind = oracle.compute_indegree(net_d["startnodes"], net_d["endnodes"])
     al, be, ch, ga = oracle.compute_coeffs(prm["K"], prm["X"], 300.0)
     onet = {"startnodes": net_d["startnodes"], "endnodes": net_d["endnodes"], "indegree": ind,
@@ -390,9 +389,107 @@ def test_run_assimilating_vs_oracle(oracle, n, M, m, seed, in_library):
         so = np.maximum(so, np.abs(o.T)); si = np.maximum(si, np.abs(i.T))
         Op, Ip, _ = oracle.enkf_update(onet, o.T, i.T, gidx, Zp[k], q, R)
         o = np.ascontiguousarray(Op.T); i = np.ascontiguousarray(Ip.T)
+    if rest:
+        oracle.run_members(onet, o, i, rest, times.astype(np.float64), table, t, 300e9, wmul=mul)
+    return mdl, o.T, i.T, so, si, tol
+
+
+@pytest.mark.parametrize("n,M,m,seed", [(2000, 64, 50, 7), (1200, 20, 30, 8), (900, 70, 40, 9)])
+@pytest.mark.parametrize("in_library", [True, False])
+def test_run_assimilating_vs_oracle(oracle, n, M, m, seed, in_library):
+    """The device-resident loop of the headline benchmark -- `every` routing steps in one window launch, the
+    ensemble row sums riding on its last step, then one EnKF update, repeated -- equals the CPU oracle's
+    routing (nutils.py:64-89 per member) + ensemble update (da.py:112-126) loop.  `in_library`: the loop runs
+    inside libtxh (txh_run_assimilating, observations as one CUDA tensor: the small system in one cluster launch, the
+    update applied by the next window launch while it loads its tasks) or in Python (a list of tensors: one launch per
+    stage, the posterior written to memory by the transform kernel)."""
+    mdl, o, i, so, si, tol = _run_assimilating_case(oracle, n, M, m, seed, in_library)
     # element-wise, relative to max(|posterior|, |forecast|): o + gain cancels on some reaches (tests/parity.py)
-    assert relerr(mdl.o_t_next, o.T, scale=so) < tol
-    assert relerr(mdl.i_t_next, i.T, scale=si) < tol
+    assert relerr(mdl.o_t_next, o, scale=so) < tol
+    assert relerr(mdl.i_t_next, i, scale=si) < tol
+
+
+@pytest.mark.parametrize("M", [64, 10])
+def test_run_assimilating_remainder_steps(oracle, M):
+    """nsteps is not a multiple of `every`: the last update is applied by the launch that routes the remaining steps
+    (txh_run_assimilating), nothing is left owed to the state."""
+    mdl, o, i, so, si, tol = _run_assimilating_case(oracle, 1500, M, 25, 11, True, every=5, nwin=2, rest=3)
+    assert relerr(mdl.o_t_next, o, scale=so) < tol
+    assert relerr(mdl.i_t_next, i, scale=si) < tol
+
+
+def test_run_assimilating_gauges_at_confluences_and_outlets(oracle):
+    """The gauge terms of the update applied at task load (route_window_kernel): a gauged reach adds qs W to its own
+    outflow and to the inflow of the reach it drains into (nutils.py:127-134).  Gauges are put where that matters: on
+    BOTH tributaries of confluences and on the confluence itself (three terms meet in one row), on reaches next to an
+    outlet and on outlets (self-loop: no inflow term), on headwaters."""
+    from tx_fast_hydrology_b200 import synthetic as S
+    n, seed = 1800, 13
+    end = S.make_network(n, seed)["endnodes"]
+    start = np.arange(n)
+    indeg = np.bincount(end[end != start], minlength=n)
+    conf = np.flatnonzero(indeg >= 2)[:6]
+    g = set()
+    for c in conf:
+        ups = np.flatnonzero((end == c) & (start != c))
+        g.update(int(u) for u in ups[:2]); g.add(int(c))
+    outlets = np.flatnonzero(end == start)
+    g.update(int(x) for x in outlets[:2])
+    for x in outlets[:2]:
+        ups = np.flatnonzero((end == x) & (start != x))
+        g.update(int(u) for u in ups[:1])
+    g.update(int(x) for x in np.flatnonzero(indeg == 0)[:4])
+    gidx = np.array(sorted(g), dtype=np.int64)
+    assert gidx.size >= 20
+    for in_library in (True, False):
+        mdl, o, i, so, si, tol = _run_assimilating_case(oracle, n, 64, gidx.size, seed, in_library, every=4, nwin=3, gidx=gidx)
+        assert relerr(mdl.o_t_next, o, scale=so) < tol
+        assert relerr(mdl.i_t_next, i, scale=si) < tol
+
+
+def test_run_assimilating_variants_agree():
+    """Every fused stage of the in-library loop has a switch (TXH_ENKF_FUSED: the small system in one cluster launch;
+    TXH_ENKF_FUSE_LOAD: the update applied at task load; TXH_PDL: programmatic dependent launch).  The switches are
+    read once per process: a child process runs the same case with all of them off (one launch per stage, the
+    posterior written by the transform kernel) and must agree with the default path to 1e-10 of the state."""
+    import subprocess
+    import sys
+    import tempfile
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from tx_fast_hydrology_b200 import synthetic as S\n"
+        "from tx_fast_hydrology_b200.muskingum import Muskingum\n"
+        "from tx_fast_hydrology_b200.da import EnsembleKalmanFilter\n"
+        "import pandas as pd\n"
+        "n, M, m, seed, every, nwin = 2500, 64, 40, 21, 6, 4\n"
+        "net = S.make_network(n, seed); prm = S.make_params(n, seed, well_posed=True)\n"
+        "rng = np.random.default_rng(seed)\n"
+        "d = S.model_dict(net, prm, dt_s=300.0); d['o_t'] = prm['o_t'][:, None] * rng.uniform(0.5, 1.5, size=(n, M))\n"
+        "mdl = Muskingum(d, members=M); t0 = int(mdl.datetime.value)\n"
+        "times, table = S.make_forcing(n, every * nwin, 300.0, seed, t0_ns=t0, rows_every=4)\n"
+        "mul = S.make_member_multipliers(times.size, M, seed)\n"
+        "g = S.make_gauges(net['endnodes'], m, seed=seed)\n"
+        "mt = t0 + (np.arange(nwin, dtype=np.int64) + 1) * int(every * 300e9)\n"
+        "meas = rng.uniform(0.5, 8.0, size=(nwin, m))\n"
+        "idx = pd.DatetimeIndex(pd.to_datetime(mt, unit='ns', utc=True)).as_unit('ns')\n"
+        "mdf = pd.DataFrame(meas, index=idx, columns=[d['reach_ids'][j] for j in g])\n"
+        "enkf = EnsembleKalmanFilter(mdl, mdf, rng.uniform(0.5, 2.0, size=n), 1e-2 * np.eye(m))\n"
+        "Zp = torch.as_tensor(meas[:, :, None] + 0.1 * rng.standard_normal((nwin, m, M)), device='cuda')\n"
+        "f = mdl.make_forcing(times_ns=times, table=table, member_mul=mul)\n"
+        "mdl.run_assimilating(f, every * nwin, enkf, every, Zp)\n"
+        "mdl.network.check()\n"
+        "np.savez(sys.argv[1], o=mdl.o_t_next, i=mdl.i_t_next)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, env in (("fused", {}), ("plain", {"TXH_ENKF_FUSED": "0", "TXH_ENKF_FUSE_LOAD": "0", "TXH_PDL": "0"})):
+            path = os.path.join(tmp, name + ".npz")
+            e = dict(os.environ); e.update(env)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=e, timeout=600)
+            z = np.load(path)
+            out[name] = (z["o"], z["i"])
+    assert normerr(out["fused"][0], out["plain"][0]) < 1e-10
+    assert normerr(out["fused"][1], out["plain"][1]) < 1e-10
 
 
 def test_headline_window_full_size(oracle):

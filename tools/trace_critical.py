@@ -69,3 +69,46 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def slow_stages(trace, n=100000, seed=2):
+    """Which tasks own the 'own' edges of the critical path, and what do they look like."""
+    from tx_fast_hydrology_b200 import synthetic as S
+    from tx_fast_hydrology_b200.network import RiverNetwork
+    net = RiverNetwork(S.make_network(n, seed)["endnodes"])
+    ws = net.window_schedule()
+    tasks, prod = ws["tasks"], ws["prod"]
+    raw = np.fromfile(trace, dtype=np.uint64)
+    pairs, ns, ntasks, nmb = (int(x) for x in raw[:4].view(np.int64))
+    tr = raw[4:].reshape(pairs, 4 + ns).astype(np.int64)
+    t0 = tr[:, 0].min()
+    loaded = tr[:, 1] - t0
+    pub = tr[:, 4:] - t0
+    kind = tr[:, 3] & 0xff
+    T = int(np.argmax(pub[:, ns - 1])); s = ns - 1
+    own = {}
+    while True:
+        cands = [(pub[T, s - 1], "own", T, s - 1)] if s > 0 else [(loaded[T], "load", T, -1)]
+        po, npr = tasks[T, 5], tasks[T, 6]
+        for p in prod[po:po + npr]:
+            cands.append((pub[p, s], "hop", int(p), s))
+        tp, k, Tn, sn = max(cands)
+        if k == "own":
+            own.setdefault(T, []).append((s, (pub[T, s] - tp) / 1e3))
+        if k == "load":
+            break
+        T, s = Tn, sn
+    for T, lst in own.items():
+        d = tasks[T]
+        steps = np.diff(pub[T]) / 1e3
+        print(f"task {T} kind {kind[T]} len {d[1]} n_words {d[4]} n_prod {d[6]} n_in {d[8]} n_out {d[9]}: own edges {[(s, round(x, 2)) for s, x in lst]}; "
+              f"its step times {np.round(steps, 2)}")
+        # how long after its last input did each step publish?
+        po, npr = tasks[T, 5], tasks[T, 6]
+        if npr:
+            last_in = np.max(pub[prod[po:po + npr]], axis=0)
+            print("   publish - last input (us):", np.round((pub[T] - last_in) / 1e3, 2))
+
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "--slow":
+    slow_stages(sys.argv[1])

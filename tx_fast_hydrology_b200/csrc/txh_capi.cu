@@ -458,6 +458,8 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
             a.off_T = wpc_upd * a.smem_per_warp;
             net->pending.T = nullptr;
         }
+        a.nap_min = 32; a.nap_max = 256;
+        if (const char* k = getenv("TXH_WINDOW_NAP")) { int lo = 32, hi = 256; if (sscanf(k, "%d,%d", &lo, &hi) >= 1) { a.nap_min = std::max(0, lo); a.nap_max = std::max(a.nap_min, hi); } }
         a.trace = nullptr;
         const char* trace_file = getenv("TXH_TRACE_FILE");
         unsigned long long* d_trace = nullptr;

@@ -131,6 +131,7 @@ struct WinArgs {
     // loaded -- p+ = p + (p - mean(p)) T + gauge terms, see route_window_kernel (n_mblocks == 1)
     const double* upT;                    // [M][M] ensemble transform, nullptr = no update pending
     int32_t off_T;                        // CTA-wide shared-memory copy of T (32 KB, behind the per-warp areas)
+    int32_t nap_min, nap_max;             // back-off (ns) of a warp polling for a row another task has not published yet
     const double* upW;                    // [gauges][M]
     const double* upQs;                   // [gauges]
     const int32_t* gfix_off;              // [n_tasks + 1] gauge terms per task
