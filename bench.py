@@ -724,6 +724,8 @@ def c3_arm(a, rank, world, local, full):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": k_ms,
                 "launches_timed": len(k_list), "bytes_per_update": ab,
+                "note": ("from the second window on the launch also applies the previous EnKF update while it loads its "
+                         "tasks (DESIGN.md 4.4); the algorithmic bytes count the routing only"),
                 "routing_share_of_step": k_ms * nwin / ms_step if ms_step > 0 else None}
     if traffic:
         # The state stays in shared memory for the 12 steps of a window, so the kernel moves ~10x fewer bytes than
