@@ -333,7 +333,7 @@ def test_enkf_update_vs_oracle(oracle, n, M, m, seed, diag):
     assert relerr(mdl.i_t_next, I_ref) < RTOL
 
 
-def _run_assimilating_case(oracle, n, M, m, seed, in_library, every=6, nwin=3, rest=0, gidx=None):
+def _run_assimilating_case(oracle, n, M, m, seed, in_library, every=6, nwin=3, rest=0, gidx=None, dense_R=False):
     """`nwin` windows of `every` routing steps + one EnKF update each, then `rest` more routing steps, on the device
     (through the Python API) and on the CPU oracle; returns what the assertions need."""
     import torch
@@ -359,6 +359,9 @@ def _run_assimilating_case(oracle, n, M, m, seed, in_library, every=6, nwin=3, r
     meas = rng.uniform(0.5, 8.0, size=(nwin, m))
     mdf = frame(mt, meas, [d["reach_ids"][j] for j in gidx])
     R = 1e-2 * np.eye(m)
+    if dense_R:                                                   # correlated observation errors: SPD, not diagonal
+        Bm = rng.standard_normal((m, m))
+        R = 1e-2 * (np.eye(m) + 0.5 * (Bm @ Bm.T) / m)
     q = rng.uniform(0.5, 2.0, size=n)
     enkf = EnsembleKalmanFilter(mdl, mdf, q, R)
     Zp = meas[:, :, None] + 0.1 * rng.standard_normal((nwin, m, M))
@@ -414,6 +417,15 @@ def test_run_assimilating_remainder_steps(oracle, M):
     """nsteps is not a multiple of `every`: the last update is applied by the launch that routes the remaining steps
     (txh_run_assimilating), nothing is left owed to the state."""
     mdl, o, i, so, si, tol = _run_assimilating_case(oracle, 1500, M, 25, 11, True, every=5, nwin=2, rest=3)
+    assert relerr(mdl.o_t_next, o, scale=so) < tol
+    assert relerr(mdl.i_t_next, i, scale=si) < tol
+
+
+@pytest.mark.parametrize("M", [48, 70])
+def test_run_assimilating_dense_R(oracle, M):
+    """Correlated observation errors (dense R): the ensemble-space system takes the general launches (D^-1 dense), the
+    update is still applied by the next window launch for M <= 64."""
+    mdl, o, i, so, si, tol = _run_assimilating_case(oracle, 1400, M, 90, 17, True, every=5, nwin=3, dense_R=True)
     assert relerr(mdl.o_t_next, o, scale=so) < tol
     assert relerr(mdl.i_t_next, i, scale=si) < tol
 

@@ -148,12 +148,14 @@ __device__ __forceinline__ double2 empty_cell()
 }
 
 // Polls `cell` (this lane's 16 bytes of a ring row) until it is full; `v` is what an earlier read saw.
-// Returns false when the launch is being abandoned (watchdog / poisoned handle).
+// Returns false when the launch is being abandoned (watchdog / poisoned handle).  (Moving the polling loop into a
+// function of its own to shrink the dozen walks that inline it costs 40 us per launch: the call spills the walk's
+// registers.)
 __device__ __forceinline__ bool wait_cell(const WinArgs& a, const double* cell, bool active, double2& v, int lane)
 {
     bool ok = !active || cell_full(v);
     if (__all_sync(0xffffffffu, ok)) return true;
-    unsigned spins = 0, nap = 32;
+    unsigned spins = 0, nap = (unsigned)a.nap_min;
     unsigned long long t0 = 0;
     for (;;) {
         if (!ok) { v = ld_cell_relaxed(cell); ok = cell_full(v); }
@@ -164,8 +166,8 @@ __device__ __forceinline__ bool wait_cell(const WinArgs& a, const double* cell, 
             if (t0 == 0) t0 = now;
             else if (now - t0 > a.watchdog_ns) { if (lane == 0) atomicExch(a.status, 1); return false; }
         }
-        __nanosleep(nap);
-        if (nap < 256u) nap <<= 1;
+        if (nap) __nanosleep(nap);
+        if (nap < (unsigned)a.nap_max) nap <<= 1;
     }
 }
 
@@ -267,7 +269,66 @@ struct Tk {
     size_t step_bytes;
 };
 
-// One step of a pocket: depth-first walk, o' = alpha*inflow + (p + gamma q), p' = beta*inflow + chi*o'.
+// p + gamma*q of this lane's two members, accumulated with fused multiply-adds (one operation less per member than
+// forming q first)
+template <bool HAS_F, bool HAS_W>
+__device__ __forceinline__ double2 forcing_add(const FCtx& c, double g0, double g1, double2 p)
+{
+    if (HAS_F) {
+        if (HAS_W) {
+            p.x = fma(c.wm1.x, g1, fma(c.wm0.x, g0, p.x));
+            p.y = fma(c.wm1.y, g1, fma(c.wm0.y, g0, p.y));
+        } else {
+            const double q = c.w0 * g0 + c.w1 * g1;
+            p.x += q; p.y += q;
+        }
+    }
+    return p;
+}
+
+// One row of a pocket step (see pocket_step)
+template <bool LAST, bool HAS_F, bool HAS_W>
+__device__ __forceinline__ void pocket_row(const WinArgs& a, const Tk& tk, InStream& ist, const FCtx& fc, char* ringS,
+                                           const RowIn& x, double2& acc, unsigned& aW, unsigned aP, double* ig, double* og, int r)
+{
+    const uint32_t h = x.h;
+    double2 inflow = (h & HDR_ACC) ? acc : make_double2(0.0, 0.0);
+    for (uint32_t k = (h >> 6) & 0x1ffffffu; k > 0; --k) {
+        const uint32_t w = lds_u32(aW);
+        aW += 4u;
+        const double2 v = (w & WIN_SLOT) ? stream_next<kInRing>(ist, a, tk.sIn, tk.sList, tk.nL, tk.step_bytes, tk.active, tk.lane)
+                                         : lds_row(tk.sScr + (w << 9));
+        inflow.x += v.x; inflow.y += v.y;
+    }
+    const double2 pq = forcing_add<HAS_F, HAS_W>(fc, x.g0, x.g1, x.p);
+    double2 on;
+    on.x = fma(x.al, inflow.x, pq.x);
+    on.y = fma(x.al, inflow.y, pq.y);
+    if (!LAST) {
+        double2 pn;
+        pn.x = x.be * inflow.x + x.ch * on.x;
+        pn.y = x.be * inflow.y + x.ch * on.y;
+        sts_row(aP, pn);
+    } else {
+        if (tk.active) { st_row(ig, inflow); st_row(og, on); }
+        if (a.rowsum) emit_rowsum(a, tk.begin + r, tk.col, on, tk.lane);
+    }
+    if (h & (HDR_PUSH | 0x3eu)) {                               // published and / or parked in a scratch row
+        if (h & HDR_PUSH) {
+            const uint32_t slot = lds_u32(aW);
+            aW += 4u;
+            if (tk.active) st_row(reinterpret_cast<double*>(ringS + (size_t)slot * tk.ld * sizeof(double)), on);
+        }
+        const uint32_t sl = (h >> 1) & 31u;
+        if (sl) sts_row(tk.sScr + ((sl - 1u) << 9), on);
+    }
+    acc = on;
+}
+
+// One step of a pocket: depth-first walk, o' = alpha*inflow + (p + gamma q), p' = beta*inflow + chi*o'.  The record of
+// a row (RowIn) is read one row ahead of the arithmetic.  (Unrolling the walk by two rows with the two records
+// alternating removes the 17 register moves at the loop edge -- and was 8 % slower: the kernel is sensitive to its code
+// size.)
 template <bool LAST, bool HAS_F, bool HAS_W>
 __device__ __forceinline__ void pocket_step(const WinArgs& a, const Tk& tk, InStream& ist, const FCtx& fc, char* ringS)
 {
@@ -279,40 +340,9 @@ __device__ __forceinline__ void pocket_step(const WinArgs& a, const Tk& tk, InSt
     for (int r = 0; r < tk.len; ++r) {
         const RowIn x = nx;
         if (r + 1 < tk.len) nx = load_rowin(aRec + kRec, aP + 512u);
-        const uint32_t h = x.h;
-        double2 inflow = (h & HDR_ACC) ? acc : make_double2(0.0, 0.0);
-        for (uint32_t k = (h >> 6) & 0x1ffffffu; k > 0; --k) {
-            const uint32_t w = lds_u32(aW);
-            aW += 4u;
-            const double2 v = (w & WIN_SLOT) ? stream_next<kInRing>(ist, a, tk.sIn, tk.sList, tk.nL, tk.step_bytes, tk.active, tk.lane)
-                                             : lds_row(tk.sScr + (w << 9));
-            inflow.x += v.x; inflow.y += v.y;
-        }
-        const double2 q = forcing_q<HAS_F, HAS_W>(fc, x.g0, x.g1);
-        double2 on;
-        on.x = x.al * inflow.x + (x.p.x + q.x);
-        on.y = x.al * inflow.y + (x.p.y + q.y);
-        if (!LAST) {
-            double2 pn;
-            pn.x = x.be * inflow.x + x.ch * on.x;
-            pn.y = x.be * inflow.y + x.ch * on.y;
-            sts_row(aP, pn);
-        } else {
-            if (tk.active) { st_row(ig, inflow); st_row(og, on); }
-            if (a.rowsum) emit_rowsum(a, tk.begin + r, tk.col, on, tk.lane);
-            ig += tk.ld; og += tk.ld;
-        }
-        if (h & (HDR_PUSH | 0x3eu)) {                               // published and / or parked in a scratch row
-            if (h & HDR_PUSH) {
-                const uint32_t slot = lds_u32(aW);
-                aW += 4u;
-                if (tk.active) st_row(reinterpret_cast<double*>(ringS + (size_t)slot * tk.ld * sizeof(double)), on);
-            }
-            const uint32_t sl = (h >> 1) & 31u;
-            if (sl) sts_row(tk.sScr + ((sl - 1u) << 9), on);
-        }
-        acc = on;
+        pocket_row<LAST, HAS_F, HAS_W>(a, tk, ist, fc, ringS, x, acc, aW, aP, ig, og, r);
         aRec += kRec; aP += 512u;
+        ig += tk.ld; og += tk.ld;
     }
 }
 
