@@ -391,17 +391,17 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     a.off_cumc = a.off_cum + up16(rc * 8);
     a.off_words = a.off_cumc + up16(rc * 8);
     a.off_list = a.off_words + up16(std::max(1, s.w_max_words) * 4);
-    a.off_steps = a.off_list + up16(std::max(1, s.w_max_words) * 4);
-    a.off_mbar = a.off_steps + 16 * 24;                       // StepInterp records of one launch (<= 16 steps)
+    a.off_mbar = a.off_list + up16(std::max(1, s.w_max_words) * 4);
     a.smem_per_warp = a.off_mbar + 16;                        // + the warp's mbarrier (bulk staging of the state rows)
+    const int steps_bytes = 16 * 24;                          // StepInterp records of one launch (<= 16 steps), once per CTA
     if (const char* k = getenv("TXH_WINDOW_BULK")) { if (atoi(k) == 0) a.off_mbar = 0; }
     if ((size_t)std::max(1, s.n_wslots) * ld * sizeof(double) >= (size_t(1) << 32)) return 1;   // 32-bit slot offsets
     const int smem_max = 227 * 1024;
-    int wpc = std::min(16, (smem_max - 1024) / a.smem_per_warp);
+    int wpc = std::min(16, (smem_max - 1024 - steps_bytes) / a.smem_per_warp);
     if (const char* k = getenv("TXH_WINDOW_WARPS")) wpc = std::max(1, std::min(wpc, atoi(k)));
     if (wpc < 2 || s.w_n_own > 0) return 1;
     // a launch that applies an ensemble update keeps the 64 x 64 transform in shared memory: fewer warps per CTA
-    const int wpc_upd = std::min(wpc, (smem_max - 1024 - 64 * 64 * (int)sizeof(double) - 16) / a.smem_per_warp);
+    const int wpc_upd = std::min(wpc, (smem_max - 1024 - steps_bytes - 64 * 64 * (int)sizeof(double) - 16) / a.smem_per_warp);
     if (probe_only) return wpc_upd >= 2 ? TXH_OK : 1;
     // ring[step][slot][ld]: one launch covers 16 steps, up to 64 while the ring stays below 64 MiB (few members):
     // a launch costs the critical path of one step before its pipeline is full, so longer launches amortise it
@@ -458,6 +458,7 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
             a.off_T = wpc_upd * a.smem_per_warp;
             net->pending.T = nullptr;
         }
+        a.off_steps = a.upT ? a.off_T + 64 * 64 * (int)sizeof(double) + 16 : wpc * a.smem_per_warp;
         a.nap_min = 32; a.nap_max = 256;
         if (const char* k = getenv("TXH_WINDOW_NAP")) { int lo = 32, hi = 256; if (sscanf(k, "%d,%d", &lo, &hi) >= 1) { a.nap_min = std::max(0, lo); a.nap_max = std::max(a.nap_min, hi); } }
         a.trace = nullptr;

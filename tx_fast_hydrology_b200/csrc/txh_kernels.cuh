@@ -121,8 +121,9 @@ struct WinArgs {
     unsigned long long watchdog_ns;
     int64_t n;
     int32_t n_tasks, n_mblocks, nsteps, n_slots, ld, M, wm_ld;
-    // per-warp shared memory (bytes): [p rows][scratch slots][input ring][row records][cumA][cumC][words][slot list][steps]
-    int32_t smem_per_warp, off_scr, off_in, off_rec, off_cum, off_cumc, off_words, off_list, off_steps;
+    // per-warp shared memory (bytes): [p rows][scratch slots][input ring][row records][cumA][cumC][words][slot list][mbarrier]
+    int32_t smem_per_warp, off_scr, off_in, off_rec, off_cum, off_cumc, off_words, off_list;
+    int32_t off_steps;                    // CTA-wide (behind the per-warp areas and T): interpolation records of the launch's steps
     int32_t off_mbar;                     // > 0: per-warp mbarrier for the bulk (TMA) staging of the state rows
     unsigned long long* trace;            // optional [pairs][4 + nsteps] timeline (claim, loaded, end, kind|smid, publish per step)
     double* rowsum;                       // optional [n]: scale * sum over the members of the final outflows (n_mblocks == 1)

@@ -512,7 +512,7 @@ route_window_kernel(const WinArgs a)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned sb = (unsigned)__cvta_generic_to_shared(smem_all + (size_t)warp * a.smem_per_warp);
-    const unsigned sSteps = sb + a.off_steps;
+    const unsigned sSteps = (unsigned)__cvta_generic_to_shared(smem_all) + (unsigned)a.off_steps;   // one copy per CTA
     const int nmb = a.n_mblocks, ld = a.ld;
     const long long total = (long long)a.n_tasks * nmb;
     Tk tk;
@@ -537,10 +537,19 @@ route_window_kernel(const WinArgs a)
     const unsigned sT = (unsigned)__cvta_generic_to_shared(smem_all) + (unsigned)a.off_T;
     const unsigned sTcount = sT + 64u * 64u * 8u;
     bool t_ready = !UPD;
-    if (UPD) {
-        if (threadIdx.x == 0) sts_u32(sTcount, 0u);
-        __syncthreads();
+    if (UPD && threadIdx.x == 0) sts_u32(sTcount, 0u);
+    // the launch's interpolation records (24 B each), once per CTA when they fit (<= kStepsStaged): copied, or -- no
+    // init kernel -- resolved here, one step per lane (nothing of this depends on the kernel in front of the launch)
+    if (HAS_F && a.nsteps <= kStepsStaged && warp == 0) {
+        if (a.steps != nullptr) {
+            for (int i = lane; i < 6 * a.nsteps; i += 32) sts_u32(sSteps + 4u * i, __ldg(reinterpret_cast<const uint32_t*>(a.steps) + i));
+        } else if (lane < a.nsteps) {
+            const StepInterp si = interp_step(a.times, a.R, (double)(a.t0_ns + (a.step_base + lane + 1) * a.dt_ns), a.method);
+            sts_u32(sSteps + 24u * lane, (uint32_t)si.r0); sts_u32(sSteps + 24u * lane + 4u, (uint32_t)si.r1);
+            sts_f64(sSteps + 24u * lane + 8u, si.w0); sts_f64(sSteps + 24u * lane + 16u, si.w1);
+        }
     }
+    __syncthreads();
     griddep_launch_dependents();
     auto stage_T = [&]() {
         griddep_wait();
@@ -580,7 +589,7 @@ route_window_kernel(const WinArgs a)
 
         // ---- load the task: input stream, step records, per-row records; rows of I and O -> p ----
         for (int i = lane; i < td.n_words; i += 32) cp_async4(tk.sWords + 4u * i, a.inw + td.in_off + i);
-        // the launch's interpolation records (24 B each): staged when they fit (<= kStepsStaged), else read in place
+        // the launch's interpolation records: in shared memory when they fit (<= kStepsStaged), else read in place
         const bool steps_staged = a.nsteps <= kStepsStaged;
         auto step_rows = [&](int s) -> int2 {
             if (steps_staged) return make_int2((int)lds_u32(sSteps + 24u * s), (int)lds_u32(sSteps + 24u * s + 4u));
@@ -590,15 +599,6 @@ route_window_kernel(const WinArgs a)
             if (steps_staged) return make_double2(lds_f64(sSteps + 24u * s + 8u), lds_f64(sSteps + 24u * s + 16u));
             return make_double2(__ldg(&a.steps[s].w0), __ldg(&a.steps[s].w1));
         };
-        if (HAS_F && steps_staged) {
-            if (a.steps != nullptr) {
-                for (int i = lane; i < 6 * a.nsteps; i += 32) cp_async4(sSteps + 4u * i, reinterpret_cast<const uint32_t*>(a.steps) + i);
-            } else if (lane < a.nsteps) {                      // no init kernel: resolved here, one step per lane
-                const StepInterp si = interp_step(a.times, a.R, (double)(a.t0_ns + (a.step_base + lane + 1) * a.dt_ns), a.method);
-                sts_u32(sSteps + 24u * lane, (uint32_t)si.r0); sts_u32(sSteps + 24u * lane + 4u, (uint32_t)si.r1);
-                sts_f64(sSteps + 24u * lane + 8u, si.w0); sts_f64(sSteps + 24u * lane + 16u, si.w1);
-            }
-        }
         // rows of O straight into their p slots, rows of I (eight at a time) into the scratch / ring area: every
         // load of the task is in flight before the first is waited for
         if (bulk) {
@@ -801,7 +801,8 @@ cudaError_t launch_window_init(const InitArgs& a, unsigned long long* ticket, cu
 
 cudaError_t launch_route_window(const WinArgs& a, int warps_per_cta, int num_sms, cudaStream_t st)
 {
-    const size_t smem = a.upT ? (size_t)a.off_T + 64 * 64 * sizeof(double) + 16 : (size_t)warps_per_cta * a.smem_per_warp;
+    const size_t smem = (size_t)a.off_steps + 16 * 24;          // [per-warp areas][T + counter (update variant)][step records]
+    (void)warps_per_cta;
     static const bool pdl = [] { const char* k = getenv("TXH_PDL"); return !(k && atoi(k) == 0); }();
     void (*kern)(const WinArgs) = nullptr;
     const bool f = a.F != nullptr, w = a.Wmul != nullptr;
