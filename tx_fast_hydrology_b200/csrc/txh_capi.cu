@@ -384,24 +384,32 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     WinArgs a{};
     auto up16 = [](int x) { return (x + 15) & ~15; };
     const int rc = std::max(1, s.w_max_len), slots = std::max(1, s.slots_used);
-    a.off_scr = rc * 512;
-    a.off_in = a.off_scr + slots * 512;
-    a.off_rec = a.off_in + std::max(4, 8 - slots) * 512;      // segments stream through [scratch | ring]: >= 8 rows
-    a.off_cum = a.off_rec + rc * 48;
-    a.off_cumc = a.off_cum + up16(rc * 8);
-    a.off_words = a.off_cumc + up16(rc * 8);
-    a.off_list = a.off_words + up16(std::max(1, s.w_max_words) * 4);
-    a.off_mbar = a.off_list + up16(std::max(1, s.w_max_words) * 4);
-    a.smem_per_warp = a.off_mbar + 16;                        // + the warp's mbarrier (bulk staging of the state rows)
+    const bool bulk_off = [] { const char* k = getenv("TXH_WINDOW_BULK"); return k && atoi(k) == 0; }();
+    // per-warp layout; `seg_ring` rows for the input stream of a segment ([scratch | ring]), `in_ring` for a pocket's
+    auto layout = [&](int in_ring, int seg_ring) {
+        a.off_scr = rc * 512;
+        a.off_in = a.off_scr + slots * 512;
+        a.off_rec = a.off_in + std::max(in_ring, seg_ring - slots) * 512;
+        a.off_cum = a.off_rec + rc * 48;
+        a.off_cumc = a.off_cum + up16(rc * 8);
+        a.off_words = a.off_cumc + up16(rc * 8);
+        a.off_list = a.off_words + up16(std::max(1, s.w_max_words) * 4);
+        a.off_mbar = a.off_list + up16(std::max(1, s.w_max_words) * 4);
+        a.smem_per_warp = a.off_mbar + 16;                    // + the warp's mbarrier (bulk staging of the state rows)
+        if (bulk_off) a.off_mbar = 0;
+    };
     const int steps_bytes = 16 * 24;                          // StepInterp records of one launch (<= 16 steps), once per CTA
-    if (const char* k = getenv("TXH_WINDOW_BULK")) { if (atoi(k) == 0) a.off_mbar = 0; }
     if ((size_t)std::max(1, s.n_wslots) * ld * sizeof(double) >= (size_t(1) << 32)) return 1;   // 32-bit slot offsets
     const int smem_max = 227 * 1024;
-    int wpc = std::min(16, (smem_max - 1024 - steps_bytes) / a.smem_per_warp);
-    if (const char* k = getenv("TXH_WINDOW_WARPS")) wpc = std::max(1, std::min(wpc, atoi(k)));
+    int warps_cap = 16;
+    if (const char* k = getenv("TXH_WINDOW_WARPS")) warps_cap = std::max(1, std::min(16, atoi(k)));
+    // a launch that applies an ensemble update keeps the 64 x 64 transform in shared memory and runs shorter input rings
+    // (txh_window.cu: kInRingUpd, kSegRingUpd): fewer warps per CTA
+    layout(3, 7);
+    const int wpc_upd = std::min(warps_cap, (smem_max - 1024 - steps_bytes - 64 * 64 * (int)sizeof(double) - 16) / a.smem_per_warp);
+    layout(4, 8);
+    const int wpc = std::min(warps_cap, (smem_max - 1024 - steps_bytes) / a.smem_per_warp);
     if (wpc < 2 || s.w_n_own > 0) return 1;
-    // a launch that applies an ensemble update keeps the 64 x 64 transform in shared memory: fewer warps per CTA
-    const int wpc_upd = std::min(wpc, (smem_max - 1024 - steps_bytes - 64 * 64 * (int)sizeof(double) - 16) / a.smem_per_warp);
     if (probe_only) return wpc_upd >= 2 ? TXH_OK : 1;
     // ring[step][slot][ld]: one launch covers 16 steps, up to 64 while the ring stays below 64 MiB (few members):
     // a launch costs the critical path of one step before its pipeline is full, so longer launches amortise it
@@ -455,9 +463,10 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
             // the ensemble update owed to the state is applied by this launch while it loads its tasks
             a.upT = net->pending.T; a.upW = net->pending.W; a.upQs = net->pending.qs;
             a.gfix_off = net->d_gfix_off; a.gfix = net->d_gfix;
+            layout(3, 7);
             a.off_T = wpc_upd * a.smem_per_warp;
             net->pending.T = nullptr;
-        }
+        } else layout(4, 8);
         a.off_steps = a.upT ? a.off_T + 64 * 64 * (int)sizeof(double) + 16 : wpc * a.smem_per_warp;
         a.nap_min = 32; a.nap_max = 256;
         if (const char* k = getenv("TXH_WINDOW_NAP")) { int lo = 32, hi = 256; if (sscanf(k, "%d,%d", &lo, &hi) >= 1) { a.nap_min = std::max(0, lo); a.nap_max = std::max(a.nap_min, hi); } }

@@ -123,6 +123,8 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 
 constexpr int kInRing = 4;                 // pockets: rows of other tasks in flight per warp (cp.async ring)
 constexpr int kSegRing = 8;                // segments: the ring also takes the (unused) scratch slots
+constexpr int kInRingUpd = 3;              // the update variant gives a ring row per warp to the CTA's copy of T (15 warps
+constexpr int kSegRingUpd = 7;             // fit instead of 14); the per-warp layout of the launch is sized accordingly
 constexpr int kStepsStaged = 16;            // interpolation records of a launch kept in shared memory
 constexpr int kWinThreads = 512;           // one CTA per SM, up to 16 warps
 constexpr uint32_t kIdMask = 0x3fffffffu;
@@ -287,7 +289,7 @@ __device__ __forceinline__ double2 forcing_add(const FCtx& c, double g0, double 
 }
 
 // One row of a pocket step (see pocket_step)
-template <bool LAST, bool HAS_F, bool HAS_W>
+template <bool LAST, bool HAS_F, bool HAS_W, int IR>
 __device__ __forceinline__ void pocket_row(const WinArgs& a, const Tk& tk, InStream& ist, const FCtx& fc, char* ringS,
                                            const RowIn& x, double2& acc, unsigned& aW, unsigned aP, double* ig, double* og, int r)
 {
@@ -296,7 +298,7 @@ __device__ __forceinline__ void pocket_row(const WinArgs& a, const Tk& tk, InStr
     for (uint32_t k = (h >> 6) & 0x1ffffffu; k > 0; --k) {
         const uint32_t w = lds_u32(aW);
         aW += 4u;
-        const double2 v = (w & WIN_SLOT) ? stream_next<kInRing>(ist, a, tk.sIn, tk.sList, tk.nL, tk.step_bytes, tk.active, tk.lane)
+        const double2 v = (w & WIN_SLOT) ? stream_next<IR>(ist, a, tk.sIn, tk.sList, tk.nL, tk.step_bytes, tk.active, tk.lane)
                                          : lds_row(tk.sScr + (w << 9));
         inflow.x += v.x; inflow.y += v.y;
     }
@@ -329,7 +331,7 @@ __device__ __forceinline__ void pocket_row(const WinArgs& a, const Tk& tk, InStr
 // a row (RowIn) is read one row ahead of the arithmetic.  (Unrolling the walk by two rows with the two records
 // alternating removes the 17 register moves at the loop edge -- and was 8 % slower: the kernel is sensitive to its code
 // size.)
-template <bool LAST, bool HAS_F, bool HAS_W>
+template <bool LAST, bool HAS_F, bool HAS_W, int IR>
 __device__ __forceinline__ void pocket_step(const WinArgs& a, const Tk& tk, InStream& ist, const FCtx& fc, char* ringS)
 {
     unsigned aRec = tk.sRec, aP = tk.sP, aW = tk.sWords;
@@ -340,7 +342,7 @@ __device__ __forceinline__ void pocket_step(const WinArgs& a, const Tk& tk, InSt
     for (int r = 0; r < tk.len; ++r) {
         const RowIn x = nx;
         if (r + 1 < tk.len) nx = load_rowin(aRec + kRec, aP + 512u);
-        pocket_row<LAST, HAS_F, HAS_W>(a, tk, ist, fc, ringS, x, acc, aW, aP, ig, og, r);
+        pocket_row<LAST, HAS_F, HAS_W, IR>(a, tk, ist, fc, ringS, x, acc, aW, aP, ig, og, r);
         aRec += kRec; aP += 512u;
         ig += tk.ld; og += tk.ld;
     }
@@ -352,7 +354,7 @@ __device__ __forceinline__ void pocket_step(const WinArgs& a, const Tk& tk, InSt
 //   C_k = beta_k A_{k-1} + chi_k A_k  (A = prefix product of alpha, A_{-1} = 1; precomputed).
 // Hop: out = A_last * o_in + B_last, handed on before anything else.  In the last step (side_k, B_k) are
 // parked in the global I / O rows for the final fix-up o_k = B_k + A_k o_in, i_k = o_{k-1} + side_k.
-template <bool LAST, bool HAS_F, bool HAS_W>
+template <bool LAST, bool HAS_F, bool HAS_W, int SR>
 __device__ __forceinline__ void segment_step(const WinArgs& a, const Tk& tk, InStream& ist, const FCtx& fc, char* ringS,
                                              int out_slot, unsigned long long* trs)
 {
@@ -368,7 +370,7 @@ __device__ __forceinline__ void segment_step(const WinArgs& a, const Tk& tk, InS
         double2 inflow = (h & HDR_ACC) ? B : make_double2(0.0, 0.0);   // side_k + B_{k-1}
         double2 side = make_double2(0.0, 0.0);
         for (uint32_t k = (h >> 6) & 0x1fffu; k > 0; --k) {
-            const double2 v = stream_next<kSegRing>(ist, a, tk.sScr, tk.sList, tk.nL, tk.step_bytes, tk.active, tk.lane);
+            const double2 v = stream_next<SR>(ist, a, tk.sScr, tk.sList, tk.nL, tk.step_bytes, tk.active, tk.lane);
             side.x += v.x; side.y += v.y;
         }
         inflow.x += side.x; inflow.y += side.y;
@@ -513,6 +515,7 @@ route_window_kernel(const WinArgs a)
     const int warp = threadIdx.x >> 5;
     const unsigned sb = (unsigned)__cvta_generic_to_shared(smem_all + (size_t)warp * a.smem_per_warp);
     const unsigned sSteps = (unsigned)__cvta_generic_to_shared(smem_all) + (unsigned)a.off_steps;   // one copy per CTA
+    constexpr int IR = UPD ? kInRingUpd : kInRing, SR = UPD ? kSegRingUpd : kSegRing;
     const int nmb = a.n_mblocks, ld = a.ld;
     const long long total = (long long)a.n_tasks * nmb;
     Tk tk;
@@ -599,14 +602,14 @@ route_window_kernel(const WinArgs a)
             if (steps_staged) return make_double2(lds_f64(sSteps + 24u * s + 8u), lds_f64(sSteps + 24u * s + 16u));
             return make_double2(__ldg(&a.steps[s].w0), __ldg(&a.steps[s].w1));
         };
-        // rows of O straight into their p slots, rows of I (eight at a time) into the scratch / ring area: every
+        // rows of O straight into their p slots, rows of I (SR at a time) into the [scratch | ring] area: every
         // load of the task is in flight before the first is waited for
         if (bulk) {
             // the rows were last touched by this warp's ordinary stores: order them before the async proxy's writes
             __syncwarp();
             if (lane == 0) {
                 fence_proxy_async();
-                const unsigned bo = 512u * (unsigned)len, bi = 512u * (unsigned)(len < 8 ? len : 8);
+                const unsigned bo = 512u * (unsigned)len, bi = 512u * (unsigned)(len < SR ? len : SR);
                 mbar_expect_tx(sMbar, bo + bi);
                 bulk_g2s(sb, a.O + (size_t)td.begin * ld, bo, sMbar);
                 bulk_g2s(sb + a.off_scr, a.I + (size_t)td.begin * ld, bi, sMbar);
@@ -614,7 +617,7 @@ route_window_kernel(const WinArgs a)
         } else if (active) {
             for (int r = 0; r < len; ++r) {
                 cp_async16(tk.sP + 512u * r, tk.Og + (size_t)r * ld);
-                if (r < 8) cp_async16(tk.sScr + 512u * r, tk.Ig + (size_t)r * ld);
+                if (r < SR) cp_async16(tk.sScr + 512u * r, tk.Ig + (size_t)r * ld);
             }
         }
         cp_async_commit();
@@ -629,25 +632,25 @@ route_window_kernel(const WinArgs a)
             sts_f64(tk.sCum + 8u * i, a.cumA[td.begin + i]);
             sts_f64(tk.sCumC + 8u * i, a.cumC[td.begin + i]);
         }
-        for (int r0 = 0; r0 < len; r0 += 8) {
+        for (int r0 = 0; r0 < len; r0 += SR) {
             if (r0 > 0) {
                 if (bulk) {
                     __syncwarp();                               // the previous chunk has been read by every lane
                     if (lane == 0) {
                         fence_proxy_async();
-                        const unsigned bi = 512u * (unsigned)(len - r0 < 8 ? len - r0 : 8);
+                        const unsigned bi = 512u * (unsigned)(len - r0 < SR ? len - r0 : SR);
                         mbar_expect_tx(sMbar, bi);
                         bulk_g2s(sb + a.off_scr, a.I + (size_t)(td.begin + r0) * ld, bi, sMbar);
                     }
                 } else if (active) {
-                    for (int r = r0; r < len && r < r0 + 8; ++r) cp_async16(tk.sScr + 512u * (r - r0), tk.Ig + (size_t)r * ld);
+                    for (int r = r0; r < len && r < r0 + SR; ++r) cp_async16(tk.sScr + 512u * (r - r0), tk.Ig + (size_t)r * ld);
                 }
                 cp_async_commit();
             }
             cp_async_wait_all();
             if (bulk) { mbar_wait(sMbar, mphase); mphase ^= 1u; }
             __syncwarp();
-            for (int r = r0; r < len && r < r0 + 8; ++r) {
+            for (int r = r0; r < len && r < r0 + SR; ++r) {
                 const double2 bc = lds_row(tk.sRec + kRec * r + 16u);
                 double2 p = make_double2(0.0, 0.0);
                 if (active) {
@@ -720,9 +723,9 @@ route_window_kernel(const WinArgs a)
         ist.psteps = nL > 0 ? a.nsteps : 0;
         ist.pbase = reinterpret_cast<char*>(a.ring + ccol);
         ist.cbase = ist.pbase;
-        for (int j = 0; j < (seg ? kSegRing : kInRing) && ist.psteps > 0; ++j) {
-            if (seg) stream_issue<kSegRing>(ist, a, ring_sa, tk.sList, nL, tk.step_bytes, active);
-            else stream_issue<kInRing>(ist, a, ring_sa, tk.sList, nL, tk.step_bytes, active);
+        for (int j = 0; j < (seg ? SR : IR) && ist.psteps > 0; ++j) {
+            if (seg) stream_issue<SR>(ist, a, ring_sa, tk.sList, nL, tk.step_bytes, active);
+            else stream_issue<IR>(ist, a, ring_sa, tk.sList, nL, tk.step_bytes, active);
         }
 
         for (int s = 0; s < a.nsteps; ++s) {
@@ -747,13 +750,13 @@ route_window_kernel(const WinArgs a)
                 if (!last) fc_next = load_fctx(s + 1);           // in flight during this step
             }
             if (!seg) {
-                if (last) pocket_step<true, HAS_F, HAS_W>(a, tk, ist, fc, ringS);
-                else pocket_step<false, HAS_F, HAS_W>(a, tk, ist, fc, ringS);
+                if (last) pocket_step<true, HAS_F, HAS_W, IR>(a, tk, ist, fc, ringS);
+                else pocket_step<false, HAS_F, HAS_W, IR>(a, tk, ist, fc, ringS);
                 if (tr && lane == 0) tr[4 + s] = globaltimer_ns();
             } else {
                 unsigned long long* trs = tr ? tr + 4 + s : nullptr;
-                if (last) segment_step<true, HAS_F, HAS_W>(a, tk, ist, fc, ringS, td.out_slot, trs);
-                else segment_step<false, HAS_F, HAS_W>(a, tk, ist, fc, ringS, td.out_slot, trs);
+                if (last) segment_step<true, HAS_F, HAS_W, SR>(a, tk, ist, fc, ringS, td.out_slot, trs);
+                else segment_step<false, HAS_F, HAS_W, SR>(a, tk, ist, fc, ringS, td.out_slot, trs);
             }
             if (ist.dead) break;
         }
