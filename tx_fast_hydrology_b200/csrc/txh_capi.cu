@@ -404,9 +404,10 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
     int warps_cap = 16;
     if (const char* k = getenv("TXH_WINDOW_WARPS")) warps_cap = std::max(1, std::min(16, atoi(k)));
     // a launch that applies an ensemble update keeps the 64 x 64 transform in shared memory and runs shorter input rings
-    // (txh_window.cu: kInRingUpd, kSegRingUpd): fewer warps per CTA
-    layout(3, 7);
-    const int wpc_upd = std::min(warps_cap, (smem_max - 1024 - steps_bytes - 64 * 64 * (int)sizeof(double) - 16) / a.smem_per_warp);
+    // (txh_window.cu: kInRingUpd, kSegRingUpd) to keep its warps: at the headline shape 16 x 12,432 B + 33,168 B of the
+    // 232,448 B a CTA may have
+    layout(2, 6);
+    const int wpc_upd = std::min(warps_cap, (smem_max - steps_bytes - 64 * 64 * (int)sizeof(double) - 16) / a.smem_per_warp);
     layout(4, 8);
     const int wpc = std::min(warps_cap, (smem_max - 1024 - steps_bytes) / a.smem_per_warp);
     if (wpc < 2 || s.w_n_own > 0) return 1;
@@ -463,7 +464,7 @@ int run_window(txh_net* net, double* O, double* I, int64_t M, const double* F, c
             // the ensemble update owed to the state is applied by this launch while it loads its tasks
             a.upT = net->pending.T; a.upW = net->pending.W; a.upQs = net->pending.qs;
             a.gfix_off = net->d_gfix_off; a.gfix = net->d_gfix;
-            layout(3, 7);
+            layout(2, 6);
             a.off_T = wpc_upd * a.smem_per_warp;
             net->pending.T = nullptr;
         } else layout(4, 8);

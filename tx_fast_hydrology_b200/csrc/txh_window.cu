@@ -123,8 +123,9 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 
 constexpr int kInRing = 4;                 // pockets: rows of other tasks in flight per warp (cp.async ring)
 constexpr int kSegRing = 8;                // segments: the ring also takes the (unused) scratch slots
-constexpr int kInRingUpd = 3;              // the update variant gives a ring row per warp to the CTA's copy of T (15 warps
-constexpr int kSegRingUpd = 7;             // fit instead of 14); the per-warp layout of the launch is sized accordingly
+constexpr int kInRingUpd = 2;              // the update variant gives two ring rows per warp to the CTA's copy of T (16 warps
+constexpr int kSegRingUpd = 6;             // fit instead of 14; measured: the ring depth does not matter, 3 / 7 rows at 15
+                                           // warps ran as fast as 2 / 6); the per-warp layout of the launch is sized accordingly
 constexpr int kStepsStaged = 16;            // interpolation records of a launch kept in shared memory
 constexpr int kWinThreads = 512;           // one CTA per SM, up to 16 warps
 constexpr uint32_t kIdMask = 0x3fffffffu;
