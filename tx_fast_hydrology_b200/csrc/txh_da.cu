@@ -637,8 +637,9 @@ enkf_small_system_kernel(double* __restrict__ HX, const double* __restrict__ O, 
     // programmatic dependent launch: this kernel may have started before the routing launch in front of it has
     // finished; what it reads is final after the wait, and the routing launch behind it (which reads T and W only
     // after a wait of its own) may start loading its tasks from here on
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // (the wait itself sits inside the first load_tile: the gauge positions, the observations and D^-1 do not come from
+    // the routing launch and are requested before it)
+    bool waited = false;
     stamp(0);
 
     // [HA | dz] of the gauges kt .. kt+63 -> sB (zero rows beyond k_hi), D^-1 -> sd; every load of a thread's
@@ -655,9 +656,19 @@ enkf_small_system_kernel(double* __restrict__ HX, const double* __restrict__ O, 
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
             const int k = kt + (tid >> 6) + 4 * u;
+            zp[u] = (pos[u] >= 0 && c < Mt) ? __ldg(Zp + (size_t)k * Mt + c) : 0.0;
+        }
+        const double dk = (tid < SS_KT && kt + tid < k_hi) ? __ldg(dinv + kt + tid) : 0.0;
+        if (!waited) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+            waited = true;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int k = kt + (tid >> 6) + 4 * u;
             const bool on = pos[u] >= 0 && c < Mt;
             hx[u] = on ? (O ? __ldcg(O + (size_t)pos[u] * ldo + c) : __ldcg(HX + (size_t)k * Mt + c)) : 0.0;
-            zp[u] = on ? __ldg(Zp + (size_t)k * Mt + c) : 0.0;
             mu[u] = on ? __ldcg(mean + pos[u]) : 0.0;
         }
 #pragma unroll
@@ -668,7 +679,7 @@ enkf_small_system_kernel(double* __restrict__ HX, const double* __restrict__ O, 
             sB[kk * SS_LDB + c] = hx[u] - mu[u];
             sB[kk * SS_LDB + 64 + c] = zp[u] - hx[u];
         }
-        if (tid < SS_KT) sd[tid] = kt + tid < k_hi ? __ldg(dinv + kt + tid) : 0.0;
+        if (tid < SS_KT) sd[tid] = dk;
     };
 
     // ---- 1. split-K partial of C = HA^T D^-1 [HA | dz]: warp tile 16 x 64 of the 64 x 128 product ----
