@@ -92,6 +92,12 @@ __device__ __forceinline__ void sts_i4(unsigned a, int4 v)
     asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void sts_u16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void cp_async8_s(unsigned sa, const void* g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(g) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async16_s(unsigned sa, const void* g)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
@@ -155,6 +161,7 @@ route_lane_kernel(const LaneArgs a)
         const unsigned sMetaV = sExt + 256u * MT * nv;         // [nv] records of the virtual rows
         const unsigned sChild = sMetaV + 16u * nv;             // children beyond the first two
         const unsigned sP = sChild + (((unsigned)(2 * rd.n_child)) + 15u & ~15u);   // [MT][nr] (MT > 4 only)
+        const unsigned sFn = sP + (PREG ? 0u : ((8u * MT * (unsigned)nr + 15u) & ~15u));   // [nr] forcing row after the bracket
         const unsigned sSteps = sbase + a.off_steps;           // [nsteps] per-step records (when they fit)
         // ---- this thread's row ----------------------------------------------------------------------------
         const bool has_row = tid < nr;
@@ -177,6 +184,7 @@ route_lane_kernel(const LaneArgs a)
                 f0 = __ldg(a.F + (size_t)r0s * a.n + pos);
                 f1 = __ldg(a.F + (size_t)r1s * a.n + pos);
                 fn = __ldg(a.F + (size_t)min(max(r0s, r1s) + 1, a.R - 1) * a.n + pos);
+                sts_d(sFn + 8u * (unsigned)tid, fn);
             }
             if (a.rec_slot) rec = a.rec_slot[pos];
             const double* og = a.O + (size_t)pos * ld;
@@ -220,9 +228,16 @@ route_lane_kernel(const LaneArgs a)
         const unsigned ra = 8u * (unsigned)tid;                 // this row's cell in an outflow buffer
         if (tr && tid == 0) { tr[1] = globaltimer_ns(); tr[4] = (unsigned long long)niter; tr[6] = 0ull; tr[7] = 0ull; }
         int dead = 0;
+        int kreq = -16;                                         // iteration of this row's last forcing request
         for (int k = 0; k < niter; ++k) {
             const unsigned obp = sOb + 8u * (unsigned)(((k & 1) ^ 1) * MT * rv);
             const unsigned obc = sOb + 8u * (unsigned)((k & 1) * MT * rv);
+            // the forcing row after a row's bracket waits in shared memory, requested with cp.async when the bracket was
+            // entered: one (possibly empty) group per iteration and thread, so everything requested nine or more
+            // iterations ago has landed after this wait.  (Kept in a register and requested with a plain load, the
+            // value blocked the whole warp: a few lanes change bracket in EVERY iteration, their load is still in flight
+            // when the next lanes read the register, and the iteration paid a global-memory latency, ~0.9 us.)
+            if (HAS_F && tid < TR) cp_async_wait_group<8>();
             const int s = k - off;
             if (has_row && (unsigned)s < (unsigned)nsteps) {
                 double w0 = 0.0, w1 = 0.0;
@@ -241,17 +256,20 @@ route_lane_kernel(const LaneArgs a)
                     }
                     fr1 = r1f & 0x3fffffff;
                     if (r1f < 0) {                               // the bracket differs from the previous step's
+                        if (k - kreq < 9) cp_async_wait_all();    // requested too recently for the wait above (dense tables)
                         if (r1f & 0x40000000) {
                             // the usual case, marked by lane_init_kernel: the bracket moved on by one row -- shift, and
-                            // request the row after it (its register is not read before the next change)
-                            f0 = f1; f1 = fn;
+                            // request the row after it
+                            f0 = f1; f1 = lds_d(sFn + ra);
                             const int nn = min(fr1 + 1, a.R - 1);
-                            if (nn != fr1) fn = __ldg(a.F + (size_t)nn * a.n + pos);
+                            if (nn != fr1) { cp_async8_s(sFn + ra, a.F + (size_t)nn * a.n + pos); kreq = k; }
                         } else {
                             int pr0, pr1;
                             if (a.off_steps > 0) { const int4 pp = lds_i4(sSteps + 32u * (s - 1) + 16u); pr0 = pp.x; pr1 = pp.y; }
                             else { pr0 = __ldg(&a.steps[s - 1].r0); pr1 = __ldg(&a.steps[s - 1].r1); }
+                            fn = lds_d(sFn + ra);
                             rotate_bracket(f0, f1, fn, a.F + pos, a.n, a.R, pr0, pr1 & 0x3fffffff, fr0, fr1);
+                            sts_d(sFn + ra, fn);
                         }
                     }
                 }
@@ -374,6 +392,7 @@ route_lane_kernel(const LaneArgs a)
                     }
                 }
             }
+            if (HAS_F && tid < TR) cp_async_commit();
             // the barrier between two iterations; every vote_every-th one also votes on abandoning the launch
             if ((k & vote_mask) == vote_mask || k + 1 == niter) {
                 if (__syncthreads_or(dead)) { abandon = true; break; }

@@ -697,7 +697,8 @@ size_t LaneSchedule::region_bytes(size_t real, size_t virt, size_t nchild, int m
            + 256 * (size_t)mt * virt       // 32 steps of every incoming stream
            + 16 * virt                     // records of the virtual rows
            + up16(2 * nchild)              // children beyond the first two of a row
-           + (mt > 4 ? up16(8 * (size_t)mt * real) : 0);   // p = beta i + chi o (in registers up to 4 members)
+           + (mt > 4 ? up16(8 * (size_t)mt * real) : 0)    // p = beta i + chi o (in registers up to 4 members)
+           + up16(8 * real);               // the forcing row after a row's bracket (cp.async target)
 }
 
 bool LaneSchedule::build(const Topology& t, const std::vector<int32_t>& pos_of_reach, int mt_, int cap_rows_,
@@ -710,7 +711,7 @@ bool LaneSchedule::build(const Topology& t, const std::vector<int32_t>& pos_of_r
     if (cap_rows < 1) { err = "lane schedule: bad row cap"; return false; }
     cap_rows = std::min(cap_rows, kLaneMaxRows);                            // one row per thread
     // weights in bytes: a real row with ~one child entry, a virtual row
-    const int64_t wr = 16 * (int64_t)mt + (mt > 4 ? 8 * (int64_t)mt : 0) + 2, wv = 16 + 272 * (int64_t)mt + 2;
+    const int64_t wr = 16 * (int64_t)mt + (mt > 4 ? 8 * (int64_t)mt : 0) + 8 + 2, wv = 16 + 272 * (int64_t)mt + 2;
     const int64_t cap_bytes = (int64_t)smem_budget - 256;               // sentinel record, alignment of the parts
     if (wr + wv > cap_bytes) { err = "lane schedule: shared-memory budget too small"; return false; }
 
