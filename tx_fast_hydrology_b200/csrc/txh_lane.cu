@@ -48,6 +48,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ void bar_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ int bar_or(int pred)
+{
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %1, 0;\n\tbar.red.or.pred p, 0, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"(pred) : "memory");
+    return r;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ bool is_empty(double v) { return __double_as_longlong(v) == -1ll; }
@@ -229,6 +237,15 @@ route_lane_kernel(const LaneArgs a)
         if (tr && tid == 0) { tr[1] = globaltimer_ns(); tr[4] = (unsigned long long)niter; tr[6] = 0ull; tr[7] = 0ull; }
         int dead = 0;
         int kreq = -16;                                         // iteration of this row's last forcing request
+        // Two loops, one per role -- the threads that own rows and the threads that mirror incoming streams -- meeting at
+        // the same barrier once per iteration (bar.sync / bar.red count arrivals, not program counters): each loop keeps
+        // only its own state live, which matters at 64 registers per thread.
+        auto iter_barrier = [&](int k) -> bool {               // every vote_every-th barrier also votes on abandoning the launch
+            if ((k & vote_mask) == vote_mask || k + 1 == niter) return bar_or(dead) != 0;
+            bar_sync();
+            return false;
+        };
+        if (tid < TR) {
         for (int k = 0; k < niter; ++k) {
             const unsigned obp = sOb + 8u * (unsigned)(((k & 1) ^ 1) * MT * rv);
             const unsigned obc = sOb + 8u * (unsigned)((k & 1) * MT * rv);
@@ -237,7 +254,7 @@ route_lane_kernel(const LaneArgs a)
             // iterations ago has landed after this wait.  (Kept in a register and requested with a plain load, the
             // value blocked the whole warp: a few lanes change bracket in EVERY iteration, their load is still in flight
             // when the next lanes read the register, and the iteration paid a global-memory latency, ~0.9 us.)
-            if (HAS_F && tid < TR) cp_async_wait_group<8>();
+            if (HAS_F) cp_async_wait_group<8>();
             const int s = k - off;
             if (has_row && (unsigned)s < (unsigned)nsteps) {
                 double w0 = 0.0, w1 = 0.0;
@@ -311,7 +328,15 @@ route_lane_kernel(const LaneArgs a)
                             a.rec_out[((size_t)(gs / a.rec_every - 1) * a.rec_count + rec) * M + m] = o;
                     }
                 }
-            } else if (tid >= TR) {
+            }
+            if (HAS_F) cp_async_commit();
+            if (iter_barrier(k)) { abandon = true; break; }
+        }
+        } else {
+        for (int k = 0; k < niter; ++k) {
+            const unsigned obp = sOb + 8u * (unsigned)(((k & 1) ^ 1) * MT * rv);
+            const unsigned obc = sOb + 8u * (unsigned)((k & 1) * MT * rv);
+            {
                 for (int v = tid - TR; v < nv; v += TV) {
                     const int4 mt = lds_i4(sMetaV + 16u * v);
                     const int sv = k - (mt.y & 0xffff);
@@ -392,13 +417,8 @@ route_lane_kernel(const LaneArgs a)
                     }
                 }
             }
-            if (HAS_F && tid < TR) cp_async_commit();
-            // the barrier between two iterations; every vote_every-th one also votes on abandoning the launch
-            if ((k & vote_mask) == vote_mask || k + 1 == niter) {
-                if (__syncthreads_or(dead)) { abandon = true; break; }
-            } else {
-                __syncthreads();
-            }
+            if (iter_barrier(k)) { abandon = true; break; }
+        }
         }
         cp_async_wait_all();
         if (tr && tid == 0) {
