@@ -21,6 +21,7 @@
 // The forcing is interpolated per step exactly as nutils.py:21-34 does; its bracket rows live in shared
 // memory and the next row is prefetched (cp.async) one bracket ahead.
 #include <algorithm>
+#include <type_traits>
 
 #include "txh_kernels.cuh"
 
@@ -246,6 +247,10 @@ route_lane_kernel(const LaneArgs a)
             return false;
         };
         if (tid < TR) {
+        // (two instances: the per-step records in shared memory -- the usual case -- or read in place; a run-time choice
+        // inside the loop keeps both address computations and both loads alive in every iteration)
+        auto real_loop = [&](auto steps_in_smem) {
+        constexpr bool SM = decltype(steps_in_smem)::value;
         for (int k = 0; k < niter; ++k) {
             const unsigned obp = sOb + 8u * (unsigned)(((k & 1) ^ 1) * MT * rv);
             const unsigned obc = sOb + 8u * (unsigned)((k & 1) * MT * rv);
@@ -261,7 +266,7 @@ route_lane_kernel(const LaneArgs a)
                 int fr0 = 0, fr1 = 0;
                 if (HAS_F) {
                     int r1f;
-                    if (a.off_steps > 0) {
+                    if (SM) {
                         const double2 ww = lds_d2(sSteps + 32u * s);
                         const int4 rr = lds_i4(sSteps + 32u * s + 16u);
                         w0 = ww.x; w1 = ww.y; fr0 = rr.x; r1f = rr.y;
@@ -282,7 +287,7 @@ route_lane_kernel(const LaneArgs a)
                             if (nn != fr1) { cp_async8_s(sFn + ra, a.F + (size_t)nn * a.n + pos); kreq = k; }
                         } else {
                             int pr0, pr1;
-                            if (a.off_steps > 0) { const int4 pp = lds_i4(sSteps + 32u * (s - 1) + 16u); pr0 = pp.x; pr1 = pp.y; }
+                            if (SM) { const int4 pp = lds_i4(sSteps + 32u * (s - 1) + 16u); pr0 = pp.x; pr1 = pp.y; }
                             else { pr0 = __ldg(&a.steps[s - 1].r0); pr1 = __ldg(&a.steps[s - 1].r1); }
                             fn = lds_d(sFn + ra);
                             rotate_bracket(f0, f1, fn, a.F + pos, a.n, a.R, pr0, pr1 & 0x3fffffff, fr0, fr1);
@@ -332,9 +337,10 @@ route_lane_kernel(const LaneArgs a)
             if (HAS_F) cp_async_commit();
             if (iter_barrier(k)) { abandon = true; break; }
         }
+        };
+        if (a.off_steps > 0) real_loop(std::true_type{}); else real_loop(std::false_type{});
         } else {
         for (int k = 0; k < niter; ++k) {
-            const unsigned obp = sOb + 8u * (unsigned)(((k & 1) ^ 1) * MT * rv);
             const unsigned obc = sOb + 8u * (unsigned)((k & 1) * MT * rv);
             {
                 for (int v = tid - TR; v < nv; v += TV) {
