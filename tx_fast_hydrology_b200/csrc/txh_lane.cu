@@ -148,7 +148,6 @@ route_lane_kernel(const LaneArgs a)
     const size_t splp = (size_t)a.splp;
     bool abandon = false;                                      // watchdog / poisoned handle: decided by a barrier vote
     int first_region = -1;
-    const int vote_mask = a.vote_every - 1;                    // barrier votes on abandoning: every vote_every-th iteration
 
     for (;;) {
         if (tid == 0) {
@@ -240,20 +239,20 @@ route_lane_kernel(const LaneArgs a)
         int kreq = -16;                                         // iteration of this row's last forcing request
         // Two loops, one per role -- the threads that own rows and the threads that mirror incoming streams -- meeting at
         // the same barrier once per iteration (bar.sync / bar.red count arrivals, not program counters): each loop keeps
-        // only its own state live, which matters at 64 registers per thread.
-        auto iter_barrier = [&](int k) -> bool {               // every vote_every-th barrier also votes on abandoning the launch
-            if ((k & vote_mask) == vote_mask || k + 1 == niter) return bar_or(dead) != 0;
-            bar_sync();
-            return false;
-        };
+        // only its own state live, which matters at 64 registers per thread.  Every vote_every-th barrier also votes on
+        // abandoning the launch.
         if (tid < TR) {
         // (two instances: the per-step records in shared memory -- the usual case -- or read in place; a run-time choice
         // inside the loop keeps both address computations and both loads alive in every iteration)
         auto real_loop = [&](auto steps_in_smem) {
         constexpr bool SM = decltype(steps_in_smem)::value;
-        for (int k = 0; k < niter; ++k) {
-            const unsigned obp = sOb + 8u * (unsigned)(((k & 1) ^ 1) * MT * rv);
-            const unsigned obc = sOb + 8u * (unsigned)((k & 1) * MT * rv);
+        // (chunks of vote_every iterations: a plain barrier inside, the voting one at the end of a chunk; the two outflow
+        // buffers swap by XOR with the difference of their addresses)
+        unsigned obc = sOb, obp = sOb + 8u * (unsigned)(MT * rv);
+        const unsigned obx = obc ^ obp;
+        for (int k0 = 0; k0 < niter && !abandon; k0 += a.vote_every) {
+        const int k1 = min(k0 + a.vote_every, niter);
+        for (int k = k0; k < k1; ++k, obc ^= obx, obp ^= obx) {
             // the forcing row after a row's bracket waits in shared memory, requested with cp.async when the bracket was
             // entered: one (possibly empty) group per iteration and thread, so everything requested nine or more
             // iterations ago has landed after this wait.  (Kept in a register and requested with a plain load, the
@@ -320,14 +319,14 @@ route_lane_kernel(const LaneArgs a)
                     if (PREG) p[m < MR ? m : 0] = pm;
                     else sts_d(sP + 8u * ((unsigned)m * nr + tid), pm);
                     sts_d(obc + mo + ra, o);
-                    if ((slot >= 0 || last) && m < M) {
+                    if ((slot >= 0 || last) && (MT == 1 || m < M)) {
                         if (slot >= 0) __stcg(a.ring + ((size_t)slot * M + m) * splp + s, o);
                         if (last) {
                             __stcg(a.O + (size_t)pos * ld + m, o);
                             __stcg(a.I + (size_t)pos * ld + m, infl);
                         }
                     }
-                    if (rec >= 0 && m < M) {
+                    if (rec >= 0 && (MT == 1 || m < M)) {
                         const long long gs = a.rec_step_base + s + 1;
                         if (gs % a.rec_every == 0)
                             a.rec_out[((size_t)(gs / a.rec_every - 1) * a.rec_count + rec) * M + m] = o;
@@ -335,13 +334,18 @@ route_lane_kernel(const LaneArgs a)
                 }
             }
             if (HAS_F) cp_async_commit();
-            if (iter_barrier(k)) { abandon = true; break; }
+            if (k + 1 < k1) bar_sync();
+        }
+        if (bar_or(dead)) abandon = true;
         }
         };
         if (a.off_steps > 0) real_loop(std::true_type{}); else real_loop(std::false_type{});
         } else {
-        for (int k = 0; k < niter; ++k) {
-            const unsigned obc = sOb + 8u * (unsigned)((k & 1) * MT * rv);
+        unsigned obc = sOb;
+        const unsigned obx = 8u * (unsigned)(MT * rv);
+        for (int k0 = 0; k0 < niter && !abandon; k0 += a.vote_every) {
+        const int k1 = min(k0 + a.vote_every, niter);
+        for (int k = k0; k < k1; ++k, obc = (obc == sOb ? sOb + obx : sOb)) {
             {
                 for (int v = tid - TR; v < nv; v += TV) {
                     const int4 mt = lds_i4(sMetaV + 16u * v);
@@ -423,7 +427,9 @@ route_lane_kernel(const LaneArgs a)
                     }
                 }
             }
-            if (iter_barrier(k)) { abandon = true; break; }
+            if (k + 1 < k1) bar_sync();
+        }
+        if (bar_or(dead)) abandon = true;
         }
         }
         cp_async_wait_all();
