@@ -57,3 +57,26 @@ def test_basin_sharding_balances_whole_basins():
     assert sub.size == sizes[1] and (sub < sub.size).all()
     # an extracted shard is closed under "downstream": its endnodes map back to the same reaches
     assert (idx[sub] == net["endnodes"][idx]).all()
+
+
+def test_coefficient_arrays_are_read_only_and_tracked():
+    """`model.alpha` ... hand out read-only arrays; assignment (or set_transmissive_boundary, muskingum.py:567-571)
+    installs a copy and marks the device copy stale -- no O(n) comparison before a launch (host logic only)."""
+    import numpy as np
+    import pytest
+    from tx_fast_hydrology_b200 import synthetic as S
+    from tx_fast_hydrology_b200.muskingum import Muskingum
+    n = 60
+    mdl = Muskingum(S.model_dict(S.make_network(n, 5), S.make_params(n, 5), dt_s=300.0))
+    assert not mdl._coef_dirty and not mdl.alpha.flags.writeable
+    with pytest.raises(ValueError):
+        mdl.alpha[0] = 1.0
+    a0 = mdl.alpha.copy()
+    mdl.set_transmissive_boundary(np.array([2, 7]))
+    assert mdl._coef_dirty
+    assert mdl.alpha[2] == 1.0 and mdl.beta[7] == 0.0 and mdl.chi[2] == 0.0 and mdl.gamma[7] == 0.0
+    assert np.array_equal(np.delete(mdl.alpha, [2, 7]), np.delete(a0, [2, 7]))
+    with pytest.raises(ValueError):
+        mdl.beta = np.zeros(n + 1)
+    c = mdl.copy()
+    assert np.array_equal(c.alpha, mdl.alpha) and c.alpha is not mdl.alpha

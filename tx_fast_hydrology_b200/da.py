@@ -554,7 +554,7 @@ class BatchedKalmanFilters:
              'o_t': np.concatenate([m._peek_state('o_t_next') for m in self.models])}
         self.union = u = Muskingum(d, load_optional=False)
         for name in ('alpha', 'beta', 'chi', 'gamma'):                 # user-mutated coefficients travel too
-            getattr(u, name)[:] = np.concatenate([getattr(m, name) for m in self.models])
+            setattr(u, name, np.concatenate([getattr(m, name) for m in self.models]))
         u.init_states(o_t_next=d['o_t'], i_t_next=np.concatenate([m._peek_state('i_t_next') for m in self.models]))
         u.o_t_prev = np.concatenate([m._peek_state('o_t_prev') for m in self.models])
         u.i_t_prev = np.concatenate([m._peek_state('i_t_prev') for m in self.models])

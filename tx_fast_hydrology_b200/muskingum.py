@@ -67,11 +67,12 @@ class Muskingum:
         self.B = None
         if create_state_space:
             raise NotImplementedError('dense state-space matrices are not built by the GPU drop-in')
+        self._coef = {}
+        self._coef_dirty = True
         self.alpha = np.zeros(n, dtype=np.float64)
         self.beta = np.zeros(n, dtype=np.float64)
         self.chi = np.zeros(n, dtype=np.float64)
         self.gamma = np.zeros(n, dtype=np.float64)
-        self._coef_seen = None
         self._dev = None                 # device tensors, created on first use
         self._dev_valid = False
         self._host_ref = {}
@@ -251,24 +252,45 @@ class Muskingum:
         X = self.X if X is None else X
         dt = self.dt if dt is None else dt
         a, b, c, g = self.network.compute_coeffs(K, X, dt)     # muskingum.py:332-360 on the handle
-        self.alpha[:] = a
-        self.beta[:] = b
-        self.chi[:] = c
-        self.gamma[:] = g
-        self._coef_seen = (a, b, c, g)
+        self.alpha, self.beta, self.chi, self.gamma = a, b, c, g
+        self._coef_dirty = False                               # the handle already holds exactly these
 
     def set_transmissive_boundary(self, index):
-        self.alpha[index] = 1.
-        self.beta[index] = 0.
-        self.chi[index] = 0.
-        self.gamma[index] = 0.
+        """muskingum.py:567-571 (which writes the four arrays in place)."""
+        for name, value in (('alpha', 1.), ('beta', 0.), ('chi', 0.), ('gamma', 0.)):
+            arr = np.array(self._coef[name])
+            arr[index] = value
+            setattr(self, name, arr)
+
+    # alpha / beta / chi / gamma: the arrays the kernels read live on the device, so a change has to be seen.  The
+    # attributes hand out READ-ONLY arrays and assignment installs a copy: `model.alpha = new_array` (or
+    # compute_muskingum_coeffs / set_transmissive_boundary) is how coefficients change; an in-place write from outside
+    # raises numpy's "assignment destination is read-only" instead of being silently missed.  (Comparing four arrays
+    # of n doubles before every launch, the alternative, cost 4.5 ms per call at CONUS scale.)
+    def _coef_get(name):
+        return lambda self: self._coef[name]
+
+    def _coef_set(name):
+        def setter(self, value):
+            arr = np.array(value, dtype=np.float64).reshape(-1)
+            if arr.size != self.n:
+                raise ValueError(f'`{name}` must hold {self.n} values, got {arr.size}')
+            arr.flags.writeable = False
+            self._coef[name] = arr
+            self._coef_dirty = True
+        return setter
+
+    alpha = property(_coef_get('alpha'), _coef_set('alpha'))
+    beta = property(_coef_get('beta'), _coef_set('beta'))
+    chi = property(_coef_get('chi'), _coef_set('chi'))
+    gamma = property(_coef_get('gamma'), _coef_set('gamma'))
+    del _coef_get, _coef_set
 
     def _sync_coeffs(self):
-        """The coefficient arrays are user-mutable (muskingum.py:567-571): re-install on change."""
-        cur = (self.alpha, self.beta, self.chi, self.gamma)
-        if self._coef_seen is None or any(not np.array_equal(x, y) for x, y in zip(cur, self._coef_seen)):
-            self.network.set_coeffs(*cur)
-            self._coef_seen = tuple(x.copy() for x in cur)
+        """Re-install the coefficients on the handle after a change (see the properties above)."""
+        if self._coef_dirty:
+            self.network.set_coeffs(self.alpha, self.beta, self.chi, self.gamma)
+            self._coef_dirty = False
 
     # ------------------------------------------------------------------ device plumbing
     def _ensure_device(self):
@@ -541,7 +563,7 @@ class Muskingum:
         new.init_states(o_t_next=self._peek_state('o_t_next'), i_t_next=self._peek_state('i_t_next'))
         new.o_t_prev = self._peek_state('o_t_prev')
         new.i_t_prev = self._peek_state('i_t_prev')
-        new.alpha[:], new.beta[:], new.chi[:], new.gamma[:] = self.alpha, self.beta, self.chi, self.gamma
+        new.alpha, new.beta, new.chi, new.gamma = self.alpha, self.beta, self.chi, self.gamma
         new.saved_states = {k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in self.saved_states.items()}
         return new
 
@@ -583,8 +605,7 @@ class Muskingum:
                  'dx': None if self.dx is None else np.asarray(self.dx)[sel],
                  'paths': [self.paths[j] for j in sel] if len(self.paths) == n else []}
             sub = type(self)(d, sched_params=self._sched_params)
-            sub.alpha[:], sub.beta[:], sub.chi[:], sub.gamma[:] = (self.alpha[sel], self.beta[sel], self.chi[sel],
-                                                                   self.gamma[sel])
+            sub.alpha, sub.beta, sub.chi, sub.gamma = self.alpha[sel], self.beta[sel], self.chi[sel], self.gamma[sel]
             sub.init_states(o_t_next=o_next[sel], i_t_next=i_next[sel])
             sub.o_t_prev = np.array(o_prev[sel]); sub.i_t_prev = np.array(i_prev[sel])
             models.append(sub)
