@@ -596,7 +596,7 @@ int run_lane(txh_net* net, double* O, double* I, int64_t M, const double* F, con
     if (smem > 227 * 1024) return 1;
     // the per-step interpolation records ride in shared memory too when they fit
     if (plan.times && smem + 32 * (size_t)spl <= 200 * 1024) { a.off_steps = (int32_t)smem; smem += 32 * (size_t)spl; }
-    a.lag = 32;
+    a.lag = 24;                                            // (measured: 24 / 32 / 48 steps -> C2 2.47 / 2.53 / 2.69 ms, C4 5.72 / 5.81 / 6.16 ms)
     if (const char* k = getenv("TXH_LANE_LAG")) a.lag = std::max(24, std::min(4096, atoi(k)));
     a.vote_every = 64;
     if (const char* k = getenv("TXH_LANE_VOTE_EVERY")) { const int v = atoi(k); if (v > 0 && (v & (v - 1)) == 0) a.vote_every = v; }
