@@ -18,6 +18,7 @@ def main():
     ap.add_argument("trace")
     ap.add_argument("--n", type=int, default=100000)
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--slow", action="store_true", help="also list the tasks that pace the critical path (its 'own' edges)")
     a = ap.parse_args()
     from tx_fast_hydrology_b200 import synthetic as S
     from tx_fast_hydrology_b200.network import RiverNetwork
@@ -65,10 +66,9 @@ def main():
     # per-step publish time of the final task and the ripple of step 0 down the longest producer chain
     print(" last task publishes (us):", " ".join(f"{x / 1e3:6.1f}" for x in pub[path[0][0]]))
     print(" path head (task, step, edge, t):", path[:6], "... tail:", path[-6:])
+    if a.slow:
+        slow_stages(a.trace, a.n, a.seed)
 
-
-if __name__ == "__main__":
-    main()
 
 
 def slow_stages(trace, n=100000, seed=2):
@@ -110,5 +110,6 @@ def slow_stages(trace, n=100000, seed=2):
             print("   publish - last input (us):", np.round((pub[T] - last_in) / 1e3, 2))
 
 
-if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "--slow":
-    slow_stages(sys.argv[1])
+
+if __name__ == "__main__":
+    main()
