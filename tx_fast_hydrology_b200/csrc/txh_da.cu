@@ -6,6 +6,9 @@
 // DMMA in SASS); everything else (means, gathers, the small SPD solve) is plain FP64.
 // Matrices are row-major.  State matrices are the routing layout: one row per reach (schedule
 // order), members contiguous, `ld` doubles per row.
+// For ensembles of up to 64 members with a diagonal observation-error covariance the whole ensemble-space system --
+// gauge gather, split-K product, reduction, Cholesky solve, W -- is ONE launch of a 16-CTA thread-block cluster
+// (enkf_small_system_kernel: distributed shared memory for the reduce-scatter and the exchange of the solution).
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 

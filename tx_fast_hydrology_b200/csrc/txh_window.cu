@@ -17,6 +17,12 @@
 // out = A_last * o_in + B_last, before handing on -- consecutive steps ripple down the path as a
 // systolic wavefront -- and fixes its interior rows up afterwards (FIX).
 // Ensemble members are the SIMD axis: a lane owns two adjacent member columns (128-bit accesses).
+//
+// Update variant (template parameter UPD; txh_run_assimilating): the launch also applies the ensemble Kalman update the
+// state still owes -- p is linear in the state rows and the update acts on the member axis, so each task transforms its
+// freshly loaded p rows with the 64 x 64 matrix T on the FP64 tensor cores (transform_p_rows) and the posterior state
+// never goes through global memory.  Such a launch may start while the kernel that computes T still runs
+// (programmatic dependent launch): it loads its first tasks and waits for T only then (stage_T).
 #include <cstdlib>
 
 #include "txh_kernels.cuh"
